@@ -1,0 +1,314 @@
+"""Independent big-integer model of the plonk_gadgets hot path (TEST INFRASTRUCTURE ONLY).
+
+This is the *second opinion* for the C oracle in this directory and the generator of the
+golden vectors under ``tests/golden``.  It is deliberately written with plain Python ints
+(canonical residues mod q, no Montgomery form, no limbs) so that it shares no arithmetic
+code with ``oracle/*.c`` or with the CUDA kernels.
+
+PARITY STATUS: the reference crate (Rust) and its dependency ``dusk-plonk 0.8`` cannot be
+built in this environment and the reference holds no row-level golden vectors, so parity is
+*pinned at verdict level* by the reference's own known-answer tests (replayed in
+``tests/test_oracle_kats.py``) and **unpinned at row level** (wire/selector/variable dumps are
+pinned only by this restatement).
+
+What it follows (reference file:line):
+  * gadgets                : /root/reference/src/range.rs:21-189, /root/reference/src/scalar.rs:21-140
+  * AllocatedScalar        : /root/reference/src/allocated_scalar.rs:17-31
+  * Error                  : /root/reference/src/errors.rs:13-18
+  * composer / Fr semantics: third-party ``dusk-plonk = "0.8"`` / ``dusk-bls12_381`` (not vendored in
+    /root/reference); restated from their published behaviour as recorded in SURVEY.md Appendix A.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline leg may import this.
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass
+
+Q = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+R = (1 << 256) % Q          # Montgomery radix residue (BlsScalar::one() raw limbs)
+R2 = (R * R) % Q
+R3 = (R2 * R) % Q
+
+SELECTORS = ("q_m", "q_l", "q_r", "q_o", "q_4", "q_c", "q_arith", "q_range", "q_logic",
+             "q_fixed_group_add", "q_variable_group_add")
+
+
+class NonExistingInverse(Exception):
+    """errors.rs:17 -- the only error the gadgets can return (scalar.rs:79)."""
+
+
+# --------------------------------------------------------------------------- Fr helpers
+def fr(x: int) -> int:
+    return x % Q
+
+
+def inv_or_none(x: int):
+    """BlsScalar::invert(): None iff x == 0, else the unique inverse."""
+    x %= Q
+    if x == 0:
+        return None
+    return pow(x, Q - 2, Q)
+
+
+def to_mont_limbs(x: int):
+    """Raw BlsScalar representation: 4 little-endian u64 limbs of x*2^256 mod q."""
+    m = (x % Q) * R % Q
+    return [(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+
+
+def to_bytes(x: int) -> bytes:
+    """BlsScalar::to_bytes(): canonical little-endian 32 bytes."""
+    return (x % Q).to_bytes(32, "little")
+
+
+def mont_bytes(x: int) -> bytes:
+    """In-memory bytes of a BlsScalar ([u64;4] LE limbs of the Montgomery form)."""
+    return ((x % Q) * R % Q).to_bytes(32, "little")
+
+
+def from_bytes_wide(b: bytes) -> int:
+    """BlsScalar::from_bytes_wide: 64 LE bytes reduced mod q (d0*R2 + d1*R3 in Montgomery terms)."""
+    assert len(b) == 64
+    return int.from_bytes(b, "little") % Q
+
+
+def bits_count(s: int) -> int:
+    """range.rs:173-181: reduce(); counter=1; while s > 1 { s >>= 1; counter += 1 }."""
+    s %= Q
+    counter = 1
+    while s > 1:
+        s >>= 1
+        counter += 1
+    return counter
+
+
+def num_bits_closest_power_of_two(s: int) -> int:
+    """range.rs:185-189: bits_count(2^bits_count(s) mod q)."""
+    n = bits_count(s)
+    return bits_count(pow(2, n, Q))
+
+
+def scalar_to_bits(s: int):
+    """range.rs:161-170: bit[8j+i] = (to_bytes()[j] >> i) & 1 -> LSB-first bits of the canonical integer."""
+    by = to_bytes(s)
+    out = []
+    for byte in by:
+        for i in range(8):
+            out.append((byte >> i) & 1)
+    return out
+
+
+# --------------------------------------------------------------------------- composer
+@dataclass(frozen=True)
+class AllocatedScalar:
+    """allocated_scalar.rs:17-23."""
+    var: int
+    scalar: int
+
+    @staticmethod
+    def allocate(composer: "StandardComposer", scalar: int) -> "AllocatedScalar":
+        """allocated_scalar.rs:27-30."""
+        return AllocatedScalar(composer.add_input(scalar), scalar % Q)
+
+
+class StandardComposer:
+    """Arithmetic-row subset of dusk-plonk 0.8's StandardComposer."""
+
+    def __init__(self):
+        self.n = 0
+        self.variables = []                       # Variable(i) -> canonical value
+        self.w_l, self.w_r, self.w_o, self.w_4 = [], [], [], []
+        self.sel = {name: [] for name in SELECTORS}
+        self.public_inputs = {}                   # sparse: row -> value
+        # new(): zero_var (placeholder Variable(0), then bound by its own constant row) and the two dummy constraints
+        self.zero_var = 0
+        self.zero_var = self.add_witness_to_circuit_description(0)
+        self._add_dummy_constraints()
+
+    # -- variables
+    def add_input(self, s: int) -> int:
+        self.variables.append(s % Q)
+        return len(self.variables) - 1
+
+    def add_witness_to_circuit_description(self, v: int) -> int:
+        var = self.add_input(v)
+        self.constrain_to_constant(var, v, None)
+        return var
+
+    # -- rows
+    def _push_row(self, a, b, c, d, q_m, q_l, q_r, q_o, q_4, q_c, pi):
+        self.w_l.append(a); self.w_r.append(b); self.w_o.append(c); self.w_4.append(d)
+        vals = dict(q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_4=q_4, q_c=q_c, q_arith=1,
+                    q_range=0, q_logic=0, q_fixed_group_add=0, q_variable_group_add=0)
+        for k in SELECTORS:
+            self.sel[k].append(vals[k] % Q)
+        if pi is not None:
+            assert self.n not in self.public_inputs, "duplicate PI position"
+            self.public_inputs[self.n] = pi % Q
+        self.n += 1
+
+    def poly_gate(self, a, b, c, q_m, q_l, q_r, q_o, q_c, pi):
+        self._push_row(a, b, c, self.zero_var, q_m, q_l, q_r, q_o, 0, q_c, pi)
+        return (a, b, c)
+
+    def constrain_to_constant(self, a, constant, pi):
+        self.poly_gate(a, a, a, 0, 1, 0, 0, -constant, pi)
+
+    def assert_equal(self, a, b):
+        self.poly_gate(a, b, self.zero_var, 0, 1, -1, 0, 0, None)
+
+    def big_add(self, q_l_a, q_r_b, q_4_d, q_c, pi):
+        q_l, a = q_l_a
+        q_r, b = q_r_b
+        q_4, d = q_4_d if q_4_d is not None else (0, self.zero_var)
+        p = 0 if pi is None else pi
+        c_eval = (q_l * self.variables[a] + q_r * self.variables[b] + q_4 * self.variables[d] + q_c + p) % Q
+        c = self.add_input(c_eval)
+        self._push_row(a, b, c, d, 0, q_l, q_r, -1, q_4, q_c, pi)
+        return c
+
+    def add(self, q_l_a, q_r_b, q_c, pi):
+        return self.big_add(q_l_a, q_r_b, None, q_c, pi)
+
+    def big_mul(self, q_m, a, b, q_4_d, q_c, pi):
+        q_4, d = q_4_d if q_4_d is not None else (0, self.zero_var)
+        p = 0 if pi is None else pi
+        c_eval = (q_m * self.variables[a] * self.variables[b] + q_4 * self.variables[d] + q_c + p) % Q
+        c = self.add_input(c_eval)
+        self._push_row(a, b, c, d, q_m, 0, 0, -1, q_4, q_c, pi)
+        return c
+
+    def mul(self, q_m, a, b, q_c, pi):
+        return self.big_mul(q_m, a, b, None, q_c, pi)
+
+    def mul_gate(self, a, b, c, q_m, q_o, q_c, pi):
+        self._push_row(a, b, c, self.zero_var, q_m, 0, 0, q_o, 0, q_c, pi)
+        return c
+
+    def boolean_gate(self, a):
+        self._push_row(a, a, a, self.zero_var, 1, 0, 0, -1, 0, 0, None)
+        return a
+
+    def _add_dummy_constraints(self):
+        var_six = self.add_input(6)
+        var_one = self.add_input(1)
+        var_seven = self.add_input(7)
+        var_min_twenty = self.add_input(-20)
+        self._push_row(var_six, var_seven, var_min_twenty, var_one, 1, 2, 3, 4, 1, 4, None)
+        self._push_row(var_min_twenty, var_six, var_seven, self.zero_var, 1, 1, 1, 1, 0, 127, None)
+
+    # -- verdict
+    def gate_value(self, i: int) -> int:
+        a = self.variables[self.w_l[i]]; b = self.variables[self.w_r[i]]
+        c = self.variables[self.w_o[i]]; d = self.variables[self.w_4[i]]
+        s = self.sel
+        pi = self.public_inputs.get(i, 0)
+        return (s["q_arith"][i] * (s["q_m"][i] * a * b + s["q_l"][i] * a + s["q_r"][i] * b
+                                   + s["q_o"][i] * c + s["q_4"][i] * d + pi + s["q_c"][i])) % Q
+
+    def unsatisfied_rows(self):
+        return [i for i in range(self.n) if self.gate_value(i) != 0]
+
+    def construct_dense_pi_vec(self):
+        v = [0] * self.n
+        for k, x in self.public_inputs.items():
+            v[k] = x
+        return v
+
+    # -- canonical dump used for golden digests (LE 32-byte canonical scalars, u64 LE indices)
+    def digest(self) -> str:
+        h = hashlib.sha256()
+        h.update(len(self.variables).to_bytes(8, "little"))
+        h.update(self.n.to_bytes(8, "little"))
+        for v in self.variables:
+            h.update(to_bytes(v))
+        for i in range(self.n):
+            for w in (self.w_l, self.w_r, self.w_o, self.w_4):
+                h.update(w[i].to_bytes(8, "little"))
+            for k in SELECTORS:
+                h.update(to_bytes(self.sel[k][i]))
+            h.update(to_bytes(self.public_inputs.get(i, 0)))
+        return h.hexdigest()
+
+
+# --------------------------------------------------------------------------- scalar.rs
+def conditionally_select_zero(composer, x, select):
+    """scalar.rs:21-27."""
+    return composer.mul(1, x, select, 0, None)
+
+
+def conditionally_select_one(composer, y, selector):
+    """scalar.rs:36-59."""
+    one = composer.add_witness_to_circuit_description(1)
+    selector_y = composer.mul(1, y, selector, 0, None)
+    one_min_selector = composer.add((1, one), (-1, selector), 0, None)
+    return composer.add((1, selector_y), (1, one_min_selector), 0, None)
+
+
+def is_non_zero(composer, var, value_assigned):
+    """scalar.rs:63-97 (raises NonExistingInverse after 1 var + 1 row were appended)."""
+    var_assigned = composer.add_input(value_assigned)
+    composer.assert_equal(var, var_assigned)
+    inverse = inv_or_none(value_assigned)
+    if inverse is None:
+        raise NonExistingInverse()
+    inv = composer.add_input(inverse)
+    one = composer.add_witness_to_circuit_description(1)
+    composer.poly_gate(var, inv, one, 1, 0, 0, -1, 0, None)
+
+
+def maybe_equal(composer, a: AllocatedScalar, b: AllocatedScalar):
+    """scalar.rs:105-140."""
+    u = composer.add((1, a.var), (-1, b.var), 0, None)
+    u_scalar = (a.scalar - b.scalar) % Q
+    u_inv = inv_or_none(u_scalar)
+    z = composer.add_input(0 if u_inv is None else u_inv)
+    y = composer.mul(-1, z, u, 1, None)
+    composer.mul_gate(y, u, u, 1, 0, 0, None)
+    return y
+
+
+# --------------------------------------------------------------------------- range.rs
+def scalar_decomposition_gadget(composer, num_bits: int, witness: AllocatedScalar):
+    """range.rs:119-158."""
+    scalar_bits = scalar_to_bits(witness.scalar)
+    scalar_bits_var = [composer.add_input(bit) for bit in scalar_bits]
+    scalar_bits_var = scalar_bits_var[:num_bits]
+    acc = AllocatedScalar(composer.add_witness_to_circuit_description(0), 0)
+    for power, bit in enumerate(scalar_bits_var):
+        composer.boolean_gate(bit)
+        two_pow = pow(2, power, Q)
+        acc_var = composer.add((two_pow, bit), (1, acc.var), 0, None)
+        acc = AllocatedScalar(acc_var, (acc.scalar + two_pow * scalar_bits[power]) % Q)
+    is_equal = maybe_equal(composer, acc, witness)
+    return is_equal, scalar_bits_var
+
+
+def range_proof(composer, value: AllocatedScalar, num_bits: int):
+    """range.rs:21-24."""
+    is_equal, _ = scalar_decomposition_gadget(composer, num_bits, value)
+    return is_equal
+
+
+def max_bound(composer, max_range: int, witness: AllocatedScalar):
+    """range.rs:82-113."""
+    max_range = (max_range - 1) % Q
+    num_bits_pow_2 = num_bits_closest_power_of_two(max_range)
+    b_minus_x_var = composer.add((-1, witness.var), (0, witness.var), max_range, None)
+    b_minus_x_scalar = (max_range - witness.scalar) % Q
+    return range_proof(composer, AllocatedScalar(b_minus_x_var, b_minus_x_scalar), num_bits_pow_2), num_bits_pow_2
+
+
+def min_bound(composer, min_range: int, witness: AllocatedScalar, num_bits: int):
+    """range.rs:53-76."""
+    x_min_a_var = composer.add((1, witness.var), (0, witness.var), -min_range, None)
+    x_min_a_scalar = (witness.scalar - min_range) % Q
+    return range_proof(composer, AllocatedScalar(x_min_a_var, x_min_a_scalar), num_bits)
+
+
+def range_check(composer, min_range: int, max_range: int, witness: AllocatedScalar):
+    """range.rs:27-43."""
+    y1, num_bits = max_bound(composer, max_range, witness)
+    y2 = min_bound(composer, min_range, witness, num_bits)
+    return composer.mul(1, y1, y2, 0, None)
