@@ -1,0 +1,184 @@
+/*
+ * pg_b200.h -- C ABI of the B200-native batched gadget engine for plonk_gadgets' hot path
+ * (witness generation + arithmetic-gate constraint evaluation over BLS12-381 Fr).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch/C++ types.  A Rust `-sys` crate binds exactly these
+ * symbols; the C++ mirror of the reference API lives in plonk_gadgets_b200/host/plonk_gadgets.hpp
+ * and the Python (ctypes) mirror used by the tests in plonk_gadgets_b200/api.py.
+ *
+ * The reference has no FFI of its own: its "operator interface" is the crate's public Rust functions, all of which take
+ * `composer: &mut StandardComposer` first.  Each entry point below cites the reference function it replaces.
+ *
+ * Model.  A pg_ctx owns ONE device-resident composer (dusk-plonk StandardComposer, arithmetic-row subset) on one GPU.
+ * Every *_batch call appends n independent gadget instances and is defined to be EQUAL to the sequential program
+ *         for i in 0..n { gadget(&mut composer, .., operand_i) }
+ * run on the reference composer: same Variable numbering, same wire columns, same selector rows, same values.
+ * Operands that are `Variable`s in the reference are *columns* here (pg_col): the n variables, one per instance, that an
+ * earlier call produced.  The composer is stored as (row template per gadget and bit width) x (per-instance variable
+ * table in structure-of-arrays form, bits packed); pg_materialize_rows / pg_read_variables expand any range of it into
+ * the reference's own representation (`Vec<BlsScalar>` columns, `Vec<Variable>` wires).
+ *
+ * Scalars cross the boundary as pg_fr: the raw in-memory form of `BlsScalar([u64;4])` (little-endian limbs of
+ * a*2^256 mod q, fully reduced).  Inputs must be fully reduced (< q); this is not checked.
+ *
+ * Threading: a pg_ctx is not thread-safe (the reference API is `&mut`).  All work is enqueued on the ctx's CUDA
+ * stream; calls that return host values synchronise that stream.  There is no CPU fallback: every entry point fails
+ * with PG_ERR_NO_DEVICE / PG_ERR_CUDA when the GPU is unavailable.
+ */
+#ifndef PG_B200_H
+#define PG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_B200_ABI_VERSION 1
+
+/* BlsScalar: /root/reference/src/allocated_scalar.rs:9-12 (dusk_plonk::bls12_381::BlsScalar) */
+typedef struct pg_fr { uint64_t l[4]; } pg_fr;
+
+typedef struct pg_ctx pg_ctx;
+
+/* A column of variables: variable `i` of the column is the one instance i of the producing call allocated.
+ * 0 is never a valid column. */
+typedef uint64_t pg_col;
+
+/* Return codes.  > 0 : gadget-level errors of the reference (/root/reference/src/errors.rs:13-18).
+ *                < 0 : engine errors (never a silent fallback). */
+enum {
+    PG_OK = 0,
+    PG_ERR_NON_EXISTING_INVERSE = 1, /* Error::NonExistingInverse, /root/reference/src/scalar.rs:79 */
+    PG_ERR_CUDA = -1,                /* a CUDA call failed; pg_last_error() has the driver's message */
+    PG_ERR_ARG = -2,                 /* bad argument (null pointer, unknown column, length mismatch, ...) */
+    PG_ERR_OOM = -3,                 /* device allocation failed */
+    PG_ERR_MIXED_BITS = -4,          /* per-instance bounds of one call do not share one bit width (num_bits) */
+    PG_ERR_NO_DEVICE = -5,           /* no CUDA device / wrong architecture */
+    PG_ERR_STATE = -6                /* call not valid in the composer's current state */
+};
+
+/* How the gate equation is evaluated by pg_check (results are identical; only the work differs):
+ *   GENERIC : q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + q_c + PI with six Montgomery multiplications per row, no
+ *             assumption about selector values (what dusk-plonk's check_circuit_satisfied / quotient evaluation do).
+ *   SPARSE  : skips products whose selector is the constant 0 and replaces products by +-1 with add/sub. */
+enum { PG_CHECK_GENERIC = 0, PG_CHECK_SPARSE = 1 };
+
+enum {
+    PG_F_TIMING = 1u        /* record CUDA events around every kernel class (pg_get_timing) */
+};
+
+typedef struct pg_cfg {
+    int32_t device;         /* CUDA ordinal */
+    int32_t check_mode;     /* PG_CHECK_* */
+    uint32_t flags;         /* PG_F_* */
+    uint32_t reserved;
+    void *stream;           /* cudaStream_t to enqueue on; NULL = the engine creates its own non-blocking stream */
+} pg_cfg;
+
+/* ---- lifetime --------------------------------------------------------------------------------------------------- */
+int pg_abi_version(void);
+const char *pg_strerror(int code);
+const char *pg_last_error(const pg_ctx *ctx);          /* detail of the last engine error on this ctx ("" if none) */
+/* StandardComposer::new() [dusk-plonk]: zero variable + two dummy rows => 3 rows, 5 variables */
+int pg_ctx_create(const pg_cfg *cfg, pg_ctx **out);
+void pg_ctx_destroy(pg_ctx *ctx);
+/* Back to a fresh composer; device buffers are kept in the ctx's pool for reuse. */
+int pg_composer_reset(pg_ctx *ctx);
+/* Blocks until everything enqueued so far has finished. */
+int pg_sync(pg_ctx *ctx);
+
+/* ---- gadgets ------------------------------------------------------------------------------------------------------
+ * `on_device` != 0: the pointer arguments of the call are device pointers on cfg.device (read asynchronously on the
+ * ctx stream; keep them alive until pg_sync); == 0: host pointers (copied with cudaMemcpyAsync on the ctx stream;
+ * pinned memory makes that copy asynchronous). */
+
+/* AllocatedScalar::allocate / composer.add_input over n scalars -- /root/reference/src/allocated_scalar.rs:27-30.
+ * Appends n variables, no rows. */
+int pg_add_input_batch(pg_ctx *ctx, uint64_t n, const pg_fr *values, int on_device, pg_col *out);
+
+/* range_check(composer, min_range, max_range, witness) -- /root/reference/src/range.rs:27-43.
+ * n_bounds == 1: one public (min,max) pair for all instances; n_bounds == n: per-instance bounds, which must all give the
+ * same num_bits (else PG_ERR_MIXED_BITS and nothing is appended).  Per instance 4k+11 rows, 2k+523 variables.
+ * *out: the returned Variable (value 1 iff min <= x < max within k bits); *num_bits: k (may be NULL). */
+int pg_range_check_batch(pg_ctx *ctx, const pg_fr *min_range, const pg_fr *max_range, uint64_t n_bounds, int on_device,
+                         pg_col witness, pg_col *out, uint64_t *num_bits);
+
+/* max_bound(composer, max_range, witness) -> (Variable, u64) -- /root/reference/src/range.rs:82-113.  2k+5 rows, k+261 vars. */
+int pg_max_bound_batch(pg_ctx *ctx, const pg_fr *max_range, uint64_t n_bounds, int on_device, pg_col witness,
+                       pg_col *out, uint64_t *num_bits);
+
+/* maybe_equal(composer, a, b) -- /root/reference/src/scalar.rs:105-140.  3 rows, 3 variables; *out = 1 iff a == b.
+ * (The AllocatedScalar's host-side `scalar` is the column's own value.) */
+int pg_maybe_equal_batch(pg_ctx *ctx, pg_col a, pg_col b, pg_col *out);
+
+/* for i { is_non_zero(composer, var_i, value_assigned_i)?; } -- /root/reference/src/scalar.rs:63-97.
+ * 3 rows, 3 variables per instance.  If some value_assigned is zero the call returns PG_ERR_NON_EXISTING_INVERSE and the
+ * composer holds what the reference loop leaves behind: the instances before the first zero complete, plus the
+ * 1 variable + 1 row the failing call had already appended (scalar.rs:69-71).  *n_err = number of zero values in the
+ * whole batch, *first_err = index of the first one (either may be NULL). */
+int pg_is_non_zero_batch(pg_ctx *ctx, pg_col var, const pg_fr *value_assigned, int on_device, uint64_t *n_err,
+                         uint64_t *first_err);
+
+/* conditionally_select_zero(composer, x, select) -- /root/reference/src/scalar.rs:21-27.  1 row, 1 variable. */
+int pg_select_zero_batch(pg_ctx *ctx, pg_col x, pg_col select, pg_col *out);
+/* conditionally_select_one(composer, y, selector) -- /root/reference/src/scalar.rs:36-59.  4 rows, 4 variables. */
+int pg_select_one_batch(pg_ctx *ctx, pg_col y, pg_col selector, pg_col *out);
+
+/* composer.constrain_to_constant(a, constant, pi) [dusk-plonk] as used by the reference's tests
+ * (/root/reference/tests/range_gadgets_tests.rs:26,:43; tests/scalar_gadgets_tests.rs:30,:78,:135).  1 row, no variable.
+ * n_const / n_pi: 1 (uniform) or n; pi == NULL: no public input. */
+int pg_constrain_to_constant_batch(pg_ctx *ctx, pg_col a, const pg_fr *constant, uint64_t n_const, const pg_fr *pi,
+                                   uint64_t n_pi, int on_device);
+
+/* ---- verdict ------------------------------------------------------------------------------------------------------ */
+/* Arithmetic part of check_circuit_satisfied [dusk-plonk]: evaluates the gate equation on every row of the composer.
+ * *n_unsat = number of rows with a non-zero value; *first_bad_row = smallest such row index or UINT64_MAX. */
+int pg_check(pg_ctx *ctx, uint64_t *n_unsat, uint64_t *first_bad_row);
+/* Same equation over caller-supplied materialised rows (w_val: 4 x n wire values, sel: 6 x n selectors in the order
+ * q_m q_l q_r q_o q_4 q_c, pi: n or NULL), column-major. */
+int pg_check_rows(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel, const pg_fr *pi, int on_device,
+                  uint64_t *n_unsat, uint64_t *first_bad_row);
+
+/* ---- reading the composer back in the reference's representation --------------------------------------------------- */
+int pg_counts(const pg_ctx *ctx, uint64_t *n_rows, uint64_t *n_vars);        /* composer.circuit_size(), variables.len() */
+/* Column geometry: Variable id of instance i = first_var + i * stride. */
+int pg_col_info(const pg_ctx *ctx, pg_col col, uint64_t *n, uint64_t *first_var, uint64_t *stride);
+/* Values of instances [i0, i0+cnt) of a column (what `composer.variables[var]` holds). */
+int pg_col_read(pg_ctx *ctx, pg_col col, uint64_t i0, uint64_t cnt, pg_fr *dst, int dst_on_device);
+/* variables[var0 .. var0+cnt) in Variable order. */
+int pg_read_variables(pg_ctx *ctx, uint64_t var0, uint64_t cnt, pg_fr *dst, int dst_on_device);
+/* Rows [row0, row0+cnt): any of the outputs may be NULL.  w_idx: 4 x cnt Variable ids (w_l,w_r,w_o,w_4), w_val: 4 x cnt
+ * wire values, sel: 6 x cnt (q_m,q_l,q_r,q_o,q_4,q_c), pi: cnt (dense public inputs), all column-major.  On every row
+ * q_arith = 1 and q_range = q_logic = q_fixed_group_add = q_variable_group_add = 0. */
+int pg_materialize_rows(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *w_idx, pg_fr *w_val, pg_fr *sel, pg_fr *pi,
+                        int dst_on_device);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------------------- */
+/* Deterministic synthetic scalars (SplitMix64 counter stream): kind 0 = uniform Fr (512-bit draw reduced mod q, as
+ * BlsScalar::from_bytes_wide), kind 1 = uniform integer of `bits` bits (bits <= 254), kind 2 = even index kind 1 / odd
+ * index kind 0, kind 3 = `bits`-bit integer with the top bit forced to 1.  dst is a device pointer (n scalars). */
+int pg_synth(pg_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t n, int kind, uint32_t bits, pg_fr *dst_device);
+
+typedef struct pg_timing {
+    double check_ms;        /* gate-check kernels */
+    double witness_ms;      /* witness-generation kernels (incl. batch inversion) */
+    double other_ms;        /* layout / materialise / synth kernels */
+    uint64_t check_launches, witness_launches, other_launches;
+    uint64_t check_rows;    /* rows evaluated by the gate-check kernels */
+} pg_timing;
+int pg_get_timing(pg_ctx *ctx, pg_timing *out, int reset);   /* needs PG_F_TIMING; synchronises */
+
+/* Integer-multiply roofline denominators measured on this GPU: 32x32+64->64 multiply-accumulates per second with
+ * IMAD.WIDE.U32 chains, and 32-bit IMAD (lo) per second. */
+int pg_measure_imad_peak(pg_ctx *ctx, double *wide_mac_per_s, double *imad_per_s);
+
+/* Element-wise Fr self-test kernels (op: 0 mul, 1 add, 2 sub, 3 neg, 4 invert-or-zero (batch inversion), 5 from_mont,
+ * 6 mul via the portable CIOS path).  a, b, out: host arrays of n scalars. */
+int pg_fr_op(pg_ctx *ctx, int op, uint64_t n, const pg_fr *a, const pg_fr *b, pg_fr *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PG_B200_H */

@@ -1,0 +1,22 @@
+"""plonk_gadgets_b200 -- B200-native batched gadget engine for plonk_gadgets' hot path.
+
+Only what the path needs: csrc/ (CUDA kernels + C ABI, built into libpg_b200.so), host/ (C++ mirror of the reference
+API over the C ABI) and this Python mirror used by the tests and the benchmark.  Importing the package does not load the
+CUDA library; creating a StandardComposer does, and fails loudly when it (or a B200) is missing -- there is no CPU path.
+"""
+from .api import (AllocatedScalar, CHECK_GENERIC, CHECK_SPARSE, DevicePtr, EngineError, Error, NonExistingInverse,  # noqa: F401
+                  StandardComposer, Variables, conditionally_select_one, conditionally_select_zero, is_non_zero,
+                  max_bound, maybe_equal, range_check)
+from . import _lib  # noqa: F401
+
+
+class RangeGadgets:      # re-export names of /root/reference/src/lib.rs:44
+    range_check = staticmethod(range_check)
+    max_bound = staticmethod(max_bound)
+
+
+class ScalarGadgets:     # /root/reference/src/lib.rs:45
+    conditionally_select_zero = staticmethod(conditionally_select_zero)
+    conditionally_select_one = staticmethod(conditionally_select_one)
+    is_non_zero = staticmethod(is_non_zero)
+    maybe_equal = staticmethod(maybe_equal)

@@ -1,0 +1,315 @@
+"""Host-side mirror of plonk_gadgets' public interface over the C ABI (include/pg_b200.h), batched.
+
+Names, argument order and error behaviour follow the reference crate (/root/reference/src/lib.rs:37-45):
+
+    reference (one instance)                                   here (n instances per call)
+    -----------------------------------------------------------------------------------------------------------------
+    AllocatedScalar::allocate(composer, scalar)                AllocatedScalar.allocate(composer, scalars)
+    range_check(composer, min_range, max_range, witness)       range_check(composer, min_range, max_range, witness)
+    max_bound(composer, max_range, witness) -> (Variable,u64)  max_bound(composer, max_range, witness) -> (Variables, k)
+    maybe_equal(composer, a, b)                                maybe_equal(composer, a, b)
+    is_non_zero(composer, var, value_assigned) -> Result       is_non_zero(composer, var, value_assigned)  raises NonExistingInverse
+    conditionally_select_zero(composer, x, select)             conditionally_select_zero(composer, x, select)
+    conditionally_select_one(composer, y, selector)            conditionally_select_one(composer, y, selector)
+
+A ``Variables`` object is a column of n composer variables (one per instance); scalars are numpy arrays of dtype uint64
+and shape (n, 4) holding raw ``BlsScalar`` limbs (Montgomery form), or CUDA tensors/pointers of the same layout.
+Every call is equal to the sequential loop ``for i in range(n): gadget(composer, .., operand_i)`` on the reference composer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+CHECK_GENERIC, CHECK_SPARSE = 0, 1
+F_TIMING = 1
+UINT64_MAX = 2 ** 64 - 1
+
+
+class Error(Exception):
+    """Gadget errors (/root/reference/src/errors.rs:13-18)."""
+
+
+class NonExistingInverse(Error):
+    """Error::NonExistingInverse (/root/reference/src/errors.rs:17, returned at /root/reference/src/scalar.rs:79)."""
+
+    def __init__(self, n_err: int, first_err: int):
+        super().__init__(f"value_assigned is zero for {n_err} instance(s), first at index {first_err}")
+        self.n_err, self.first_err = n_err, first_err
+
+
+class EngineError(RuntimeError):
+    """Negative return codes of the C ABI (CUDA failure, bad argument, out of memory, ...)."""
+
+    def __init__(self, code: int, what: str, detail: str):
+        super().__init__(f"{what} (code {code}): {detail}")
+        self.code = code
+
+
+class DevicePtr:
+    """n scalars living in device memory (32 bytes each, 16-byte aligned)."""
+
+    def __init__(self, ptr: int, n: int, owner=None):
+        self.ptr, self.n, self.owner = int(ptr), int(n), owner
+
+
+def _scalars(x):
+    """-> (pointer, on_device, n, keepalive)"""
+    if isinstance(x, DevicePtr):
+        return C.c_void_p(x.ptr), 1, x.n, x
+    if hasattr(x, "data_ptr") and hasattr(x, "is_cuda"):          # torch tensor, without importing torch here
+        if not x.is_contiguous():
+            raise ValueError("scalar tensors must be contiguous")
+        n = x.numel() * x.element_size() // 32
+        if x.is_cuda:
+            return C.c_void_p(x.data_ptr()), 1, n, x
+        return C.c_void_p(x.data_ptr()), 0, n, x
+    a = np.ascontiguousarray(x, dtype=np.uint64)
+    if a.ndim == 1 and a.shape[0] == 4:
+        a = a.reshape(1, 4)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("scalars must have shape (n, 4) uint64")
+    return a.ctypes.data_as(C.c_void_p), 0, a.shape[0], a
+
+
+@dataclass(frozen=True)
+class Variables:
+    """A column of n `Variable`s: element i is the variable instance i of the producing call allocated."""
+    composer: "StandardComposer"
+    col: int
+    n: int
+
+    def ids(self) -> np.ndarray:
+        """The reference's Variable indices (first + i*stride)."""
+        first, stride = self.composer._col_geometry(self.col)
+        return first + stride * np.arange(self.n, dtype=np.uint64)
+
+    def values(self, i0: int = 0, cnt: int | None = None) -> np.ndarray:
+        """composer.variables[var] for the column, as (cnt, 4) uint64."""
+        return self.composer.read_column(self, i0, cnt)
+
+
+@dataclass(frozen=True)
+class AllocatedScalar:
+    """/root/reference/src/allocated_scalar.rs:17-31 -- here `var` is a column and `scalar` its values (read on demand)."""
+    var: Variables
+
+    @property
+    def scalar(self) -> np.ndarray:
+        return self.var.values()
+
+    @staticmethod
+    def allocate(composer: "StandardComposer", scalar) -> "AllocatedScalar":
+        return AllocatedScalar(composer.add_input(scalar))
+
+
+class StandardComposer:
+    """Device-resident batched composer (dusk-plonk StandardComposer, arithmetic-row subset).  Fresh state: 3 rows, 5 variables."""
+
+    def __init__(self, device: int = 0, check_mode: int = CHECK_GENERIC, timing: bool = False, stream: int | None = None, _cdll=None):
+        self._L = _cdll if _cdll is not None else _lib.load()
+        cfg = _lib.pg_cfg(device=device, check_mode=check_mode, flags=F_TIMING if timing else 0, reserved=0, stream=stream)
+        ctx = C.c_void_p()
+        rc = self._L.pg_ctx_create(C.byref(cfg), C.byref(ctx))
+        if rc != 0:
+            raise EngineError(rc, "pg_ctx_create", self._L.pg_strerror(rc).decode())
+        self._ctx = ctx
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.pg_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing
+    def _ok(self, rc: int, what: str):
+        if rc < 0:
+            raise EngineError(rc, what, self._L.pg_last_error(self._ctx).decode())
+        return rc
+
+    def _col_geometry(self, col: int):
+        n, first, stride = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ok(self._L.pg_col_info(self._ctx, col, C.byref(n), C.byref(first), C.byref(stride)), "pg_col_info")
+        return first.value, stride.value
+
+    def reset(self):
+        self._ok(self._L.pg_composer_reset(self._ctx), "pg_composer_reset")
+        self._keep.clear()
+
+    def sync(self):
+        self._ok(self._L.pg_sync(self._ctx), "pg_sync")
+        self._keep.clear()
+
+    # -- composer surface used by the gadgets and the reference's tests
+    def add_input(self, scalars) -> Variables:
+        p, dev, n, keep = _scalars(scalars)
+        self._keep.append(keep)
+        out = C.c_uint64()
+        self._ok(self._L.pg_add_input_batch(self._ctx, n, p, dev, C.byref(out)), "pg_add_input_batch")
+        return Variables(self, out.value, n)
+
+    def constrain_to_constant(self, a: Variables, constant, pi=None):
+        pc, dev, nc, k1 = _scalars(constant)
+        pp, npi, k2 = None, 0, None
+        if pi is not None:
+            pp, dev2, npi, k2 = _scalars(pi)
+            if dev2 != dev:
+                raise ValueError("constant and pi must both be host or both be device scalars")
+        self._keep += [k1, k2]
+        self._ok(self._L.pg_constrain_to_constant_batch(self._ctx, a.col, pc, nc, pp, npi, dev), "pg_constrain_to_constant_batch")
+
+    def circuit_size(self) -> int:
+        r, v = C.c_uint64(), C.c_uint64()
+        self._ok(self._L.pg_counts(self._ctx, C.byref(r), C.byref(v)), "pg_counts")
+        return r.value
+
+    def num_variables(self) -> int:
+        r, v = C.c_uint64(), C.c_uint64()
+        self._ok(self._L.pg_counts(self._ctx, C.byref(r), C.byref(v)), "pg_counts")
+        return v.value
+
+    def check_circuit_satisfied(self):
+        """(number of unsatisfied rows, first unsatisfied row or None): the arithmetic gate equation on every row."""
+        bad, first = C.c_uint64(), C.c_uint64()
+        self._ok(self._L.pg_check(self._ctx, C.byref(bad), C.byref(first)), "pg_check")
+        return bad.value, (None if first.value == UINT64_MAX else first.value)
+
+    # -- read-back in the reference's representation
+    def read_column(self, v: Variables, i0: int = 0, cnt: int | None = None) -> np.ndarray:
+        cnt = v.n - i0 if cnt is None else cnt
+        out = np.empty((cnt, 4), dtype=np.uint64)
+        self._ok(self._L.pg_col_read(self._ctx, v.col, i0, cnt, out.ctypes.data_as(C.c_void_p), 0), "pg_col_read")
+        return out
+
+    def read_column_into(self, v: Variables, dst, i0: int = 0, cnt: int | None = None):
+        """Device (or pinned host) destination variant of read_column."""
+        cnt = v.n - i0 if cnt is None else cnt
+        p, dev, n, _ = _scalars(dst)
+        if n < cnt:
+            raise ValueError("destination too small")
+        self._ok(self._L.pg_col_read(self._ctx, v.col, i0, cnt, p, dev), "pg_col_read")
+
+    def variables(self, var0: int = 0, cnt: int | None = None) -> np.ndarray:
+        cnt = self.num_variables() - var0 if cnt is None else cnt
+        out = np.empty((cnt, 4), dtype=np.uint64)
+        self._ok(self._L.pg_read_variables(self._ctx, var0, cnt, out.ctypes.data_as(C.c_void_p), 0), "pg_read_variables")
+        return out
+
+    def rows(self, row0: int = 0, cnt: int | None = None, want=("w_idx", "w_val", "sel", "pi")) -> dict:
+        """Materialised rows: w_idx (4,cnt) uint64, w_val (4,cnt,4), sel (6,cnt,4) in q_m q_l q_r q_o q_4 q_c order, pi (cnt,4)."""
+        cnt = self.circuit_size() - row0 if cnt is None else cnt
+        out = {}
+        if "w_idx" in want: out["w_idx"] = np.empty((4, cnt), dtype=np.uint64)
+        if "w_val" in want: out["w_val"] = np.empty((4, cnt, 4), dtype=np.uint64)
+        if "sel" in want: out["sel"] = np.empty((6, cnt, 4), dtype=np.uint64)
+        if "pi" in want: out["pi"] = np.empty((cnt, 4), dtype=np.uint64)
+        ptr = lambda k: out[k].ctypes.data_as(C.c_void_p) if k in out else None
+        self._ok(self._L.pg_materialize_rows(self._ctx, row0, cnt, ptr("w_idx"), ptr("w_val"), ptr("sel"), ptr("pi"), 0), "pg_materialize_rows")
+        return out
+
+    def check_rows(self, w_val, sel, pi=None):
+        """Gate equation over caller-supplied materialised rows (host arrays)."""
+        w = np.ascontiguousarray(w_val, dtype=np.uint64); s = np.ascontiguousarray(sel, dtype=np.uint64)
+        n = w.shape[1]
+        p = np.ascontiguousarray(pi, dtype=np.uint64) if pi is not None else None
+        bad, first = C.c_uint64(), C.c_uint64()
+        self._ok(self._L.pg_check_rows(self._ctx, n, w.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p),
+                                       p.ctypes.data_as(C.c_void_p) if p is not None else None, 0, C.byref(bad), C.byref(first)), "pg_check_rows")
+        return bad.value, (None if first.value == UINT64_MAX else first.value)
+
+    # -- measurement helpers
+    def synth(self, seed: int, stream: int, kind: int, bits: int, dst) -> None:
+        p, dev, n, _ = _scalars(dst)
+        if not dev:
+            raise ValueError("synth writes to device memory")
+        self._ok(self._L.pg_synth(self._ctx, seed, stream, n, kind, bits, p), "pg_synth")
+
+    def timing(self, reset: bool = True) -> dict:
+        t = _lib.pg_timing()
+        self._ok(self._L.pg_get_timing(self._ctx, C.byref(t), int(reset)), "pg_get_timing")
+        return {k: getattr(t, k) for k, _ in _lib.pg_timing._fields_}
+
+    def measure_imad_peak(self):
+        w, l = C.c_double(), C.c_double()
+        self._ok(self._L.pg_measure_imad_peak(self._ctx, C.byref(w), C.byref(l)), "pg_measure_imad_peak")
+        return w.value, l.value
+
+    def fr_op(self, op: int, a, b=None) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64) if b is not None else None
+        out = np.empty_like(a)
+        self._ok(self._L.pg_fr_op(self._ctx, op, a.shape[0], a.ctypes.data_as(C.c_void_p),
+                                  b.ctypes.data_as(C.c_void_p) if b is not None else None, out.ctypes.data_as(C.c_void_p)), "pg_fr_op")
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------- RangeGadgets
+def _var(x) -> Variables:
+    return x.var if isinstance(x, AllocatedScalar) else x
+
+
+def range_check(composer: StandardComposer, min_range, max_range, witness) -> Variables:
+    """/root/reference/src/range.rs:27-43.  Bounds: one scalar (uniform) or n scalars of one bit width."""
+    w = _var(witness)
+    pmn, dev, n1, k1 = _scalars(min_range)
+    pmx, dev2, n2, k2 = _scalars(max_range)
+    if dev != dev2 or n1 != n2:
+        raise ValueError("min_range and max_range must have the same length and residency")
+    composer._keep += [k1, k2]
+    out, k = C.c_uint64(), C.c_uint64()
+    composer._ok(composer._L.pg_range_check_batch(composer._ctx, pmn, pmx, n1, dev, w.col, C.byref(out), C.byref(k)), "pg_range_check_batch")
+    return Variables(composer, out.value, w.n)
+
+
+def max_bound(composer: StandardComposer, max_range, witness):
+    """/root/reference/src/range.rs:82-113 -> (Variables, num_bits)."""
+    w = _var(witness)
+    pmx, dev, n1, k1 = _scalars(max_range)
+    composer._keep.append(k1)
+    out, k = C.c_uint64(), C.c_uint64()
+    composer._ok(composer._L.pg_max_bound_batch(composer._ctx, pmx, n1, dev, w.col, C.byref(out), C.byref(k)), "pg_max_bound_batch")
+    return Variables(composer, out.value, w.n), k.value
+
+
+# ---------------------------------------------------------------------------------------------------- ScalarGadgets
+def conditionally_select_zero(composer: StandardComposer, x: Variables, select: Variables) -> Variables:
+    """/root/reference/src/scalar.rs:21-27."""
+    out = C.c_uint64()
+    composer._ok(composer._L.pg_select_zero_batch(composer._ctx, _var(x).col, _var(select).col, C.byref(out)), "pg_select_zero_batch")
+    return Variables(composer, out.value, _var(x).n)
+
+
+def conditionally_select_one(composer: StandardComposer, y: Variables, selector: Variables) -> Variables:
+    """/root/reference/src/scalar.rs:36-59."""
+    out = C.c_uint64()
+    composer._ok(composer._L.pg_select_one_batch(composer._ctx, _var(y).col, _var(selector).col, C.byref(out)), "pg_select_one_batch")
+    return Variables(composer, out.value, _var(y).n)
+
+
+def is_non_zero(composer: StandardComposer, var: Variables, value_assigned) -> None:
+    """/root/reference/src/scalar.rs:63-97.  Raises NonExistingInverse like `is_non_zero(..)?` in a loop would."""
+    p, dev, n, keep = _scalars(value_assigned)
+    if n != _var(var).n:
+        raise ValueError("value_assigned must have one scalar per variable")
+    composer._keep.append(keep)
+    n_err, first = C.c_uint64(), C.c_uint64()
+    rc = composer._ok(composer._L.pg_is_non_zero_batch(composer._ctx, _var(var).col, p, dev, C.byref(n_err), C.byref(first)), "pg_is_non_zero_batch")
+    if rc == 1:
+        raise NonExistingInverse(n_err.value, first.value)
+
+
+def maybe_equal(composer: StandardComposer, a, b) -> Variables:
+    """/root/reference/src/scalar.rs:105-140."""
+    out = C.c_uint64()
+    composer._ok(composer._L.pg_maybe_equal_batch(composer._ctx, _var(a).col, _var(b).col, C.byref(out)), "pg_maybe_equal_batch")
+    return Variables(composer, out.value, _var(a).n)

@@ -1,0 +1,406 @@
+// bodies.cuh -- per-instance kernel bodies ("one gadget instance per thread").
+//
+// Every body is a plain __host__ __device__ function of (arguments, instance index).  The CUDA backend (kernels.cuh)
+// wraps them in __global__ kernels; the test-only host backend (tests/emu) calls them in a loop so that templates,
+// numbering and witness arithmetic can be checked on a machine without a GPU.  Bodies that need a field inversion are
+// split in pre() / post() around the block-wide Montgomery batch inversion.
+//
+// Reference functions restated here (witness arithmetic only; row structure lives in templates.hpp):
+//   RangeBody       /root/reference/src/range.rs:27-43 (range_check), :82-113 (max_bound), :53-76 (min_bound),
+//                   :119-158 (scalar_decomposition_gadget), :161-170 (scalar_to_bits)
+//   MaybeEqualBody  /root/reference/src/scalar.rs:105-140      IsNonZeroBody  /root/reference/src/scalar.rs:63-97
+//   SelectZeroBody  /root/reference/src/scalar.rs:21-27        SelectOneBody  /root/reference/src/scalar.rs:36-59
+#pragma once
+#include "layout.h"
+
+namespace pg {
+
+// 2^i * R mod q for i in 0..255 (Montgomery form of the q_l selectors / accumulator increments of range.rs:146-152)
+#if defined(__CUDACC__)
+__constant__ Fr c_pow2[256];
+#endif
+extern Fr h_pow2[256];
+PG_HD const Fr& pow2_entry(uint32_t i) {
+#if defined(__CUDA_ARCH__)
+    return c_pow2[i];
+#else
+    return h_pow2[i];
+#endif
+}
+
+// counters shared by all kernels of a ctx (device memory, 8 x u64)
+enum { CNT_UNSAT = 0, CNT_FIRST_BAD = 1, CNT_MIXED_BITS = 2, CNT_N_ERR = 3, CNT_FIRST_ERR = 4, CNT_WORDS = 8 };
+
+PG_HD void counter_add(unsigned long long* c, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(c, v);
+#else
+    *c += v;
+#endif
+}
+PG_HD void counter_min(unsigned long long* c, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(c, v);
+#else
+    if (v < *c) *c = v;
+#endif
+}
+
+// bit length of a canonical (non-Montgomery) 256-bit integer
+PG_HD uint32_t limbs_bitlen(const Fr& c) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (c.v[i]) {
+#if defined(__CUDA_ARCH__)
+            n = 32u * i + (32u - __clz(c.v[i]));
+#else
+            n = 32u * i + (32u - (uint32_t)__builtin_clz(c.v[i]));
+#endif
+        }
+    }
+    return n;
+}
+// num_bits_closest_power_of_two(max-1): bits_count(2^bits_count(s) mod q)  -- range.rs:173-189.
+// bits_count(s) = max(1, bitlen(s)); for n <= 254, 2^n < q so the result is n + 1; n = 255 cannot happen for s < q
+// (q < 2^255), the table value below covers it anyway: bitlen(2^255 mod q) = 252.
+PG_HD uint32_t num_bits_from_canonical(const Fr& c) {
+    uint32_t n = limbs_bitlen(c);
+    if (n < 1) n = 1;
+    return n <= 254 ? n + 1 : 252;
+}
+
+// ---------------------------------------------------------------------------------------------------- add_input
+struct AddInputBody {
+    struct Args { const uint4* src; uint4* fr; uint64_t stride; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t i) { tab_store_fr(a.fr, a.stride, 0, i, aos_load(a.src, i)); }
+};
+
+// ---------------------------------------------------------------------------------------------------- range gadgets
+struct DecompSlots { uint32_t v, a0, u, z, y, plane; };   // a0..a0+k are the accumulators A_0..A_k
+
+struct RangeArgs {
+    DevTab x_tab; uint32_t x_loc;
+    uint4* fr; uint32_t* bits; uint4* param; uint64_t stride;
+    uint64_t n; uint32_t k;
+    int uniform; Fr m; Fr negmin;                    // uniform bounds: max-1 and -min
+    const uint4* max_aos; const uint4* min_aos;      // per-instance bounds
+    uint32_t param_m, param_negmin;
+    DecompSlots d[2]; uint32_t slot_o;
+    unsigned long long* counters;
+};
+
+template <bool RANGE>
+struct RangeBody {
+    static constexpr int E = RANGE ? 2 : 1;
+    typedef RangeArgs Args;
+    struct State { Fr u[E]; };
+
+    // scalar_decomposition_gadget up to (and including) u = acc - v; returns u
+    PG_HD static Fr decompose(const Args& a, uint64_t i, const DecompSlots& s, const Fr& v) {
+        tab_store_fr(a.fr, a.stride, s.v, i, v);
+        const Fr c = fr_from_mont(v);                                          // to_bytes(): canonical integer, range.rs:163
+#pragma unroll
+        for (int w = 0; w < 8; w++) a.bits[(uint64_t)(s.plane * 8 + w) * a.stride + i] = c.v[w];   // the 256 bit variables
+        Fr acc = fr_zero();
+        tab_store_fr(a.fr, a.stride, s.a0, i, acc);                            // A_0 = 0, range.rs:138-141
+        for (uint32_t p = 0; p < a.k; p++) {                                   // range.rs:143-153
+            const uint32_t bit = (c.v[p >> 5] >> (p & 31u)) & 1u;
+            if (bit) acc = fr_add(acc, pow2_entry(p));
+            tab_store_fr(a.fr, a.stride, s.a0 + 1 + p, i, acc);
+        }
+        const Fr u = fr_sub(acc, v);                                           // maybe_equal: u = a - b, scalar.rs:111-121
+        tab_store_fr(a.fr, a.stride, s.u, i, u);
+        return u;
+    }
+
+    PG_HD static void pre(const Args& a, uint64_t i, State& st, Fr (&inv_in)[E]) {
+        const Fr x = loc_load(&a.x_tab, a.x_loc, i);
+        Fr m = a.m, negmin = a.negmin;
+        if (!a.uniform) {
+            m = fr_sub(aos_load(a.max_aos, i), fr_one());                      // max_range - one, range.rs:87
+            tab_store_fr(a.param, a.stride, a.param_m, i, m);
+            if (num_bits_from_canonical(fr_from_mont(m)) != a.k) counter_add(a.counters + CNT_MIXED_BITS, 1ull);
+            if (RANGE) {
+                negmin = fr_neg(aos_load(a.min_aos, i));                       // q_c = -min_range, range.rs:62
+                tab_store_fr(a.param, a.stride, a.param_negmin, i, negmin);
+            }
+        }
+        st.u[0] = decompose(a, i, a.d[0], fr_sub(m, x));                       // b - x, range.rs:93-102
+        inv_in[0] = st.u[0];
+        if (RANGE) {
+            st.u[E - 1] = decompose(a, i, a.d[E - 1], fr_add(x, negmin));      // x - a, range.rs:60-69
+            inv_in[E - 1] = st.u[E - 1];
+        }
+    }
+    PG_HD static void post(const Args& a, uint64_t i, const State& st, const Fr (&inv)[E]) {
+        Fr y[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            tab_store_fr(a.fr, a.stride, a.d[e].z, i, inv[e]);                 // z = u^-1 or 0, scalar.rs:122-123
+            y[e] = fr_sub(fr_one(), fr_mul(inv[e], st.u[e]));                  // y = 1 - z*u, scalar.rs:126
+            tab_store_fr(a.fr, a.stride, a.d[e].y, i, y[e]);
+        }
+        if (RANGE) tab_store_fr(a.fr, a.stride, a.slot_o, i, fr_mul(y[0], y[E - 1]));   // y1*y2, range.rs:42
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- maybe_equal
+struct MaybeEqualBody {
+    static constexpr int E = 1;
+    struct Args { DevTab a_tab, b_tab; uint32_t a_loc, b_loc; uint4* fr; uint64_t stride; uint64_t n; };
+    struct State { Fr u[1]; };
+    PG_HD static void pre(const Args& a, uint64_t i, State& st, Fr (&inv_in)[1]) {
+        st.u[0] = fr_sub(loc_load(&a.a_tab, a.a_loc, i), loc_load(&a.b_tab, a.b_loc, i));   // scalar.rs:111-121
+        tab_store_fr(a.fr, a.stride, 0, i, st.u[0]);
+        inv_in[0] = st.u[0];
+    }
+    PG_HD static void post(const Args& a, uint64_t i, const State& st, const Fr (&inv)[1]) {
+        tab_store_fr(a.fr, a.stride, 1, i, inv[0]);                                          // z, scalar.rs:122-123
+        tab_store_fr(a.fr, a.stride, 2, i, fr_sub(fr_one(), fr_mul(inv[0], st.u[0])));       // y, scalar.rs:126
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- is_non_zero
+struct IsNonZeroBody {
+    static constexpr int E = 1;
+    struct Args { const uint4* assigned; uint4* fr; uint64_t stride; uint64_t n; unsigned long long* counters; };
+    struct State { int dummy; };
+    PG_HD static void pre(const Args& a, uint64_t i, State&, Fr (&inv_in)[1]) {
+        const Fr va = aos_load(a.assigned, i);
+        tab_store_fr(a.fr, a.stride, 0, i, va);                                              // var_assigned, scalar.rs:69
+        if (fr_is_zero(va)) {                                                                // invert() is None, scalar.rs:73-80
+            counter_add(a.counters + CNT_N_ERR, 1ull);
+            counter_min(a.counters + CNT_FIRST_ERR, (unsigned long long)i);
+        }
+        inv_in[0] = va;
+    }
+    PG_HD static void post(const Args& a, uint64_t i, const State&, const Fr (&inv)[1]) {
+        tab_store_fr(a.fr, a.stride, 1, i, inv[0]);                                          // inv, scalar.rs:77
+        tab_store_fr(a.fr, a.stride, 2, i, fr_one());                                        // one, scalar.rs:83
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- selections
+struct SelectZeroBody {
+    struct Args { DevTab x_tab, s_tab; uint32_t x_loc, s_loc; uint4* fr; uint64_t stride; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        tab_store_fr(a.fr, a.stride, 0, i, fr_mul(loc_load(&a.x_tab, a.x_loc, i), loc_load(&a.s_tab, a.s_loc, i)));   // scalar.rs:26
+    }
+};
+struct SelectOneBody {
+    struct Args { DevTab y_tab, s_tab; uint32_t y_loc, s_loc; uint4* fr; uint64_t stride; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const Fr y = loc_load(&a.y_tab, a.y_loc, i), s = loc_load(&a.s_tab, a.s_loc, i), one = fr_one();
+        const Fr sy = fr_mul(y, s);                                                           // scalar.rs:43
+        const Fr oms = fr_sub(one, s);                                                        // scalar.rs:45-50
+        tab_store_fr(a.fr, a.stride, 0, i, one);                                              // scalar.rs:41
+        tab_store_fr(a.fr, a.stride, 1, i, sy);
+        tab_store_fr(a.fr, a.stride, 2, i, oms);
+        tab_store_fr(a.fr, a.stride, 3, i, fr_add(sy, oms));                                  // scalar.rs:53-58
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- constrain_to_constant
+struct ConstrainBody {   // only launched when the constant and/or the public input is per-instance
+    struct Args { const uint4* constant; const uint4* pi; uint4* param; uint64_t stride; uint64_t n; int32_t param_qc, param_pi; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        if (a.param_qc >= 0) tab_store_fr(a.param, a.stride, (uint32_t)a.param_qc, i, fr_neg(aos_load(a.constant, i)));   // q_c = -constant
+        if (a.param_pi >= 0) tab_store_fr(a.param, a.stride, (uint32_t)a.param_pi, i, aos_load(a.pi, i));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- gate check
+// q_arith*(q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + PI + q_c) for every row of every instance of one segment.
+struct CheckArgs {
+    DevTab tab[MAX_TABS];
+    const uint4* param; uint64_t param_stride;
+    const DevRow* rows; const uint32_t* pool;
+    uint32_t n_rows, n_pool;
+    uint64_t n_inst; uint64_t base_row;
+    unsigned long long* counters;
+    int mode;
+};
+
+PG_HD Fr gate_term(const Fr& sel, uint32_t sel_idx, const Fr& w, int sparse) {
+    if (sparse) {
+        if (sel_idx == POOL_ZERO) return fr_zero();
+        if (sel_idx == POOL_ONE) return w;
+        if (sel_idx == POOL_MINUS_ONE) return fr_neg(w);
+    }
+    return fr_mul(sel, w);
+}
+
+struct CheckBody {
+    typedef CheckArgs Args;
+    // evaluates all rows of instance i; returns the number of unsatisfied rows, updates first_bad (global row index)
+    template <class PoolT>
+    PG_HD static uint32_t run(const Args& a, const PoolT& pool, uint64_t i, unsigned long long& first_bad) {
+        uint32_t bad = 0;
+        for (uint32_t r = 0; r < a.n_rows; r++) {
+            const DevRow row = a.rows[r];
+            const Fr wa = loc_load(a.tab, row.loc[0], i), wb = loc_load(a.tab, row.loc[1], i);
+            const Fr wc = loc_load(a.tab, row.loc[2], i), wd = loc_load(a.tab, row.loc[3], i);
+            Fr t;
+            if (a.mode && row.sel[0] == POOL_ZERO) t = fr_zero();
+            else t = gate_term(pool(row.sel[0]), row.sel[0], fr_mul(wa, wb), a.mode);
+            t = fr_add(t, gate_term(pool(row.sel[1]), row.sel[1], wa, a.mode));
+            t = fr_add(t, gate_term(pool(row.sel[2]), row.sel[2], wb, a.mode));
+            t = fr_add(t, gate_term(pool(row.sel[3]), row.sel[3], wc, a.mode));
+            t = fr_add(t, gate_term(pool(row.sel[4]), row.sel[4], wd, a.mode));
+            const Fr qc = row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]);
+            t = fr_add(t, qc);
+            if (row.pi_param >= 0) t = fr_add(t, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
+            else if (row.pi_sel != POOL_ZERO) t = fr_add(t, pool(row.pi_sel));
+            if (!fr_is_zero(t)) {
+                bad++;
+                const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
+                if (g < first_bad) first_bad = g;
+            }
+        }
+        return bad;
+    }
+};
+
+// caller-supplied materialised rows (column-major AoS scalars)
+struct CheckRowsBody {
+    struct Args { const uint4* w; const uint4* sel; const uint4* pi; uint64_t n; unsigned long long* counters; };
+    PG_HD static uint32_t run(const Args& a, uint64_t i) {
+        const Fr wa = aos_load(a.w, i), wb = aos_load(a.w, a.n + i), wc = aos_load(a.w, 2 * a.n + i), wd = aos_load(a.w, 3 * a.n + i);
+        Fr t = fr_mul(aos_load(a.sel, i), fr_mul(wa, wb));
+        t = fr_add(t, fr_mul(aos_load(a.sel, a.n + i), wa));
+        t = fr_add(t, fr_mul(aos_load(a.sel, 2 * a.n + i), wb));
+        t = fr_add(t, fr_mul(aos_load(a.sel, 3 * a.n + i), wc));
+        t = fr_add(t, fr_mul(aos_load(a.sel, 4 * a.n + i), wd));
+        t = fr_add(t, aos_load(a.sel, 5 * a.n + i));
+        if (a.pi) t = fr_add(t, aos_load(a.pi, i));
+        return fr_is_zero(t) ? 0u : 1u;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- read-back
+struct DevSeg {
+    uint64_t base_row, base_var, n_inst;
+    uint32_t n_rows, n_vars;
+    DevTab tab[MAX_TABS];
+    const DevRow* rows; const uint32_t* varloc; const uint32_t* pool;
+    const uint4* param; uint64_t param_stride;
+};
+
+PG_HD uint32_t seg_find(const DevSeg* segs, uint32_t n_segs, uint64_t id, bool by_row) {
+    uint32_t lo = 0, hi = n_segs;                      // last segment whose base <= id and that is not empty
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint64_t base = by_row ? segs[mid].base_row : segs[mid].base_var;
+        if (base <= id) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct ReadVarsBody {
+    struct Args { const DevSeg* segs; uint32_t n_segs; uint64_t var0; uint64_t n; uint4* dst; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        const uint64_t v = a.var0 + t;
+        const DevSeg& s = a.segs[seg_find(a.segs, a.n_segs, v, false)];
+        const uint64_t off = v - s.base_var;
+        const uint64_t i = off / s.n_vars; const uint32_t j = (uint32_t)(off % s.n_vars);
+        aos_store(a.dst, t, loc_load(s.tab, s.varloc[j], i));
+    }
+};
+
+struct ColReadBody {   // one column (strided variables) -> contiguous scalars
+    struct Args { DevTab tab; uint32_t loc; uint4* dst; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t i) { aos_store(a.dst, i, loc_load(&a.tab, a.loc, i)); }
+};
+
+struct MaterializeBody {
+    struct Args { const DevSeg* segs; uint32_t n_segs; uint64_t row0; uint64_t n; unsigned long long* w_idx; uint4* w_val; uint4* sel; uint4* pi; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        const uint64_t g = a.row0 + t;
+        const DevSeg& s = a.segs[seg_find(a.segs, a.n_segs, g, true)];
+        const uint64_t off = g - s.base_row;
+        const uint64_t i = off / s.n_rows; const uint32_t r = (uint32_t)(off % s.n_rows);
+        const DevRow row = s.rows[r];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const uint32_t loc = row.loc[w];
+            if (a.w_idx) {
+                const DevTab& tb = s.tab[loc_tab(loc)];
+                a.w_idx[(uint64_t)w * a.n + t] = loc_kind(loc) == LOC_ZERO ? 0ull : tb.var_base + i * tb.var_stride + row.var[w];
+            }
+            if (a.w_val) aos_store(a.w_val, (uint64_t)w * a.n + t, loc_load(s.tab, loc, i));
+        }
+        if (a.sel) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) aos_store(a.sel, (uint64_t)k * a.n + t, pool_load(s.pool, row.sel[k]));
+            aos_store(a.sel, 5ull * a.n + t, row.qc_param >= 0 ? tab_load_fr(s.param, s.param_stride, (uint32_t)row.qc_param, i)
+                                                               : pool_load(s.pool, row.sel[5]));
+        }
+        if (a.pi) aos_store(a.pi, t, row.pi_param >= 0 ? tab_load_fr(s.param, s.param_stride, (uint32_t)row.pi_param, i)
+                                                       : pool_load(s.pool, row.pi_sel));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- synthetic inputs
+PG_HD uint64_t splitmix64_at(uint64_t seed, uint64_t index1) {   // output number index1 (1-based) of SplitMix64(seed)
+    uint64_t z = seed + index1 * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct SynthBody {
+    struct Args { uint64_t seed; uint64_t n; int kind; uint32_t bits; uint4* dst; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        Fr lo, hi;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t w0 = splitmix64_at(a.seed, 8 * i + j + 1), w1 = splitmix64_at(a.seed, 8 * i + 4 + j + 1);
+            lo.v[2 * j] = (uint32_t)w0; lo.v[2 * j + 1] = (uint32_t)(w0 >> 32);
+            hi.v[2 * j] = (uint32_t)w1; hi.v[2 * j + 1] = (uint32_t)(w1 >> 32);
+        }
+        int kind = a.kind;
+        if (kind == 2) kind = (i & 1) ? 0 : 1;
+        Fr out;
+        if (kind == 0) {                                    // from_bytes_wide: lo*R2 + hi*R3 (Montgomery products)
+            out = fr_add(fr_mul(fr_r2(), lo), fr_mul(fr_r3(), hi));
+        } else {                                            // low `bits` bits of the draw (bits <= 254 < log2 q)
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int rem = (int)a.bits - 32 * k;
+                if (rem <= 0) lo.v[k] = 0; else if (rem < 32) lo.v[k] &= (1u << rem) - 1u;
+            }
+            if (kind == 3 && a.bits > 0) lo.v[(a.bits - 1) >> 5] |= 1u << ((a.bits - 1) & 31u);
+            out = fr_mul(fr_r2(), lo);
+        }
+        aos_store(a.dst, i, out);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- Fr self-test
+struct FrOpBody {
+    struct Args { int op; const uint4* a; const uint4* b; uint4* out; uint64_t n; };
+    PG_HD static void run(const Args& g, uint64_t i) {
+        const Fr a = aos_load(g.a, i);
+        Fr b = fr_zero(); if (g.b) b = aos_load(g.b, i);
+        Fr r;
+        switch (g.op) {
+            case 0: r = fr_mul(a, b); break;
+            case 1: r = fr_add(a, b); break;
+            case 2: r = fr_sub(a, b); break;
+            case 3: r = fr_neg(a); break;
+            case 5: r = fr_from_mont(a); break;
+            case 6: r = fr_mul_cios(a, b); break;
+            default: r = fr_zero(); break;
+        }
+        aos_store(g.out, i, r);
+    }
+};
+struct FrInvBody {   // op 4: element-wise invert-or-zero through the block batch inversion
+    static constexpr int E = 1;
+    struct Args { const uint4* a; uint4* out; uint64_t n; };
+    struct State { int dummy; };
+    PG_HD static void pre(const Args& g, uint64_t i, State&, Fr (&inv_in)[1]) { inv_in[0] = aos_load(g.a, i); }
+    PG_HD static void post(const Args& g, uint64_t i, const State&, const Fr (&inv)[1]) { aos_store(g.out, i, inv[0]); }
+};
+
+}  // namespace pg

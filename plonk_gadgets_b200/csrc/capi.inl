@@ -1,0 +1,121 @@
+// capi.inl -- the extern "C" entry points of include/pg_b200.h over Engine<PG_BACKEND>.
+// Included once by engine.cu (PG_BACKEND = pg::CudaBackend: the shipped library) and once by tests/emu (host backend,
+// test infrastructure only).
+struct pg_ctx { pg::Engine<PG_BACKEND> e; };
+
+static bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+#define PG_NEED_CTX(ctx) do { if (!(ctx)) return PG_ERR_ARG; } while (0)
+#define PG_ALIGNED(ctx, p, dev) do { if ((dev) && (p) && misaligned(p)) return (ctx)->e.fail(PG_ERR_ARG, "device pointers must be 16-byte aligned"); } while (0)
+
+extern "C" {
+
+int pg_abi_version(void) { return PG_B200_ABI_VERSION; }
+
+const char* pg_strerror(int code) {
+    switch (code) {
+        case PG_OK: return "ok";
+        case PG_ERR_NON_EXISTING_INVERSE: return "NonExistingInverse";
+        case PG_ERR_CUDA: return "CUDA error";
+        case PG_ERR_ARG: return "bad argument";
+        case PG_ERR_OOM: return "out of device memory";
+        case PG_ERR_MIXED_BITS: return "bounds of one batch must share one bit width";
+        case PG_ERR_NO_DEVICE: return "no usable CUDA device (sm_100a required)";
+        case PG_ERR_STATE: return "invalid state";
+        default: return "unknown error";
+    }
+}
+const char* pg_last_error(const pg_ctx* ctx) { return ctx ? ctx->e.err.c_str() : "null ctx"; }
+
+int pg_ctx_create(const pg_cfg* cfg, pg_ctx** out) {
+    if (!cfg || !out) return PG_ERR_ARG;
+    *out = nullptr;
+    pg_ctx* c = new (std::nothrow) pg_ctx();
+    if (!c) return PG_ERR_OOM;
+    int rc = c->e.create(*cfg);
+    if (rc != PG_OK) { fprintf(stderr, "pg_ctx_create: %s (%s)\n", pg_strerror(rc), c->e.err.c_str()); delete c; return rc; }
+    *out = c;
+    return PG_OK;
+}
+void pg_ctx_destroy(pg_ctx* ctx) { if (ctx) { ctx->e.destroy(); delete ctx; } }
+int pg_composer_reset(pg_ctx* ctx) { PG_NEED_CTX(ctx); return ctx->e.reset(); }
+int pg_sync(pg_ctx* ctx) { PG_NEED_CTX(ctx); return ctx->e.be.sync() ? PG_OK : ctx->e.fail(PG_ERR_CUDA, "sync"); }
+
+int pg_add_input_batch(pg_ctx* ctx, uint64_t n, const pg_fr* values, int on_device, pg_col* out) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, values, on_device);
+    return ctx->e.add_input_batch(n, values, on_device, out);
+}
+int pg_range_check_batch(pg_ctx* ctx, const pg_fr* mn, const pg_fr* mx, uint64_t n_bounds, int on_device, pg_col witness, pg_col* out, uint64_t* num_bits) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, mn, on_device); PG_ALIGNED(ctx, mx, on_device);
+    return ctx->e.range_batch(true, mn, mx, n_bounds, on_device, witness, out, num_bits);
+}
+int pg_max_bound_batch(pg_ctx* ctx, const pg_fr* mx, uint64_t n_bounds, int on_device, pg_col witness, pg_col* out, uint64_t* num_bits) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, mx, on_device);
+    return ctx->e.range_batch(false, nullptr, mx, n_bounds, on_device, witness, out, num_bits);
+}
+int pg_maybe_equal_batch(pg_ctx* ctx, pg_col a, pg_col b, pg_col* out) { PG_NEED_CTX(ctx); return ctx->e.maybe_equal_batch(a, b, out); }
+int pg_is_non_zero_batch(pg_ctx* ctx, pg_col var, const pg_fr* value_assigned, int on_device, uint64_t* n_err, uint64_t* first_err) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, value_assigned, on_device);
+    return ctx->e.is_non_zero_batch(var, value_assigned, on_device, n_err, first_err);
+}
+int pg_select_zero_batch(pg_ctx* ctx, pg_col x, pg_col select, pg_col* out) { PG_NEED_CTX(ctx); return ctx->e.select_batch(false, x, select, out); }
+int pg_select_one_batch(pg_ctx* ctx, pg_col y, pg_col selector, pg_col* out) { PG_NEED_CTX(ctx); return ctx->e.select_batch(true, y, selector, out); }
+int pg_constrain_to_constant_batch(pg_ctx* ctx, pg_col a, const pg_fr* constant, uint64_t n_const, const pg_fr* pi, uint64_t n_pi, int on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, constant, on_device); PG_ALIGNED(ctx, pi, on_device);
+    return ctx->e.constrain_batch(a, constant, n_const, pi, n_pi, on_device);
+}
+
+int pg_check(pg_ctx* ctx, uint64_t* n_unsat, uint64_t* first_bad_row) { PG_NEED_CTX(ctx); return ctx->e.check(n_unsat, first_bad_row); }
+int pg_check_rows(pg_ctx* ctx, uint64_t n, const pg_fr* w_val, const pg_fr* sel, const pg_fr* pi, int on_device, uint64_t* n_unsat, uint64_t* first_bad_row) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, w_val, on_device); PG_ALIGNED(ctx, sel, on_device); PG_ALIGNED(ctx, pi, on_device);
+    return ctx->e.check_rows(n, w_val, sel, pi, on_device, n_unsat, first_bad_row);
+}
+
+int pg_counts(const pg_ctx* ctx, uint64_t* n_rows, uint64_t* n_vars) {
+    PG_NEED_CTX(ctx);
+    if (n_rows) *n_rows = ctx->e.n_rows;
+    if (n_vars) *n_vars = ctx->e.n_vars;
+    return PG_OK;
+}
+int pg_col_info(const pg_ctx* ctx, pg_col col, uint64_t* n, uint64_t* first_var, uint64_t* stride) {
+    PG_NEED_CTX(ctx);
+    const pg::Column* c = ctx->e.column(col);
+    if (!c) return PG_ERR_ARG;
+    const pg::Segment& s = ctx->e.segs[c->seg];
+    if (n) *n = c->n;
+    if (first_var) *first_var = s.base_var + c->inst_off * s.t.n_vars + c->local;
+    if (stride) *stride = s.t.n_vars;
+    return PG_OK;
+}
+int pg_col_read(pg_ctx* ctx, pg_col col, uint64_t i0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device);
+    return ctx->e.col_read(col, i0, cnt, dst, dst_on_device);
+}
+int pg_read_variables(pg_ctx* ctx, uint64_t var0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device);
+    return ctx->e.read_variables(var0, cnt, dst, dst_on_device);
+}
+int pg_materialize_rows(pg_ctx* ctx, uint64_t row0, uint64_t cnt, uint64_t* w_idx, pg_fr* w_val, pg_fr* sel, pg_fr* pi, int dst_on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, w_val, dst_on_device); PG_ALIGNED(ctx, sel, dst_on_device); PG_ALIGNED(ctx, pi, dst_on_device);
+    return ctx->e.materialize(row0, cnt, w_idx, w_val, sel, pi, dst_on_device);
+}
+
+int pg_synth(pg_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t n, int kind, uint32_t bits, pg_fr* dst_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst_device, 1);
+    return ctx->e.synth(seed, stream, n, kind, bits, dst_device);
+}
+int pg_get_timing(pg_ctx* ctx, pg_timing* out, int reset) {
+    PG_NEED_CTX(ctx);
+    if (!out) return PG_ERR_ARG;
+    return ctx->e.be.timing(out, reset != 0) ? PG_OK : ctx->e.fail(PG_ERR_CUDA, "timing");
+}
+int pg_measure_imad_peak(pg_ctx* ctx, double* wide_mac_per_s, double* imad_per_s) {
+    PG_NEED_CTX(ctx);
+    double w = 0, l = 0;
+    if (!ctx->e.be.imad_peak(&w, &l)) return ctx->e.fail(PG_ERR_CUDA, "imad peak");
+    if (wide_mac_per_s) *wide_mac_per_s = w;
+    if (imad_per_s) *imad_per_s = l;
+    return PG_OK;
+}
+int pg_fr_op(pg_ctx* ctx, int op, uint64_t n, const pg_fr* a, const pg_fr* b, pg_fr* out) { PG_NEED_CTX(ctx); return ctx->e.fr_op(op, n, a, b, out); }
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// engine.cu -- CUDA backend (sm_100a) and the extern "C" ABI of include/pg_b200.h.
+//
+// This translation unit is the whole shipped library: Engine<CudaBackend>.  There is no CPU path in it -- when no B200 is
+// present pg_ctx_create fails with PG_ERR_NO_DEVICE and nothing else can be called.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <new>
+#include "engine.hpp"
+#include "kernels.cuh"
+
+namespace pg {
+
+Fr h_pow2[256];
+
+#define PG_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) { snprintf(errbuf, sizeof(errbuf), "%s: %s", #call, cudaGetErrorString(e_)); return false; } \
+    } while (0)
+
+class CudaBackend {
+public:
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool nodev = false;
+    bool timing_on = false;
+    char errbuf[512] = {0};
+    int sm_count = 0;
+    struct Ev { cudaEvent_t a, b; int cls; uint64_t rows; };
+    std::vector<Ev> events;
+    std::vector<cudaEvent_t> ev_free;
+    pg_timing acc{};
+
+    const char* error() const { return errbuf; }
+    bool no_device() const { return nodev; }
+
+    bool init(const pg_cfg& cfg) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) { nodev = true; snprintf(errbuf, sizeof(errbuf), "no CUDA device: %s", cudaGetErrorString(e)); return false; }
+        if (cfg.device < 0 || cfg.device >= count) { nodev = true; snprintf(errbuf, sizeof(errbuf), "device %d out of range (%d devices)", cfg.device, count); return false; }
+        PG_CUDA(cudaSetDevice(cfg.device));
+        cudaDeviceProp prop;
+        PG_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+        if (prop.major != 10) { nodev = true; snprintf(errbuf, sizeof(errbuf), "device %d is sm_%d%d; this library is built for sm_100a only", cfg.device, prop.major, prop.minor); return false; }
+        sm_count = prop.multiProcessorCount;
+        if (cfg.stream) { stream = (cudaStream_t)cfg.stream; own_stream = false; }
+        else { PG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        timing_on = (cfg.flags & PG_F_TIMING) != 0;
+        PG_CUDA(cudaFuncSetAttribute(k_check, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        return true;
+    }
+    void shutdown() {
+        for (auto& ev : events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+        for (auto& ev : ev_free) cudaEventDestroy(ev);
+        events.clear(); ev_free.clear();
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+    void* alloc(size_t bytes) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { snprintf(errbuf, sizeof(errbuf), "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+        return p;
+    }
+    void release(void* p) { cudaFree(p); }
+    bool h2d(void* dst, const void* src, size_t bytes) { PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); return true; }
+    bool d2h(void* dst, const void* src, size_t bytes) {
+        PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        return true;
+    }
+    bool d2d(void* dst, const void* src, size_t bytes) { PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); return true; }
+    bool sync() { PG_CUDA(cudaStreamSynchronize(stream)); return true; }
+    bool upload_pow2(const Fr* table) {
+        PG_CUDA(cudaMemcpyToSymbolAsync(c_pow2, table, 256 * sizeof(Fr), 0, cudaMemcpyHostToDevice, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        return true;
+    }
+
+    // ---- timing --------------------------------------------------------------------------------------------------
+    cudaEvent_t get_event() {
+        if (!ev_free.empty()) { cudaEvent_t e = ev_free.back(); ev_free.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void tic(int cls, uint64_t rows) {
+        if (!timing_on) return;
+        Ev ev{get_event(), get_event(), cls, rows};
+        cudaEventRecord(ev.a, stream);
+        events.push_back(ev);
+    }
+    void toc() { if (timing_on) cudaEventRecord(events.back().b, stream); }
+    bool timing(pg_timing* out, bool reset) {
+        PG_CUDA(cudaStreamSynchronize(stream));
+        for (auto& ev : events) {
+            float ms = 0.f; cudaEventElapsedTime(&ms, ev.a, ev.b);
+            if (ev.cls == CLS_CHECK) { acc.check_ms += ms; acc.check_launches++; acc.check_rows += ev.rows; }
+            else if (ev.cls == CLS_WITNESS) { acc.witness_ms += ms; acc.witness_launches++; }
+            else { acc.other_ms += ms; acc.other_launches++; }
+            ev_free.push_back(ev.a); ev_free.push_back(ev.b);
+        }
+        events.clear();
+        *out = acc;
+        if (reset) acc = pg_timing{};
+        return true;
+    }
+    bool launched(const char* what) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { snprintf(errbuf, sizeof(errbuf), "%s launch: %s", what, cudaGetErrorString(e)); return false; }
+        return true;
+    }
+    static unsigned grid_for(uint64_t n) { return (unsigned)((n + BLOCK - 1) / BLOCK); }
+
+    // ---- launches ------------------------------------------------------------------------------------------------
+    template <class Body>
+    bool run_simple(const typename Body::Args& a, uint64_t n, int cls) {
+        tic(cls, 0);
+        k_simple<Body><<<grid_for(n), BLOCK, 0, stream>>>(a);
+        toc();
+        return launched("k_simple");
+    }
+    template <class Body>
+    bool run_inv(const typename Body::Args& a, uint64_t n, int cls) {
+        tic(cls, 0);
+        k_inv<Body><<<grid_for(n), BLOCK, 0, stream>>>(a);
+        toc();
+        return launched("k_inv");
+    }
+    bool run_check(const CheckArgs& a) {
+        const size_t smem = (size_t)a.n_pool * sizeof(Fr);
+        if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
+        tic(CLS_CHECK, a.n_inst * a.n_rows);
+        k_check<<<grid_for(a.n_inst), BLOCK, smem, stream>>>(a);
+        toc();
+        return launched("k_check");
+    }
+    bool run_check_rows(const CheckRowsBody::Args& a) {
+        tic(CLS_CHECK, a.n);
+        k_check_rows<<<grid_for(a.n), BLOCK, 0, stream>>>(a);
+        toc();
+        return launched("k_check_rows");
+    }
+    bool imad_peak(double* wide, double* lo) {
+        const int iters = 8192, blocks = sm_count * 8;
+        uint64_t* buf = nullptr;
+        PG_CUDA(cudaMalloc(&buf, (size_t)blocks * BLOCK * sizeof(uint64_t)));
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        double best[2] = {0, 0};
+        for (int which = 0; which < 2; which++) {
+            for (int rep = 0; rep < 4; rep++) {
+                cudaEventRecord(a, stream);
+                if (which == 0) k_imad_wide<<<blocks, BLOCK, 0, stream>>>(buf, 12345u + rep, 0x9e3779b1u, iters);
+                else k_imad_lo<<<blocks, BLOCK, 0, stream>>>((uint32_t*)buf, 12345u + rep, 0x9e3779b1u, iters);
+                cudaEventRecord(b, stream);
+                cudaEventSynchronize(b);
+                float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
+                const double ops = (double)blocks * BLOCK * (double)iters * 8.0;
+                if (rep > 0 && ms > 0.f && ops / (ms * 1e-3) > best[which]) best[which] = ops / (ms * 1e-3);
+            }
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf);
+        if (!launched("k_imad")) return false;
+        *wide = best[0]; *lo = best[1];
+        return true;
+    }
+};
+
+}  // namespace pg
+
+#define PG_BACKEND pg::CudaBackend
+#include "capi.inl"

@@ -1,0 +1,498 @@
+// engine.hpp -- host logic of the device-resident batched composer, generic over a Backend.
+//
+// The shipped library (engine.cu) instantiates Engine<CudaBackend> only.  tests/emu instantiates the same logic over a
+// host backend that runs the per-instance bodies in a loop, which lets template construction, Variable/row numbering,
+// operand resolution and witness arithmetic be tested without a GPU; that build is test infrastructure and is never
+// loaded by the package.
+//
+// Backend concept:
+//   bool init(const pg_cfg&), void shutdown(), const char* error()
+//   void* alloc(size_t), void release(void*)                       -- device memory
+//   bool h2d(void*, const void*, size_t), bool d2h(void*, const void*, size_t) [d2h returns after the data arrived]
+//   bool d2d(void*, const void*, size_t), bool sync()
+//   template<class Body> bool run_simple(const typename Body::Args&, uint64_t n, int cls)
+//   template<class Body> bool run_inv(const typename Body::Args&, uint64_t n, int cls)
+//   bool run_check(const CheckArgs&), bool run_check_rows(const CheckRowsBody::Args&)
+//   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), timing(pg_timing*, bool reset)
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/pg_b200.h"
+#include "templates.hpp"
+
+namespace pg {
+
+enum { CLS_CHECK = 0, CLS_WITNESS = 1, CLS_OTHER = 2 };
+
+struct Column { uint32_t seg; uint32_t local; uint64_t inst_off; uint64_t n; };
+
+struct Segment {
+    Template t;
+    uint64_t n_inst = 0, n_alloc = 0, base_row = 0, base_var = 0;
+    uint4* fr = nullptr; uint32_t* bits = nullptr; uint4* param = nullptr;
+    DevRow* d_rows = nullptr; uint32_t* d_varloc = nullptr; uint32_t* d_pool = nullptr;
+    DevTab tabs[MAX_TABS] = {};
+    std::vector<DevRow> rows;
+};
+
+inline Fr fr_from_pg(const pg_fr& x) {
+    Fr r;
+    for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)x.l[i]; r.v[2 * i + 1] = (uint32_t)(x.l[i] >> 32); }
+    return r;
+}
+
+template <class BE>
+class Engine {
+public:
+    BE be;
+    pg_cfg cfg{};
+    std::string err;
+    std::vector<Segment> segs;
+    std::vector<Column> cols;
+    std::vector<DevSeg> dsegs;
+    DevSeg* d_segs = nullptr; size_t d_segs_cap = 0;
+    unsigned long long* d_counters = nullptr;
+    uint64_t n_rows = 0, n_vars = 0;
+    std::multimap<size_t, void*> pool_free;          // size -> buffer (exact-size reuse across composer resets)
+    std::map<void*, size_t> pool_live;
+    std::vector<void*> scratch;                      // temporaries that must outlive the enqueued work (freed on reset)
+
+    // ------------------------------------------------------------------------------------------------ memory
+    void* dalloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        auto it = pool_free.find(bytes);
+        void* p;
+        if (it != pool_free.end()) { p = it->second; pool_free.erase(it); }
+        else p = be.alloc(bytes);
+        if (p) pool_live[p] = bytes;
+        return p;
+    }
+    void dfree(void* p) {
+        if (!p) return;
+        auto it = pool_live.find(p);
+        if (it == pool_live.end()) return;
+        pool_free.insert({it->second, p});
+        pool_live.erase(it);
+    }
+    int fail(int code, const std::string& what) { err = what; if (code == PG_ERR_CUDA && be.error()[0]) err += std::string(": ") + be.error(); return code; }
+
+    // ------------------------------------------------------------------------------------------------ lifetime
+    int create(const pg_cfg& c) {
+        cfg = c;
+        if (!be.init(cfg)) return fail(be.no_device() ? PG_ERR_NO_DEVICE : PG_ERR_CUDA, "backend init");
+        // 2^i * R table (selectors of range.rs:146 and accumulator increments)
+        h_pow2[0] = fr_one();
+        for (int i = 1; i < 256; i++) h_pow2[i] = fr_add(h_pow2[i - 1], h_pow2[i - 1]);
+        if (!be.upload_pow2(h_pow2)) return fail(PG_ERR_CUDA, "upload 2^i table");
+        d_counters = (unsigned long long*)dalloc(CNT_WORDS * sizeof(unsigned long long));
+        if (!d_counters) return fail(PG_ERR_OOM, "counters");
+        return reset();
+    }
+    void destroy() {
+        be.sync();
+        release_segments();
+        dfree(d_counters); dfree(d_segs);
+        for (auto& kv : pool_free) be.release(kv.second);
+        for (auto& kv : pool_live) be.release(kv.first);
+        pool_free.clear(); pool_live.clear();
+        be.shutdown();
+    }
+    void release_segments() {
+        for (auto& s : segs) { dfree(s.fr); dfree(s.bits); dfree(s.param); dfree(s.d_rows); dfree(s.d_varloc); dfree(s.d_pool); }
+        for (void* p : scratch) dfree(p);
+        scratch.clear(); segs.clear(); cols.clear(); dsegs.clear();
+        n_rows = 0; n_vars = 0;
+    }
+    // StandardComposer::new(): 5 variables, 3 rows
+    int reset() {
+        if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
+        release_segments();
+        std::vector<Fr> vals;
+        Template t = make_preamble_template(&vals);
+        int rc = push_segment(std::move(t), 1, nullptr, 0);
+        if (rc) return rc;
+        Segment& s = segs.back();
+        std::vector<uint4> img(2 * vals.size());
+        for (size_t j = 0; j < vals.size(); j++) {
+            img[2 * j] = make_uint4(vals[j].v[0], vals[j].v[1], vals[j].v[2], vals[j].v[3]);
+            img[2 * j + 1] = make_uint4(vals[j].v[4], vals[j].v[5], vals[j].v[6], vals[j].v[7]);
+        }
+        if (!be.h2d(s.fr, img.data(), img.size() * sizeof(uint4)) || !be.sync()) return fail(PG_ERR_CUDA, "preamble upload");
+        return PG_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------------ segments
+    const Column* column(pg_col c) const { return (c >= 1 && c <= cols.size()) ? &cols[c - 1] : nullptr; }
+    pg_col new_column(uint32_t seg, uint32_t local, uint64_t n) { cols.push_back(Column{seg, local, 0, n}); return (pg_col)cols.size(); }
+
+    DevTab view_of(const Column& c) const {
+        const Segment& s = segs[c.seg];
+        DevTab v;
+        v.fr = s.fr ? s.fr + c.inst_off : nullptr;
+        v.bits = s.bits ? s.bits + c.inst_off : nullptr;
+        v.stride = s.n_alloc; v.var_base = s.base_var + c.inst_off * s.t.n_vars; v.var_stride = s.t.n_vars;
+        return v;
+    }
+    uint32_t loc_of(const Column& c) const { return segs[c.seg].t.var_loc[c.local]; }
+
+    // Appends a segment of n instances of template t whose operands are the given columns.  Allocates the variable
+    // table, resolves the symbolic wires and uploads the row program.  The witness kernels run afterwards.
+    int push_segment(Template&& t, uint64_t n, const Column* operands, uint32_t n_operands) {
+        Segment s;
+        s.t = std::move(t);
+        s.n_inst = n; s.n_alloc = n ? n : 1;
+        s.base_row = n_rows; s.base_var = n_vars;
+        const Template& T = s.t;
+        if (T.n_fr) { s.fr = (uint4*)dalloc((size_t)T.n_fr * 2 * s.n_alloc * sizeof(uint4)); if (!s.fr) return fail(PG_ERR_OOM, "variable table"); }
+        if (T.n_planes) { s.bits = (uint32_t*)dalloc((size_t)T.n_planes * 8 * s.n_alloc * sizeof(uint32_t)); if (!s.bits) return fail(PG_ERR_OOM, "bit planes"); }
+        if (T.n_params) { s.param = (uint4*)dalloc((size_t)T.n_params * 2 * s.n_alloc * sizeof(uint4)); if (!s.param) return fail(PG_ERR_OOM, "parameter table"); }
+        s.tabs[0].fr = s.fr; s.tabs[0].bits = s.bits; s.tabs[0].stride = s.n_alloc; s.tabs[0].var_base = s.base_var; s.tabs[0].var_stride = T.n_vars;
+        for (uint32_t e = 0; e < n_operands; e++) s.tabs[e + 1] = view_of(operands[e]);
+        s.rows.resize(T.rows.size());
+        for (size_t r = 0; r < T.rows.size(); r++) {
+            const RowT& src = T.rows[r]; DevRow d; memset(&d, 0, sizeof(d));
+            for (int w = 0; w < 4; w++) {
+                const WireRef& wr = src.w[w];
+                if (wr.src == 0) { d.loc[w] = loc_make(LOC_ZERO, 0, 0); d.var[w] = 0; }
+                else if (wr.src == 1) { d.loc[w] = T.var_loc[wr.idx]; d.var[w] = wr.idx; }
+                else { const uint32_t e = wr.src - 2u; d.loc[w] = loc_with_tab(loc_of(operands[e]), e + 1); d.var[w] = operands[e].local; }
+            }
+            for (int k = 0; k < 6; k++) d.sel[k] = src.sel[k];
+            d.pi_sel = src.pi_sel; d.qc_param = src.qc_param; d.pi_param = src.pi_param;
+            s.rows[r] = d;
+        }
+        if (!s.rows.empty()) {
+            s.d_rows = (DevRow*)dalloc(s.rows.size() * sizeof(DevRow));
+            if (!s.d_rows || !be.h2d(s.d_rows, s.rows.data(), s.rows.size() * sizeof(DevRow))) return fail(PG_ERR_CUDA, "row template upload");
+        }
+        if (!T.var_loc.empty()) {
+            s.d_varloc = (uint32_t*)dalloc(T.var_loc.size() * sizeof(uint32_t));
+            if (!s.d_varloc || !be.h2d(s.d_varloc, T.var_loc.data(), T.var_loc.size() * sizeof(uint32_t))) return fail(PG_ERR_CUDA, "variable map upload");
+        }
+        s.d_pool = (uint32_t*)dalloc(T.pool.size() * sizeof(Fr));
+        if (!s.d_pool || !be.h2d(s.d_pool, T.pool.data(), T.pool.size() * sizeof(Fr))) return fail(PG_ERR_CUDA, "selector pool upload");
+        // (pageable sources: cudaMemcpyAsync has consumed them when it returns; they stay alive in the Segment anyway)
+        segs.push_back(std::move(s));
+        Segment& S = segs.back();
+        n_rows += n * S.t.rows.size(); n_vars += n * (uint64_t)S.t.n_vars;
+        return sync_dsegs();
+    }
+    DevSeg make_dseg(const Segment& s) const {
+        DevSeg d; memset(&d, 0, sizeof(d));
+        d.base_row = s.base_row; d.base_var = s.base_var; d.n_inst = s.n_inst;
+        d.n_rows = (uint32_t)s.t.rows.size(); d.n_vars = s.t.n_vars;
+        for (int k = 0; k < MAX_TABS; k++) d.tab[k] = s.tabs[k];
+        d.rows = s.d_rows; d.varloc = s.d_varloc; d.pool = s.d_pool; d.param = s.param; d.param_stride = s.n_alloc;
+        return d;
+    }
+    int sync_dsegs() {
+        dsegs.resize(segs.size());
+        for (size_t k = 0; k < segs.size(); k++) dsegs[k] = make_dseg(segs[k]);
+        if (dsegs.size() > d_segs_cap) {
+            if (d_segs) scratch.push_back(d_segs);       // may still be read by enqueued kernels
+            d_segs_cap = dsegs.size() * 2 + 8;
+            d_segs = (DevSeg*)dalloc(d_segs_cap * sizeof(DevSeg));
+            if (!d_segs) return fail(PG_ERR_OOM, "segment table");
+        }
+        if (!be.h2d(d_segs, dsegs.data(), dsegs.size() * sizeof(DevSeg))) return fail(PG_ERR_CUDA, "segment table upload");
+        return PG_OK;
+    }
+    // removes the last segment again (used when a call is rejected after its witness kernel ran)
+    void pop_segment() {
+        Segment& s = segs.back();
+        n_rows -= s.n_inst * s.t.rows.size(); n_vars -= s.n_inst * (uint64_t)s.t.n_vars;
+        scratch.push_back(s.fr); scratch.push_back(s.bits); scratch.push_back(s.param);
+        scratch.push_back(s.d_rows); scratch.push_back(s.d_varloc); scratch.push_back(s.d_pool);
+        segs.pop_back();
+        sync_dsegs();
+    }
+
+    // host pointer -> device scratch copy (or pass-through for device pointers)
+    const uint4* stage(const pg_fr* p, uint64_t count, int on_device, int* rc) {
+        *rc = PG_OK;
+        if (on_device) return reinterpret_cast<const uint4*>(p);
+        void* d = dalloc(count * sizeof(pg_fr));
+        if (!d) { *rc = fail(PG_ERR_OOM, "staging buffer"); return nullptr; }
+        scratch.push_back(d);
+        if (!be.h2d(d, p, count * sizeof(pg_fr))) { *rc = fail(PG_ERR_CUDA, "input copy"); return nullptr; }
+        return reinterpret_cast<const uint4*>(d);
+    }
+    int read_counters(unsigned long long* out) {
+        if (!be.d2h(out, d_counters, CNT_WORDS * sizeof(unsigned long long))) return fail(PG_ERR_CUDA, "counter read");
+        return PG_OK;
+    }
+    int reset_counters() {
+        unsigned long long init[CNT_WORDS] = {0, ~0ull, 0, 0, ~0ull, 0, 0, 0};
+        if (!be.h2d(d_counters, init, sizeof(init))) return fail(PG_ERR_CUDA, "counter reset");
+        return PG_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------------ gadgets
+    int add_input_batch(uint64_t n, const pg_fr* values, int on_device, pg_col* out) {
+        if (!out || (n && !values)) return fail(PG_ERR_ARG, "add_input_batch: null argument");
+        int rc; const uint4* src = n ? stage(values, n, on_device, &rc) : nullptr;
+        if (n && !src) return rc;
+        rc = push_segment(make_add_input_template(), n, nullptr, 0);
+        if (rc) return rc;
+        Segment& s = segs.back();
+        AddInputBody::Args a{src, s.fr, s.n_alloc, n};
+        if (n && !be.template run_simple<AddInputBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "add_input kernel");
+        *out = new_column((uint32_t)segs.size() - 1, 0, n);
+        return PG_OK;
+    }
+
+    int range_batch(bool is_range_check, const pg_fr* mn, const pg_fr* mx, uint64_t n_bounds, int on_device, pg_col wit, pg_col* out, uint64_t* num_bits) {
+        const Column* w = column(wit);
+        if (!w || !out || !mx || (is_range_check && !mn)) return fail(PG_ERR_ARG, "range gadget: bad argument");
+        const uint64_t n = w->n;
+        if (n_bounds != 1 && n_bounds != n) return fail(PG_ERR_ARG, "range gadget: n_bounds must be 1 or the column length");
+        const bool uniform = n_bounds == 1;
+        // the first bound fixes num_bits (public data): k = num_bits_closest_power_of_two(max - 1), range.rs:87-90
+        pg_fr mx0, mn0 = {{0, 0, 0, 0}};
+        if (on_device) {
+            if (!be.d2h(&mx0, mx, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "bound read");
+            if (is_range_check && !be.d2h(&mn0, mn, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "bound read");
+        } else { mx0 = mx[0]; if (is_range_check) mn0 = mn[0]; }
+        const Fr m0 = fr_sub(fr_from_pg(mx0), fr_one());
+        const Fr negmin0 = fr_neg(fr_from_pg(mn0));
+        const uint32_t k = num_bits_from_canonical(fr_from_mont(m0));
+        int rc = PG_OK;
+        const uint4 *d_mx = nullptr, *d_mn = nullptr;
+        if (!uniform) {
+            d_mx = stage(mx, n, on_device, &rc); if (!d_mx) return rc;
+            if (is_range_check) { d_mn = stage(mn, n, on_device, &rc); if (!d_mn) return rc; }
+            if ((rc = reset_counters())) return rc;
+        }
+        uint32_t result_local = 0;
+        Column operand = *w;
+        rc = push_segment(make_range_template(is_range_check, k, uniform, m0, negmin0, &result_local), n, &operand, 1);
+        if (rc) return rc;
+        Segment& s = segs.back();
+        RangeArgs a; memset(&a, 0, sizeof(a));
+        a.x_tab = s.tabs[1]; a.x_loc = loc_with_tab(loc_of(operand), 0);     // the body indexes its single operand table directly
+        a.fr = s.fr; a.bits = s.bits; a.param = s.param; a.stride = s.n_alloc; a.n = n; a.k = k;
+        a.uniform = uniform ? 1 : 0; a.m = m0; a.negmin = negmin0; a.max_aos = d_mx; a.min_aos = d_mn;
+        a.param_m = s.t.param_m >= 0 ? (uint32_t)s.t.param_m : 0; a.param_negmin = s.t.param_negmin >= 0 ? (uint32_t)s.t.param_negmin : 0;
+        a.d[0] = s.t.decomp[0]; a.d[1] = s.t.decomp[1]; a.slot_o = s.t.slot_o; a.counters = d_counters;
+        if (n) {
+            const bool ok = is_range_check ? be.template run_inv<RangeBody<true>>(a, n, CLS_WITNESS) : be.template run_inv<RangeBody<false>>(a, n, CLS_WITNESS);
+            if (!ok) return fail(PG_ERR_CUDA, "range witness kernel");
+        }
+        if (!uniform && n) {
+            unsigned long long c[CNT_WORDS];
+            if ((rc = read_counters(c))) return rc;
+            if (c[CNT_MIXED_BITS]) { pop_segment(); return fail(PG_ERR_MIXED_BITS, "per-instance bounds give different num_bits"); }
+        }
+        if (num_bits) *num_bits = k;
+        *out = new_column((uint32_t)segs.size() - 1, result_local, n);
+        return PG_OK;
+    }
+
+    int maybe_equal_batch(pg_col ca, pg_col cb, pg_col* out) {
+        const Column *a = column(ca), *b = column(cb);
+        if (!a || !b || !out || a->n != b->n) return fail(PG_ERR_ARG, "maybe_equal_batch: bad columns");
+        Column ops[2] = {*a, *b}; uint32_t result_local = 0;
+        int rc = push_segment(make_maybe_equal_template(&result_local), ops[0].n, ops, 2);
+        if (rc) return rc;
+        Segment& s = segs.back();
+        MaybeEqualBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, ops[0].n};
+        if (g.n && !be.template run_inv<MaybeEqualBody>(g, g.n, CLS_WITNESS)) return fail(PG_ERR_CUDA, "maybe_equal kernel");
+        *out = new_column((uint32_t)segs.size() - 1, result_local, g.n);
+        return PG_OK;
+    }
+
+    int is_non_zero_batch(pg_col cv, const pg_fr* assigned, int on_device, uint64_t* n_err, uint64_t* first_err) {
+        const Column* v = column(cv);
+        if (!v || (v->n && !assigned)) return fail(PG_ERR_ARG, "is_non_zero_batch: bad argument");
+        const uint64_t n = v->n;
+        int rc; const uint4* src = n ? stage(assigned, n, on_device, &rc) : nullptr;
+        if (n && !src) return rc;
+        if ((rc = reset_counters())) return rc;
+        Column operand = *v;
+        rc = push_segment(make_is_non_zero_template(false), n, &operand, 1);
+        if (rc) return rc;
+        {
+            Segment& s = segs.back();
+            IsNonZeroBody::Args g{src, s.fr, s.n_alloc, n, d_counters};
+            if (n && !be.template run_inv<IsNonZeroBody>(g, n, CLS_WITNESS)) return fail(PG_ERR_CUDA, "is_non_zero kernel");
+        }
+        unsigned long long c[CNT_WORDS];
+        if ((rc = read_counters(c))) return rc;
+        if (n_err) *n_err = c[CNT_N_ERR];
+        if (first_err) *first_err = c[CNT_N_ERR] ? c[CNT_FIRST_ERR] : ~0ull;
+        if (!c[CNT_N_ERR]) return PG_OK;
+        // Err(NonExistingInverse) at instance f: instances < f are complete; instance f has appended var_assigned and the
+        // assert_equal row (scalar.rs:69-71) before returning at :79; nothing after it runs.
+        const uint64_t f = c[CNT_FIRST_ERR];
+        {
+            Segment& s = segs.back();
+            n_rows -= (n - f) * s.t.rows.size(); n_vars -= (n - f) * (uint64_t)s.t.n_vars;
+            s.n_inst = f;
+        }
+        Column part = *v; part.inst_off += f; part.n = 1;
+        rc = push_segment(make_is_non_zero_template(true), 1, &part, 1);
+        if (rc) return rc;
+        Segment& p = segs.back();
+        AddInputBody::Args g{src + 2 * f, p.fr, p.n_alloc, 1};
+        if (!be.template run_simple<AddInputBody>(g, 1, CLS_OTHER)) return fail(PG_ERR_CUDA, "is_non_zero partial kernel");
+        err = "is_non_zero: value_assigned is zero (NonExistingInverse)";
+        return PG_ERR_NON_EXISTING_INVERSE;
+    }
+
+    int select_batch(bool one, pg_col cx, pg_col csel, pg_col* out) {
+        const Column *x = column(cx), *s0 = column(csel);
+        if (!x || !s0 || !out || x->n != s0->n) return fail(PG_ERR_ARG, "select: bad columns");
+        Column ops[2] = {*x, *s0}; uint32_t result_local = 0;
+        int rc = push_segment(make_select_template(one, &result_local), ops[0].n, ops, 2);
+        if (rc) return rc;
+        Segment& s = segs.back();
+        const uint64_t n = ops[0].n;
+        bool ok = true;
+        if (one) { SelectOneBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, n}; if (n) ok = be.template run_simple<SelectOneBody>(g, n, CLS_WITNESS); }
+        else { SelectZeroBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, n}; if (n) ok = be.template run_simple<SelectZeroBody>(g, n, CLS_WITNESS); }
+        if (!ok) return fail(PG_ERR_CUDA, "select kernel");
+        *out = new_column((uint32_t)segs.size() - 1, result_local, n);
+        return PG_OK;
+    }
+
+    int constrain_batch(pg_col ca, const pg_fr* constant, uint64_t n_const, const pg_fr* pi, uint64_t n_pi, int on_device) {
+        const Column* a = column(ca);
+        if (!a || !constant) return fail(PG_ERR_ARG, "constrain_to_constant_batch: bad argument");
+        const uint64_t n = a->n;
+        if ((n_const != 1 && n_const != n) || (pi && n_pi != 1 && n_pi != n)) return fail(PG_ERR_ARG, "constrain_to_constant_batch: lengths must be 1 or n");
+        const bool cu = n_const == 1, pu = pi && n_pi == 1;
+        pg_fr c0 = {{0, 0, 0, 0}}, p0 = {{0, 0, 0, 0}};
+        if (cu) { if (on_device) { if (!be.d2h(&c0, constant, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "constant read"); } else c0 = constant[0]; }
+        if (pu) { if (on_device) { if (!be.d2h(&p0, pi, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "pi read"); } else p0 = pi[0]; }
+        int rc = PG_OK; const uint4 *d_c = nullptr, *d_p = nullptr;
+        if (!cu) { d_c = stage(constant, n, on_device, &rc); if (!d_c) return rc; }
+        if (pi && !pu) { d_p = stage(pi, n, on_device, &rc); if (!d_p) return rc; }
+        Column operand = *a;
+        rc = push_segment(make_constrain_template(cu, fr_neg(fr_from_pg(c0)), pi != nullptr, pu, fr_from_pg(p0)), n, &operand, 1);
+        if (rc) return rc;
+        Segment& s = segs.back();
+        if (s.t.n_params && n) {
+            ConstrainBody::Args g{d_c, d_p, s.param, s.n_alloc, n, s.t.param_qc, s.t.param_pi};
+            if (!be.template run_simple<ConstrainBody>(g, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "constrain kernel");
+        }
+        return PG_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------------ verdict
+    int check(uint64_t* n_unsat, uint64_t* first_bad) {
+        int rc = reset_counters();
+        if (rc) return rc;
+        for (const Segment& s : segs) {
+            if (!s.n_inst || s.t.rows.empty()) continue;
+            CheckArgs a; memset(&a, 0, sizeof(a));
+            for (int k = 0; k < MAX_TABS; k++) a.tab[k] = s.tabs[k];
+            a.param = s.param; a.param_stride = s.n_alloc; a.rows = s.d_rows; a.pool = s.d_pool;
+            a.n_rows = (uint32_t)s.t.rows.size(); a.n_pool = (uint32_t)s.t.pool.size();
+            a.n_inst = s.n_inst; a.base_row = s.base_row; a.counters = d_counters; a.mode = cfg.check_mode;
+            if (!be.run_check(a)) return fail(PG_ERR_CUDA, "gate-check kernel");
+        }
+        unsigned long long c[CNT_WORDS];
+        if ((rc = read_counters(c))) return rc;
+        if (n_unsat) *n_unsat = c[CNT_UNSAT];
+        if (first_bad) *first_bad = c[CNT_FIRST_BAD];
+        return PG_OK;
+    }
+    int check_rows(uint64_t n, const pg_fr* w, const pg_fr* sel, const pg_fr* pi, int on_device, uint64_t* n_unsat, uint64_t* first_bad) {
+        if (n && (!w || !sel)) return fail(PG_ERR_ARG, "check_rows: null argument");
+        int rc = reset_counters();
+        if (rc) return rc;
+        if (n) {
+            const uint4* dw = stage(w, 4 * n, on_device, &rc); if (!dw) return rc;
+            const uint4* ds = stage(sel, 6 * n, on_device, &rc); if (!ds) return rc;
+            const uint4* dp = nullptr;
+            if (pi) { dp = stage(pi, n, on_device, &rc); if (!dp) return rc; }
+            CheckRowsBody::Args a{dw, ds, dp, n, d_counters};
+            if (!be.run_check_rows(a)) return fail(PG_ERR_CUDA, "row-check kernel");
+        }
+        unsigned long long c[CNT_WORDS];
+        if ((rc = read_counters(c))) return rc;
+        if (n_unsat) *n_unsat = c[CNT_UNSAT];
+        if (first_bad) *first_bad = c[CNT_FIRST_BAD];
+        return PG_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------------ read-back
+    template <class T>
+    int deliver(T* dst, const void* dev, size_t bytes, int dst_on_device) {   // dev -> caller memory
+        if (dst_on_device) { if (!be.d2d(dst, dev, bytes)) return fail(PG_ERR_CUDA, "device copy"); }
+        else if (!be.d2h(dst, dev, bytes)) return fail(PG_ERR_CUDA, "result copy");
+        return PG_OK;
+    }
+    int read_variables(uint64_t var0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
+        if (var0 + cnt > n_vars || (cnt && !dst)) return fail(PG_ERR_ARG, "read_variables: range");
+        if (!cnt) return PG_OK;
+        uint4* out = dst_on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(cnt * sizeof(pg_fr));
+        if (!out) return fail(PG_ERR_OOM, "read buffer");
+        if (!dst_on_device) scratch.push_back(out);
+        ReadVarsBody::Args a{d_segs, (uint32_t)dsegs.size(), var0, cnt, out};
+        if (!be.template run_simple<ReadVarsBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "read_variables kernel");
+        return dst_on_device ? PG_OK : deliver(dst, out, cnt * sizeof(pg_fr), 0);
+    }
+    int col_read(pg_col c, uint64_t i0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
+        const Column* col = column(c);
+        if (!col || i0 + cnt > col->n || (cnt && !dst)) return fail(PG_ERR_ARG, "col_read: range");
+        if (!cnt) return PG_OK;
+        // a column is a strided set of variables: gather it with the add_input body run "in reverse" (SoA -> AoS)
+        uint4* out = dst_on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(cnt * sizeof(pg_fr));
+        if (!out) return fail(PG_ERR_OOM, "read buffer");
+        if (!dst_on_device) scratch.push_back(out);
+        Column sub = *col; sub.inst_off += i0; sub.n = cnt;
+        ColReadBody::Args a{view_of(sub), loc_with_tab(loc_of(sub), 0), out, cnt};
+        if (!be.template run_simple<ColReadBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "col_read kernel");
+        return dst_on_device ? PG_OK : deliver(dst, out, cnt * sizeof(pg_fr), 0);
+    }
+    int materialize(uint64_t row0, uint64_t cnt, uint64_t* w_idx, pg_fr* w_val, pg_fr* sel, pg_fr* pi, int dst_on_device) {
+        if (row0 + cnt > n_rows) return fail(PG_ERR_ARG, "materialize_rows: range");
+        if (!cnt) return PG_OK;
+        unsigned long long* d_idx = nullptr; uint4 *d_val = nullptr, *d_sel = nullptr, *d_pi = nullptr;
+        auto buf = [&](void* user, size_t bytes) -> void* {
+            if (!user) return nullptr;
+            if (dst_on_device) return user;
+            void* p = dalloc(bytes); if (p) scratch.push_back(p); return p;
+        };
+        d_idx = (unsigned long long*)buf(w_idx, 4 * cnt * sizeof(uint64_t));
+        d_val = (uint4*)buf(w_val, 4 * cnt * sizeof(pg_fr));
+        d_sel = (uint4*)buf(sel, 6 * cnt * sizeof(pg_fr));
+        d_pi = (uint4*)buf(pi, cnt * sizeof(pg_fr));
+        if ((w_idx && !d_idx) || (w_val && !d_val) || (sel && !d_sel) || (pi && !d_pi)) return fail(PG_ERR_OOM, "materialize buffers");
+        MaterializeBody::Args a{d_segs, (uint32_t)dsegs.size(), row0, cnt, d_idx, d_val, d_sel, d_pi};
+        if (!be.template run_simple<MaterializeBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "materialize kernel");
+        if (dst_on_device) return PG_OK;
+        int rc = PG_OK;
+        if (w_idx && (rc = deliver(w_idx, d_idx, 4 * cnt * sizeof(uint64_t), 0))) return rc;
+        if (w_val && (rc = deliver(w_val, d_val, 4 * cnt * sizeof(pg_fr), 0))) return rc;
+        if (sel && (rc = deliver(sel, d_sel, 6 * cnt * sizeof(pg_fr), 0))) return rc;
+        if (pi && (rc = deliver(pi, d_pi, cnt * sizeof(pg_fr), 0))) return rc;
+        return PG_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------------ helpers
+    int synth(uint64_t seed, uint64_t stream, uint64_t n, int kind, uint32_t bits, pg_fr* dst) {
+        if (n && !dst) return fail(PG_ERR_ARG, "synth: null destination");
+        if (kind < 0 || kind > 3 || (kind != 0 && bits > 254)) return fail(PG_ERR_ARG, "synth: kind/bits");
+        SynthBody::Args a{seed ^ (stream * 0xD1342543DE82EF95ull), n, kind, bits, reinterpret_cast<uint4*>(dst)};
+        if (n && !be.template run_simple<SynthBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "synth kernel");
+        return PG_OK;
+    }
+    int fr_op(int op, uint64_t n, const pg_fr* a, const pg_fr* b, pg_fr* out) {
+        if (!n) return PG_OK;
+        if (!a || !out) return fail(PG_ERR_ARG, "fr_op: null argument");
+        int rc; const uint4* da = stage(a, n, 0, &rc); if (!da) return rc;
+        const uint4* db = nullptr; if (b) { db = stage(b, n, 0, &rc); if (!db) return rc; }
+        uint4* dout = (uint4*)dalloc(n * sizeof(pg_fr)); if (!dout) return fail(PG_ERR_OOM, "fr_op buffer");
+        scratch.push_back(dout);
+        bool ok;
+        if (op == 4) { FrInvBody::Args g{da, dout, n}; ok = be.template run_inv<FrInvBody>(g, n, CLS_OTHER); }
+        else { FrOpBody::Args g{op, da, db, dout, n}; ok = be.template run_simple<FrOpBody>(g, n, CLS_OTHER); }
+        if (!ok) return fail(PG_ERR_CUDA, "fr_op kernel");
+        return deliver(out, dout, n * sizeof(pg_fr), 0);
+    }
+};
+
+}  // namespace pg

@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing: one process per GPU, instances sharded contiguously, no collective inside the data path.
+
+Gadget instances are independent (each call touches only its own new variables plus the shared zero variable,
+/root/reference/src/range.rs:119-158, /root/reference/src/scalar.rs:41,:83), so a batch of n instances is split into
+contiguous ranges, each rank runs the same kernels on its range, and the only exchanges are
+  * an all-reduce of the verdict (sum of unsatisfied-row counts and error counts, min of the first bad row), and
+  * an optional all-gather of the per-instance results / witness shards,
+both through torch.distributed (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests).
+Row and Variable numbering of rank r's shard is offset by what ranks < r appended, so that the union of the shards is the
+sequential composer of the whole batch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+UINT64_MAX = 2 ** 64 - 1
+FRESH_ROWS, FRESH_VARS = 3, 5     # StandardComposer::new(): every rank's local composer starts with these
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous instance range [lo, hi) of `rank`: floor(n*r/G) .. floor(n*(r+1)/G)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+@dataclass
+class ShardOffsets:
+    """Where a rank's gadget rows/variables sit in the sequential composer of the whole batch."""
+    row_offset: int
+    var_offset: int
+
+
+def shard_offsets(n: int, rank: int, world: int, rows_per_instance: int, vars_per_instance: int) -> ShardOffsets:
+    """Global id = local id - (fresh composer part) + offset, for one batched call of uniform instances."""
+    lo, _ = shard_range(n, rank, world)
+    return ShardOffsets(lo * rows_per_instance, lo * vars_per_instance)
+
+
+def allreduce_verdict(n_unsat: int, first_bad_global: int | None, n_err: int, device=None):
+    """Combine per-shard verdicts: (sum n_unsat, min first_bad, sum n_err).  `first_bad_global` must already be in global row
+    numbering (or None).  Works on any initialised torch.distributed backend; returns the local values when not initialised."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return n_unsat, first_bad_global, n_err
+    fb = UINT64_MAX if first_bad_global is None else first_bad_global
+    # int64 tensors: counts are < 2^63; the first-bad row is sent as two 32-bit halves to keep the MIN reduction exact
+    sums = torch.tensor([n_unsat, n_err], dtype=torch.int64, device=device)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    hi = torch.tensor([fb >> 32], dtype=torch.int64, device=device)
+    dist.all_reduce(hi, op=dist.ReduceOp.MIN)
+    lo_val = (fb & 0xFFFFFFFF) if (fb >> 32) == int(hi.item()) else 0xFFFFFFFF
+    lo = torch.tensor([lo_val], dtype=torch.int64, device=device)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    first = (int(hi.item()) << 32) | int(lo.item())
+    return int(sums[0].item()), (None if first == UINT64_MAX else first), int(sums[1].item())
+
+
+def allgather_scalars(local, device=None):
+    """All-gather of per-instance scalar shards ((n_local, 4) int64/uint64 tensors of equal n_local) -> (world*n_local, 4)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size()
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out

@@ -1,0 +1,75 @@
+// tests/emu/engine_emu.cpp -- TEST INFRASTRUCTURE ONLY: the engine's host logic (engine.hpp, templates.hpp) and the
+// per-instance kernel bodies (bodies.cuh) compiled by g++ over a host backend that runs the bodies in a loop.
+//
+// Purpose: check template construction, Variable/row numbering, operand resolution and witness arithmetic against the
+// oracle on a machine without a GPU.  What it does NOT cover: the __global__ wrappers, the block-wide batch inversion
+// (replaced here by one Fermat inversion per element) and the PTX carry chains (covered by fr_emu.cpp) -- those are
+// checked on the B200 by the `-m gpu` tests.  This library is built into tests/emu/_build and loaded only by
+// tests/test_emu_*.py; the package plonk_gadgets_b200 never loads it and has no CPU fallback.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "../../plonk_gadgets_b200/csrc/engine.hpp"
+
+namespace pg {
+
+Fr h_pow2[256];
+
+struct HostPool {
+    const uint32_t* p;
+    Fr operator()(uint32_t idx) const { return pool_load(p, idx); }
+};
+
+class HostBackend {
+public:
+    const char* error() const { return ""; }
+    bool no_device() const { return false; }
+    bool init(const pg_cfg&) { return true; }
+    void shutdown() {}
+    void* alloc(size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 64, bytes ? bytes : 64)) return nullptr; memset(p, 0xA5, bytes); return p; }
+    void release(void* p) { free(p); }
+    bool h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
+    bool d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
+    bool d2d(void* d, const void* s, size_t n) { memmove(d, s, n); return true; }
+    bool sync() { return true; }
+    bool upload_pow2(const Fr*) { return true; }
+    bool timing(pg_timing* out, bool) { memset(out, 0, sizeof(*out)); return true; }
+    bool imad_peak(double*, double*) { return false; }
+
+    template <class Body>
+    bool run_simple(const typename Body::Args& a, uint64_t n, int) {
+        for (uint64_t i = 0; i < n; i++) Body::run(a, i);
+        return true;
+    }
+    template <class Body>
+    bool run_inv(const typename Body::Args& a, uint64_t n, int) {
+        for (uint64_t i = 0; i < n; i++) {
+            typename Body::State st;
+            Fr v[Body::E];
+            Body::pre(a, i, st, v);
+            for (int e = 0; e < Body::E; e++) v[e] = fr_is_zero(v[e]) ? fr_zero() : fr_inv_fermat(v[e]);
+            Body::post(a, i, st, v);
+        }
+        return true;
+    }
+    bool run_check(const CheckArgs& a) {
+        HostPool pool = {a.pool};
+        for (uint64_t i = 0; i < a.n_inst; i++) {
+            unsigned long long fb = ~0ull;
+            const uint32_t bad = CheckBody::run(a, pool, i, fb);
+            if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
+        }
+        return true;
+    }
+    bool run_check_rows(const CheckRowsBody::Args& a) {
+        for (uint64_t i = 0; i < a.n; i++)
+            if (CheckRowsBody::run(a, i)) { a.counters[CNT_UNSAT]++; if (i < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = i; }
+        return true;
+    }
+};
+
+}  // namespace pg
+
+#define PG_BACKEND pg::HostBackend
+#include "../../plonk_gadgets_b200/csrc/capi.inl"

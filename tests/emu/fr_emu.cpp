@@ -1,0 +1,23 @@
+// tests/emu/fr_emu.cpp -- host build of plonk_gadgets_b200/csrc/fr.cuh (TEST ONLY).
+// The device multiplier's even/odd carry-chain algorithm is compiled here through its host emulation so that its limb
+// logic (and the "dropped carry is zero" claims) can be checked against big-int arithmetic without a GPU.
+#define PG_EMU_CHECKS 1
+#include "../../plonk_gadgets_b200/csrc/fr.cuh"
+#include <cstdio>
+#include <cstdlib>
+
+static int g_violations = 0;
+void pg_emu_carry_violation() { g_violations++; }
+
+using pg::Fr;
+extern "C" {
+int emu_violations() { return g_violations; }
+void emu_mul_eo(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_mul_eo(a[i], b[i]); }
+void emu_mul_cios(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_mul_cios(a[i], b[i]); }
+void emu_add(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_add(a[i], b[i]); }
+void emu_sub(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_sub(a[i], b[i]); }
+void emu_neg(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_neg(a[i]); }
+void emu_inv(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_inv_fermat(a[i]); }
+void emu_from_mont(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_from_mont(a[i]); }
+void emu_to_mont(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_to_mont(a[i]); }
+}

@@ -1,0 +1,114 @@
+"""CPU tests of the engine's HOST LOGIC (templates, Variable/row numbering, operand resolution, witness arithmetic)
+through tests/emu: the same engine.hpp/bodies.cuh compiled by g++ over a loop backend.  Test infrastructure only -- the
+CUDA kernels themselves are tested on the B200 by the `-m gpu` tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import plonk_gadgets_b200 as pg
+from plonk_gadgets_b200 import _lib
+from tests.engine_runner import run_engine
+from tests.programs import Q, hx, run_oracle, synth_wide
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+ROOT = os.path.dirname(HERE)
+
+
+def _build(name, src):
+    out = os.path.join(EMU_DIR, "_build", name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    deps = [os.path.join(EMU_DIR, src)] + [os.path.join(ROOT, "plonk_gadgets_b200", "csrc", f)
+                                          for f in os.listdir(os.path.join(ROOT, "plonk_gadgets_b200", "csrc"))]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, os.path.join(EMU_DIR, src)], check=True)
+    return out
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return _lib.bind(C.CDLL(_build("libpg_emu.so", "engine_emu.cpp")))
+
+
+@pytest.fixture(scope="module")
+def fr_emu():
+    return C.CDLL(_build("libfr_emu.so", "fr_emu.cpp"))
+
+
+def test_emu_exports_the_abi(emu):
+    assert emu.pg_abi_version() == 1
+
+
+def test_emu_matches_golden(emu, golden, oracle):
+    for name, spec in golden.items():
+        exp = spec["expected"]
+        snap = run_engine(spec["program"], lambda: pg.StandardComposer(_cdll=emu), oracle)
+        assert (snap.n_rows, snap.n_vars) == (exp["n_rows"], exp["n_vars"]), name
+        assert snap.unsat == exp["unsat"], name
+        assert (list(snap.error) if snap.error else None) == exp["error"], name
+        assert snap.digest() == exp["digest"], name
+        for k, vals in exp["results"].items():
+            assert [hx(v) for v in snap.results(int(k))] == vals, (name, k)
+
+
+@pytest.mark.parametrize("bits", [1, 2, 31, 32, 33, 64, 65, 127, 128, 200, 252, 253])
+def test_emu_range_check_vs_oracle(emu, oracle, bits):
+    r = synth_wide(50 + bits, 12)
+    mx = ((r[0] % 2 ** (bits - 1)) | 2 ** (bits - 1)) + 1 if bits > 1 else 2
+    mn = r[1] % mx
+    wit = [mn, mx - 1, mx, (mn - 1) % Q, 0, Q - 1, r[2], r[3] % mx, (r[4] % mx + mn) % Q, 2 ** bits, 2 ** bits - 1, 1]
+    prog = [dict(op="add_input", values=[hx(x) for x in wit]), dict(op="range_check", min=hx(mn), max=hx(mx), witness=0),
+            dict(op="max_bound", max=hx(mx), witness=0)]
+    so = run_oracle(prog)
+    se = run_engine(prog, lambda: pg.StandardComposer(_cdll=emu), oracle)
+    assert se.digest() == so.digest()
+    assert se.unsat == so.unsat == []
+
+
+def test_emu_mixed_bits_rejected(emu, oracle):
+    c = pg.StandardComposer(_cdll=emu)
+    w = c.add_input(oracle.from_ints([1, 2]))
+    with pytest.raises(pg.EngineError) as e:
+        pg.range_check(c, oracle.from_ints([0, 0]), oracle.from_ints([2 ** 10, 2 ** 20]), w)
+    assert e.value.code == -4
+    assert c.circuit_size() == 3 and c.num_variables() == 5 + 2     # nothing was appended
+    assert c.check_circuit_satisfied() == (0, None)
+
+
+def test_emu_fault_injection(emu, oracle):
+    """Flip one materialised wire value: exactly the rows that read it become unsatisfied (L4 of SURVEY.md 4.5)."""
+    c = pg.StandardComposer(_cdll=emu)
+    w = c.add_input(oracle.from_ints([12345, 2 ** 70]))
+    pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    rows = c.rows()
+    assert c.check_rows(rows["w_val"], rows["sel"], rows["pi"]) == (0, None)
+    bad_w = rows["w_val"].copy()
+    bad_w[2, 100] = oracle.from_ints([424242])[0]      # output wire of row 100
+    assert c.check_rows(bad_w, rows["sel"], rows["pi"]) == (1, 100)
+
+
+def test_fr_even_odd_multiplier_host_emulation(fr_emu):
+    """The device multiplier's even/odd carry-chain algorithm (fr.cuh) through its host emulation, against big ints; and no
+    dropped carry is ever non-zero."""
+    import random
+    R = (1 << 256) % Q
+    rinv = pow(R, -1, Q)
+    rng = random.Random(5)
+    edge = [0, 1, 2, Q - 1, Q - 2, R, Q - R, 2 ** 32 - 1, 2 ** 64 - 1, (1 << 254) + 12345, Q >> 1, (0xffffffff << 224) % Q, Q - 2 ** 224]
+    pairs = [(a, b) for a in edge for b in edge] + [(rng.randrange(Q), rng.randrange(Q)) for _ in range(3000)]
+    pack = lambda vs: np.frombuffer(b"".join(v.to_bytes(32, "little") for v in vs), dtype=np.uint64).reshape(-1, 4).copy()
+    unpack = lambda a: [int.from_bytes(a[i].tobytes(), "little") for i in range(a.shape[0])]
+    A, B = pack([p[0] for p in pairs]), pack([p[1] for p in pairs])
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for fn in ("emu_mul_eo", "emu_mul_cios"):
+        out = np.zeros_like(A)
+        getattr(fr_emu, fn)(C.c_uint64(len(pairs)), vp(A), vp(B), vp(out))
+        assert unpack(out) == [a * b * rinv % Q for a, b in pairs], fn
+    assert fr_emu.emu_violations() == 0
+    for fn, f in (("emu_add", lambda a, b: (a + b) % Q), ("emu_sub", lambda a, b: (a - b) % Q)):
+        out = np.zeros_like(A)
+        getattr(fr_emu, fn)(C.c_uint64(len(pairs)), vp(A), vp(B), vp(out))
+        assert unpack(out) == [f(a, b) for a, b in pairs], fn

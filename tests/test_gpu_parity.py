@@ -1,0 +1,271 @@
+"""Parity tests proper: the CUDA path (libpg_b200.so, through the C ABI) against the CPU oracle and the golden vectors.
+Bit-exact everywhere (integer arithmetic mod q); sizes the oracle finishes in seconds, plus size-independent properties at
+the BASELINE.json sizes.  Run on the B200 box with `pytest -m gpu`."""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+
+import plonk_gadgets_b200 as pg
+from tests.engine_runner import run_engine
+from tests.programs import Q, SEED, hx, run_oracle, synth_wide
+
+pytestmark = pytest.mark.gpu
+
+R = (1 << 256) % Q
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+def gpu_composer(**kw):
+    return pg.StandardComposer(device=0, **kw)
+
+
+def test_cuda_library_is_what_runs():
+    """No fallback: the composer is backed by the in-tree CUDA library and a real device context."""
+    c = gpu_composer()
+    with open("/proc/self/maps") as f:
+        assert "libpg_b200.so" in f.read()
+    assert c.circuit_size() == 3 and c.num_variables() == 5
+    assert c.check_circuit_satisfied() == (0, None)
+
+
+def test_fr_kernels_vs_oracle(oracle):
+    rng = random.Random(11)
+    edge = [0, 1, 2, Q - 1, Q - 2, R, Q - R, 2 ** 32 - 1, 2 ** 64 - 1, (1 << 254) + 12345, Q >> 1, (0xffffffff << 224) % Q, Q - 2 ** 224]
+    pairs = [(a, b) for a in edge for b in edge] + [(rng.randrange(Q), rng.randrange(Q)) for _ in range(20000)]
+    A = oracle.from_ints([p[0] for p in pairs]); B = oracle.from_ints([p[1] for p in pairs])
+    c = gpu_composer()
+    exp = {0: lambda a, b: a * b % Q, 6: lambda a, b: a * b % Q, 1: lambda a, b: (a + b) % Q, 2: lambda a, b: (a - b) % Q}
+    for op, f in exp.items():
+        got = oracle.to_ints(c.fr_op(op, A, B))
+        assert got == [f(a, b) for a, b in pairs], f"fr op {op}"
+    assert oracle.to_ints(c.fr_op(3, A)) == [(-a) % Q for a, _ in pairs]
+    # from_mont: raw limbs of the result are the canonical integer
+    fm = c.fr_op(5, A)
+    assert [int.from_bytes(fm[i].tobytes(), "little") for i in range(len(pairs))] == [a for a, _ in pairs]
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 255, 256, 257, 1000, 4096 + 17])
+def test_block_batch_inversion(oracle, n):
+    """Montgomery's trick across a thread block: zeros anywhere (including whole warps / whole blocks), ragged tails."""
+    rng = random.Random(n)
+    vals = [rng.randrange(Q) for _ in range(n)]
+    for i in range(0, n, 7):
+        vals[i] = 0
+    if n >= 64:
+        for i in range(32, 64):
+            vals[i] = 0                       # a whole warp of zeros
+    if n >= 1000:
+        for i in range(512, 768):
+            vals[i] = 0                       # a whole block of zeros
+    c = gpu_composer()
+    got = oracle.to_ints(c.fr_op(4, oracle.from_ints(vals)))
+    assert got == [0 if v == 0 else pow(v, -1, Q) for v in vals]
+
+
+def test_golden_programs(golden, oracle):
+    """Every golden program (reference KATs + batched programs): counts, verdict, error behaviour, returned values and the
+    digest of the complete composer state."""
+    for name, spec in golden.items():
+        exp = spec["expected"]
+        snap = run_engine(spec["program"], gpu_composer, oracle)
+        assert (snap.n_rows, snap.n_vars) == (exp["n_rows"], exp["n_vars"]), name
+        assert snap.unsat == exp["unsat"], name
+        assert (list(snap.error) if snap.error else None) == exp["error"], name
+        assert snap.digest() == exp["digest"], name
+        for k, vals in exp["results"].items():
+            assert [hx(v) for v in snap.results(int(k))] == vals, (name, k)
+        if "satisfied" in spec:
+            assert (len(snap.unsat) == 0) == spec["satisfied"], name
+
+
+@pytest.mark.parametrize("mode", [pg.CHECK_GENERIC, pg.CHECK_SPARSE])
+def test_check_modes_agree(golden, oracle, mode):
+    for name in ("batch_mixed_circuit", "batch_max_bound_k8_claims", "kat_range_check_1_wrongclaim", "kat_is_non_zero_mismatch"):
+        spec = golden[name]
+        snap = run_engine(spec["program"], lambda: gpu_composer(check_mode=mode), oracle)
+        assert snap.unsat == spec["expected"]["unsat"], name
+
+
+@pytest.mark.parametrize("bits", [1, 2, 31, 32, 33, 64, 65, 127, 128, 200, 252, 253])
+def test_range_check_vs_oracle(oracle, bits):
+    """Random and boundary witnesses (min, max-1, max, min-1, 0, q-1, 2^k ...) at many bit widths, against the C oracle run on
+    the same program: full composer state equal."""
+    r = synth_wide(50 + bits, 300)
+    mx = ((r[0] % 2 ** (bits - 1)) | 2 ** (bits - 1)) + 1 if bits > 1 else 2
+    mn = r[1] % mx
+    wit = [mn, mx - 1, mx, (mn - 1) % Q, 0, Q - 1, 2 ** bits, 2 ** bits - 1, 1] + [x % mx for x in r[2:150]] + r[150:]
+    prog = [dict(op="add_input", values=[hx(x) for x in wit]), dict(op="range_check", min=hx(mn), max=hx(mx), witness=0),
+            dict(op="max_bound", max=hx(mx), witness=0)]
+    so = run_oracle(prog)
+    se = run_engine(prog, gpu_composer, oracle)
+    assert se.digest() == so.digest()
+    assert se.unsat == so.unsat == []
+    assert se.results(1) == so.results(1) and se.results(2) == so.results(2)
+
+
+def test_per_instance_bounds_and_mixed_bits(oracle):
+    r = synth_wide(77, 400)
+    mx = [((x % 2 ** 63) | 2 ** 63) + 1 for x in r[:100]]
+    mn = [r[100 + i] % mx[i] for i in range(100)]
+    wit = [(r[200 + i] % (2 ** 65)) if i % 3 else mn[i] for i in range(100)]
+    prog = [dict(op="add_input", values=[hx(x) for x in wit]),
+            dict(op="range_check", min=[hx(x) for x in mn], max=[hx(x) for x in mx], witness=0)]
+    so, se = run_oracle(prog), run_engine(prog, gpu_composer, oracle)
+    assert se.digest() == so.digest() and se.unsat == []
+    c = gpu_composer()
+    w = c.add_input(oracle.from_ints([1, 2, 3]))
+    with pytest.raises(pg.EngineError) as e:
+        pg.range_check(c, oracle.from_ints([0, 0, 0]), oracle.from_ints([2 ** 10, 2 ** 10, 2 ** 20]), w)
+    assert e.value.code == -4 and c.circuit_size() == 3 and c.check_circuit_satisfied() == (0, None)
+
+
+def test_scalar_gadgets_vs_oracle(oracle):
+    r = synth_wide(5, 3000)
+    n = 1000
+    a = r[:n]; b = [a[i] if i % 2 == 0 else r[n + i] for i in range(n)]
+    sel = [i % 2 for i in range(n)]
+    prog = [dict(op="add_input", values=[hx(x) for x in a]), dict(op="add_input", values=[hx(x) for x in b]),
+            dict(op="add_input", values=[hx(x) for x in sel]),
+            dict(op="maybe_equal", a=0, b=1), dict(op="select_zero", x=0, select=2), dict(op="select_one", y=1, select=3),
+            dict(op="is_non_zero", var=0, assigned=[hx(a[i] if i % 5 else r[2 * n + i]) for i in range(n)])]
+    so, se = run_oracle(prog), run_engine(prog, gpu_composer, oracle)
+    assert se.digest() == so.digest()
+    assert se.unsat == so.unsat and len(se.unsat) == 2 * (n // 5)      # mismatching value_assigned: two rows each
+    # is_non_zero stops at the first zero like `?`
+    vals = r[:700] + [0] + r[700:900] + [0]
+    prog = [dict(op="add_input", values=[hx(x) for x in vals]), dict(op="is_non_zero", var=0, assigned=[hx(x) for x in vals])]
+    so, se = run_oracle(prog), run_engine(prog, gpu_composer, oracle)
+    assert se.error == so.error == (1, "NonExistingInverse", 700)
+    assert se.digest() == so.digest()
+
+
+def test_synth_matches_python_generator(oracle, torch_cuda):
+    torch = torch_cuda
+    c = gpu_composer()
+    n = 513
+    buf = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    c.synth(SEED, 3, 0, 0, buf); c.sync()
+    assert oracle.to_ints(buf.cpu().numpy().view(np.uint64)) == synth_wide(3, n)
+    c.synth(SEED, 3, 1, 64, buf); c.sync()
+    assert oracle.to_ints(buf.cpu().numpy().view(np.uint64)) == _low_bits(3, n, 64)
+    c.synth(SEED, 3, 3, 64, buf); c.sync()
+    assert oracle.to_ints(buf.cpu().numpy().view(np.uint64)) == [v | 2 ** 63 for v in _low_bits(3, n, 64)]
+
+
+def _low_bits(stream, n, bits):
+    from tests.programs import splitmix64
+    words = splitmix64(SEED ^ (stream * 0xD1342543DE82EF95 & (2 ** 64 - 1)), 8 * n).reshape(n, 8)
+    out = []
+    for row in words:
+        v = sum(int(row[j]) << (64 * j) for j in range(4))
+        out.append(v & (2 ** bits - 1))
+    return out
+
+
+def test_fault_injection_rows(oracle):
+    c = gpu_composer()
+    w = c.add_input(oracle.from_ints([12345, 2 ** 70, Q - 5]))
+    pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    rows = c.rows()
+    assert c.check_rows(rows["w_val"], rows["sel"], rows["pi"]) == (0, None)
+    rng = random.Random(2)
+    for _ in range(20):
+        r_, col = rng.randrange(3, c.circuit_size()), rng.randrange(3)
+        bad = rows["w_val"].copy()
+        bad[col, r_] = oracle.from_ints([rng.randrange(1, Q)])[0]
+        n_bad, first = c.check_rows(bad, rows["sel"], rows["pi"])
+        # a changed wire can only break its own row; selector 0 on that wire leaves the row satisfied
+        assert (n_bad, first) in ((1, r_), (0, None))
+
+
+@pytest.mark.parametrize("log2n", [20, 22])
+def test_range_check_c2_properties(oracle, torch_cuda, log2n):
+    """BASELINE config C2 (2^20 range_check, 64-bit bound) and 4x larger: verdict 0 unsatisfied rows; even instances (uniform
+    u64) are in range, odd ones (uniform Fr) are not; a random sample of instances is compared row by row with the oracle."""
+    torch = torch_cuda
+    n = 1 << log2n
+    c = gpu_composer()
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    c.synth(SEED, 2, 2, 64, wit)
+    w = c.add_input(wit)
+    y = pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    assert c.circuit_size() == 3 + 271 * n and c.num_variables() == 5 + n + 653 * n
+    assert c.check_circuit_satisfied() == (0, None)
+    res = y.values()
+    one = oracle.from_ints([1])[0]
+    assert (res[0::2] == one).all() and (res[1::2] == 0).all()
+    # sample: instances -> the oracle's single-instance composer, renumbered
+    rng = random.Random(log2n)
+    sample = [0, 1, n - 2, n - 1] + [rng.randrange(n) for _ in range(12)]
+    wv = w.values()
+    for i in sample:
+        oc = oracle.Composer()
+        ov = oc.add_input_batch(wv[i:i + 1])
+        oc.range_check_batch(oracle.from_ints([0]), oracle.from_ints([2 ** 64]), ov)
+        o_vars = oc.variables()[6:]                              # the 653 variables of the gadget
+        g_vars = c.variables(5 + n + 653 * i, 653)
+        assert (o_vars == g_vars).all(), f"variables of instance {i}"
+        rows = c.rows(3 + 271 * i, 271, want=("w_idx", "sel"))
+        o_w = oc.wires()[:, 3:]; o_sel = oc.selectors()[:6, 3:]
+        # oracle numbering: witness = var 5, gadget vars 6.. ; engine: witness = 5+i, gadget vars 5+n+653*i ..
+        remap = np.where(o_w == 0, 0, np.where(o_w == 5, 5 + i, o_w - 6 + 5 + n + 653 * i)).astype(np.uint64)
+        assert (rows["w_idx"] == remap).all(), f"wires of instance {i}"
+        assert (rows["sel"] == o_sel).all(), f"selectors of instance {i}"
+
+
+def test_max_bound_c3_and_scalar_c4_properties(oracle, torch_cuda):
+    """C3 shape (max_bound, 252-bit per-instance bounds, k=253) and C4 shape (is_non_zero + maybe_equal) at 2^18."""
+    torch = torch_cuda
+    n = 1 << 18
+    c = gpu_composer()
+    mx = torch.empty((n, 4), dtype=torch.int64, device="cuda"); wit = torch.empty_like(mx)
+    c.synth(SEED, 31, 3, 252, mx)           # max in [2^251, 2^252): max-1 has 252 bits unless max = 2^251 exactly
+    c.synth(SEED, 32, 2, 250, wit)          # even: 250-bit (below every bound), odd: uniform Fr
+    w = c.add_input(wit)
+    y, k = pg.max_bound(c, mx, w)
+    assert k == 253 and c.circuit_size() == 3 + 511 * n
+    assert c.check_circuit_satisfied() == (0, None)
+    res = y.values(); one = oracle.from_ints([1])[0]
+    assert (res[0::2] == one).all()
+    frac_in = float((res[1::2] == one).all(axis=1).mean())
+    assert frac_in < 0.2                     # uniform Fr is below a 252-bit bound w.p. ~ 2^252/q ~ 0.14 (or wraps)
+    # C4
+    c.reset()
+    a = torch.empty((n, 4), dtype=torch.int64, device="cuda"); b = torch.empty_like(a)
+    c.synth(SEED, 41, 0, 0, a); c.synth(SEED, 42, 0, 0, b)
+    b[0::2] = a[0::2]
+    va, vb = c.add_input(a), c.add_input(b)
+    eq = pg.maybe_equal(c, va, vb)
+    pg.is_non_zero(c, va, a)
+    assert c.check_circuit_satisfied() == (0, None)
+    r = eq.values()
+    assert (r[0::2] == one).all() and (r[1::2] == 0).all()
+
+
+def test_full_size_metric_config(oracle, torch_cuda):
+    """The headline configuration: 2^24 range_check instances, 64-bit bound (4.55e9 rows) -- verdict and result pattern."""
+    torch = torch_cuda
+    free, _total = torch.cuda.mem_get_info()
+    n = 1 << 24
+    if free < 90 * 2 ** 30:
+        pytest.skip("needs ~80 GB of free HBM")
+    c = gpu_composer()
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    c.synth(SEED, 2, 2, 64, wit)
+    w = c.add_input(wit)
+    y = pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    assert c.check_circuit_satisfied() == (0, None)
+    res = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    c.read_column_into(y, res); c.sync()
+    one = torch.from_numpy(oracle.from_ints([1]).view(np.int64)).cuda()
+    assert bool((res[0::2] == one).all()) and bool((res[1::2] == 0).all())
+    c.close()
