@@ -63,6 +63,7 @@ SIGNATURES = {
     "pg_synth": (_i32, [_vp, _u64, _u64, _u64, _i32, _u32, _vp]),
     "pg_get_timing": (_i32, [_vp, C.POINTER(pg_timing), _i32]),
     "pg_measure_imad_peak": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pg_microbench": (_i32, [_vp, _i32, C.POINTER(C.c_double)]),
     "pg_fr_op": (_i32, [_vp, _i32, _u64, _vp, _vp, _vp]),
 }
 

@@ -244,6 +244,13 @@ class StandardComposer:
         self._ok(self._L.pg_measure_imad_peak(self._ctx, C.byref(w), C.byref(l)), "pg_measure_imad_peak")
         return w.value, l.value
 
+    MICROBENCH_MODES = ("imad_lo", "imad_wide_mul", "imad_wide_acc", "imad_hi", "carry_chain_product", "iadd3", "fr_mul", "fr_mul_cios", "fr_add")
+
+    def microbench(self, mode: int) -> float:
+        v = C.c_double()
+        self._ok(self._L.pg_microbench(self._ctx, mode, C.byref(v)), "pg_microbench")
+        return v.value
+
     def fr_op(self, op: int, a, b=None) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint64)
         b = np.ascontiguousarray(b, dtype=np.uint64) if b is not None else None

@@ -2,8 +2,10 @@
 //
 // Every body is a plain __host__ __device__ function of (arguments, instance index).  The CUDA backend (kernels.cuh)
 // wraps them in __global__ kernels; the test-only host backend (tests/emu) calls them in a loop so that templates,
-// numbering and witness arithmetic can be checked on a machine without a GPU.  Bodies that need a field inversion are
-// split in pre() / post() around the block-wide Montgomery batch inversion.
+// numbering and witness arithmetic can be checked on a machine without a GPU.  Gadgets that need a field inversion are
+// split in a Pre body (everything up to the value to invert, written to its table slot), the stand-alone batch-inversion
+// kernel over those slots (kernels.cuh: Montgomery's trick, 8 elements per thread, one Fermat inversion per 2048
+// elements) and a Post body.
 //
 // Reference functions restated here (witness arithmetic only; row structure lives in templates.hpp):
 //   RangeBody       /root/reference/src/range.rs:27-43 (range_check), :82-113 (max_bound), :53-76 (min_bound),
@@ -90,14 +92,16 @@ struct RangeArgs {
     unsigned long long* counters;
 };
 
+// which table slots the batch inversion reads and writes: out[j] = in[j]^-1 (or 0) for every instance
+struct BatchInvArgs { uint4* fr; uint64_t stride; uint64_t n; uint32_t n_pairs; uint32_t in_slot[4]; uint32_t out_slot[4]; };
+
 template <bool RANGE>
-struct RangeBody {
+struct RangePre {
     static constexpr int E = RANGE ? 2 : 1;
     typedef RangeArgs Args;
-    struct State { Fr u[E]; };
 
-    // scalar_decomposition_gadget up to (and including) u = acc - v; returns u
-    PG_HD static Fr decompose(const Args& a, uint64_t i, const DecompSlots& s, const Fr& v) {
+    // scalar_decomposition_gadget up to (and including) u = acc - v
+    PG_HD static void decompose(const Args& a, uint64_t i, const DecompSlots& s, const Fr& v) {
         tab_store_fr(a.fr, a.stride, s.v, i, v);
         const Fr c = fr_from_mont(v);                                          // to_bytes(): canonical integer, range.rs:163
 #pragma unroll
@@ -109,12 +113,9 @@ struct RangeBody {
             if (bit) acc = fr_add(acc, pow2_entry(p));
             tab_store_fr(a.fr, a.stride, s.a0 + 1 + p, i, acc);
         }
-        const Fr u = fr_sub(acc, v);                                           // maybe_equal: u = a - b, scalar.rs:111-121
-        tab_store_fr(a.fr, a.stride, s.u, i, u);
-        return u;
+        tab_store_fr(a.fr, a.stride, s.u, i, fr_sub(acc, v));                  // maybe_equal: u = a - b, scalar.rs:111-121
     }
-
-    PG_HD static void pre(const Args& a, uint64_t i, State& st, Fr (&inv_in)[E]) {
+    PG_HD static void run(const Args& a, uint64_t i) {
         const Fr x = loc_load(&a.x_tab, a.x_loc, i);
         Fr m = a.m, negmin = a.negmin;
         if (!a.uniform) {
@@ -126,19 +127,20 @@ struct RangeBody {
                 tab_store_fr(a.param, a.stride, a.param_negmin, i, negmin);
             }
         }
-        st.u[0] = decompose(a, i, a.d[0], fr_sub(m, x));                       // b - x, range.rs:93-102
-        inv_in[0] = st.u[0];
-        if (RANGE) {
-            st.u[E - 1] = decompose(a, i, a.d[E - 1], fr_add(x, negmin));      // x - a, range.rs:60-69
-            inv_in[E - 1] = st.u[E - 1];
-        }
+        decompose(a, i, a.d[0], fr_sub(m, x));                                 // b - x, range.rs:93-102
+        if (RANGE) decompose(a, i, a.d[E - 1], fr_add(x, negmin));             // x - a, range.rs:60-69
     }
-    PG_HD static void post(const Args& a, uint64_t i, const State& st, const Fr (&inv)[E]) {
+};
+template <bool RANGE>
+struct RangePost {   // after z = u^-1 (or 0) has been written by the batch inversion (scalar.rs:122-123)
+    static constexpr int E = RANGE ? 2 : 1;
+    typedef RangeArgs Args;
+    PG_HD static void run(const Args& a, uint64_t i) {
         Fr y[E];
 #pragma unroll
         for (int e = 0; e < E; e++) {
-            tab_store_fr(a.fr, a.stride, a.d[e].z, i, inv[e]);                 // z = u^-1 or 0, scalar.rs:122-123
-            y[e] = fr_sub(fr_one(), fr_mul(inv[e], st.u[e]));                  // y = 1 - z*u, scalar.rs:126
+            const Fr u = tab_load_fr(a.fr, a.stride, a.d[e].u, i), z = tab_load_fr(a.fr, a.stride, a.d[e].z, i);
+            y[e] = fr_sub(fr_one(), fr_mul(z, u));                             // y = 1 - z*u, scalar.rs:126
             tab_store_fr(a.fr, a.stride, a.d[e].y, i, y[e]);
         }
         if (RANGE) tab_store_fr(a.fr, a.stride, a.slot_o, i, fr_mul(y[0], y[E - 1]));   // y1*y2, range.rs:42
@@ -146,37 +148,31 @@ struct RangeBody {
 };
 
 // ---------------------------------------------------------------------------------------------------- maybe_equal
-struct MaybeEqualBody {
-    static constexpr int E = 1;
-    struct Args { DevTab a_tab, b_tab; uint32_t a_loc, b_loc; uint4* fr; uint64_t stride; uint64_t n; };
-    struct State { Fr u[1]; };
-    PG_HD static void pre(const Args& a, uint64_t i, State& st, Fr (&inv_in)[1]) {
-        st.u[0] = fr_sub(loc_load(&a.a_tab, a.a_loc, i), loc_load(&a.b_tab, a.b_loc, i));   // scalar.rs:111-121
-        tab_store_fr(a.fr, a.stride, 0, i, st.u[0]);
-        inv_in[0] = st.u[0];
+struct MaybeEqualArgs { DevTab a_tab, b_tab; uint32_t a_loc, b_loc; uint4* fr; uint64_t stride; uint64_t n; };
+struct MaybeEqualPre {    // slots: 0 = u, 1 = z, 2 = y
+    typedef MaybeEqualArgs Args;
+    PG_HD static void run(const Args& a, uint64_t i) {
+        tab_store_fr(a.fr, a.stride, 0, i, fr_sub(loc_load(&a.a_tab, a.a_loc, i), loc_load(&a.b_tab, a.b_loc, i)));   // scalar.rs:111-121
     }
-    PG_HD static void post(const Args& a, uint64_t i, const State& st, const Fr (&inv)[1]) {
-        tab_store_fr(a.fr, a.stride, 1, i, inv[0]);                                          // z, scalar.rs:122-123
-        tab_store_fr(a.fr, a.stride, 2, i, fr_sub(fr_one(), fr_mul(inv[0], st.u[0])));       // y, scalar.rs:126
+};
+struct MaybeEqualPost {
+    typedef MaybeEqualArgs Args;
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const Fr u = tab_load_fr(a.fr, a.stride, 0, i), z = tab_load_fr(a.fr, a.stride, 1, i);
+        tab_store_fr(a.fr, a.stride, 2, i, fr_sub(fr_one(), fr_mul(z, u)));                                           // y, scalar.rs:126
     }
 };
 
 // ---------------------------------------------------------------------------------------------------- is_non_zero
-struct IsNonZeroBody {
-    static constexpr int E = 1;
+struct IsNonZeroPre {     // slots: 0 = var_assigned, 1 = inv (written by the batch inversion), 2 = one
     struct Args { const uint4* assigned; uint4* fr; uint64_t stride; uint64_t n; unsigned long long* counters; };
-    struct State { int dummy; };
-    PG_HD static void pre(const Args& a, uint64_t i, State&, Fr (&inv_in)[1]) {
+    PG_HD static void run(const Args& a, uint64_t i) {
         const Fr va = aos_load(a.assigned, i);
         tab_store_fr(a.fr, a.stride, 0, i, va);                                              // var_assigned, scalar.rs:69
         if (fr_is_zero(va)) {                                                                // invert() is None, scalar.rs:73-80
             counter_add(a.counters + CNT_N_ERR, 1ull);
             counter_min(a.counters + CNT_FIRST_ERR, (unsigned long long)i);
         }
-        inv_in[0] = va;
-    }
-    PG_HD static void post(const Args& a, uint64_t i, const State&, const Fr (&inv)[1]) {
-        tab_store_fr(a.fr, a.stride, 1, i, inv[0]);                                          // inv, scalar.rs:77
         tab_store_fr(a.fr, a.stride, 2, i, fr_one());                                        // one, scalar.rs:83
     }
 };
@@ -395,12 +391,4 @@ struct FrOpBody {
         aos_store(g.out, i, r);
     }
 };
-struct FrInvBody {   // op 4: element-wise invert-or-zero through the block batch inversion
-    static constexpr int E = 1;
-    struct Args { const uint4* a; uint4* out; uint64_t n; };
-    struct State { int dummy; };
-    PG_HD static void pre(const Args& g, uint64_t i, State&, Fr (&inv_in)[1]) { inv_in[0] = aos_load(g.a, i); }
-    PG_HD static void post(const Args& g, uint64_t i, const State&, const Fr (&inv)[1]) { aos_store(g.out, i, inv[0]); }
-};
-
 }  // namespace pg

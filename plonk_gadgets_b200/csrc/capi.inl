@@ -116,6 +116,13 @@ int pg_measure_imad_peak(pg_ctx* ctx, double* wide_mac_per_s, double* imad_per_s
     if (imad_per_s) *imad_per_s = l;
     return PG_OK;
 }
+int pg_microbench(pg_ctx* ctx, int mode, double* ops_per_s) {
+    PG_NEED_CTX(ctx);
+    double v = 0;
+    if (!ctx->e.be.ubench(mode, &v)) return ctx->e.fail(PG_ERR_CUDA, "microbench");
+    if (ops_per_s) *ops_per_s = v;
+    return PG_OK;
+}
 int pg_fr_op(pg_ctx* ctx, int op, uint64_t n, const pg_fr* a, const pg_fr* b, pg_fr* out) { PG_NEED_CTX(ctx); return ctx->e.fr_op(op, n, a, b, out); }
 
 }  // extern "C"

@@ -119,12 +119,13 @@ public:
         toc();
         return launched("k_simple");
     }
-    template <class Body>
-    bool run_inv(const typename Body::Args& a, uint64_t n, int cls) {
+    bool run_batch_inv(const BatchInvArgs& a, int cls) {
+        const uint64_t total = (uint64_t)a.n_pairs * a.n;
+        if (!total) return true;
         tic(cls, 0);
-        k_inv<Body><<<grid_for(n), BLOCK, 0, stream>>>(a);
+        k_batch_inv<<<(unsigned)((total + BLOCK * INV_E - 1) / (BLOCK * INV_E)), BLOCK, 0, stream>>>(a);
         toc();
-        return launched("k_inv");
+        return launched("k_batch_inv");
     }
     bool run_check(const CheckArgs& a) {
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
@@ -140,29 +141,37 @@ public:
         toc();
         return launched("k_check_rows");
     }
-    bool imad_peak(double* wide, double* lo) {
-        const int iters = 8192, blocks = sm_count * 8;
-        uint64_t* buf = nullptr;
-        PG_CUDA(cudaMalloc(&buf, (size_t)blocks * BLOCK * sizeof(uint64_t)));
+    template <int MODE>
+    void ubench_launch(uint32_t* buf, int blocks, int iters, int rep) { k_ubench<MODE><<<blocks, BLOCK, 0, stream>>>(buf, 12345u + rep, 0x9e3779b1u, iters); }
+    // operations per second of one micro-benchmark mode (best of 3 after a warm-up launch)
+    bool ubench(int mode, double* ops_per_s) {
+        if (mode < 0 || mode >= UB_MODES) { snprintf(errbuf, sizeof(errbuf), "unknown micro-benchmark mode %d", mode); return false; }
+        const int blocks = sm_count * 8, iters = mode >= UB_FR_MUL ? 512 : 4096;
+        uint32_t* buf = nullptr;
+        PG_CUDA(cudaMalloc(&buf, (size_t)blocks * BLOCK * sizeof(uint32_t)));
         cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-        double best[2] = {0, 0};
-        for (int which = 0; which < 2; which++) {
-            for (int rep = 0; rep < 4; rep++) {
-                cudaEventRecord(a, stream);
-                if (which == 0) k_imad_wide<<<blocks, BLOCK, 0, stream>>>(buf, 12345u + rep, 0x9e3779b1u, iters);
-                else k_imad_lo<<<blocks, BLOCK, 0, stream>>>((uint32_t*)buf, 12345u + rep, 0x9e3779b1u, iters);
-                cudaEventRecord(b, stream);
-                cudaEventSynchronize(b);
-                float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
-                const double ops = (double)blocks * BLOCK * (double)iters * 8.0;
-                if (rep > 0 && ms > 0.f && ops / (ms * 1e-3) > best[which]) best[which] = ops / (ms * 1e-3);
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(a, stream);
+            switch (mode) {
+                case 0: ubench_launch<0>(buf, blocks, iters, rep); break; case 1: ubench_launch<1>(buf, blocks, iters, rep); break;
+                case 2: ubench_launch<2>(buf, blocks, iters, rep); break; case 3: ubench_launch<3>(buf, blocks, iters, rep); break;
+                case 4: ubench_launch<4>(buf, blocks, iters, rep); break; case 5: ubench_launch<5>(buf, blocks, iters, rep); break;
+                case 6: ubench_launch<6>(buf, blocks, iters, rep); break; case 7: ubench_launch<7>(buf, blocks, iters, rep); break;
+                default: ubench_launch<8>(buf, blocks, iters, rep); break;
             }
+            cudaEventRecord(b, stream);
+            cudaEventSynchronize(b);
+            float ms = 0.f; cudaEventElapsedTime(&ms, a, b);
+            const double ops = (double)blocks * BLOCK * (double)iters * ubench_ops_per_iter(mode);
+            if (rep > 0 && ms > 0.f && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
         }
         cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf);
-        if (!launched("k_imad")) return false;
-        *wide = best[0]; *lo = best[1];
+        if (!launched("k_ubench")) return false;
+        *ops_per_s = best;
         return true;
     }
+    bool imad_peak(double* wide, double* lo) { return ubench(UB_WIDE_ACC, wide) && ubench(UB_IMAD_LO, lo); }
 };
 
 }  // namespace pg

@@ -11,9 +11,9 @@
 //   bool h2d(void*, const void*, size_t), bool d2h(void*, const void*, size_t) [d2h returns after the data arrived]
 //   bool d2d(void*, const void*, size_t), bool sync()
 //   template<class Body> bool run_simple(const typename Body::Args&, uint64_t n, int cls)
-//   template<class Body> bool run_inv(const typename Body::Args&, uint64_t n, int cls)
+//   bool run_batch_inv(const BatchInvArgs&, int cls)            -- out_slot = in_slot^-1 (or 0) over table slots
 //   bool run_check(const CheckArgs&), bool run_check_rows(const CheckRowsBody::Args&)
-//   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), timing(pg_timing*, bool reset)
+//   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), bool ubench(int, double*), timing(pg_timing*, bool reset)
 #pragma once
 #include <map>
 #include <string>
@@ -276,8 +276,14 @@ public:
         a.param_m = s.t.param_m >= 0 ? (uint32_t)s.t.param_m : 0; a.param_negmin = s.t.param_negmin >= 0 ? (uint32_t)s.t.param_negmin : 0;
         a.d[0] = s.t.decomp[0]; a.d[1] = s.t.decomp[1]; a.slot_o = s.t.slot_o; a.counters = d_counters;
         if (n) {
-            const bool ok = is_range_check ? be.template run_inv<RangeBody<true>>(a, n, CLS_WITNESS) : be.template run_inv<RangeBody<false>>(a, n, CLS_WITNESS);
-            if (!ok) return fail(PG_ERR_CUDA, "range witness kernel");
+            // witness generation: decomposition (everything up to u = acc - v) -> batch inversion z = u^-1|0 -> y (and y1*y2)
+            BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
+            inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = is_range_check ? 2 : 1;
+            for (uint32_t e = 0; e < inv.n_pairs; e++) { inv.in_slot[e] = a.d[e].u; inv.out_slot[e] = a.d[e].z; }
+            const bool ok = is_range_check
+                ? be.template run_simple<RangePre<true>>(a, n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true>>(a, n, CLS_WITNESS)
+                : be.template run_simple<RangePre<false>>(a, n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false>>(a, n, CLS_WITNESS);
+            if (!ok) return fail(PG_ERR_CUDA, "range witness kernels");
         }
         if (!uniform && n) {
             unsigned long long c[CNT_WORDS];
@@ -296,8 +302,13 @@ public:
         int rc = push_segment(make_maybe_equal_template(&result_local), ops[0].n, ops, 2);
         if (rc) return rc;
         Segment& s = segs.back();
-        MaybeEqualBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, ops[0].n};
-        if (g.n && !be.template run_inv<MaybeEqualBody>(g, g.n, CLS_WITNESS)) return fail(PG_ERR_CUDA, "maybe_equal kernel");
+        MaybeEqualArgs g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, ops[0].n};
+        if (g.n) {
+            BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
+            inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = g.n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
+            if (!(be.template run_simple<MaybeEqualPre>(g, g.n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS) &&
+                  be.template run_simple<MaybeEqualPost>(g, g.n, CLS_WITNESS))) return fail(PG_ERR_CUDA, "maybe_equal kernels");
+        }
         *out = new_column((uint32_t)segs.size() - 1, result_local, g.n);
         return PG_OK;
     }
@@ -314,8 +325,10 @@ public:
         if (rc) return rc;
         {
             Segment& s = segs.back();
-            IsNonZeroBody::Args g{src, s.fr, s.n_alloc, n, d_counters};
-            if (n && !be.template run_inv<IsNonZeroBody>(g, n, CLS_WITNESS)) return fail(PG_ERR_CUDA, "is_non_zero kernel");
+            IsNonZeroPre::Args g{src, s.fr, s.n_alloc, n, d_counters};
+            BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
+            inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
+            if (n && !(be.template run_simple<IsNonZeroPre>(g, n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS))) return fail(PG_ERR_CUDA, "is_non_zero kernels");
         }
         unsigned long long c[CNT_WORDS];
         if ((rc = read_counters(c))) return rc;
@@ -488,7 +501,16 @@ public:
         uint4* dout = (uint4*)dalloc(n * sizeof(pg_fr)); if (!dout) return fail(PG_ERR_OOM, "fr_op buffer");
         scratch.push_back(dout);
         bool ok;
-        if (op == 4) { FrInvBody::Args g{da, dout, n}; ok = be.template run_inv<FrInvBody>(g, n, CLS_OTHER); }
+        if (op == 4) {   // invert-or-zero through the batch-inversion kernel: a 2-slot scratch table (slot 0 in, slot 1 out)
+            uint4* tab = (uint4*)dalloc(n * 4 * sizeof(uint4)); if (!tab) return fail(PG_ERR_OOM, "fr_op table");
+            scratch.push_back(tab);
+            AddInputBody::Args in{da, tab, n, n};
+            BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
+            inv.fr = tab; inv.stride = n; inv.n = n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
+            DevTab view; memset(&view, 0, sizeof(view)); view.fr = tab; view.stride = n;
+            ColReadBody::Args rd{view, loc_make(LOC_FR, 0, 1), dout, n};
+            ok = be.template run_simple<AddInputBody>(in, n, CLS_OTHER) && be.run_batch_inv(inv, CLS_OTHER) && be.template run_simple<ColReadBody>(rd, n, CLS_OTHER);
+        }
         else { FrOpBody::Args g{op, da, db, dout, n}; ok = be.template run_simple<FrOpBody>(g, n, CLS_OTHER); }
         if (!ok) return fail(PG_ERR_CUDA, "fr_op kernel");
         return deliver(out, dout, n * sizeof(pg_fr), 0);

@@ -24,66 +24,75 @@ __device__ __forceinline__ Fr shfl_xor_fr(const Fr& a, int mask) {
     return r;
 }
 
-// Montgomery's trick across a whole thread block, zero-aware.
-//   in : v[e] arbitrary field elements (zeros allowed), E per thread, every thread of the block must call
-//   out: v[e] = v[e]^-1, or 0 where v[e] was 0          (== BlsScalar::invert().unwrap_or(zero), scalar.rs:122)
+// Inverse of one NON-ZERO field element per thread, for a whole thread block, with ONE Fermat inversion per block.
 // Products are combined with an xor-butterfly over warp shuffles (each lane keeps the sibling product of every level),
-// warp totals are staged in shared memory and combined by warp 0 with the same butterfly; ONE Fermat inversion is
-// executed per block; inverses are pushed back down the two butterflies with one multiplication per level.
-template <int E>
-__device__ __forceinline__ void block_batch_invert(Fr (&v)[E], Fr* smem /* NWARPS entries */) {
+// warp totals are staged in shared memory and combined by warp 0 with the same butterfly; the inverse of the block product
+// is pushed back down the two butterflies with one multiplication per level.  Every thread of the block must call.
+__device__ __forceinline__ Fr block_invert_nonzero(const Fr& p, Fr* smem /* NWARPS entries */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Fr one = fr_one();
-    bool nz[E]; Fr pre[E];                       // pre[e] = product of the (zero-patched) elements 0..e of this thread
+    Fr g = p, sib[5];
 #pragma unroll
-    for (int e = 0; e < E; e++) {
-        nz[e] = !fr_is_zero(v[e]);
-        if (!nz[e]) v[e] = one;
-        pre[e] = e == 0 ? v[0] : fr_mul(pre[e - 1], v[e]);
-    }
-    // up-sweep inside the warp
-    Fr g = pre[E - 1], sib[5];
-#pragma unroll
-    for (int l = 0; l < 5; l++) { sib[l] = shfl_xor_fr(g, 1 << l); g = fr_mul(g, sib[l]); }
+    for (int l = 0; l < 5; l++) { sib[l] = shfl_xor_fr(g, 1 << l); g = fr_mul(g, sib[l]); }      // up-sweep inside the warp
     if (lane == 0) smem[warp] = g;
     __syncthreads();
     if (warp == 0) {
-        Fr h = lane < NWARPS ? smem[lane] : one, hs[3];
+        Fr h = lane < NWARPS ? smem[lane] : fr_one(), hs[3];
 #pragma unroll
-        for (int l = 0; l < 3; l++) { hs[l] = shfl_xor_fr(h, 1 << l); h = fr_mul(h, hs[l]); }   // NWARPS == 8 -> 3 levels
-        Fr ih = fr_inv_fermat(h);                                                               // the block's only inversion
+        for (int l = 0; l < 3; l++) { hs[l] = shfl_xor_fr(h, 1 << l); h = fr_mul(h, hs[l]); }    // NWARPS == 8 -> 3 levels
+        Fr ih = fr_inv_fermat(h);                                                                // the block's only inversion
 #pragma unroll
-        for (int l = 2; l >= 0; l--) ih = fr_mul(ih, hs[l]);                                    // inverse of smem[lane]
+        for (int l = 2; l >= 0; l--) ih = fr_mul(ih, hs[l]);                                     // inverse of smem[lane]
         if (lane < NWARPS) smem[lane] = ih;
     }
     __syncthreads();
-    Fr ig = smem[warp];                                                                         // inverse of the warp total
+    Fr ig = smem[warp];                                                                          // inverse of the warp total
 #pragma unroll
-    for (int l = 4; l >= 0; l--) ig = fr_mul(ig, sib[l]);                                       // inverse of this thread's product
-#pragma unroll
-    for (int e = E - 1; e >= 1; e--) {
-        const Fr inv_e = fr_mul(ig, pre[e - 1]);
-        ig = fr_mul(ig, v[e]);
-        v[e] = nz[e] ? inv_e : fr_zero();
-    }
-    v[0] = nz[0] ? ig : fr_zero();
+    for (int l = 4; l >= 0; l--) ig = fr_mul(ig, sib[l]);                                        // inverse of this thread's p
+    return ig;
 }
-static_assert(NWARPS == 8, "block_batch_invert's cross-warp butterfly is written for 8 warps");
+static_assert(NWARPS == 8, "block_invert_nonzero's cross-warp butterfly is written for 8 warps");
 
-template <class Body>
-__global__ void __launch_bounds__(BLOCK) k_inv(const typename Body::Args a) {
+// Montgomery's trick over table slots, zero-aware:  out_slot[j][i] = in_slot[j][i]^-1, or 0 where the input is 0
+// (== BlsScalar::invert().unwrap_or(zero), /root/reference/src/scalar.rs:122; is_non_zero flags the zeros separately).
+// The n_pairs x n elements are flattened; a block owns a tile of BLOCK*INV_E consecutive elements and thread t walks the
+// elements tile + e*BLOCK + t (every step is a coalesced 128-bit access).
+//   pass 1: running product of the thread's elements (zeros patched to 1), each prefix parked in the OUTPUT slot;
+//   block : one Fermat inversion for the product of all BLOCK*INV_E elements (block_invert_nonzero);
+//   pass 2: walk back -- inverse_e = inv(prefix_e) * prefix_{e-1}, inv(prefix_{e-1}) = inv(prefix_e) * x_e.
+// 3 multiplications per element, no per-element state in registers, one inversion per 8192 elements.
+constexpr int INV_E = 32;
+__global__ void __launch_bounds__(BLOCK, 2) k_batch_inv(const BatchInvArgs a) {
     __shared__ Fr smem[NWARPS];
-    const uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
-    const bool active = i < a.n;
-    typename Body::State st;
-    Fr v[Body::E];
-    if (active) Body::pre(a, i, st, v);
-    else {
-#pragma unroll
-        for (int e = 0; e < Body::E; e++) v[e] = fr_one();
+    const uint64_t total = (uint64_t)a.n_pairs * a.n;
+    const uint64_t tile = (uint64_t)blockIdx.x * (BLOCK * INV_E);
+    Fr p = fr_one();
+#pragma unroll 1
+    for (int e = 0; e < INV_E; e++) {
+        const uint64_t idx = tile + (uint64_t)e * BLOCK + threadIdx.x;
+        if (idx < total) {
+            const uint32_t j = (uint32_t)(idx / a.n); const uint64_t i = idx - (uint64_t)j * a.n;
+            const Fr x = tab_load_fr(a.fr, a.stride, a.in_slot[j], i);
+            if (!fr_is_zero(x)) p = fr_mul(p, x);
+            tab_store_fr(a.fr, a.stride, a.out_slot[j], i, p);
+        }
     }
-    block_batch_invert<Body::E>(v, smem);
-    if (active) Body::post(a, i, st, v);
+    Fr ig = block_invert_nonzero(p, smem);                           // inverse of the product of this thread's elements
+#pragma unroll 1
+    for (int e = INV_E - 1; e >= 0; e--) {
+        const uint64_t idx = tile + (uint64_t)e * BLOCK + threadIdx.x;
+        if (idx < total) {
+            const uint32_t j = (uint32_t)(idx / a.n); const uint64_t i = idx - (uint64_t)j * a.n;
+            const Fr x = tab_load_fr(a.fr, a.stride, a.in_slot[j], i);
+            Fr prev = fr_one();
+            if (e > 0) {                                             // prefix of the previous element of this thread
+                const uint64_t pidx = idx - BLOCK;
+                const uint32_t pj = (uint32_t)(pidx / a.n); const uint64_t pi = pidx - (uint64_t)pj * a.n;
+                prev = tab_load_fr(a.fr, a.stride, a.out_slot[pj], pi);
+            }
+            if (fr_is_zero(x)) tab_store_fr(a.fr, a.stride, a.out_slot[j], i, fr_zero());
+            else { tab_store_fr(a.fr, a.stride, a.out_slot[j], i, fr_mul(ig, prev)); ig = fr_mul(ig, x); }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- gate check
@@ -135,40 +144,82 @@ __global__ void __launch_bounds__(BLOCK) k_check_rows(const CheckRowsBody::Args 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------- IMAD roofline
-// 8 independent accumulator chains per thread so that the multiplier pipe, not the 4-cycle dependent-issue latency, is
-// the limit.  `iters` x 8 multiply-accumulates per thread.
-__global__ void __launch_bounds__(BLOCK) k_imad_wide(uint64_t* out, uint32_t x, uint32_t y, int iters) {
-    uint64_t acc[8];
+// ---------------------------------------------------------------------------------------------------- pipe micro-benchmarks
+// Roofline denominators and instruction-cost evidence, measured on the device the engine runs on.  Every chain feeds its
+// own previous result back into a multiplier/adder INPUT, so ptxas can neither hoist, share nor re-associate the
+// operations; 8 independent chains per thread and 8 blocks per SM hide the dependent-issue latency.
+//   0 IMAD (32-bit lo, accumulate)         acc = acc*b + c
+//   1 IMAD.WIDE.U32, no addend              p   = hi(p)*b            (64-bit product only)
+//   2 IMAD.WIDE.U32, 64-bit accumulate      acc = lo(acc)*b + acc
+//   3 IMAD.HI.U32, accumulate               acc = hi(acc*b) + c
+//   4 mad.lo.cc/madc.hi.cc rows             the carry-chain rows of fr_mul (IMAD.WIDE.U32.X): 4 products per row
+//   5 IADD3 (3-input add)                   acc = acc + b + c
+//   6 Fr Montgomery multiplication          acc = fr_mul(acc, b)     (even/odd carry-chain multiplier)
+//   7 Fr Montgomery multiplication          acc = fr_mul_cios(acc, b) (portable 64-bit C)
+//   8 Fr addition                           acc = fr_add(acc, b)
+enum { UB_IMAD_LO = 0, UB_WIDE_MUL = 1, UB_WIDE_ACC = 2, UB_IMAD_HI = 3, UB_CARRY_ROWS = 4, UB_IADD3 = 5, UB_FR_MUL = 6, UB_FR_MUL_CIOS = 7, UB_FR_ADD = 8, UB_MODES = 9 };
+
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK) k_ubench(uint32_t* out, uint32_t x, uint32_t y, int iters) {
+    const uint32_t tid = blockIdx.x * BLOCK + threadIdx.x;
+    uint32_t b = y | 1u, c = x ^ 0x5bd1e995u;
+    uint32_t sink = 0;
+    if (MODE == UB_IMAD_LO || MODE == UB_IMAD_HI || MODE == UB_IADD3) {
+        uint32_t acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = (uint64_t)threadIdx.x * (k + 1) + blockIdx.x;
-    uint32_t a = x + threadIdx.x, b = y | 1u;
-    for (int it = 0; it < iters; it++) {
+        for (int k = 0; k < 8; k++) acc[k] = tid * (2 * k + 3) + x;
+        for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
-        a += 0x9e3779b9u;
+            for (int k = 0; k < 8; k++) {
+                if (MODE == UB_IMAD_LO) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"(c));
+                if (MODE == UB_IMAD_HI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"(c));
+                if (MODE == UB_IADD3) asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(acc[k]) : "r"(b), "r"(c));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) sink ^= acc[k];
+    } else if (MODE == UB_WIDE_MUL || MODE == UB_WIDE_ACC) {
+        uint64_t acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = ((uint64_t)(tid * (2 * k + 3) + x) << 32) | (tid + k);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (MODE == UB_WIDE_MUL) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mul.wide.u32 %0, hi, %1; }" : "+l"(acc[k]) : "r"(b));
+                if (MODE == UB_WIDE_ACC) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[k]) : "r"(b));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) sink ^= (uint32_t)acc[k] ^ (uint32_t)(acc[k] >> 32);
+    } else if (MODE == UB_CARRY_ROWS) {
+        uint32_t acc[2][8], top[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; k++) { acc[0][k] = tid * (2 * k + 3) + x; acc[1][k] = tid * (2 * k + 5) + y; }
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) mad_row(acc[r], top[r], b, c, x, y, acc[r][1]);   // multiplier input depends on the chain
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) sink ^= acc[0][k] ^ acc[1][k];
+        sink ^= top[0] ^ top[1];
+    } else {
+        Fr acc[2], m;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { acc[0].v[k] = (tid * (2 * k + 3) + x) & 0x3fffffffu; acc[1].v[k] = (tid * (2 * k + 5) + y) & 0x3fffffffu; m.v[k] = (b * (k + 7)) & 0x3fffffffu; }
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (MODE == UB_FR_MUL) acc[r] = fr_mul(acc[r], m);
+                if (MODE == UB_FR_MUL_CIOS) acc[r] = fr_mul_cios(acc[r], m);
+                if (MODE == UB_FR_ADD) acc[r] = fr_add(acc[r], m);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) sink ^= acc[0].v[k] ^ acc[1].v[k];
     }
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
-    out[(uint64_t)blockIdx.x * BLOCK + threadIdx.x] = s;
+    out[tid] = sink;
 }
-__global__ void __launch_bounds__(BLOCK) k_imad_lo(uint32_t* out, uint32_t x, uint32_t y, int iters) {
-    uint32_t acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = threadIdx.x * (k + 1) + blockIdx.x;
-    uint32_t a = x + threadIdx.x, b = y | 1u;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a), "r"(b));
-        a += 0x9e3779b9u;
-    }
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
-    out[(uint64_t)blockIdx.x * BLOCK + threadIdx.x] = s;
-}
+// operations per thread per loop iteration in each mode
+__host__ __device__ constexpr int ubench_ops_per_iter(int mode) { return mode <= UB_IMAD_HI || mode == UB_IADD3 ? 8 : (mode == UB_CARRY_ROWS ? 8 : 2); }
 
 }  // namespace pg

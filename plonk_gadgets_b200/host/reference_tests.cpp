@@ -1,0 +1,148 @@
+// reference_tests.cpp -- the reference crate's integration tests, replayed through the C++ mirror on the GPU.
+//
+// Mirrors /root/reference/tests/range_gadgets_tests.rs (max_bound_test :46-107, range_check_test :108-201) and
+// /root/reference/tests/scalar_gadgets_tests.rs (test_maybe_equal :13-68, test_conditionally_select_0 :70-122,
+// test_conditionally_select_1 :124-178, test_is_not_zero :180-236).  The reference decides each case with a
+// prove -> verify round trip (out of scope here); the verdict of this engine is "every row
+// satisfies the gate equation", which is equivalent for these circuits (copy constraints hold by construction).
+// All cases of one test are batched into ONE gadget call (one instance per case).  Exit code 0 = all verdicts as expected.
+#include <cstdio>
+#include <vector>
+#include "plonk_gadgets.hpp"
+
+using namespace plonk_gadgets;
+using RangeGadgets::max_bound;
+using RangeGadgets::range_check;
+using namespace ScalarGadgets;
+
+static int failures = 0;
+#define EXPECT(cond, msg) do { if (!(cond)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, msg); failures++; } } while (0)
+
+static BlsScalar two_pow(uint64_t e) { return BlsScalar::pow_of_2(e); }     // BlsScalar::from(2).pow(&[e,0,0,0])
+
+// constrain every instance's output to the claimed boolean and return the verdict (tests/range_gadgets_tests.rs:22-26)
+static bool satisfied_with_claims(StandardComposer& c, Variables res, const std::vector<bool>& claims) {
+    std::vector<BlsScalar> outcome;
+    for (bool b : claims) outcome.push_back(b ? BlsScalar::one() : BlsScalar::zero());
+    c.constrain_to_constant(res, outcome);
+    return c.check_circuit_satisfied().first == 0;
+}
+
+static void max_bound_test() {
+    struct TestCase { BlsScalar max_range, witness; bool expected_result; };
+    std::vector<TestCase> cases = {
+        {two_pow(128) - BlsScalar::one(), two_pow(127), true},
+        {BlsScalar::from(200), BlsScalar::from(100), true},
+        {BlsScalar::from(100), BlsScalar::from(200), false},
+        {two_pow(128) - BlsScalar::one(), two_pow(130), false},
+    };
+    // bounds of different bit widths cannot share one batched call: one call per case (n = 1), as in the reference's loop
+    for (auto& tc : cases) {
+        for (bool flip : {false, true}) {
+            StandardComposer composer;
+            auto witness = AllocatedScalar::allocate(composer, {tc.witness});
+            auto res = max_bound(composer, {tc.max_range}, witness).first;
+            bool ok = satisfied_with_claims(composer, res, {tc.expected_result != flip});
+            EXPECT(ok == !flip, "max_bound verdict");
+        }
+    }
+}
+
+static void range_check_test() {
+    struct TestCase { BlsScalar min_range, max_range, witness; bool expected_result; };
+    std::vector<TestCase> cases = {
+        {BlsScalar::from(50000), BlsScalar::from(250000), BlsScalar::from(50001), true},
+        {BlsScalar::from(50000), BlsScalar::from(250000), BlsScalar::from(250001), false},
+        {BlsScalar::from(50000), BlsScalar::from(250000), BlsScalar::from(250000), false},
+        {BlsScalar::from(50000), BlsScalar::from(250000), BlsScalar::from(249000), true},
+        {BlsScalar::from(50000), BlsScalar::from(250000), BlsScalar::from(50000), true},
+        {BlsScalar::from(50000), BlsScalar::from(250000), BlsScalar::from(49999), false},
+        {BlsScalar::from(50000), BlsScalar::from(250000), BlsScalar::from(18598), false},
+    };
+    // the seven cases with the same public bounds run as ONE batched call
+    StandardComposer composer;
+    std::vector<BlsScalar> w; std::vector<bool> claims;
+    for (auto& tc : cases) { w.push_back(tc.witness); claims.push_back(tc.expected_result); }
+    auto witness = AllocatedScalar::allocate(composer, w);
+    auto res = range_check(composer, {cases[0].min_range}, {cases[0].max_range}, witness);
+    EXPECT(composer.circuit_size() == 3 + 7 * (4 * 19 + 11), "row count 4k+11, k=19");
+    EXPECT(satisfied_with_claims(composer, res, claims), "range_check verdicts");
+    // and the negated claims are all rejected: 7 unsatisfied rows
+    StandardComposer c2;
+    auto w2 = AllocatedScalar::allocate(c2, w);
+    auto r2 = range_check(c2, {cases[0].min_range}, {cases[0].max_range}, w2);
+    std::vector<BlsScalar> neg;
+    for (bool b : claims) neg.push_back(b ? BlsScalar::zero() : BlsScalar::one());
+    c2.constrain_to_constant(r2, neg);
+    EXPECT(c2.check_circuit_satisfied().first == 7, "negated claims rejected");
+    // the 127-bit case (tests/range_gadgets_tests.rs:158-163)
+    StandardComposer c3;
+    auto w3 = AllocatedScalar::allocate(c3, {two_pow(127) - BlsScalar::one()});
+    auto r3 = range_check(c3, {two_pow(126)}, {two_pow(127) + BlsScalar::one()}, w3);
+    EXPECT(satisfied_with_claims(c3, r3, {true}), "127-bit range");
+}
+
+static void test_maybe_equal() {
+    StandardComposer composer;
+    auto a = AllocatedScalar::allocate(composer, {BlsScalar::from(100), BlsScalar::from(20)});
+    auto b = AllocatedScalar::allocate(composer, {BlsScalar::from(100), BlsScalar::from(3330)});
+    auto bit = maybe_equal(composer, a, b);
+    EXPECT(satisfied_with_claims(composer, bit, {true, false}), "maybe_equal");
+}
+
+static void test_conditionally_select_0() {
+    StandardComposer composer;
+    BlsScalar rnd = BlsScalar::from(0x1234567890abcdefULL) * BlsScalar::from(0xfedcba9876543211ULL);
+    auto value = composer.add_input({rnd, rnd});
+    auto selector = composer.add_input({BlsScalar::zero(), BlsScalar::one()});
+    auto res = conditionally_select_zero(composer, value, selector);
+    composer.constrain_to_constant(res, {BlsScalar::zero()});
+    auto v = composer.check_circuit_satisfied();
+    // selector 0 -> 0 (ok); selector 1 with a random value -> the claim "0" is rejected (scalar_gadgets_tests.rs:106,:119)
+    EXPECT(v.first == 1, "select_zero: exactly the selector=1 instance violates res == 0");
+}
+
+static void test_conditionally_select_1() {
+    StandardComposer composer;
+    BlsScalar rnd = BlsScalar::from(0x0123456789abcdefULL) * BlsScalar::from(0x1111111111111111ULL);
+    auto value = composer.add_input({rnd, rnd});
+    auto selector = composer.add_input({BlsScalar::zero(), BlsScalar::one()});
+    auto res = conditionally_select_one(composer, value, selector);
+    // constrain_to_constant(res, 0, Some(-expected)): selector 0 -> 1, selector 1 -> value
+    composer.constrain_to_constant(res, {BlsScalar::zero()}, {-BlsScalar::one(), -rnd});
+    EXPECT(composer.check_circuit_satisfied().first == 0, "select_one");
+}
+
+static void test_is_not_zero() {
+    BlsScalar r1 = BlsScalar::from(77) * BlsScalar::from(0xabcdef0123456789ULL), r2 = BlsScalar::from(78) * BlsScalar::from(0xabcdef0123456789ULL);
+    {   // zero -> Err(NonExistingInverse)
+        StandardComposer composer;
+        auto value = composer.add_input({BlsScalar::zero()});
+        Error e; EXPECT(!is_non_zero(composer, value, {BlsScalar::zero()}, &e) && e == Error::NonExistingInverse, "is_non_zero(0) errs");
+        EXPECT(composer.circuit_size() == 3 + 1 && composer.num_variables() == 5 + 1 + 1, "partial append: 1 var + 1 row");
+    }
+    {   // different value / value_assigned -> Ok, but unsatisfied
+        StandardComposer composer;
+        auto value = composer.add_input({r1});
+        EXPECT(is_non_zero(composer, value, {r2}), "is_non_zero mismatch returns Ok");
+        EXPECT(composer.check_circuit_satisfied().first != 0, "is_non_zero mismatch rejected");
+    }
+    {   // equal and non-zero -> satisfied
+        StandardComposer composer;
+        auto value = composer.add_input({r1});
+        EXPECT(is_non_zero(composer, value, {r1}), "is_non_zero ok");
+        EXPECT(composer.check_circuit_satisfied().first == 0, "is_non_zero satisfied");
+    }
+}
+
+int main() {
+    try {
+        max_bound_test(); range_check_test(); test_maybe_equal();
+        test_conditionally_select_0(); test_conditionally_select_1(); test_is_not_zero();
+    } catch (const EngineError& e) {
+        std::printf("EngineError %d: %s\n", e.code, e.what());
+        return 2;
+    }
+    std::printf(failures ? "reference tests: %d FAILED\n" : "reference tests: all passed\n", failures);
+    return failures ? 1 : 0;
+}

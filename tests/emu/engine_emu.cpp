@@ -36,21 +36,19 @@ public:
     bool upload_pow2(const Fr*) { return true; }
     bool timing(pg_timing* out, bool) { memset(out, 0, sizeof(*out)); return true; }
     bool imad_peak(double*, double*) { return false; }
+    bool ubench(int, double*) { return false; }
 
     template <class Body>
     bool run_simple(const typename Body::Args& a, uint64_t n, int) {
         for (uint64_t i = 0; i < n; i++) Body::run(a, i);
         return true;
     }
-    template <class Body>
-    bool run_inv(const typename Body::Args& a, uint64_t n, int) {
-        for (uint64_t i = 0; i < n; i++) {
-            typename Body::State st;
-            Fr v[Body::E];
-            Body::pre(a, i, st, v);
-            for (int e = 0; e < Body::E; e++) v[e] = fr_is_zero(v[e]) ? fr_zero() : fr_inv_fermat(v[e]);
-            Body::post(a, i, st, v);
-        }
+    bool run_batch_inv(const BatchInvArgs& a, int) {   // one Fermat inversion per element (the block-wide trick is GPU-only)
+        for (uint32_t j = 0; j < a.n_pairs; j++)
+            for (uint64_t i = 0; i < a.n; i++) {
+                const Fr x = tab_load_fr(a.fr, a.stride, a.in_slot[j], i);
+                tab_store_fr(a.fr, a.stride, a.out_slot[j], i, fr_is_zero(x) ? fr_zero() : fr_inv_fermat(x));
+            }
         return true;
     }
     bool run_check(const CheckArgs& a) {
