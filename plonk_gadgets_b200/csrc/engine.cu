@@ -47,7 +47,8 @@ public:
         if (cfg.stream) { stream = (cudaStream_t)cfg.stream; own_stream = false; }
         else { PG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
-        PG_CUDA(cudaFuncSetAttribute(k_check, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         return true;
     }
     void shutdown() {
@@ -131,7 +132,8 @@ public:
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         tic(CLS_CHECK, a.n_inst * a.n_rows);
-        k_check<<<grid_for(a.n_inst), BLOCK, smem, stream>>>(a);
+        if (a.mode == PG_CHECK_SPARSE) k_check<1><<<grid_for(a.n_inst), BLOCK, smem, stream>>>(a);
+        else k_check<0><<<grid_for(a.n_inst), BLOCK, smem, stream>>>(a);
         toc();
         return launched("k_check");
     }
@@ -146,7 +148,7 @@ public:
     // operations per second of one micro-benchmark mode (best of 3 after a warm-up launch)
     bool ubench(int mode, double* ops_per_s) {
         if (mode < 0 || mode >= UB_MODES) { snprintf(errbuf, sizeof(errbuf), "unknown micro-benchmark mode %d", mode); return false; }
-        const int blocks = sm_count * 8, iters = mode >= UB_FR_MUL ? 512 : 4096;
+        const int blocks = sm_count * 8, iters = (mode >= UB_FR_MUL && mode <= UB_FR_ADD) ? 512 : 4096;
         uint32_t* buf = nullptr;
         PG_CUDA(cudaMalloc(&buf, (size_t)blocks * BLOCK * sizeof(uint32_t)));
         cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -158,7 +160,8 @@ public:
                 case 2: ubench_launch<2>(buf, blocks, iters, rep); break; case 3: ubench_launch<3>(buf, blocks, iters, rep); break;
                 case 4: ubench_launch<4>(buf, blocks, iters, rep); break; case 5: ubench_launch<5>(buf, blocks, iters, rep); break;
                 case 6: ubench_launch<6>(buf, blocks, iters, rep); break; case 7: ubench_launch<7>(buf, blocks, iters, rep); break;
-                default: ubench_launch<8>(buf, blocks, iters, rep); break;
+                case 8: ubench_launch<8>(buf, blocks, iters, rep); break;
+                default: ubench_launch<9>(buf, blocks, iters, rep); break;
             }
             cudaEventRecord(b, stream);
             cudaEventSynchronize(b);

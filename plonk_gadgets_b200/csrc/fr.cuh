@@ -50,6 +50,19 @@ struct Fr { uint32_t v[8]; };
 #define PG_Q6 0x299d7d48u
 #define PG_Q7 0x73eda753u
 
+// The same limbs behind a __constant__ array: as immediates ptxas splits every reduction product into IMAD.HI + IMAD
+// (6 multiplier-pipe cycles); as constant-bank operands they stay one IMAD.WIDE.U32.X (4 cycles).
+#if defined(__CUDACC__)
+__constant__ uint32_t c_q[8] = {PG_Q0, PG_Q1, PG_Q2, PG_Q3, PG_Q4, PG_Q5, PG_Q6, PG_Q7};
+#endif
+PG_HD uint32_t fr_qc(int i) {
+#if defined(__CUDA_ARCH__)
+    return c_q[i];
+#else
+    const uint32_t q[8] = {PG_Q0, PG_Q1, PG_Q2, PG_Q3, PG_Q4, PG_Q5, PG_Q6, PG_Q7};
+    return q[i];
+#endif
+}
 PG_HD uint32_t fr_q(int i) {
     switch (i) { case 0: return PG_Q0; case 1: return PG_Q1; case 2: return PG_Q2; case 3: return PG_Q3;
                  case 4: return PG_Q4; case 5: return PG_Q5; case 6: return PG_Q6; default: return PG_Q7; }
@@ -260,15 +273,15 @@ PG_HD void mont_step_first(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t
     mul_row(Y, a[1], a[3], a[5], a[7], bi);
     mul_row(X, a[0], a[2], a[4], a[6], bi);
     uint32_t m = 0u - X[0];
-    mad_row_nc(Y, PG_Q1, PG_Q3, PG_Q5, PG_Q7, m);            // top limb of q is < 2^31: no carry out of Y[7]
-    mad_row(X, Y[7], PG_Q0, PG_Q2, PG_Q4, PG_Q6, m);
+    mad_row_nc(Y, fr_qc(1), fr_qc(3), fr_qc(5), fr_qc(7), m);   // top limb of q is < 2^31: no carry out of Y[7]
+    mad_row(X, Y[7], fr_qc(0), fr_qc(2), fr_qc(4), fr_qc(6), m);
 }
 PG_HD void mont_step(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
     mad_row_shift(Y, X[0], a[1], a[3], a[5], a[7], bi);       // X[0] += Y[1]; Y = (Y >> 64) + a_odd*bi
     mad_row(X, Y[7], a[0], a[2], a[4], a[6], bi);
     uint32_t m = 0u - X[0];
-    mad_row_nc(Y, PG_Q1, PG_Q3, PG_Q5, PG_Q7, m);
-    mad_row(X, Y[7], PG_Q0, PG_Q2, PG_Q4, PG_Q6, m);
+    mad_row_nc(Y, fr_qc(1), fr_qc(3), fr_qc(5), fr_qc(7), m);
+    mad_row(X, Y[7], fr_qc(0), fr_qc(2), fr_qc(4), fr_qc(6), m);
 }
 
 PG_HD Fr fr_mul_eo(const Fr& a, const Fr& b) {
@@ -284,6 +297,169 @@ PG_HD Fr fr_mul_eo(const Fr& a, const Fr& b) {
     Fr r;
     merge_even_odd(r.v, even, odd);                           // (even + odd>>32), odd[0] == 0
     return fr_reduce_once(r);
+}
+
+// ---- dot-product Montgomery: sum_p a_p*b_p with ONE interleaved reduction ----------------------------------------------
+// The gate equation needs q_m*(ab) + q_l*a + q_r*b + q_o*c + q_4*d only up to "is it 0 mod q", so the five double-width
+// products are accumulated into one running value that is reduced once per limb step (operand scanning over the b_p limbs):
+//     for i in 0..8:  T += sum_p a_p * b_p[i];  m = -T[0];  T += m*q;  T >>= 32
+// 5*64 + 8*6 multiplier instructions instead of 5*(64+64).  T is held as an even array X (limbs 0..7), an odd array Y
+// (limbs 1..8) and a top word Z (limb 9): with K products T stays below (K+1)*q*(2^32+1) < 2^320, every carry out of limb 7
+// or 8 is caught (X -> Y[7] -> Z, Y -> Z).  The reduction rows use the shape of q: q0 = 1 (m*q0 = m) and q1 = 2^32-1
+// (m*q1 = m*2^32 - m) need no multiplier.  Result: 9 limbs r < (K+1)*q + small, congruent to sum_p a_p*b_p / 2^256 mod q.
+#if defined(__CUDA_ARCH__)
+// X[0..7] += (x0,x2,x4,x6)*y ; carry -> y7 -> z
+PG_D void dmad_row_x(uint32_t* X, uint32_t& y7, uint32_t& z, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %10, %14, %0;\n\tmadc.hi.cc.u32 %1, %10, %14, %1;\n\tmadc.lo.cc.u32 %2, %11, %14, %2;\n\tmadc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\tmadc.hi.cc.u32 %5, %12, %14, %5;\n\tmadc.lo.cc.u32 %6, %13, %14, %6;\n\tmadc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "addc.cc.u32 %8, %8, 0;\n\taddc.u32 %9, %9, 0;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(y7), "+r"(z)
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+}
+// Y[0..7] += (x1,x3,x5,x7)*y ; carry -> z
+PG_D void dmad_row_y(uint32_t* Y, uint32_t& z, uint32_t x1, uint32_t x3, uint32_t x5, uint32_t x7, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\tmadc.hi.cc.u32 %1, %9, %13, %1;\n\tmadc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\tmadc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(z)
+        : "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+}
+// division by 2^32 fused with the first odd row of the next step:
+//   e0 += o[1];  o <- (o >> 2 limbs | z at the top) + (x1,x3,x5,x7)*y ;  z <- carry
+PG_D void dmad_row_shift(uint32_t* o, uint32_t& e0, uint32_t& z, uint32_t x1, uint32_t x3, uint32_t x5, uint32_t x7, uint32_t y) {
+    asm("add.cc.u32 %8, %8, %1;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %2;\n\tmadc.hi.cc.u32 %1, %10, %14, %3;\n\tmadc.lo.cc.u32 %2, %11, %14, %4;\n\tmadc.hi.cc.u32 %3, %11, %14, %5;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %6;\n\tmadc.hi.cc.u32 %5, %12, %14, %7;\n\tmadc.lo.cc.u32 %6, %13, %14, 0;\n\tmadc.hi.cc.u32 %7, %13, %14, %9;\n\t"
+        "addc.u32 %9, 0, 0;"
+        : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(e0), "+r"(z)
+        : "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+}
+// reduction rows for m = -X[0]:  Y += m*(q1,q3,q5,q7) with m*q1 = (m<<32) - m done by the adder;  X += m*(q0,q2,q4,q6) with m*q0 = m
+PG_D void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z) {
+    const uint32_t m = 0u - X[0];
+    uint32_t lo, hi;
+    asm("sub.cc.u32 %0, 0, %2;\n\tsubc.u32 %1, %2, 0;" : "=&r"(lo), "=&r"(hi) : "r"(m));            // m*(2^32-1) = hi:lo
+    asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, %10;\n\tmadc.lo.cc.u32 %2, %11, %14, %2;\n\tmadc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\tmadc.hi.cc.u32 %5, %12, %14, %5;\n\tmadc.lo.cc.u32 %6, %13, %14, %6;\n\tmadc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(z)
+        : "r"(lo), "r"(hi), "r"(fr_qc(3)), "r"(fr_qc(5)), "r"(fr_qc(7)), "r"(m));
+    asm("add.cc.u32 %0, %0, %13;\n\taddc.cc.u32 %1, %1, 0;\n\tmadc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\tmadc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.cc.u32 %8, %8, 0;\n\taddc.u32 %9, %9, 0;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(Y[7]), "+r"(z)
+        : "r"(fr_qc(2)), "r"(fr_qc(4)), "r"(fr_qc(6)), "r"(m));
+}
+// r[0..8] = (X >> 32) + Y + (z << 256)
+PG_D void dmerge(uint32_t* r, const uint32_t* X, const uint32_t* Y, uint32_t z) {
+    asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, 0;\n\taddc.u32 %8, %24, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8])
+        : "r"(Y[0]), "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]),
+          "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]), "r"(z));
+}
+// r[0..8] += a[0..7]   (no carry out of limb 8 by the bound on r)
+PG_D void add9_fr(uint32_t* r, const Fr& a) {
+    asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, %10;\n\taddc.cc.u32 %2, %2, %11;\n\taddc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\taddc.cc.u32 %5, %5, %14;\n\taddc.cc.u32 %6, %6, %15;\n\taddc.cc.u32 %7, %7, %16;\n\taddc.u32 %8, %8, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+}
+#else
+inline void dmad_row_x(uint32_t* X, uint32_t& y7, uint32_t& z, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y) {
+    const uint32_t x[4] = {x0, x2, x4, x6};
+    const uint32_t c = emu_mad_chain(X, x, y, 0);
+    const uint64_t s = (uint64_t)y7 + c; y7 = (uint32_t)s;
+    if (z + (uint32_t)(s >> 32) < z) PG_EMU_VIOLATION();
+    z += (uint32_t)(s >> 32);
+}
+inline void dmad_row_y(uint32_t* Y, uint32_t& z, uint32_t x1, uint32_t x3, uint32_t x5, uint32_t x7, uint32_t y) {
+    const uint32_t x[4] = {x1, x3, x5, x7};
+    const uint32_t c = emu_mad_chain(Y, x, y, 0);
+    if (z + c < z) PG_EMU_VIOLATION();
+    z += c;
+}
+inline void dmad_row_shift(uint32_t* o, uint32_t& e0, uint32_t& z, uint32_t x1, uint32_t x3, uint32_t x5, uint32_t x7, uint32_t y) {
+    const uint32_t x[4] = {x1, x3, x5, x7};
+    if (o[0] != 0) PG_EMU_VIOLATION();                                  // the reduction must have cleared the lowest limb
+    const uint64_t s = (uint64_t)e0 + o[1]; e0 = (uint32_t)s;
+    uint32_t sh[8] = {o[2], o[3], o[4], o[5], o[6], o[7], 0, z};
+    z = emu_mad_chain(sh, x, y, (uint32_t)(s >> 32));
+    for (int i = 0; i < 8; i++) o[i] = sh[i];
+}
+inline void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z) {
+    const uint32_t m = 0u - X[0];
+    const uint32_t qo[4] = {PG_Q1, PG_Q3, PG_Q5, PG_Q7}, qe[4] = {PG_Q0, PG_Q2, PG_Q4, PG_Q6};
+    uint32_t c = emu_mad_chain(Y, qo, m, 0);
+    if (z + c < z) PG_EMU_VIOLATION();
+    z += c;
+    c = emu_mad_chain(X, qe, m, 0);
+    const uint64_t s = (uint64_t)Y[7] + c; Y[7] = (uint32_t)s;
+    if (z + (uint32_t)(s >> 32) < z) PG_EMU_VIOLATION();
+    z += (uint32_t)(s >> 32);
+}
+inline void dmerge(uint32_t* r, const uint32_t* X, const uint32_t* Y, uint32_t z) {
+    uint64_t c = 0;
+    for (int i = 0; i < 7; i++) { const uint64_t s = (uint64_t)Y[i] + X[i + 1] + c; r[i] = (uint32_t)s; c = s >> 32; }
+    const uint64_t s = (uint64_t)Y[7] + c; r[7] = (uint32_t)s;
+    if ((uint64_t)z + (s >> 32) > 0xffffffffull) PG_EMU_VIOLATION();
+    r[8] = z + (uint32_t)(s >> 32);
+}
+inline void add9_fr(uint32_t* r, const Fr& a) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { const uint64_t s = (uint64_t)r[i] + a.v[i] + c; r[i] = (uint32_t)s; c = s >> 32; }
+    if ((uint64_t)r[8] + c > 0xffffffffull) PG_EMU_VIOLATION();
+    r[8] += (uint32_t)c;
+}
+#endif
+
+// One limb step of the dot product for products p = 0..K-1: multiplicands a[p] (8 limbs), scanned limbs bi[p].
+// (X | Y | z) as in mont_step; FIRST = the very first step (nothing to shift in).
+template <int K, bool FIRST>
+PG_HD void dot_step(uint32_t* X, uint32_t* Y, uint32_t& z, const Fr* a, const uint32_t* bi) {
+    if (FIRST) {
+        mul_row(Y, a[0].v[1], a[0].v[3], a[0].v[5], a[0].v[7], bi[0]);
+        mul_row(X, a[0].v[0], a[0].v[2], a[0].v[4], a[0].v[6], bi[0]);
+        z = 0;
+    } else {
+        dmad_row_shift(Y, X[0], z, a[0].v[1], a[0].v[3], a[0].v[5], a[0].v[7], bi[0]);   // X[0] += Y[1]; Y = (Y >> 64 | z) + a_odd*bi
+        dmad_row_x(X, Y[7], z, a[0].v[0], a[0].v[2], a[0].v[4], a[0].v[6], bi[0]);
+    }
+#pragma unroll
+    for (int p = 1; p < K; p++) {
+        dmad_row_y(Y, z, a[p].v[1], a[p].v[3], a[p].v[5], a[p].v[7], bi[p]);
+        dmad_row_x(X, Y[7], z, a[p].v[0], a[p].v[2], a[p].v[4], a[p].v[6], bi[p]);
+    }
+    dred_rows(X, Y, z);
+}
+// r[0..8] = (sum_p a[p]*b[p]) / 2^256 mod q up to a multiple of q, r < (K+1)*q + 2^224.  a[p], b[p] < 2q.
+template <int K>
+PG_HD void fr_dot_wide(uint32_t* r, const Fr* a, const Fr* b) {
+    uint32_t even[8], odd[8], z, bi[K];
+#define PG_DOT_STEP(I, XX, YY, FIRST)                          \
+    _Pragma("unroll") for (int p = 0; p < K; p++) bi[p] = b[p].v[I]; \
+    dot_step<K, FIRST>(XX, YY, z, a, bi);
+    PG_DOT_STEP(0, even, odd, true)
+    PG_DOT_STEP(1, odd, even, false)
+    PG_DOT_STEP(2, even, odd, false)
+    PG_DOT_STEP(3, odd, even, false)
+    PG_DOT_STEP(4, even, odd, false)
+    PG_DOT_STEP(5, odd, even, false)
+    PG_DOT_STEP(6, even, odd, false)
+    PG_DOT_STEP(7, odd, even, false)
+#undef PG_DOT_STEP
+    dmerge(r, odd, even, z);          // the last step cleared odd[0]: value = (odd >> 32) + even + (z << 256)
+}
+// k*q for k = 0..15 (9 limbs each): since q0 = 1, k*q = k (mod 2^32), so a 9-limb r is 0 mod q iff r == k*q for k = r[0] (r < 16q)
+PG_HD bool limbs9_is_multiple_of_q(const uint32_t* r) {
+    const uint32_t k = r[0];
+    if (k > 15u) return false;
+    const uint32_t q[8] = {PG_Q0, PG_Q1, PG_Q2, PG_Q3, PG_Q4, PG_Q5, PG_Q6, PG_Q7};
+    uint32_t diff = 0; uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const uint64_t t = (uint64_t)q[i] * k + c; diff |= (uint32_t)t ^ r[i]; c = t >> 32; }
+    diff |= (uint32_t)c ^ r[8];
+    return diff == 0;
 }
 
 #if defined(__CUDA_ARCH__)

@@ -107,6 +107,7 @@ struct SmemPool {
 
 // One instance per thread; the row template is walked by all threads in lock step (selector pool in shared memory,
 // template rows read with warp-uniform addresses), wire values come from the SoA variable table with coalesced loads.
+template <int MODE>
 __global__ void __launch_bounds__(BLOCK, 2) k_check(const CheckArgs a) {
     extern __shared__ __align__(16) uint32_t s_pool[];
     for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += BLOCK) s_pool[t] = a.pool[t];
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_check(const CheckArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
-    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run(a, pool, i, first_bad); }
+    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, i, first_bad); }
     // warp-level reduction, then one atomic per warp that saw a violation
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(BLOCK) k_check_rows(const CheckRowsBody::Args 
 //   6 Fr Montgomery multiplication          acc = fr_mul(acc, b)     (even/odd carry-chain multiplier)
 //   7 Fr Montgomery multiplication          acc = fr_mul_cios(acc, b) (portable 64-bit C)
 //   8 Fr addition                           acc = fr_add(acc, b)
-enum { UB_IMAD_LO = 0, UB_WIDE_MUL = 1, UB_WIDE_ACC = 2, UB_IMAD_HI = 3, UB_CARRY_ROWS = 4, UB_IADD3 = 5, UB_FR_MUL = 6, UB_FR_MUL_CIOS = 7, UB_FR_ADD = 8, UB_MODES = 9 };
+//   9 DFMA (fp64 fused multiply-add)        acc = acc*b + c          (the other wide multiplier on the SM, for reference)
+enum { UB_IMAD_LO = 0, UB_WIDE_MUL = 1, UB_WIDE_ACC = 2, UB_IMAD_HI = 3, UB_CARRY_ROWS = 4, UB_IADD3 = 5, UB_FR_MUL = 6, UB_FR_MUL_CIOS = 7, UB_FR_ADD = 8, UB_DFMA = 9, UB_MODES = 10 };
 
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK) k_ubench(uint32_t* out, uint32_t x, uint32_t y, int iters) {
@@ -191,6 +193,16 @@ __global__ void __launch_bounds__(BLOCK) k_ubench(uint32_t* out, uint32_t x, uin
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) sink ^= (uint32_t)acc[k] ^ (uint32_t)(acc[k] >> 32);
+    } else if (MODE == UB_DFMA) {
+        double acc[8]; const double fb = 1.0 + (double)(b & 0xffu) * 1e-9, fc = (double)(c & 0xffu) * 1e-3;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = (double)(tid + k);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[k]) : "d"(fb), "d"(fc));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) sink ^= (uint32_t)__double2ll_rn(acc[k]);
     } else if (MODE == UB_CARRY_ROWS) {
         uint32_t acc[2][8], top[2] = {0, 0};
 #pragma unroll
@@ -220,6 +232,6 @@ __global__ void __launch_bounds__(BLOCK) k_ubench(uint32_t* out, uint32_t x, uin
     out[tid] = sink;
 }
 // operations per thread per loop iteration in each mode
-__host__ __device__ constexpr int ubench_ops_per_iter(int mode) { return mode <= UB_IMAD_HI || mode == UB_IADD3 ? 8 : (mode == UB_CARRY_ROWS ? 8 : 2); }
+__host__ __device__ constexpr int ubench_ops_per_iter(int mode) { return mode <= UB_IMAD_HI || mode == UB_IADD3 || mode == UB_DFMA ? 8 : (mode == UB_CARRY_ROWS ? 8 : 2); }
 
 }  // namespace pg

@@ -19,5 +19,15 @@ void emu_sub(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0;
 void emu_neg(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_neg(a[i]); }
 void emu_inv(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_inv_fermat(a[i]); }
 void emu_from_mont(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_from_mont(a[i]); }
+// r (9 limbs) = dot product of K=5 pairs through fr_dot_wide; ok[i] = limbs9_is_multiple_of_q(r + c)
+void emu_dot5(uint64_t n, const Fr* a, const Fr* b, const Fr* c, uint32_t* r9, uint8_t* is_mult) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t r[9];
+        pg::fr_dot_wide<5>(r, a + 5 * i, b + 5 * i);
+        pg::add9_fr(r, c[i]);
+        for (int k = 0; k < 9; k++) r9[9 * i + k] = r[k];
+        is_mult[i] = pg::limbs9_is_multiple_of_q(r) ? 1 : 0;
+    }
+}
 void emu_to_mont(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_to_mont(a[i]); }
 }
