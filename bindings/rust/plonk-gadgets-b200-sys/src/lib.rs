@@ -1,0 +1,84 @@
+//! SOURCE ONLY (never compiled in this repository's environment: no rustc).
+//! Hand-written `extern "C"` declarations mirroring `include/pg_b200.h` one to one (bindgen is not available either).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+/// `BlsScalar([u64; 4])`: Montgomery limbs, little endian.
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default, PartialEq, Eq)]
+pub struct pg_fr {
+    pub l: [u64; 4],
+}
+#[repr(C)]
+pub struct pg_ctx {
+    _private: [u8; 0],
+}
+pub type pg_col = u64;
+
+pub const PG_OK: c_int = 0;
+pub const PG_ERR_NON_EXISTING_INVERSE: c_int = 1;
+pub const PG_ERR_CUDA: c_int = -1;
+pub const PG_ERR_ARG: c_int = -2;
+pub const PG_ERR_OOM: c_int = -3;
+pub const PG_ERR_MIXED_BITS: c_int = -4;
+pub const PG_ERR_NO_DEVICE: c_int = -5;
+pub const PG_ERR_STATE: c_int = -6;
+pub const PG_CHECK_GENERIC: i32 = 0;
+pub const PG_CHECK_SPARSE: i32 = 1;
+pub const PG_F_TIMING: u32 = 1;
+
+#[repr(C)]
+pub struct pg_cfg {
+    pub device: i32,
+    pub check_mode: i32,
+    pub flags: u32,
+    pub reserved: u32,
+    pub stream: *mut c_void,
+}
+#[repr(C)]
+#[derive(Default)]
+pub struct pg_timing {
+    pub check_ms: f64,
+    pub witness_ms: f64,
+    pub other_ms: f64,
+    pub check_launches: u64,
+    pub witness_launches: u64,
+    pub other_launches: u64,
+    pub check_rows: u64,
+}
+
+extern "C" {
+    pub fn pg_abi_version() -> c_int;
+    pub fn pg_strerror(code: c_int) -> *const c_char;
+    pub fn pg_last_error(ctx: *const pg_ctx) -> *const c_char;
+    pub fn pg_ctx_create(cfg: *const pg_cfg, out: *mut *mut pg_ctx) -> c_int;
+    pub fn pg_ctx_destroy(ctx: *mut pg_ctx);
+    pub fn pg_composer_reset(ctx: *mut pg_ctx) -> c_int;
+    pub fn pg_sync(ctx: *mut pg_ctx) -> c_int;
+    pub fn pg_add_input_batch(ctx: *mut pg_ctx, n: u64, values: *const pg_fr, on_device: c_int, out: *mut pg_col) -> c_int;
+    pub fn pg_range_check_batch(ctx: *mut pg_ctx, min_range: *const pg_fr, max_range: *const pg_fr, n_bounds: u64, on_device: c_int,
+                                witness: pg_col, out: *mut pg_col, num_bits: *mut u64) -> c_int;
+    pub fn pg_max_bound_batch(ctx: *mut pg_ctx, max_range: *const pg_fr, n_bounds: u64, on_device: c_int, witness: pg_col,
+                              out: *mut pg_col, num_bits: *mut u64) -> c_int;
+    pub fn pg_maybe_equal_batch(ctx: *mut pg_ctx, a: pg_col, b: pg_col, out: *mut pg_col) -> c_int;
+    pub fn pg_is_non_zero_batch(ctx: *mut pg_ctx, var: pg_col, value_assigned: *const pg_fr, on_device: c_int, n_err: *mut u64,
+                                first_err: *mut u64) -> c_int;
+    pub fn pg_select_zero_batch(ctx: *mut pg_ctx, x: pg_col, select: pg_col, out: *mut pg_col) -> c_int;
+    pub fn pg_select_one_batch(ctx: *mut pg_ctx, y: pg_col, selector: pg_col, out: *mut pg_col) -> c_int;
+    pub fn pg_constrain_to_constant_batch(ctx: *mut pg_ctx, a: pg_col, constant: *const pg_fr, n_const: u64, pi: *const pg_fr,
+                                          n_pi: u64, on_device: c_int) -> c_int;
+    pub fn pg_check(ctx: *mut pg_ctx, n_unsat: *mut u64, first_bad_row: *mut u64) -> c_int;
+    pub fn pg_check_rows(ctx: *mut pg_ctx, n: u64, w_val: *const pg_fr, sel: *const pg_fr, pi: *const pg_fr, on_device: c_int,
+                         n_unsat: *mut u64, first_bad_row: *mut u64) -> c_int;
+    pub fn pg_counts(ctx: *const pg_ctx, n_rows: *mut u64, n_vars: *mut u64) -> c_int;
+    pub fn pg_col_info(ctx: *const pg_ctx, col: pg_col, n: *mut u64, first_var: *mut u64, stride: *mut u64) -> c_int;
+    pub fn pg_col_read(ctx: *mut pg_ctx, col: pg_col, i0: u64, cnt: u64, dst: *mut pg_fr, dst_on_device: c_int) -> c_int;
+    pub fn pg_read_variables(ctx: *mut pg_ctx, var0: u64, cnt: u64, dst: *mut pg_fr, dst_on_device: c_int) -> c_int;
+    pub fn pg_materialize_rows(ctx: *mut pg_ctx, row0: u64, cnt: u64, w_idx: *mut u64, w_val: *mut pg_fr, sel: *mut pg_fr,
+                               pi: *mut pg_fr, dst_on_device: c_int) -> c_int;
+    pub fn pg_synth(ctx: *mut pg_ctx, seed: u64, stream: u64, n: u64, kind: c_int, bits: u32, dst_device: *mut pg_fr) -> c_int;
+    pub fn pg_get_timing(ctx: *mut pg_ctx, out: *mut pg_timing, reset: c_int) -> c_int;
+    pub fn pg_measure_imad_peak(ctx: *mut pg_ctx, wide_mac_per_s: *mut f64, imad_per_s: *mut f64) -> c_int;
+    pub fn pg_microbench(ctx: *mut pg_ctx, mode: c_int, ops_per_s: *mut f64) -> c_int;
+    pub fn pg_fr_op(ctx: *mut pg_ctx, op: c_int, n: u64, a: *const pg_fr, b: *const pg_fr, out: *mut pg_fr) -> c_int;
+}

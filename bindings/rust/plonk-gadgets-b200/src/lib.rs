@@ -1,0 +1,114 @@
+//! SOURCE ONLY (never compiled in this repository's environment).
+//!
+//! The reference crate (`plonk_gadgets`) stays untouched -- `#![deny(unsafe_code)]` and `#![no_std]` forbid FFI inside
+//! it (/root/reference/src/lib.rs:32-33) -- and remains the one-instance path: `AllocatedScalar`, `range_check`,
+//! `max_bound`, `is_non_zero`, `maybe_equal`, `conditionally_select_one/zero` keep their signatures.  This crate adds the
+//! batched variants with the same names suffixed `_batch`, over a device-resident `BatchComposer`.
+//!
+//! `Variable(pub(crate) usize)` cannot be forged outside dusk-plonk, so batched calls return `Variables` (a column id plus
+//! the reference's Variable numbering `first + i*stride`) instead of `Variable`s.
+use dusk_plonk::prelude::BlsScalar;
+pub use plonk_gadgets::{AllocatedScalar, Error};
+use plonk_gadgets_b200_sys as sys;
+use std::{ffi::CStr, ptr};
+
+/// Engine failures (negative codes of the C ABI).  Never mapped to a gadget `Error`, never a silent CPU fallback.
+#[derive(Debug)]
+pub struct EngineError {
+    pub code: i32,
+    pub detail: String,
+}
+
+/// n `Variable`s, one per gadget instance of the call that produced them.
+#[derive(Copy, Clone, Debug)]
+pub struct Variables {
+    pub col: sys::pg_col,
+    pub n: u64,
+}
+
+/// Device-resident batched `StandardComposer` (fresh: 3 rows, 5 variables -- `StandardComposer::new()`).
+pub struct BatchComposer {
+    ctx: *mut sys::pg_ctx,
+}
+
+fn as_fr(s: &[BlsScalar]) -> *const sys::pg_fr {
+    // BlsScalar is `pub struct Scalar(pub [u64; 4])`: same layout as pg_fr
+    s.as_ptr() as *const sys::pg_fr
+}
+
+impl BatchComposer {
+    pub fn new(device: i32) -> Result<Self, EngineError> {
+        let cfg = sys::pg_cfg { device, check_mode: sys::PG_CHECK_GENERIC, flags: 0, reserved: 0, stream: ptr::null_mut() };
+        let mut ctx = ptr::null_mut();
+        let rc = unsafe { sys::pg_ctx_create(&cfg, &mut ctx) };
+        if rc != sys::PG_OK {
+            let detail = unsafe { CStr::from_ptr(sys::pg_strerror(rc)) }.to_string_lossy().into_owned();
+            return Err(EngineError { code: rc, detail });
+        }
+        Ok(BatchComposer { ctx })
+    }
+    fn ok(&self, rc: i32) -> Result<i32, EngineError> {
+        if rc < 0 {
+            let detail = unsafe { CStr::from_ptr(sys::pg_last_error(self.ctx)) }.to_string_lossy().into_owned();
+            Err(EngineError { code: rc, detail })
+        } else {
+            Ok(rc)
+        }
+    }
+    /// `AllocatedScalar::allocate` over n scalars.
+    pub fn allocate_batch(&mut self, scalars: &[BlsScalar]) -> Result<Variables, EngineError> {
+        let mut col = 0;
+        self.ok(unsafe { sys::pg_add_input_batch(self.ctx, scalars.len() as u64, as_fr(scalars), 0, &mut col) })?;
+        Ok(Variables { col, n: scalars.len() as u64 })
+    }
+    /// `range_check(composer, min_range, max_range, witness)` for every element of `witness`.
+    pub fn range_check_batch(&mut self, min_range: BlsScalar, max_range: BlsScalar, witness: Variables) -> Result<Variables, EngineError> {
+        let (mut col, mut k) = (0, 0);
+        self.ok(unsafe { sys::pg_range_check_batch(self.ctx, as_fr(&[min_range]), as_fr(&[max_range]), 1, 0, witness.col, &mut col, &mut k) })?;
+        Ok(Variables { col, n: witness.n })
+    }
+    /// `max_bound(composer, max_range, witness) -> (Variable, u64)`.
+    pub fn max_bound_batch(&mut self, max_range: BlsScalar, witness: Variables) -> Result<(Variables, u64), EngineError> {
+        let (mut col, mut k) = (0, 0);
+        self.ok(unsafe { sys::pg_max_bound_batch(self.ctx, as_fr(&[max_range]), 1, 0, witness.col, &mut col, &mut k) })?;
+        Ok((Variables { col, n: witness.n }, k))
+    }
+    pub fn maybe_equal_batch(&mut self, a: Variables, b: Variables) -> Result<Variables, EngineError> {
+        let mut col = 0;
+        self.ok(unsafe { sys::pg_maybe_equal_batch(self.ctx, a.col, b.col, &mut col) })?;
+        Ok(Variables { col, n: a.n })
+    }
+    /// `for i { is_non_zero(composer, var_i, value_assigned_i)?; }` -- `Ok(Err(NonExistingInverse))` mirrors the gadget error.
+    pub fn is_non_zero_batch(&mut self, var: Variables, value_assigned: &[BlsScalar]) -> Result<Result<(), Error>, EngineError> {
+        let (mut n_err, mut first) = (0, 0);
+        let rc = self.ok(unsafe { sys::pg_is_non_zero_batch(self.ctx, var.col, as_fr(value_assigned), 0, &mut n_err, &mut first) })?;
+        Ok(if rc == sys::PG_ERR_NON_EXISTING_INVERSE { Err(Error::NonExistingInverse) } else { Ok(()) })
+    }
+    pub fn conditionally_select_zero_batch(&mut self, x: Variables, select: Variables) -> Result<Variables, EngineError> {
+        let mut col = 0;
+        self.ok(unsafe { sys::pg_select_zero_batch(self.ctx, x.col, select.col, &mut col) })?;
+        Ok(Variables { col, n: x.n })
+    }
+    pub fn conditionally_select_one_batch(&mut self, y: Variables, selector: Variables) -> Result<Variables, EngineError> {
+        let mut col = 0;
+        self.ok(unsafe { sys::pg_select_one_batch(self.ctx, y.col, selector.col, &mut col) })?;
+        Ok(Variables { col, n: y.n })
+    }
+    /// Satisfaction verdict: (unsatisfied rows, first unsatisfied row).
+    pub fn check(&mut self) -> Result<(u64, Option<u64>), EngineError> {
+        let (mut bad, mut first) = (0, 0);
+        self.ok(unsafe { sys::pg_check(self.ctx, &mut bad, &mut first) })?;
+        Ok((bad, if first == u64::MAX { None } else { Some(first) }))
+    }
+    /// `composer.variables[var]` of a column.
+    pub fn values(&mut self, v: Variables) -> Result<Vec<BlsScalar>, EngineError> {
+        let mut out = vec![BlsScalar::zero(); v.n as usize];
+        self.ok(unsafe { sys::pg_col_read(self.ctx, v.col, 0, v.n, out.as_mut_ptr() as *mut sys::pg_fr, 0) })?;
+        Ok(out)
+    }
+}
+impl Drop for BatchComposer {
+    fn drop(&mut self) {
+        unsafe { sys::pg_ctx_destroy(self.ctx) }
+    }
+}
