@@ -226,7 +226,7 @@ struct CheckBody {
     typedef CheckArgs Args;
     // evaluates all rows of instance i; returns the number of unsatisfied rows, updates first_bad (global row index)
     template <int MODE, class PoolT>
-    PG_HD static uint32_t run(const Args& a, const PoolT& pool, uint64_t i, unsigned long long& first_bad) {
+    PG_HD static uint32_t run(const Args& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t bad = 0;
         for (uint32_t r = 0; r < a.n_rows; r++) {
             const DevRow row = a.rows[r];
@@ -235,11 +235,11 @@ struct CheckBody {
             w[3] = loc_load(a.tab, row.loc[2], i); w[4] = loc_load(a.tab, row.loc[3], i);
             uint32_t t[9];
             if (MODE == 0) {
-                w[0] = fr_mul(w[1], w[2]);                                   // a*b
+                w[0] = fr_mul_eo(w[1], w[2], q);                             // a*b
                 Fr sel[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) sel[k] = pool(row.sel[k]);       // q_m q_l q_r q_o q_4
-                fr_dot_wide<5>(t, w, sel);
+                fr_dot_wide<5>(t, w, sel, q);
             } else {
 #pragma unroll
                 for (int k = 0; k < 9; k++) t[k] = 0;
@@ -247,8 +247,8 @@ struct CheckBody {
                 for (int k = 0; k < 5; k++) {
                     const uint32_t si = row.sel[k];
                     if (si == POOL_ZERO) continue;
-                    const Fr v = k == 0 ? fr_mul(w[1], w[2]) : w[k];
-                    add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul(pool(si), v)));
+                    const Fr v = k == 0 ? fr_mul_eo(w[1], w[2], q) : w[k];
+                    add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_eo(pool(si), v, q)));
                 }
             }
             add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));

@@ -63,6 +63,11 @@ PG_HD uint32_t fr_qc(int i) {
     return q[i];
 #endif
 }
+// Modulus limbs held in ordinary (vector) registers.  With a uniform-register / constant-bank operand ptxas cannot form
+// IMAD.WIDE.U32.X (carry-in) and splits each reduction product into IMAD.X + IMAD.HI.U32.X (6 multiplier cycles instead of 4);
+// the hot kernels therefore load q once per thread from shared memory into a QRegs and pass it down.
+struct QRegs { uint32_t v[8]; };
+PG_HD QRegs q_regs_default() { QRegs q; for (int i = 0; i < 8; i++) q.v[i] = fr_qc(i); return q; }
 PG_HD uint32_t fr_q(int i) {
     switch (i) { case 0: return PG_Q0; case 1: return PG_Q1; case 2: return PG_Q2; case 3: return PG_Q3;
                  case 4: return PG_Q4; case 5: return PG_Q5; case 6: return PG_Q6; default: return PG_Q7; }
@@ -150,6 +155,20 @@ PG_HD Fr fr_sub(const Fr& a, const Fr& b) {
 PG_HD Fr fr_neg(const Fr& a) { return fr_sub(fr_zero(), a); }   // q - a, and 0 for a == 0 (0 - 0 does not borrow)
 
 // conditional final subtraction: t in [0, 2q) -> [0, q)
+#if defined(__CUDA_ARCH__)
+PG_D Fr fr_reduce_once(const Fr& t) {
+    Fr d; uint32_t bw;
+    asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(d.v[0]), "=&r"(d.v[1]), "=&r"(d.v[2]), "=&r"(d.v[3]), "=&r"(d.v[4]), "=&r"(d.v[5]), "=&r"(d.v[6]), "=&r"(d.v[7]), "=&r"(bw)
+        : "r"(t.v[0]), "r"(t.v[1]), "r"(t.v[2]), "r"(t.v[3]), "r"(t.v[4]), "r"(t.v[5]), "r"(t.v[6]), "r"(t.v[7]),
+          "r"(PG_Q0), "r"(PG_Q1), "r"(PG_Q2), "r"(PG_Q3), "r"(PG_Q4), "r"(PG_Q5), "r"(PG_Q6), "r"(PG_Q7));
+#pragma unroll
+    for (int i = 0; i < 8; i++) d.v[i] = bw ? t.v[i] : d.v[i];
+    return d;
+}
+#else
 PG_HD Fr fr_reduce_once(const Fr& t) {
     Fr d; const uint32_t q[8] = {PG_Q0, PG_Q1, PG_Q2, PG_Q3, PG_Q4, PG_Q5, PG_Q6, PG_Q7};
     uint32_t bw = fr_sub_limbs(d.v, t.v, q);
@@ -158,6 +177,7 @@ PG_HD Fr fr_reduce_once(const Fr& t) {
     for (int i = 0; i < 8; i++) r.v[i] = bw ? t.v[i] : d.v[i];
     return r;
 }
+#endif
 
 // ---- portable CIOS Montgomery multiplication (host + device) --------------------------------------------------------
 PG_HD Fr fr_mul_cios(const Fr& a, const Fr& b) {
@@ -269,35 +289,56 @@ inline void merge_even_odd(uint32_t* r, const uint32_t* e, const uint32_t* o) {
 
 // One operand-scanning step: (X | Y) hold T = sum X[j] 2^(32j) + sum Y[j] 2^(32(j+1)).  Adds a*bi, then m*q with
 // m = -T[0], leaving X[0] == 0; the caller swaps the roles of X and Y for the next step (division by 2^32).
-PG_HD void mont_step_first(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+// reduction rows of one step for m = -X[0]:  Y += m*(q1,q3,q5,q7) (m*q1 = (m << 32) - m by the adder, no carry out of Y[7]
+// because q7 < 2^31),  X += m*(q0,q2,q4,q6) (m*q0 = m), carry -> Y[7]
+#if defined(__CUDA_ARCH__)
+PG_D void red_rows(uint32_t* X, uint32_t* Y, const QRegs& q) {
+    const uint32_t m = 0u - X[0];
+    uint32_t lo, hi;
+    asm("sub.cc.u32 %0, 0, %2;\n\tsubc.u32 %1, %2, 0;" : "=&r"(lo), "=&r"(hi) : "r"(m));
+    asm("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %9;\n\tmadc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\tmadc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.u32 %7, %12, %13, %7;"
+        : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7])
+        : "r"(lo), "r"(hi), "r"(q.v[3]), "r"(q.v[5]), "r"(q.v[7]), "r"(m));
+    asm("add.cc.u32 %0, %0, %12;\n\taddc.cc.u32 %1, %1, 0;\n\tmadc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\tmadc.hi.cc.u32 %5, %10, %12, %5;\n\tmadc.lo.cc.u32 %6, %11, %12, %6;\n\tmadc.hi.cc.u32 %7, %11, %12, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(Y[7])
+        : "r"(q.v[2]), "r"(q.v[4]), "r"(q.v[6]), "r"(m));
+}
+#else
+inline void red_rows(uint32_t* X, uint32_t* Y, const QRegs& q) {
+    const uint32_t m = 0u - X[0];
+    mad_row_nc(Y, q.v[1], q.v[3], q.v[5], q.v[7], m);
+    mad_row(X, Y[7], q.v[0], q.v[2], q.v[4], q.v[6], m);
+}
+#endif
+PG_HD void mont_step_first(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi, const QRegs& q) {
     mul_row(Y, a[1], a[3], a[5], a[7], bi);
     mul_row(X, a[0], a[2], a[4], a[6], bi);
-    uint32_t m = 0u - X[0];
-    mad_row_nc(Y, fr_qc(1), fr_qc(3), fr_qc(5), fr_qc(7), m);   // top limb of q is < 2^31: no carry out of Y[7]
-    mad_row(X, Y[7], fr_qc(0), fr_qc(2), fr_qc(4), fr_qc(6), m);
+    red_rows(X, Y, q);
 }
-PG_HD void mont_step(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+PG_HD void mont_step(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi, const QRegs& q) {
     mad_row_shift(Y, X[0], a[1], a[3], a[5], a[7], bi);       // X[0] += Y[1]; Y = (Y >> 64) + a_odd*bi
     mad_row(X, Y[7], a[0], a[2], a[4], a[6], bi);
-    uint32_t m = 0u - X[0];
-    mad_row_nc(Y, fr_qc(1), fr_qc(3), fr_qc(5), fr_qc(7), m);
-    mad_row(X, Y[7], fr_qc(0), fr_qc(2), fr_qc(4), fr_qc(6), m);
+    red_rows(X, Y, q);
 }
 
-PG_HD Fr fr_mul_eo(const Fr& a, const Fr& b) {
+PG_HD Fr fr_mul_eo(const Fr& a, const Fr& b, const QRegs& q) {
     uint32_t even[8], odd[8];
-    mont_step_first(even, odd, a.v, b.v[0]);
-    mont_step(odd, even, a.v, b.v[1]);
-    mont_step(even, odd, a.v, b.v[2]);
-    mont_step(odd, even, a.v, b.v[3]);
-    mont_step(even, odd, a.v, b.v[4]);
-    mont_step(odd, even, a.v, b.v[5]);
-    mont_step(even, odd, a.v, b.v[6]);
-    mont_step(odd, even, a.v, b.v[7]);
+    mont_step_first(even, odd, a.v, b.v[0], q);
+    mont_step(odd, even, a.v, b.v[1], q);
+    mont_step(even, odd, a.v, b.v[2], q);
+    mont_step(odd, even, a.v, b.v[3], q);
+    mont_step(even, odd, a.v, b.v[4], q);
+    mont_step(odd, even, a.v, b.v[5], q);
+    mont_step(even, odd, a.v, b.v[6], q);
+    mont_step(odd, even, a.v, b.v[7], q);
     Fr r;
     merge_even_odd(r.v, even, odd);                           // (even + odd>>32), odd[0] == 0
     return fr_reduce_once(r);
 }
+PG_HD Fr fr_mul_eo(const Fr& a, const Fr& b) { return fr_mul_eo(a, b, q_regs_default()); }
 
 // ---- dot-product Montgomery: sum_p a_p*b_p with ONE interleaved reduction ----------------------------------------------
 // The gate equation needs q_m*(ab) + q_l*a + q_r*b + q_o*c + q_4*d only up to "is it 0 mod q", so the five double-width
@@ -335,7 +376,7 @@ PG_D void dmad_row_shift(uint32_t* o, uint32_t& e0, uint32_t& z, uint32_t x1, ui
         : "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
 }
 // reduction rows for m = -X[0]:  Y += m*(q1,q3,q5,q7) with m*q1 = (m<<32) - m done by the adder;  X += m*(q0,q2,q4,q6) with m*q0 = m
-PG_D void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z) {
+PG_D void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z, const QRegs& q) {
     const uint32_t m = 0u - X[0];
     uint32_t lo, hi;
     asm("sub.cc.u32 %0, 0, %2;\n\tsubc.u32 %1, %2, 0;" : "=&r"(lo), "=&r"(hi) : "r"(m));            // m*(2^32-1) = hi:lo
@@ -343,12 +384,12 @@ PG_D void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z) {
         "madc.lo.cc.u32 %4, %12, %14, %4;\n\tmadc.hi.cc.u32 %5, %12, %14, %5;\n\tmadc.lo.cc.u32 %6, %13, %14, %6;\n\tmadc.hi.cc.u32 %7, %13, %14, %7;\n\t"
         "addc.u32 %8, %8, 0;"
         : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(z)
-        : "r"(lo), "r"(hi), "r"(fr_qc(3)), "r"(fr_qc(5)), "r"(fr_qc(7)), "r"(m));
+        : "r"(lo), "r"(hi), "r"(q.v[3]), "r"(q.v[5]), "r"(q.v[7]), "r"(m));
     asm("add.cc.u32 %0, %0, %13;\n\taddc.cc.u32 %1, %1, 0;\n\tmadc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
         "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\tmadc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.cc.u32 %7, %12, %13, %7;\n\t"
         "addc.cc.u32 %8, %8, 0;\n\taddc.u32 %9, %9, 0;"
         : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(Y[7]), "+r"(z)
-        : "r"(fr_qc(2)), "r"(fr_qc(4)), "r"(fr_qc(6)), "r"(m));
+        : "r"(q.v[2]), "r"(q.v[4]), "r"(q.v[6]), "r"(m));
 }
 // r[0..8] = (X >> 32) + Y + (z << 256)
 PG_D void dmerge(uint32_t* r, const uint32_t* X, const uint32_t* Y, uint32_t z) {
@@ -387,9 +428,9 @@ inline void dmad_row_shift(uint32_t* o, uint32_t& e0, uint32_t& z, uint32_t x1, 
     z = emu_mad_chain(sh, x, y, (uint32_t)(s >> 32));
     for (int i = 0; i < 8; i++) o[i] = sh[i];
 }
-inline void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z) {
+inline void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z, const QRegs& q) {
     const uint32_t m = 0u - X[0];
-    const uint32_t qo[4] = {PG_Q1, PG_Q3, PG_Q5, PG_Q7}, qe[4] = {PG_Q0, PG_Q2, PG_Q4, PG_Q6};
+    const uint32_t qo[4] = {q.v[1], q.v[3], q.v[5], q.v[7]}, qe[4] = {q.v[0], q.v[2], q.v[4], q.v[6]};
     uint32_t c = emu_mad_chain(Y, qo, m, 0);
     if (z + c < z) PG_EMU_VIOLATION();
     z += c;
@@ -416,7 +457,7 @@ inline void add9_fr(uint32_t* r, const Fr& a) {
 // One limb step of the dot product for products p = 0..K-1: multiplicands a[p] (8 limbs), scanned limbs bi[p].
 // (X | Y | z) as in mont_step; FIRST = the very first step (nothing to shift in).
 template <int K, bool FIRST>
-PG_HD void dot_step(uint32_t* X, uint32_t* Y, uint32_t& z, const Fr* a, const uint32_t* bi) {
+PG_HD void dot_step(uint32_t* X, uint32_t* Y, uint32_t& z, const Fr* a, const uint32_t* bi, const QRegs& q) {
     if (FIRST) {
         mul_row(Y, a[0].v[1], a[0].v[3], a[0].v[5], a[0].v[7], bi[0]);
         mul_row(X, a[0].v[0], a[0].v[2], a[0].v[4], a[0].v[6], bi[0]);
@@ -430,15 +471,15 @@ PG_HD void dot_step(uint32_t* X, uint32_t* Y, uint32_t& z, const Fr* a, const ui
         dmad_row_y(Y, z, a[p].v[1], a[p].v[3], a[p].v[5], a[p].v[7], bi[p]);
         dmad_row_x(X, Y[7], z, a[p].v[0], a[p].v[2], a[p].v[4], a[p].v[6], bi[p]);
     }
-    dred_rows(X, Y, z);
+    dred_rows(X, Y, z, q);
 }
 // r[0..8] = (sum_p a[p]*b[p]) / 2^256 mod q up to a multiple of q, r < (K+1)*q + 2^224.  a[p], b[p] < 2q.
 template <int K>
-PG_HD void fr_dot_wide(uint32_t* r, const Fr* a, const Fr* b) {
+PG_HD void fr_dot_wide(uint32_t* r, const Fr* a, const Fr* b, const QRegs& q) {
     uint32_t even[8], odd[8], z, bi[K];
 #define PG_DOT_STEP(I, XX, YY, FIRST)                          \
     _Pragma("unroll") for (int p = 0; p < K; p++) bi[p] = b[p].v[I]; \
-    dot_step<K, FIRST>(XX, YY, z, a, bi);
+    dot_step<K, FIRST>(XX, YY, z, a, bi, q);
     PG_DOT_STEP(0, even, odd, true)
     PG_DOT_STEP(1, odd, even, false)
     PG_DOT_STEP(2, even, odd, false)
@@ -450,6 +491,8 @@ PG_HD void fr_dot_wide(uint32_t* r, const Fr* a, const Fr* b) {
 #undef PG_DOT_STEP
     dmerge(r, odd, even, z);          // the last step cleared odd[0]: value = (odd >> 32) + even + (z << 256)
 }
+template <int K>
+PG_HD void fr_dot_wide(uint32_t* r, const Fr* a, const Fr* b) { fr_dot_wide<K>(r, a, b, q_regs_default()); }
 // k*q for k = 0..15 (9 limbs each): since q0 = 1, k*q = k (mod 2^32), so a 9-limb r is 0 mod q iff r == k*q for k = r[0] (r < 16q)
 PG_HD bool limbs9_is_multiple_of_q(const uint32_t* r) {
     const uint32_t k = r[0];

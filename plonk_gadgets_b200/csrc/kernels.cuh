@@ -110,12 +110,17 @@ struct SmemPool {
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK, 2) k_check(const CheckArgs a) {
     extern __shared__ __align__(16) uint32_t s_pool[];
+    __shared__ uint32_t s_q[8];
     for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += BLOCK) s_pool[t] = a.pool[t];
+    if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
     __syncthreads();
+    QRegs q;                                   // modulus limbs in vector registers (see QRegs in fr.cuh)
+#pragma unroll
+    for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
     const uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
-    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, i, first_bad); }
+    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, q, i, first_bad); }
     // warp-level reduction, then one atomic per warp that saw a violation
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -55,7 +55,8 @@ public:
         HostPool pool = {a.pool};
         for (uint64_t i = 0; i < a.n_inst; i++) {
             unsigned long long fb = ~0ull;
-            const uint32_t bad = a.mode ? CheckBody::run<1>(a, pool, i, fb) : CheckBody::run<0>(a, pool, i, fb);
+            const QRegs q = q_regs_default();
+            const uint32_t bad = a.mode ? CheckBody::run<1>(a, pool, q, i, fb) : CheckBody::run<0>(a, pool, q, i, fb);
             if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
         }
         return true;
