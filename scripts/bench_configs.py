@@ -1,0 +1,136 @@
+"""Throughput of the other BASELINE.json configurations (C2-C5 of SURVEY.md section 8) and of the read-back kernels.
+One JSON line per configuration; inputs resident in HBM, CUDA events on the engine's stream, verdicts asserted."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import plonk_gadgets_b200 as pg
+
+SEED = 0x706C6F6E6B5F6732
+R2 = np.array([[0xc999e990f3f29c6d, 0x2b6cedcb87925c23, 0x05d314967254398f, 0x0748d9d99f59ff11]], dtype=np.uint64)
+dev = torch.device("cuda", 0)
+stream = torch.cuda.current_stream(dev)
+
+
+def to_mont(c, canonical_ints):
+    raw = np.array([[(v >> (64 * k)) & (2 ** 64 - 1) for k in range(4)] for v in canonical_ints], dtype=np.uint64)
+    return c.fr_op(0, raw, np.repeat(R2, len(canonical_ints), axis=0))
+
+
+def timed(c, fn, steps=3, warmup=2):
+    for _ in range(warmup):
+        out = fn()
+    c.timing(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(steps):
+        out = fn()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    tim = c.timing(reset=True)
+    return e0.elapsed_time(e1) / steps, {k: (v / steps if k.endswith("_ms") else v) for k, v in tim.items()}, out
+
+
+def emit(name, rows, ms, tim, extra=None):
+    line = {"config": name, "rows_per_step": rows, "ms_per_step": ms, "gate_evals_per_s": rows / (ms * 1e-3),
+            "kernel_ms": {k: tim[k] for k in ("check_ms", "witness_ms", "other_ms")}}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    mode = pg.CHECK_SPARSE if "--sparse" in sys.argv else pg.CHECK_GENERIC
+    c = pg.StandardComposer(device=0, check_mode=mode, timing=True, stream=stream.cuda_stream)
+    zero_2p64 = to_mont(c, [0, 2 ** 64])
+    mn, mx = zero_2p64[0:1].copy(), zero_2p64[1:2].copy()
+
+    # ---- C2: 2^20 range_check, 64-bit bound
+    n = 1 << 20
+    wit = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 2, 2, 64, wit)
+
+    def c2():
+        c.reset(); w = c.add_input(wit); pg.range_check(c, mn, mx, w)
+        bad, _ = c.check_circuit_satisfied(); assert bad == 0
+    ms, tim, _ = timed(c, c2)
+    emit("C2: 2^20 range_check, 64-bit bound (k=65)", 271 * n, ms, tim)
+
+    # ---- C3: 2^22 max_bound with 252-bit per-instance bounds (k=253)
+    n = 1 << 22
+    mx3 = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 31, 3, 252, mx3)
+    wit3 = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 32, 2, 250, wit3)
+
+    def c3():
+        c.reset(); w = c.add_input(wit3); _, k = pg.max_bound(c, mx3, w); assert k == 253
+        bad, _ = c.check_circuit_satisfied(); assert bad == 0
+    ms, tim, _ = timed(c, c3, steps=2, warmup=1)
+    emit("C3: 2^22 max_bound, per-instance 252-bit bounds (k=253, 511 rows each)", 511 * n, ms, tim)
+    del mx3, wit3
+
+    # ---- C4: 2^24 x (is_non_zero + maybe_equal)
+    n = 1 << 24
+    a = torch.empty((n, 4), dtype=torch.int64, device=dev); b = torch.empty_like(a)
+    c.synth(SEED, 41, 0, 0, a); c.synth(SEED, 42, 0, 0, b); b[0::2] = a[0::2]
+
+    def c4():
+        c.reset(); va = c.add_input(a); vb = c.add_input(b)
+        pg.maybe_equal(c, va, vb); pg.is_non_zero(c, va, a)
+        bad, _ = c.check_circuit_satisfied(); assert bad == 0
+    ms, tim, _ = timed(c, c4)
+    emit("C4: 2^24 x (is_non_zero + maybe_equal): 2^25 inversions, 6 rows per pair", 6 * n, ms, tim,
+         {"inversions_per_s": 2 * n / (ms * 1e-3)})
+    del a, b
+
+    # ---- C5: mixed circuit, 2^26 rows: range_check k=65 / max_bound k=253 / is_non_zero / select_one+select_zero, a quarter each
+    q = 1 << 24
+    n_rc, n_mb, n_nz, n_sel = q // 271, q // 511, q // 3, q // 5
+    x_rc = torch.empty((n_rc, 4), dtype=torch.int64, device=dev); c.synth(SEED, 51, 2, 64, x_rc)
+    x_mb = torch.empty((n_mb, 4), dtype=torch.int64, device=dev); c.synth(SEED, 52, 2, 250, x_mb)
+    x_nz = torch.empty((n_nz, 4), dtype=torch.int64, device=dev); c.synth(SEED, 53, 0, 0, x_nz)
+    x_sel = torch.empty((n_sel, 4), dtype=torch.int64, device=dev); c.synth(SEED, 54, 0, 0, x_sel)
+    s_sel = torch.empty((n_sel, 4), dtype=torch.int64, device=dev); c.synth(SEED, 55, 1, 1, s_sel)   # 1-bit selectors
+    mx252 = to_mont(c, [2 ** 252])
+
+    def c5():
+        c.reset()
+        w = c.add_input(x_rc); pg.range_check(c, mn, mx, w)
+        w = c.add_input(x_mb); pg.max_bound(c, mx252, w)
+        w = c.add_input(x_nz); pg.is_non_zero(c, w, x_nz)
+        x = c.add_input(x_sel); s = c.add_input(s_sel)
+        y = pg.conditionally_select_one(c, x, s); pg.conditionally_select_zero(c, y, s)
+        bad, _ = c.check_circuit_satisfied(); assert bad == 0
+        return c.circuit_size()
+    ms, tim, rows = timed(c, c5)
+    emit("C5: mixed circuit (range_check k=65 / max_bound k=253 / is_non_zero / select_one+select_zero), ~2^26 rows", rows - 3, ms, tim)
+
+    # ---- read-back kernels: materialise rows / variables of the last composer to device buffers (reference representation)
+    cnt = 1 << 22
+    w_idx = torch.empty((4, cnt), dtype=torch.int64, device=dev)
+    w_val = torch.empty((4, cnt, 4), dtype=torch.int64, device=dev)
+    sel = torch.empty((6, cnt, 4), dtype=torch.int64, device=dev)
+    pi = torch.empty((cnt, 4), dtype=torch.int64, device=dev)
+    import ctypes as C
+
+    def mat():
+        c._ok(c._L.pg_materialize_rows(c._ctx, 3, cnt, C.c_void_p(w_idx.data_ptr()), C.c_void_p(w_val.data_ptr()), C.c_void_p(sel.data_ptr()),
+                                       C.c_void_p(pi.data_ptr()), 1), "pg_materialize_rows")
+    ms, tim, _ = timed(c, mat)
+    emit("materialize 2^22 rows (4 wire ids + 4 wire values + 6 selectors + PI = 384 B/row) to device buffers", cnt, ms, tim,
+         {"GB_per_s_written": cnt * 384 / (ms * 1e-3) / 1e9})
+    vars_buf = torch.empty((cnt, 4), dtype=torch.int64, device=dev)
+
+    def rv():
+        c._ok(c._L.pg_read_variables(c._ctx, 5, cnt, C.c_void_p(vars_buf.data_ptr()), 1), "pg_read_variables")
+    ms, tim, _ = timed(c, rv)
+    emit("read 2^22 variables (Variable order, 32 B each) to a device buffer", cnt, ms, tim, {"GB_per_s_written": cnt * 32 / (ms * 1e-3) / 1e9})
+
+
+if __name__ == "__main__":
+    main()
