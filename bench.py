@@ -173,9 +173,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = 1 << args.log2n
     warm = max(args.warmup, 3)
-    stream = torch.cuda.current_stream(dev)
+    # one non-default torch stream shared with the engine: torch.cuda.Event and the engine's kernels see the same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     mode = pg.CHECK_GENERIC if args.check_mode == "generic" else pg.CHECK_SPARSE
     c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream)
+    assert stream.cuda_stream != 0
 
     # synthetic witnesses: even index uniform u64 (in range), odd index uniform Fr (out of range); per-rank stream id
     wit = torch.empty((n, 4), dtype=torch.int64, device=dev)

@@ -93,7 +93,7 @@ struct RangeArgs {
 };
 
 // which table slots the batch inversion reads and writes: out[j] = in[j]^-1 (or 0) for every instance
-struct BatchInvArgs { uint4* fr; uint64_t stride; uint64_t n; uint32_t n_pairs; uint32_t in_slot[4]; uint32_t out_slot[4]; };
+struct BatchInvArgs { uint4* fr; uint64_t stride; uint64_t n; uint32_t n_pairs; uint32_t in_slot[4]; uint32_t out_slot[4]; uint32_t elems_per_thread; };
 
 template <bool RANGE>
 struct RangePre {

@@ -120,11 +120,16 @@ public:
         toc();
         return launched("k_simple");
     }
-    bool run_batch_inv(const BatchInvArgs& a, int cls) {
+    bool run_batch_inv(const BatchInvArgs& a_in, int cls) {
+        BatchInvArgs a = a_in;
         const uint64_t total = (uint64_t)a.n_pairs * a.n;
         if (!total) return true;
+        a.elems_per_thread = 8;
+        for (uint32_t e : {128u, 32u})
+            if (total / ((uint64_t)BLOCK * e) >= (uint64_t)sm_count * 4) { a.elems_per_thread = e; break; }
+        const uint64_t per_block = (uint64_t)BLOCK * a.elems_per_thread;
         tic(cls, 0);
-        k_batch_inv<<<(unsigned)((total + BLOCK * INV_E - 1) / (BLOCK * INV_E)), BLOCK, 0, stream>>>(a);
+        k_batch_inv<<<(unsigned)((total + per_block - 1) / per_block), BLOCK, 0, stream>>>(a);
         toc();
         return launched("k_batch_inv");
     }

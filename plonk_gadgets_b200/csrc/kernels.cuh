@@ -59,12 +59,14 @@ static_assert(NWARPS == 8, "block_invert_nonzero's cross-warp butterfly is writt
 //   pass 1: running product of the thread's elements (zeros patched to 1), each prefix parked in the OUTPUT slot;
 //   block : one Fermat inversion for the product of all BLOCK*INV_E elements (block_invert_nonzero);
 //   pass 2: walk back -- inverse_e = inv(prefix_e) * prefix_{e-1}, inv(prefix_{e-1}) = inv(prefix_e) * x_e.
-// 3 multiplications per element, no per-element state in registers, one inversion per 8192 elements.
-constexpr int INV_E = 32;
+// 3 multiplications per element, no per-element state in registers, one inversion per BLOCK*E elements.  E (elements per
+// thread) is chosen per launch: large enough that the block's single Fermat chain (~333 dependent multiplications on one
+// warp) is amortised, small enough that the grid still fills the chip twice.
 __global__ void __launch_bounds__(BLOCK, 2) k_batch_inv(const BatchInvArgs a) {
     __shared__ Fr smem[NWARPS];
     const uint64_t total = (uint64_t)a.n_pairs * a.n;
-    const uint64_t tile = (uint64_t)blockIdx.x * (BLOCK * INV_E);
+    const int INV_E = (int)a.elems_per_thread;
+    const uint64_t tile = (uint64_t)blockIdx.x * ((uint64_t)BLOCK * INV_E);
     Fr p = fr_one();
 #pragma unroll 1
     for (int e = 0; e < INV_E; e++) {

@@ -15,7 +15,8 @@ import plonk_gadgets_b200 as pg
 SEED = 0x706C6F6E6B5F6732
 R2 = np.array([[0xc999e990f3f29c6d, 0x2b6cedcb87925c23, 0x05d314967254398f, 0x0748d9d99f59ff11]], dtype=np.uint64)
 dev = torch.device("cuda", 0)
-stream = torch.cuda.current_stream(dev)
+stream = torch.cuda.Stream(device=dev)      # non-default stream shared by torch (events, tensor ops) and the engine's kernels
+torch.cuda.set_stream(stream)
 
 
 def to_mont(c, canonical_ints):

@@ -242,7 +242,9 @@ def test_max_bound_c3_and_scalar_c4_properties(oracle, torch_cuda):
     c.reset()
     a = torch.empty((n, 4), dtype=torch.int64, device="cuda"); b = torch.empty_like(a)
     c.synth(SEED, 41, 0, 0, a); c.synth(SEED, 42, 0, 0, b)
+    c.sync()                                 # the engine runs on its own stream: finish before torch touches the buffers
     b[0::2] = a[0::2]
+    torch.cuda.synchronize()
     va, vb = c.add_input(a), c.add_input(b)
     eq = pg.maybe_equal(c, va, vb)
     pg.is_non_zero(c, va, a)
