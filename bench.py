@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--check-mode", default="generic", choices=["generic", "sparse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check-shape", type=int, default=0, help="launch shape of the gate-check kernel (tuning knob)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,7 +178,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     mode = pg.CHECK_GENERIC if args.check_mode == "generic" else pg.CHECK_SPARSE
-    c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream)
+    c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream, check_shape=args.check_shape)
     assert stream.cuda_stream != 0
 
     # synthetic witnesses: even index uniform u64 (in range), odd index uniform Fr (out of range); per-rank stream id

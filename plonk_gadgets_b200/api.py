@@ -110,9 +110,9 @@ class AllocatedScalar:
 class StandardComposer:
     """Device-resident batched composer (dusk-plonk StandardComposer, arithmetic-row subset).  Fresh state: 3 rows, 5 variables."""
 
-    def __init__(self, device: int = 0, check_mode: int = CHECK_GENERIC, timing: bool = False, stream: int | None = None, _cdll=None):
+    def __init__(self, device: int = 0, check_mode: int = CHECK_GENERIC, timing: bool = False, stream: int | None = None, check_shape: int = 0, _cdll=None):
         self._L = _cdll if _cdll is not None else _lib.load()
-        cfg = _lib.pg_cfg(device=device, check_mode=check_mode, flags=F_TIMING if timing else 0, reserved=0, stream=stream)
+        cfg = _lib.pg_cfg(device=device, check_mode=check_mode, flags=F_TIMING if timing else 0, reserved=check_shape, stream=stream)
         ctx = C.c_void_p()
         rc = self._L.pg_ctx_create(C.byref(cfg), C.byref(ctx))
         if rc != 0:

@@ -26,6 +26,7 @@ public:
     bool timing_on = false;
     char errbuf[512] = {0};
     int sm_count = 0;
+    int check_shape = 0;
     struct Ev { cudaEvent_t a, b; int cls; uint64_t rows; };
     std::vector<Ev> events;
     std::vector<cudaEvent_t> ev_free;
@@ -47,8 +48,11 @@ public:
         if (cfg.stream) { stream = (cudaStream_t)cfg.stream; own_stream = false; }
         else { PG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
-        PG_CUDA(cudaFuncSetAttribute(k_check<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k_check<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        check_shape = cfg.reserved == 1 ? 1 : 0;
         return true;
     }
     void shutdown() {
@@ -137,8 +141,14 @@ public:
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         tic(CLS_CHECK, a.n_inst * a.n_rows);
-        if (a.mode == PG_CHECK_SPARSE) k_check<1><<<grid_for(a.n_inst), BLOCK, smem, stream>>>(a);
-        else k_check<0><<<grid_for(a.n_inst), BLOCK, smem, stream>>>(a);
+        const bool sparse = a.mode == PG_CHECK_SPARSE;
+        if (check_shape == 1) {
+            const unsigned grid = (unsigned)((a.n_inst + 127) / 128);
+            if (sparse) k_check<1, 1><<<grid, 128, smem, stream>>>(a); else k_check<0, 1><<<grid, 128, smem, stream>>>(a);
+        } else {
+            const unsigned grid = (unsigned)((a.n_inst + 255) / 256);
+            if (sparse) k_check<1, 0><<<grid, 256, smem, stream>>>(a); else k_check<0, 0><<<grid, 256, smem, stream>>>(a);
+        }
         toc();
         return launched("k_check");
     }

@@ -202,6 +202,19 @@ PG_HD Fr fr_mul_cios(const Fr& a, const Fr& b) {
     return fr_reduce_once(r);                                     // t[8] == 0 here because the running value stays < 2q
 }
 
+// m = -t0 mod 2^32 (t0 * q' with q' = 2^32 - 1).  On the device the negation is kept inside an asm statement: when the
+// compiler can see `0 - x` feeding the reduction rows it breaks every IMAD.WIDE.U32.X of the row into IMAD.X + IMAD.HI.U32.X
+// (6 multiplier-pipe cycles per product instead of 4; found in SASS, see profiles/README.md).
+PG_HD uint32_t mont_m(uint32_t t0) {
+#if defined(__CUDA_ARCH__)
+    uint32_t m;
+    asm("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(t0));
+    return m;
+#else
+    return 0u - t0;
+#endif
+}
+
 // ---- even/odd carry-chain primitives -------------------------------------------------------------------------------
 // Each primitive is ONE asm statement holding ONE complete carry chain, so the condition-code register never has to
 // survive between statements.  Host versions emulate the same dataflow with 64-bit arithmetic (tests/emu).
@@ -293,7 +306,7 @@ inline void merge_even_odd(uint32_t* r, const uint32_t* e, const uint32_t* o) {
 // because q7 < 2^31),  X += m*(q0,q2,q4,q6) (m*q0 = m), carry -> Y[7]
 #if defined(__CUDA_ARCH__)
 PG_D void red_rows(uint32_t* X, uint32_t* Y, const QRegs& q) {
-    const uint32_t m = 0u - X[0];
+    const uint32_t m = mont_m(X[0]);
     uint32_t lo, hi;
     asm("sub.cc.u32 %0, 0, %2;\n\tsubc.u32 %1, %2, 0;" : "=&r"(lo), "=&r"(hi) : "r"(m));
     asm("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %9;\n\tmadc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
@@ -308,7 +321,7 @@ PG_D void red_rows(uint32_t* X, uint32_t* Y, const QRegs& q) {
 }
 #else
 inline void red_rows(uint32_t* X, uint32_t* Y, const QRegs& q) {
-    const uint32_t m = 0u - X[0];
+    const uint32_t m = mont_m(X[0]);
     mad_row_nc(Y, q.v[1], q.v[3], q.v[5], q.v[7], m);
     mad_row(X, Y[7], q.v[0], q.v[2], q.v[4], q.v[6], m);
 }
@@ -377,7 +390,7 @@ PG_D void dmad_row_shift(uint32_t* o, uint32_t& e0, uint32_t& z, uint32_t x1, ui
 }
 // reduction rows for m = -X[0]:  Y += m*(q1,q3,q5,q7) with m*q1 = (m<<32) - m done by the adder;  X += m*(q0,q2,q4,q6) with m*q0 = m
 PG_D void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z, const QRegs& q) {
-    const uint32_t m = 0u - X[0];
+    const uint32_t m = mont_m(X[0]);
     uint32_t lo, hi;
     asm("sub.cc.u32 %0, 0, %2;\n\tsubc.u32 %1, %2, 0;" : "=&r"(lo), "=&r"(hi) : "r"(m));            // m*(2^32-1) = hi:lo
     asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, %10;\n\tmadc.lo.cc.u32 %2, %11, %14, %2;\n\tmadc.hi.cc.u32 %3, %11, %14, %3;\n\t"
@@ -429,7 +442,7 @@ inline void dmad_row_shift(uint32_t* o, uint32_t& e0, uint32_t& z, uint32_t x1, 
     for (int i = 0; i < 8; i++) o[i] = sh[i];
 }
 inline void dred_rows(uint32_t* X, uint32_t* Y, uint32_t& z, const QRegs& q) {
-    const uint32_t m = 0u - X[0];
+    const uint32_t m = mont_m(X[0]);
     const uint32_t qo[4] = {q.v[1], q.v[3], q.v[5], q.v[7]}, qe[4] = {q.v[0], q.v[2], q.v[4], q.v[6]};
     uint32_t c = emu_mad_chain(Y, qo, m, 0);
     if (z + c < z) PG_EMU_VIOLATION();

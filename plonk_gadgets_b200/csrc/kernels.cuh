@@ -109,17 +109,23 @@ struct SmemPool {
 
 // One instance per thread; the row template is walked by all threads in lock step (selector pool in shared memory,
 // template rows read with warp-uniform addresses), wire values come from the SoA variable table with coalesced loads.
-template <int MODE>
-__global__ void __launch_bounds__(BLOCK, 2) k_check(const CheckArgs a) {
+// Launch shapes of the gate-check kernel (pg_cfg.reserved selects one; 0 is the default):
+//   shape 0: 256 threads x 2 blocks/SM (<=128 registers, 16 warps/SM)      shape 1: 128 threads x 5 blocks/SM (<=102 registers, 20 warps/SM)
+template <int SHAPE> struct CheckShape;
+template <> struct CheckShape<0> { static constexpr int BLOCK_T = 256, MIN_BLOCKS = 2; };
+template <> struct CheckShape<1> { static constexpr int BLOCK_T = 128, MIN_BLOCKS = 5; };
+template <int MODE, int SHAPE>
+__global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>::MIN_BLOCKS) k_check(const CheckArgs a) {
+    constexpr int CHECK_BLOCK = CheckShape<SHAPE>::BLOCK_T;
     extern __shared__ __align__(16) uint32_t s_pool[];
     __shared__ uint32_t s_q[8];
-    for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += BLOCK) s_pool[t] = a.pool[t];
+    for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += CHECK_BLOCK) s_pool[t] = a.pool[t];
     if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
     __syncthreads();
     QRegs q;                                   // modulus limbs in vector registers (see QRegs in fr.cuh)
 #pragma unroll
     for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
-    const uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
     if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, q, i, first_bad); }
