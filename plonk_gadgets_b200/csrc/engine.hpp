@@ -64,7 +64,15 @@ public:
         auto it = pool_free.find(bytes);
         void* p;
         if (it != pool_free.end()) { p = it->second; pool_free.erase(it); }
-        else p = be.alloc(bytes);
+        else {
+            p = be.alloc(bytes);
+            if (!p && !pool_free.empty()) {          // out of memory with idle buffers parked in the pool: give them back and retry
+                be.sync();
+                for (auto& kv : pool_free) be.release(kv.second);
+                pool_free.clear();
+                p = be.alloc(bytes);
+            }
+        }
         if (p) pool_live[p] = bytes;
         return p;
     }
