@@ -35,6 +35,17 @@ IMAD_PER_ROW = 816               # 6 Fr mul x 136 32x32->64 multiply-accumulates
 PACKED_BYTES_PER_INSTANCE = 141 * 32 + 2 * 32   # variable table written by witness generation (141 Fr slots + 2 bit planes)
 
 
+def ncu_traffic(log2n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_check per launch, from the committed `ncu --set full` capture of this
+    command at the metric size (profiles/k_check_traffic.json); None for sizes that were not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_check_traffic.json")) as f:
+            t = json.load(f)
+        return t["bytes_per_launch"] if t.get("log2n") == log2n else None
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -286,10 +297,10 @@ def main():
                          "unit": "T 32x32->64 multiply-accumulates/s, ALGORITHMIC count 816 per gate eval (6 Fr mul x 136, SURVEY.md 8d)",
                          "frac": imad_achieved / wide_peak if wide_peak else None,
                          "peak_source": "measured in this run: IMAD.WIDE.U32 products on all SMs (pg_microbench mode 1); the kernel executes "
-                                        "~514 wide products per gate eval (dot-product reduction), so frac can exceed the executed-instruction share",
-                         "executed_wide_products_per_row": 514, "frac_executed": (rows_per_launch * 514 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
+                                        "496 wide products per gate eval (dot-product reduction), so frac can exceed the executed-instruction share",
+                         "executed_wide_products_per_row": 496, "frac_executed": (rows_per_launch * 496 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
                          "carry_chain_peak": chain_peak / 1e12, "imad_lo_peak": lo_peak / 1e12, "isolated_fr_mul_per_s": fr_mul_peak,
-                         "traffic": None, "ms_per_launch": check_ms,
+                         "traffic": ncu_traffic(args.log2n), "ms_per_launch": check_ms,
                          "hbm": {"kernel": "RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", "achieved": n * PACKED_BYTES_PER_INSTANCE / (wit_ms * 1e-3) / 1e9 if wit_ms else None,
                                  "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                                  "frac": (n * PACKED_BYTES_PER_INSTANCE / (wit_ms * 1e-3) / 1e9 / hbm_peak) if wit_ms else None, "ms_per_launch": wit_ms}},

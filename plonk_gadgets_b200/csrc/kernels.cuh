@@ -109,8 +109,8 @@ struct SmemPool {
 
 // One instance per thread; the row template is walked by all threads in lock step (selector pool in shared memory,
 // template rows read with warp-uniform addresses), wire values come from the SoA variable table with coalesced loads.
-// Launch shapes of the gate-check kernel (pg_cfg.reserved selects one; 0 is the default):
-//   shape 0: 256 threads x 2 blocks/SM (<=128 registers, 16 warps/SM)      shape 1: 128 threads x 5 blocks/SM (<=102 registers, 20 warps/SM)
+// Launch shapes of the gate-check kernel (pg_cfg.reserved = 1 selects the alternative):
+//   shape 1 (default): 128 threads x 5 blocks/SM (<=102 registers, 20 warps/SM)      shape 0: 256 threads x 2 blocks/SM (<=128 registers, 16 warps/SM)
 template <int SHAPE> struct CheckShape;
 template <> struct CheckShape<0> { static constexpr int BLOCK_T = 256, MIN_BLOCKS = 2; };
 template <> struct CheckShape<1> { static constexpr int BLOCK_T = 128, MIN_BLOCKS = 5; };
