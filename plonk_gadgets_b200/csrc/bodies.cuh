@@ -218,9 +218,11 @@ struct CheckArgs {
     int mode;
 };
 
-// GENERIC mode: one Montgomery multiplication for a*b, then the five selector products as ONE dot product with a single
-// interleaved reduction (fr_dot_wide): 64+48 + 5*64+48 = 480 wide multiplier instructions per row instead of 6*(64+64),
-// still without looking at the selector values.  The 9-limb result plus q_c and PI is tested for "0 mod q" directly.
+// GENERIC mode evaluates  a*(q_m*b + q_l) + q_r*b + q_o*c + q_4*d + q_c + PI  -- the gate polynomial with the bilinear term
+// factored, five multiplications instead of six, still without looking at any selector value: one Montgomery
+// multiplication u = q_m*b (fully reduced, + q_l without reduction), then the four remaining products as ONE dot product with
+// a single interleaved reduction (fr_dot_wide): 64+48 + 4*64+48 = 416 wide multiplier instructions per row instead of
+// 6*(64+64).  The 9-limb result plus q_c and PI is tested for "0 mod q" directly.
 // SPARSE mode: products whose selector is the constant 0 are skipped, selectors +-1 become additions.
 struct CheckBody {
     typedef CheckArgs Args;
@@ -231,15 +233,19 @@ struct CheckBody {
         for (uint32_t r = 0; r < a.n_rows; r++) {
             const DevRow row = a.rows[r];
             Fr w[5];
+            if (r + 1 < a.n_rows) {            // request the next row's wire values now: ~2000 multiplier cycles cover the latency
+                const uint4 nl = *reinterpret_cast<const uint4*>(a.rows[r + 1].loc);
+                loc_prefetch(a.tab, nl.x, i); loc_prefetch(a.tab, nl.y, i); loc_prefetch(a.tab, nl.z, i); loc_prefetch(a.tab, nl.w, i);
+            }
             w[1] = loc_load(a.tab, row.loc[0], i); w[2] = loc_load(a.tab, row.loc[1], i);
             w[3] = loc_load(a.tab, row.loc[2], i); w[4] = loc_load(a.tab, row.loc[3], i);
             uint32_t t[9];
             if (MODE == 0) {
-                w[0] = fr_mul_eo(w[1], w[2], q);                             // a*b
-                Fr sel[5];
+                Fr sel[4];
+                sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));   // q_m*b + q_l  (< 2q < 2^256)
 #pragma unroll
-                for (int k = 0; k < 5; k++) sel[k] = pool(row.sel[k]);       // q_m q_l q_r q_o q_4
-                fr_dot_wide<5>(t, w, sel, q);
+                for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
+                fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
             } else {
 #pragma unroll
                 for (int k = 0; k < 9; k++) t[k] = 0;
@@ -270,11 +276,11 @@ struct CheckRowsBody {
     PG_HD static uint32_t run(const Args& a, uint64_t i) {
         Fr w[5], sel[5];
         w[1] = aos_load(a.w, i); w[2] = aos_load(a.w, a.n + i); w[3] = aos_load(a.w, 2 * a.n + i); w[4] = aos_load(a.w, 3 * a.n + i);
-        w[0] = fr_mul(w[1], w[2]);
+        sel[0] = fr_add_noreduce(fr_mul(aos_load(a.sel, i), w[2]), aos_load(a.sel, a.n + i));         // q_m*b + q_l
 #pragma unroll
-        for (int k = 0; k < 5; k++) sel[k] = aos_load(a.sel, (uint64_t)k * a.n + i);
+        for (int k = 1; k < 4; k++) sel[k] = aos_load(a.sel, (uint64_t)(k + 1) * a.n + i);             // q_r q_o q_4
         uint32_t t[9];
-        fr_dot_wide<5>(t, w, sel);
+        fr_dot_wide<4>(t, w + 1, sel);
         add9_fr(t, aos_load(a.sel, 5 * a.n + i));
         if (a.pi) add9_fr(t, aos_load(a.pi, i));
         return limbs9_is_multiple_of_q(t) ? 0u : 1u;

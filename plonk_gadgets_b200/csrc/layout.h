@@ -85,6 +85,24 @@ PG_HD Fr loc_load(const DevTab* tabs, uint32_t loc, uint64_t i) {
     for (int k = 0; k < 8; k++) r.v[k] = b ? one.v[k] : 0u;
     return r;
 }
+// request the cache lines a later loc_load(tabs, loc, i) will touch (no destination registers)
+PG_HD void loc_prefetch(const DevTab* tabs, uint32_t loc, uint64_t i) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t kind = loc_kind(loc);
+    if (kind == LOC_ZERO) return;
+    const DevTab& t = tabs[loc_tab(loc)];
+    if (kind == LOC_FR) {
+        const uint32_t slot = loc_payload(loc);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.fr + (uint64_t)(2 * slot) * t.stride + i));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.fr + (uint64_t)(2 * slot + 1) * t.stride + i));
+    } else {
+        const uint32_t pb = loc_payload(loc);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.bits + (uint64_t)((pb >> 8) * 8 + ((pb & 255u) >> 5)) * t.stride + i));
+    }
+#else
+    (void)tabs; (void)loc; (void)i;
+#endif
+}
 // AoS scalar (caller memory: BlsScalar[n]) access
 PG_HD Fr aos_load(const uint4* p, uint64_t i) {
     const uint4 lo = p[2 * i], hi = p[2 * i + 1];
