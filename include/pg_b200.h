@@ -155,6 +155,23 @@ int pg_read_variables(pg_ctx *ctx, uint64_t var0, uint64_t cnt, pg_fr *dst, int 
 int pg_materialize_rows(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *w_idx, pg_fr *w_val, pg_fr *sel, pg_fr *pi,
                         int dst_on_device);
 
+/* ---- copy constraints ----------------------------------------------------------------------
+ * The permutation argument's input: dusk-plonk appends the four wire positions of every row to perm.variable_map[var]
+ * (add_variables_to_map, called by every gate method listed above) and links the positions of one Variable into a cycle.
+ * sigma is 4 x cnt, column-major: sigma[w*cnt + t] = successor, in that cycle, of wire w (0 w_l, 1 w_r, 2 w_o, 3 w_4) of
+ * row row0 + t, encoded as row*4 + wire.  A position whose Variable is used once maps to itself. */
+int pg_permutation(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *sigma, int dst_on_device);
+
+/* ---- wire format -------------------------------------------------------------------------
+ * BlsScalar::to_bytes / from_bytes [dusk_bytes::Serializable<32>, called at /root/reference/src/range.rs:163]: the canonical
+ * little-endian 32-byte encoding used for witness / selector / public-input dumps exchanged with Rust tooling.  n scalars;
+ * src and dst are both host (on_device == 0; dst may be unaligned-safe only for host) or both device pointers.
+ * from_bytes rejects encodings >= q like the reference: they are counted in *n_invalid (first index in *first_invalid, or
+ * UINT64_MAX) and decode to 0. */
+int pg_fr_to_bytes(pg_ctx *ctx, uint64_t n, const pg_fr *src, uint8_t *dst, int on_device);
+int pg_fr_from_bytes(pg_ctx *ctx, uint64_t n, const uint8_t *src, pg_fr *dst, int on_device, uint64_t *n_invalid,
+                     uint64_t *first_invalid);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------------------- */
 /* Deterministic synthetic scalars (SplitMix64 counter stream): kind 0 = uniform Fr (512-bit draw reduced mod q, as
  * BlsScalar::from_bytes_wide), kind 1 = uniform integer of `bits` bits (bits <= 254), kind 2 = even index kind 1 / odd

@@ -60,6 +60,9 @@ SIGNATURES = {
     "pg_col_read": (_i32, [_vp, _u64, _u64, _u64, _vp, _i32]),
     "pg_read_variables": (_i32, [_vp, _u64, _u64, _vp, _i32]),
     "pg_materialize_rows": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _i32]),
+    "pg_permutation": (_i32, [_vp, _u64, _u64, _vp, _i32]),
+    "pg_fr_to_bytes": (_i32, [_vp, _u64, _vp, _vp, _i32]),
+    "pg_fr_from_bytes": (_i32, [_vp, _u64, _vp, _vp, _i32, _pu64, _pu64]),
     "pg_synth": (_i32, [_vp, _u64, _u64, _u64, _i32, _u32, _vp]),
     "pg_get_timing": (_i32, [_vp, C.POINTER(pg_timing), _i32]),
     "pg_measure_imad_peak": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -227,6 +227,29 @@ class StandardComposer:
                                        p.ctypes.data_as(C.c_void_p) if p is not None else None, 0, C.byref(bad), C.byref(first)), "pg_check_rows")
         return bad.value, (None if first.value == UINT64_MAX else first.value)
 
+    def permutation(self, row0: int = 0, cnt: int | None = None) -> np.ndarray:
+        """(4, cnt) uint64: cycle successor (row*4 + wire) of every wire position -- the copy-constraint map of the composer."""
+        cnt = self.circuit_size() - row0 if cnt is None else cnt
+        out = np.empty((4, cnt), dtype=np.uint64)
+        self._ok(self._L.pg_permutation(self._ctx, row0, cnt, out.ctypes.data_as(C.c_void_p), 0), "pg_permutation")
+        return out
+
+    # -- wire format: canonical little-endian bytes <-> Montgomery limbs (BlsScalar::to_bytes / from_bytes)
+    def to_bytes(self, scalars) -> np.ndarray:
+        a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty((a.shape[0], 32), dtype=np.uint8)
+        self._ok(self._L.pg_fr_to_bytes(self._ctx, a.shape[0], a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 0), "pg_fr_to_bytes")
+        return out
+
+    def from_bytes(self, raw):
+        """(n,32) uint8 -> ((n,4) uint64 Montgomery limbs, number of rejected encodings >= q, index of the first one or None)."""
+        r = np.ascontiguousarray(raw, dtype=np.uint8).reshape(-1, 32)
+        out = np.empty((r.shape[0], 4), dtype=np.uint64)
+        bad, first = C.c_uint64(), C.c_uint64()
+        self._ok(self._L.pg_fr_from_bytes(self._ctx, r.shape[0], r.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 0,
+                                          C.byref(bad), C.byref(first)), "pg_fr_from_bytes")
+        return out, bad.value, (None if first.value == UINT64_MAX else first.value)
+
     # -- measurement helpers
     def synth(self, seed: int, stream: int, kind: int, bits: int, dst) -> None:
         p, dev, n, _ = _scalars(dst)

@@ -350,6 +350,85 @@ struct MaterializeBody {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------- permutation map
+// Copy constraints.  dusk-plonk records, for every row it appends, the four wire positions in
+// `perm.variable_map[var]` (add_variables_to_map: Left(n), Right(n), Output(n), Fourth(n) in that order) and later links the
+// positions of one Variable into a cycle: sigma(position_k) = position_{k+1 mod len}.  Here the cycle successor of every
+// wire position is computed directly from (template x instance) structure: the uses of a variable are its uses inside the
+// instance that allocated it (template order), followed by its uses in later calls that took its column as an operand, in
+// call order; the zero variable's uses are chained through every instance of every segment.
+// Positions are encoded as row*4 + wire (wire: 0 = w_l, 1 = w_r, 2 = w_o, 3 = w_4).
+constexpr uint32_t PERM_NONE = 0xffffffffu;
+struct PermCons { uint32_t seg, op; uint64_t inst_off, n; uint32_t next; uint32_t pad; };   // a consumer of a column: segment `seg` binds it as operand `op`
+struct PermSeg {
+    uint64_t base_row, n_inst; uint32_t n_rows, pad;
+    const uint32_t* next_in_inst;    // [n_rows*4]: next use (r*4+w) of the same variable inside the same instance, or PERM_NONE
+    const uint32_t* ref;             // [n_rows*4]: 0 = zero variable, 1+j = local variable j, 0x80000000|e = operand e (canonicalised)
+    const uint32_t* first_local;     // [n_vars]: first use of local variable j in its own instance, or PERM_NONE
+    const uint32_t* cons_head;       // [n_vars]: index+1 into the consumer array of the first consumer of local variable j's column, 0 = none
+    uint32_t first_op[4];            // first use of operand e inside an instance of this segment
+    uint32_t first_zero;             // first use of the zero variable inside an instance, or PERM_NONE
+    uint32_t next_zero_seg;          // next segment (index) with zero-variable uses and instances, or PERM_NONE
+    uint32_t op_src_seg[4], op_src_local[4]; uint64_t op_inst_off[4]; uint32_t op_cons_idx[4];   // operand e: source column and this segment's record in its consumer list
+};
+struct PermBody {
+    struct Args { const DevSeg* segs; const PermSeg* psegs; const PermCons* cons; uint32_t n_segs; uint32_t first_zero_seg; uint64_t row0; uint64_t n; unsigned long long* sigma; };
+
+    // first consumer at or after list position `c` (index+1) that covers source instance i: returns its first use as a global position
+    PG_HD static bool consumer_first_use(const Args& a, uint32_t c, uint64_t i, unsigned long long* out) {
+        while (c) {
+            const PermCons& k = a.cons[c - 1];
+            if (i >= k.inst_off && i - k.inst_off < k.n) {
+                const PermSeg& t = a.psegs[k.seg];
+                const uint32_t f = t.first_op[k.op];
+                *out = (t.base_row + (i - k.inst_off) * t.n_rows + (f >> 2)) * 4ull + (f & 3u);
+                return true;
+            }
+            c = k.next;
+        }
+        return false;
+    }
+    // first use overall of local variable j of instance i of segment s
+    PG_HD static unsigned long long variable_first_use(const Args& a, uint32_t s, uint32_t j, uint64_t i) {
+        const PermSeg& t = a.psegs[s];
+        const uint32_t f = t.first_local[j];
+        if (f != PERM_NONE) return (t.base_row + i * t.n_rows + (f >> 2)) * 4ull + (f & 3u);
+        unsigned long long out = 0;
+        consumer_first_use(a, t.cons_head[j], i, &out);          // a used variable without own uses has a consumer
+        return out;
+    }
+    PG_HD static void run(const Args& a, uint64_t tix) {
+        const uint64_t g = a.row0 + tix;
+        const uint32_t si = seg_find(a.segs, a.n_segs, g, true);
+        const PermSeg& s = a.psegs[si];
+        const uint64_t off = g - s.base_row;
+        const uint64_t i = off / s.n_rows; const uint32_t r = (uint32_t)(off % s.n_rows);
+#pragma unroll
+        for (uint32_t w = 0; w < 4; w++) {
+            const uint32_t ref = s.ref[r * 4 + w], nxt = s.next_in_inst[r * 4 + w];
+            unsigned long long out;
+            if (nxt != PERM_NONE) out = (s.base_row + i * s.n_rows + (nxt >> 2)) * 4ull + (nxt & 3u);
+            else if (ref == 0) {                                 // zero variable: next instance, next segment, or wrap to the very first use
+                if (i + 1 < s.n_inst) out = (s.base_row + (i + 1) * s.n_rows + (s.first_zero >> 2)) * 4ull + (s.first_zero & 3u);
+                else {
+                    const uint32_t ns = s.next_zero_seg != PERM_NONE ? s.next_zero_seg : a.first_zero_seg;
+                    const PermSeg& t = a.psegs[ns];
+                    out = (t.base_row + (t.first_zero >> 2)) * 4ull + (t.first_zero & 3u);
+                }
+            } else if (ref & 0x80000000u) {                      // operand: later consumers of the same column, else wrap to the variable's first use
+                const uint32_t e = ref & 3u;
+                const uint64_t i_src = i + s.op_inst_off[e];
+                if (!consumer_first_use(a, a.cons[s.op_cons_idx[e]].next, i_src, &out))
+                    out = variable_first_use(a, s.op_src_seg[e], s.op_src_local[e], i_src);
+            } else {                                             // own variable: consumers of its column, else wrap
+                const uint32_t j = ref - 1u;
+                if (!consumer_first_use(a, s.cons_head[j], i, &out)) out = variable_first_use(a, si, j, i);
+            }
+            a.sigma[(uint64_t)w * a.n + tix] = out;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------- synthetic inputs
 PG_HD uint64_t splitmix64_at(uint64_t seed, uint64_t index1) {   // output number index1 (1-based) of SplitMix64(seed)
     uint64_t z = seed + index1 * 0x9E3779B97F4A7C15ull;
@@ -382,6 +461,24 @@ struct SynthBody {
             out = fr_mul(fr_r2(), lo);
         }
         aos_store(a.dst, i, out);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- wire format
+// BlsScalar::to_bytes / from_bytes (dusk_bytes::Serializable<32>, used at /root/reference/src/range.rs:163): canonical
+// little-endian 32 bytes <-> Montgomery limbs.  from_bytes rejects encodings >= q (counted; the output is then 0).
+struct ToBytesBody {
+    struct Args { const uint4* src; uint4* dst; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t i) { aos_store(a.dst, i, fr_from_mont(aos_load(a.src, i))); }
+};
+struct FromBytesBody {
+    struct Args { const uint4* src; uint4* dst; uint64_t n; unsigned long long* counters; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const Fr c = aos_load(a.src, i);
+        const uint32_t q[8] = {PG_Q0, PG_Q1, PG_Q2, PG_Q3, PG_Q4, PG_Q5, PG_Q6, PG_Q7};
+        Fr d;
+        if (!fr_sub_limbs(d.v, c.v, q)) { counter_add(a.counters + CNT_N_ERR, 1ull); counter_min(a.counters + CNT_FIRST_ERR, (unsigned long long)i); aos_store(a.dst, i, fr_zero()); }
+        else aos_store(a.dst, i, fr_to_mont(c));
     }
 };
 

@@ -99,6 +99,19 @@ int pg_materialize_rows(pg_ctx* ctx, uint64_t row0, uint64_t cnt, uint64_t* w_id
     return ctx->e.materialize(row0, cnt, w_idx, w_val, sel, pi, dst_on_device);
 }
 
+int pg_permutation(pg_ctx* ctx, uint64_t row0, uint64_t cnt, uint64_t* sigma, int dst_on_device) {
+    PG_NEED_CTX(ctx);
+    return ctx->e.permutation(row0, cnt, sigma, dst_on_device);
+}
+int pg_fr_to_bytes(pg_ctx* ctx, uint64_t n, const pg_fr* src, uint8_t* dst, int on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, src, on_device); PG_ALIGNED(ctx, dst, on_device);
+    return ctx->e.convert(true, n, src, reinterpret_cast<pg_fr*>(dst), on_device, nullptr, nullptr);
+}
+int pg_fr_from_bytes(pg_ctx* ctx, uint64_t n, const uint8_t* src, pg_fr* dst, int on_device, uint64_t* n_invalid, uint64_t* first_invalid) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, src, on_device); PG_ALIGNED(ctx, dst, on_device);
+    return ctx->e.convert(false, n, reinterpret_cast<const pg_fr*>(src), dst, on_device, n_invalid, first_invalid);
+}
+
 int pg_synth(pg_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t n, int kind, uint32_t bits, pg_fr* dst_device) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst_device, 1);
     return ctx->e.synth(seed, stream, n, kind, bits, dst_device);

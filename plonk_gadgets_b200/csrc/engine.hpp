@@ -34,6 +34,7 @@ struct Segment {
     DevRow* d_rows = nullptr; uint32_t* d_varloc = nullptr; uint32_t* d_pool = nullptr;
     DevTab tabs[MAX_TABS] = {};
     std::vector<DevRow> rows;
+    std::vector<Column> operands;       // the columns bound as operands (for the permutation map)
 };
 
 inline Fr fr_from_pg(const pg_fr& x) {
@@ -156,7 +157,7 @@ public:
         if (T.n_planes) { s.bits = (uint32_t*)dalloc((size_t)T.n_planes * 8 * s.n_alloc * sizeof(uint32_t)); if (!s.bits) return fail(PG_ERR_OOM, "bit planes"); }
         if (T.n_params) { s.param = (uint4*)dalloc((size_t)T.n_params * 2 * s.n_alloc * sizeof(uint4)); if (!s.param) return fail(PG_ERR_OOM, "parameter table"); }
         s.tabs[0].fr = s.fr; s.tabs[0].bits = s.bits; s.tabs[0].stride = s.n_alloc; s.tabs[0].var_base = s.base_var; s.tabs[0].var_stride = T.n_vars;
-        for (uint32_t e = 0; e < n_operands; e++) s.tabs[e + 1] = view_of(operands[e]);
+        for (uint32_t e = 0; e < n_operands; e++) { s.tabs[e + 1] = view_of(operands[e]); s.operands.push_back(operands[e]); }
         s.rows.resize(T.rows.size());
         for (size_t r = 0; r < T.rows.size(); r++) {
             const RowT& src = T.rows[r]; DevRow d; memset(&d, 0, sizeof(d));
@@ -493,6 +494,87 @@ public:
         return PG_OK;
     }
 
+    // ------------------------------------------------------------------------------------------------ permutation map
+    // sigma[w][t] = cycle successor (row*4 + wire) of wire position (row0 + t, w); see PermBody.
+    int permutation(uint64_t row0, uint64_t cnt, uint64_t* sigma, int dst_on_device) {
+        if (row0 + cnt > n_rows || (cnt && !sigma)) return fail(PG_ERR_ARG, "permutation: range");
+        if (!cnt) return PG_OK;
+        const size_t S = segs.size();
+        std::vector<PermSeg> ps(S);
+        std::vector<PermCons> cons;
+        std::vector<std::vector<uint32_t>> next_in(S), ref(S), first_local(S), cons_head(S);
+        for (size_t k = 0; k < S; k++) cons_head[k].assign(segs[k].t.n_vars, 0);
+        uint32_t prev_zero_seg = PERM_NONE, first_zero_seg = PERM_NONE;
+        for (size_t k = 0; k < S; k++) {
+            const Segment& sg = segs[k]; const Template& T = sg.t;
+            PermSeg& p = ps[k]; memset(&p, 0, sizeof(p));
+            p.base_row = sg.base_row; p.n_inst = sg.n_inst; p.n_rows = (uint32_t)T.rows.size();
+            p.first_zero = PERM_NONE; p.next_zero_seg = PERM_NONE;
+            for (int e = 0; e < 4; e++) p.first_op[e] = PERM_NONE;
+            // canonical operand index: operands bound to the same column are one variable
+            uint32_t canon[4] = {0, 1, 2, 3};
+            for (size_t e = 0; e < sg.operands.size(); e++)
+                for (size_t f = 0; f < e; f++)
+                    if (sg.operands[f].seg == sg.operands[e].seg && sg.operands[f].local == sg.operands[e].local && sg.operands[f].inst_off == sg.operands[e].inst_off) { canon[e] = (uint32_t)f; break; }
+            const size_t NW = T.rows.size() * 4;
+            ref[k].assign(NW, 0); next_in[k].assign(NW, PERM_NONE); first_local[k].assign(T.n_vars, PERM_NONE);
+            std::vector<uint32_t> last_local(T.n_vars, PERM_NONE); uint32_t last_op[4] = {PERM_NONE, PERM_NONE, PERM_NONE, PERM_NONE}, last_zero = PERM_NONE;
+            for (size_t r = 0; r < T.rows.size(); r++)
+                for (uint32_t w = 0; w < 4; w++) {
+                    const WireRef& wr = T.rows[r].w[w]; const uint32_t pos = (uint32_t)(r * 4 + w);
+                    uint32_t* last; uint32_t* first;
+                    if (wr.src == 0 || (T.kind == G_PREAMBLE && wr.src == 1 && wr.idx == 0)) { ref[k][pos] = 0; last = &last_zero; first = &p.first_zero; }
+                    else if (wr.src == 1) { ref[k][pos] = 1 + wr.idx; last = &last_local[wr.idx]; first = &first_local[k][wr.idx]; }
+                    else { const uint32_t e = canon[wr.src - 2]; ref[k][pos] = 0x80000000u | e; last = &last_op[e]; first = &p.first_op[e]; }
+                    if (*last != PERM_NONE) next_in[k][*last] = pos; else *first = pos;
+                    *last = pos;
+                }
+            if (sg.n_inst && p.first_zero != PERM_NONE) {
+                if (prev_zero_seg != PERM_NONE) ps[prev_zero_seg].next_zero_seg = (uint32_t)k; else first_zero_seg = (uint32_t)k;
+                prev_zero_seg = (uint32_t)k;
+            }
+            // register this segment as a consumer of its operand columns (call order = list order)
+            for (size_t e = 0; e < sg.operands.size(); e++) {
+                p.op_src_seg[e] = sg.operands[e].seg; p.op_src_local[e] = sg.operands[e].local; p.op_inst_off[e] = sg.operands[e].inst_off;
+                if (canon[e] != e) { p.op_cons_idx[e] = p.op_cons_idx[canon[e]]; continue; }
+                if (p.first_op[e] == PERM_NONE || !sg.n_inst) { p.op_cons_idx[e] = 0; continue; }     // operand never appears on a wire / no instances
+                PermCons c; memset(&c, 0, sizeof(c));
+                c.seg = (uint32_t)k; c.op = (uint32_t)e; c.inst_off = sg.operands[e].inst_off; c.n = sg.n_inst; c.next = 0;
+                cons.push_back(c);
+                const uint32_t me = (uint32_t)cons.size();                                              // index + 1
+                uint32_t* head = &cons_head[sg.operands[e].seg][sg.operands[e].local];
+                if (!*head) *head = me;
+                else { uint32_t t = *head; while (cons[t - 1].next) t = cons[t - 1].next; cons[t - 1].next = me; }
+                p.op_cons_idx[e] = me - 1;
+            }
+        }
+        // upload
+        auto up = [&](const void* src, size_t bytes) -> void* {
+            void* d = dalloc(bytes ? bytes : 16); if (!d) return nullptr;
+            scratch.push_back(d);
+            if (bytes && !be.h2d(d, src, bytes)) return nullptr;
+            return d;
+        };
+        for (size_t k = 0; k < S; k++) {
+            ps[k].next_in_inst = (const uint32_t*)up(next_in[k].data(), next_in[k].size() * 4);
+            ps[k].ref = (const uint32_t*)up(ref[k].data(), ref[k].size() * 4);
+            ps[k].first_local = (const uint32_t*)up(first_local[k].data(), first_local[k].size() * 4);
+            ps[k].cons_head = (const uint32_t*)up(cons_head[k].data(), cons_head[k].size() * 4);
+            if (!ps[k].next_in_inst || !ps[k].ref || !ps[k].first_local || !ps[k].cons_head) return fail(PG_ERR_OOM, "permutation tables");
+        }
+        if (cons.empty()) { PermCons c; memset(&c, 0, sizeof(c)); cons.push_back(c); }
+        const PermSeg* d_ps = (const PermSeg*)up(ps.data(), ps.size() * sizeof(PermSeg));
+        const PermCons* d_cons = (const PermCons*)up(cons.data(), cons.size() * sizeof(PermCons));
+        if (!d_ps || !d_cons) return fail(PG_ERR_OOM, "permutation tables");
+        unsigned long long* out = dst_on_device ? reinterpret_cast<unsigned long long*>(sigma) : (unsigned long long*)dalloc(4 * cnt * sizeof(uint64_t));
+        if (!out) return fail(PG_ERR_OOM, "permutation buffer");
+        if (!dst_on_device) scratch.push_back(out);
+        if (!be.sync()) return fail(PG_ERR_CUDA, "sync");            // the host vectors above are the sources of the copies
+        PermBody::Args a{d_segs, d_ps, d_cons, (uint32_t)dsegs.size(), first_zero_seg, row0, cnt, out};
+        if (!be.template run_simple<PermBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "permutation kernel");
+        return dst_on_device ? PG_OK : deliver(sigma, out, 4 * cnt * sizeof(uint64_t), 0);
+    }
+
     // ------------------------------------------------------------------------------------------------ helpers
     int synth(uint64_t seed, uint64_t stream, uint64_t n, int kind, uint32_t bits, pg_fr* dst) {
         if (n && !dst) return fail(PG_ERR_ARG, "synth: null destination");
@@ -500,6 +582,30 @@ public:
         SynthBody::Args a{seed ^ (stream * 0xD1342543DE82EF95ull), n, kind, bits, reinterpret_cast<uint4*>(dst)};
         if (n && !be.template run_simple<SynthBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "synth kernel");
         return PG_OK;
+    }
+    // canonical little-endian bytes <-> Montgomery limbs, n scalars; src/dst both host or both device
+    int convert(bool to_bytes, uint64_t n, const pg_fr* src, pg_fr* dst, int on_device, uint64_t* n_invalid, uint64_t* first_invalid) {
+        if (n_invalid) *n_invalid = 0;
+        if (first_invalid) *first_invalid = ~0ull;
+        if (!n) return PG_OK;
+        if (!src || !dst) return fail(PG_ERR_ARG, "convert: null argument");
+        int rc; const uint4* ds = stage(src, n, on_device, &rc); if (!ds) return rc;
+        uint4* dd = on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(n * sizeof(pg_fr));
+        if (!dd) return fail(PG_ERR_OOM, "convert buffer");
+        if (!on_device) scratch.push_back(dd);
+        if (to_bytes) {
+            ToBytesBody::Args a{ds, dd, n};
+            if (!be.template run_simple<ToBytesBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "to_bytes kernel");
+        } else {
+            if ((rc = reset_counters())) return rc;
+            FromBytesBody::Args a{ds, dd, n, d_counters};
+            if (!be.template run_simple<FromBytesBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "from_bytes kernel");
+            unsigned long long c[CNT_WORDS];
+            if ((rc = read_counters(c))) return rc;
+            if (n_invalid) *n_invalid = c[CNT_N_ERR];
+            if (first_invalid) *first_invalid = c[CNT_N_ERR] ? c[CNT_FIRST_ERR] : ~0ull;
+        }
+        return on_device ? PG_OK : deliver(dst, dd, n * sizeof(pg_fr), 0);
     }
     int fr_op(int op, uint64_t n, const pg_fr* a, const pg_fr* b, pg_fr* out) {
         if (!n) return PG_OK;

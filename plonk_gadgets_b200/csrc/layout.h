@@ -58,18 +58,22 @@ enum : uint16_t { POOL_ZERO = 0, POOL_ONE = 1, POOL_MINUS_ONE = 2 };
 
 // ---- table accessors ------------------------------------------------------------------------------------------------
 PG_HD Fr tab_load_fr(const uint4* base, uint64_t stride, uint32_t slot, uint64_t i) {
-    const uint4 lo = base[(uint64_t)(2 * slot) * stride + i];
-    const uint4 hi = base[(uint64_t)(2 * slot + 1) * stride + i];
+    // (base + i) first: the per-thread part is loop-invariant and the slot offset is warp-uniform (uniform datapath), so the
+    // address costs adder instructions instead of a 64-bit IMAD on the multiplier pipe
+    const uint4* p = base + i;
+    const uint4 lo = p[(uint64_t)(2 * slot) * stride];
+    const uint4 hi = p[(uint64_t)(2 * slot + 1) * stride];
     Fr r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
     return r;
 }
 PG_HD void tab_store_fr(uint4* base, uint64_t stride, uint32_t slot, uint64_t i, const Fr& v) {
-    base[(uint64_t)(2 * slot) * stride + i] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-    base[(uint64_t)(2 * slot + 1) * stride + i] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    uint4* p = base + i;
+    p[(uint64_t)(2 * slot) * stride] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    p[(uint64_t)(2 * slot + 1) * stride] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
 }
 PG_HD uint32_t tab_load_bit(const uint32_t* bits, uint64_t stride, uint32_t plane_bit, uint64_t i) {
     const uint32_t plane = plane_bit >> 8, bit = plane_bit & 255u;
-    const uint32_t w = bits[(uint64_t)(plane * 8 + (bit >> 5)) * stride + i];
+    const uint32_t w = (bits + i)[(uint64_t)(plane * 8 + (bit >> 5)) * stride];
     return (w >> (bit & 31u)) & 1u;
 }
 // value of a located variable for instance i
@@ -93,11 +97,12 @@ PG_HD void loc_prefetch(const DevTab* tabs, uint32_t loc, uint64_t i) {
     const DevTab& t = tabs[loc_tab(loc)];
     if (kind == LOC_FR) {
         const uint32_t slot = loc_payload(loc);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.fr + (uint64_t)(2 * slot) * t.stride + i));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.fr + (uint64_t)(2 * slot + 1) * t.stride + i));
+        const uint4* p = t.fr + i;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (uint64_t)(2 * slot) * t.stride));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (uint64_t)(2 * slot + 1) * t.stride));
     } else {
         const uint32_t pb = loc_payload(loc);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.bits + (uint64_t)((pb >> 8) * 8 + ((pb & 255u) >> 5)) * t.stride + i));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"((t.bits + i) + (uint64_t)((pb >> 8) * 8 + ((pb & 255u) >> 5)) * t.stride));
     }
 #else
     (void)tabs; (void)loc; (void)i;

@@ -125,6 +125,12 @@ def main():
     ms, tim, _ = timed(c, mat)
     emit("materialize 2^22 rows (4 wire ids + 4 wire values + 6 selectors + PI = 384 B/row) to device buffers", cnt, ms, tim,
          {"GB_per_s_written": cnt * 384 / (ms * 1e-3) / 1e9})
+    sig = torch.empty((4, cnt), dtype=torch.int64, device=dev)
+
+    def perm():
+        c._ok(c._L.pg_permutation(c._ctx, 3, cnt, C.c_void_p(sig.data_ptr()), 1), "pg_permutation")
+    ms, tim, _ = timed(c, perm)
+    emit("permutation map (copy-constraint cycle successors) of 2^22 rows, 32 B/row written", cnt, ms, tim, {"GB_per_s_written": cnt * 32 / (ms * 1e-3) / 1e9})
     vars_buf = torch.empty((cnt, 4), dtype=torch.int64, device=dev)
 
     def rv():

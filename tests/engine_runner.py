@@ -7,7 +7,7 @@ import plonk_gadgets_b200 as pg
 from tests.programs import SEL_NAMES, Snapshot, _vals, unsat_rows
 
 
-def run_engine(program, make_composer, ob) -> Snapshot:
+def run_engine(program, make_composer, ob, return_composer: bool = False):
     """`make_composer()` -> plonk_gadgets_b200.StandardComposer; `ob` = oracle.binding (only used to convert between
     canonical integers and Montgomery limbs -- the engine's verdict and dumps are its own)."""
     c = make_composer()
@@ -37,7 +37,8 @@ def run_engine(program, make_composer, ob) -> Snapshot:
             c.constrain_to_constant(cols[op["a"]], ob.from_ints(_vals(op, "constant")), pi)
         else:
             raise ValueError(kind)
-    return snapshot_of_engine(c, cols, error, ob)
+    snap = snapshot_of_engine(c, cols, error, ob)
+    return (snap, c) if return_composer else snap
 
 
 def snapshot_of_engine(c, cols, error, ob) -> Snapshot:

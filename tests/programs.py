@@ -128,7 +128,7 @@ def snapshot_of_oracle(c, cols=None, error=None) -> Snapshot:
     return snap
 
 
-def run_oracle(program) -> Snapshot:
+def run_oracle(program, return_composer: bool = False):
     from oracle import binding as ob
     c = ob.Composer()
     cols, error = {}, None
@@ -166,7 +166,8 @@ def run_oracle(program) -> Snapshot:
             c.constrain_to_constant_batch(a, bounds(op, "constant", len(a)), pi)
         else:
             raise ValueError(kind)
-    return snapshot_of_oracle(c, {k: [int(x) for x in v] for k, v in cols.items()}, error)
+    snap = snapshot_of_oracle(c, {k: [int(x) for x in v] for k, v in cols.items()}, error)
+    return (snap, c) if return_composer else snap
 
 
 def unsat_rows(s: Snapshot) -> list:
@@ -205,3 +206,19 @@ def synth_wide(stream: int, n: int) -> list:
             v |= int(row[j]) << (64 * j)
         out.append(v % Q)
     return out
+
+
+def expected_sigma(oracle_composer) -> np.ndarray:
+    """Copy-constraint cycles from the oracle's perm.variable_map: (4, n_rows) uint64, sigma[w, r] = successor (row*4 + wire)
+    of wire position (r, w) in the cycle of its Variable (positions in insertion order, last wraps to first)."""
+    n = oracle_composer.n
+    sigma = np.zeros((4, n), dtype=np.uint64)
+    seen = 0
+    for v in range(oracle_composer.n_vars):
+        uses = oracle_composer.perm_of(v)
+        for k, (r, w) in enumerate(uses):
+            nr, nw = uses[(k + 1) % len(uses)]
+            sigma[w, r] = nr * 4 + nw
+        seen += len(uses)
+    assert seen == 4 * n
+    return sigma

@@ -112,3 +112,46 @@ def test_fr_even_odd_multiplier_host_emulation(fr_emu):
         out = np.zeros_like(A)
         getattr(fr_emu, fn)(C.c_uint64(len(pairs)), vp(A), vp(B), vp(out))
         assert unpack(out) == [f(a, b) for a, b in pairs], fn
+
+
+def test_emu_wire_format(emu, oracle):
+    """to_bytes / from_bytes (canonical LE 32 bytes) against the oracle's, including rejection of encodings >= q."""
+    import random
+    rng = random.Random(3)
+    vals = [0, 1, Q - 1, 2 ** 255 % Q] + [rng.randrange(Q) for _ in range(50)]
+    c = pg.StandardComposer(_cdll=emu)
+    m = oracle.from_ints(vals)
+    raw = c.to_bytes(m)
+    assert [int.from_bytes(raw[i].tobytes(), "little") for i in range(len(vals))] == vals
+    back, bad, first = c.from_bytes(raw)
+    assert bad == 0 and first is None and (back == m).all()
+    bogus = raw.copy()
+    bogus[7] = np.frombuffer(Q.to_bytes(32, "little"), dtype=np.uint8)            # == q: rejected
+    bogus[9] = 0xFF                                                                 # 2^256-1: rejected
+    back, bad, first = c.from_bytes(bogus)
+    assert (bad, first) == (2, 7) and (back[7] == 0).all() and (back[9] == 0).all() and (back[8] == m[8]).all()
+
+
+def test_emu_permutation_map(emu, golden, oracle):
+    """pg_permutation (copy-constraint cycles) against the oracle's perm.variable_map on every golden program, whole range and
+    a sub-range."""
+    from tests.programs import expected_sigma
+    for name, spec in golden.items():
+        so, oc = run_oracle(spec["program"], return_composer=True)
+        se, c = run_engine(spec["program"], lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
+        exp = expected_sigma(oc)
+        got = c.permutation()
+        assert got.shape == exp.shape and (got == exp).all(), name
+        if so.n_rows > 10:
+            assert (c.permutation(5, so.n_rows - 9) == exp[:, 5:so.n_rows - 4]).all(), name
+
+
+def test_emu_permutation_same_column_twice(emu, oracle):
+    """maybe_equal(a, a) / select(x, x): both operands are one Variable, its uses must form one cycle."""
+    from tests.programs import expected_sigma
+    prog = [dict(op="add_input", values=[hx(5), hx(0), hx(1)]), dict(op="maybe_equal", a=0, b=0), dict(op="select_one", y=1, select=1),
+            dict(op="select_zero", x=0, select=0), dict(op="constrain_to_constant", a=1, constant=hx(1))]
+    so, oc = run_oracle(prog, return_composer=True)
+    se, c = run_engine(prog, lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
+    assert se.digest() == so.digest()
+    assert (c.permutation() == expected_sigma(oc)).all()

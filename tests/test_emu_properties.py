@@ -62,11 +62,13 @@ def test_random_gadget_compositions(emu, oracle, n, vals, seq, seed):
             prog.append(dict(op=op, max=hx(2 ** int(rng.integers(1, 250))), witness=a)); cols.append(len(prog) - 1)
         else:
             prog.append(dict(op="constrain_to_constant", a=a, constant=hx(int(rng.integers(0, 3))), pi=[hx(v) for v in vals[:n]] if seed % 2 else None))
-    so = run_oracle(prog)
-    se = run_engine(prog, lambda: pg.StandardComposer(_cdll=emu), oracle)
+    from tests.programs import expected_sigma
+    so, oc = run_oracle(prog, return_composer=True)
+    se, c = run_engine(prog, lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
     assert se.error == so.error
     assert se.digest() == so.digest()
     assert se.unsat == so.unsat
+    assert (c.permutation() == expected_sigma(oc)).all()          # copy-constraint cycles
 
 
 @settings(max_examples=20, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
