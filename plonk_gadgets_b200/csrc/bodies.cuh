@@ -322,10 +322,16 @@ struct ColReadBody {   // one column (strided variables) -> contiguous scalars
     PG_HD static void run(const Args& a, uint64_t i) { aos_store(a.dst, i, loc_load(&a.tab, a.loc, i)); }
 };
 
+// Expands rows into the reference composer's representation.  Outputs are column-major with `stride` rows per column; this
+// launch covers rows [row0, row0 + n) and writes them at column offsets [out_off, out_off + n).  `what` selects the columns:
+// the tiled kernel (kernels.cuh, k_materialize_tiled) produces wire values and the five instance-independent selector columns
+// for whole instances; this body then only adds w_idx, q_c and PI for those rows, and everything for the ragged ends.
+enum : uint32_t { MAT_W_IDX = 1u, MAT_W_VAL = 2u, MAT_SEL5 = 4u, MAT_QC = 8u, MAT_PI = 16u, MAT_ALL = 31u };
 struct MaterializeBody {
-    struct Args { const DevSeg* segs; uint32_t n_segs; uint64_t row0; uint64_t n; unsigned long long* w_idx; uint4* w_val; uint4* sel; uint4* pi; };
+    struct Args { const DevSeg* segs; uint32_t n_segs; uint32_t what; uint64_t row0; uint64_t n; uint64_t stride; uint64_t out_off;
+                  unsigned long long* w_idx; uint4* w_val; uint4* sel; uint4* pi; };
     PG_HD static void run(const Args& a, uint64_t t) {
-        const uint64_t g = a.row0 + t;
+        const uint64_t g = a.row0 + t, o = a.out_off + t;
         const DevSeg& s = a.segs[seg_find(a.segs, a.n_segs, g, true)];
         const uint64_t off = g - s.base_row;
         const uint64_t i = off / s.n_rows; const uint32_t r = (uint32_t)(off % s.n_rows);
@@ -333,22 +339,25 @@ struct MaterializeBody {
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             const uint32_t loc = row.loc[w];
-            if (a.w_idx) {
+            if (a.w_idx && (a.what & MAT_W_IDX)) {
                 const DevTab& tb = s.tab[loc_tab(loc)];
-                a.w_idx[(uint64_t)w * a.n + t] = loc_kind(loc) == LOC_ZERO ? 0ull : tb.var_base + i * tb.var_stride + row.var[w];
+                a.w_idx[(uint64_t)w * a.stride + o] = loc_kind(loc) == LOC_ZERO ? 0ull : tb.var_base + i * tb.var_stride + row.var[w];
             }
-            if (a.w_val) aos_store(a.w_val, (uint64_t)w * a.n + t, loc_load(s.tab, loc, i));
+            if (a.w_val && (a.what & MAT_W_VAL)) aos_store(a.w_val, (uint64_t)w * a.stride + o, loc_load(s.tab, loc, i));
         }
-        if (a.sel) {
+        if (a.sel && (a.what & MAT_SEL5)) {
 #pragma unroll
-            for (int k = 0; k < 5; k++) aos_store(a.sel, (uint64_t)k * a.n + t, pool_load(s.pool, row.sel[k]));
-            aos_store(a.sel, 5ull * a.n + t, row.qc_param >= 0 ? tab_load_fr(s.param, s.param_stride, (uint32_t)row.qc_param, i)
-                                                               : pool_load(s.pool, row.sel[5]));
+            for (int k = 0; k < 5; k++) aos_store(a.sel, (uint64_t)k * a.stride + o, pool_load(s.pool, row.sel[k]));
         }
-        if (a.pi) aos_store(a.pi, t, row.pi_param >= 0 ? tab_load_fr(s.param, s.param_stride, (uint32_t)row.pi_param, i)
-                                                       : pool_load(s.pool, row.pi_sel));
+        if (a.sel && (a.what & MAT_QC))
+            aos_store(a.sel, 5ull * a.stride + o, row.qc_param >= 0 ? tab_load_fr(s.param, s.param_stride, (uint32_t)row.qc_param, i)
+                                                                   : pool_load(s.pool, row.sel[5]));
+        if (a.pi && (a.what & MAT_PI)) aos_store(a.pi, o, row.pi_param >= 0 ? tab_load_fr(s.param, s.param_stride, (uint32_t)row.pi_param, i)
+                                                                          : pool_load(s.pool, row.pi_sel));
     }
 };
+// whole instances [inst0, inst0 + n_inst) of ONE segment, written from column offset out_off (row of instance inst0, local row 0)
+struct MatTileArgs { DevSeg seg; uint64_t inst0, n_inst; uint64_t stride, out_off; uint4* w_val; uint4* sel; };
 
 // ---------------------------------------------------------------------------------------------------- permutation map
 // Copy constraints.  dusk-plonk records, for every row it appends, the four wire positions in

@@ -152,6 +152,13 @@ public:
         toc();
         return launched("k_check");
     }
+    bool run_mat_tiled(const MatTileArgs& a) {
+        const uint64_t tiles = ((a.n_inst + MT_I - 1) / MT_I) * ((a.seg.n_rows + MT_R - 1) / MT_R);
+        tic(CLS_OTHER, 0);
+        k_materialize_tiled<<<(unsigned)tiles, BLOCK, 0, stream>>>(a);
+        toc();
+        return launched("k_materialize_tiled");
+    }
     bool run_check_rows(const CheckRowsBody::Args& a) {
         tic(CLS_CHECK, a.n);
         k_check_rows<<<grid_for(a.n), BLOCK, 0, stream>>>(a);

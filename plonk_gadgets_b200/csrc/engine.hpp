@@ -15,6 +15,7 @@
 //   bool run_check(const CheckArgs&), bool run_check_rows(const CheckRowsBody::Args&)
 //   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), bool ubench(int, double*), timing(pg_timing*, bool reset)
 #pragma once
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -483,8 +484,30 @@ public:
         d_sel = (uint4*)buf(sel, 6 * cnt * sizeof(pg_fr));
         d_pi = (uint4*)buf(pi, cnt * sizeof(pg_fr));
         if ((w_idx && !d_idx) || (w_val && !d_val) || (sel && !d_sel) || (pi && !d_pi)) return fail(PG_ERR_OOM, "materialize buffers");
-        MaterializeBody::Args a{d_segs, (uint32_t)dsegs.size(), row0, cnt, d_idx, d_val, d_sel, d_pi};
-        if (!be.template run_simple<MaterializeBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "materialize kernel");
+        // per segment: whole instances go through the tiled kernel (wire values + the 5 instance-independent selector columns),
+        // the simple body adds w_idx / q_c / PI for them and does everything for the ragged ends of the requested range
+        auto simple = [&](uint64_t r0, uint64_t n, uint32_t what) -> bool {
+            if (!n || !what) return true;
+            MaterializeBody::Args a{d_segs, (uint32_t)dsegs.size(), what, r0, n, cnt, r0 - row0, d_idx, d_val, d_sel, d_pi};
+            return be.template run_simple<MaterializeBody>(a, n, CLS_OTHER);
+        };
+        const uint64_t row_end = row0 + cnt;
+        for (size_t k = 0; k < segs.size(); k++) {
+            const Segment& sg = segs[k];
+            const uint64_t nr = sg.t.rows.size();
+            if (!nr || !sg.n_inst) continue;
+            const uint64_t s_lo = std::max(row0, sg.base_row), s_hi = std::min(row_end, sg.base_row + sg.n_inst * nr);
+            if (s_lo >= s_hi) continue;
+            const uint64_t iA = (s_lo - sg.base_row + nr - 1) / nr, iB = (s_hi - sg.base_row) / nr;      // whole instances [iA, iB)
+            const bool tiled = (d_val || d_sel) && iB > iA && iB - iA >= 32 && nr >= 8;
+            if (!tiled) { if (!simple(s_lo, s_hi - s_lo, MAT_ALL)) return fail(PG_ERR_CUDA, "materialize kernel"); continue; }
+            const uint64_t t_lo = sg.base_row + iA * nr, t_hi = sg.base_row + iB * nr;
+            MatTileArgs ta; memset(&ta, 0, sizeof(ta));
+            ta.seg = dsegs[k]; ta.inst0 = iA; ta.n_inst = iB - iA; ta.stride = cnt; ta.out_off = t_lo - row0; ta.w_val = d_val; ta.sel = d_sel;
+            if (!be.run_mat_tiled(ta)) return fail(PG_ERR_CUDA, "tiled materialize kernel");
+            if (!simple(s_lo, t_lo - s_lo, MAT_ALL) || !simple(t_hi, s_hi - t_hi, MAT_ALL) ||
+                !simple(t_lo, t_hi - t_lo, MAT_W_IDX | MAT_QC | MAT_PI)) return fail(PG_ERR_CUDA, "materialize kernel");
+        }
         if (dst_on_device) return PG_OK;
         int rc = PG_OK;
         if (w_idx && (rc = deliver(w_idx, d_idx, 4 * cnt * sizeof(uint64_t), 0))) return rc;

@@ -158,6 +158,71 @@ __global__ void __launch_bounds__(BLOCK) k_check_rows(const CheckRowsBody::Args 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- tiled materialisation
+// Wire values and selector columns of whole instances in the reference composer's row order (pure HBM streaming).
+// A block owns a tile of 32 instances x 32 template rows.
+//   wire values: read with lanes = instances (one slot of the SoA table -> 512 contiguous bytes per half), transposed through
+//                padded shared memory, written with lanes = rows (the 32 rows of one instance are 1 KiB contiguous in every
+//                output column) -- both sides fully coalesced 128-bit accesses;
+//   selectors  : instance-independent.  The tile's 32 x 32 B selector values are staged once in shared memory and replicated
+//                into the 32 instances' output runs with TMA bulk copies (cp.async.bulk shared -> global, 1 KiB each): no
+//                register traffic at all for 5/11 of the bytes written.
+constexpr int MT_I = 32, MT_R = 32;                  // instances x rows per tile
+constexpr int MT_PITCH = MT_I * 2 + 1;               // uint4 per staged row (+1: conflict-free transposed reads)
+__global__ void __launch_bounds__(BLOCK) k_materialize_tiled(const MatTileArgs a) {
+    __shared__ __align__(128) uint4 s_val[MT_R * MT_PITCH];          // [row][instance][half]
+    __shared__ __align__(128) uint4 s_sel[5][MT_R * 2];              // [selector][row][half]
+    const DevSeg& s = a.seg;
+    const uint32_t tiles_r = (s.n_rows + MT_R - 1) / MT_R;
+    const uint64_t ti = blockIdx.x / tiles_r; const uint32_t tr = blockIdx.x % tiles_r;
+    const uint64_t i_lo = a.inst0 + ti * MT_I;                        // first instance of the tile
+    const uint32_t r_lo = tr * MT_R;
+    const uint32_t n_i = (uint32_t)min((uint64_t)MT_I, a.inst0 + a.n_inst - i_lo), n_r = min((uint32_t)MT_R, s.n_rows - r_lo);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // output column offset of (instance i_lo + ii, row r_lo + rr):
+    const uint64_t o_base = a.out_off + (i_lo - a.inst0) * (uint64_t)s.n_rows + r_lo;
+
+    if (a.sel) {                                                      // stage the tile's selector values: 5 x n_r scalars
+        for (uint32_t t = threadIdx.x; t < 5 * n_r; t += BLOCK) {
+            const uint32_t k = t / n_r, rr = t % n_r;
+            const Fr v = pool_load(s.pool, s.rows[r_lo + rr].sel[k]);
+            s_sel[k][2 * rr] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]); s_sel[k][2 * rr + 1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+        }
+    }
+    for (int w = 0; w < 4; w++) {
+        if (a.w_val) {
+            __syncthreads();                                          // previous transposed reads of s_val are done
+            for (uint32_t rr = warp; rr < n_r; rr += NWARPS) {        // lanes = instances
+                if ((uint32_t)lane < n_i) {
+                    const Fr v = loc_load(s.tab, s.rows[r_lo + rr].loc[w], i_lo + lane);
+                    s_val[rr * MT_PITCH + 2 * lane] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+                    s_val[rr * MT_PITCH + 2 * lane + 1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+                }
+            }
+            __syncthreads();
+            for (uint32_t ii = warp; ii < n_i; ii += NWARPS) {        // lanes = rows: 1 KiB contiguous per instance
+                if ((uint32_t)lane < n_r) {
+                    uint4* dst = a.w_val + 2 * ((uint64_t)w * a.stride + o_base + (uint64_t)ii * s.n_rows + lane);
+                    dst[0] = s_val[lane * MT_PITCH + 2 * ii]; dst[1] = s_val[lane * MT_PITCH + 2 * ii + 1];
+                }
+            }
+        }
+    }
+    if (a.sel) {
+        __syncthreads();                                              // s_sel complete
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // make the generic-proxy smem writes visible to the bulk-copy engine
+        // 5 selector columns x n_i instances: one bulk copy of n_r*32 bytes each, issued by distinct threads
+        for (uint32_t t = threadIdx.x; t < 5 * n_i; t += BLOCK) {
+            const uint32_t k = t / n_i, ii = t % n_i;
+            uint4* dst = a.sel + 2 * ((uint64_t)k * a.stride + o_base + (uint64_t)ii * s.n_rows);
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(&s_sel[k][0]);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(n_r * 32u) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // smem may be released only after the engine has read it
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- pipe micro-benchmarks
 // Roofline denominators and instruction-cost evidence, measured on the device the engine runs on.  Every chain feeds its
 // own previous result back into a multiplier/adder INPUT, so ptxas can neither hoist, share nor re-associate the

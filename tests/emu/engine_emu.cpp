@@ -61,6 +61,16 @@ public:
         }
         return true;
     }
+    bool run_mat_tiled(const MatTileArgs& a) {      // same outputs as the tiled CUDA kernel, element by element
+        const DevSeg& s = a.seg;
+        for (uint64_t ii = 0; ii < a.n_inst; ii++)
+            for (uint32_t r = 0; r < s.n_rows; r++) {
+                const uint64_t o = a.out_off + ii * s.n_rows + r;
+                for (int w = 0; w < 4; w++) if (a.w_val) aos_store(a.w_val, (uint64_t)w * a.stride + o, loc_load(s.tab, s.rows[r].loc[w], a.inst0 + ii));
+                for (int k = 0; k < 5; k++) if (a.sel) aos_store(a.sel, (uint64_t)k * a.stride + o, pool_load(s.pool, s.rows[r].sel[k]));
+            }
+        return true;
+    }
     bool run_check_rows(const CheckRowsBody::Args& a) {
         for (uint64_t i = 0; i < a.n; i++)
             if (CheckRowsBody::run(a, i)) { a.counters[CNT_UNSAT]++; if (i < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = i; }

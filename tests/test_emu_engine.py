@@ -155,3 +155,34 @@ def test_emu_permutation_same_column_twice(emu, oracle):
     se, c = run_engine(prog, lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
     assert se.digest() == so.digest()
     assert (c.permutation() == expected_sigma(oc)).all()
+
+
+def _materialize_vs_oracle(make_composer, oracle, n=70):
+    """Whole-instance ranges go through the tiled path (>= 32 instances), ragged ends through the simple body: every column of
+    pg_materialize_rows must equal the oracle's composer columns for arbitrary sub-ranges."""
+    vals = synth_wide(21, n)
+    wit = [v % 300 for v in vals]
+    c = make_composer()
+    w = c.add_input(oracle.from_ints(wit))
+    mx = oracle.from_ints([200 + (i % 50) for i in range(n)])            # per-instance bounds, all 8 bits wide -> q_c parameters
+    mn = oracle.from_ints([i % 7 for i in range(n)])
+    y = pg.range_check(c, mn, mx, w)
+    c.constrain_to_constant(y, oracle.from_ints([1]), oracle.from_ints(list(range(n))))   # per-instance PI
+    oc = oracle.Composer()
+    ow = oc.add_input_batch(oracle.from_ints(wit))
+    oy = oc.range_check_batch(mn, mx, ow)
+    oc.constrain_to_constant_batch(oy, oracle.from_ints([1]), oracle.from_ints(list(range(n))))
+    assert c.circuit_size() == oc.n
+    o_w, o_sel, o_pi, o_vars = oc.wires(), oc.selectors()[:6], oc.dense_pi(), oc.variables()
+    total = oc.n
+    for row0, cnt in ((0, total), (3, total - 3), (10, total - 25), (3 + 47 * 5 + 11, 47 * 40 + 5), (total - 60, 60)):
+        rows = c.rows(row0, cnt)
+        sl = slice(row0, row0 + cnt)
+        assert (rows["w_idx"] == o_w[:, sl]).all(), (row0, cnt)
+        assert (rows["sel"] == o_sel[:, sl]).all(), (row0, cnt)
+        assert (rows["pi"] == o_pi[sl]).all(), (row0, cnt)
+        assert (rows["w_val"] == o_vars[o_w[:, sl].astype(np.int64)]).all(), (row0, cnt)
+
+
+def test_emu_materialize_ranges(emu, oracle):
+    _materialize_vs_oracle(lambda: pg.StandardComposer(_cdll=emu), oracle)

@@ -320,3 +320,10 @@ def test_permutation_map_gpu(golden, oracle):
     w_idx = c.rows(want=("w_idx",))["w_idx"]
     nxt_row, nxt_wire = (sigma // 4).astype(np.int64), (sigma % 4).astype(np.int64)
     assert (w_idx[nxt_wire, nxt_row] == w_idx).all()
+
+
+def test_materialize_tiled_gpu(oracle):
+    """The tiled materialisation kernel (smem transpose + TMA bulk stores) and the simple body on ragged ranges vs the oracle."""
+    from tests.test_emu_engine import _materialize_vs_oracle
+    _materialize_vs_oracle(gpu_composer, oracle, n=70)
+    _materialize_vs_oracle(gpu_composer, oracle, n=1000)
