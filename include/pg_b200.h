@@ -90,7 +90,7 @@ int pg_composer_reset(pg_ctx *ctx);
 int pg_sync(pg_ctx *ctx);
 
 /* ---- gadgets ------------------------------------------------------------------------------------------------------
- * `on_device` != 0: the pointer arguments of the call are device pointers on cfg.device (read asynchronously on the
+ * `on_device` != 0: the pointer arguments of the call are 32-byte aligned device pointers on cfg.device (read asynchronously on the
  * ctx stream; keep them alive until pg_sync); == 0: host pointers (copied with cudaMemcpyAsync on the ctx stream;
  * pinned memory makes that copy asynchronous). */
 

@@ -3,9 +3,9 @@
 // test infrastructure only).
 struct pg_ctx { pg::Engine<PG_BACKEND> e; };
 
-static bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+static bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) != 0; }
 #define PG_NEED_CTX(ctx) do { if (!(ctx)) return PG_ERR_ARG; } while (0)
-#define PG_ALIGNED(ctx, p, dev) do { if ((dev) && (p) && misaligned(p)) return (ctx)->e.fail(PG_ERR_ARG, "device pointers must be 16-byte aligned"); } while (0)
+#define PG_ALIGNED(ctx, p, dev) do { if ((dev) && (p) && misaligned(p)) return (ctx)->e.fail(PG_ERR_ARG, "device pointers must be 32-byte aligned"); } while (0)
 
 extern "C" {
 

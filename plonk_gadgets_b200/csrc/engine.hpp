@@ -139,7 +139,7 @@ public:
     DevTab view_of(const Column& c) const {
         const Segment& s = segs[c.seg];
         DevTab v;
-        v.fr = s.fr ? s.fr + c.inst_off : nullptr;
+        v.fr = s.fr ? s.fr + 2 * c.inst_off : nullptr;
         v.bits = s.bits ? s.bits + c.inst_off : nullptr;
         v.stride = s.n_alloc; v.var_base = s.base_var + c.inst_off * s.t.n_vars; v.var_stride = s.t.n_vars;
         return v;

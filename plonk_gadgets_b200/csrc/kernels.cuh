@@ -202,8 +202,9 @@ __global__ void __launch_bounds__(BLOCK) k_materialize_tiled(const MatTileArgs a
             __syncthreads();
             for (uint32_t ii = warp; ii < n_i; ii += NWARPS) {        // lanes = rows: 1 KiB contiguous per instance
                 if ((uint32_t)lane < n_r) {
-                    uint4* dst = a.w_val + 2 * ((uint64_t)w * a.stride + o_base + (uint64_t)ii * s.n_rows + lane);
-                    dst[0] = s_val[lane * MT_PITCH + 2 * ii]; dst[1] = s_val[lane * MT_PITCH + 2 * ii + 1];
+                    const uint4 lo = s_val[lane * MT_PITCH + 2 * ii], hi = s_val[lane * MT_PITCH + 2 * ii + 1];
+                    const Fr v = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+                    st256(a.w_val + 2 * ((uint64_t)w * a.stride + o_base + (uint64_t)ii * s.n_rows + lane), v);   // one full sector per lane
                 }
             }
         }

@@ -8,12 +8,12 @@
 //   * a row TEMPLATE (rows x {4 wire references, 6 selector pool indices, optional per-instance q_c / PI parameter});
 //   * a selector POOL (the distinct Fr constants of the template: 0, 1, -1, 2^i, bounds ...);
 //   * the per-instance VARIABLE TABLE in structure-of-arrays form, sized n_alloc instances:
-//       fr   [slot][half][n_alloc]  uint4   -- 32-byte Montgomery scalars split in two 16-byte halves, so that a warp
-//                                             reading/writing slot s touches 512 contiguous bytes per half (128-bit
-//                                             coalesced accesses);
+//       fr   [slot][n_alloc]        32 B    -- one 32-byte Montgomery scalar per (slot, instance): a warp reading/writing
+//                                             slot s touches 1 KiB of contiguous memory with ONE 256-bit access per thread
+//                                             (sm_100 LDG/STG.E.ENL2.256: a whole 32-byte sector per lane);
 //       bits [plane][word][n_alloc] u32    -- the 256 bit-variables of one decomposition packed as the canonical
 //                                             little-endian 256-bit integer (bit b of the plane = Variable B_b);
-//       param[slot][half][n_alloc]  uint4   -- per-instance selector/public-input values (q_c overrides, PI).
+//       param[slot][n_alloc]        32 B    -- per-instance selector/public-input values (q_c overrides, PI).
 //
 // Variable numbering is the reference's: Variable id of local variable j of instance i = base_var + i*n_vars + j;
 // row id of local row r = base_row + i*n_rows + r (instances are appended one after another by the sequential loop).
@@ -35,7 +35,7 @@ PG_HD uint32_t loc_with_tab(uint32_t l, uint32_t tab) { return (l & ~(7u << 27))
 constexpr int MAX_TABS = 5;   // own table + up to 4 operand columns
 
 struct DevTab {
-    const uint4* fr;          // pre-offset by the operand's first instance
+    const uint4* fr;          // pre-offset by the operand's first instance (2 uint4 per scalar)
     const uint32_t* bits;
     uint64_t stride;          // n_alloc of the owning segment
     uint64_t var_base;        // Variable id of (instance 0 of this view, local variable 0)
@@ -56,21 +56,33 @@ static_assert(sizeof(DevRow) == 64, "DevRow must stay 64 bytes");
 // reserved pool entries
 enum : uint16_t { POOL_ZERO = 0, POOL_ONE = 1, POOL_MINUS_ONE = 2 };
 
-// ---- table accessors ------------------------------------------------------------------------------------------------
-PG_HD Fr tab_load_fr(const uint4* base, uint64_t stride, uint32_t slot, uint64_t i) {
-    // (base + i) first: the per-thread part is loop-invariant and the slot offset is warp-uniform (uniform datapath), so the
-    // address costs adder instructions instead of a 64-bit IMAD on the multiplier pipe
-    const uint4* p = base + i;
-    const uint4 lo = p[(uint64_t)(2 * slot) * stride];
-    const uint4 hi = p[(uint64_t)(2 * slot + 1) * stride];
-    Fr r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+// ---- 256-bit accesses -------------------------------------------------------------------------------------------------
+// A scalar is exactly one 32-byte DRAM sector.  sm_100 has 256-bit global loads/stores (ld/st.global.v8.b32 ->
+// LDG/STG.E.ENL2.256); with two 128-bit accesses per scalar every warp instruction would touch only half of each sector.
+// Pointers are kept as uint4* (16-byte units); addresses passed here are 32-byte aligned.
+PG_HD Fr ld256(const uint4* p) {
+    Fr r;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+#else
+    const uint4 lo = p[0], hi = p[1];
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+#endif
     return r;
 }
-PG_HD void tab_store_fr(uint4* base, uint64_t stride, uint32_t slot, uint64_t i, const Fr& v) {
-    uint4* p = base + i;
-    p[(uint64_t)(2 * slot) * stride] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-    p[(uint64_t)(2 * slot + 1) * stride] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+PG_HD void st256(uint4* p, const Fr& v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(v.v[0]), "r"(v.v[1]), "r"(v.v[2]), "r"(v.v[3]), "r"(v.v[4]), "r"(v.v[5]), "r"(v.v[6]), "r"(v.v[7]) : "memory");
+#else
+    p[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]); p[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+#endif
 }
+
+// ---- table accessors ------------------------------------------------------------------------------------------------
+PG_HD Fr tab_load_fr(const uint4* base, uint64_t stride, uint32_t slot, uint64_t i) { return ld256(base + 2 * ((uint64_t)slot * stride + i)); }
+PG_HD void tab_store_fr(uint4* base, uint64_t stride, uint32_t slot, uint64_t i, const Fr& v) { st256(base + 2 * ((uint64_t)slot * stride + i), v); }
 PG_HD uint32_t tab_load_bit(const uint32_t* bits, uint64_t stride, uint32_t plane_bit, uint64_t i) {
     const uint32_t plane = plane_bit >> 8, bit = plane_bit & 255u;
     const uint32_t w = (bits + i)[(uint64_t)(plane * 8 + (bit >> 5)) * stride];
@@ -97,9 +109,7 @@ PG_HD void loc_prefetch(const DevTab* tabs, uint32_t loc, uint64_t i) {
     const DevTab& t = tabs[loc_tab(loc)];
     if (kind == LOC_FR) {
         const uint32_t slot = loc_payload(loc);
-        const uint4* p = t.fr + i;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (uint64_t)(2 * slot) * t.stride));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (uint64_t)(2 * slot + 1) * t.stride));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.fr + 2 * ((uint64_t)slot * t.stride + i)));
     } else {
         const uint32_t pb = loc_payload(loc);
         asm volatile("prefetch.global.L1 [%0];" ::"l"((t.bits + i) + (uint64_t)((pb >> 8) * 8 + ((pb & 255u) >> 5)) * t.stride));
@@ -109,15 +119,8 @@ PG_HD void loc_prefetch(const DevTab* tabs, uint32_t loc, uint64_t i) {
 #endif
 }
 // AoS scalar (caller memory: BlsScalar[n]) access
-PG_HD Fr aos_load(const uint4* p, uint64_t i) {
-    const uint4 lo = p[2 * i], hi = p[2 * i + 1];
-    Fr r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
-    return r;
-}
-PG_HD void aos_store(uint4* p, uint64_t i, const Fr& v) {
-    p[2 * i] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-    p[2 * i + 1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
-}
+PG_HD Fr aos_load(const uint4* p, uint64_t i) { return ld256(p + 2 * i); }
+PG_HD void aos_store(uint4* p, uint64_t i, const Fr& v) { st256(p + 2 * i, v); }
 PG_HD Fr pool_load(const uint32_t* pool, uint32_t idx) {
     Fr r;
 #pragma unroll
