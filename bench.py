@@ -5,8 +5,8 @@
 
 One "step" = one pass of the hot path over one batch of synthetic witnesses:
     fresh composer -> add_input(2^log2n witnesses) -> range_check(0, 2^64) [witness generation: 271 rows / 653 variables
-    per instance, written to HBM as the packed variable table] -> gate check of every row (generic 6-multiplication
-    evaluation of q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + q_c + PI) -> verdict.
+    per instance, written to HBM as the packed variable table] -> gate check of every row (generic evaluation of
+    q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + q_c + PI, no selector value inspected) -> verdict.
 `value`  : rows generated and evaluated per second with the witnesses already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same step through the C ABI with HOST buffers: pinned-host witnesses copied in, per-instance results
            (32 B each) and the verdict copied out, inside the timed region.
@@ -298,7 +298,7 @@ def main():
                          "frac": imad_achieved / wide_peak if wide_peak else None,
                          "peak_source": "measured in this run: IMAD.WIDE.U32 products on all SMs (pg_microbench mode 1); the kernel executes "
                                         "496 wide products per gate eval (dot-product reduction), so frac can exceed the executed-instruction share",
-                         "executed_wide_products_per_row": 496, "frac_executed": (rows_per_launch * 496 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
+                         "executed_wide_products_per_row": 424, "frac_executed": (rows_per_launch * 424 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
                          "carry_chain_peak": chain_peak / 1e12, "imad_lo_peak": lo_peak / 1e12, "isolated_fr_mul_per_s": fr_mul_peak,
                          "traffic": ncu_traffic(args.log2n), "ms_per_launch": check_ms,
                          "hbm": {"kernel": "RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", "achieved": n * PACKED_BYTES_PER_INSTANCE / (wit_ms * 1e-3) / 1e9 if wit_ms else None,

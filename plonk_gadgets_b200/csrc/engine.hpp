@@ -85,6 +85,11 @@ public:
         pool_free.insert({it->second, p});
         pool_live.erase(it);
     }
+    // give back temporaries allocated since `mark`; only valid right after a call that synchronised the stream (d2h)
+    void release_scratch_from(size_t mark) {
+        for (size_t k = mark; k < scratch.size(); k++) dfree(scratch[k]);
+        scratch.resize(mark);
+    }
     int fail(int code, const std::string& what) { err = what; if (code == PG_ERR_CUDA && be.error()[0]) err += std::string(": ") + be.error(); return code; }
 
     // ------------------------------------------------------------------------------------------------ lifetime
@@ -450,29 +455,38 @@ public:
     int read_variables(uint64_t var0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
         if (var0 + cnt > n_vars || (cnt && !dst)) return fail(PG_ERR_ARG, "read_variables: range");
         if (!cnt) return PG_OK;
+        const size_t mark = scratch.size();
         uint4* out = dst_on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(cnt * sizeof(pg_fr));
         if (!out) return fail(PG_ERR_OOM, "read buffer");
         if (!dst_on_device) scratch.push_back(out);
         ReadVarsBody::Args a{d_segs, (uint32_t)dsegs.size(), var0, cnt, out};
         if (!be.template run_simple<ReadVarsBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "read_variables kernel");
-        return dst_on_device ? PG_OK : deliver(dst, out, cnt * sizeof(pg_fr), 0);
+        if (dst_on_device) return PG_OK;
+        const int rc = deliver(dst, out, cnt * sizeof(pg_fr), 0);
+        release_scratch_from(mark);
+        return rc;
     }
     int col_read(pg_col c, uint64_t i0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
         const Column* col = column(c);
         if (!col || i0 + cnt > col->n || (cnt && !dst)) return fail(PG_ERR_ARG, "col_read: range");
         if (!cnt) return PG_OK;
         // a column is a strided set of variables: gather it with the add_input body run "in reverse" (SoA -> AoS)
+        const size_t mark = scratch.size();
         uint4* out = dst_on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(cnt * sizeof(pg_fr));
         if (!out) return fail(PG_ERR_OOM, "read buffer");
         if (!dst_on_device) scratch.push_back(out);
         Column sub = *col; sub.inst_off += i0; sub.n = cnt;
         ColReadBody::Args a{view_of(sub), loc_with_tab(loc_of(sub), 0), out, cnt};
         if (!be.template run_simple<ColReadBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "col_read kernel");
-        return dst_on_device ? PG_OK : deliver(dst, out, cnt * sizeof(pg_fr), 0);
+        if (dst_on_device) return PG_OK;
+        const int rc = deliver(dst, out, cnt * sizeof(pg_fr), 0);
+        release_scratch_from(mark);
+        return rc;
     }
     int materialize(uint64_t row0, uint64_t cnt, uint64_t* w_idx, pg_fr* w_val, pg_fr* sel, pg_fr* pi, int dst_on_device) {
         if (row0 + cnt > n_rows) return fail(PG_ERR_ARG, "materialize_rows: range");
         if (!cnt) return PG_OK;
+        const size_t mark = scratch.size();
         unsigned long long* d_idx = nullptr; uint4 *d_val = nullptr, *d_sel = nullptr, *d_pi = nullptr;
         auto buf = [&](void* user, size_t bytes) -> void* {
             if (!user) return nullptr;
@@ -514,6 +528,8 @@ public:
         if (w_val && (rc = deliver(w_val, d_val, 4 * cnt * sizeof(pg_fr), 0))) return rc;
         if (sel && (rc = deliver(sel, d_sel, 6 * cnt * sizeof(pg_fr), 0))) return rc;
         if (pi && (rc = deliver(pi, d_pi, cnt * sizeof(pg_fr), 0))) return rc;
+        if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
+        release_scratch_from(mark);
         return PG_OK;
     }
 
@@ -522,6 +538,7 @@ public:
     int permutation(uint64_t row0, uint64_t cnt, uint64_t* sigma, int dst_on_device) {
         if (row0 + cnt > n_rows || (cnt && !sigma)) return fail(PG_ERR_ARG, "permutation: range");
         if (!cnt) return PG_OK;
+        const size_t mark = scratch.size();
         const size_t S = segs.size();
         std::vector<PermSeg> ps(S);
         std::vector<PermCons> cons;
@@ -595,7 +612,10 @@ public:
         if (!be.sync()) return fail(PG_ERR_CUDA, "sync");            // the host vectors above are the sources of the copies
         PermBody::Args a{d_segs, d_ps, d_cons, (uint32_t)dsegs.size(), first_zero_seg, row0, cnt, out};
         if (!be.template run_simple<PermBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "permutation kernel");
-        return dst_on_device ? PG_OK : deliver(sigma, out, 4 * cnt * sizeof(uint64_t), 0);
+        if (dst_on_device) return PG_OK;                             // tables stay parked until the next composer reset
+        const int rc = deliver(sigma, out, 4 * cnt * sizeof(uint64_t), 0);
+        release_scratch_from(mark);
+        return rc;
     }
 
     // ------------------------------------------------------------------------------------------------ helpers
@@ -612,6 +632,7 @@ public:
         if (first_invalid) *first_invalid = ~0ull;
         if (!n) return PG_OK;
         if (!src || !dst) return fail(PG_ERR_ARG, "convert: null argument");
+        const size_t mark = scratch.size();
         int rc; const uint4* ds = stage(src, n, on_device, &rc); if (!ds) return rc;
         uint4* dd = on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(n * sizeof(pg_fr));
         if (!dd) return fail(PG_ERR_OOM, "convert buffer");
@@ -628,11 +649,15 @@ public:
             if (n_invalid) *n_invalid = c[CNT_N_ERR];
             if (first_invalid) *first_invalid = c[CNT_N_ERR] ? c[CNT_FIRST_ERR] : ~0ull;
         }
-        return on_device ? PG_OK : deliver(dst, dd, n * sizeof(pg_fr), 0);
+        if (on_device) return PG_OK;
+        rc = deliver(dst, dd, n * sizeof(pg_fr), 0);
+        release_scratch_from(mark);
+        return rc;
     }
     int fr_op(int op, uint64_t n, const pg_fr* a, const pg_fr* b, pg_fr* out) {
         if (!n) return PG_OK;
         if (!a || !out) return fail(PG_ERR_ARG, "fr_op: null argument");
+        const size_t mark = scratch.size();
         int rc; const uint4* da = stage(a, n, 0, &rc); if (!da) return rc;
         const uint4* db = nullptr; if (b) { db = stage(b, n, 0, &rc); if (!db) return rc; }
         uint4* dout = (uint4*)dalloc(n * sizeof(pg_fr)); if (!dout) return fail(PG_ERR_OOM, "fr_op buffer");
@@ -650,7 +675,9 @@ public:
         }
         else { FrOpBody::Args g{op, da, db, dout, n}; ok = be.template run_simple<FrOpBody>(g, n, CLS_OTHER); }
         if (!ok) return fail(PG_ERR_CUDA, "fr_op kernel");
-        return deliver(out, dout, n * sizeof(pg_fr), 0);
+        rc = deliver(out, dout, n * sizeof(pg_fr), 0);
+        release_scratch_from(mark);
+        return rc;
     }
 };
 
