@@ -76,6 +76,10 @@ extern "C" {
     pub fn pg_read_variables(ctx: *mut pg_ctx, var0: u64, cnt: u64, dst: *mut pg_fr, dst_on_device: c_int) -> c_int;
     pub fn pg_materialize_rows(ctx: *mut pg_ctx, row0: u64, cnt: u64, w_idx: *mut u64, w_val: *mut pg_fr, sel: *mut pg_fr,
                                pi: *mut pg_fr, dst_on_device: c_int) -> c_int;
+    pub fn pg_permutation(ctx: *mut pg_ctx, row0: u64, cnt: u64, sigma: *mut u64, dst_on_device: c_int) -> c_int;
+    pub fn pg_fr_to_bytes(ctx: *mut pg_ctx, n: u64, src: *const pg_fr, dst: *mut u8, on_device: c_int) -> c_int;
+    pub fn pg_fr_from_bytes(ctx: *mut pg_ctx, n: u64, src: *const u8, dst: *mut pg_fr, on_device: c_int, n_invalid: *mut u64,
+                            first_invalid: *mut u64) -> c_int;
     pub fn pg_synth(ctx: *mut pg_ctx, seed: u64, stream: u64, n: u64, kind: c_int, bits: u32, dst_device: *mut pg_fr) -> c_int;
     pub fn pg_get_timing(ctx: *mut pg_ctx, out: *mut pg_timing, reset: c_int) -> c_int;
     pub fn pg_measure_imad_peak(ctx: *mut pg_ctx, wide_mac_per_s: *mut f64, imad_per_s: *mut f64) -> c_int;

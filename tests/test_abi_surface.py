@@ -39,3 +39,9 @@ def test_no_cpu_fallback():
     with pytest.raises(pg.EngineError) as e:
         pg.StandardComposer(device=0)
     assert e.value.code == -5          # PG_ERR_NO_DEVICE
+
+
+def test_rust_sys_crate_declares_the_same_symbols():
+    """bindings/rust/plonk-gadgets-b200-sys (source only: no rustc here) must stay in step with the header."""
+    src = open(os.path.join(ROOT, "bindings", "rust", "plonk-gadgets-b200-sys", "src", "lib.rs")).read()
+    assert sorted(set(re.findall(r"pub fn (pg_[a-z0-9_]+)", src))) == _declared()
