@@ -145,7 +145,9 @@ int pg_check_rows(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel,
 int pg_counts(const pg_ctx *ctx, uint64_t *n_rows, uint64_t *n_vars);        /* composer.circuit_size(), variables.len() */
 /* Column geometry: Variable id of instance i = first_var + i * stride. */
 int pg_col_info(const pg_ctx *ctx, pg_col col, uint64_t *n, uint64_t *first_var, uint64_t *stride);
-/* Values of instances [i0, i0+cnt) of a column (what `composer.variables[var]` holds). */
+/* Values of instances [i0, i0+cnt) of a column (what `composer.variables[var]` holds).
+ * dst_on_device: 0 = host memory (returns when the data has arrived), 1 = device memory, 2 = PINNED host memory, asynchronous:
+ * the copy runs on a second stream, overlaps with kernels enqueued afterwards (e.g. pg_check) and is complete after pg_sync. */
 int pg_col_read(pg_ctx *ctx, pg_col col, uint64_t i0, uint64_t cnt, pg_fr *dst, int dst_on_device);
 /* variables[var0 .. var0+cnt) in Variable order. */
 int pg_read_variables(pg_ctx *ctx, uint64_t var0, uint64_t cnt, pg_fr *dst, int dst_on_device);

@@ -191,12 +191,18 @@ class StandardComposer:
         self._ok(self._L.pg_col_read(self._ctx, v.col, i0, cnt, out.ctypes.data_as(C.c_void_p), 0), "pg_col_read")
         return out
 
-    def read_column_into(self, v: Variables, dst, i0: int = 0, cnt: int | None = None):
-        """Device (or pinned host) destination variant of read_column."""
+    def read_column_into(self, v: Variables, dst, i0: int = 0, cnt: int | None = None, asynchronous: bool = False):
+        """Device (or host) destination variant of read_column.  asynchronous=True (pinned host tensors only): the copy runs on
+        the engine's copy stream, overlaps with whatever is enqueued next, and is complete after sync()."""
         cnt = v.n - i0 if cnt is None else cnt
-        p, dev, n, _ = _scalars(dst)
+        p, dev, n, keep = _scalars(dst)
         if n < cnt:
             raise ValueError("destination too small")
+        if asynchronous:
+            if dev or not (hasattr(dst, "is_pinned") and dst.is_pinned()):
+                raise ValueError("asynchronous reads need a pinned host tensor")
+            self._keep.append(keep)
+            dev = 2
         self._ok(self._L.pg_col_read(self._ctx, v.col, i0, cnt, p, dev), "pg_col_read")
 
     def variables(self, var0: int = 0, cnt: int | None = None) -> np.ndarray:

@@ -87,7 +87,8 @@ int pg_col_info(const pg_ctx* ctx, pg_col col, uint64_t* n, uint64_t* first_var,
     return PG_OK;
 }
 int pg_col_read(pg_ctx* ctx, pg_col col, uint64_t i0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
-    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device);
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device == 1);
+    if (dst_on_device < 0 || dst_on_device > 2) return ctx->e.fail(PG_ERR_ARG, "pg_col_read: dst_on_device must be 0, 1 or 2");
     return ctx->e.col_read(col, i0, cnt, dst, dst_on_device);
 }
 int pg_read_variables(pg_ctx* ctx, uint64_t var0, uint64_t cnt, pg_fr* dst, int dst_on_device) {

@@ -21,6 +21,8 @@ Fr h_pow2[256];
 class CudaBackend {
 public:
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device -> pinned-host result copies that overlap with later kernels
+    cudaEvent_t copy_ready = nullptr;
     bool own_stream = false;
     bool nodev = false;
     bool timing_on = false;
@@ -47,6 +49,8 @@ public:
         sm_count = prop.multiProcessorCount;
         if (cfg.stream) { stream = (cudaStream_t)cfg.stream; own_stream = false; }
         else { PG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        PG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        PG_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
         PG_CUDA(cudaFuncSetAttribute(k_check<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k_check<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -59,6 +63,9 @@ public:
         for (auto& ev : events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
         for (auto& ev : ev_free) cudaEventDestroy(ev);
         events.clear(); ev_free.clear();
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (copy_ready) cudaEventDestroy(copy_ready);
+        copy_stream = nullptr; copy_ready = nullptr;
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -76,7 +83,14 @@ public:
         return true;
     }
     bool d2d(void* dst, const void* src, size_t bytes) { PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); return true; }
-    bool sync() { PG_CUDA(cudaStreamSynchronize(stream)); return true; }
+    bool sync() { PG_CUDA(cudaStreamSynchronize(stream)); PG_CUDA(cudaStreamSynchronize(copy_stream)); return true; }
+    // copy to (pinned) host memory on the copy stream, ordered after everything enqueued so far; complete after sync()
+    bool d2h_async(void* dst, const void* src, size_t bytes) {
+        PG_CUDA(cudaEventRecord(copy_ready, stream));
+        PG_CUDA(cudaStreamWaitEvent(copy_stream, copy_ready, 0));
+        PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, copy_stream));
+        return true;
+    }
     bool upload_pow2(const Fr* table) {
         PG_CUDA(cudaMemcpyToSymbolAsync(c_pow2, table, 256 * sizeof(Fr), 0, cudaMemcpyHostToDevice, stream));
         PG_CUDA(cudaStreamSynchronize(stream));

@@ -246,13 +246,11 @@ public:
     // ------------------------------------------------------------------------------------------------ gadgets
     int add_input_batch(uint64_t n, const pg_fr* values, int on_device, pg_col* out) {
         if (!out || (n && !values)) return fail(PG_ERR_ARG, "add_input_batch: null argument");
-        int rc; const uint4* src = n ? stage(values, n, on_device, &rc) : nullptr;
-        if (n && !src) return rc;
-        rc = push_segment(make_add_input_template(), n, nullptr, 0);
+        int rc = push_segment(make_add_input_template(), n, nullptr, 0);
         if (rc) return rc;
         Segment& s = segs.back();
-        AddInputBody::Args a{src, s.fr, s.n_alloc, n};
-        if (n && !be.template run_simple<AddInputBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "add_input kernel");
+        // a one-slot table of 32-byte scalars has exactly the caller's layout (BlsScalar[n]): the values are copied straight in
+        if (n && !(on_device ? be.d2d(s.fr, values, n * sizeof(pg_fr)) : be.h2d(s.fr, values, n * sizeof(pg_fr)))) return fail(PG_ERR_CUDA, "add_input copy");
         *out = new_column((uint32_t)segs.size() - 1, 0, n);
         return PG_OK;
     }
@@ -472,13 +470,18 @@ public:
         if (!cnt) return PG_OK;
         // a column is a strided set of variables: gather it with the add_input body run "in reverse" (SoA -> AoS)
         const size_t mark = scratch.size();
-        uint4* out = dst_on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(cnt * sizeof(pg_fr));
+        const bool to_device = dst_on_device == 1;
+        uint4* out = to_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(cnt * sizeof(pg_fr));
         if (!out) return fail(PG_ERR_OOM, "read buffer");
-        if (!dst_on_device) scratch.push_back(out);
+        if (!to_device) scratch.push_back(out);
         Column sub = *col; sub.inst_off += i0; sub.n = cnt;
         ColReadBody::Args a{view_of(sub), loc_with_tab(loc_of(sub), 0), out, cnt};
         if (!be.template run_simple<ColReadBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "col_read kernel");
-        if (dst_on_device) return PG_OK;
+        if (to_device) return PG_OK;
+        if (dst_on_device == 2) {                 // pinned host, asynchronous: the staging buffer lives until the next reset
+            if (!be.d2h_async(dst, out, cnt * sizeof(pg_fr))) return fail(PG_ERR_CUDA, "asynchronous result copy");
+            return PG_OK;
+        }
         const int rc = deliver(dst, out, cnt * sizeof(pg_fr), 0);
         release_scratch_from(mark);
         return rc;

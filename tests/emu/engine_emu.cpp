@@ -32,6 +32,7 @@ public:
     bool h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
     bool d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
     bool d2d(void* d, const void* s, size_t n) { memmove(d, s, n); return true; }
+    bool d2h_async(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
     bool sync() { return true; }
     bool upload_pow2(const Fr*) { return true; }
     bool timing(pg_timing* out, bool) { memset(out, 0, sizeof(*out)); return true; }

@@ -327,3 +327,18 @@ def test_materialize_tiled_gpu(oracle):
     from tests.test_emu_engine import _materialize_vs_oracle
     _materialize_vs_oracle(gpu_composer, oracle, n=70)
     _materialize_vs_oracle(gpu_composer, oracle, n=1000)
+
+
+def test_async_result_copy(oracle, torch_cuda):
+    """pg_col_read with dst_on_device = 2: pinned host destination filled on the copy stream, valid after pg_sync."""
+    torch = torch_cuda
+    n = 1 << 16
+    c = gpu_composer()
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 2, 2, 64, wit)
+    w = c.add_input(wit)
+    y = pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    host = torch.zeros((n, 4), dtype=torch.int64).pin_memory()
+    c.read_column_into(y, host, asynchronous=True)
+    assert c.check_circuit_satisfied() == (0, None)
+    c.sync()
+    assert (host.numpy().view(np.uint64) == y.values()).all()
