@@ -53,6 +53,21 @@ def main():
     zero_2p64 = to_mont(c, [0, 2 ** 64])
     mn, mx = zero_2p64[0:1].copy(), zero_2p64[1:2].copy()
 
+    # ---- C1: ONE range_check instance (latency of the whole path for a single gadget call, host overheads included)
+    one = torch.empty((1, 4), dtype=torch.int64, device=dev); c.synth(SEED, 1, 1, 64, one)
+
+    def c1():
+        c.reset(); w = c.add_input(one); y = pg.range_check(c, mn, mx, w)
+        bad, _ = c.check_circuit_satisfied(); assert bad == 0
+        return y.values()
+    import time as _t
+    for _ in range(20): c1()
+    t0 = _t.perf_counter()
+    for _ in range(200): c1()
+    lat = (_t.perf_counter() - t0) / 200
+    print(json.dumps({"config": "C1: single range_check of one 64-bit witness (reset + allocate + gadget + verdict + result read-back)",
+                      "latency_us": lat * 1e6, "rows": 271}), flush=True)
+
     # ---- C2: 2^20 range_check, 64-bit bound
     n = 1 << 20
     wit = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 2, 2, 64, wit)
