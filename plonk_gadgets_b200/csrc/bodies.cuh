@@ -8,9 +8,9 @@
 // elements) and a Post body.
 //
 // Reference functions restated here (witness arithmetic only; row structure lives in templates.hpp):
-//   RangeBody       /root/reference/src/range.rs:27-43 (range_check), :82-113 (max_bound), :53-76 (min_bound),
+//   RangePre/Post   /root/reference/src/range.rs:27-43 (range_check), :82-113 (max_bound), :53-76 (min_bound),
 //                   :119-158 (scalar_decomposition_gadget), :161-170 (scalar_to_bits)
-//   MaybeEqualBody  /root/reference/src/scalar.rs:105-140      IsNonZeroBody  /root/reference/src/scalar.rs:63-97
+//   MaybeEqualPre/Post /root/reference/src/scalar.rs:105-140   IsNonZeroPre   /root/reference/src/scalar.rs:63-97
 //   SelectZeroBody  /root/reference/src/scalar.rs:21-27        SelectOneBody  /root/reference/src/scalar.rs:36-59
 #pragma once
 #include "layout.h"
