@@ -4,7 +4,8 @@
 struct pg_ctx { pg::Engine<PG_BACKEND> e; };
 
 static bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) != 0; }
-#define PG_NEED_CTX(ctx) do { if (!(ctx)) return PG_ERR_ARG; } while (0)
+// every entry point first makes the ctx's device current (a process may hold contexts on several GPUs)
+#define PG_NEED_CTX(ctx) do { if (!(ctx)) return PG_ERR_ARG; const_cast<pg_ctx*>(ctx)->e.be.activate(); } while (0)
 #define PG_ALIGNED(ctx, p, dev) do { if ((dev) && (p) && misaligned(p)) return (ctx)->e.fail(PG_ERR_ARG, "device pointers must be 32-byte aligned"); } while (0)
 
 extern "C" {
@@ -36,7 +37,7 @@ int pg_ctx_create(const pg_cfg* cfg, pg_ctx** out) {
     *out = c;
     return PG_OK;
 }
-void pg_ctx_destroy(pg_ctx* ctx) { if (ctx) { ctx->e.destroy(); delete ctx; } }
+void pg_ctx_destroy(pg_ctx* ctx) { if (ctx) { ctx->e.be.activate(); ctx->e.destroy(); delete ctx; } }
 int pg_composer_reset(pg_ctx* ctx) { PG_NEED_CTX(ctx); return ctx->e.reset(); }
 int pg_sync(pg_ctx* ctx) { PG_NEED_CTX(ctx); return ctx->e.be.sync() ? PG_OK : ctx->e.fail(PG_ERR_CUDA, "sync"); }
 

@@ -36,6 +36,8 @@ public:
 
     const char* error() const { return errbuf; }
     bool no_device() const { return nodev; }
+    int device = 0;
+    void activate() { cudaSetDevice(device); }
 
     bool init(const pg_cfg& cfg) {
         int count = 0;
@@ -43,6 +45,7 @@ public:
         if (e != cudaSuccess || count == 0) { nodev = true; snprintf(errbuf, sizeof(errbuf), "no CUDA device: %s", cudaGetErrorString(e)); return false; }
         if (cfg.device < 0 || cfg.device >= count) { nodev = true; snprintf(errbuf, sizeof(errbuf), "device %d out of range (%d devices)", cfg.device, count); return false; }
         PG_CUDA(cudaSetDevice(cfg.device));
+        device = cfg.device;
         cudaDeviceProp prop;
         PG_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
         if (prop.major != 10) { nodev = true; snprintf(errbuf, sizeof(errbuf), "device %d is sm_%d%d; this library is built for sm_100a only", cfg.device, prop.major, prop.minor); return false; }

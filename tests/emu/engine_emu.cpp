@@ -25,6 +25,7 @@ class HostBackend {
 public:
     const char* error() const { return ""; }
     bool no_device() const { return false; }
+    void activate() {}
     bool init(const pg_cfg&) { return true; }
     void shutdown() {}
     void* alloc(size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 64, bytes ? bytes : 64)) return nullptr; memset(p, 0xA5, bytes); return p; }
