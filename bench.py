@@ -139,7 +139,8 @@ def run_reference(args):
     vals, secs = [], []
     info = None
     for s in range(args.warmup + args.steps):
-        info = cpu_reference_run(None, threads, budget_s=max(2.0, 40.0 / max(1, args.warmup + args.steps)))
+        budget = float(os.environ.get("PG_BENCH_CPU_BUDGET_S", max(2.0, 40.0 / max(1, args.warmup + args.steps))))
+        info = cpu_reference_run(None, threads, budget_s=budget)
         if s >= args.warmup:
             vals.append(info["value"]); secs.append(info["seconds"])
     v = sum(vals) / len(vals)

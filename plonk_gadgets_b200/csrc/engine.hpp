@@ -32,7 +32,8 @@ struct Segment {
     Template t;
     uint64_t n_inst = 0, n_alloc = 0, base_row = 0, base_var = 0;
     uint4* fr = nullptr; uint32_t* bits = nullptr; uint4* param = nullptr;
-    DevRow* d_rows = nullptr; uint32_t* d_varloc = nullptr; uint32_t* d_pool = nullptr;
+    DevRow* d_rows = nullptr; uint32_t* d_varloc = nullptr; uint32_t* d_pool = nullptr;   // views into d_image
+    void* d_image = nullptr;
     DevTab tabs[MAX_TABS] = {};
     std::vector<DevRow> rows;
     std::vector<Column> operands;       // the columns bound as operands (for the permutation map)
@@ -53,7 +54,7 @@ public:
     std::vector<Segment> segs;
     std::vector<Column> cols;
     std::vector<DevSeg> dsegs;
-    DevSeg* d_segs = nullptr; size_t d_segs_cap = 0;
+    DevSeg* d_segs = nullptr; size_t d_segs_cap = 0; bool dsegs_dirty = true;
     unsigned long long* d_counters = nullptr;
     uint64_t n_rows = 0, n_vars = 0;
     std::multimap<size_t, void*> pool_free;          // size -> buffer (exact-size reuse across composer resets)
@@ -114,9 +115,9 @@ public:
         be.shutdown();
     }
     void release_segments() {
-        for (auto& s : segs) { dfree(s.fr); dfree(s.bits); dfree(s.param); dfree(s.d_rows); dfree(s.d_varloc); dfree(s.d_pool); }
+        for (auto& s : segs) { dfree(s.fr); dfree(s.bits); dfree(s.param); dfree(s.d_image); }
         for (void* p : scratch) dfree(p);
-        scratch.clear(); segs.clear(); cols.clear(); dsegs.clear();
+        scratch.clear(); segs.clear(); cols.clear(); dsegs.clear(); dsegs_dirty = true;
         n_rows = 0; n_vars = 0;
     }
     // StandardComposer::new(): 5 variables, 3 rows
@@ -177,21 +178,24 @@ public:
             d.pi_sel = src.pi_sel; d.qc_param = src.qc_param; d.pi_param = src.pi_param;
             s.rows[r] = d;
         }
-        if (!s.rows.empty()) {
-            s.d_rows = (DevRow*)dalloc(s.rows.size() * sizeof(DevRow));
-            if (!s.d_rows || !be.h2d(s.d_rows, s.rows.data(), s.rows.size() * sizeof(DevRow))) return fail(PG_ERR_CUDA, "row template upload");
-        }
-        if (!T.var_loc.empty()) {
-            s.d_varloc = (uint32_t*)dalloc(T.var_loc.size() * sizeof(uint32_t));
-            if (!s.d_varloc || !be.h2d(s.d_varloc, T.var_loc.data(), T.var_loc.size() * sizeof(uint32_t))) return fail(PG_ERR_CUDA, "variable map upload");
-        }
-        s.d_pool = (uint32_t*)dalloc(T.pool.size() * sizeof(Fr));
-        if (!s.d_pool || !be.h2d(s.d_pool, T.pool.data(), T.pool.size() * sizeof(Fr))) return fail(PG_ERR_CUDA, "selector pool upload");
+        // rows | variable map | selector pool go up in ONE copy (one staging image per segment)
+        const size_t b_rows = s.rows.size() * sizeof(DevRow), b_var = (T.var_loc.size() * sizeof(uint32_t) + 31) & ~(size_t)31, b_pool = T.pool.size() * sizeof(Fr);
+        std::vector<unsigned char> img(b_rows + b_var + b_pool);
+        if (b_rows) memcpy(img.data(), s.rows.data(), b_rows);
+        if (!T.var_loc.empty()) memcpy(img.data() + b_rows, T.var_loc.data(), T.var_loc.size() * sizeof(uint32_t));
+        memcpy(img.data() + b_rows + b_var, T.pool.data(), b_pool);
+        unsigned char* d_img = (unsigned char*)dalloc(img.size());
+        if (!d_img || !be.h2d(d_img, img.data(), img.size())) return fail(d_img ? PG_ERR_CUDA : PG_ERR_OOM, "template upload");
+        s.d_rows = b_rows ? (DevRow*)d_img : nullptr;
+        s.d_varloc = T.var_loc.empty() ? nullptr : (uint32_t*)(d_img + b_rows);
+        s.d_pool = (uint32_t*)(d_img + b_rows + b_var);
+        s.d_image = d_img;
         // (pageable sources: cudaMemcpyAsync has consumed them when it returns; they stay alive in the Segment anyway)
         segs.push_back(std::move(s));
         Segment& S = segs.back();
         n_rows += n * S.t.rows.size(); n_vars += n * (uint64_t)S.t.n_vars;
-        return sync_dsegs();
+        dsegs_dirty = true;                         // the device copy of the segment table is refreshed by the read-back calls
+        return PG_OK;
     }
     DevSeg make_dseg(const Segment& s) const {
         DevSeg d; memset(&d, 0, sizeof(d));
@@ -202,6 +206,8 @@ public:
         return d;
     }
     int sync_dsegs() {
+        if (!dsegs_dirty) return PG_OK;
+        dsegs_dirty = false;
         dsegs.resize(segs.size());
         for (size_t k = 0; k < segs.size(); k++) dsegs[k] = make_dseg(segs[k]);
         if (dsegs.size() > d_segs_cap) {
@@ -218,9 +224,9 @@ public:
         Segment& s = segs.back();
         n_rows -= s.n_inst * s.t.rows.size(); n_vars -= s.n_inst * (uint64_t)s.t.n_vars;
         scratch.push_back(s.fr); scratch.push_back(s.bits); scratch.push_back(s.param);
-        scratch.push_back(s.d_rows); scratch.push_back(s.d_varloc); scratch.push_back(s.d_pool);
+        scratch.push_back(s.d_image);
         segs.pop_back();
-        sync_dsegs();
+        dsegs_dirty = true;
     }
 
     // host pointer -> device scratch copy (or pass-through for device pointers)
@@ -355,6 +361,7 @@ public:
             Segment& s = segs.back();
             n_rows -= (n - f) * s.t.rows.size(); n_vars -= (n - f) * (uint64_t)s.t.n_vars;
             s.n_inst = f;
+            dsegs_dirty = true;
         }
         Column part = *v; part.inst_off += f; part.n = 1;
         rc = push_segment(make_is_non_zero_template(true), 1, &part, 1);
@@ -457,6 +464,7 @@ public:
         uint4* out = dst_on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(cnt * sizeof(pg_fr));
         if (!out) return fail(PG_ERR_OOM, "read buffer");
         if (!dst_on_device) scratch.push_back(out);
+        { const int rcs = sync_dsegs(); if (rcs) return rcs; }
         ReadVarsBody::Args a{d_segs, (uint32_t)dsegs.size(), var0, cnt, out};
         if (!be.template run_simple<ReadVarsBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "read_variables kernel");
         if (dst_on_device) return PG_OK;
@@ -501,6 +509,7 @@ public:
         d_sel = (uint4*)buf(sel, 6 * cnt * sizeof(pg_fr));
         d_pi = (uint4*)buf(pi, cnt * sizeof(pg_fr));
         if ((w_idx && !d_idx) || (w_val && !d_val) || (sel && !d_sel) || (pi && !d_pi)) return fail(PG_ERR_OOM, "materialize buffers");
+        { const int rcs = sync_dsegs(); if (rcs) return rcs; }
         // per segment: whole instances go through the tiled kernel (wire values + the 5 instance-independent selector columns),
         // the simple body adds w_idx / q_c / PI for them and does everything for the ragged ends of the requested range
         auto simple = [&](uint64_t r0, uint64_t n, uint32_t what) -> bool {
@@ -542,6 +551,7 @@ public:
         if (row0 + cnt > n_rows || (cnt && !sigma)) return fail(PG_ERR_ARG, "permutation: range");
         if (!cnt) return PG_OK;
         const size_t mark = scratch.size();
+        { const int rcs = sync_dsegs(); if (rcs) return rcs; }
         const size_t S = segs.size();
         std::vector<PermSeg> ps(S);
         std::vector<PermCons> cons;

@@ -10,6 +10,8 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <array>
+#include <map>
 #include <vector>
 #include "bodies.cuh"
 
@@ -48,15 +50,22 @@ struct Template {
 class TemplateComposer {
 public:
     Template t;
+    std::map<std::array<uint32_t, 8>, uint16_t> pool_index;
     TemplateComposer() {
-        t.pool.push_back(fr_zero());                 // POOL_ZERO
-        t.pool.push_back(fr_one());                  // POOL_ONE
-        t.pool.push_back(fr_neg(fr_one()));          // POOL_MINUS_ONE
+        constant(fr_zero());                         // POOL_ZERO
+        constant(fr_one());                          // POOL_ONE
+        constant(fr_neg(fr_one()));                  // POOL_MINUS_ONE
     }
+    // index of a selector constant in the pool (each distinct value once)
     uint16_t constant(const Fr& v) {
-        for (size_t i = 0; i < t.pool.size(); i++) if (fr_eq(t.pool[i], v)) return (uint16_t)i;
+        std::array<uint32_t, 8> key;
+        for (int i = 0; i < 8; i++) key[i] = v.v[i];
+        auto it = pool_index.find(key);
+        if (it != pool_index.end()) return it->second;
         t.pool.push_back(v);
-        return (uint16_t)(t.pool.size() - 1);
+        const uint16_t idx = (uint16_t)(t.pool.size() - 1);
+        pool_index[key] = idx;
+        return idx;
     }
     // composer.add_input(scalar): a new variable holding a full scalar -> one fr slot
     WireRef add_input() {
