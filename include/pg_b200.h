@@ -73,7 +73,7 @@ typedef struct pg_cfg {
     int32_t device;         /* CUDA ordinal */
     int32_t check_mode;     /* PG_CHECK_* */
     uint32_t flags;         /* PG_F_* */
-    uint32_t reserved;      /* tuning knob: launch shape of the gate-check kernel (0 = default 128 threads x 5 blocks/SM, 1 = 256 x 2) */
+    uint32_t reserved;      /* tuning knob: launch shape of the gate-check kernel (0 = default; 1..4 = alternatives, see kernels.cuh CheckShape) */
     void *stream;           /* cudaStream_t to enqueue on; NULL = the engine creates its own non-blocking stream */
 } pg_cfg;
 

@@ -55,12 +55,21 @@ public:
         PG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         PG_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
-        PG_CUDA(cudaFuncSetAttribute(k_check<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k_check<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k_check<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k_check<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        check_shape = cfg.reserved == 1 ? 0 : 1;   // default: 128 threads x 5 blocks/SM (2 % faster than 256 x 2 at the metric size, profiles/README.md)
+        check_shape = cfg.reserved < (uint32_t)CHECK_SHAPES ? (int)cfg.reserved : 0;
+        if (!set_check_attrs<0>() || !set_check_attrs<1>() || !set_check_attrs<2>() || !set_check_attrs<3>() || !set_check_attrs<4>()) return false;
         return true;
+    }
+    template <int SHAPE>
+    bool set_check_attrs() {
+        PG_CUDA(cudaFuncSetAttribute(k_check<0, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check<1, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        return true;
+    }
+    template <int SHAPE>
+    void launch_check(const CheckArgs& a, size_t smem) {
+        constexpr int T = CheckShape<SHAPE>::BLOCK_T;
+        const unsigned grid = (unsigned)((a.n_inst + T - 1) / T);
+        if (a.mode == PG_CHECK_SPARSE) k_check<1, SHAPE><<<grid, T, smem, stream>>>(a); else k_check<0, SHAPE><<<grid, T, smem, stream>>>(a);
     }
     void shutdown() {
         for (auto& ev : events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -158,13 +167,10 @@ public:
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         tic(CLS_CHECK, a.n_inst * a.n_rows);
-        const bool sparse = a.mode == PG_CHECK_SPARSE;
-        if (check_shape == 1) {
-            const unsigned grid = (unsigned)((a.n_inst + 127) / 128);
-            if (sparse) k_check<1, 1><<<grid, 128, smem, stream>>>(a); else k_check<0, 1><<<grid, 128, smem, stream>>>(a);
-        } else {
-            const unsigned grid = (unsigned)((a.n_inst + 255) / 256);
-            if (sparse) k_check<1, 0><<<grid, 256, smem, stream>>>(a); else k_check<0, 0><<<grid, 256, smem, stream>>>(a);
+        switch (check_shape) {
+            case 1: launch_check<1>(a, smem); break; case 2: launch_check<2>(a, smem); break;
+            case 3: launch_check<3>(a, smem); break; case 4: launch_check<4>(a, smem); break;
+            default: launch_check<0>(a, smem); break;
         }
         toc();
         return launched("k_check");

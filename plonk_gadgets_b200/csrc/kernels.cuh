@@ -109,11 +109,15 @@ struct SmemPool {
 
 // One instance per thread; the row template is walked by all threads in lock step (selector pool in shared memory,
 // template rows read with warp-uniform addresses), wire values come from the SoA variable table with coalesced loads.
-// Launch shapes of the gate-check kernel (pg_cfg.reserved = 1 selects the alternative):
-//   shape 1 (default): 128 threads x 5 blocks/SM (<=102 registers, 20 warps/SM)      shape 0: 256 threads x 2 blocks/SM (<=128 registers, 16 warps/SM)
+// Launch shapes of the gate-check kernel: threads per block x minimum blocks per SM (=> register budget, warps per SM).
+// pg_cfg.reserved selects one (0 = default); the alternatives are kept for tuning runs (profiles/README.md).
 template <int SHAPE> struct CheckShape;
-template <> struct CheckShape<0> { static constexpr int BLOCK_T = 256, MIN_BLOCKS = 2; };
-template <> struct CheckShape<1> { static constexpr int BLOCK_T = 128, MIN_BLOCKS = 5; };
+template <> struct CheckShape<0> { static constexpr int BLOCK_T = 128, MIN_BLOCKS = 5; };   // <=102 regs, 20 warps/SM
+template <> struct CheckShape<1> { static constexpr int BLOCK_T = 256, MIN_BLOCKS = 2; };   // <=128 regs, 16 warps/SM
+template <> struct CheckShape<2> { static constexpr int BLOCK_T = 128, MIN_BLOCKS = 6; };   // <= 85 regs, 24 warps/SM
+template <> struct CheckShape<3> { static constexpr int BLOCK_T = 128, MIN_BLOCKS = 7; };   // <= 73 regs, 28 warps/SM
+template <> struct CheckShape<4> { static constexpr int BLOCK_T = 128, MIN_BLOCKS = 8; };   // <= 64 regs, 32 warps/SM
+constexpr int CHECK_SHAPES = 5;
 template <int MODE, int SHAPE>
 __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>::MIN_BLOCKS) k_check(const CheckArgs a) {
     constexpr int CHECK_BLOCK = CheckShape<SHAPE>::BLOCK_T;
