@@ -234,11 +234,12 @@ struct CheckBody {
             const DevRow row = a.rows[r];
             Fr w[5];
             if (r + 1 < a.n_rows) {            // request the next row's wire values now: ~2000 multiplier cycles cover the latency
-                const uint4 nl = *reinterpret_cast<const uint4*>(a.rows[r + 1].loc);
-                loc_prefetch(a.tab, nl.x, i); loc_prefetch(a.tab, nl.y, i); loc_prefetch(a.tab, nl.z, i); loc_prefetch(a.tab, nl.w, i);
+                const DevRow& nr = a.rows[r + 1];
+#pragma unroll
+                for (int k = 0; k < 4; k++) row_prefetch(nr.loc[k], nr.addr[k], i);
             }
-            w[1] = loc_load(a.tab, row.loc[0], i); w[2] = loc_load(a.tab, row.loc[1], i);
-            w[3] = loc_load(a.tab, row.loc[2], i); w[4] = loc_load(a.tab, row.loc[3], i);
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
             uint32_t t[9];
             if (MODE == 0) {
                 Fr sel[4];

@@ -176,6 +176,13 @@ public:
             }
             for (int k = 0; k < 6; k++) d.sel[k] = src.sel[k];
             d.pi_sel = src.pi_sel; d.qc_param = src.qc_param; d.pi_param = src.pi_param;
+            for (int w = 0; w < 4; w++) {            // instance-0 address of each wire value (see DevRow::addr)
+                const uint32_t kind = loc_kind(d.loc[w]), pay = loc_payload(d.loc[w]);
+                const DevTab& tb = s.tabs[loc_tab(d.loc[w])];
+                if (kind == LOC_FR) d.addr[w] = (uint64_t)(uintptr_t)(tb.fr + 2 * ((uint64_t)pay * tb.stride));
+                else if (kind == LOC_BIT) d.addr[w] = (uint64_t)(uintptr_t)(tb.bits + (uint64_t)((pay >> 8) * 8 + ((pay & 255u) >> 5)) * tb.stride);
+                else d.addr[w] = 0;
+            }
             s.rows[r] = d;
         }
         // rows | variable map | selector pool go up in ONE copy (one staging image per segment)

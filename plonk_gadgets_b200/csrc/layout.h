@@ -42,7 +42,7 @@ struct DevTab {
     uint64_t var_stride;      // n_vars of the owning segment
 };
 
-struct DevRow {               // 64 bytes
+struct DevRow {               // 96 bytes
     uint32_t loc[4];          // where the values of w_l, w_r, w_o, w_4 live
     uint32_t var[4];          // local Variable index inside the owning table's segment (unused for LOC_ZERO)
     uint16_t sel[6];          // pool indices: q_m q_l q_r q_o q_4 q_c
@@ -50,8 +50,12 @@ struct DevRow {               // 64 bytes
     int16_t qc_param;         // >= 0: q_c is param slot qc_param of the instance (sel[5] ignored)
     int16_t pi_param;         // >= 0: PI is param slot pi_param of the instance
     uint16_t pad[7];
+    // pre-resolved device address of instance 0 of each wire value (FR: the 32-byte scalar; BIT: the 32-bit word holding the
+    // bit; ZERO: 0).  The gate-check kernel adds i*32 (or i*4) and never touches the table descriptors: no per-row
+    // slot*stride products on the multiplier pipe.
+    uint64_t addr[4];
 };
-static_assert(sizeof(DevRow) == 64, "DevRow must stay 64 bytes");
+static_assert(sizeof(DevRow) == 96, "DevRow must stay 96 bytes");
 
 // reserved pool entries
 enum : uint16_t { POOL_ZERO = 0, POOL_ONE = 1, POOL_MINUS_ONE = 2 };
@@ -100,6 +104,28 @@ PG_HD Fr loc_load(const DevTab* tabs, uint32_t loc, uint64_t i) {
 #pragma unroll
     for (int k = 0; k < 8; k++) r.v[k] = b ? one.v[k] : 0u;
     return r;
+}
+// the same through the pre-resolved addresses of a DevRow
+PG_HD Fr row_load(const DevRow& row, int w, uint64_t i) {
+    const uint32_t kind = loc_kind(row.loc[w]);
+    if (kind == LOC_ZERO) return fr_zero();
+    if (kind == LOC_FR) return ld256(reinterpret_cast<const uint4*>(row.addr[w]) + 2 * i);
+    const uint32_t word = reinterpret_cast<const uint32_t*>(row.addr[w])[i];
+    const uint32_t b = (word >> (row.loc[w] & 31u)) & 1u;
+    const Fr one = fr_one();
+    Fr r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = b ? one.v[k] : 0u;
+    return r;
+}
+PG_HD void row_prefetch(uint32_t loc, uint64_t addr, uint64_t i) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t kind = loc_kind(loc);
+    if (kind == LOC_FR) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint4*>(addr) + 2 * i));
+    else if (kind == LOC_BIT) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint32_t*>(addr) + i));
+#else
+    (void)loc; (void)addr; (void)i;
+#endif
 }
 // request the cache lines a later loc_load(tabs, loc, i) will touch (no destination registers)
 PG_HD void loc_prefetch(const DevTab* tabs, uint32_t loc, uint64_t i) {
