@@ -299,7 +299,8 @@ def main():
                          "frac": imad_achieved / wide_peak if wide_peak else None,
                          "peak_source": "measured in this run: IMAD.WIDE.U32 products on all SMs (pg_microbench mode 1); the kernel executes "
                                         "496 wide products per gate eval (dot-product reduction), so frac can exceed the executed-instruction share",
-                         "executed_wide_products_per_row": 424, "frac_executed": (rows_per_launch * 424 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
+                         "executed_wide_products_per_row": 425, "frac_executed": (rows_per_launch * 425 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
+                         "frac_executed_of_carry_chain_peak": (rows_per_launch * 425 / (check_ms * 1e-3)) / chain_peak if chain_peak else None,
                          "carry_chain_peak": chain_peak / 1e12, "imad_lo_peak": lo_peak / 1e12, "isolated_fr_mul_per_s": fr_mul_peak,
                          "traffic": ncu_traffic(args.log2n), "ms_per_launch": check_ms,
                          "hbm": {"kernel": "RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", "achieved": n * PACKED_BYTES_PER_INSTANCE / (wit_ms * 1e-3) / 1e9 if wit_ms else None,
