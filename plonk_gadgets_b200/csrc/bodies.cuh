@@ -218,6 +218,18 @@ struct CheckArgs {
     int mode;
 };
 
+// one shared (not inlined) multiplier body for the SPARSE path: it may multiply in up to six places per row, and six inlined
+// copies push the loop past the instruction cache
+#if defined(__CUDACC__)
+__device__ __noinline__ Fr fr_mul_shared(const Fr& a, const Fr& b, const QRegs& q) { return fr_mul_eo(a, b, q); }
+#endif
+PG_HD Fr fr_mul_sparse(const Fr& a, const Fr& b, const QRegs& q) {
+#if defined(__CUDA_ARCH__)
+    return fr_mul_shared(a, b, q);
+#else
+    return fr_mul_eo(a, b, q);
+#endif
+}
 // GENERIC mode evaluates  a*(q_m*b + q_l) + q_r*b + q_o*c + q_4*d + q_c + PI  -- the gate polynomial with the bilinear term
 // factored, five multiplications instead of six, still without looking at any selector value: one Montgomery
 // multiplication u = q_m*b (fully reduced, + q_l without reduction), then the four remaining products as ONE dot product with
@@ -227,8 +239,12 @@ struct CheckArgs {
 struct CheckBody {
     typedef CheckArgs Args;
     // evaluates all rows of instance i; returns the number of unsatisfied rows, updates first_bad (global row index)
-    template <int MODE, class PoolT>
-    PG_HD static uint32_t run(const Args& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
+    // MODE 0 = GENERIC (integer multiplier only), 1 = SPARSE, 2 = GENERIC HYBRID: the same five-multiplication evaluation with
+    // c*q_o + d*q_4 computed on the fp64 pipe (exact 22-bit-limb DFMA columns, fr.cuh) and injected into the integer dot
+    // product a*u + b*q_r: 112 + 128 + 48 = 288 wide integer products per row instead of 416, the rest on the otherwise idle
+    // DFMA pipe.  `pool_d(idx)` returns a pool entry as 12 double limbs.
+    template <int MODE, class PoolT, class PoolDT>
+    PG_HD static uint32_t run(const Args& a, const PoolT& pool, const PoolDT& pool_d, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t bad = 0;
         for (uint32_t r = 0; r < a.n_rows; r++) {
             const DevRow row = a.rows[r];
@@ -247,6 +263,20 @@ struct CheckBody {
 #pragma unroll
                 for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
                 fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
+            } else if (MODE == 2) {
+                uint32_t P[17];
+                {
+                    double acc[FP_COLS];
+#pragma unroll
+                    for (int k = 0; k < FP_COLS; k++) acc[k] = 0.0;
+                    fp_mul_acc(acc, fr_to_limbs22(w[3]), pool_d(row.sel[3]));                          // c*q_o
+                    fp_mul_acc(acc, fr_to_limbs22(w[4]), pool_d(row.sel[4]));                          // d*q_4
+                    fp_columns_to_limbs(P, acc);
+                }
+                Fr sel[2];
+                sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));      // q_m*b + q_l
+                sel[1] = pool(row.sel[2]);                                                             // q_r
+                fr_dot_wide_inject<2>(t, w + 1, sel, P, q);                                            // (a*u + b*q_r + P) / 2^256
             } else {
 #pragma unroll
                 for (int k = 0; k < 9; k++) t[k] = 0;
@@ -254,8 +284,8 @@ struct CheckBody {
                 for (int k = 0; k < 5; k++) {
                     const uint32_t si = row.sel[k];
                     if (si == POOL_ZERO) continue;
-                    const Fr v = k == 0 ? fr_mul_eo(w[1], w[2], q) : w[k];
-                    add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_eo(pool(si), v, q)));
+                    const Fr v = k == 0 ? fr_mul_sparse(w[1], w[2], q) : w[k];
+                    add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_sparse(pool(si), v, q)));
                 }
             }
             add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));
