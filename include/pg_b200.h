@@ -197,7 +197,7 @@ int pg_measure_imad_peak(pg_ctx *ctx, double *wide_mac_per_s, double *imad_per_s
 /* Pipe micro-benchmarks (operations per second on all SMs): mode 0 IMAD lo, 1 IMAD.WIDE product only, 2 IMAD.WIDE with
  * 64-bit accumulate, 3 IMAD.HI, 4 the mad.lo.cc/madc.hi.cc carry-chain rows of the Fr multiplier (per 32x32 product),
  * 5 IADD3, 6 Fr Montgomery multiplications (device multiplier), 7 the same through the portable CIOS code, 8 Fr additions,
- * 9 fp64 DFMA. */
+ * 9 fp64 DFMA, 10 IMAD.WIDE and DFMA interleaved 1:1 (both counted). */
 int pg_microbench(pg_ctx *ctx, int mode, double *ops_per_s);
 
 /* Element-wise Fr self-test kernels (op: 0 mul, 1 add, 2 sub, 3 neg, 4 invert-or-zero (batch inversion), 5 from_mont,

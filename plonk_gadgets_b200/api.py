@@ -273,7 +273,7 @@ class StandardComposer:
         self._ok(self._L.pg_measure_imad_peak(self._ctx, C.byref(w), C.byref(l)), "pg_measure_imad_peak")
         return w.value, l.value
 
-    MICROBENCH_MODES = ("imad_lo", "imad_wide_mul", "imad_wide_acc", "imad_hi", "carry_chain_product", "iadd3", "fr_mul", "fr_mul_cios", "fr_add", "dfma")
+    MICROBENCH_MODES = ("imad_lo", "imad_wide_mul", "imad_wide_acc", "imad_hi", "carry_chain_product", "iadd3", "fr_mul", "fr_mul_cios", "fr_add", "dfma", "imad_wide_plus_dfma_interleaved")
 
     def microbench(self, mode: int) -> float:
         v = C.c_double()

@@ -218,18 +218,6 @@ struct CheckArgs {
     int mode;
 };
 
-// one shared (not inlined) multiplier body for the SPARSE path: it may multiply in up to six places per row, and six inlined
-// copies push the loop past the instruction cache
-#if defined(__CUDACC__)
-__device__ __noinline__ Fr fr_mul_shared(const Fr& a, const Fr& b, const QRegs& q) { return fr_mul_eo(a, b, q); }
-#endif
-PG_HD Fr fr_mul_sparse(const Fr& a, const Fr& b, const QRegs& q) {
-#if defined(__CUDA_ARCH__)
-    return fr_mul_shared(a, b, q);
-#else
-    return fr_mul_eo(a, b, q);
-#endif
-}
 // GENERIC mode evaluates  a*(q_m*b + q_l) + q_r*b + q_o*c + q_4*d + q_c + PI  -- the gate polynomial with the bilinear term
 // factored, five multiplications instead of six, still without looking at any selector value: one Montgomery
 // multiplication u = q_m*b (fully reduced, + q_l without reduction), then the four remaining products as ONE dot product with
@@ -284,8 +272,8 @@ struct CheckBody {
                 for (int k = 0; k < 5; k++) {
                     const uint32_t si = row.sel[k];
                     if (si == POOL_ZERO) continue;
-                    const Fr v = k == 0 ? fr_mul_sparse(w[1], w[2], q) : w[k];
-                    add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_sparse(pool(si), v, q)));
+                    const Fr v = k == 0 ? fr_mul_eo(w[1], w[2], q) : w[k];
+                    add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_eo(pool(si), v, q)));
                 }
             }
             add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));

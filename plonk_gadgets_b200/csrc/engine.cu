@@ -209,7 +209,8 @@ public:
                 case 4: ubench_launch<4>(buf, blocks, iters, rep); break; case 5: ubench_launch<5>(buf, blocks, iters, rep); break;
                 case 6: ubench_launch<6>(buf, blocks, iters, rep); break; case 7: ubench_launch<7>(buf, blocks, iters, rep); break;
                 case 8: ubench_launch<8>(buf, blocks, iters, rep); break;
-                default: ubench_launch<9>(buf, blocks, iters, rep); break;
+                case 9: ubench_launch<9>(buf, blocks, iters, rep); break;
+                default: ubench_launch<10>(buf, blocks, iters, rep); break;
             }
             cudaEventRecord(b, stream);
             cudaEventSynchronize(b);

@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(BLOCK) k_materialize_tiled(const MatTileArgs a
 //   7 Fr Montgomery multiplication          acc = fr_mul_cios(acc, b) (portable 64-bit C)
 //   8 Fr addition                           acc = fr_add(acc, b)
 //   9 DFMA (fp64 fused multiply-add)        acc = acc*b + c          (the other wide multiplier on the SM, for reference)
-enum { UB_IMAD_LO = 0, UB_WIDE_MUL = 1, UB_WIDE_ACC = 2, UB_IMAD_HI = 3, UB_CARRY_ROWS = 4, UB_IADD3 = 5, UB_FR_MUL = 6, UB_FR_MUL_CIOS = 7, UB_FR_ADD = 8, UB_DFMA = 9, UB_MODES = 10 };
+//  10 IMAD.WIDE and DFMA interleaved 1:1    do the integer multiplier and the fp64 pipe run concurrently?  (ops = both kinds)
+enum { UB_IMAD_LO = 0, UB_WIDE_MUL = 1, UB_WIDE_ACC = 2, UB_IMAD_HI = 3, UB_CARRY_ROWS = 4, UB_IADD3 = 5, UB_FR_MUL = 6, UB_FR_MUL_CIOS = 7, UB_FR_ADD = 8, UB_DFMA = 9, UB_WIDE_DFMA_MIX = 10, UB_MODES = 11 };
 
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK) k_ubench(uint32_t* out, uint32_t x, uint32_t y, int iters) {
@@ -295,6 +296,19 @@ __global__ void __launch_bounds__(BLOCK) k_ubench(uint32_t* out, uint32_t x, uin
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) sink ^= (uint32_t)acc[k] ^ (uint32_t)(acc[k] >> 32);
+    } else if (MODE == UB_WIDE_DFMA_MIX) {
+        uint64_t acc[4]; double dacc[4]; const double fb = 1.0 + (double)(b & 0xffu) * 1e-9, fc = (double)(c & 0xffu) * 1e-3;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { acc[k] = ((uint64_t)(tid * (2 * k + 3) + x) << 32) | (tid + k); dacc[k] = (double)(tid + k); }
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[k]) : "r"(b));
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dacc[k]) : "d"(fb), "d"(fc));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) sink ^= (uint32_t)acc[k] ^ (uint32_t)(acc[k] >> 32) ^ (uint32_t)__double2ll_rn(dacc[k]);
     } else if (MODE == UB_DFMA) {
         double acc[8]; const double fb = 1.0 + (double)(b & 0xffu) * 1e-9, fc = (double)(c & 0xffu) * 1e-3;
 #pragma unroll
@@ -334,6 +348,6 @@ __global__ void __launch_bounds__(BLOCK) k_ubench(uint32_t* out, uint32_t x, uin
     out[tid] = sink;
 }
 // operations per thread per loop iteration in each mode
-__host__ __device__ constexpr int ubench_ops_per_iter(int mode) { return mode <= UB_IMAD_HI || mode == UB_IADD3 || mode == UB_DFMA ? 8 : (mode == UB_CARRY_ROWS ? 8 : 2); }
+__host__ __device__ constexpr int ubench_ops_per_iter(int mode) { return mode <= UB_IMAD_HI || mode == UB_IADD3 || mode == UB_DFMA || mode == UB_WIDE_DFMA_MIX ? 8 : (mode == UB_CARRY_ROWS ? 8 : 2); }
 
 }  // namespace pg
