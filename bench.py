@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=24, help="instances per GPU = 2^log2n (24 = the BASELINE metric configuration)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--check-mode", default="generic", choices=["generic", "sparse", "hybrid"])
+    ap.add_argument("--check-mode", default="generic", choices=["generic", "sparse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check-shape", type=int, default=0, help="launch shape of the gate-check kernel (tuning knob)")
     args = ap.parse_args()
@@ -189,7 +189,7 @@ def main():
     # one non-default torch stream shared with the engine: torch.cuda.Event and the engine's kernels see the same stream
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    mode = {"generic": pg.CHECK_GENERIC, "sparse": pg.CHECK_SPARSE, "hybrid": pg.CHECK_GENERIC_HYBRID}[args.check_mode]
+    mode = pg.CHECK_GENERIC if args.check_mode == "generic" else pg.CHECK_SPARSE
     c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream, check_shape=args.check_shape)
     assert stream.cuda_stream != 0
 

@@ -63,9 +63,8 @@ enum {
  *   GENERIC : q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + q_c + PI for arbitrary selector values, no selector inspected (what
  *             dusk-plonk's check_circuit_satisfied / quotient evaluation do); evaluated as a*(q_m*b + q_l) + q_r*b + q_o*c +
  *             q_4*d with one Montgomery multiplication and one four-term dot product sharing a single reduction.
- *   SPARSE  : skips products whose selector is the constant 0 and replaces products by +-1 with add/sub.
- *   GENERIC_HYBRID : GENERIC with two of the selector products (q_o*c, q_4*d) computed exactly on the fp64 pipe. */
-enum { PG_CHECK_GENERIC = 0, PG_CHECK_SPARSE = 1, PG_CHECK_GENERIC_HYBRID = 2 };
+ *   SPARSE  : skips products whose selector is the constant 0 and replaces products by +-1 with add/sub. */
+enum { PG_CHECK_GENERIC = 0, PG_CHECK_SPARSE = 1 };
 
 enum {
     PG_F_TIMING = 1u        /* record CUDA events around every kernel class (pg_get_timing) */

@@ -4,7 +4,7 @@ Only what the path needs: csrc/ (CUDA kernels + C ABI, built into libpg_b200.so)
 API over the C ABI) and this Python mirror used by the tests and the benchmark.  Importing the package does not load the
 CUDA library; creating a StandardComposer does, and fails loudly when it (or a B200) is missing -- there is no CPU path.
 """
-from .api import (AllocatedScalar, CHECK_GENERIC, CHECK_GENERIC_HYBRID, CHECK_SPARSE, DevicePtr, EngineError, Error, NonExistingInverse,  # noqa: F401
+from .api import (AllocatedScalar, CHECK_GENERIC, CHECK_SPARSE, DevicePtr, EngineError, Error, NonExistingInverse,  # noqa: F401
                   StandardComposer, Variables, conditionally_select_one, conditionally_select_zero, is_non_zero,
                   max_bound, maybe_equal, range_check)
 from . import _lib  # noqa: F401

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CHECK_GENERIC, CHECK_SPARSE, CHECK_GENERIC_HYBRID = 0, 1, 2
+CHECK_GENERIC, CHECK_SPARSE = 0, 1
 F_TIMING = 1
 UINT64_MAX = 2 ** 64 - 1
 

@@ -227,12 +227,8 @@ struct CheckArgs {
 struct CheckBody {
     typedef CheckArgs Args;
     // evaluates all rows of instance i; returns the number of unsatisfied rows, updates first_bad (global row index)
-    // MODE 0 = GENERIC (integer multiplier only), 1 = SPARSE, 2 = GENERIC HYBRID: the same five-multiplication evaluation with
-    // c*q_o + d*q_4 computed on the fp64 pipe (exact 22-bit-limb DFMA columns, fr.cuh) and injected into the integer dot
-    // product a*u + b*q_r: 112 + 128 + 48 = 288 wide integer products per row instead of 416, the rest on the otherwise idle
-    // DFMA pipe.  `pool_d(idx)` returns a pool entry as 12 double limbs.
-    template <int MODE, class PoolT, class PoolDT>
-    PG_HD static uint32_t run(const Args& a, const PoolT& pool, const PoolDT& pool_d, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
+    template <int MODE, class PoolT>
+    PG_HD static uint32_t run(const Args& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t bad = 0;
         for (uint32_t r = 0; r < a.n_rows; r++) {
             const DevRow row = a.rows[r];
@@ -251,20 +247,6 @@ struct CheckBody {
 #pragma unroll
                 for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
                 fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
-            } else if (MODE == 2) {
-                uint32_t P[17];
-                {
-                    double acc[FP_COLS];
-#pragma unroll
-                    for (int k = 0; k < FP_COLS; k++) acc[k] = 0.0;
-                    fp_mul_acc(acc, fr_to_limbs22(w[3]), pool_d(row.sel[3]));                          // c*q_o
-                    fp_mul_acc(acc, fr_to_limbs22(w[4]), pool_d(row.sel[4]));                          // d*q_4
-                    fp_columns_to_limbs(P, acc);
-                }
-                Fr sel[2];
-                sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));      // q_m*b + q_l
-                sel[1] = pool(row.sel[2]);                                                             // q_r
-                fr_dot_wide_inject<2>(t, w + 1, sel, P, q);                                            // (a*u + b*q_r + P) / 2^256
             } else {
 #pragma unroll
                 for (int k = 0; k < 9; k++) t[k] = 0;

@@ -63,16 +63,13 @@ public:
     bool set_check_attrs() {
         PG_CUDA(cudaFuncSetAttribute(k_check<0, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k_check<1, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        PG_CUDA(cudaFuncSetAttribute(k_check<2, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         return true;
     }
     template <int SHAPE>
     void launch_check(const CheckArgs& a, size_t smem) {
         constexpr int T = CheckShape<SHAPE>::BLOCK_T;
         const unsigned grid = (unsigned)((a.n_inst + T - 1) / T);
-        if (a.mode == PG_CHECK_SPARSE) k_check<1, SHAPE><<<grid, T, smem, stream>>>(a);
-        else if (a.mode == PG_CHECK_GENERIC_HYBRID) k_check<2, SHAPE><<<grid, T, smem, stream>>>(a);
-        else k_check<0, SHAPE><<<grid, T, smem, stream>>>(a);
+        if (a.mode == PG_CHECK_SPARSE) k_check<1, SHAPE><<<grid, T, smem, stream>>>(a); else k_check<0, SHAPE><<<grid, T, smem, stream>>>(a);
     }
     void shutdown() {
         for (auto& ev : events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -167,7 +164,7 @@ public:
         return launched("k_batch_inv");
     }
     bool run_check(const CheckArgs& a) {
-        const size_t smem = (size_t)a.n_pool * (sizeof(Fr) + (a.mode == PG_CHECK_GENERIC_HYBRID ? FP_LIMBS * sizeof(double) : 0));
+        const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         tic(CLS_CHECK, a.n_inst * a.n_rows);
         switch (check_shape) {

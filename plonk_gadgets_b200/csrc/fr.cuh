@@ -504,51 +504,6 @@ PG_HD void fr_dot_wide(uint32_t* r, const Fr* a, const Fr* b, const QRegs& q) {
 #undef PG_DOT_STEP
     dmerge(r, odd, even, z);          // the last step cleared odd[0]: value = (odd >> 32) + even + (z << 256)
 }
-// The same with a plain (non-Montgomery-reduced) 17-limb integer P injected: r = (sum_p a[p]*b[p] + P) / 2^256 mod q up to a
-// multiple of q.  P[0..7] seed the even array, P[8+i] enters at the top of the window in step i, P[16] lands in r[8].
-#if defined(__CUDA_ARCH__)
-PG_D void dadd_top(uint32_t& y7, uint32_t& z, uint32_t v) { asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+r"(y7), "+r"(z) : "r"(v)); }
-#else
-inline void dadd_top(uint32_t& y7, uint32_t& z, uint32_t v) {
-    const uint64_t s = (uint64_t)y7 + v; y7 = (uint32_t)s;
-    if (z + (uint32_t)(s >> 32) < z) PG_EMU_VIOLATION();
-    z += (uint32_t)(s >> 32);
-}
-#endif
-template <int K, bool FIRST>
-PG_HD void dot_step_inject(uint32_t* X, uint32_t* Y, uint32_t& z, const Fr* a, const uint32_t* bi, uint32_t p_top, const QRegs& q) {
-    if (!FIRST) {
-        dmad_row_shift(Y, X[0], z, a[0].v[1], a[0].v[3], a[0].v[5], a[0].v[7], bi[0]);
-        dmad_row_x(X, Y[7], z, a[0].v[0], a[0].v[2], a[0].v[4], a[0].v[6], bi[0]);
-    }
-#pragma unroll
-    for (int p = FIRST ? 0 : 1; p < K; p++) {
-        dmad_row_y(Y, z, a[p].v[1], a[p].v[3], a[p].v[5], a[p].v[7], bi[p]);
-        dmad_row_x(X, Y[7], z, a[p].v[0], a[p].v[2], a[p].v[4], a[p].v[6], bi[p]);
-    }
-    dadd_top(Y[7], z, p_top);
-    dred_rows(X, Y, z, q);
-}
-template <int K>
-PG_HD void fr_dot_wide_inject(uint32_t* r, const Fr* a, const Fr* b, const uint32_t* P, const QRegs& q) {
-    uint32_t even[8], odd[8], z = 0, bi[K];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { even[k] = P[k]; odd[k] = 0; }
-#define PG_DOT_STEP(I, XX, YY, FIRST)                          \
-    _Pragma("unroll") for (int p = 0; p < K; p++) bi[p] = b[p].v[I]; \
-    dot_step_inject<K, FIRST>(XX, YY, z, a, bi, P[8 + I], q);
-    PG_DOT_STEP(0, even, odd, true)
-    PG_DOT_STEP(1, odd, even, false)
-    PG_DOT_STEP(2, even, odd, false)
-    PG_DOT_STEP(3, odd, even, false)
-    PG_DOT_STEP(4, even, odd, false)
-    PG_DOT_STEP(5, odd, even, false)
-    PG_DOT_STEP(6, even, odd, false)
-    PG_DOT_STEP(7, odd, even, false)
-#undef PG_DOT_STEP
-    dmerge(r, odd, even, z);
-    r[8] += P[16];
-}
 template <int K>
 PG_HD void fr_dot_wide(uint32_t* r, const Fr* a, const Fr* b) { fr_dot_wide<K>(r, a, b, q_regs_default()); }
 // plain 256-bit addition a + b (no reduction); the caller guarantees a + b < 2^256 (e.g. both < q)
@@ -565,83 +520,6 @@ PG_HD Fr fr_add_noreduce(const Fr& a, const Fr& b) {
 #endif
     return r;
 }
-// ---- fp64-pipe products (hybrid gate check) -----------------------------------------------------------------------------
-// The integer multiplier (fmaheavy) is the bound of the gate check; the fp64 pipe next to it is idle (DFMA 57.9/SM/clk,
-// pg_microbench mode 9).  A 256-bit integer is cut into 12 limbs of 22 bits held as doubles; limb products are < 2^44, a
-// column of the schoolbook product of TWO operand pairs sums at most 24 of them (< 2^49), so every DFMA below is exact.
-// The 23 columns are carry-normalised in the double domain (floor by the 2^52 trick, no integer instructions) and packed
-// into 32-bit limbs; the resulting plain product P = x1*s1 + x2*s2 (17 limbs) is then *injected* into the Montgomery
-// dot product, which divides everything by 2^256 together.
-constexpr int FP_LIMBS = 12;           // 12 x 22 = 264 bits
-constexpr int FP_COLS = 2 * FP_LIMBS - 1;
-struct FrD { double d[FP_LIMBS]; };    // 22-bit limbs of the 256-bit integer (the Montgomery representative), as doubles
-
-PG_HD double fp_from_u32(uint32_t v) {  // exact conversion of v < 2^32 without I2F: (2^52 + v) - 2^52
-#if defined(__CUDA_ARCH__)
-    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
-#else
-    return (double)v;
-#endif
-}
-PG_HD uint32_t fp_to_u32(double x) {    // exact integer 0 <= x < 2^32 -> its value: low word of (x + 2^52)
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)__double2loint(x + 4503599627370496.0);
-#else
-    return (uint32_t)(uint64_t)x;
-#endif
-}
-PG_HD double fp_fma(double a, double b, double c) {
-#if defined(__CUDA_ARCH__)
-    return __fma_rn(a, b, c);
-#else
-    return __builtin_fma(a, b, c);
-#endif
-}
-PG_HD FrD fr_to_limbs22(const Fr& x) {
-    FrD r;
-#pragma unroll
-    for (int k = 0; k < FP_LIMBS; k++) {
-        const int bit = 22 * k, j = bit >> 5, sh = bit & 31;
-        uint32_t v = x.v[j] >> sh;
-        if (sh > 10 && j + 1 < 8) v |= x.v[j + 1] << (32 - sh);
-        r.d[k] = fp_from_u32(v & 0x3fffffu);
-    }
-    return r;
-}
-// acc[i+j] += x[i] * s[j]   (144 exact DFMAs)
-PG_HD void fp_mul_acc(double* acc, const FrD& x, const FrD& s) {
-#pragma unroll
-    for (int j = 0; j < FP_LIMBS; j++)
-#pragma unroll
-        for (int i = 0; i < FP_LIMBS; i++) acc[i + j] = fp_fma(x.d[i], s.d[j], acc[i + j]);
-}
-// columns (exact integers < 2^50) -> 17 x 32-bit limbs of sum_k acc[k] * 2^(22k)
-PG_HD void fp_columns_to_limbs(uint32_t* P, const double* acc) {
-    uint32_t dig[FP_COLS + 2];                       // 22-bit digits; the final carry (< 2^28) goes into two more digits
-    double carry = 0.0;
-#pragma unroll
-    for (int k = 0; k < FP_COLS; k++) {
-        const double t = acc[k] + carry;                                             // exact, < 2^51
-        // floor(t / 2^22): t*2^-22 - 0.5 + 2^-23 is never a tie, so round-to-nearest in the [2^52, 2^53) binade floors it
-        const double y = fp_fma(t, 2.384185791015625e-07, -0.49999988079071045);     // 2^-22, -(0.5 - 2^-23)
-        carry = (y + 6755399441055744.0) - 6755399441055744.0;                        // 1.5 * 2^52: ulp 1 on both sides of 0
-        dig[k] = fp_to_u32(fp_fma(carry, -4194304.0, t));                            // t - carry*2^22, in [0, 2^22)
-    }
-    const uint32_t c = fp_to_u32(carry);
-    dig[FP_COLS] = c & 0x3fffffu; dig[FP_COLS + 1] = c >> 22;
-#pragma unroll
-    for (int m = 0; m < 17; m++) {                   // limb m = bits [32m, 32m+32) of the digit string
-        uint32_t v = 0;
-#pragma unroll
-        for (int k = 0; k < FP_COLS + 2; k++) {
-            const int lo = 22 * k - 32 * m;          // bit offset of digit k inside limb m
-            if (lo >= 32 || lo + 22 <= 0) continue;
-            v |= lo >= 0 ? dig[k] << lo : dig[k] >> (-lo);
-        }
-        P[m] = v;
-    }
-}
-
 // k*q for k = 0..15 (9 limbs each): since q0 = 1, k*q = k (mod 2^32), so a 9-limb r is 0 mod q iff r == k*q for k = r[0] (r < 16q)
 PG_HD bool limbs9_is_multiple_of_q(const uint32_t* r) {
     const uint32_t k = r[0];

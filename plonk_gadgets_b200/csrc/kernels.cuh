@@ -107,16 +107,6 @@ struct SmemPool {
     }
 };
 
-struct SmemPoolD {
-    const double* p;
-    __device__ __forceinline__ FrD operator()(uint32_t idx) const {
-        FrD r;
-#pragma unroll
-        for (int k = 0; k < FP_LIMBS; k++) r.d[k] = p[FP_LIMBS * idx + k];
-        return r;
-    }
-};
-
 // One instance per thread; the row template is walked by all threads in lock step (selector pool in shared memory,
 // template rows read with warp-uniform addresses), wire values come from the SoA variable table with coalesced loads.
 // Launch shapes of the gate-check kernel: threads per block x minimum blocks per SM (=> register budget, warps per SM).
@@ -131,19 +121,10 @@ constexpr int CHECK_SHAPES = 5;
 template <int MODE, int SHAPE>
 __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>::MIN_BLOCKS) k_check(const CheckArgs a) {
     constexpr int CHECK_BLOCK = CheckShape<SHAPE>::BLOCK_T;
-    extern __shared__ __align__(16) uint32_t s_pool[];               // n_pool x 8 u32, then (hybrid mode) n_pool x 12 doubles
+    extern __shared__ __align__(16) uint32_t s_pool[];
     __shared__ uint32_t s_q[8];
     for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += CHECK_BLOCK) s_pool[t] = a.pool[t];
     if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
-    double* s_pool_d = reinterpret_cast<double*>(s_pool + a.n_pool * 8);
-    if (MODE == 2) {                                                  // selector constants as 22-bit double limbs for the fp64 path
-        for (uint32_t t = threadIdx.x; t < a.n_pool * FP_LIMBS; t += CHECK_BLOCK) {
-            const uint32_t e = t / FP_LIMBS, k = t % FP_LIMBS, bit = 22 * k, j = bit >> 5, sh = bit & 31;
-            uint32_t v = a.pool[8 * e + j] >> sh;
-            if (sh > 10 && j + 1 < 8) v |= a.pool[8 * e + j + 1] << (32 - sh);
-            s_pool_d[t] = fp_from_u32(v & 0x3fffffu);
-        }
-    }
     __syncthreads();
     QRegs q;                                   // modulus limbs in vector registers (see QRegs in fr.cuh)
 #pragma unroll
@@ -151,7 +132,7 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
     const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
-    if (i < a.n_inst) { SmemPool pool = {s_pool}; SmemPoolD pool_d = {s_pool_d}; bad = CheckBody::run<MODE>(a, pool, pool_d, q, i, first_bad); }
+    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, q, i, first_bad); }
     // warp-level reduction, then one atomic per warp that saw a violation
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -20,10 +20,6 @@ struct HostPool {
     const uint32_t* p;
     Fr operator()(uint32_t idx) const { return pool_load(p, idx); }
 };
-struct HostPoolD {
-    const uint32_t* p;
-    FrD operator()(uint32_t idx) const { return fr_to_limbs22(pool_load(p, idx)); }
-};
 
 class HostBackend {
 public:
@@ -62,8 +58,7 @@ public:
         for (uint64_t i = 0; i < a.n_inst; i++) {
             unsigned long long fb = ~0ull;
             const QRegs q = q_regs_default();
-            HostPoolD pool_d = {a.pool};
-            const uint32_t bad = a.mode == 1 ? CheckBody::run<1>(a, pool, pool_d, q, i, fb) : (a.mode == 2 ? CheckBody::run<2>(a, pool, pool_d, q, i, fb) : CheckBody::run<0>(a, pool, pool_d, q, i, fb));
+            const uint32_t bad = a.mode ? CheckBody::run<1>(a, pool, q, i, fb) : CheckBody::run<0>(a, pool, q, i, fb);
             if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
         }
         return true;

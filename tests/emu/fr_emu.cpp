@@ -29,24 +29,5 @@ void emu_dot5(uint64_t n, const Fr* a, const Fr* b, const Fr* c, uint32_t* r9, u
         is_mult[i] = pg::limbs9_is_multiple_of_q(r) ? 1 : 0;
     }
 }
-// hybrid: P = x1*s1 + x2*s2 through the fp64 path (17 limbs), and r = (a1*b1 + a2*b2 + P)/2^256 through the injected dot product
-void emu_fp_dot2(uint64_t n, const Fr* x, const Fr* s, uint32_t* P17) {
-    for (uint64_t i = 0; i < n; i++) {
-        double acc[pg::FP_COLS];
-        for (int k = 0; k < pg::FP_COLS; k++) acc[k] = 0.0;
-        pg::fp_mul_acc(acc, pg::fr_to_limbs22(x[2 * i]), pg::fr_to_limbs22(s[2 * i]));
-        pg::fp_mul_acc(acc, pg::fr_to_limbs22(x[2 * i + 1]), pg::fr_to_limbs22(s[2 * i + 1]));
-        pg::fp_columns_to_limbs(P17 + 17 * i, acc);
-    }
-}
-void emu_dot2_inject(uint64_t n, const Fr* a, const Fr* b, const uint32_t* P17, const Fr* c, uint32_t* r9, uint8_t* is_mult) {
-    for (uint64_t i = 0; i < n; i++) {
-        uint32_t r[9];
-        pg::fr_dot_wide_inject<2>(r, a + 2 * i, b + 2 * i, P17 + 17 * i, pg::q_regs_default());
-        pg::add9_fr(r, c[i]);
-        for (int k = 0; k < 9; k++) r9[9 * i + k] = r[k];
-        is_mult[i] = pg::limbs9_is_multiple_of_q(r) ? 1 : 0;
-    }
-}
 void emu_to_mont(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_to_mont(a[i]); }
 }
