@@ -196,3 +196,40 @@ def test_emu_check_modes_agree(emu, golden, oracle, mode):
         spec = golden[name]
         snap = run_engine(spec["program"], lambda: pg.StandardComposer(check_mode=mode, _cdll=emu), oracle)
         assert snap.unsat == spec["expected"]["unsat"], name
+
+
+def test_emu_degenerate_num_bits(emu, oracle):
+    """bitlen(max-1) = 255: 2^255 wraps mod q and the reference's num_bits_closest_power_of_two returns bitlen(2^255 mod q)
+    (SURVEY.md 8a row a7).  The engine must follow the reference into that corner, uniform and per-instance bounds alike."""
+    mx = 2 ** 254 + 12345
+    k_ref = (2 ** 255 % Q).bit_length()
+    prog = [dict(op="add_input", values=[hx(5), hx(2 ** 254), hx(Q - 1)]), dict(op="max_bound", max=hx(mx), witness=0),
+            dict(op="range_check", min=[hx(1), hx(2), hx(3)], max=[hx(mx), hx(mx + 1), hx(Q - 1)], witness=0)]
+    so = run_oracle(prog)
+    se = run_engine(prog, lambda: pg.StandardComposer(_cdll=emu), oracle)
+    assert se.digest() == so.digest() and se.unsat == so.unsat == []
+    assert so.n_rows == 3 + (2 * k_ref + 5) * 3 + (4 * k_ref + 11) * 3
+
+
+def _empty_and_ragged(make_composer, oracle):
+    """Empty batches append nothing; ragged batch sizes (1, 31, 33, 257) hit every tail path of the kernels."""
+    c = make_composer()
+    e = c.add_input(np.empty((0, 4), dtype=np.uint64))
+    y = pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), e)
+    m = pg.maybe_equal(c, e, y)
+    pg.is_non_zero(c, e, np.empty((0, 4), dtype=np.uint64))
+    c.constrain_to_constant(m, oracle.from_ints([1]))
+    assert (y.n, m.n) == (0, 0) and c.circuit_size() == 3 and c.num_variables() == 5
+    assert c.check_circuit_satisfied() == (0, None)
+    assert c.rows()["w_idx"].shape == (4, 3) and y.values().shape == (0, 4)
+    for n in (1, 31, 33, 257):
+        vals = [v % 2 ** 70 for v in synth_wide(n, n)]
+        prog = [dict(op="add_input", values=[hx(v) for v in vals]), dict(op="range_check", min=hx(3), max=hx(2 ** 64), witness=0),
+                dict(op="maybe_equal", a=0, b=1), dict(op="select_one", y=0, select=1)]
+        so = run_oracle(prog)
+        se = run_engine(prog, make_composer, oracle)
+        assert se.digest() == so.digest() and se.unsat == so.unsat == [], n
+
+
+def test_emu_empty_and_ragged(emu, oracle):
+    _empty_and_ragged(lambda: pg.StandardComposer(_cdll=emu), oracle)

@@ -359,3 +359,8 @@ def test_check_modes_at_scale(oracle, torch_cuda, mode):
     c.constrain_to_constant(sub, claims)
     bad, first = c.check_circuit_satisfied()
     assert bad == 2 and first == 3 + 271 * n + 3
+
+
+def test_empty_and_ragged_gpu(oracle):
+    from tests.test_emu_engine import _empty_and_ragged
+    _empty_and_ragged(gpu_composer, oracle)
