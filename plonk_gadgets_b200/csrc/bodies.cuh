@@ -226,48 +226,62 @@ struct CheckArgs {
 // SPARSE mode: products whose selector is the constant 0 are skipped, selectors +-1 become additions.
 struct CheckBody {
     typedef CheckArgs Args;
+    // gate equation of row `row` for instance i: true iff it holds
+    template <int MODE, class PoolT>
+    PG_HD static bool row_holds(const Args& a, const DevRow& row, const PoolT& pool, const QRegs& q, uint64_t i) {
+        Fr w[5];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
+        uint32_t t[9];
+        if (MODE == 0) {
+            Fr sel[4];
+            sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));   // q_m*b + q_l  (< 2q < 2^256)
+#pragma unroll
+            for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
+            fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) t[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const uint32_t si = row.sel[k];
+                if (si == POOL_ZERO) continue;
+                const Fr v = k == 0 ? fr_mul_eo(w[1], w[2], q) : w[k];
+                add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_eo(pool(si), v, q)));
+            }
+        }
+        add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));
+        if (row.pi_param >= 0) add9_fr(t, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
+        else if (row.pi_sel != POOL_ZERO) add9_fr(t, pool(row.pi_sel));
+        return limbs9_is_multiple_of_q(t);
+    }
     // evaluates all rows of instance i; returns the number of unsatisfied rows, updates first_bad (global row index)
     template <int MODE, class PoolT>
     PG_HD static uint32_t run(const Args& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t bad = 0;
         for (uint32_t r = 0; r < a.n_rows; r++) {
             const DevRow row = a.rows[r];
-            Fr w[5];
             if (r + 1 < a.n_rows) {            // request the next row's wire values now: ~2000 multiplier cycles cover the latency
                 const DevRow& nr = a.rows[r + 1];
 #pragma unroll
                 for (int k = 0; k < 4; k++) row_prefetch(nr.loc[k], nr.addr[k], i);
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
-            uint32_t t[9];
-            if (MODE == 0) {
-                Fr sel[4];
-                sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));   // q_m*b + q_l  (< 2q < 2^256)
-#pragma unroll
-                for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
-                fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
-            } else {
-#pragma unroll
-                for (int k = 0; k < 9; k++) t[k] = 0;
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const uint32_t si = row.sel[k];
-                    if (si == POOL_ZERO) continue;
-                    const Fr v = k == 0 ? fr_mul_eo(w[1], w[2], q) : w[k];
-                    add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_eo(pool(si), v, q)));
-                }
-            }
-            add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));
-            if (row.pi_param >= 0) add9_fr(t, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
-            else if (row.pi_sel != POOL_ZERO) add9_fr(t, pool(row.pi_sel));
-            if (!limbs9_is_multiple_of_q(t)) {
+            if (!row_holds<MODE>(a, row, pool, q, i)) {
                 bad++;
                 const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
                 if (g < first_bad) first_bad = g;
             }
         }
         return bad;
+    }
+    // one (instance, row) pair per call: the mapping used for segments too small to fill the GPU with one thread per instance
+    template <int MODE, class PoolT>
+    PG_HD static uint32_t run_one(const Args& a, const PoolT& pool, const QRegs& q, uint64_t t, unsigned long long& first_bad) {
+        const uint64_t i = t / a.n_rows; const uint32_t r = (uint32_t)(t - i * a.n_rows);
+        const DevRow row = a.rows[r];
+        if (row_holds<MODE>(a, row, pool, q, i)) return 0u;
+        first_bad = a.base_row + t;
+        return 1u;
     }
 };
 

@@ -56,6 +56,8 @@ public:
         PG_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
         check_shape = cfg.reserved < (uint32_t)CHECK_SHAPES ? (int)cfg.reserved : 0;
+        PG_CUDA(cudaFuncSetAttribute(k_check_rowpar<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check_rowpar<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         if (!set_check_attrs<0>() || !set_check_attrs<1>() || !set_check_attrs<2>() || !set_check_attrs<3>() || !set_check_attrs<4>()) return false;
         return true;
     }
@@ -167,6 +169,13 @@ public:
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         tic(CLS_CHECK, a.n_inst * a.n_rows);
+        if (a.n_inst < (uint64_t)sm_count * 320 && a.n_rows > 1) {      // fewer instances than half the resident threads: one thread per row
+            const uint64_t total = a.n_inst * a.n_rows;
+            const unsigned grid = (unsigned)((total + 127) / 128);
+            if (a.mode == PG_CHECK_SPARSE) k_check_rowpar<1><<<grid, 128, smem, stream>>>(a); else k_check_rowpar<0><<<grid, 128, smem, stream>>>(a);
+            toc();
+            return launched("k_check_rowpar");
+        }
         switch (check_shape) {
             case 1: launch_check<1>(a, smem); break; case 2: launch_check<2>(a, smem); break;
             case 3: launch_check<3>(a, smem); break; case 4: launch_check<4>(a, smem); break;

@@ -55,9 +55,17 @@ public:
     }
     bool run_check(const CheckArgs& a) {
         HostPool pool = {a.pool};
+        const QRegs q = q_regs_default();
+        if (a.n_inst < 48 && a.n_rows > 1) {            // the row-parallel mapping (thread = one row of one instance), as for small segments on the GPU
+            for (uint64_t t = 0; t < a.n_inst * a.n_rows; t++) {
+                unsigned long long fb = ~0ull;
+                const uint32_t bad = a.mode ? CheckBody::run_one<1>(a, pool, q, t, fb) : CheckBody::run_one<0>(a, pool, q, t, fb);
+                if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
+            }
+            return true;
+        }
         for (uint64_t i = 0; i < a.n_inst; i++) {
             unsigned long long fb = ~0ull;
-            const QRegs q = q_regs_default();
             const uint32_t bad = a.mode ? CheckBody::run<1>(a, pool, q, i, fb) : CheckBody::run<0>(a, pool, q, i, fb);
             if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
         }
