@@ -116,15 +116,8 @@ public:
         if (!ev_free.empty()) { cudaEvent_t e = ev_free.back(); ev_free.pop_back(); return e; }
         cudaEvent_t e; cudaEventCreate(&e); return e;
     }
-    void tic(int cls, uint64_t rows) {
-        if (!timing_on) return;
-        Ev ev{get_event(), get_event(), cls, rows};
-        cudaEventRecord(ev.a, stream);
-        events.push_back(ev);
-    }
-    void toc() { if (timing_on) cudaEventRecord(events.back().b, stream); }
-    bool timing(pg_timing* out, bool reset) {
-        PG_CUDA(cudaStreamSynchronize(stream));
+    void fold_events() {                         // resolve recorded event pairs into the accumulators (synchronises)
+        cudaStreamSynchronize(stream);
         for (auto& ev : events) {
             float ms = 0.f; cudaEventElapsedTime(&ms, ev.a, ev.b);
             if (ev.cls == CLS_CHECK) { acc.check_ms += ms; acc.check_launches++; acc.check_rows += ev.rows; }
@@ -133,6 +126,18 @@ public:
             ev_free.push_back(ev.a); ev_free.push_back(ev.b);
         }
         events.clear();
+    }
+    void tic(int cls, uint64_t rows) {
+        if (!timing_on) return;
+        if (events.size() >= 4096) fold_events();    // bounded bookkeeping when nobody collects the timings
+        Ev ev{get_event(), get_event(), cls, rows};
+        cudaEventRecord(ev.a, stream);
+        events.push_back(ev);
+    }
+    void toc() { if (timing_on) cudaEventRecord(events.back().b, stream); }
+    bool timing(pg_timing* out, bool reset) {
+        PG_CUDA(cudaStreamSynchronize(stream));
+        fold_events();
         *out = acc;
         if (reset) acc = pg_timing{};
         return true;
