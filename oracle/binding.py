@@ -65,6 +65,8 @@ def lib():
             "orc_fr_from_bytes_many": (i32, [u64, vp, vp]), "orc_fr_to_bytes_many": (None, [u64, vp, vp]),
             "orc_fr_from_bytes_wide_many": (None, [u64, vp, vp]),
             "orc_bits_count_api": (u64, [vp]), "orc_num_bits_api": (u64, [vp]),
+            "orc_fft": (i32, [vp, C.c_uint, i32]), "orc_domain_group_gen": (None, [C.c_uint, vp]),
+            "orc_domain_log_size": (C.c_uint, [u64]), "orc_wire_polynomials": (C.c_uint, [vp, vp]),
             "orc_bench_range": (dbl, [i32, u64, vp, vp, vp, i32, i32, i32, u64, vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
@@ -244,8 +246,32 @@ class Composer:
                 u = 0
         lib().orc_constrain_to_constant_batch(self._c, len(vars_), _p(vars_), _p(k), _p(pi) if pi is not None else None, u)
 
+    def wire_polynomials(self) -> np.ndarray:
+        """(4, 2^k, 4) uint64: coefficients of w_l, w_r, w_o, w_4 over the padded evaluation domain (oracle/fft.c)."""
+        L = lib()
+        size = 1 << L.orc_domain_log_size(self.n)
+        out = np.zeros((4, size, 4), dtype=np.uint64)
+        L.orc_wire_polynomials(self._c, _p(out))
+        return out
+
     def decomposition(self, num_bits: int, var: int) -> int:
         return lib().orc_decomposition_api(self._c, num_bits, var)
+
+
+def fft(a, inverse: bool = False) -> np.ndarray:
+    """EvaluationDomain::fft / ifft of a vector of 2^k Montgomery scalars ((n, 4) uint64); returns a new array."""
+    a = np.ascontiguousarray(_fr_arr(a)).copy()
+    n = a.shape[0]
+    assert n and n & (n - 1) == 0
+    rc = lib().orc_fft(_p(a), n.bit_length() - 1, 1 if inverse else 0)
+    assert rc == 0
+    return a
+
+
+def domain_group_gen(log_n: int) -> int:
+    out = np.zeros((1, 4), dtype=np.uint64)
+    lib().orc_domain_group_gen(log_n, _p(out))
+    return to_ints(out)[0]
 
 
 def bench_range(gadget: int, wit, mn, mx, threads: int, mode: int = FAITHFUL, chunk: int = 64, want_results=False):

@@ -312,3 +312,46 @@ def range_check(composer, min_range: int, max_range: int, witness: AllocatedScal
     y1, num_bits = max_bound(composer, max_range, witness)
     y2 = min_bound(composer, min_range, witness, num_bits)
     return composer.mul(1, y1, y2, 0, None)
+
+
+# ------------------------------------------------------------------------------------------------ evaluation domain
+# [DEP] dusk-plonk 0.8 src/fft/domain.rs (EvaluationDomain) and the first step of Prover::prove, reached from
+# /root/reference/tests/range_gadgets_tests.rs:90-91.  Independent of oracle/fft.c: plain O(n^2) DFT sums on Python ints.
+TWO_ADICITY = 32
+GENERATOR = 7
+ROOT_OF_UNITY = pow(GENERATOR, (Q - 1) >> TWO_ADICITY, Q)
+
+
+def domain_log_size(circuit_size: int) -> int:
+    return max(circuit_size - 1, 0).bit_length()          # log2(next_power_of_two)
+
+
+def group_gen(log_n: int) -> int:
+    assert log_n <= TWO_ADICITY
+    return pow(ROOT_OF_UNITY, 1 << (TWO_ADICITY - log_n), Q)
+
+
+def dft(values, inverse: bool = False):
+    """EvaluationDomain::fft (A_k = sum_j a_j w^(jk)) / ifft (w^-1 and a factor n^-1) by the defining sums."""
+    n = len(values)
+    assert n and n & (n - 1) == 0
+    log_n = n.bit_length() - 1
+    w = group_gen(log_n)
+    if inverse:
+        w = pow(w, Q - 2, Q)
+    pw = [pow(w, e, Q) for e in range(n)]
+    out = [sum(values[j] * pw[(j * k) % n] for j in range(n)) % Q for k in range(n)]
+    if inverse:
+        n_inv = pow(n, Q - 2, Q)
+        out = [x * n_inv % Q for x in out]
+    return out
+
+
+def wire_polynomials(composer: "StandardComposer"):
+    """Coefficient vectors of w_l, w_r, w_o, w_4: wire values zero-padded to the domain size, then ifft."""
+    size = 1 << domain_log_size(composer.n)
+    cols = []
+    for wires in (composer.w_l, composer.w_r, composer.w_o, composer.w_4):
+        vals = [composer.variables[v] for v in wires] + [0] * (size - composer.n)
+        cols.append(dft(vals, inverse=True))
+    return cols

@@ -223,32 +223,75 @@ struct CheckArgs {
 // multiplication u = q_m*b (fully reduced, + q_l without reduction), then the four remaining products as ONE dot product with
 // a single interleaved reduction (fr_dot_wide): 64+48 + 4*64+48 = 416 wide multiplier instructions per row instead of
 // 6*(64+64).  The 9-limb result plus q_c and PI is tested for "0 mod q" directly.
-// SPARSE mode: products whose selector is the constant 0 are skipped, selectors +-1 become additions.
+// SPARSE mode: structure-aware, see sparse_terms.
 struct CheckBody {
     typedef CheckArgs Args;
     // gate equation of row `row` for instance i: true iff it holds
+    // 0 or ~0 according to the bit variable behind wire w
+    PG_HD static uint32_t wire_bit_mask(const DevRow& row, int w, uint64_t i) {
+        const uint32_t word = reinterpret_cast<const uint32_t*>(row.addr[w])[i];
+        return 0u - ((word >> (row.loc[w] & 31u)) & 1u);
+    }
+    PG_HD static Fr wire_fr(const DevRow& row, int w, uint64_t i) { return ld256(reinterpret_cast<const uint4*>(row.addr[w]) + 2 * i); }
+
+    // Structure-aware evaluation: the same polynomial on the same stored values, but a term costs what its structure needs.
+    //  * selector is the constant 0, or the wire is the zero variable: nothing (the value is not even loaded);
+    //  * the wire is a packed bit variable (its value is 0 or 1 by construction): selector AND mask, no multiplication;
+    //  * selector +-1: addition / subtraction;   * otherwise: one Montgomery multiplication.
+    // All decisions are taken on the row template, i.e. they are uniform across the warp.  One multiplier site in a rolled loop.
+    template <class PoolT>
+    PG_HD static void sparse_terms(uint32_t (&t)[9], const DevRow& row, const PoolT& pool, const QRegs& q, uint64_t i) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) t[k] = 0;
+#pragma unroll 1
+        for (int k = 0; k < 5; k++) {
+            const uint32_t si = row.sel[k];
+            const int w = k ? k - 1 : 0;
+            const uint32_t kind = loc_kind(row.loc[w]);
+            if (si == POOL_ZERO || kind == LOC_ZERO) continue;
+            uint32_t mask = ~0u;                 // product of the bit-valued factors
+            bool have_v = false; Fr v = fr_zero();  // product of the scalar-valued factors (so far at most one)
+            int n_mul = 0; Fr x = fr_zero();
+            if (kind == LOC_BIT) mask = wire_bit_mask(row, w, i); else { v = wire_fr(row, w, i); have_v = true; }
+            if (k == 0) {                        // bilinear term: times w_r
+                const uint32_t kb = loc_kind(row.loc[1]);
+                if (kb == LOC_ZERO) continue;
+                if (kb == LOC_BIT) mask &= wire_bit_mask(row, 1, i);
+                else if (!have_v) { v = wire_fr(row, 1, i); have_v = true; }
+                else { x = wire_fr(row, 1, i); n_mul = 1; }
+            }
+            const bool general = si != POOL_ONE && si != POOL_MINUS_ONE;
+            if (!have_v) {                       // bits only: the term is the selector or nothing
+                Fr sv = pool(si);
+#pragma unroll
+                for (int j = 0; j < 8; j++) sv.v[j] &= mask;
+                add9_fr(t, sv);
+                continue;
+            }
+            if (general) { if (n_mul == 0) x = pool(si); n_mul++; }
+            for (int p = 0; p < n_mul; p++) { v = fr_mul_eo(x, v, q); x = pool(si); }
+            if (si == POOL_MINUS_ONE) v = fr_neg(v);
+#pragma unroll
+            for (int j = 0; j < 8; j++) v.v[j] &= mask;
+            add9_fr(t, v);
+        }
+    }
+
+    // gate equation of row `row` for instance i: true iff it holds
     template <int MODE, class PoolT>
     PG_HD static bool row_holds(const Args& a, const DevRow& row, const PoolT& pool, const QRegs& q, uint64_t i) {
-        Fr w[5];
-#pragma unroll
-        for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
         uint32_t t[9];
         if (MODE == 0) {
+            Fr w[5];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
             Fr sel[4];
             sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));   // q_m*b + q_l  (< 2q < 2^256)
 #pragma unroll
             for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
             fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
         } else {
-#pragma unroll
-            for (int k = 0; k < 9; k++) t[k] = 0;
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const uint32_t si = row.sel[k];
-                if (si == POOL_ZERO) continue;
-                const Fr v = k == 0 ? fr_mul_eo(w[1], w[2], q) : w[k];
-                add9_fr(t, si == POOL_ONE ? v : (si == POOL_MINUS_ONE ? fr_neg(v) : fr_mul_eo(pool(si), v, q)));
-            }
+            sparse_terms(t, row, pool, q, i);
         }
         add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));
         if (row.pi_param >= 0) add9_fr(t, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
@@ -260,13 +303,21 @@ struct CheckBody {
     PG_HD static uint32_t run(const Args& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t bad = 0;
         for (uint32_t r = 0; r < a.n_rows; r++) {
-            const DevRow row = a.rows[r];
             if (r + 1 < a.n_rows) {            // request the next row's wire values now: ~2000 multiplier cycles cover the latency
                 const DevRow& nr = a.rows[r + 1];
 #pragma unroll
-                for (int k = 0; k < 4; k++) row_prefetch(nr.loc[k], nr.addr[k], i);
+                for (int k = 0; k < 4; k++) {
+                    if (MODE != 0) {           // structure-aware: only the wires some non-zero selector reads
+                        const bool used = k == 0 ? (nr.sel[0] | nr.sel[1]) != 0 : k == 1 ? (nr.sel[0] | nr.sel[2]) != 0 : nr.sel[k + 1] != 0;
+                        if (!used) continue;
+                    }
+                    row_prefetch(nr.loc[k], nr.addr[k], i);
+                }
             }
-            if (!row_holds<MODE>(a, row, pool, q, i)) {
+            bool ok;
+            if (MODE == 0) { const DevRow row = a.rows[r]; ok = row_holds<MODE>(a, row, pool, q, i); }
+            else ok = row_holds<MODE>(a, a.rows[r], pool, q, i);      // fields are read where needed (rolled term loop)
+            if (!ok) {
                 bad++;
                 const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
                 if (g < first_bad) first_bad = g;
@@ -278,8 +329,10 @@ struct CheckBody {
     template <int MODE, class PoolT>
     PG_HD static uint32_t run_one(const Args& a, const PoolT& pool, const QRegs& q, uint64_t t, unsigned long long& first_bad) {
         const uint64_t i = t / a.n_rows; const uint32_t r = (uint32_t)(t - i * a.n_rows);
-        const DevRow row = a.rows[r];
-        if (row_holds<MODE>(a, row, pool, q, i)) return 0u;
+        bool ok;
+        if (MODE == 0) { const DevRow row = a.rows[r]; ok = row_holds<MODE>(a, row, pool, q, i); }
+        else ok = row_holds<MODE>(a, a.rows[r], pool, q, i);
+        if (ok) return 0u;
         first_bad = a.base_row + t;
         return 1u;
     }

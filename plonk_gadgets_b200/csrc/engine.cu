@@ -181,7 +181,8 @@ public:
             toc();
             return launched("k_check_rowpar");
         }
-        switch (check_shape) {
+        // the structure-aware check needs few registers and is latency-bound: 32 warps/SM unless a shape was asked for
+        switch (a.mode == PG_CHECK_SPARSE && check_shape == 0 ? 4 : check_shape) {
             case 1: launch_check<1>(a, smem); break; case 2: launch_check<2>(a, smem); break;
             case 3: launch_check<3>(a, smem); break; case 4: launch_check<4>(a, smem); break;
             default: launch_check<0>(a, smem); break;
