@@ -77,6 +77,8 @@ extern "C" {
     pub fn pg_materialize_rows(ctx: *mut pg_ctx, row0: u64, cnt: u64, w_idx: *mut u64, w_val: *mut pg_fr, sel: *mut pg_fr,
                                pi: *mut pg_fr, dst_on_device: c_int) -> c_int;
     pub fn pg_permutation(ctx: *mut pg_ctx, row0: u64, cnt: u64, sigma: *mut u64, dst_on_device: c_int) -> c_int;
+    pub fn pg_fft(ctx: *mut pg_ctx, log_n: u32, inverse: c_int, src: *const pg_fr, dst: *mut pg_fr, on_device: c_int) -> c_int;
+    pub fn pg_wire_polynomials(ctx: *mut pg_ctx, log_n: u32, dst: *mut pg_fr, dst_on_device: c_int) -> c_int;
     pub fn pg_fr_to_bytes(ctx: *mut pg_ctx, n: u64, src: *const pg_fr, dst: *mut u8, on_device: c_int) -> c_int;
     pub fn pg_fr_from_bytes(ctx: *mut pg_ctx, n: u64, src: *const u8, dst: *mut pg_fr, on_device: c_int, n_invalid: *mut u64,
                             first_invalid: *mut u64) -> c_int;

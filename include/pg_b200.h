@@ -165,6 +165,21 @@ int pg_materialize_rows(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *w_id
  * row row0 + t, encoded as row*4 + wire.  A position whose Variable is used once maps to itself. */
 int pg_permutation(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *sigma, int dst_on_device);
 
+/* ---- evaluation domain (first half) -------------------------------------------------------------
+ * The step that follows the gadget hot path inside Prover::prove [DEP dusk-plonk 0.8, reached from
+ * /root/reference/tests/range_gadgets_tests.rs:90-91 and tests/scalar_gadgets_tests.rs (prover.prove)]:
+ *     let w_l_scalar = &[&self.to_scalars(&self.cs.w_l)[..], &pad].concat();       // pad = zeros up to domain.size()
+ *     let w_l_poly = Polynomial::from_coefficients_vec(domain.ifft(w_l_scalar));   // same for w_r, w_o, w_4
+ * pg_fft is EvaluationDomain::fft (inverse == 0) / ifft (inverse != 0) [DEP src/fft/domain.rs] of a vector of 2^log_n
+ * scalars, natural order in and out, over the subgroup generated by ROOT_OF_UNITY^(2^(32-log_n)), ROOT_OF_UNITY =
+ * 7^((q-1)/2^32); log_n <= 32 (TWO_ADICITY) or PG_ERR_ARG.  src and dst are both host or both device pointers and may be
+ * the same buffer.
+ * pg_wire_polynomials writes the coefficient vectors of w_l, w_r, w_o, w_4 (4 x 2^log_n scalars, column-major) for the
+ * composer's current rows; 2^log_n must be >= the circuit size (EvaluationDomain::new(circuit_size) takes the next power of
+ * two: pass ceil(log2(n_rows)) for the reference's domain).  Commitments (MSM) are out of scope. */
+int pg_fft(pg_ctx *ctx, uint32_t log_n, int inverse, const pg_fr *src, pg_fr *dst, int on_device);
+int pg_wire_polynomials(pg_ctx *ctx, uint32_t log_n, pg_fr *dst, int dst_on_device);
+
 /* ---- wire format -------------------------------------------------------------------------
  * BlsScalar::to_bytes / from_bytes [dusk_bytes::Serializable<32>, called at /root/reference/src/range.rs:163]: the canonical
  * little-endian 32-byte encoding used for witness / selector / public-input dumps exchanged with Rust tooling.  n scalars;

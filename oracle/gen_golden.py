@@ -148,6 +148,63 @@ def main():
     with open(path, "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print(f"wrote {len(out)} programs to {path}")
+    dom = domain_vectors(out)
+    path = os.path.join(os.path.dirname(path), "domain.json")
+    with open(path, "w") as f:
+        json.dump(dom, f, indent=1, sort_keys=True)
+    print(f"wrote {len(dom['fft'])} transforms and {len(dom['wire_polynomials'])} wire-polynomial sets to {path}")
+
+
+def coeff_digest(cols) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for col in cols:
+        for v in col:
+            h.update(int(v).to_bytes(32, "little"))
+    return h.hexdigest()
+
+
+def domain_vectors(programs, max_domain: int = 512, max_programs: int = 6):
+    """Evaluation-domain fixtures from the defining DFT sums of oracle/pymodel.py: subgroup generators,
+    fft / ifft of seeded vectors, and the wire polynomials (ifft of the zero-padded wire columns) of small golden programs."""
+    from oracle import pymodel as pm
+    dom = dict(group_gen={str(k): hx(pm.group_gen(k)) for k in (0, 1, 2, 5, 16, 31, 32)}, fft={}, wire_polynomials={})
+    for log_n in (0, 1, 2, 3, 6):
+        vals = synth_wide(90 + log_n, 1 << log_n)
+        dom["fft"][str(log_n)] = dict(input=[hx(v) for v in vals], fft=[hx(v) for v in pm.dft(vals)],
+                                      ifft=[hx(v) for v in pm.dft(vals, inverse=True)])
+    for name in sorted(programs):
+        if len(dom["wire_polynomials"]) >= max_programs:
+            break
+        spec = programs[name]
+        if spec["expected"]["error"] or (1 << pm.domain_log_size(spec["expected"]["n_rows"])) > max_domain:
+            continue
+        if name.startswith("kat_") and not name.endswith("_0_ok"):
+            continue                                            # one KAT per gadget is enough here
+        c = run_pymodel_composer(spec["program"])
+        cols = pm.wire_polynomials(c)
+        dom["wire_polynomials"][name] = dict(log_n=pm.domain_log_size(c.n), digest=coeff_digest(cols),
+                                             head=[[hx(v) for v in col[:3]] for col in cols])
+    return dom
+
+
+def run_pymodel_composer(program):
+    """The pymodel composer itself after `program` (run_pymodel returns a snapshot only)."""
+    from tests import programs as P
+    from oracle import pymodel as pm
+    holder = {}
+    orig = pm.StandardComposer
+
+    class Capturing(orig):
+        def __init__(self):
+            super().__init__()
+            holder["c"] = self
+    pm.StandardComposer = Capturing
+    try:
+        P.run_pymodel(program)
+    finally:
+        pm.StandardComposer = orig
+    return holder["c"]
 
 
 if __name__ == "__main__":

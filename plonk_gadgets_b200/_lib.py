@@ -61,6 +61,8 @@ SIGNATURES = {
     "pg_read_variables": (_i32, [_vp, _u64, _u64, _vp, _i32]),
     "pg_materialize_rows": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _i32]),
     "pg_permutation": (_i32, [_vp, _u64, _u64, _vp, _i32]),
+    "pg_fft": (_i32, [_vp, _u32, _i32, _vp, _vp, _i32]),
+    "pg_wire_polynomials": (_i32, [_vp, _u32, _vp, _i32]),
     "pg_fr_to_bytes": (_i32, [_vp, _u64, _vp, _vp, _i32]),
     "pg_fr_from_bytes": (_i32, [_vp, _u64, _vp, _vp, _i32, _pu64, _pu64]),
     "pg_synth": (_i32, [_vp, _u64, _u64, _u64, _i32, _u32, _vp]),

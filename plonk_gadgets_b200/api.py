@@ -240,6 +240,40 @@ class StandardComposer:
         self._ok(self._L.pg_permutation(self._ctx, row0, cnt, out.ctypes.data_as(C.c_void_p), 0), "pg_permutation")
         return out
 
+    # -- evaluation domain: EvaluationDomain::fft / ifft and the wire polynomials of Prover::prove ([DEP] dusk-plonk 0.8)
+    def fft(self, scalars, inverse: bool = False, out=None):
+        """FFT / inverse FFT of 2^k scalars over dusk-plonk's evaluation domain (natural order in and out).
+        Host: (n, 4) uint64 array in, new array out.  Device: anything with data_ptr() (in place unless `out` is given)."""
+        if hasattr(scalars, "data_ptr"):
+            n = scalars.shape[0]
+            dst = scalars if out is None else out
+            src_p, dst_p, on_dev = C.c_void_p(scalars.data_ptr()), C.c_void_p(dst.data_ptr()), 1
+        else:
+            a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+            n = a.shape[0]
+            dst = np.empty_like(a)
+            src_p, dst_p, on_dev = a.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), 0
+        if n == 0 or n & (n - 1):
+            raise ValueError("fft: the number of scalars must be a power of two")
+        self._ok(self._L.pg_fft(self._ctx, n.bit_length() - 1, 1 if inverse else 0, src_p, dst_p, on_dev), "pg_fft")
+        return dst
+
+    def domain_log_size(self) -> int:
+        """log2 of EvaluationDomain::new(circuit_size).size()."""
+        return max(self.circuit_size() - 1, 0).bit_length()
+
+    def wire_polynomials(self, log_n: int | None = None, out=None):
+        """Coefficients of w_l, w_r, w_o, w_4: (4, 2^log_n, 4) uint64 (host array, or written to the device tensor `out`)."""
+        log_n = self.domain_log_size() if log_n is None else log_n
+        if not 0 <= log_n <= 32 or (1 << log_n) < self.circuit_size():
+            raise EngineError(-2, "pg_wire_polynomials", f"a domain of 2^{log_n} cannot hold {self.circuit_size()} rows (or exceeds 2^32)")
+        if out is not None:
+            self._ok(self._L.pg_wire_polynomials(self._ctx, log_n, C.c_void_p(out.data_ptr()), 1), "pg_wire_polynomials")
+            return out
+        dst = np.empty((4, 1 << log_n, 4), dtype=np.uint64)
+        self._ok(self._L.pg_wire_polynomials(self._ctx, log_n, dst.ctypes.data_as(C.c_void_p), 0), "pg_wire_polynomials")
+        return dst
+
     # -- wire format: canonical little-endian bytes <-> Montgomery limbs (BlsScalar::to_bytes / from_bytes)
     def to_bytes(self, scalars) -> np.ndarray:
         a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)

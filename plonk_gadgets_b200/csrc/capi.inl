@@ -105,6 +105,14 @@ int pg_permutation(pg_ctx* ctx, uint64_t row0, uint64_t cnt, uint64_t* sigma, in
     PG_NEED_CTX(ctx);
     return ctx->e.permutation(row0, cnt, sigma, dst_on_device);
 }
+int pg_fft(pg_ctx* ctx, uint32_t log_n, int inverse, const pg_fr* src, pg_fr* dst, int on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, src, on_device); PG_ALIGNED(ctx, dst, on_device);
+    return ctx->e.fft(log_n, inverse, src, dst, on_device);
+}
+int pg_wire_polynomials(pg_ctx* ctx, uint32_t log_n, pg_fr* dst, int dst_on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device);
+    return ctx->e.wire_polynomials(log_n, dst, dst_on_device);
+}
 int pg_fr_to_bytes(pg_ctx* ctx, uint64_t n, const pg_fr* src, uint8_t* dst, int on_device) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, src, on_device); PG_ALIGNED(ctx, dst, on_device);
     return ctx->e.convert(true, n, src, reinterpret_cast<pg_fr*>(dst), on_device, nullptr, nullptr);

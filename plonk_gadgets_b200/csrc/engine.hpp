@@ -13,6 +13,7 @@
 //   template<class Body> bool run_simple(const typename Body::Args&, uint64_t n, int cls)
 //   bool run_batch_inv(const BatchInvArgs&, int cls)            -- out_slot = in_slot^-1 (or 0) over table slots
 //   bool run_check(const CheckArgs&), bool run_check_rows(const CheckRowsBody::Args&)
+//   bool run_ntt_pass(const NttPassArgs&, uint64_t n_blocks)    -- one group of butterfly stages over all tiles (ntt.cuh)
 //   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), bool ubench(int, double*), timing(pg_timing*, bool reset)
 #pragma once
 #include <algorithm>
@@ -21,6 +22,7 @@
 #include <vector>
 #include "../../include/pg_b200.h"
 #include "templates.hpp"
+#include "ntt.cuh"
 
 namespace pg {
 
@@ -108,7 +110,7 @@ public:
     void destroy() {
         be.sync();
         release_segments();
-        dfree(d_counters); dfree(d_segs);
+        dfree(d_counters); dfree(d_segs); dfree(ntt_tw); ntt_tw = nullptr;
         for (auto& kv : pool_free) be.release(kv.second);
         for (auto& kv : pool_live) be.release(kv.first);
         pool_free.clear(); pool_live.clear();
@@ -501,6 +503,35 @@ public:
         release_scratch_from(mark);
         return rc;
     }
+    // device side of materialize: rows [row0, row0 + cnt) into column-major device buffers of `stride` rows per column
+    int materialize_dev(uint64_t row0, uint64_t cnt, uint64_t stride, unsigned long long* d_idx, uint4* d_val, uint4* d_sel, uint4* d_pi) {
+        { const int rcs = sync_dsegs(); if (rcs) return rcs; }
+        // per segment: whole instances go through the tiled kernel (wire values + the 5 instance-independent selector columns),
+        // the simple body adds w_idx / q_c / PI for them and does everything for the ragged ends of the requested range
+        auto simple = [&](uint64_t r0, uint64_t n, uint32_t what) -> bool {
+            if (!n || !what) return true;
+            MaterializeBody::Args a{d_segs, (uint32_t)dsegs.size(), what, r0, n, stride, r0 - row0, d_idx, d_val, d_sel, d_pi};
+            return be.template run_simple<MaterializeBody>(a, n, CLS_OTHER);
+        };
+        const uint64_t row_end = row0 + cnt;
+        for (size_t k = 0; k < segs.size(); k++) {
+            const Segment& sg = segs[k];
+            const uint64_t nr = sg.t.rows.size();
+            if (!nr || !sg.n_inst) continue;
+            const uint64_t s_lo = std::max(row0, sg.base_row), s_hi = std::min(row_end, sg.base_row + sg.n_inst * nr);
+            if (s_lo >= s_hi) continue;
+            const uint64_t iA = (s_lo - sg.base_row + nr - 1) / nr, iB = (s_hi - sg.base_row) / nr;      // whole instances [iA, iB)
+            const bool tiled = (d_val || d_sel) && iB > iA && iB - iA >= 32 && nr >= 8;
+            if (!tiled) { if (!simple(s_lo, s_hi - s_lo, MAT_ALL)) return fail(PG_ERR_CUDA, "materialize kernel"); continue; }
+            const uint64_t t_lo = sg.base_row + iA * nr, t_hi = sg.base_row + iB * nr;
+            MatTileArgs ta; memset(&ta, 0, sizeof(ta));
+            ta.seg = dsegs[k]; ta.inst0 = iA; ta.n_inst = iB - iA; ta.stride = stride; ta.out_off = t_lo - row0; ta.w_val = d_val; ta.sel = d_sel;
+            if (!be.run_mat_tiled(ta)) return fail(PG_ERR_CUDA, "tiled materialize kernel");
+            if (!simple(s_lo, t_lo - s_lo, MAT_ALL) || !simple(t_hi, s_hi - t_hi, MAT_ALL) ||
+                !simple(t_lo, t_hi - t_lo, MAT_W_IDX | MAT_QC | MAT_PI)) return fail(PG_ERR_CUDA, "materialize kernel");
+        }
+        return PG_OK;
+    }
     int materialize(uint64_t row0, uint64_t cnt, uint64_t* w_idx, pg_fr* w_val, pg_fr* sel, pg_fr* pi, int dst_on_device) {
         if (row0 + cnt > n_rows) return fail(PG_ERR_ARG, "materialize_rows: range");
         if (!cnt) return PG_OK;
@@ -516,33 +547,9 @@ public:
         d_sel = (uint4*)buf(sel, 6 * cnt * sizeof(pg_fr));
         d_pi = (uint4*)buf(pi, cnt * sizeof(pg_fr));
         if ((w_idx && !d_idx) || (w_val && !d_val) || (sel && !d_sel) || (pi && !d_pi)) return fail(PG_ERR_OOM, "materialize buffers");
-        { const int rcs = sync_dsegs(); if (rcs) return rcs; }
-        // per segment: whole instances go through the tiled kernel (wire values + the 5 instance-independent selector columns),
-        // the simple body adds w_idx / q_c / PI for them and does everything for the ragged ends of the requested range
-        auto simple = [&](uint64_t r0, uint64_t n, uint32_t what) -> bool {
-            if (!n || !what) return true;
-            MaterializeBody::Args a{d_segs, (uint32_t)dsegs.size(), what, r0, n, cnt, r0 - row0, d_idx, d_val, d_sel, d_pi};
-            return be.template run_simple<MaterializeBody>(a, n, CLS_OTHER);
-        };
-        const uint64_t row_end = row0 + cnt;
-        for (size_t k = 0; k < segs.size(); k++) {
-            const Segment& sg = segs[k];
-            const uint64_t nr = sg.t.rows.size();
-            if (!nr || !sg.n_inst) continue;
-            const uint64_t s_lo = std::max(row0, sg.base_row), s_hi = std::min(row_end, sg.base_row + sg.n_inst * nr);
-            if (s_lo >= s_hi) continue;
-            const uint64_t iA = (s_lo - sg.base_row + nr - 1) / nr, iB = (s_hi - sg.base_row) / nr;      // whole instances [iA, iB)
-            const bool tiled = (d_val || d_sel) && iB > iA && iB - iA >= 32 && nr >= 8;
-            if (!tiled) { if (!simple(s_lo, s_hi - s_lo, MAT_ALL)) return fail(PG_ERR_CUDA, "materialize kernel"); continue; }
-            const uint64_t t_lo = sg.base_row + iA * nr, t_hi = sg.base_row + iB * nr;
-            MatTileArgs ta; memset(&ta, 0, sizeof(ta));
-            ta.seg = dsegs[k]; ta.inst0 = iA; ta.n_inst = iB - iA; ta.stride = cnt; ta.out_off = t_lo - row0; ta.w_val = d_val; ta.sel = d_sel;
-            if (!be.run_mat_tiled(ta)) return fail(PG_ERR_CUDA, "tiled materialize kernel");
-            if (!simple(s_lo, t_lo - s_lo, MAT_ALL) || !simple(t_hi, s_hi - t_hi, MAT_ALL) ||
-                !simple(t_lo, t_hi - t_lo, MAT_W_IDX | MAT_QC | MAT_PI)) return fail(PG_ERR_CUDA, "materialize kernel");
-        }
+        int rc = materialize_dev(row0, cnt, cnt, d_idx, d_val, d_sel, d_pi);
+        if (rc) return rc;
         if (dst_on_device) return PG_OK;
-        int rc = PG_OK;
         if (w_idx && (rc = deliver(w_idx, d_idx, 4 * cnt * sizeof(uint64_t), 0))) return rc;
         if (w_val && (rc = deliver(w_val, d_val, 4 * cnt * sizeof(pg_fr), 0))) return rc;
         if (sel && (rc = deliver(sel, d_sel, 6 * cnt * sizeof(pg_fr), 0))) return rc;
@@ -550,6 +557,81 @@ public:
         if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
         release_scratch_from(mark);
         return PG_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------------ evaluation domain
+    // SURVEY.md 8f.2 (first half): EvaluationDomain::fft / ifft and the wire polynomials of Prover::prove; see ntt.cuh.
+    uint4* ntt_tw = nullptr; uint32_t ntt_tw_log_n = 0;
+    int ntt_twiddles(uint32_t log_n) {
+        if (ntt_tw && ntt_tw_log_n == log_n) return PG_OK;
+        if (ntt_tw) { be.sync(); dfree(ntt_tw); ntt_tw = nullptr; }
+        const uint64_t n_half = 1ull << (log_n - 1);
+        ntt_tw = (uint4*)dalloc(n_half * sizeof(pg_fr));
+        if (!ntt_tw) return fail(PG_ERR_OOM, "twiddle table");
+        ntt_tw_log_n = log_n;
+        NttTwiddleBody::Args a;
+        a.tw = ntt_tw; a.n_half = n_half; a.n = (n_half + 15) / 16; a.log_n = log_n;
+        Fr w = fr_root_of_unity();                                       // EvaluationDomain::new: group_gen
+        for (uint32_t i = log_n; i < NTT_TWO_ADICITY; i++) w = fr_sqr(w);
+        a.pw2[0] = w;
+        for (uint32_t b = 1; b < NTT_TWO_ADICITY; b++) a.pw2[b] = fr_sqr(a.pw2[b - 1]);
+        if (!be.template run_simple<NttTwiddleBody>(a, a.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "twiddle kernel");
+        return PG_OK;
+    }
+    int ntt_inplace(uint4* data, uint32_t log_n, bool inverse) {
+        if (log_n == 0) return PG_OK;                                    // one element: the transform is the identity
+        int rc = ntt_twiddles(log_n);
+        if (rc) return rc;
+        const uint64_t n = 1ull << log_n;
+        NttBitrevBody::Args b; b.data = data; b.n = n; b.log_n = log_n; b.scale = inverse ? 1 : 0; b.factor = fr_one();
+        if (inverse) { Fr raw = fr_zero(); raw.v[0] = (uint32_t)n; raw.v[1] = (uint32_t)(n >> 32); b.factor = fr_inv_fermat(fr_to_mont(raw)); }   // size_inv
+        if (!be.template run_simple<NttBitrevBody>(b, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "bit-reversal kernel");
+        const NttPlan plan = ntt_plan(log_n);
+        for (uint32_t p = 0; p < plan.n_pass; p++) {
+            NttPassArgs a{data, ntt_tw, log_n, plan.t0[p], plan.s[p], plan.log_c[p], inverse ? 1 : 0};
+            if (!be.run_ntt_pass(a, n >> (plan.s[p] + plan.log_c[p]))) return fail(PG_ERR_CUDA, "NTT pass kernel");
+        }
+        return PG_OK;
+    }
+    int fft(uint32_t log_n, int inverse, const pg_fr* src, pg_fr* dst, int on_device) {
+        if (log_n > NTT_TWO_ADICITY || !src || !dst) return fail(PG_ERR_ARG, "fft: domain larger than 2^32 or null buffer");
+        const uint64_t n = 1ull << log_n; const size_t bytes = n * sizeof(pg_fr);
+        const size_t mark = scratch.size();
+        uint4* buf;
+        if (on_device) { buf = reinterpret_cast<uint4*>(dst); if (src != dst && !be.d2d(dst, src, bytes)) return fail(PG_ERR_CUDA, "device copy"); }
+        else {
+            buf = (uint4*)dalloc(bytes);
+            if (!buf) return fail(PG_ERR_OOM, "fft buffer");
+            scratch.push_back(buf);
+            if (!be.h2d(buf, src, bytes)) return fail(PG_ERR_CUDA, "input copy");
+        }
+        int rc = ntt_inplace(buf, log_n, inverse != 0);
+        if (rc || on_device) return rc;
+        rc = deliver(dst, buf, bytes, 0);
+        release_scratch_from(mark);
+        return rc;
+    }
+    // dst: 4 columns (w_l, w_r, w_o, w_4) of 2^log_n coefficients each
+    int wire_polynomials(uint32_t log_n, pg_fr* dst, int dst_on_device) {
+        if (log_n > NTT_TWO_ADICITY || (1ull << log_n) < n_rows || !dst) return fail(PG_ERR_ARG, "wire_polynomials: domain smaller than the circuit, larger than 2^32, or null buffer");
+        const uint64_t n = 1ull << log_n; const size_t bytes = 4 * n * sizeof(pg_fr);
+        const size_t mark = scratch.size();
+        uint4* buf = reinterpret_cast<uint4*>(dst);
+        if (!dst_on_device) { buf = (uint4*)dalloc(bytes); if (!buf) return fail(PG_ERR_OOM, "wire polynomial buffer"); scratch.push_back(buf); }
+        int rc = materialize_dev(0, n_rows, n, nullptr, buf, nullptr, nullptr);      // to_scalars(w_l..w_4)
+        if (rc) return rc;
+        for (int w = 0; w < 4; w++) {
+            uint4* col = buf + 2 * (uint64_t)w * n;
+            if (n > n_rows) {                                                        // pad with zeros up to the domain size
+                NttZeroBody::Args z{col, n_rows, n - n_rows};
+                if (!be.template run_simple<NttZeroBody>(z, z.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "padding kernel");
+            }
+            if ((rc = ntt_inplace(col, log_n, true))) return rc;                     // domain.ifft
+        }
+        if (dst_on_device) return PG_OK;
+        rc = deliver(dst, buf, bytes, 0);
+        release_scratch_from(mark);
+        return rc;
     }
 
     // ------------------------------------------------------------------------------------------------ permutation map

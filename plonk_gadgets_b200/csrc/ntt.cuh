@@ -1,0 +1,183 @@
+// ntt.cuh -- number-theoretic transform over the BLS12-381 scalar field on dusk-plonk's evaluation domain
+// (first half: the step right after the gadget hot path inside `Prover::prove`:
+// wire columns -> zero-padded scalar vectors -> `domain.ifft` -> coefficients of w_l, w_r, w_o, w_4).
+//
+// Semantics ([DEP] dusk-plonk 0.8 src/fft/domain.rs, reached from /root/reference/tests/range_gadgets_tests.rs:90-91):
+//   fft :  A_k = sum_j a_j w^(jk),   w = ROOT_OF_UNITY^(2^(32 - log_n)),  ROOT_OF_UNITY = 7^((q-1)/2^32)
+//   ifft:  the same with w^-1, every element multiplied by n^-1.
+// Both are natural order in, natural order out.  The DFT of a vector is unique and Fr elements are kept fully reduced, so any
+// correct schedule yields the same limbs as the reference's serial radix-2 loop; the schedule here is chosen for the B200:
+//
+//   1. k_simple<NttBitrevBody>: in-place bit-reversal permutation (pairs swapped by the thread of the smaller index), fused
+//      with the n^-1 scaling of the inverse transform;
+//   2. k_ntt_pass, ceil((log_n - 11) / 8) + 1 launches: a block owns a tile of 2^s x C elements (s butterfly stages; C >= 8
+//      neighbouring sub-transforms so that every global access of a warp covers whole 256-byte runs), keeps it in shared
+//      memory as 8 limb planes, and runs the s stages there -- one decimation-in-time butterfly (1 Montgomery
+//      multiplication, 1 add, 1 sub) per thread and step.  The vector crosses HBM once per pass (3 passes at 2^26) while the
+//      log_n/2 multiplications per element stay on the multiplier pipe: the transform is IMAD-bound like the gate check.
+//   Twiddles w^i (i < n/2) come from a table built once per domain size by k_simple<NttTwiddleBody> (inverse transform:
+//   w^-i = -w^(n/2 - i)); a pass touches about as many table bytes as data bytes, mostly out of L2.
+#pragma once
+#include "layout.h"
+
+namespace pg {
+
+constexpr uint32_t NTT_TWO_ADICITY = 32;
+constexpr uint32_t NTT_MAX_LOG_TILE = 11;     // 2048 elements = 64 KiB of shared memory per block
+constexpr int NTT_THREADS = 256;
+
+// 7^((q-1)/2^32) in Montgomery form (dusk-bls12_381 ROOT_OF_UNITY; recomputed by tests/test_oracle_fft.py)
+PG_HD Fr fr_root_of_unity() { Fr r = {{0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u, 0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau}}; return r; }
+
+PG_HD uint64_t bitrev64(uint64_t x, uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+    return bits ? __brevll(x) >> (64 - bits) : 0;
+#else
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+#endif
+}
+
+// ---- twiddle table: tw[i] = w^i, i < n/2; 16 consecutive entries per call --------------------------------------------
+struct NttTwiddleBody {
+    struct Args { uint4* tw; uint64_t n_half; uint64_t n; /* calls */ uint32_t log_n; Fr pw2[NTT_TWO_ADICITY]; /* w^(2^b) */ };
+    PG_HD static void run(const Args& a, uint64_t j) {
+        const uint64_t i0 = j * 16;
+        Fr x = fr_one();
+        for (uint32_t b = 4; b + 1 < a.log_n; b++)
+            if ((i0 >> b) & 1) x = fr_mul(x, a.pw2[b]);
+        for (uint32_t r = 0; r < 16 && i0 + r < a.n_half; r++) { aos_store(a.tw, i0 + r, x); x = fr_mul(x, a.pw2[0]); }
+    }
+};
+
+// ---- bit-reversal permutation (+ scaling) ------------------------------------------------------------------------------
+struct NttBitrevBody {
+    struct Args { uint4* data; uint64_t n; uint32_t log_n; int scale; Fr factor; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const uint64_t r = bitrev64(i, a.log_n);
+        if (i > r) return;
+        Fr x = aos_load(a.data, i);
+        if (i == r) { if (a.scale) aos_store(a.data, i, fr_mul(x, a.factor)); return; }
+        Fr y = aos_load(a.data, r);
+        if (a.scale) { x = fr_mul(x, a.factor); y = fr_mul(y, a.factor); }
+        aos_store(a.data, i, y); aos_store(a.data, r, x);
+    }
+};
+
+// zero-fill of the padding rows [n0, n) of a column
+struct NttZeroBody {
+    struct Args { uint4* data; uint64_t n0; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t i) { aos_store(a.data, a.n0 + i, fr_zero()); }
+};
+
+// ---- one pass = s consecutive butterfly stages [t0, t0 + s) ------------------------------------------------------------
+// Index of an element: (g_hi, v, g_lo) with g_lo < 2^t0 and v < 2^s; the pass couples elements that differ in v only.
+// Tile `blk` holds the C = 2^log_c values g = blk*C + c of the combined index g = (g_hi, g_lo), all v: tile element
+// e = v*C + c.  With t0 >= log_c the C elements of a v share g_hi and are neighbours in memory.
+struct NttPassArgs { uint4* data; const uint4* tw; uint32_t log_n, t0, s, log_c; int inverse; };
+
+PG_HD uint64_t ntt_index(const NttPassArgs& a, uint64_t blk, uint32_t e) {
+    const uint32_t c = e & ((1u << a.log_c) - 1u), v = e >> a.log_c;
+    const uint64_t g = (blk << a.log_c) | c;
+    const uint64_t g_lo = g & ((1ull << a.t0) - 1ull), g_hi = g >> a.t0;
+    return (g_hi << (a.t0 + a.s)) | ((uint64_t)v << a.t0) | g_lo;
+}
+// butterfly b (< 2^(s-1) * C) of step u (stage t0 + u): tile elements e0 < e1 and the twiddle exponent
+PG_HD void ntt_butterfly(const NttPassArgs& a, uint64_t blk, uint32_t u, uint32_t b, uint32_t& e0, uint32_t& e1, uint64_t& tw_index) {
+    const uint32_t c = b & ((1u << a.log_c) - 1u), bf = b >> a.log_c;
+    const uint32_t low = bf & ((1u << u) - 1u);
+    const uint32_t v0 = ((bf >> u) << (u + 1)) | low;
+    e0 = (v0 << a.log_c) | c;
+    e1 = e0 + (1u << (u + a.log_c));
+    const uint64_t g = (blk << a.log_c) | c;
+    const uint64_t pos = ((uint64_t)low << a.t0) | (g & ((1ull << a.t0) - 1ull));     // index inside the half block of size m = 2^(t0+u)
+    tw_index = pos << (a.log_n - 1u - (a.t0 + u));                                    // pos * n / (2m)  < n/2
+}
+PG_HD Fr ntt_twiddle(const NttPassArgs& a, uint64_t tw_index) {
+    if (!a.inverse) return aos_load(a.tw, tw_index);
+    if (tw_index == 0) return fr_one();
+    return fr_neg(aos_load(a.tw, (1ull << (a.log_n - 1u)) - tw_index));                // w^-i = -w^(n/2 - i)
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const NttPassArgs a) {
+    extern __shared__ __align__(16) uint32_t s_tile[];            // [8 limbs][E]
+    __shared__ uint32_t s_q[8];
+    const uint32_t log_e = a.s + a.log_c, E = 1u << log_e;
+    const uint64_t blk = blockIdx.x;
+    if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
+    for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS) {
+        const Fr x = aos_load(a.data, ntt_index(a, blk, e));
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_tile[k * E + e] = x.v[k];
+    }
+    __syncthreads();
+    QRegs q;
+#pragma unroll
+    for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
+    for (uint32_t u = 0; u < a.s; u++) {
+#pragma unroll 1
+        for (uint32_t b = threadIdx.x; b < E / 2; b += NTT_THREADS) {
+            uint32_t e0, e1; uint64_t ti;
+            ntt_butterfly(a, blk, u, b, e0, e1, ti);
+            const Fr w = ntt_twiddle(a, ti);
+            Fr x0, x1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { x0.v[k] = s_tile[k * E + e0]; x1.v[k] = s_tile[k * E + e1]; }
+            const Fr t = fr_mul_eo(x1, w, q);
+            const Fr y0 = fr_add(x0, t), y1 = fr_sub(x0, t);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { s_tile[k * E + e0] = y0.v[k]; s_tile[k * E + e1] = y1.v[k]; }
+        }
+        __syncthreads();
+    }
+    for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS) {
+        Fr x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) x.v[k] = s_tile[k * E + e];
+        aos_store(a.data, ntt_index(a, blk, e), x);
+    }
+}
+#endif
+
+// the same tile schedule on the host (tests/emu backend and documentation of the kernel's data flow)
+inline void ntt_pass_host(const NttPassArgs& a, uint64_t n_blocks) {
+    const uint32_t E = 1u << (a.s + a.log_c);
+    Fr* tile = new Fr[E];
+    for (uint64_t blk = 0; blk < n_blocks; blk++) {
+        for (uint32_t e = 0; e < E; e++) tile[e] = aos_load(a.data, ntt_index(a, blk, e));
+        for (uint32_t u = 0; u < a.s; u++)
+            for (uint32_t b = 0; b < E / 2; b++) {
+                uint32_t e0, e1; uint64_t ti;
+                ntt_butterfly(a, blk, u, b, e0, e1, ti);
+                const Fr t = fr_mul(tile[e1], ntt_twiddle(a, ti));
+                const Fr x0 = tile[e0];
+                tile[e0] = fr_add(x0, t); tile[e1] = fr_sub(x0, t);
+            }
+        for (uint32_t e = 0; e < E; e++) aos_store(a.data, ntt_index(a, blk, e), tile[e]);
+    }
+    delete[] tile;
+}
+
+// pass plan: the first pass runs on contiguous tiles (C = 1) and takes up to 11 stages, the others at most 8 stages with C >= 8
+struct NttPlan { uint32_t n_pass; uint32_t t0[8], s[8], log_c[8]; };
+inline NttPlan ntt_plan(uint32_t log_n) {
+    NttPlan p; p.n_pass = 0;
+    uint32_t t0 = 0;
+    while (t0 < log_n) {
+        uint32_t s, log_c;
+        if (t0 == 0) { s = log_n < NTT_MAX_LOG_TILE ? log_n : NTT_MAX_LOG_TILE; log_c = 0; }
+        else {
+            const uint32_t rem = log_n - t0, more = (rem + 7) / 8;
+            s = (rem + more - 1) / more;
+            log_c = NTT_MAX_LOG_TILE - s;
+            if (log_c > log_n - s) log_c = log_n - s;
+        }
+        p.t0[p.n_pass] = t0; p.s[p.n_pass] = s; p.log_c[p.n_pass] = log_c; p.n_pass++;
+        t0 += s;
+    }
+    return p;
+}
+
+}  // namespace pg

@@ -20,6 +20,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_domain():
+    with open(os.path.join(ROOT, "tests", "golden", "domain.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import binding
     binding.build()

@@ -81,6 +81,7 @@ public:
             }
         return true;
     }
+    bool run_ntt_pass(const NttPassArgs& a, uint64_t n_blocks) { ntt_pass_host(a, n_blocks); return true; }
     bool run_check_rows(const CheckRowsBody::Args& a) {
         for (uint64_t i = 0; i < a.n; i++)
             if (CheckRowsBody::run(a, i)) { a.counters[CNT_UNSAT]++; if (i < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = i; }

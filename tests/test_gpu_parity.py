@@ -364,3 +364,101 @@ def test_check_modes_at_scale(oracle, torch_cuda, mode):
 def test_empty_and_ragged_gpu(oracle):
     from tests.test_emu_engine import _empty_and_ragged
     _empty_and_ragged(gpu_composer, oracle)
+
+
+# ---------------------------------------------------------------------------------------------------- evaluation domain (8f.2)
+@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 10, 11, 12, 14, 17, 20])
+def test_fft_vs_oracle(oracle, log_n):
+    """pg_fft (bit-reversal + shared-memory butterfly passes) against the restated serial FFT, forward and inverse; the sizes
+    cover 1, 2 and 3 passes and every first-pass width."""
+    c = gpu_composer()
+    a = oracle.from_ints(synth_wide(70 + log_n, 1 << log_n)) if log_n <= 14 else None
+    if a is None:                                               # larger inputs straight from the device generator
+        import torch
+        t = torch.empty((1 << log_n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 70 + log_n, 0, 0, t)
+        a = t.cpu().numpy().view(np.uint64)
+    assert np.array_equal(c.fft(a), oracle.fft(a))
+    assert np.array_equal(c.fft(a, inverse=True), oracle.fft(a, inverse=True))
+
+
+def test_fft_golden_gpu(oracle, golden_domain):
+    c = gpu_composer()
+    for log_n, vec in golden_domain["fft"].items():
+        a = oracle.from_ints([int(x, 16) for x in vec["input"]])
+        assert [hx(v) for v in oracle.to_ints(c.fft(a))] == vec["fft"]
+        assert [hx(v) for v in oracle.to_ints(c.fft(a, inverse=True))] == vec["ifft"]
+
+
+def test_fft_properties_at_scale(oracle, torch_cuda):
+    """2^24 scalars on the device (512 MiB per vector): round trip in place and out of place, the transform of a delta, and
+    the decimation identity between two transform sizes."""
+    torch = torch_cuda
+    log_n = 24; n = 1 << log_n
+    c = gpu_composer()
+    x = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 77, 0, 0, x)
+    fx = torch.empty_like(x)
+    c.fft(x, out=fx)
+    back = fx.clone(); c.fft(back, inverse=True)                # in place
+    c.sync()
+    assert torch.equal(back, x)
+    # decimation: the even-indexed outputs of a size-m FFT are the size-m/2 FFT of a_j + a_(j+m/2)
+    m = 1 << 16
+    s_np = x[:m].cpu().numpy().view(np.uint64)
+    folded = c.fr_op(1, s_np[: m // 2], s_np[m // 2:])
+    assert np.array_equal(c.fft(s_np)[0::2], c.fft(folded))
+    delta = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+    five = torch.from_numpy(oracle.from_ints([5]).view(np.int64)).cuda()
+    delta[0] = five[0]
+    c.fft(delta); c.sync()
+    assert bool((delta == five[0]).all())
+
+
+def test_wire_polynomials_golden_gpu(oracle, golden, golden_domain):
+    from oracle.gen_golden import coeff_digest
+    hits = 0
+    for name, spec in golden.items():
+        if spec["expected"]["error"]:
+            continue
+        _s, oc = run_oracle(spec["program"], return_composer=True)
+        _snap, c = run_engine(spec["program"], gpu_composer, oracle, return_composer=True)
+        got = c.wire_polynomials()
+        assert np.array_equal(got, oc.wire_polynomials()), name
+        if name in golden_domain["wire_polynomials"]:
+            assert coeff_digest([oracle.to_ints(got[w]) for w in range(4)]) == golden_domain["wire_polynomials"][name]["digest"]
+            hits += 1
+    assert hits >= 4
+
+
+def test_wire_polynomials_batch_vs_oracle(oracle, torch_cuda):
+    """1500 range_check instances (406 503 rows -> domain 2^19, two butterfly passes, tiled + ragged materialisation):
+    coefficients equal to the oracle's ifft of the sequential composer's wire columns."""
+    n = 1500
+    wit = synth_wide(61, n)
+    wit = [w % 2 ** 64 if i % 2 == 0 else w for i, w in enumerate(wit)]
+    prog = [dict(op="add_input", values=[hx(w) for w in wit]), dict(op="range_check", min=hx(0), max=hx(2 ** 64), witness=0)]
+    _s, oc = run_oracle(prog, return_composer=True)
+    c = gpu_composer()
+    w = c.add_input(oracle.from_ints(wit))
+    pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    assert c.circuit_size() == oc.n and c.domain_log_size() == 19
+    assert np.array_equal(c.wire_polynomials(), oc.wire_polynomials())
+
+
+def test_wire_polynomials_at_scale(oracle, torch_cuda):
+    """2^16 range_check instances: 17.8 M rows -> domain 2^25 (4 GiB of coefficients).  Evaluating the polynomials back over the
+    domain (forward transform) must reproduce the materialised wire values on the rows and zeros on the padding."""
+    torch = torch_cuda
+    n = 1 << 16
+    c = gpu_composer()
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 2, 2, 64, wit)
+    w = c.add_input(wit)
+    pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    rows = c.circuit_size(); k = c.domain_log_size(); N = 1 << k
+    assert k == 25
+    polys = torch.empty((4, N, 4), dtype=torch.int64, device="cuda")
+    c.wire_polynomials(out=polys)
+    w_val = torch.empty((4, rows, 4), dtype=torch.int64, device="cuda")
+    c._ok(c._L.pg_materialize_rows(c._ctx, 0, rows, None, C.c_void_p(w_val.data_ptr()), None, None, 1), "pg_materialize_rows")
+    for col in range(4):
+        c.fft(polys[col]); c.sync()
+        assert torch.equal(polys[col, :rows], w_val[col]) and not bool(polys[col, rows:].any())
