@@ -375,7 +375,7 @@ def test_fft_vs_oracle(oracle, log_n):
     a = oracle.from_ints(synth_wide(70 + log_n, 1 << log_n)) if log_n <= 14 else None
     if a is None:                                               # larger inputs straight from the device generator
         import torch
-        t = torch.empty((1 << log_n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 70 + log_n, 0, 0, t)
+        t = torch.empty((1 << log_n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 70 + log_n, 0, 0, t); c.sync()   # the engine runs on its own stream
         a = t.cpu().numpy().view(np.uint64)
     assert np.array_equal(c.fft(a), oracle.fft(a))
     assert np.array_equal(c.fft(a, inverse=True), oracle.fft(a, inverse=True))
@@ -397,9 +397,9 @@ def test_fft_properties_at_scale(oracle, torch_cuda):
     c = gpu_composer()
     x = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 77, 0, 0, x)
     fx = torch.empty_like(x)
-    c.fft(x, out=fx)
-    back = fx.clone(); c.fft(back, inverse=True)                # in place
-    c.sync()
+    c.fft(x, out=fx); c.sync()                                  # the engine runs on its own stream: join before torch touches fx
+    back = fx.clone(); torch.cuda.synchronize()
+    c.fft(back, inverse=True); c.sync()                         # in place
     assert torch.equal(back, x)
     # decimation: the even-indexed outputs of a size-m FFT are the size-m/2 FFT of a_j + a_(j+m/2)
     m = 1 << 16
@@ -408,7 +408,7 @@ def test_fft_properties_at_scale(oracle, torch_cuda):
     assert np.array_equal(c.fft(s_np)[0::2], c.fft(folded))
     delta = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
     five = torch.from_numpy(oracle.from_ints([5]).view(np.int64)).cuda()
-    delta[0] = five[0]
+    delta[0] = five[0]; torch.cuda.synchronize()
     c.fft(delta); c.sync()
     assert bool((delta == five[0]).all())
 
@@ -456,6 +456,7 @@ def test_wire_polynomials_at_scale(oracle, torch_cuda):
     rows = c.circuit_size(); k = c.domain_log_size(); N = 1 << k
     assert k == 25
     polys = torch.empty((4, N, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     c.wire_polynomials(out=polys)
     w_val = torch.empty((4, rows, 4), dtype=torch.int64, device="cuda")
     c._ok(c._L.pg_materialize_rows(c._ctx, 0, rows, None, C.c_void_p(w_val.data_ptr()), None, None, 1), "pg_materialize_rows")
