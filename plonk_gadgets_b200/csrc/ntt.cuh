@@ -12,8 +12,9 @@
 //      with the n^-1 scaling of the inverse transform;
 //   2. k_ntt_pass, ceil((log_n - 11) / 8) + 1 launches: a block owns a tile of 2^s x C elements (s butterfly stages; C >= 8
 //      neighbouring sub-transforms so that every global access of a warp covers whole 256-byte runs), keeps it in shared
-//      memory as 8 limb planes, and runs the s stages there -- one decimation-in-time butterfly (1 Montgomery
-//      multiplication, 1 add, 1 sub) per thread and step.  The vector crosses HBM once per pass (3 passes at 2^26) while the
+//      memory (64 KiB, 128-bit accesses), and runs the s stages there two at a time: a thread holds four elements in
+//      registers and does the four decimation-in-time butterflies (1 Montgomery multiplication, 1 add, 1 sub each) of a
+//      stage pair between two barriers.  The vector crosses HBM once per pass (3 passes at 2^26) while the
 //      log_n/2 multiplications per element stay on the multiplier pipe: the transform is IMAD-bound like the gate check.
 //   Twiddles w^i (i < n/2) come from a table built once per domain size by k_simple<NttTwiddleBody> (inverse transform:
 //   w^-i = -w^(n/2 - i)); a pass touches about as many table bytes as data bytes, mostly out of L2.
@@ -101,43 +102,97 @@ PG_HD Fr ntt_twiddle(const NttPassArgs& a, uint64_t tw_index) {
 }
 
 #if defined(__CUDACC__)
+// Shared-memory tile: two planes of 16-byte half scalars, [lo half of every element][hi half of every element]; a warp that
+// touches consecutive elements makes conflict-free 128-bit accesses.
+__device__ __forceinline__ Fr tile_load(const uint4* tile, uint32_t E, uint32_t e) {
+    const uint4 lo = tile[e], hi = tile[E + e];
+    Fr r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+__device__ __forceinline__ void tile_store(uint4* tile, uint32_t E, uint32_t e, const Fr& x) {
+    tile[e] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    tile[E + e] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+// 32-bit index arithmetic throughout: element indices are < 2^32 (log_n <= 32), only the final byte address is 64-bit.
+__device__ __forceinline__ uint32_t ntt_index32(const NttPassArgs& a, uint32_t blk, uint32_t e) {
+    const uint32_t c = e & ((1u << a.log_c) - 1u), v = e >> a.log_c;
+    const uint32_t g = (blk << a.log_c) | c;
+    const uint32_t g_lo = a.t0 ? g & (0xffffffffu >> (32u - a.t0)) : 0u, g_hi = a.t0 < 32u ? g >> a.t0 : 0u;
+    const uint32_t sh = a.t0 + a.s;
+    return (sh < 32u ? g_hi << sh : 0u) | (v << a.t0) | g_lo;
+}
+__device__ __forceinline__ Fr ntt_twiddle32(const NttPassArgs& a, uint32_t ti) {
+    if (!a.inverse) return aos_load(a.tw, ti);
+    if (ti == 0) return fr_one();
+    return fr_neg(aos_load(a.tw, (1u << (a.log_n - 1u)) - ti));
+}
+
+// Two butterfly stages per trip through shared memory: a thread takes the four elements that differ in bits u and u+1 of v,
+// runs stage t0+u on the pairs (0,1), (2,3) -- they share one twiddle -- and stage t0+u+1 on (0,2), (1,3), whose twiddle
+// exponents differ by n/4.  An odd stage count ends with one radix-2 step.
 __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const NttPassArgs a) {
-    extern __shared__ __align__(16) uint32_t s_tile[];            // [8 limbs][E]
+    extern __shared__ __align__(16) uint4 s_tile[];               // [2 halves][E]
     __shared__ uint32_t s_q[8];
     const uint32_t log_e = a.s + a.log_c, E = 1u << log_e;
-    const uint64_t blk = blockIdx.x;
+    const uint32_t blk = blockIdx.x;
     if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
-    for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS) {
-        const Fr x = aos_load(a.data, ntt_index(a, blk, e));
-#pragma unroll
-        for (int k = 0; k < 8; k++) s_tile[k * E + e] = x.v[k];
-    }
+    for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS)
+        tile_store(s_tile, E, e, aos_load(a.data, ntt_index32(a, blk, e)));
     __syncthreads();
     QRegs q;
 #pragma unroll
     for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
-    for (uint32_t u = 0; u < a.s; u++) {
+    const uint32_t c_mask = (1u << a.log_c) - 1u, lo_mask = a.t0 ? 0xffffffffu >> (32u - a.t0) : 0u;
+    uint32_t u = 0;
+    for (; u + 2 <= a.s; u += 2) {
+        const uint32_t sh = a.log_n - 1u - (a.t0 + u);            // stage t0+u: exponent = pos << sh
 #pragma unroll 1
-        for (uint32_t b = threadIdx.x; b < E / 2; b += NTT_THREADS) {
-            uint32_t e0, e1; uint64_t ti;
-            ntt_butterfly(a, blk, u, b, e0, e1, ti);
-            const Fr w = ntt_twiddle(a, ti);
-            Fr x0, x1;
-#pragma unroll
-            for (int k = 0; k < 8; k++) { x0.v[k] = s_tile[k * E + e0]; x1.v[k] = s_tile[k * E + e1]; }
-            const Fr t = fr_mul_eo(x1, w, q);
-            const Fr y0 = fr_add(x0, t), y1 = fr_sub(x0, t);
-#pragma unroll
-            for (int k = 0; k < 8; k++) { s_tile[k * E + e0] = y0.v[k]; s_tile[k * E + e1] = y1.v[k]; }
+        for (uint32_t r = threadIdx.x; r < E / 4; r += NTT_THREADS) {
+            const uint32_t c = r & c_mask, bf = r >> a.log_c;
+            const uint32_t low = bf & ((1u << u) - 1u);
+            const uint32_t v0 = ((bf >> u) << (u + 2)) | low;
+            const uint32_t e0 = (v0 << a.log_c) | c, d = 1u << (u + a.log_c);
+            const uint32_t pos = (low << a.t0) | (((blk << a.log_c) | c) & lo_mask);
+            const uint32_t ti = pos << sh;
+            Fr x0 = tile_load(s_tile, E, e0), x1 = tile_load(s_tile, E, e0 + d);
+            Fr x2 = tile_load(s_tile, E, e0 + 2 * d), x3 = tile_load(s_tile, E, e0 + 3 * d);
+            {
+                const Fr w = ntt_twiddle32(a, ti);
+                const Fr t1 = fr_mul_eo(x1, w, q), t3 = fr_mul_eo(x3, w, q);
+                x1 = fr_sub(x0, t1); x0 = fr_add(x0, t1);
+                x3 = fr_sub(x2, t3); x2 = fr_add(x2, t3);
+            }
+            {
+                const Fr wa = ntt_twiddle32(a, ti >> 1);
+                const Fr t2 = fr_mul_eo(x2, wa, q);
+                x2 = fr_sub(x0, t2); x0 = fr_add(x0, t2);
+                const Fr wb = ntt_twiddle32(a, (ti >> 1) + (1u << (a.log_n - 2u)));
+                const Fr t3 = fr_mul_eo(x3, wb, q);
+                x3 = fr_sub(x1, t3); x1 = fr_add(x1, t3);
+            }
+            tile_store(s_tile, E, e0, x0); tile_store(s_tile, E, e0 + d, x1);
+            tile_store(s_tile, E, e0 + 2 * d, x2); tile_store(s_tile, E, e0 + 3 * d, x3);
         }
         __syncthreads();
     }
-    for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS) {
-        Fr x;
-#pragma unroll
-        for (int k = 0; k < 8; k++) x.v[k] = s_tile[k * E + e];
-        aos_store(a.data, ntt_index(a, blk, e), x);
+    if (u < a.s) {                                                // last single stage
+        const uint32_t sh = a.log_n - 1u - (a.t0 + u);
+#pragma unroll 1
+        for (uint32_t b = threadIdx.x; b < E / 2; b += NTT_THREADS) {
+            const uint32_t c = b & c_mask, bf = b >> a.log_c;
+            const uint32_t low = bf & ((1u << u) - 1u);
+            const uint32_t v0 = ((bf >> u) << (u + 1)) | low;
+            const uint32_t e0 = (v0 << a.log_c) | c, e1 = e0 + (1u << (u + a.log_c));
+            const uint32_t pos = (low << a.t0) | (((blk << a.log_c) | c) & lo_mask);
+            const Fr w = ntt_twiddle32(a, pos << sh);
+            const Fr x0 = tile_load(s_tile, E, e0);
+            const Fr t = fr_mul_eo(tile_load(s_tile, E, e1), w, q);
+            tile_store(s_tile, E, e0, fr_add(x0, t)); tile_store(s_tile, E, e1, fr_sub(x0, t));
+        }
+        __syncthreads();
     }
+    for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS)
+        aos_store(a.data, ntt_index32(a, blk, e), tile_load(s_tile, E, e));
 }
 #endif
 
