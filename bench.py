@@ -183,6 +183,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line; NCCL's banner goes to stderr
         dist.init_process_group("nccl", device_id=dev)
     n = 1 << args.log2n
     warm = max(args.warmup, 3)
