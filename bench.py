@@ -153,11 +153,30 @@ def run_reference(args):
             "gpu_launches": 0,
             "note": "the Rust reference cannot be built here (no cargo, dusk-plonk not vendored): this is the C restatement "
                     "oracle/ with the reference's cost structure, all host cores, one composer per thread"}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep the real stdout for it and send everything libraries print to fd 1
+    (NCCL's version banner, for one) to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -183,7 +202,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line; NCCL's banner goes to stderr
         dist.init_process_group("nccl", device_id=dev)
     n = 1 << args.log2n
     warm = max(args.warmup, 3)
@@ -312,7 +330,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_run(None, os.cpu_count() or 1)
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
