@@ -67,6 +67,10 @@ def lib():
             "orc_bits_count_api": (u64, [vp]), "orc_num_bits_api": (u64, [vp]),
             "orc_fft": (i32, [vp, C.c_uint, i32]), "orc_domain_group_gen": (None, [C.c_uint, vp]),
             "orc_domain_log_size": (C.c_uint, [u64]), "orc_wire_polynomials": (C.c_uint, [vp, vp]),
+            "orc_fp_from_raw": (None, [vp, vp]), "orc_fp_to_raw": (None, [vp, vp]), "orc_fp_mul": (None, [vp, vp, vp]),
+            "orc_fp_add": (None, [vp, vp, vp]), "orc_fp_sub": (None, [vp, vp, vp]), "orc_fp_neg": (None, [vp, vp]), "orc_fp_inv": (None, [vp, vp]),
+            "orc_g1_generator": (None, [vp]), "orc_g1_on_curve": (i32, [vp]), "orc_g1_add": (None, [vp, vp, vp]),
+            "orc_g1_mul": (None, [vp, vp, vp]), "orc_g1_msm": (None, [u64, vp, vp, vp]), "orc_srs_powers": (None, [vp, vp, u64, vp]),
             "orc_bench_range": (dbl, [i32, u64, vp, vp, vp, i32, i32, i32, u64, vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
@@ -272,6 +276,80 @@ def domain_group_gen(log_n: int) -> int:
     out = np.zeros((1, 4), dtype=np.uint64)
     lib().orc_domain_group_gen(log_n, _p(out))
     return to_ints(out)[0]
+
+
+# ---- G1 (oracle/g1.c).  A point is 13 uint64: 6 limbs of x, 6 limbs of y (Montgomery form, like the crate's Fp), infinity flag.
+P_FIELD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+R_FIELD = (1 << 384) % P_FIELD
+
+
+def g1_from_ints(points) -> np.ndarray:
+    """[(x, y) | None, ...] canonical integers -> (n, 13) uint64 oracle points."""
+    out = np.zeros((len(points), 13), dtype=np.uint64)
+    for i, pt in enumerate(points):
+        if pt is None:
+            out[i, 12] = 1
+            continue
+        for c, v in enumerate(pt):
+            m = v * R_FIELD % P_FIELD
+            for k in range(6):
+                out[i, 6 * c + k] = (m >> (64 * k)) & (2 ** 64 - 1)
+    return out
+
+
+def g1_to_ints(a: np.ndarray) -> list:
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 13)
+    r_inv = pow(R_FIELD, -1, P_FIELD)
+    out = []
+    for row in a:
+        if int(row[12]) & 0xffffffff:
+            out.append(None)
+            continue
+        x = sum(int(row[k]) << (64 * k) for k in range(6)) * r_inv % P_FIELD
+        y = sum(int(row[6 + k]) << (64 * k) for k in range(6)) * r_inv % P_FIELD
+        out.append((x, y))
+    return out
+
+
+def g1_generator() -> np.ndarray:
+    out = np.zeros((1, 13), dtype=np.uint64)
+    lib().orc_g1_generator(_p(out))
+    return out
+
+
+def g1_add(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 13); b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 13)
+    out = np.zeros_like(a)
+    for i in range(a.shape[0]):
+        lib().orc_g1_add(_p(a[i:i + 1]), _p(b[i:i + 1]), _p(out[i:i + 1]))
+    return out
+
+
+def g1_mul(a: np.ndarray, k) -> np.ndarray:
+    """k: (n, 4) Montgomery scalars."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 13); k = np.ascontiguousarray(_fr_arr(k))
+    out = np.zeros_like(a)
+    for i in range(a.shape[0]):
+        lib().orc_g1_mul(_p(a[i:i + 1]), _p(k[i:i + 1]), _p(out[i:i + 1]))
+    return out
+
+
+def g1_msm(points: np.ndarray, scalars) -> np.ndarray:
+    """msm_variable_base(points, scalars) -> one point."""
+    points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 13); scalars = np.ascontiguousarray(_fr_arr(scalars))
+    assert points.shape[0] == scalars.shape[0]
+    out = np.zeros((1, 13), dtype=np.uint64)
+    lib().orc_g1_msm(points.shape[0], _p(points), _p(scalars), _p(out))
+    return out
+
+
+def srs_powers(beta, n: int, base: np.ndarray | None = None) -> np.ndarray:
+    """powers_of_g[i] = beta^i * g (PublicParameters::setup); beta: one Montgomery scalar."""
+    base = g1_generator() if base is None else np.ascontiguousarray(base, dtype=np.uint64).reshape(1, 13)
+    beta = np.ascontiguousarray(_fr_arr(beta))
+    out = np.zeros((n, 13), dtype=np.uint64)
+    lib().orc_srs_powers(_p(beta), _p(base), n, _p(out))
+    return out
 
 
 def bench_range(gadget: int, wit, mn, mx, threads: int, mode: int = FAITHFUL, chunk: int = 64, want_results=False):

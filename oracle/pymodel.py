@@ -355,3 +355,66 @@ def wire_polynomials(composer: "StandardComposer"):
         vals = [composer.variables[v] for v in wires] + [0] * (size - composer.n)
         cols.append(dft(vals, inverse=True))
     return cols
+
+
+# ------------------------------------------------------------------------------------------------ G1 / commitments
+# [DEP] dusk-bls12_381 G1Affine/G1Projective and dusk-plonk 0.8 `CommitKey::commit` (src/commitment_scheme/kzg10/key.rs):
+#     commitment = msm_variable_base(&self.powers_of_g, &polynomial.coeffs)
+# reached from /root/reference/tests/range_gadgets_tests.rs:90-91 through Prover::prove (w_l_poly_commit ... w_4_poly_commit).
+# Independent of oracle/g1.c: affine chord-and-tangent formulas on Python ints, one field inversion per addition.
+P_FIELD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+G1_B = 4
+G1_GENERATOR = (0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb,
+                0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1)
+
+
+def g1_on_curve(pt) -> bool:
+    return pt is None or (pt[1] * pt[1] - pt[0] ** 3 - G1_B) % P_FIELD == 0
+
+
+def g1_add(a, b):
+    """Affine addition; None is the point at infinity."""
+    if a is None:
+        return b
+    if b is None:
+        return a
+    if a[0] == b[0]:
+        if (a[1] + b[1]) % P_FIELD == 0:
+            return None
+        lam = 3 * a[0] * a[0] * pow(2 * a[1], P_FIELD - 2, P_FIELD) % P_FIELD
+    else:
+        lam = (b[1] - a[1]) * pow(b[0] - a[0], P_FIELD - 2, P_FIELD) % P_FIELD
+    x3 = (lam * lam - a[0] - b[0]) % P_FIELD
+    return x3, (lam * (a[0] - x3) - a[1]) % P_FIELD
+
+
+def g1_neg(a):
+    return None if a is None else (a[0], (-a[1]) % P_FIELD)
+
+
+def g1_mul(k: int, pt):
+    k %= Q
+    acc = None
+    while k:
+        if k & 1:
+            acc = g1_add(acc, pt)
+        pt = g1_add(pt, pt)
+        k >>= 1
+    return acc
+
+
+def g1_msm(scalars, points):
+    """sum_i scalars[i] * points[i] by the definition (msm_variable_base)."""
+    acc = None
+    for k, pt in zip(scalars, points):
+        acc = g1_add(acc, g1_mul(k, pt))
+    return acc
+
+
+def srs_powers(beta: int, n: int, base=G1_GENERATOR):
+    """PublicParameters::setup: powers_of_g[i] = beta^i * g (util::powers_of + slow_multiscalar_mul_single_base)."""
+    out, e = [], 1
+    for _ in range(n):
+        out.append(g1_mul(e, base))
+        e = e * beta % Q
+    return out
