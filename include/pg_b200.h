@@ -180,6 +180,25 @@ int pg_permutation(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *sigma, in
 int pg_fft(pg_ctx *ctx, uint32_t log_n, int inverse, const pg_fr *src, pg_fr *dst, int on_device);
 int pg_wire_polynomials(pg_ctx *ctx, uint32_t log_n, pg_fr *dst, int dst_on_device);
 
+/* ---- commitments (second half) -----------------------------------------------------------------
+ * KZG commitments of coefficient vectors in the BLS12-381 group G1 [DEP dusk-plonk 0.8 CommitKey::commit =
+ * dusk-bls12_381 msm_variable_base(&powers_of_g, &poly.coeffs); Prover::prove computes w_l_poly_commit .. w_4_poly_commit right
+ * after the wire polynomials; reached from /root/reference/tests/range_gadgets_tests.rs:90-91].
+ * pg_g1_affine = the in-memory G1Affine { x: Fp, y: Fp } of dusk-bls12_381 (Fp([u64; 6]), Montgomery form, R = 2^384) without
+ * its `infinity` flag byte: the point at infinity is the all-zero pair.
+ * pg_msm: out = sum_i scalars[i] * points[i] (one point, written to HOST memory); points/scalars both host or both device.
+ * pg_srs_powers: out[i] = beta^i * base, base == NULL meaning the G1 generator (PublicParameters::setup: powers_of_g).
+ * pg_g1_fixed_base_mul: out[i] = scalars[i] * base.  base and beta are host pointers to one element.
+ * pg_commit_wire_polynomials: the four commitments of the composer's wire polynomials over the domain 2^log_n against
+ * powers_of_g[0 .. 2^log_n), written to host memory (w_l, w_r, w_o, w_4).  The reference blinds nothing in this version. */
+typedef struct pg_g1_affine { uint64_t x[6]; uint64_t y[6]; } pg_g1_affine;
+int pg_msm(pg_ctx *ctx, uint64_t n, const pg_g1_affine *points, const pg_fr *scalars, pg_g1_affine *out, int on_device);
+int pg_srs_powers(pg_ctx *ctx, const pg_fr *beta, const pg_g1_affine *base, uint64_t n, pg_g1_affine *out, int out_on_device);
+int pg_g1_fixed_base_mul(pg_ctx *ctx, uint64_t n, const pg_g1_affine *base, const pg_fr *scalars, pg_g1_affine *out, int on_device);
+int pg_commit_wire_polynomials(pg_ctx *ctx, uint32_t log_n, const pg_g1_affine *powers_of_g, int powers_on_device, pg_g1_affine *out4);
+/* self-test helper: op 0: out[i] = a[i] + b[i]; op 1: out[i].x[0] = 1 if a[i] is on the curve (or infinity) else 0.  Host buffers. */
+int pg_g1_op(pg_ctx *ctx, int op, uint64_t n, const pg_g1_affine *a, const pg_g1_affine *b, pg_g1_affine *out);
+
 /* ---- wire format -------------------------------------------------------------------------
  * BlsScalar::to_bytes / from_bytes [dusk_bytes::Serializable<32>, called at /root/reference/src/range.rs:163]: the canonical
  * little-endian 32-byte encoding used for witness / selector / public-input dumps exchanged with Rust tooling.  n scalars;

@@ -274,6 +274,67 @@ class StandardComposer:
         self._ok(self._L.pg_wire_polynomials(self._ctx, log_n, dst.ctypes.data_as(C.c_void_p), 0), "pg_wire_polynomials")
         return dst
 
+    # -- commitments: G1 multi-scalar multiplication, SRS powers, wire-polynomial commitments ([DEP] dusk-plonk 0.8 / dusk-bls12_381)
+    @staticmethod
+    def _points(x):
+        """(pointer, on_device, n, keep-alive): points are (n, 12) uint64 = n x {x: Fp, y: Fp} Montgomery limbs; all-zero = infinity."""
+        if hasattr(x, "data_ptr"):
+            return C.c_void_p(x.data_ptr()), 1, x.shape[0], x
+        a = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 12)
+        return a.ctypes.data_as(C.c_void_p), 0, a.shape[0], a
+
+    def msm(self, points, scalars) -> np.ndarray:
+        """sum_i scalars[i] * points[i] -> (12,) uint64 affine point (msm_variable_base)."""
+        pp, pdev, n, _k1 = self._points(points)
+        if hasattr(scalars, "data_ptr"):
+            sp, sdev, sn, _k2 = C.c_void_p(scalars.data_ptr()), 1, scalars.shape[0], scalars
+        else:
+            _k2 = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+            sp, sdev, sn = _k2.ctypes.data_as(C.c_void_p), 0, _k2.shape[0]
+        if n != sn or pdev != sdev:
+            raise ValueError("msm: points and scalars must have the same length and live on the same side")
+        out = np.zeros(12, dtype=np.uint64)
+        self._ok(self._L.pg_msm(self._ctx, n, pp, sp, out.ctypes.data_as(C.c_void_p), pdev), "pg_msm")
+        return out
+
+    def srs_powers(self, beta, n: int, base=None, out=None):
+        """powers_of_g[i] = beta^i * base (default base: the G1 generator) -- PublicParameters::setup."""
+        b = np.ascontiguousarray(beta, dtype=np.uint64).reshape(4)
+        bp = None if base is None else np.ascontiguousarray(base, dtype=np.uint64).reshape(12)
+        bptr = None if bp is None else bp.ctypes.data_as(C.c_void_p)
+        if out is not None:
+            self._ok(self._L.pg_srs_powers(self._ctx, b.ctypes.data_as(C.c_void_p), bptr, n, C.c_void_p(out.data_ptr()), 1), "pg_srs_powers")
+            return out
+        res = np.zeros((n, 12), dtype=np.uint64)
+        self._ok(self._L.pg_srs_powers(self._ctx, b.ctypes.data_as(C.c_void_p), bptr, n, res.ctypes.data_as(C.c_void_p), 0), "pg_srs_powers")
+        return res
+
+    def g1_fixed_base_mul(self, scalars, base=None) -> np.ndarray:
+        a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        bp = None if base is None else np.ascontiguousarray(base, dtype=np.uint64).reshape(12)
+        res = np.zeros((a.shape[0], 12), dtype=np.uint64)
+        self._ok(self._L.pg_g1_fixed_base_mul(self._ctx, a.shape[0], None if bp is None else bp.ctypes.data_as(C.c_void_p),
+                                              a.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p), 0), "pg_g1_fixed_base_mul")
+        return res
+
+    def commit_wire_polynomials(self, powers_of_g, log_n: int | None = None) -> np.ndarray:
+        """(4, 12) uint64: commitments to w_l, w_r, w_o, w_4 against powers_of_g[0 .. 2^log_n)."""
+        log_n = self.domain_log_size() if log_n is None else log_n
+        pp, pdev, n, _keep = self._points(powers_of_g)
+        if n < (1 << log_n):
+            raise ValueError("commit_wire_polynomials: the SRS holds fewer powers than the domain size")
+        out = np.zeros((4, 12), dtype=np.uint64)
+        self._ok(self._L.pg_commit_wire_polynomials(self._ctx, log_n, pp, pdev, out.ctypes.data_as(C.c_void_p)), "pg_commit_wire_polynomials")
+        return out
+
+    def g1_op(self, op: int, a, b=None) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 12)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 12) if b is not None else None
+        out = np.zeros_like(a)
+        self._ok(self._L.pg_g1_op(self._ctx, op, a.shape[0], a.ctypes.data_as(C.c_void_p),
+                                  b.ctypes.data_as(C.c_void_p) if b is not None else None, out.ctypes.data_as(C.c_void_p)), "pg_g1_op")
+        return out
+
     # -- wire format: canonical little-endian bytes <-> Montgomery limbs (BlsScalar::to_bytes / from_bytes)
     def to_bytes(self, scalars) -> np.ndarray:
         a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)

@@ -113,6 +113,23 @@ int pg_wire_polynomials(pg_ctx* ctx, uint32_t log_n, pg_fr* dst, int dst_on_devi
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device);
     return ctx->e.wire_polynomials(log_n, dst, dst_on_device);
 }
+int pg_msm(pg_ctx* ctx, uint64_t n, const pg_g1_affine* points, const pg_fr* scalars, pg_g1_affine* out, int on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, points, on_device); PG_ALIGNED(ctx, scalars, on_device);
+    return ctx->e.msm(n, points, scalars, out, on_device);
+}
+int pg_srs_powers(pg_ctx* ctx, const pg_fr* beta, const pg_g1_affine* base, uint64_t n, pg_g1_affine* out, int out_on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, out, out_on_device);
+    return ctx->e.srs_powers(beta, base, n, out, out_on_device);
+}
+int pg_g1_fixed_base_mul(pg_ctx* ctx, uint64_t n, const pg_g1_affine* base, const pg_fr* scalars, pg_g1_affine* out, int on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, scalars, on_device); PG_ALIGNED(ctx, out, on_device);
+    return ctx->e.g1_fixed_base_mul(n, base, scalars, out, on_device);
+}
+int pg_commit_wire_polynomials(pg_ctx* ctx, uint32_t log_n, const pg_g1_affine* powers_of_g, int powers_on_device, pg_g1_affine* out4) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, powers_of_g, powers_on_device);
+    return ctx->e.commit_wire_polynomials(log_n, powers_of_g, powers_on_device, out4);
+}
+int pg_g1_op(pg_ctx* ctx, int op, uint64_t n, const pg_g1_affine* a, const pg_g1_affine* b, pg_g1_affine* out) { PG_NEED_CTX(ctx); return ctx->e.g1_op(op, n, a, b, out); }
 int pg_fr_to_bytes(pg_ctx* ctx, uint64_t n, const pg_fr* src, uint8_t* dst, int on_device) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, src, on_device); PG_ALIGNED(ctx, dst, on_device);
     return ctx->e.convert(true, n, src, reinterpret_cast<pg_fr*>(dst), on_device, nullptr, nullptr);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <new>
+#include <cub/device/device_radix_sort.cuh>
 #include "engine.hpp"
 #include "kernels.cuh"
 
@@ -78,6 +79,7 @@ public:
         for (auto& ev : events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
         for (auto& ev : ev_free) cudaEventDestroy(ev);
         events.clear(); ev_free.clear();
+        if (sort_tmp) { cudaFree(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0; }
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (copy_ready) cudaEventDestroy(copy_ready);
         copy_stream = nullptr; copy_ready = nullptr;
@@ -197,6 +199,21 @@ public:
         k_materialize_tiled<<<(unsigned)tiles, BLOCK, 0, stream>>>(a);
         toc();
         return launched("k_materialize_tiled");
+    }
+    // radix sort of (key, value) pairs by the low key_bits of the key (CUB; temporary storage kept for the context's lifetime)
+    void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+    bool sort_pairs(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t n, uint32_t key_bits) {
+        size_t need = 0;
+        PG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys_out, vals, vals_out, (long long)n, 0, (int)key_bits, stream));
+        if (need > sort_tmp_bytes) {
+            if (sort_tmp) { PG_CUDA(cudaStreamSynchronize(stream)); cudaFree(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0; }
+            PG_CUDA(cudaMalloc(&sort_tmp, need));
+            sort_tmp_bytes = need;
+        }
+        tic(CLS_OTHER, 0);
+        PG_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, need, keys, keys_out, vals, vals_out, (long long)n, 0, (int)key_bits, stream));
+        toc();
+        return launched("cub::DeviceRadixSort::SortPairs");
     }
     bool run_ntt_pass(const NttPassArgs& a, uint64_t n_blocks) {
         const size_t smem = (size_t)32 << (a.s + a.log_c);

@@ -13,6 +13,7 @@
 //   template<class Body> bool run_simple(const typename Body::Args&, uint64_t n, int cls)
 //   bool run_batch_inv(const BatchInvArgs&, int cls)            -- out_slot = in_slot^-1 (or 0) over table slots
 //   bool run_check(const CheckArgs&), bool run_check_rows(const CheckRowsBody::Args&)
+//   bool sort_pairs(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t n, uint32_t key_bits)
 //   bool run_ntt_pass(const NttPassArgs&, uint64_t n_blocks)    -- one group of butterfly stages over all tiles (ntt.cuh)
 //   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), bool ubench(int, double*), timing(pg_timing*, bool reset)
 #pragma once
@@ -23,6 +24,7 @@
 #include "../../include/pg_b200.h"
 #include "templates.hpp"
 #include "ntt.cuh"
+#include "msm.cuh"
 
 namespace pg {
 
@@ -778,6 +780,117 @@ public:
         else { FrOpBody::Args g{op, da, db, dout, n}; ok = be.template run_simple<FrOpBody>(g, n, CLS_OTHER); }
         if (!ok) return fail(PG_ERR_CUDA, "fr_op kernel");
         rc = deliver(out, dout, n * sizeof(pg_fr), 0);
+        release_scratch_from(mark);
+        return rc;
+    }
+    // ------------------------------------------------------------------------------------------------ commitments
+    // msm_variable_base / CommitKey::commit / PublicParameters::setup powers; see msm.cuh.  Points are 96-byte affine pairs.
+    const uint4* stage_bytes(const void* p, size_t bytes, int on_device, int* rc) {
+        return stage(reinterpret_cast<const pg_fr*>(p), (bytes + sizeof(pg_fr) - 1) / sizeof(pg_fr), on_device, rc);   // whole 32-byte units
+    }
+    // device-side MSM: d_points (n affine), d_scalars (n Montgomery scalars) -> d_out (one affine point, 96 bytes)
+    int msm_dev(uint64_t n, const uint4* d_points, const uint4* d_scalars, uint4* d_out) {
+        const size_t mark = scratch.size();
+        auto tmp = [&](size_t bytes) -> void* { void* q = dalloc(bytes); if (q) scratch.push_back(q); return q; };
+        const MsmPlan plan = msm_plan(n);
+        const uint64_t count = (uint64_t)plan.n_windows * n, n_buckets = (uint64_t)plan.n_windows << plan.c;
+        uint32_t key_bits = plan.c; while ((1u << (key_bits - plan.c)) < plan.n_windows) key_bits++;
+        uint32_t* keys = (uint32_t*)tmp(count * 4); uint32_t* vals = (uint32_t*)tmp(count * 4);
+        uint32_t* keys2 = (uint32_t*)tmp(count * 4); uint32_t* vals2 = (uint32_t*)tmp(count * 4);
+        uint4* buckets = (uint4*)tmp(n_buckets * sizeof(G1X));
+        const uint64_t n_chunks = n_buckets / plan.chunk;
+        uint4* ping = (uint4*)tmp(n_chunks * sizeof(G1X)); uint4* pong = (uint4*)tmp(((n_chunks + 15) / 16 + plan.n_windows) * sizeof(G1X));
+        if (!keys || !vals || !keys2 || !vals2 || !buckets || !ping || !pong) return fail(PG_ERR_OOM, "msm buffers");
+        MsmDigitsBody::Args dg{d_scalars, keys, vals, n, plan.c, plan.n_windows};
+        if (!be.template run_simple<MsmDigitsBody>(dg, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm digits kernel");
+        if (!be.sort_pairs(keys, vals, keys2, vals2, count, key_bits)) return fail(PG_ERR_CUDA, "msm sort");
+        MsmBucketBody::Args bk{keys2, vals2, d_points, buckets, count, n_buckets, plan.c};
+        if (!be.template run_simple<MsmBucketBody>(bk, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm bucket kernel");
+        MsmChunkBody::Args ck{buckets, ping, n_chunks, plan.c, plan.chunk};
+        if (!be.template run_simple<MsmChunkBody>(ck, n_chunks, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm chunk kernel");
+        uint32_t seg = (1u << plan.c) / plan.chunk;                    // partial sums per window
+        uint4 *src = ping, *dst = pong;
+        while (seg > 1) {
+            const uint32_t seg_out = (seg + 15) / 16;
+            MsmSumBody::Args sm{src, dst, (uint64_t)plan.n_windows * seg_out, seg, seg_out, 16};
+            if (!be.template run_simple<MsmSumBody>(sm, sm.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm sum kernel");
+            std::swap(src, dst); seg = seg_out;
+        }
+        MsmFinalBody::Args fin{src, d_out, 1, plan.c, plan.n_windows};
+        if (!be.template run_simple<MsmFinalBody>(fin, 1, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm final kernel");
+        release_scratch_from(mark);      // work buffers are only touched by kernels on the engine's stream: stream order makes their reuse safe
+        return PG_OK;
+    }
+    int msm(uint64_t n, const pg_g1_affine* points, const pg_fr* scalars, pg_g1_affine* out, int on_device) {
+        if (!out || (n && (!points || !scalars))) return fail(PG_ERR_ARG, "msm: null argument");
+        if (n >= (1ull << 32)) return fail(PG_ERR_ARG, "msm: more than 2^32 - 1 terms");
+        if (!n) { memset(out, 0, sizeof(*out)); return PG_OK; }          // empty sum: the point at infinity
+        const size_t mark = scratch.size();
+        int rc; const uint4* dp = stage_bytes(points, n * sizeof(pg_g1_affine), on_device, &rc); if (!dp) return rc;
+        const uint4* ds = stage(scalars, n, on_device, &rc); if (!ds) return rc;
+        uint4* d_out = (uint4*)dalloc(sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "msm result"); scratch.push_back(d_out);
+        if ((rc = msm_dev(n, dp, ds, d_out))) return rc;
+        rc = deliver(out, d_out, sizeof(pg_g1_affine), 0);
+        release_scratch_from(mark);
+        return rc;
+    }
+    // out[i] = scalars[i] * base (base == nullptr: the G1 generator)
+    int g1_fixed_base_mul(uint64_t n, const pg_g1_affine* base, const pg_fr* scalars, pg_g1_affine* out, int on_device) {
+        if (n && (!scalars || !out)) return fail(PG_ERR_ARG, "g1_fixed_base_mul: null argument");
+        if (!n) return PG_OK;
+        const size_t mark = scratch.size();
+        int rc; const uint4* ds = stage(scalars, n, on_device, &rc); if (!ds) return rc;
+        uint4* d_out = reinterpret_cast<uint4*>(out);
+        if (!on_device) { d_out = (uint4*)dalloc(n * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "point buffer"); scratch.push_back(d_out); }
+        G1FixedBaseMulBody::Args a; a.scalars = ds; a.out = d_out; a.n = n;
+        if (base) memcpy(&a.base, base, sizeof(G1Affine)); else a.base = g1_generator();      // base is always a host pointer (one point)
+        if (!be.template run_simple<G1FixedBaseMulBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base kernel");
+        if (on_device) return PG_OK;
+        rc = deliver(out, d_out, n * sizeof(pg_g1_affine), 0);
+        release_scratch_from(mark);
+        return rc;
+    }
+    // powers_of_g[i] = beta^i * base, i < n  (PublicParameters::setup)
+    int srs_powers(const pg_fr* beta, const pg_g1_affine* base, uint64_t n, pg_g1_affine* out, int out_on_device) {
+        if (!beta || (n && !out)) return fail(PG_ERR_ARG, "srs_powers: null argument");
+        if (!n) return PG_OK;
+        std::vector<pg_fr> pw(n);                                       // util::powers_of(beta, n)
+        Fr b, e = fr_one(); memcpy(&b, beta, sizeof(Fr));
+        for (uint64_t i = 0; i < n; i++) { memcpy(&pw[i], &e, sizeof(Fr)); e = fr_mul(e, b); }
+        if (!out_on_device) return g1_fixed_base_mul(n, base, pw.data(), out, 0);
+        const size_t mark = scratch.size();
+        int rc; const uint4* ds = stage(pw.data(), n, 0, &rc); if (!ds) return rc;
+        rc = g1_fixed_base_mul(n, base, reinterpret_cast<const pg_fr*>(ds), out, 1);
+        if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
+        release_scratch_from(mark);
+        return rc;
+    }
+    // the four wire-polynomial commitments of Prover::prove: out[w] = commit(w-th wire polynomial) against powers_of_g[0 .. 2^log_n)
+    int commit_wire_polynomials(uint32_t log_n, const pg_g1_affine* powers, int powers_on_device, pg_g1_affine* out) {
+        if (!powers || !out) return fail(PG_ERR_ARG, "commit_wire_polynomials: null argument");
+        if (log_n > NTT_TWO_ADICITY || (1ull << log_n) < n_rows) return fail(PG_ERR_ARG, "commit_wire_polynomials: domain smaller than the circuit or larger than 2^32");
+        const uint64_t n = 1ull << log_n;
+        const size_t mark = scratch.size();
+        int rc; const uint4* dp = stage_bytes(powers, n * sizeof(pg_g1_affine), powers_on_device, &rc); if (!dp) return rc;
+        uint4* polys = (uint4*)dalloc(4 * n * sizeof(pg_fr)); if (!polys) return fail(PG_ERR_OOM, "wire polynomial buffer"); scratch.push_back(polys);
+        uint4* d_out = (uint4*)dalloc(4 * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "commitments"); scratch.push_back(d_out);
+        if ((rc = wire_polynomials(log_n, reinterpret_cast<pg_fr*>(polys), 1))) return rc;
+        for (int w = 0; w < 4; w++)
+            if ((rc = msm_dev(n, dp, polys + 2 * (uint64_t)w * n, d_out + 6 * w))) return rc;
+        rc = deliver(out, d_out, 4 * sizeof(pg_g1_affine), 0);
+        release_scratch_from(mark);
+        return rc;
+    }
+    int g1_op(int op, uint64_t n, const pg_g1_affine* a, const pg_g1_affine* b, pg_g1_affine* out) {
+        if (!n) return PG_OK;
+        if (!a || !out || (op == 0 && !b)) return fail(PG_ERR_ARG, "g1_op: null argument");
+        const size_t mark = scratch.size();
+        int rc; const uint4* da = stage_bytes(a, n * sizeof(pg_g1_affine), 0, &rc); if (!da) return rc;
+        const uint4* db = nullptr; if (b) { db = stage_bytes(b, n * sizeof(pg_g1_affine), 0, &rc); if (!db) return rc; }
+        uint4* d_out = (uint4*)dalloc(n * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "g1_op buffer"); scratch.push_back(d_out);
+        G1OpBody::Args g{da, db, d_out, n, op};
+        if (!be.template run_simple<G1OpBody>(g, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "g1_op kernel");
+        rc = deliver(out, d_out, n * sizeof(pg_g1_affine), 0);
         release_scratch_from(mark);
         return rc;
     }

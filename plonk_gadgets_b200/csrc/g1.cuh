@@ -1,0 +1,206 @@
+// g1.cuh -- BLS12-381 base field Fp and the group G1 (y^2 = x^3 + 4), as far as KZG commitments need them
+// (second half: `commit_key.commit(&w_l_poly)` = msm_variable_base(powers_of_g, coeffs)).
+//
+// Fp: 12 x u32 little-endian limbs of a*2^384 mod p, always fully reduced -- byte-identical to dusk-bls12_381's `Fp([u64; 6])`.
+// Points cross the C ABI as pg_g1_affine { x, y } (96 bytes, Montgomery limbs); the point at infinity is the all-zero pair
+// (not on the curve since b = 4 != 0).  Sums are kept in XYZZ coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; ZZ = 0 marks
+// infinity): a mixed addition costs 8 multiplications + 2 squarings, no inversion until the final conversion.
+// Every formula handles its exceptional cases (equal points, opposite points, infinity) -- bucket sums of real polynomials
+// rarely hit them, the parity tests do on purpose.
+#pragma once
+#include "fr.cuh"
+
+namespace pg {
+
+struct Fp { uint32_t v[12]; };
+struct G1Affine { Fp x, y; };
+struct G1X { Fp x, y, zz, zzz; };
+
+constexpr uint32_t FP_INV32 = 0xfffcfffdu;     // -p^-1 mod 2^32
+PG_HD uint32_t fp_p(int i) {
+    const uint32_t P[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                            0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+    return P[i];
+}
+PG_HD Fp fp_zero() { Fp r; for (int i = 0; i < 12; i++) r.v[i] = 0; return r; }
+PG_HD Fp fp_one() {   // 2^384 mod p
+    Fp r = {{0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u, 0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u}};
+    return r;
+}
+PG_HD bool fp_is_zero(const Fp& a) { uint32_t o = 0; for (int i = 0; i < 12; i++) o |= a.v[i]; return o == 0; }
+PG_HD bool fp_eq(const Fp& a, const Fp& b) { uint32_t o = 0; for (int i = 0; i < 12; i++) o |= a.v[i] ^ b.v[i]; return o == 0; }
+
+// r in [0, 2p) -> r mod p
+PG_HD Fp fp_reduce_once(const Fp& t) {
+    Fp d; uint64_t bw = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { const uint64_t s = (uint64_t)t.v[i] - fp_p(i) - bw; d.v[i] = (uint32_t)s; bw = (s >> 32) & 1u; }
+    return bw ? t : d;
+}
+PG_HD Fp fp_add(const Fp& a, const Fp& b) {
+    Fp s; uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { const uint64_t t = (uint64_t)a.v[i] + b.v[i] + c; s.v[i] = (uint32_t)t; c = t >> 32; }
+    return fp_reduce_once(s);                       // p < 2^381: no carry out of limb 11
+}
+PG_HD Fp fp_sub(const Fp& a, const Fp& b) {
+    Fp d; uint64_t bw = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { const uint64_t s = (uint64_t)a.v[i] - b.v[i] - bw; d.v[i] = (uint32_t)s; bw = (s >> 32) & 1u; }
+    const uint32_t mask = 0u - (uint32_t)bw;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { const uint64_t t = (uint64_t)d.v[i] + (fp_p(i) & mask) + c; d.v[i] = (uint32_t)t; c = t >> 32; }
+    return d;
+}
+PG_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
+PG_HD Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
+
+// CIOS Montgomery multiplication, 12 limb steps (each: 12 products a*b_i, m = t0 * (-p^-1), 12 products m*p)
+PG_HD Fp fp_mul(const Fp& a, const Fp& b) {
+    uint32_t t[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 12; j++) { const uint64_t s = (uint64_t)a.v[j] * b.v[i] + t[j] + c; t[j] = (uint32_t)s; c = s >> 32; }
+        uint64_t s = (uint64_t)t[12] + c; t[12] = (uint32_t)s; t[13] = (uint32_t)(s >> 32);
+        const uint32_t m = t[0] * FP_INV32;
+        c = ((uint64_t)m * fp_p(0) + t[0]) >> 32;
+#pragma unroll
+        for (int j = 1; j < 12; j++) { const uint64_t u = (uint64_t)m * fp_p(j) + t[j] + c; t[j - 1] = (uint32_t)u; c = u >> 32; }
+        s = (uint64_t)t[12] + c; t[11] = (uint32_t)s; t[12] = t[13] + (uint32_t)(s >> 32);
+    }
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = t[i];
+    return fp_reduce_once(r);                       // a, b < p => t < 2p < 2^382: t[12] == 0
+}
+PG_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
+PG_HD Fp fp_to_mont(const Fp& raw) {
+    const Fp r2 = {{0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u}};
+    return fp_mul(raw, r2);
+}
+// a^(p-2); a != 0
+PG_HD Fp fp_inv(const Fp& a) {
+    Fp res = fp_one();
+#pragma unroll 1
+    for (int i = 11; i >= 0; i--) {
+        const uint32_t e = i == 0 ? fp_p(0) - 2u : fp_p(i);
+#pragma unroll 1
+        for (int b = 31; b >= 0; b--) {
+            res = fp_sqr(res);
+            if ((e >> b) & 1u) res = fp_mul(res, a);
+        }
+    }
+    return res;
+}
+
+// ---- G1 ----------------------------------------------------------------------------------------------------------------
+PG_HD G1Affine g1_generator() {
+    G1Affine g = {{{0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u, 0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u}},
+                  {{0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u, 0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu}}};
+    return g;
+}
+PG_HD bool g1_affine_is_inf(const G1Affine& a) { return fp_is_zero(a.x) && fp_is_zero(a.y); }
+PG_HD G1Affine g1_affine_inf() { G1Affine a; a.x = fp_zero(); a.y = fp_zero(); return a; }
+PG_HD G1X g1x_inf() { G1X r; r.x = fp_one(); r.y = fp_one(); r.zz = fp_zero(); r.zzz = fp_zero(); return r; }
+PG_HD bool g1x_is_inf(const G1X& a) { return fp_is_zero(a.zz); }
+PG_HD G1X g1x_from_affine(const G1Affine& a) {
+    if (g1_affine_is_inf(a)) return g1x_inf();
+    G1X r; r.x = a.x; r.y = a.y; r.zz = fp_one(); r.zzz = fp_one(); return r;
+}
+// 2 * (affine point)
+PG_HD G1X g1x_dbl_affine(const G1Affine& a) {
+    if (g1_affine_is_inf(a) || fp_is_zero(a.y)) return g1x_inf();
+    const Fp u = fp_dbl(a.y), v = fp_sqr(u), w = fp_mul(u, v), s = fp_mul(a.x, v);
+    const Fp x2 = fp_sqr(a.x), m = fp_add(fp_dbl(x2), x2);
+    G1X r;
+    r.x = fp_sub(fp_sqr(m), fp_dbl(s));
+    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, a.y));
+    r.zz = v; r.zzz = w;
+    return r;
+}
+PG_HD G1X g1x_dbl(const G1X& p) {
+    if (g1x_is_inf(p) || fp_is_zero(p.y)) return g1x_inf();
+    const Fp u = fp_dbl(p.y), v = fp_sqr(u), w = fp_mul(u, v), s = fp_mul(p.x, v);
+    const Fp x2 = fp_sqr(p.x), m = fp_add(fp_dbl(x2), x2);
+    G1X r;
+    r.x = fp_sub(fp_sqr(m), fp_dbl(s));
+    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
+    r.zz = fp_mul(v, p.zz); r.zzz = fp_mul(w, p.zzz);
+    return r;
+}
+// p + q, q affine
+PG_HD G1X g1x_madd(const G1X& p, const G1Affine& q) {
+    if (g1_affine_is_inf(q)) return p;
+    if (g1x_is_inf(p)) return g1x_from_affine(q);
+    const Fp u2 = fp_mul(q.x, p.zz), s2 = fp_mul(q.y, p.zzz);
+    const Fp pp_ = fp_sub(u2, p.x), r_ = fp_sub(s2, p.y);
+    if (fp_is_zero(pp_)) return fp_is_zero(r_) ? g1x_dbl_affine(q) : g1x_inf();
+    const Fp pp = fp_sqr(pp_), ppp = fp_mul(pp_, pp), qq = fp_mul(p.x, pp);
+    G1X r;
+    r.x = fp_sub(fp_sub(fp_sqr(r_), ppp), fp_dbl(qq));
+    r.y = fp_sub(fp_mul(r_, fp_sub(qq, r.x)), fp_mul(p.y, ppp));
+    r.zz = fp_mul(p.zz, pp); r.zzz = fp_mul(p.zzz, ppp);
+    return r;
+}
+PG_HD G1X g1x_add(const G1X& p, const G1X& q) {
+    if (g1x_is_inf(q)) return p;
+    if (g1x_is_inf(p)) return q;
+    const Fp u1 = fp_mul(p.x, q.zz), u2 = fp_mul(q.x, p.zz), s1 = fp_mul(p.y, q.zzz), s2 = fp_mul(q.y, p.zzz);
+    const Fp pp_ = fp_sub(u2, u1), r_ = fp_sub(s2, s1);
+    if (fp_is_zero(pp_)) return fp_is_zero(r_) ? g1x_dbl(p) : g1x_inf();
+    const Fp pp = fp_sqr(pp_), ppp = fp_mul(pp_, pp), qq = fp_mul(u1, pp);
+    G1X r;
+    r.x = fp_sub(fp_sub(fp_sqr(r_), ppp), fp_dbl(qq));
+    r.y = fp_sub(fp_mul(r_, fp_sub(qq, r.x)), fp_mul(s1, ppp));
+    r.zz = fp_mul(fp_mul(p.zz, q.zz), pp); r.zzz = fp_mul(fp_mul(p.zzz, q.zzz), ppp);
+    return r;
+}
+PG_HD G1Affine g1x_to_affine(const G1X& p) {
+    if (g1x_is_inf(p)) return g1_affine_inf();
+    const Fp i5 = fp_inv(fp_mul(p.zz, p.zzz));            // Z^-5
+    G1Affine a;
+    a.x = fp_mul(p.x, fp_mul(i5, p.zzz));                 // X / ZZ
+    a.y = fp_mul(p.y, fp_mul(i5, p.zz));                  // Y / ZZZ
+    return a;
+}
+// k * p for a canonical (non-Montgomery) 256-bit k given as 8 limbs, most significant bit first
+PG_HD G1X g1x_mul_limbs(const G1X& p, const uint32_t* k, int n_limbs) {
+    G1X acc = g1x_inf();
+    bool started = false;
+#pragma unroll 1
+    for (int i = n_limbs - 1; i >= 0; i--) {
+#pragma unroll 1
+        for (int b = 31; b >= 0; b--) {
+            if (started) acc = g1x_dbl(acc);
+            if ((k[i] >> b) & 1u) { acc = g1x_add(acc, p); started = true; }
+        }
+    }
+    return acc;
+}
+
+// AoS access to caller memory / scratch (96-byte affine points, 192-byte XYZZ points), 16-byte units
+PG_HD Fp fp_load(const uint4* p) {
+    Fp r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const uint4 q = p[k]; r.v[4 * k] = q.x; r.v[4 * k + 1] = q.y; r.v[4 * k + 2] = q.z; r.v[4 * k + 3] = q.w; }
+    return r;
+}
+PG_HD void fp_store(uint4* p, const Fp& a) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = make_uint4(a.v[4 * k], a.v[4 * k + 1], a.v[4 * k + 2], a.v[4 * k + 3]);
+}
+PG_HD G1Affine g1_affine_load(const uint4* base, uint64_t i) { G1Affine a; a.x = fp_load(base + 6 * i); a.y = fp_load(base + 6 * i + 3); return a; }
+PG_HD void g1_affine_store(uint4* base, uint64_t i, const G1Affine& a) { fp_store(base + 6 * i, a.x); fp_store(base + 6 * i + 3, a.y); }
+PG_HD G1X g1x_load(const uint4* base, uint64_t i) {
+    G1X r; r.x = fp_load(base + 12 * i); r.y = fp_load(base + 12 * i + 3); r.zz = fp_load(base + 12 * i + 6); r.zzz = fp_load(base + 12 * i + 9); return r;
+}
+PG_HD void g1x_store(uint4* base, uint64_t i, const G1X& a) {
+    fp_store(base + 12 * i, a.x); fp_store(base + 12 * i + 3, a.y); fp_store(base + 12 * i + 6, a.zz); fp_store(base + 12 * i + 9, a.zzz);
+}
+
+}  // namespace pg

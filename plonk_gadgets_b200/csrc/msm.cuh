@@ -1,0 +1,137 @@
+// msm.cuh -- multi-scalar multiplication in G1: sum_i scalar_i * point_i  (KZG commitment of a coefficient vector against
+// the SRS powers; SURVEY.md section 8f item 2, second half; [DEP] dusk-bls12_381 `msm_variable_base`, dusk-plonk 0.8
+// `CommitKey::commit`, reached from /root/reference/tests/range_gadgets_tests.rs:90-91 through prover.prove).
+//
+// The reference's CPU routine is a serial Pippenger; the sum it returns is a group element, independent of the schedule.  Here:
+//   1. k_simple<MsmDigitsBody>    scalars out of Montgomery form, cut into W = ceil(255/c) unsigned c-bit digits;
+//                                 one (key = window*2^c + digit, value = point index) pair per scalar and window;
+//   2. sort_pairs                 radix sort of the W*n pairs by key (CUB on the device): every bucket becomes a contiguous run;
+//   3. k_simple<MsmBucketBody>    one thread per (window, digit) bucket: binary search of its run, mixed additions of its
+//                                 points into an XYZZ accumulator -- W*n additions in total, W*2^c independent threads;
+//   4. k_simple<MsmChunkBody>     per window, chunks of L consecutive buckets: running-sum trick gives sum (d - lo) * B_d,
+//                                 plus lo * (sum B_d) by double-and-add on the small factor lo;
+//   5. k_simple<MsmSumBody>       tree of 16-way sums of the chunk results down to one point per window;
+//   6. k_simple<MsmFinalBody>     Horner over the windows (c doublings each) and the conversion to affine.
+// c is chosen from n (MsmPlan).  All group formulas are complete (g1.cuh).
+#pragma once
+#include "g1.cuh"
+#include "layout.h"
+
+namespace pg {
+
+struct MsmPlan { uint32_t c, n_windows, chunk; };          // chunk = L, a power of two <= 2^c
+inline MsmPlan msm_plan(uint64_t n) {
+    uint32_t log_n = 0;
+    while ((1ull << (log_n + 1)) <= n) log_n++;
+    MsmPlan p;
+    p.c = log_n <= 6 ? 3 : (log_n - 4 > 16 ? 16 : log_n - 4);
+    p.n_windows = (255 + p.c - 1) / p.c;
+    p.chunk = p.c >= 8 ? 256u : (1u << p.c);
+    return p;
+}
+
+// digit w of the canonical scalar
+PG_HD uint32_t msm_digit(const Fr& canon, uint32_t w, uint32_t c) {
+    const uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31u;
+    uint64_t v = canon.v[limb];
+    if (limb + 1 < 8) v |= (uint64_t)canon.v[limb + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+struct MsmDigitsBody {
+    struct Args { const uint4* scalars; uint32_t* keys; uint32_t* vals; uint64_t n; uint32_t c, n_windows; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const Fr s = fr_from_mont(aos_load(a.scalars, i));
+        for (uint32_t w = 0; w < a.n_windows; w++) {
+            a.keys[(uint64_t)w * a.n + i] = (w << a.c) | msm_digit(s, w, a.c);
+            a.vals[(uint64_t)w * a.n + i] = (uint32_t)i;
+        }
+    }
+};
+
+// first position in sorted keys[0..count) whose key is >= key
+PG_HD uint64_t msm_lower_bound(const uint32_t* keys, uint64_t count, uint32_t key) {
+    uint64_t lo = 0, hi = count;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+struct MsmBucketBody {
+    struct Args { const uint32_t* keys; const uint32_t* vals; const uint4* points; uint4* buckets; uint64_t count; uint64_t n; /* buckets */ uint32_t c; };
+    PG_HD static void run(const Args& a, uint64_t b) {
+        G1X acc = g1x_inf();
+        if (b & ((1ull << a.c) - 1ull)) {                      // digit 0 contributes nothing
+            const uint64_t lo = msm_lower_bound(a.keys, a.count, (uint32_t)b);
+            for (uint64_t j = lo; j < a.count && a.keys[j] == (uint32_t)b; j++) acc = g1x_madd(acc, g1_affine_load(a.points, a.vals[j]));
+        }
+        g1x_store(a.buckets, b, acc);
+    }
+};
+
+// chunk t of the flattened (window, digit) space: sum_{d in chunk} d * B_d for its window
+struct MsmChunkBody {
+    struct Args { const uint4* buckets; uint4* out; uint64_t n; /* chunks */ uint32_t c, chunk; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        const uint64_t first = t * a.chunk;                    // flattened index of the chunk's first bucket
+        const uint32_t lo = (uint32_t)(first & ((1ull << a.c) - 1ull));
+        G1X running = g1x_inf(), acc = g1x_inf();
+        for (uint32_t k = a.chunk; k-- > 0;) {                 // acc = sum (d - lo) * B_d, running = sum B_d
+            acc = g1x_add(acc, running);
+            running = g1x_add(running, g1x_load(a.buckets, first + k));
+        }
+        if (lo) { const uint32_t kk[1] = {lo}; acc = g1x_add(acc, g1x_mul_limbs(running, kk, 1)); }
+        g1x_store(a.out, t, acc);
+    }
+};
+
+// out[t] = sum of in[t*group .. t*group + group) (clipped to per-window segments of seg_in entries -> seg_out entries)
+struct MsmSumBody {
+    struct Args { const uint4* in; uint4* out; uint64_t n; /* outputs */ uint32_t seg_in, seg_out, group; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        const uint64_t w = t / a.seg_out, j = t % a.seg_out;
+        G1X acc = g1x_inf();
+        for (uint32_t k = 0; k < a.group; k++) {
+            const uint64_t idx = j * a.group + k;
+            if (idx < a.seg_in) acc = g1x_add(acc, g1x_load(a.in, w * a.seg_in + idx));
+        }
+        g1x_store(a.out, t, acc);
+    }
+};
+
+// result = sum_w 2^(c*w) * window[w], as an affine point
+struct MsmFinalBody {
+    struct Args { const uint4* windows; uint4* out; uint64_t n; /* 1 */ uint32_t c, n_windows; };
+    PG_HD static void run(const Args& a, uint64_t) {
+        G1X total = g1x_inf();
+        for (uint32_t w = a.n_windows; w-- > 0;) {
+            for (uint32_t k = 0; k < a.c; k++) total = g1x_dbl(total);
+            total = g1x_add(total, g1x_load(a.windows, w));
+        }
+        g1_affine_store(a.out, 0, g1x_to_affine(total));
+    }
+};
+
+// out[i] = scalar_i * base  (PublicParameters::setup: powers_of_g = slow_multiscalar_mul_single_base(powers_of_beta, g))
+struct G1FixedBaseMulBody {
+    struct Args { const uint4* scalars; uint4* out; uint64_t n; G1Affine base; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const Fr k = fr_from_mont(aos_load(a.scalars, i));
+        g1_affine_store(a.out, i, g1x_to_affine(g1x_mul_limbs(g1x_from_affine(a.base), k.v, 8)));
+    }
+};
+
+// group-law self-test entry (pg_g1_op): 0 = a + b (affine in, affine out), 1 = on-curve flag of a
+struct G1OpBody {
+    struct Args { const uint4* a; const uint4* b; uint4* out; uint64_t n; int op; };
+    PG_HD static void run(const Args& x, uint64_t i) {
+        const G1Affine p = g1_affine_load(x.a, i);
+        if (x.op == 0) { g1_affine_store(x.out, i, g1x_to_affine(g1x_madd(g1x_from_affine(p), g1_affine_load(x.b, i)))); return; }
+        G1Affine r = g1_affine_inf();
+        const Fp four = fp_dbl(fp_dbl(fp_one()));
+        const bool ok = g1_affine_is_inf(p) || fp_eq(fp_sqr(p.y), fp_add(fp_mul(fp_sqr(p.x), p.x), four));
+        r.x.v[0] = ok ? 1u : 0u;
+        g1_affine_store(x.out, i, r);
+    }
+};
+
+}  // namespace pg

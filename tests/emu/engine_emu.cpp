@@ -81,6 +81,13 @@ public:
             }
         return true;
     }
+    bool sort_pairs(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t n, uint32_t) {
+        std::vector<uint64_t> idx(n);
+        for (uint64_t i = 0; i < n; i++) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return keys[a] < keys[b]; });
+        for (uint64_t i = 0; i < n; i++) { keys_out[i] = keys[idx[i]]; vals_out[i] = vals[idx[i]]; }
+        return true;
+    }
     bool run_ntt_pass(const NttPassArgs& a, uint64_t n_blocks) { ntt_pass_host(a, n_blocks); return true; }
     bool run_check_rows(const CheckRowsBody::Args& a) {
         for (uint64_t i = 0; i < a.n; i++)

@@ -1,0 +1,91 @@
+"""CPU tests of the commitment path (pg_msm, pg_srs_powers, pg_commit_wire_polynomials, pg_g1_op) through tests/emu: the
+Fp / G1 formulas (g1.cuh) and the bucket-method bodies (msm.cuh) run on the loop backend and are compared with the oracle.
+The CUDA launches (and the CUB sort) are checked on the B200 by tests/test_gpu_parity.py."""
+import random
+
+import numpy as np
+import pytest
+
+import plonk_gadgets_b200 as pg
+from tests.engine_runner import run_engine
+from tests.programs import Q, run_oracle, synth_wide
+from tests.test_emu_engine import emu  # noqa: F401  (fixture)
+
+
+def to_engine(points13: np.ndarray) -> np.ndarray:
+    """oracle points (n, 13) -> engine points (n, 12): infinity becomes the all-zero pair."""
+    p = np.ascontiguousarray(points13, dtype=np.uint64).reshape(-1, 13)
+    out = p[:, :12].copy()
+    out[(p[:, 12] & np.uint64(0xffffffff)) != 0] = 0
+    return out
+
+
+def to_oracle(points12: np.ndarray) -> np.ndarray:
+    p = np.ascontiguousarray(points12, dtype=np.uint64).reshape(-1, 12)
+    out = np.zeros((p.shape[0], 13), dtype=np.uint64)
+    out[:, :12] = p
+    out[:, 12] = (~p.any(axis=1)).astype(np.uint64)
+    return out
+
+
+def test_emu_group_law(emu, oracle):
+    c = pg.StandardComposer(_cdll=emu)
+    g = oracle.g1_generator()
+    rnd = random.Random(8)
+    ks = [1, 2, 3, Q - 1, Q - 2, rnd.randrange(Q), rnd.randrange(Q)]
+    pts = oracle.g1_mul(np.repeat(g, len(ks), axis=0), oracle.from_ints(ks))
+    inf = np.zeros((1, 13), dtype=np.uint64); inf[0, 12] = 1
+    lhs = np.concatenate([pts[0:1], pts[1:2], pts[1:2], inf, pts[5:6], inf, pts[2:3]])
+    rhs = np.concatenate([pts[1:2], pts[1:2], pts[4:5], pts[6:7], inf, inf, pts[3:4]])   # generic, doubling, inverse (2G + (q-2)G), inf+P, P+inf, inf+inf, 3G+(q-1)G
+    got = c.g1_op(0, to_engine(lhs), to_engine(rhs))
+    assert np.array_equal(to_oracle(got), oracle.g1_add(lhs, rhs))
+    flags = c.g1_op(1, to_engine(np.concatenate([pts, inf])))
+    assert flags[:, 0].tolist() == [1] * (len(ks) + 1)
+    bad = to_engine(pts[:1]); bad[0, 0] ^= np.uint64(1)
+    assert c.g1_op(1, bad)[0, 0] == 0
+    # fixed-base multiples against the oracle, including 0 and q-1
+    sc = oracle.from_ints([0, 1, 5, Q - 1, rnd.randrange(Q)])
+    assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, 5, axis=0), sc))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 33, 100, 300])
+def test_emu_msm_matches_oracle(emu, oracle, n):
+    c = pg.StandardComposer(_cdll=emu)
+    rnd = random.Random(n)
+    srs = oracle.srs_powers(oracle.from_ints([rnd.randrange(Q)]), n)
+    sc = synth_wide(40 + n, n)
+    sc[0] = 1
+    if n > 4:
+        sc[2] = 0; sc[3] = 1; sc[4] = Q - 1
+    if n > 40:
+        srs[7] = srs[6]                                         # a repeated point: equal-point additions inside a bucket
+        sc[7] = sc[6]
+        srs[9, :12] = 0; srs[9, 12] = 1                         # a point at infinity
+    got = c.msm(to_engine(srs), oracle.from_ints(sc))
+    assert np.array_equal(to_oracle(got.reshape(1, 12)), oracle.g1_msm(srs, oracle.from_ints(sc)))
+
+
+def test_emu_msm_edge_cases(emu, oracle):
+    c = pg.StandardComposer(_cdll=emu)
+    srs = oracle.srs_powers(oracle.from_ints([77]), 16)
+    assert not c.msm(to_engine(srs), oracle.from_ints([0] * 16)).any()                  # all-zero scalars: infinity
+    assert not c.msm(np.zeros((0, 12), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64)).any()   # empty sum
+    same = np.repeat(srs[3:4], 16, axis=0)                                              # 16 copies of one point, scalar 1 each: 16 * P
+    got = c.msm(to_engine(same), oracle.from_ints([1] * 16))
+    assert np.array_equal(to_oracle(got.reshape(1, 12)), oracle.g1_mul(srs[3:4], oracle.from_ints([16])))
+    pair = np.concatenate([srs[3:4], srs[3:4]])                                         # P - P
+    assert not c.msm(to_engine(pair), oracle.from_ints([5, Q - 5])).any()
+
+
+def test_emu_srs_and_wire_commitments(emu, oracle, golden):
+    spec = golden["kat_range_check_0_ok"]
+    _s, oc = run_oracle(spec["program"], return_composer=True)
+    _snap, c = run_engine(spec["program"], lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
+    k = c.domain_log_size()
+    beta = oracle.from_ints([0x1234567890abcdef1234567890abcdef])
+    srs = c.srs_powers(beta[0], 1 << k)
+    assert np.array_equal(to_oracle(srs), oracle.srs_powers(beta, 1 << k))
+    got = c.commit_wire_polynomials(srs)
+    polys = oc.wire_polynomials()
+    for w in range(4):
+        assert np.array_equal(to_oracle(got[w:w + 1]), oracle.g1_msm(to_oracle(srs), polys[w])), w
