@@ -381,9 +381,9 @@ def g1_add(a, b):
     if a[0] == b[0]:
         if (a[1] + b[1]) % P_FIELD == 0:
             return None
-        lam = 3 * a[0] * a[0] * pow(2 * a[1], P_FIELD - 2, P_FIELD) % P_FIELD
+        lam = 3 * a[0] * a[0] * pow(2 * a[1], -1, P_FIELD) % P_FIELD
     else:
-        lam = (b[1] - a[1]) * pow(b[0] - a[0], P_FIELD - 2, P_FIELD) % P_FIELD
+        lam = (b[1] - a[1]) * pow(b[0] - a[0], -1, P_FIELD) % P_FIELD
     x3 = (lam * lam - a[0] - b[0]) % P_FIELD
     return x3, (lam * (a[0] - x3) - a[1]) % P_FIELD
 

@@ -463,3 +463,90 @@ def test_wire_polynomials_at_scale(oracle, torch_cuda):
     for col in range(4):
         c.fft(polys[col]); c.sync()
         assert torch.equal(polys[col, :rows], w_val[col]) and not bool(polys[col, rows:].any())
+
+
+# ---------------------------------------------------------------------------------------------------- commitments (8f.2, second half)
+def test_g1_group_law_gpu(oracle):
+    from tests.test_emu_msm import to_engine, to_oracle
+    c = gpu_composer()
+    g = oracle.g1_generator()
+    rnd = random.Random(8)
+    ks = [1, 2, 3, Q - 1, Q - 2, rnd.randrange(Q), rnd.randrange(Q)]
+    pts = oracle.g1_mul(np.repeat(g, len(ks), axis=0), oracle.from_ints(ks))
+    inf = np.zeros((1, 13), dtype=np.uint64); inf[0, 12] = 1
+    lhs = np.concatenate([pts[0:1], pts[1:2], pts[1:2], inf, pts[5:6], inf, pts[2:3]])
+    rhs = np.concatenate([pts[1:2], pts[1:2], pts[4:5], pts[6:7], inf, inf, pts[3:4]])
+    assert np.array_equal(to_oracle(c.g1_op(0, to_engine(lhs), to_engine(rhs))), oracle.g1_add(lhs, rhs))
+    assert c.g1_op(1, to_engine(np.concatenate([pts, inf])))[:, 0].tolist() == [1] * (len(ks) + 1)
+    sc = oracle.from_ints([0, 1, 5, Q - 1] + [rnd.randrange(Q) for _ in range(60)])
+    assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, 64, axis=0), sc))
+    beta = oracle.from_ints([rnd.randrange(Q)])
+    assert np.array_equal(to_oracle(c.srs_powers(beta[0], 48)), oracle.srs_powers(beta, 48))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 33, 100, 1000, 6000])
+def test_msm_vs_oracle(oracle, n):
+    """pg_msm (digits, CUB sort, bucket sums, chunked running sums, Horner) against the restated serial Pippenger."""
+    from tests.test_emu_msm import to_engine, to_oracle
+    c = gpu_composer()
+    rnd = random.Random(n)
+    srs = c.srs_powers(oracle.from_ints([rnd.randrange(Q)])[0], n)            # checked against the oracle in test_g1_group_law_gpu
+    sc = synth_wide(40 + n, n)
+    sc[0] = 1
+    if n > 4:
+        sc[2] = 0; sc[3] = 1; sc[4] = Q - 1
+    if n > 40:
+        srs[7] = srs[6]; sc[7] = sc[6]                                        # equal points in one bucket
+        srs[9] = 0                                                            # a point at infinity
+    got = c.msm(srs, oracle.from_ints(sc))
+    assert np.array_equal(to_oracle(got.reshape(1, 12)), oracle.g1_msm(to_oracle(srs), oracle.from_ints(sc)))
+
+
+def test_msm_edge_cases_gpu(oracle):
+    from tests.test_emu_msm import to_engine, to_oracle
+    c = gpu_composer()
+    srs = c.srs_powers(oracle.from_ints([77])[0], 16)
+    assert not c.msm(srs, oracle.from_ints([0] * 16)).any()
+    assert not c.msm(np.zeros((0, 12), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64)).any()
+    same = np.repeat(srs[3:4], 16, axis=0)
+    assert np.array_equal(to_oracle(c.msm(same, oracle.from_ints([1] * 16)).reshape(1, 12)), oracle.g1_mul(to_oracle(srs[3:4]), oracle.from_ints([16])))
+    assert not c.msm(np.concatenate([srs[3:4], srs[3:4]]), oracle.from_ints([5, Q - 5])).any()
+
+
+def test_commitment_is_polynomial_at_beta(oracle, torch_cuda):
+    """Size-independent check at 2^18 terms, device-resident: against powers_of_g[i] = beta^i * G the commitment of a coefficient
+    vector is poly(beta) * G -- the right-hand side needs one Horner evaluation on big ints and one fixed-base multiplication."""
+    from tests.test_emu_msm import to_oracle
+    torch = torch_cuda
+    n = 1 << 18
+    c = gpu_composer()
+    beta = 0x2b6cedcb87925c23c999e990f3f29c6d0748d9d99f59ff1105d314967254398f % Q
+    srs = torch.empty((n, 12), dtype=torch.int64, device="cuda")
+    c.srs_powers(oracle.from_ints([beta])[0], n, out=srs)
+    coeffs = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 91, 0, 0, coeffs); c.sync()
+    got = c.msm(srs, coeffs)
+    vals = oracle.to_ints(coeffs.cpu().numpy().view(np.uint64))
+    acc = 0
+    for v in reversed(vals):
+        acc = (acc * beta + v) % Q
+    want = c.g1_fixed_base_mul(oracle.from_ints([acc]))
+    assert np.array_equal(got, want[0])
+    assert np.array_equal(to_oracle(want), oracle.g1_mul(oracle.g1_generator(), oracle.from_ints([acc])))
+
+
+def test_commit_wire_polynomials_gpu(oracle, golden):
+    """The four wire commitments of a 40-instance range_check batch (10 843 rows, domain 2^14) and of a golden program equal
+    the oracle's msm_variable_base over the oracle's ifft of the sequential composer's wire columns."""
+    from tests.test_emu_msm import to_oracle
+    wit = synth_wide(62, 40)
+    prog = [dict(op="add_input", values=[hx(w % 2 ** 64 if i % 2 == 0 else w) for i, w in enumerate(wit)]),
+            dict(op="range_check", min=hx(0), max=hx(2 ** 64), witness=0)]
+    for program in (golden["kat_max_bound_0_ok"]["program"], prog):
+        _s, oc = run_oracle(program, return_composer=True)
+        _snap, c = run_engine(program, gpu_composer, oracle, return_composer=True)
+        k = c.domain_log_size()
+        srs = c.srs_powers(oracle.from_ints([0x51ac582950405194])[0], 1 << k)
+        got = c.commit_wire_polynomials(srs)
+        polys = oc.wire_polynomials()
+        for w in range(4):
+            assert np.array_equal(to_oracle(got[w:w + 1]), oracle.g1_msm(to_oracle(srs), polys[w])), w
