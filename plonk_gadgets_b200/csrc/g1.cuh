@@ -56,8 +56,9 @@ PG_HD Fp fp_sub(const Fp& a, const Fp& b) {
 PG_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
 PG_HD Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
 
-// CIOS Montgomery multiplication, 12 limb steps (each: 12 products a*b_i, m = t0 * (-p^-1), 12 products m*p)
-PG_HD Fp fp_mul(const Fp& a, const Fp& b) {
+// CIOS Montgomery multiplication, 12 limb steps (each: 12 products a*b_i, m = t0 * (-p^-1), 12 products m*p): the host version
+// and the definition the device version below is tested against (through the oracle) on the GPU
+PG_HD Fp fp_mul_generic(const Fp& a, const Fp& b) {
     uint32_t t[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) t[i] = 0;
@@ -78,6 +79,131 @@ PG_HD Fp fp_mul(const Fp& a, const Fp& b) {
     for (int i = 0; i < 12; i++) r.v[i] = t[i];
     return fp_reduce_once(r);                       // a, b < p => t < 2p < 2^382: t[12] == 0
 }
+
+#if defined(__CUDACC__)
+__device__ __constant__ uint32_t c_p[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                            0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+#endif
+#if defined(__CUDA_ARCH__)
+// ---- device multiplier: the even/odd carry-chain scheme of fr.cuh (fr_mul_eo) for 12 limbs ---------------------------------
+// Partial products are split into an even and an odd accumulator so that every row of 6 products is ONE
+// mad.lo.cc / madc.hi.cc chain (-> IMAD.WIDE.U32.X); each primitive is one asm statement holding one complete chain.
+// Bounds: the running value stays below p*(2^33 + 2) < 2^415, so the odd array (limbs 1..12) never carries out and the carry
+// out of the even array (limbs 0..11) is absorbed by limb 12 = odd[11].  The modulus limbs come from constant memory as
+// register operands (immediates would split the wide products, see fr.cuh).
+PG_D void mul_row6(uint32_t* acc, const uint32_t* x, int off, uint32_t y) {
+    asm("mul.lo.u32 %0, %12, %18;\n\tmul.hi.u32 %1, %12, %18;\n\t"
+        "mul.lo.u32 %2, %13, %18;\n\tmul.hi.u32 %3, %13, %18;\n\t"
+        "mul.lo.u32 %4, %14, %18;\n\tmul.hi.u32 %5, %14, %18;\n\t"
+        "mul.lo.u32 %6, %15, %18;\n\tmul.hi.u32 %7, %15, %18;\n\t"
+        "mul.lo.u32 %8, %16, %18;\n\tmul.hi.u32 %9, %16, %18;\n\t"
+        "mul.lo.u32 %10, %17, %18;\n\tmul.hi.u32 %11, %17, %18;"
+        : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]), "=&r"(acc[6]), "=&r"(acc[7]), "=&r"(acc[8]), "=&r"(acc[9]), "=&r"(acc[10]), "=&r"(acc[11])
+        : "r"(x[off + 0]), "r"(x[off + 2]), "r"(x[off + 4]), "r"(x[off + 6]), "r"(x[off + 8]), "r"(x[off + 10]), "r"(y));
+}
+
+PG_D void mad_row6(uint32_t* acc, uint32_t& top, const uint32_t* x, int off, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %13, %19, %0;\n\tmadc.hi.cc.u32 %1, %13, %19, %1;\n\t"
+        "madc.lo.cc.u32 %2, %14, %19, %2;\n\tmadc.hi.cc.u32 %3, %14, %19, %3;\n\t"
+        "madc.lo.cc.u32 %4, %15, %19, %4;\n\tmadc.hi.cc.u32 %5, %15, %19, %5;\n\t"
+        "madc.lo.cc.u32 %6, %16, %19, %6;\n\tmadc.hi.cc.u32 %7, %16, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %17, %19, %8;\n\tmadc.hi.cc.u32 %9, %17, %19, %9;\n\t"
+        "madc.lo.cc.u32 %10, %18, %19, %10;\n\tmadc.hi.cc.u32 %11, %18, %19, %11;\n\t"
+        "addc.u32 %12, %12, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(top)
+        : "r"(x[off + 0]), "r"(x[off + 2]), "r"(x[off + 4]), "r"(x[off + 6]), "r"(x[off + 8]), "r"(x[off + 10]), "r"(y));
+}
+
+PG_D void mad_row6_nc(uint32_t* acc, const uint32_t* x, int off, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %12, %18, %0;\n\tmadc.hi.cc.u32 %1, %12, %18, %1;\n\t"
+        "madc.lo.cc.u32 %2, %13, %18, %2;\n\tmadc.hi.cc.u32 %3, %13, %18, %3;\n\t"
+        "madc.lo.cc.u32 %4, %14, %18, %4;\n\tmadc.hi.cc.u32 %5, %14, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %15, %18, %6;\n\tmadc.hi.cc.u32 %7, %15, %18, %7;\n\t"
+        "madc.lo.cc.u32 %8, %16, %18, %8;\n\tmadc.hi.cc.u32 %9, %16, %18, %9;\n\t"
+        "madc.lo.cc.u32 %10, %17, %18, %10;\n\tmadc.hi.u32 %11, %17, %18, %11;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11])
+        : "r"(x[off + 0]), "r"(x[off + 2]), "r"(x[off + 4]), "r"(x[off + 6]), "r"(x[off + 8]), "r"(x[off + 10]), "r"(y));
+}
+
+PG_D void mad_row6_shift(uint32_t* o, uint32_t& e0, const uint32_t* x, int off, uint32_t y) {
+    asm("add.cc.u32 %12, %12, %1;\n\t"
+        "madc.lo.cc.u32 %0, %13, %19, %2;\n\tmadc.hi.cc.u32 %1, %13, %19, %3;\n\t"
+        "madc.lo.cc.u32 %2, %14, %19, %4;\n\tmadc.hi.cc.u32 %3, %14, %19, %5;\n\t"
+        "madc.lo.cc.u32 %4, %15, %19, %6;\n\tmadc.hi.cc.u32 %5, %15, %19, %7;\n\t"
+        "madc.lo.cc.u32 %6, %16, %19, %8;\n\tmadc.hi.cc.u32 %7, %16, %19, %9;\n\t"
+        "madc.lo.cc.u32 %8, %17, %19, %10;\n\tmadc.hi.cc.u32 %9, %17, %19, %11;\n\t"
+        "madc.lo.cc.u32 %10, %18, %19, 0;\n\tmadc.hi.u32 %11, %18, %19, 0;"
+        : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(e0)
+        : "r"(x[off + 0]), "r"(x[off + 2]), "r"(x[off + 4]), "r"(x[off + 6]), "r"(x[off + 8]), "r"(x[off + 10]), "r"(y));
+}
+
+PG_D void merge_even_odd12(uint32_t* r, const uint32_t* e, const uint32_t* o) {
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, %33;\n\t"
+        "addc.cc.u32 %10, %22, %34;\n\t"
+        "addc.u32 %11, %23, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11])
+        : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]));
+}
+
+PG_D void fp_red_rows(uint32_t* X, uint32_t* Y, const uint32_t* p) {
+    uint32_t m;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(m) : "r"(X[0]), "r"(FP_INV32));
+    mad_row6_nc(Y, p, 1, m);
+    mad_row6(X, Y[11], p, 0, m);
+}
+PG_D void fp_step_first(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi, const uint32_t* p) {
+    mul_row6(Y, a, 1, bi);
+    mul_row6(X, a, 0, bi);
+    fp_red_rows(X, Y, p);
+}
+PG_D void fp_step(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi, const uint32_t* p) {
+    mad_row6_shift(Y, X[0], a, 1, bi);          // X[0] += Y[1]; Y = (Y >> 64) + a_odd*bi
+    mad_row6(X, Y[11], a, 0, bi);
+    fp_red_rows(X, Y, p);
+}
+PG_D Fp fp_sub_p_if_ge(const Fp& t, const uint32_t* p) {      // t in [0, 2p) -> t mod p
+    Fp d; uint32_t bw;
+    asm("sub.cc.u32 %0, %13, %25;\n\tsubc.cc.u32 %1, %14, %26;\n\tsubc.cc.u32 %2, %15, %27;\n\tsubc.cc.u32 %3, %16, %28;\n\t"
+        "subc.cc.u32 %4, %17, %29;\n\tsubc.cc.u32 %5, %18, %30;\n\tsubc.cc.u32 %6, %19, %31;\n\tsubc.cc.u32 %7, %20, %32;\n\t"
+        "subc.cc.u32 %8, %21, %33;\n\tsubc.cc.u32 %9, %22, %34;\n\tsubc.cc.u32 %10, %23, %35;\n\tsubc.cc.u32 %11, %24, %36;\n\t"
+        "subc.u32 %12, 0, 0;"
+        : "=&r"(d.v[0]), "=&r"(d.v[1]), "=&r"(d.v[2]), "=&r"(d.v[3]), "=&r"(d.v[4]), "=&r"(d.v[5]), "=&r"(d.v[6]), "=&r"(d.v[7]),
+          "=&r"(d.v[8]), "=&r"(d.v[9]), "=&r"(d.v[10]), "=&r"(d.v[11]), "=&r"(bw)
+        : "r"(t.v[0]), "r"(t.v[1]), "r"(t.v[2]), "r"(t.v[3]), "r"(t.v[4]), "r"(t.v[5]), "r"(t.v[6]), "r"(t.v[7]), "r"(t.v[8]), "r"(t.v[9]), "r"(t.v[10]), "r"(t.v[11]),
+          "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]), "r"(p[8]), "r"(p[9]), "r"(p[10]), "r"(p[11]));
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = bw ? t.v[i] : d.v[i];
+    return r;
+}
+PG_D Fp fp_mul(const Fp& a, const Fp& b) {
+    uint32_t p[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) p[i] = c_p[i];
+    uint32_t even[12], odd[12];
+    fp_step_first(even, odd, a.v, b.v[0], p);
+#pragma unroll
+    for (int i = 1; i < 12; i += 2) {
+        fp_step(odd, even, a.v, b.v[i], p);
+        if (i + 1 < 12) fp_step(even, odd, a.v, b.v[i + 1], p);
+    }
+    // 12 steps: the last one ran with X = odd, Y = even, so the value is odd[1..11] (limbs 0..10) + even (limbs 0..11)
+    Fp r;
+    merge_even_odd12(r.v, even, odd);
+    return fp_sub_p_if_ge(r, p);
+}
+#else
+PG_HD Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_generic(a, b); }
+#endif
 PG_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
 PG_HD Fp fp_to_mont(const Fp& raw) {
     const Fp r2 = {{0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u}};
