@@ -4,6 +4,7 @@
 // present pg_ctx_create fails with PG_ERR_NO_DEVICE and nothing else can be called.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <new>
 #include <cub/device/device_radix_sort.cuh>
 #include "engine.hpp"
@@ -159,6 +160,21 @@ public:
         k_simple<Body><<<grid_for(n), BLOCK, 0, stream>>>(a);
         toc();
         return launched("k_simple");
+    }
+    // bucket sums of the MSM: 128 threads x 3 blocks/SM (168 registers, no spills that matter) measured best; PG_MSM_SHAPE selects
+    // the alternatives for tuning runs (profiles/README.md)
+    int msm_shape = -1;
+    bool run_msm_buckets(const MsmBucketBody::Args& a) {
+        if (msm_shape < 0) { const char* e = getenv("PG_MSM_SHAPE"); msm_shape = e ? atoi(e) : 1; }
+        tic(CLS_OTHER, 0);
+        switch (msm_shape) {
+            case 1: k_simple_shaped<MsmBucketBody, 128, 3><<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a); break;    // <=168 regs, 12 warps/SM
+            case 2: k_simple_shaped<MsmBucketBody, 128, 4><<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a); break;    // <=128 regs, 16 warps/SM
+            case 3: k_simple_shaped<MsmBucketBody, 128, 5><<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a); break;    // <=96 regs, 20 warps/SM
+            default: k_simple<MsmBucketBody><<<grid_for(a.n), BLOCK, 0, stream>>>(a); break;
+        }
+        toc();
+        return launched("k_simple<MsmBucketBody>");
     }
     bool run_batch_inv(const BatchInvArgs& a_in, int cls) {
         BatchInvArgs a = a_in;

@@ -14,6 +14,7 @@
 //   bool run_batch_inv(const BatchInvArgs&, int cls)            -- out_slot = in_slot^-1 (or 0) over table slots
 //   bool run_check(const CheckArgs&), bool run_check_rows(const CheckRowsBody::Args&)
 //   bool sort_pairs(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t n, uint32_t key_bits)
+//   bool run_msm_buckets(const MsmBucketBody::Args&)             -- one thread per bucket (launch shape chosen by the backend)
 //   bool run_ntt_pass(const NttPassArgs&, uint64_t n_blocks)    -- one group of butterfly stages over all tiles (ntt.cuh)
 //   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), bool ubench(int, double*), timing(pg_timing*, bool reset)
 #pragma once
@@ -805,7 +806,7 @@ public:
         if (!be.template run_simple<MsmDigitsBody>(dg, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm digits kernel");
         if (!be.sort_pairs(keys, vals, keys2, vals2, count, key_bits)) return fail(PG_ERR_CUDA, "msm sort");
         MsmBucketBody::Args bk{keys2, vals2, d_points, buckets, count, n_buckets, plan.c};
-        if (!be.template run_simple<MsmBucketBody>(bk, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm bucket kernel");
+        if (!be.run_msm_buckets(bk)) return fail(PG_ERR_CUDA, "msm bucket kernel");
         MsmChunkBody::Args ck{buckets, ping, n_chunks, plan.c, plan.chunk};
         if (!be.template run_simple<MsmChunkBody>(ck, n_chunks, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm chunk kernel");
         uint32_t seg = (1u << plan.c) / plan.chunk;                    // partial sums per window

@@ -37,13 +37,13 @@ PG_HD Fp fp_reduce_once(const Fp& t) {
     for (int i = 0; i < 12; i++) { const uint64_t s = (uint64_t)t.v[i] - fp_p(i) - bw; d.v[i] = (uint32_t)s; bw = (s >> 32) & 1u; }
     return bw ? t : d;
 }
-PG_HD Fp fp_add(const Fp& a, const Fp& b) {
+PG_HD Fp fp_add_generic(const Fp& a, const Fp& b) {
     Fp s; uint64_t c = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) { const uint64_t t = (uint64_t)a.v[i] + b.v[i] + c; s.v[i] = (uint32_t)t; c = t >> 32; }
     return fp_reduce_once(s);                       // p < 2^381: no carry out of limb 11
 }
-PG_HD Fp fp_sub(const Fp& a, const Fp& b) {
+PG_HD Fp fp_sub_generic(const Fp& a, const Fp& b) {
     Fp d; uint64_t bw = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) { const uint64_t s = (uint64_t)a.v[i] - b.v[i] - bw; d.v[i] = (uint32_t)s; bw = (s >> 32) & 1u; }
@@ -53,8 +53,6 @@ PG_HD Fp fp_sub(const Fp& a, const Fp& b) {
     for (int i = 0; i < 12; i++) { const uint64_t t = (uint64_t)d.v[i] + (fp_p(i) & mask) + c; d.v[i] = (uint32_t)t; c = t >> 32; }
     return d;
 }
-PG_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
-PG_HD Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
 
 // CIOS Montgomery multiplication, 12 limb steps (each: 12 products a*b_i, m = t0 * (-p^-1), 12 products m*p): the host version
 // and the definition the device version below is tested against (through the oracle) on the GPU
@@ -185,6 +183,29 @@ PG_D Fp fp_sub_p_if_ge(const Fp& t, const uint32_t* p) {      // t in [0, 2p) ->
     for (int i = 0; i < 12; i++) r.v[i] = bw ? t.v[i] : d.v[i];
     return r;
 }
+
+// device add / sub: one carry chain each (the 64-bit emulation above costs three instructions per limb)
+PG_D Fp fp_add(const Fp& a, const Fp& b) {
+    Fp s;
+    asm("add.cc.u32 %0, %12, %24;\n\taddc.cc.u32 %1, %13, %25;\n\taddc.cc.u32 %2, %14, %26;\n\taddc.cc.u32 %3, %15, %27;\n\taddc.cc.u32 %4, %16, %28;\n\taddc.cc.u32 %5, %17, %29;\n\taddc.cc.u32 %6, %18, %30;\n\taddc.cc.u32 %7, %19, %31;\n\taddc.cc.u32 %8, %20, %32;\n\taddc.cc.u32 %9, %21, %33;\n\taddc.cc.u32 %10, %22, %34;\n\taddc.u32 %11, %23, %35;"
+        : "=&r"(s.v[0]), "=&r"(s.v[1]), "=&r"(s.v[2]), "=&r"(s.v[3]), "=&r"(s.v[4]), "=&r"(s.v[5]), "=&r"(s.v[6]), "=&r"(s.v[7]), "=&r"(s.v[8]), "=&r"(s.v[9]), "=&r"(s.v[10]), "=&r"(s.v[11])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]), "r"(b.v[8]), "r"(b.v[9]), "r"(b.v[10]), "r"(b.v[11]));
+    uint32_t p[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) p[i] = c_p[i];
+    return fp_sub_p_if_ge(s, p);
+}
+PG_D Fp fp_sub(const Fp& a, const Fp& b) {
+    Fp d; uint32_t bw;
+    asm("sub.cc.u32 %0, %13, %25;\n\tsubc.cc.u32 %1, %14, %26;\n\tsubc.cc.u32 %2, %15, %27;\n\tsubc.cc.u32 %3, %16, %28;\n\tsubc.cc.u32 %4, %17, %29;\n\tsubc.cc.u32 %5, %18, %30;\n\tsubc.cc.u32 %6, %19, %31;\n\tsubc.cc.u32 %7, %20, %32;\n\tsubc.cc.u32 %8, %21, %33;\n\tsubc.cc.u32 %9, %22, %34;\n\tsubc.cc.u32 %10, %23, %35;\n\tsubc.cc.u32 %11, %24, %36;\n\tsubc.u32 %12, 0, 0;"
+        : "=&r"(d.v[0]), "=&r"(d.v[1]), "=&r"(d.v[2]), "=&r"(d.v[3]), "=&r"(d.v[4]), "=&r"(d.v[5]), "=&r"(d.v[6]), "=&r"(d.v[7]), "=&r"(d.v[8]), "=&r"(d.v[9]), "=&r"(d.v[10]), "=&r"(d.v[11]), "=&r"(bw)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]), "r"(b.v[8]), "r"(b.v[9]), "r"(b.v[10]), "r"(b.v[11]));
+    Fp r;
+    asm("add.cc.u32 %0, %12, %24;\n\taddc.cc.u32 %1, %13, %25;\n\taddc.cc.u32 %2, %14, %26;\n\taddc.cc.u32 %3, %15, %27;\n\taddc.cc.u32 %4, %16, %28;\n\taddc.cc.u32 %5, %17, %29;\n\taddc.cc.u32 %6, %18, %30;\n\taddc.cc.u32 %7, %19, %31;\n\taddc.cc.u32 %8, %20, %32;\n\taddc.cc.u32 %9, %21, %33;\n\taddc.cc.u32 %10, %22, %34;\n\taddc.u32 %11, %23, %35;"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(r.v[8]), "=&r"(r.v[9]), "=&r"(r.v[10]), "=&r"(r.v[11])
+        : "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]), "r"(d.v[6]), "r"(d.v[7]), "r"(d.v[8]), "r"(d.v[9]), "r"(d.v[10]), "r"(d.v[11]), "r"(c_p[0] & bw), "r"(c_p[1] & bw), "r"(c_p[2] & bw), "r"(c_p[3] & bw), "r"(c_p[4] & bw), "r"(c_p[5] & bw), "r"(c_p[6] & bw), "r"(c_p[7] & bw), "r"(c_p[8] & bw), "r"(c_p[9] & bw), "r"(c_p[10] & bw), "r"(c_p[11] & bw));
+    return r;
+}
 PG_D Fp fp_mul(const Fp& a, const Fp& b) {
     uint32_t p[12];
 #pragma unroll
@@ -203,7 +224,11 @@ PG_D Fp fp_mul(const Fp& a, const Fp& b) {
 }
 #else
 PG_HD Fp fp_mul(const Fp& a, const Fp& b) { return fp_mul_generic(a, b); }
+PG_HD Fp fp_add(const Fp& a, const Fp& b) { return fp_add_generic(a, b); }
+PG_HD Fp fp_sub(const Fp& a, const Fp& b) { return fp_sub_generic(a, b); }
 #endif
+PG_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
+PG_HD Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
 PG_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
 PG_HD Fp fp_to_mont(const Fp& raw) {
     const Fp r2 = {{0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u}};

@@ -16,6 +16,13 @@ __global__ void __launch_bounds__(BLOCK) k_simple(const typename Body::Args a) {
     if (i < a.n) Body::run(a, i);
 }
 
+// the same with an explicit launch shape (register budget) for bodies that need one: T threads, at least MINB blocks per SM
+template <class Body, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_simple_shaped(const typename Body::Args a) {
+    const uint64_t i = (uint64_t)blockIdx.x * T + threadIdx.x;
+    if (i < a.n) Body::run(a, i);
+}
+
 // ---------------------------------------------------------------------------------------------------- batch inversion
 __device__ __forceinline__ Fr shfl_xor_fr(const Fr& a, int mask) {
     Fr r;

@@ -110,6 +110,44 @@ public:
     }
     void reset() { ok(pg_composer_reset(ctx_), "pg_composer_reset"); }
 
+    // ---- the prover's first round ([DEP] dusk-plonk 0.8 Prover::prove: to_scalars + pad, domain.ifft, commit_key.commit) ----
+    /// log2 of EvaluationDomain::new(circuit_size).size()
+    uint32_t domain_log_size() const { uint32_t l = 0; while ((1ull << l) < circuit_size()) l++; return l; }
+    /// coefficients of w_l, w_r, w_o, w_4: 4 x 2^log_n scalars, column after column
+    std::vector<BlsScalar> wire_polynomials(uint32_t log_n) {
+        std::vector<BlsScalar> out((size_t)4 << log_n);
+        ok(pg_wire_polynomials(ctx_, log_n, reinterpret_cast<pg_fr*>(out.data()), 0), "pg_wire_polynomials");
+        return out;
+    }
+    /// EvaluationDomain::fft / ifft of 2^k scalars
+    std::vector<BlsScalar> fft(const std::vector<BlsScalar>& v, bool inverse) {
+        uint32_t log_n = 0; while ((1ull << log_n) < v.size()) log_n++;
+        if (v.empty() || (1ull << log_n) != v.size()) throw EngineError(PG_ERR_ARG, "fft: the length must be a power of two");
+        std::vector<BlsScalar> out(v.size());
+        ok(pg_fft(ctx_, log_n, inverse ? 1 : 0, reinterpret_cast<const pg_fr*>(v.data()), reinterpret_cast<pg_fr*>(out.data()), 0), "pg_fft");
+        return out;
+    }
+    /// PublicParameters::setup: powers_of_g[i] = beta^i * G1 generator
+    std::vector<pg_g1_affine> srs_powers(const BlsScalar& beta, uint64_t n) {
+        std::vector<pg_g1_affine> out(n);
+        ok(pg_srs_powers(ctx_, reinterpret_cast<const pg_fr*>(&beta), nullptr, n, out.data(), 0), "pg_srs_powers");
+        return out;
+    }
+    /// CommitKey::commit of a coefficient vector (msm_variable_base)
+    pg_g1_affine commit(const std::vector<pg_g1_affine>& powers_of_g, const std::vector<BlsScalar>& coeffs) {
+        if (coeffs.size() > powers_of_g.size()) throw EngineError(PG_ERR_ARG, "commit: polynomial degree exceeds the SRS");
+        pg_g1_affine out{};
+        ok(pg_msm(ctx_, coeffs.size(), powers_of_g.data(), reinterpret_cast<const pg_fr*>(coeffs.data()), &out, 0), "pg_msm");
+        return out;
+    }
+    /// w_l_poly_commit .. w_4_poly_commit
+    std::vector<pg_g1_affine> commit_wire_polynomials(const std::vector<pg_g1_affine>& powers_of_g, uint32_t log_n) {
+        if (powers_of_g.size() < (1ull << log_n)) throw EngineError(PG_ERR_ARG, "commit_wire_polynomials: the SRS holds fewer powers than the domain size");
+        std::vector<pg_g1_affine> out(4);
+        ok(pg_commit_wire_polynomials(ctx_, log_n, powers_of_g.data(), 0, out.data()), "pg_commit_wire_polynomials");
+        return out;
+    }
+
 private:
     pg_ctx* ctx_ = nullptr;
 };

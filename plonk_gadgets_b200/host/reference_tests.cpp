@@ -7,6 +7,7 @@
 // satisfies the gate equation", which is equivalent for these circuits (copy constraints hold by construction).
 // All cases of one test are batched into ONE gadget call (one instance per case).  Exit code 0 = all verdicts as expected.
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include "plonk_gadgets.hpp"
 
@@ -135,10 +136,38 @@ static void test_is_not_zero() {
     }
 }
 
+// What the reference tests do next is prover.prove(&ck) (range_gadgets_tests.rs:90-91).  Its first round -- wire polynomials by
+// ifft, then their KZG commitments -- is checked here through the structure of the SRS: against powers_of_g[i] = beta^i * G
+// the commitment of a polynomial is poly(beta) * G.
+static void prover_first_round_test() {
+    StandardComposer composer;
+    auto witness = AllocatedScalar::allocate(composer, {BlsScalar::from(50001), BlsScalar::from(250001)});
+    range_check(composer, {BlsScalar::from(50000)}, {BlsScalar::from(250000)}, witness);
+    EXPECT(composer.check_circuit_satisfied().first == 0, "range_check satisfied before the prover round");
+    const uint32_t k = composer.domain_log_size();
+    const uint64_t n = 1ull << k;
+    EXPECT(n >= composer.circuit_size() && n / 2 < composer.circuit_size(), "domain = next power of two");
+    const BlsScalar beta = BlsScalar::from(0x5eed5eed5eedULL) * BlsScalar::from(0x9e3779b97f4a7c15ULL);
+    const auto powers = composer.srs_powers(beta, n);
+    const auto polys = composer.wire_polynomials(k);
+    const auto commits = composer.commit_wire_polynomials(powers, k);
+    for (int w = 0; w < 4; w++) {
+        BlsScalar at_beta = BlsScalar::zero();
+        for (uint64_t i = n; i-- > 0;) at_beta = at_beta * beta + polys[(size_t)w * n + i];        // Horner
+        const pg_g1_affine want = composer.commit({powers[0]}, {at_beta});
+        EXPECT(std::memcmp(&want, &commits[w], sizeof(want)) == 0, "commit(w_poly) == w_poly(beta) * G");
+    }
+    // ifft then fft is the identity on a wire-polynomial column
+    std::vector<BlsScalar> col(polys.begin(), polys.begin() + n);
+    const auto evals = composer.fft(col, false);
+    EXPECT(composer.fft(evals, true) == col, "ifft(fft(x)) == x");
+}
+
 int main() {
     try {
         max_bound_test(); range_check_test(); test_maybe_equal();
         test_conditionally_select_0(); test_conditionally_select_1(); test_is_not_zero();
+        prover_first_round_test();
     } catch (const EngineError& e) {
         std::printf("EngineError %d: %s\n", e.code, e.what());
         return 2;

@@ -88,6 +88,7 @@ public:
         for (uint64_t i = 0; i < n; i++) { keys_out[i] = keys[idx[i]]; vals_out[i] = vals[idx[i]]; }
         return true;
     }
+    bool run_msm_buckets(const MsmBucketBody::Args& a) { for (uint64_t b = 0; b < a.n; b++) MsmBucketBody::run(a, b); return true; }
     bool run_ntt_pass(const NttPassArgs& a, uint64_t n_blocks) { ntt_pass_host(a, n_blocks); return true; }
     bool run_check_rows(const CheckRowsBody::Args& a) {
         for (uint64_t i = 0; i < a.n; i++)
