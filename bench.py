@@ -317,7 +317,7 @@ def main():
                          "unit": "T 32x32->64 multiply-accumulates/s, ALGORITHMIC count 816 per gate eval (6 Fr mul x 136, SURVEY.md 8d)",
                          "frac": imad_achieved / wide_peak if wide_peak else None,
                          "peak_source": "measured in this run: IMAD.WIDE.U32 products on all SMs (pg_microbench mode 1); the kernel executes "
-                                        "496 wide products per gate eval (dot-product reduction), so frac can exceed the executed-instruction share",
+                                        "425 wide products per gate eval (factored polynomial, dot-product reduction), so frac can exceed the executed-instruction share",
                          "executed_wide_products_per_row": 425, "frac_executed": (rows_per_launch * 425 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
                          "frac_executed_of_carry_chain_peak": (rows_per_launch * 425 / (check_ms * 1e-3)) / chain_peak if chain_peak else None,
                          "carry_chain_peak": chain_peak / 1e12, "imad_lo_peak": lo_peak / 1e12, "isolated_fr_mul_per_s": fr_mul_peak,
