@@ -190,7 +190,8 @@ int pg_wire_polynomials(pg_ctx *ctx, uint32_t log_n, pg_fr *dst, int dst_on_devi
  * pg_srs_powers: out[i] = beta^i * base, base == NULL meaning the G1 generator (PublicParameters::setup: powers_of_g).
  * pg_g1_fixed_base_mul: out[i] = scalars[i] * base.  base and beta are host pointers to one element.
  * pg_commit_wire_polynomials: the four commitments of the composer's wire polynomials over the domain 2^log_n against
- * powers_of_g[0 .. 2^log_n), written to host memory (w_l, w_r, w_o, w_4).  The reference blinds nothing in this version. */
+ * powers_of_g[0 .. 2^log_n), written to host memory (w_l, w_r, w_o, w_4).  The reference blinds nothing in this version.
+ * Points are taken as given: no on-curve / subgroup check (the reference validates when it deserialises; use pg_g1_op(1, ..)). */
 typedef struct pg_g1_affine { uint64_t x[6]; uint64_t y[6]; } pg_g1_affine;
 int pg_msm(pg_ctx *ctx, uint64_t n, const pg_g1_affine *points, const pg_fr *scalars, pg_g1_affine *out, int on_device);
 int pg_srs_powers(pg_ctx *ctx, const pg_fr *beta, const pg_g1_affine *base, uint64_t n, pg_g1_affine *out, int out_on_device);
