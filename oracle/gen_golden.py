@@ -153,6 +153,40 @@ def main():
     with open(path, "w") as f:
         json.dump(dom, f, indent=1, sort_keys=True)
     print(f"wrote {len(dom['fft'])} transforms and {len(dom['wire_polynomials'])} wire-polynomial sets to {path}")
+    g1 = g1_vectors(out)
+    path = os.path.join(os.path.dirname(path), "g1.json")
+    with open(path, "w") as f:
+        json.dump(g1, f, indent=1, sort_keys=True)
+    print(f"wrote {len(g1['multiples'])} generator multiples, {len(g1['msm'])} sums and {len(g1['wire_commitments'])} commitment sets to {path}")
+
+
+def _pt(pt):
+    return None if pt is None else [hex(pt[0]), hex(pt[1])]
+
+
+def g1_vectors(programs):
+    """G1 / commitment fixtures from the affine big-int model of oracle/pymodel.py (second half): multiples of the
+    generator, SRS powers, multi-scalar sums (with a zero scalar, a one, q-1, a repeated point and the point at infinity), and
+    the four wire-polynomial commitments of two small golden programs against powers_of_g = beta^i * G."""
+    from oracle import pymodel as pm
+    G = pm.G1_GENERATOR
+    ks = [1, 2, 3, 5, Q - 1, Q - 2] + synth_wide(97, 4)
+    out = dict(multiples={hx(k): _pt(pm.g1_mul(k, G)) for k in ks}, msm={}, wire_commitments={})
+    beta = synth_wide(98, 1)[0]
+    out["srs"] = dict(beta=hx(beta), powers=[_pt(p) for p in pm.srs_powers(beta, 8)])
+    for n in (1, 8, 40):
+        pts = pm.srs_powers(synth_wide(99, 1)[0], n)
+        sc = synth_wide(100 + n, n)
+        sc[0] = 1
+        if n >= 8:
+            sc[2] = 0; sc[3] = Q - 1; pts[5] = pts[4]; pts[6] = None
+        out["msm"][str(n)] = dict(points=[_pt(p) for p in pts], scalars=[hx(v) for v in sc], sum=_pt(pm.g1_msm(sc, pts)))
+    for name in ("batch_is_non_zero_maybe_equal", "kat_range_check_0_ok"):
+        c = run_pymodel_composer(programs[name]["program"])
+        cols = pm.wire_polynomials(c)
+        srs = pm.srs_powers(beta, len(cols[0]))
+        out["wire_commitments"][name] = dict(log_n=pm.domain_log_size(c.n), commitments=[_pt(pm.g1_msm(col, srs)) for col in cols])
+    return out
 
 
 def coeff_digest(cols) -> str:

@@ -26,6 +26,12 @@ def golden_domain():
 
 
 @pytest.fixture(scope="session")
+def golden_g1():
+    with open(os.path.join(ROOT, "tests", "golden", "g1.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import binding
     binding.build()

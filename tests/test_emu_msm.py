@@ -89,3 +89,26 @@ def test_emu_srs_and_wire_commitments(emu, oracle, golden):
     polys = oc.wire_polynomials()
     for w in range(4):
         assert np.array_equal(to_oracle(got[w:w + 1]), oracle.g1_msm(to_oracle(srs), polys[w])), w
+
+
+def check_g1_golden(make_composer, oracle, golden, golden_g1):
+    """Engine (emu or CUDA) against tests/golden/g1.json: generator multiples, SRS powers, sums, wire commitments."""
+    from tests.test_oracle_g1 import _pts
+    c = make_composer()
+    ks = [int(k, 16) for k in golden_g1["multiples"]]
+    assert oracle.g1_to_ints(to_oracle(c.g1_fixed_base_mul(oracle.from_ints(ks)))) == _pts(golden_g1["multiples"].values())
+    beta = oracle.from_ints([int(golden_g1["srs"]["beta"], 16)])
+    assert oracle.g1_to_ints(to_oracle(c.srs_powers(beta[0], 8))) == _pts(golden_g1["srs"]["powers"])
+    for n, vec in golden_g1["msm"].items():
+        pts = to_engine(oracle.g1_from_ints(_pts(vec["points"])))
+        got = c.msm(pts, oracle.from_ints([int(v, 16) for v in vec["scalars"]]))
+        assert oracle.g1_to_ints(to_oracle(got.reshape(1, 12))) == _pts([vec["sum"]]), n
+    for name, exp in golden_g1["wire_commitments"].items():
+        _snap, cc = run_engine(golden[name]["program"], make_composer, oracle, return_composer=True)
+        assert cc.domain_log_size() == exp["log_n"]
+        got = cc.commit_wire_polynomials(cc.srs_powers(beta[0], 1 << exp["log_n"]))
+        assert oracle.g1_to_ints(to_oracle(got)) == _pts(exp["commitments"]), name
+
+
+def test_emu_g1_golden(emu, oracle, golden, golden_g1):
+    check_g1_golden(lambda: pg.StandardComposer(_cdll=emu), oracle, golden, golden_g1)

@@ -550,3 +550,8 @@ def test_commit_wire_polynomials_gpu(oracle, golden):
         polys = oc.wire_polynomials()
         for w in range(4):
             assert np.array_equal(to_oracle(got[w:w + 1]), oracle.g1_msm(to_oracle(srs), polys[w])), w
+
+
+def test_g1_golden_gpu(oracle, golden, golden_g1):
+    from tests.test_emu_msm import check_g1_golden
+    check_g1_golden(gpu_composer, oracle, golden, golden_g1)

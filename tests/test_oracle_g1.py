@@ -46,3 +46,30 @@ def test_msm_and_srs(oracle):
         got = oracle.g1_to_ints(oracle.g1_msm(oracle.g1_from_ints(base), oracle.from_ints(sc)))[0]
         assert got == pm.g1_msm(sc, base), n
     assert oracle.g1_to_ints(oracle.srs_powers(oracle.from_ints([12345]), 6)) == pm.srs_powers(12345, 6)
+
+
+def _pts(lst):
+    return [None if p is None else (int(p[0], 16), int(p[1], 16)) for p in lst]
+
+
+def test_g1_golden(oracle, golden, golden_g1):
+    """oracle/g1.c against the committed fixtures tests/golden/g1.json (generated from the big-int model by oracle/gen_golden.py)."""
+    from tests.programs import run_oracle
+    from oracle import pymodel as pm
+    g = oracle.g1_generator()
+    ks = [int(k, 16) for k in golden_g1["multiples"]]
+    for k in ks[:2] + ks[-2:]:                                                   # the fixture is what the big-int model produces
+        assert _pts([golden_g1["multiples"][hex(k)]]) == [pm.g1_mul(k, pm.G1_GENERATOR)]
+    got = oracle.g1_to_ints(oracle.g1_mul(np.repeat(g, len(ks), axis=0), oracle.from_ints(ks)))
+    assert got == _pts(golden_g1["multiples"].values())
+    beta = int(golden_g1["srs"]["beta"], 16)
+    assert oracle.g1_to_ints(oracle.srs_powers(oracle.from_ints([beta]), 8)) == _pts(golden_g1["srs"]["powers"])
+    for n, vec in golden_g1["msm"].items():
+        pts = oracle.g1_from_ints(_pts(vec["points"]))
+        sc = oracle.from_ints([int(v, 16) for v in vec["scalars"]])
+        assert oracle.g1_to_ints(oracle.g1_msm(pts, sc)) == _pts([vec["sum"]]), n
+    for name, exp in golden_g1["wire_commitments"].items():
+        _s, oc = run_oracle(golden[name]["program"], return_composer=True)
+        polys = oc.wire_polynomials()
+        srs = oracle.srs_powers(oracle.from_ints([beta]), 1 << exp["log_n"])
+        assert [oracle.g1_to_ints(oracle.g1_msm(srs, polys[w]))[0] for w in range(4)] == _pts(exp["commitments"]), name
