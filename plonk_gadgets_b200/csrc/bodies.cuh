@@ -216,6 +216,7 @@ struct CheckArgs {
     uint64_t n_inst; uint64_t base_row;
     unsigned long long* counters;
     int mode;
+    const SpOp* sp; uint32_t n_sp;      // structure-aware row program of the segment (PG_CHECK_SPARSE), or null
 };
 
 // GENERIC mode evaluates  a*(q_m*b + q_l) + q_r*b + q_o*c + q_4*d + q_c + PI  -- the gate polynomial with the bilinear term
@@ -227,6 +228,11 @@ struct CheckArgs {
 struct CheckBody {
     typedef CheckArgs Args;
     // gate equation of row `row` for instance i: true iff it holds
+    PG_HD static void masked_add(uint32_t (&t)[9], Fr v, uint32_t mask) {      // t += v & mask
+#pragma unroll
+        for (int j = 0; j < 8; j++) v.v[j] &= mask;
+        add9_fr(t, v);
+    }
     // 0 or ~0 according to the bit variable behind wire w
     PG_HD static uint32_t wire_bit_mask(const DevRow& row, int w, uint64_t i) {
         const uint32_t word = reinterpret_cast<const uint32_t*>(row.addr[w])[i];
@@ -335,6 +341,63 @@ struct CheckBody {
         if (ok) return 0u;
         first_bad = a.base_row + t;
         return 1u;
+    }
+};
+
+// Structure-aware check as a linear program (layout.h, SpOp): the template's rows compiled on the host into the term operations
+// a row needs -- nothing is decided per row on the device, operand addresses are known SP_AHEAD operations ahead (prefetch),
+// and a range_check row costs a handful of adds: the check becomes bound by instruction issue and HBM, not by the multiplier.
+constexpr uint32_t SP_AHEAD = 12;
+struct SparseProgBody {
+    template <class PoolT>
+    PG_HD static uint32_t run(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
+        uint32_t t[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) t[k] = 0;
+        uint32_t mask = ~0u, bad = 0, r = 0;
+        Fr v = fr_zero();
+#pragma unroll 1
+        for (uint32_t j = 0; j < a.n_sp; j++) {
+            const SpOp op = a.sp[j];
+#if defined(__CUDA_ARCH__)
+            if (j + SP_AHEAD < a.n_sp) {
+                const SpOp& nx = a.sp[j + SP_AHEAD];
+                if (nx.stride) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx.addr + i * nx.stride));
+            }
+#endif
+            Fr x = fr_zero(), y = fr_zero();
+            bool mul = false;
+            switch (op.op) {
+                case SP_ADD_FR: add9_fr(t, ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
+                case SP_SUB_FR: add9_fr(t, fr_neg(ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i))); break;
+                case SP_MASK: mask &= 0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u); break;
+                case SP_BITSEL: {
+                    const uint32_t m = mask & (0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u));
+                    CheckBody::masked_add(t, pool(op.sel), m); mask = ~0u;
+                } break;
+                case SP_MUL_SEL_FR: x = pool(op.sel); y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
+                case SP_LOAD_FR: v = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); break;
+                case SP_MUL_FR: x = v; y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
+                case SP_MULSEL_V: x = pool(op.sel); y = v; mul = true; break;
+                case SP_ADD_V: CheckBody::masked_add(t, op.sh ? fr_neg(v) : v, mask); mask = ~0u; break;
+                case SP_ADD_POOL: add9_fr(t, pool(op.sel)); break;
+                default: {                                  // SP_END: the row is complete
+                    if (!limbs9_is_multiple_of_q(t)) {
+                        bad++;
+                        const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
+                        if (g < first_bad) first_bad = g;
+                    }
+                    r++; mask = ~0u;
+#pragma unroll
+                    for (int k = 0; k < 9; k++) t[k] = 0;
+                } break;
+            }
+            if (mul) {                                      // the one multiplier site
+                const Fr p = fr_mul_eo(x, y, q);
+                if (op.op == SP_MUL_SEL_FR) add9_fr(t, p); else v = p;
+            }
+        }
+        return bad;
     }
 };
 

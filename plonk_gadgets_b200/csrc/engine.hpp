@@ -41,6 +41,7 @@ struct Segment {
     void* d_image = nullptr;
     DevTab tabs[MAX_TABS] = {};
     std::vector<DevRow> rows;
+    std::vector<SpOp> sp_ops; SpOp* d_sp = nullptr;    // structure-aware row program (PG_CHECK_SPARSE only)
     std::vector<Column> operands;       // the columns bound as operands (for the permutation map)
 };
 
@@ -157,6 +158,50 @@ public:
     }
     uint32_t loc_of(const Column& c) const { return segs[c.seg].t.var_loc[c.local]; }
 
+    // Compiles the resolved rows of a segment into the structure-aware program (layout.h SpOp, bodies.cuh SparseProgBody):
+    // per term -- selector 0 or zero-variable wire: nothing; packed bit variables: masks; selector +-1: add / subtract;
+    // otherwise one multiplication -- then q_c, PI and the end-of-row test.
+    static void build_sparse_program(Segment& s) {
+        auto mem = [](uint8_t op, uint64_t addr, uint32_t stride, uint16_t sel, uint8_t sh) { SpOp o; o.addr = addr; o.stride = stride; o.sel = sel; o.op = op; o.sh = sh; return o; };
+        auto& out = s.sp_ops; out.clear();
+        for (const DevRow& d : s.rows) {
+            for (int k = 0; k < 5; k++) {
+                const uint16_t si = d.sel[k];
+                if (si == POOL_ZERO) continue;
+                int wires[2], nw = 0;
+                wires[nw++] = k ? k - 1 : 0;
+                if (k == 0) wires[nw++] = 1;
+                bool zero = false; int bits[2], nb = 0, frs[2], nf = 0;
+                for (int j = 0; j < nw; j++) {
+                    const uint32_t kind = loc_kind(d.loc[wires[j]]);
+                    if (kind == LOC_ZERO) zero = true; else if (kind == LOC_BIT) bits[nb++] = wires[j]; else frs[nf++] = wires[j];
+                }
+                if (zero) continue;
+                const bool general = si != POOL_ONE && si != POOL_MINUS_ONE;
+                auto bit_op = [&](uint8_t op, int w, uint16_t sel) { return mem(op, d.addr[w], 4, sel, (uint8_t)(d.loc[w] & 31u)); };
+                if (nf == 0) {                                      // bits only: the term is the selector or nothing
+                    for (int j = 0; j + 1 < nb; j++) out.push_back(bit_op(SP_MASK, bits[j], 0));
+                    out.push_back(bit_op(SP_BITSEL, bits[nb - 1], si));
+                    continue;
+                }
+                for (int j = 0; j < nb; j++) out.push_back(bit_op(SP_MASK, bits[j], 0));
+                if (nf == 1 && nb == 0) {
+                    out.push_back(mem(si == POOL_ONE ? SP_ADD_FR : si == POOL_MINUS_ONE ? SP_SUB_FR : SP_MUL_SEL_FR, d.addr[frs[0]], 32, si, 0));
+                    continue;
+                }
+                out.push_back(mem(SP_LOAD_FR, d.addr[frs[0]], 32, 0, 0));
+                if (nf == 2) out.push_back(mem(SP_MUL_FR, d.addr[frs[1]], 32, 0, 0));
+                if (general) out.push_back(mem(SP_MULSEL_V, 0, 0, si, 0));
+                out.push_back(mem(SP_ADD_V, 0, 0, 0, si == POOL_MINUS_ONE ? 1 : 0));
+            }
+            auto param_addr = [&](int slot) { return (uint64_t)(uintptr_t)(s.param + 2 * ((uint64_t)slot * s.n_alloc)); };
+            if (d.qc_param >= 0) out.push_back(mem(SP_ADD_FR, param_addr(d.qc_param), 32, 0, 0));
+            else if (d.sel[5] != POOL_ZERO) out.push_back(mem(SP_ADD_POOL, 0, 0, d.sel[5], 0));
+            if (d.pi_param >= 0) out.push_back(mem(SP_ADD_FR, param_addr(d.pi_param), 32, 0, 0));
+            else if (d.pi_sel != POOL_ZERO) out.push_back(mem(SP_ADD_POOL, 0, 0, d.pi_sel, 0));
+            out.push_back(mem(SP_END, 0, 0, 0, 0));
+        }
+    }
     // Appends a segment of n instances of template t whose operands are the given columns.  Allocates the variable
     // table, resolves the symbolic wires and uploads the row program.  The witness kernels run afterwards.
     int push_segment(Template&& t, uint64_t n, const Column* operands, uint32_t n_operands) {
@@ -190,9 +235,12 @@ public:
             }
             s.rows[r] = d;
         }
-        // rows | variable map | selector pool go up in ONE copy (one staging image per segment)
+        if (cfg.check_mode == PG_CHECK_SPARSE) build_sparse_program(s);
+        // rows | variable map | selector pool | structure-aware program go up in ONE copy (one staging image per segment)
         const size_t b_rows = s.rows.size() * sizeof(DevRow), b_var = (T.var_loc.size() * sizeof(uint32_t) + 31) & ~(size_t)31, b_pool = T.pool.size() * sizeof(Fr);
-        std::vector<unsigned char> img(b_rows + b_var + b_pool);
+        const size_t b_sp = s.sp_ops.size() * sizeof(SpOp);
+        std::vector<unsigned char> img(b_rows + b_var + b_pool + b_sp);
+        if (b_sp) memcpy(img.data() + b_rows + b_var + b_pool, s.sp_ops.data(), b_sp);
         if (b_rows) memcpy(img.data(), s.rows.data(), b_rows);
         if (!T.var_loc.empty()) memcpy(img.data() + b_rows, T.var_loc.data(), T.var_loc.size() * sizeof(uint32_t));
         memcpy(img.data() + b_rows + b_var, T.pool.data(), b_pool);
@@ -201,6 +249,7 @@ public:
         s.d_rows = b_rows ? (DevRow*)d_img : nullptr;
         s.d_varloc = T.var_loc.empty() ? nullptr : (uint32_t*)(d_img + b_rows);
         s.d_pool = (uint32_t*)(d_img + b_rows + b_var);
+        s.d_sp = b_sp ? (SpOp*)(d_img + b_rows + b_var + b_pool) : nullptr;
         s.d_image = d_img;
         // (pageable sources: cudaMemcpyAsync has consumed them when it returns; they stay alive in the Segment anyway)
         segs.push_back(std::move(s));
@@ -435,6 +484,7 @@ public:
             a.param = s.param; a.param_stride = s.n_alloc; a.rows = s.d_rows; a.pool = s.d_pool;
             a.n_rows = (uint32_t)s.t.rows.size(); a.n_pool = (uint32_t)s.t.pool.size();
             a.n_inst = s.n_inst; a.base_row = s.base_row; a.counters = d_counters; a.mode = cfg.check_mode;
+            a.sp = s.d_sp; a.n_sp = (uint32_t)s.sp_ops.size();
             if (!be.run_check(a)) return fail(PG_ERR_CUDA, "gate-check kernel");
         }
         unsigned long long c[CNT_WORDS];

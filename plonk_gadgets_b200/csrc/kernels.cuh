@@ -139,7 +139,11 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
     const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
-    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, q, i, first_bad); }
+    if (i < a.n_inst) {
+        SmemPool pool = {s_pool};
+        if (MODE == 1 && a.sp) bad = SparseProgBody::run(a, pool, q, i, first_bad);     // compiled row program (layout.h, SpOp)
+        else bad = CheckBody::run<MODE>(a, pool, q, i, first_bad);
+    }
     // warp-level reduction, then one atomic per warp that saw a violation
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -57,6 +57,14 @@ struct DevRow {               // 96 bytes
 };
 static_assert(sizeof(DevRow) == 96, "DevRow must stay 96 bytes");
 
+// ---- structure-aware row program (PG_CHECK_SPARSE) ----------------------------------------------------------------------
+// The rows of a template compiled, once per segment on the host, into a linear list of term operations (bodies.cuh,
+// SparseProgBody): what a structure-aware check has to do and nothing else.  `addr` is the pre-resolved instance-0 address of
+// the operand, `stride` its size per instance (32: scalar, 4: word of packed bits, 0: no memory operand).
+enum : uint8_t { SP_END = 0, SP_ADD_FR, SP_SUB_FR, SP_MASK, SP_BITSEL, SP_MUL_SEL_FR, SP_LOAD_FR, SP_MUL_FR, SP_MULSEL_V, SP_ADD_V, SP_ADD_POOL };
+struct SpOp { uint64_t addr; uint32_t stride; uint16_t sel; uint8_t op; uint8_t sh; };
+static_assert(sizeof(SpOp) == 16, "SpOp must stay 16 bytes");
+
 // reserved pool entries
 enum : uint16_t { POOL_ZERO = 0, POOL_ONE = 1, POOL_MINUS_ONE = 2 };
 

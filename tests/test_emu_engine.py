@@ -233,3 +233,29 @@ def _empty_and_ragged(make_composer, oracle):
 
 def test_emu_empty_and_ragged(emu, oracle):
     _empty_and_ragged(lambda: pg.StandardComposer(_cdll=emu), oracle)
+
+
+def test_emu_sparse_program_on_batches(emu, oracle):
+    """Batches large enough for the one-thread-per-instance mapping, i.e. for the compiled structure-aware row program
+    (SparseProgBody): the verdict (count and first bad row) must equal the generic evaluation's, on satisfied circuits and with
+    wrong claims, wrong witnesses for is_non_zero, per-instance bounds (q_c parameters) and public inputs."""
+    n = 64
+    wit = synth_wide(55, n)
+    wit = [w % 2 ** 40 if i % 2 == 0 else w for i, w in enumerate(wit)]
+    mx = [(2 ** 39 | (w % 2 ** 39)) + 1 for w in synth_wide(56, n)]
+    mn = [m // 3 for m in mx]
+    claims = [1 if mn[i] <= wit[i] < mx[i] else 0 for i in range(n)]
+    claims[5] ^= 1; claims[40] ^= 1                                             # two wrong claims
+    prog = [dict(op="add_input", values=[hx(w) for w in wit]),
+            dict(op="range_check", min=[hx(v) for v in mn], max=[hx(v) for v in mx], witness=0),
+            dict(op="constrain_to_constant", a=1, constant=[hx(c) for c in claims]),
+            dict(op="maybe_equal", a=0, b=1),
+            dict(op="select_one", y=0, select=1),
+            dict(op="select_zero", x=0, select=1),
+            dict(op="constrain_to_constant", a=5, constant=hx(0), pi=[hx(-(0 if c else w)) for c, w in zip(claims, wit)]),
+            dict(op="is_non_zero", var=0, assigned=[hx(w if i != 9 else w + 1) for i, w in enumerate(wit)])]
+    ref = run_oracle(prog)
+    assert len(ref.unsat) >= 3
+    for mode in (pg.CHECK_GENERIC, pg.CHECK_SPARSE):
+        snap = run_engine(prog, lambda: pg.StandardComposer(check_mode=mode, _cdll=emu), oracle)
+        assert snap.unsat == ref.unsat and snap.digest() == ref.digest(), mode
