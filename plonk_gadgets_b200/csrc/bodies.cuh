@@ -362,12 +362,12 @@ struct SparseProgBody {
 #if defined(__CUDA_ARCH__)
             if (j + SP_AHEAD < a.n_sp) {
                 const SpOp& nx = a.sp[j + SP_AHEAD];
-                if (nx.stride) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx.addr + i * nx.stride));
+                if (nx.addr) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx.addr + i * nx.stride));
             }
 #endif
             Fr x = fr_zero(), y = fr_zero();
             bool mul = false;
-            switch (op.op) {
+            switch (op.op & 0x7fu) {
                 case SP_ADD_FR: add9_fr(t, ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
                 case SP_SUB_FR: add9_fr(t, fr_neg(ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i))); break;
                 case SP_MASK: mask &= 0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u); break;
@@ -381,20 +381,22 @@ struct SparseProgBody {
                 case SP_MULSEL_V: x = pool(op.sel); y = v; mul = true; break;
                 case SP_ADD_V: CheckBody::masked_add(t, op.sh ? fr_neg(v) : v, mask); mask = ~0u; break;
                 case SP_ADD_POOL: add9_fr(t, pool(op.sel)); break;
-                default: {                                  // SP_END: the row is complete
-                    if (!limbs9_is_multiple_of_q(t)) {
-                        bad++;
-                        const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
-                        if (g < first_bad) first_bad = g;
-                    }
-                    r++; mask = ~0u;
-#pragma unroll
-                    for (int k = 0; k < 9; k++) t[k] = 0;
-                } break;
+                case SP_TRIVIAL: r += op.stride; break;             // `stride` consecutive rows that hold for every witness
+                default: break;                                     // SP_END: nothing to add
             }
-            if (mul) {                                      // the one multiplier site
+            if (mul) {                                              // the one multiplier site
                 const Fr p = fr_mul_eo(x, y, q);
-                if (op.op == SP_MUL_SEL_FR) add9_fr(t, p); else v = p;
+                if ((op.op & 0x7fu) == SP_MUL_SEL_FR) add9_fr(t, p); else v = p;
+            }
+            if ((op.op & SP_ROW_END) || op.op == SP_END) {          // the row is complete
+                if (!limbs9_is_multiple_of_q(t)) {
+                    bad++;
+                    const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
+                    if (g < first_bad) first_bad = g;
+                }
+                r++; mask = ~0u;
+#pragma unroll
+                for (int k = 0; k < 9; k++) t[k] = 0;
             }
         }
         return bad;

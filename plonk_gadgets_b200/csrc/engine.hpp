@@ -159,12 +159,22 @@ public:
     uint32_t loc_of(const Column& c) const { return segs[c.seg].t.var_loc[c.local]; }
 
     // Compiles the resolved rows of a segment into the structure-aware program (layout.h SpOp, bodies.cuh SparseProgBody):
-    // per term -- selector 0 or zero-variable wire: nothing; packed bit variables: masks; selector +-1: add / subtract;
-    // otherwise one multiplication -- then q_c, PI and the end-of-row test.
+    // per term -- selector 0 or zero-variable wire: nothing; packed bit variables: masks (b*b = b; the selectors of all terms
+    // on the same bits are summed on the host, a sum of 0 removes them); selector +-1: add / subtract; otherwise one
+    // multiplication -- then q_c and PI.  The last operation of a row carries SP_ROW_END; rows left without any operation
+    // hold for every witness and are merged into SP_TRIVIAL runs.  Folded selector sums are appended to the segment's pool.
     static void build_sparse_program(Segment& s) {
         auto mem = [](uint8_t op, uint64_t addr, uint32_t stride, uint16_t sel, uint8_t sh) { SpOp o; o.addr = addr; o.stride = stride; o.sel = sel; o.op = op; o.sh = sh; return o; };
+        auto pool_index = [&](const Fr& c) -> uint16_t {
+            for (size_t k = 0; k < s.t.pool.size(); k++) if (fr_eq(s.t.pool[k], c)) return (uint16_t)k;
+            s.t.pool.push_back(c);
+            return (uint16_t)(s.t.pool.size() - 1);
+        };
+        struct BitTerm { uint64_t addr[2]; uint8_t sh[2]; int n; Fr sum; };
         auto& out = s.sp_ops; out.clear();
         for (const DevRow& d : s.rows) {
+            const size_t row_start = out.size();
+            std::vector<BitTerm> bit_terms;
             for (int k = 0; k < 5; k++) {
                 const uint16_t si = d.sel[k];
                 if (si == POOL_ZERO) continue;
@@ -177,11 +187,20 @@ public:
                     if (kind == LOC_ZERO) zero = true; else if (kind == LOC_BIT) bits[nb++] = wires[j]; else frs[nf++] = wires[j];
                 }
                 if (zero) continue;
+                if (nb == 2 && d.addr[bits[0]] == d.addr[bits[1]] && (d.loc[bits[0]] & 31u) == (d.loc[bits[1]] & 31u)) nb = 1;   // b*b = b
                 const bool general = si != POOL_ONE && si != POOL_MINUS_ONE;
                 auto bit_op = [&](uint8_t op, int w, uint16_t sel) { return mem(op, d.addr[w], 4, sel, (uint8_t)(d.loc[w] & 31u)); };
-                if (nf == 0) {                                      // bits only: the term is the selector or nothing
-                    for (int j = 0; j + 1 < nb; j++) out.push_back(bit_op(SP_MASK, bits[j], 0));
-                    out.push_back(bit_op(SP_BITSEL, bits[nb - 1], si));
+                if (nf == 0) {                                      // bits only: selector * (product of bits); fold equal bit sets
+                    BitTerm bt; bt.n = nb; bt.sum = s.t.pool[si];
+                    for (int j = 0; j < nb; j++) { bt.addr[j] = d.addr[bits[j]]; bt.sh[j] = (uint8_t)(d.loc[bits[j]] & 31u); }
+                    if (nb == 2 && (bt.addr[0] > bt.addr[1] || (bt.addr[0] == bt.addr[1] && bt.sh[0] > bt.sh[1]))) { std::swap(bt.addr[0], bt.addr[1]); std::swap(bt.sh[0], bt.sh[1]); }
+                    bool merged = false;
+                    for (BitTerm& o : bit_terms) {
+                        bool same = o.n == bt.n;
+                        for (int j = 0; same && j < bt.n; j++) same = o.addr[j] == bt.addr[j] && o.sh[j] == bt.sh[j];
+                        if (same) { o.sum = fr_add(o.sum, bt.sum); merged = true; break; }
+                    }
+                    if (!merged) bit_terms.push_back(bt);
                     continue;
                 }
                 for (int j = 0; j < nb; j++) out.push_back(bit_op(SP_MASK, bits[j], 0));
@@ -194,12 +213,20 @@ public:
                 if (general) out.push_back(mem(SP_MULSEL_V, 0, 0, si, 0));
                 out.push_back(mem(SP_ADD_V, 0, 0, 0, si == POOL_MINUS_ONE ? 1 : 0));
             }
+            for (const BitTerm& bt : bit_terms) {
+                if (fr_is_zero(bt.sum)) continue;                   // e.g. b*b - b: (1 + -1) * b
+                const uint16_t sel = pool_index(bt.sum);
+                for (int j = 0; j + 1 < bt.n; j++) out.push_back(mem(SP_MASK, bt.addr[j], 4, 0, bt.sh[j]));
+                out.push_back(mem(SP_BITSEL, bt.addr[bt.n - 1], 4, sel, bt.sh[bt.n - 1]));
+            }
             auto param_addr = [&](int slot) { return (uint64_t)(uintptr_t)(s.param + 2 * ((uint64_t)slot * s.n_alloc)); };
             if (d.qc_param >= 0) out.push_back(mem(SP_ADD_FR, param_addr(d.qc_param), 32, 0, 0));
             else if (d.sel[5] != POOL_ZERO) out.push_back(mem(SP_ADD_POOL, 0, 0, d.sel[5], 0));
             if (d.pi_param >= 0) out.push_back(mem(SP_ADD_FR, param_addr(d.pi_param), 32, 0, 0));
             else if (d.pi_sel != POOL_ZERO) out.push_back(mem(SP_ADD_POOL, 0, 0, d.pi_sel, 0));
-            out.push_back(mem(SP_END, 0, 0, 0, 0));
+            if (out.size() > row_start) { out.back().op |= SP_ROW_END; continue; }
+            if (!out.empty() && out.back().op == SP_TRIVIAL) out.back().stride++;      // `stride` of SP_TRIVIAL counts the rows (no memory operand: addr = 0)
+            else out.push_back(mem(SP_TRIVIAL, 0, 1, 0, 0));
         }
     }
     // Appends a segment of n instances of template t whose operands are the given columns.  Allocates the variable

@@ -61,7 +61,10 @@ static_assert(sizeof(DevRow) == 96, "DevRow must stay 96 bytes");
 // The rows of a template compiled, once per segment on the host, into a linear list of term operations (bodies.cuh,
 // SparseProgBody): what a structure-aware check has to do and nothing else.  `addr` is the pre-resolved instance-0 address of
 // the operand, `stride` its size per instance (32: scalar, 4: word of packed bits, 0: no memory operand).
-enum : uint8_t { SP_END = 0, SP_ADD_FR, SP_SUB_FR, SP_MASK, SP_BITSEL, SP_MUL_SEL_FR, SP_LOAD_FR, SP_MUL_FR, SP_MULSEL_V, SP_ADD_V, SP_ADD_POOL };
+// Flag SP_ROW_END on an operation: the row is complete after it (test the sum, next row).  SP_TRIVIAL: a row whose folded
+// polynomial is identically zero (e.g. b*b - b on a packed bit variable): nothing to evaluate, only the row counter moves.
+enum : uint8_t { SP_END = 0, SP_ADD_FR, SP_SUB_FR, SP_MASK, SP_BITSEL, SP_MUL_SEL_FR, SP_LOAD_FR, SP_MUL_FR, SP_MULSEL_V, SP_ADD_V, SP_ADD_POOL, SP_TRIVIAL,
+                 SP_ROW_END = 0x80 };
 struct SpOp { uint64_t addr; uint32_t stride; uint16_t sel; uint8_t op; uint8_t sh; };
 static_assert(sizeof(SpOp) == 16, "SpOp must stay 16 bytes");
 
