@@ -513,12 +513,14 @@ def test_msm_edge_cases_gpu(oracle):
     assert not c.msm(np.concatenate([srs[3:4], srs[3:4]]), oracle.from_ints([5, Q - 5])).any()
 
 
-def test_commitment_is_polynomial_at_beta(oracle, torch_cuda):
-    """Size-independent check at 2^18 terms, device-resident: against powers_of_g[i] = beta^i * G the commitment of a coefficient
-    vector is poly(beta) * G -- the right-hand side needs one Horner evaluation on big ints and one fixed-base multiplication."""
+@pytest.mark.parametrize("log_n", [18, 22])
+def test_commitment_is_polynomial_at_beta(oracle, torch_cuda, log_n):
+    """Size-independent check at 2^18 (15-bit windows) and 2^22 terms (17-bit windows), device-resident: against
+    powers_of_g[i] = beta^i * G the commitment of a coefficient vector is poly(beta) * G -- the right-hand side needs one Horner
+    evaluation on big ints and one fixed-base multiplication."""
     from tests.test_emu_msm import to_oracle
     torch = torch_cuda
-    n = 1 << 18
+    n = 1 << log_n
     c = gpu_composer()
     beta = 0x2b6cedcb87925c23c999e990f3f29c6d0748d9d99f59ff1105d314967254398f % Q
     srs = torch.empty((n, 12), dtype=torch.int64, device="cuda")
@@ -532,6 +534,24 @@ def test_commitment_is_polynomial_at_beta(oracle, torch_cuda):
     want = c.g1_fixed_base_mul(oracle.from_ints([acc]))
     assert np.array_equal(got, want[0])
     assert np.array_equal(to_oracle(want), oracle.g1_mul(oracle.g1_generator(), oracle.from_ints([acc])))
+
+
+def test_msm_split_consistency_at_scale(oracle, torch_cuda):
+    """2^24 terms (20-bit windows): the sum over all terms equals the sum of the two half-size sums (17-bit windows), which in turn
+    are anchored by the 2^22 polynomial-at-beta check above."""
+    torch = torch_cuda
+    n = 1 << 24
+    c = gpu_composer()
+    pts = torch.empty((n, 12), dtype=torch.int64, device="cuda")
+    ks = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 92, 0, 0, ks); c.sync()
+    # cheap distinct points: a 2^12-entry table of multiples of G, repeated (MSM does not care about repeated points)
+    table = torch.from_numpy(c.srs_powers(oracle.from_ints([3])[0], 1 << 12).view(np.int64)).cuda()
+    pts.view(n >> 12, 1 << 12, 12)[:] = table
+    sc = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 93, 0, 0, sc); c.sync(); torch.cuda.synchronize()
+    whole = c.msm(pts, sc)
+    h = n // 2
+    lo, hi = c.msm(pts[:h], sc[:h]), c.msm(pts[h:], sc[h:])
+    assert np.array_equal(c.g1_op(0, lo.reshape(1, 12), hi.reshape(1, 12))[0], whole) and whole.any()
 
 
 def test_commit_wire_polynomials_gpu(oracle, golden):
