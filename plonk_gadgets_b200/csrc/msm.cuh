@@ -20,7 +20,7 @@
 namespace pg {
 
 struct MsmPlan { uint32_t c, n_windows, chunk; };          // chunk = L, a power of two <= 2^c
-// Window widths are taken from {3, 5, 8, 15, 16, 17, 20}: for these the top window (255 - c*(W-1) bits) is as wide as the others or
+// Window widths are taken from {3, 5, 8, 15, 16}: for these the top window (255 - c*(W-1) bits) is as wide as the others or
 // one bit short, so no bucket is much fuller than average (with c = 12 the top window would have 3 bits: 8 buckets of n/8
 // points each, summed by 8 threads).  Buckets per window grow with n so that bucket sums (W*n additions) and bucket
 // reduction (2 * W * 2^c additions) stay balanced.
@@ -28,7 +28,7 @@ inline MsmPlan msm_plan(uint64_t n) {
     uint32_t log_n = 0;
     while ((1ull << (log_n + 1)) <= n) log_n++;
     MsmPlan p;
-    p.c = log_n <= 6 ? 3 : log_n <= 9 ? 5 : log_n <= 15 ? 8 : log_n <= 19 ? 15 : log_n <= 21 ? 16 : log_n <= 23 ? 17 : 20;
+    p.c = log_n <= 6 ? 3 : log_n <= 9 ? 5 : log_n <= 15 ? 8 : log_n <= 19 ? 15 : 16;      // 17 / 20 bits measured slower even at 2^22 / 2^25
     p.n_windows = (255 + p.c - 1) / p.c;
     p.chunk = p.c >= 8 ? 32u : (1u << p.c);
     return p;

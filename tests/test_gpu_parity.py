@@ -515,7 +515,7 @@ def test_msm_edge_cases_gpu(oracle):
 
 @pytest.mark.parametrize("log_n", [18, 22])
 def test_commitment_is_polynomial_at_beta(oracle, torch_cuda, log_n):
-    """Size-independent check at 2^18 (15-bit windows) and 2^22 terms (17-bit windows), device-resident: against
+    """Size-independent check at 2^18 (15-bit windows) and 2^22 terms (16-bit windows), device-resident: against
     powers_of_g[i] = beta^i * G the commitment of a coefficient vector is poly(beta) * G -- the right-hand side needs one Horner
     evaluation on big ints and one fixed-base multiplication."""
     from tests.test_emu_msm import to_oracle
@@ -537,8 +537,8 @@ def test_commitment_is_polynomial_at_beta(oracle, torch_cuda, log_n):
 
 
 def test_msm_split_consistency_at_scale(oracle, torch_cuda):
-    """2^24 terms (20-bit windows): the sum over all terms equals the sum of the two half-size sums (17-bit windows), which in turn
-    are anchored by the 2^22 polynomial-at-beta check above."""
+    """2^24 terms: the sum over all terms equals the sum of the two half-size sums, which in turn are anchored by the 2^22
+    polynomial-at-beta check above."""
     torch = torch_cuda
     n = 1 << 24
     c = gpu_composer()
