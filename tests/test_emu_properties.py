@@ -92,3 +92,34 @@ def test_fault_injection_flips_exactly_its_row(emu, oracle, row, col, delta):
     if col < 2:
         change += sel[0] * delta * others[1 - col]
     assert (n_bad, first) == ((1, row) if change % Q else (0, None)), sel_names[col]
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(vals=st.lists(scalars, min_size=8, max_size=8), seq=st.lists(ops, min_size=1, max_size=5), seed=st.integers(0, 1000))
+def test_sparse_program_random_compositions(emu, oracle, vals, seq, seed):
+    """Batches of 48 instances go through the compiled structure-aware row program (SparseProgBody): for random gadget
+    sequences -- satisfied or not -- its list of violated rows must be the oracle's, like the generic evaluation's."""
+    rng = np.random.default_rng(seed)
+    n = 48
+    col_a = [vals[i % 8] if i % 3 else (vals[i % 8] + i) % Q for i in range(n)]
+    col_b = [vals[(i + 3) % 8] if i % 2 else col_a[i] for i in range(n)]
+    prog = [dict(op="add_input", values=[hx(v) for v in col_a]), dict(op="add_input", values=[hx(v) for v in col_b])]
+    cols = [0, 1]
+    for op in seq:
+        a, b = int(rng.choice(cols)), int(rng.choice(cols))
+        if op == "maybe_equal":
+            prog.append(dict(op=op, a=a, b=b)); cols.append(len(prog) - 1)
+        elif op in ("select_zero", "select_one"):
+            prog.append(dict(op=op, **({"x": a} if op == "select_zero" else {"y": a}), select=b)); cols.append(len(prog) - 1)
+        elif op == "is_non_zero":
+            prog.append(dict(op=op, var=a, assigned=[hx(v if v else 1) for v in col_a]))
+        elif op == "max_bound":
+            bits = int(rng.integers(1, 250))
+            prog.append(dict(op=op, max=[hx(2 ** bits + int(rng.integers(0, 2 ** min(bits, 60)))) for _ in range(n)] if seed % 3 == 0 else hx(2 ** bits), witness=a))
+            cols.append(len(prog) - 1)
+        else:
+            prog.append(dict(op="constrain_to_constant", a=a, constant=hx(int(rng.integers(0, 3))), pi=[hx(v) for v in col_b] if seed % 2 else None))
+    so = run_oracle(prog)
+    for mode in (pg.CHECK_SPARSE, pg.CHECK_GENERIC):
+        se = run_engine(prog, lambda: pg.StandardComposer(check_mode=mode, _cdll=emu), oracle)
+        assert se.error == so.error and se.digest() == so.digest() and se.unsat == so.unsat, mode
