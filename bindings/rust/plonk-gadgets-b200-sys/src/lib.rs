@@ -90,7 +90,7 @@ extern "C" {
     pub fn pg_srs_powers(ctx: *mut pg_ctx, beta: *const pg_fr, base: *const pg_g1_affine, n: u64, out: *mut pg_g1_affine, out_on_device: c_int) -> c_int;
     pub fn pg_g1_fixed_base_mul(ctx: *mut pg_ctx, n: u64, base: *const pg_g1_affine, scalars: *const pg_fr, out: *mut pg_g1_affine,
                                 on_device: c_int) -> c_int;
-    pub fn pg_commit_wire_polynomials(ctx: *mut pg_ctx, log_n: u32, powers_of_g: *const pg_g1_affine, powers_on_device: c_int,
+    pub fn pg_commit_wire_polynomials(ctx: *mut pg_ctx, log_n: u32, powers_of_g: *const pg_g1_affine, n_powers: u64, powers_on_device: c_int,
                                       out4: *mut pg_g1_affine) -> c_int;
     pub fn pg_g1_op(ctx: *mut pg_ctx, op: c_int, n: u64, a: *const pg_g1_affine, b: *const pg_g1_affine, out: *mut pg_g1_affine) -> c_int;
     pub fn pg_fr_to_bytes(ctx: *mut pg_ctx, n: u64, src: *const pg_fr, dst: *mut u8, on_device: c_int) -> c_int;

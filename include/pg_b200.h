@@ -190,13 +190,15 @@ int pg_wire_polynomials(pg_ctx *ctx, uint32_t log_n, pg_fr *dst, int dst_on_devi
  * pg_srs_powers: out[i] = beta^i * base, base == NULL meaning the G1 generator (PublicParameters::setup: powers_of_g).
  * pg_g1_fixed_base_mul: out[i] = scalars[i] * base.  base and beta are host pointers to one element.
  * pg_commit_wire_polynomials: the four commitments of the composer's wire polynomials over the domain 2^log_n against
- * powers_of_g[0 .. 2^log_n), written to host memory (w_l, w_r, w_o, w_4).  The reference blinds nothing in this version.
+ * powers_of_g[0 .. 2^log_n), written to host memory (w_l, w_r, w_o, w_4); PG_ERR_ARG when n_powers < 2^log_n (the reference's
+ * check_commit_degree_is_within_bounds / Error::PolynomialDegreeTooLarge).  The reference blinds nothing in this version.
  * Points are taken as given: no on-curve / subgroup check (the reference validates when it deserialises; use pg_g1_op(1, ..)). */
 typedef struct pg_g1_affine { uint64_t x[6]; uint64_t y[6]; } pg_g1_affine;
 int pg_msm(pg_ctx *ctx, uint64_t n, const pg_g1_affine *points, const pg_fr *scalars, pg_g1_affine *out, int on_device);
 int pg_srs_powers(pg_ctx *ctx, const pg_fr *beta, const pg_g1_affine *base, uint64_t n, pg_g1_affine *out, int out_on_device);
 int pg_g1_fixed_base_mul(pg_ctx *ctx, uint64_t n, const pg_g1_affine *base, const pg_fr *scalars, pg_g1_affine *out, int on_device);
-int pg_commit_wire_polynomials(pg_ctx *ctx, uint32_t log_n, const pg_g1_affine *powers_of_g, int powers_on_device, pg_g1_affine *out4);
+int pg_commit_wire_polynomials(pg_ctx *ctx, uint32_t log_n, const pg_g1_affine *powers_of_g, uint64_t n_powers, int powers_on_device,
+                               pg_g1_affine *out4);
 /* self-test helper: op 0: out[i] = a[i] + b[i]; op 1: out[i].x[0] = 1 if a[i] is on the curve (or infinity) else 0.  Host buffers. */
 int pg_g1_op(pg_ctx *ctx, int op, uint64_t n, const pg_g1_affine *a, const pg_g1_affine *b, pg_g1_affine *out);
 

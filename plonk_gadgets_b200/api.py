@@ -321,10 +321,8 @@ class StandardComposer:
         """(4, 12) uint64: commitments to w_l, w_r, w_o, w_4 against powers_of_g[0 .. 2^log_n)."""
         log_n = self.domain_log_size() if log_n is None else log_n
         pp, pdev, n, _keep = self._points(powers_of_g)
-        if n < (1 << log_n):
-            raise ValueError("commit_wire_polynomials: the SRS holds fewer powers than the domain size")
         out = np.zeros((4, 12), dtype=np.uint64)
-        self._ok(self._L.pg_commit_wire_polynomials(self._ctx, log_n, pp, pdev, out.ctypes.data_as(C.c_void_p)), "pg_commit_wire_polynomials")
+        self._ok(self._L.pg_commit_wire_polynomials(self._ctx, log_n, pp, n, pdev, out.ctypes.data_as(C.c_void_p)), "pg_commit_wire_polynomials")
         return out
 
     def g1_op(self, op: int, a, b=None) -> np.ndarray:

@@ -125,9 +125,9 @@ int pg_g1_fixed_base_mul(pg_ctx* ctx, uint64_t n, const pg_g1_affine* base, cons
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, scalars, on_device); PG_ALIGNED(ctx, out, on_device);
     return ctx->e.g1_fixed_base_mul(n, base, scalars, out, on_device);
 }
-int pg_commit_wire_polynomials(pg_ctx* ctx, uint32_t log_n, const pg_g1_affine* powers_of_g, int powers_on_device, pg_g1_affine* out4) {
+int pg_commit_wire_polynomials(pg_ctx* ctx, uint32_t log_n, const pg_g1_affine* powers_of_g, uint64_t n_powers, int powers_on_device, pg_g1_affine* out4) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, powers_of_g, powers_on_device);
-    return ctx->e.commit_wire_polynomials(log_n, powers_of_g, powers_on_device, out4);
+    return ctx->e.commit_wire_polynomials(log_n, powers_of_g, n_powers, powers_on_device, out4);
 }
 int pg_g1_op(pg_ctx* ctx, int op, uint64_t n, const pg_g1_affine* a, const pg_g1_affine* b, pg_g1_affine* out) { PG_NEED_CTX(ctx); return ctx->e.g1_op(op, n, a, b, out); }
 int pg_fr_to_bytes(pg_ctx* ctx, uint64_t n, const pg_fr* src, uint8_t* dst, int on_device) {

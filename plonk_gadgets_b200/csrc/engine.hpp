@@ -944,8 +944,9 @@ public:
         return rc;
     }
     // the four wire-polynomial commitments of Prover::prove: out[w] = commit(w-th wire polynomial) against powers_of_g[0 .. 2^log_n)
-    int commit_wire_polynomials(uint32_t log_n, const pg_g1_affine* powers, int powers_on_device, pg_g1_affine* out) {
+    int commit_wire_polynomials(uint32_t log_n, const pg_g1_affine* powers, uint64_t n_powers, int powers_on_device, pg_g1_affine* out) {
         if (!powers || !out) return fail(PG_ERR_ARG, "commit_wire_polynomials: null argument");
+        if (log_n <= NTT_TWO_ADICITY && n_powers < (1ull << log_n)) return fail(PG_ERR_ARG, "commit_wire_polynomials: the SRS holds fewer powers than the domain size (polynomial degree too large)");
         if (log_n > NTT_TWO_ADICITY || (1ull << log_n) < n_rows) return fail(PG_ERR_ARG, "commit_wire_polynomials: domain smaller than the circuit or larger than 2^32");
         const uint64_t n = 1ull << log_n;
         const size_t mark = scratch.size();

@@ -142,9 +142,8 @@ public:
     }
     /// w_l_poly_commit .. w_4_poly_commit
     std::vector<pg_g1_affine> commit_wire_polynomials(const std::vector<pg_g1_affine>& powers_of_g, uint32_t log_n) {
-        if (powers_of_g.size() < (1ull << log_n)) throw EngineError(PG_ERR_ARG, "commit_wire_polynomials: the SRS holds fewer powers than the domain size");
         std::vector<pg_g1_affine> out(4);
-        ok(pg_commit_wire_polynomials(ctx_, log_n, powers_of_g.data(), 0, out.data()), "pg_commit_wire_polynomials");
+        ok(pg_commit_wire_polynomials(ctx_, log_n, powers_of_g.data(), powers_of_g.size(), 0, out.data()), "pg_commit_wire_polynomials");
         return out;
     }
 

@@ -112,3 +112,27 @@ def check_g1_golden(make_composer, oracle, golden, golden_g1):
 
 def test_emu_g1_golden(emu, oracle, golden, golden_g1):
     check_g1_golden(lambda: pg.StandardComposer(_cdll=emu), oracle, golden, golden_g1)
+
+
+def test_emu_argument_errors(emu, oracle, golden):
+    """Bad arguments of the evaluation-domain / commitment entry points are rejected with PG_ERR_ARG, not executed."""
+    import ctypes as C
+    spec = golden["kat_range_check_0_ok"]
+    _snap, c = run_engine(spec["program"], lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
+    k = c.domain_log_size()
+    srs = c.srs_powers(oracle.from_ints([9])[0], 1 << k)
+    with pytest.raises(pg.EngineError) as e:
+        c.commit_wire_polynomials(srs[: (1 << k) - 1])                       # SRS one power short: polynomial degree too large
+    assert e.value.code == -2
+    with pytest.raises(pg.EngineError):
+        c.commit_wire_polynomials(srs, log_n=k - 1)                          # domain smaller than the circuit
+    buf = np.zeros((2, 4), dtype=np.uint64)
+    p = buf.ctypes.data_as(C.c_void_p)
+    assert c._L.pg_fft(c._ctx, 33, 0, p, p, 0) == -2                         # beyond the two-adicity of Fr
+    assert c._L.pg_fft(c._ctx, 1, 0, None, p, 0) == -2
+    assert c._L.pg_msm(c._ctx, 2, None, p, p, 0) == -2
+    assert c._L.pg_wire_polynomials(c._ctx, k, None, 0) == -2
+    with pytest.raises(ValueError):
+        c.fft(np.zeros((3, 4), dtype=np.uint64))                             # not a power of two
+    with pytest.raises(ValueError):
+        c.msm(srs[:4], oracle.from_ints([1, 2, 3]))                          # length mismatch
