@@ -14,6 +14,7 @@
 //   6. k_simple<MsmFinalBody>     Horner over the windows (c doublings each) and the conversion to affine.
 // c is chosen from n (MsmPlan).  All group formulas are complete (g1.cuh).
 #pragma once
+#include <stdlib.h>
 #include "g1.cuh"
 #include "layout.h"
 
@@ -28,7 +29,8 @@ inline MsmPlan msm_plan(uint64_t n) {
     uint32_t log_n = 0;
     while ((1ull << (log_n + 1)) <= n) log_n++;
     MsmPlan p;
-    p.c = log_n <= 6 ? 3 : log_n <= 9 ? 5 : log_n <= 15 ? 8 : log_n <= 19 ? 15 : 16;      // 17 / 20 bits measured slower even at 2^22 / 2^25
+    p.c = log_n <= 6 ? 3 : log_n <= 9 ? 5 : log_n <= 15 ? 8 : log_n <= 22 ? 15 : 16;      // measured; 17 / 20 bits are slower even at 2^22 / 2^25
+    if (const char* e = getenv("PG_MSM_C")) { const int c = atoi(e); if (c >= 2 && c <= 20) p.c = (uint32_t)c; }   // tuning runs only
     p.n_windows = (255 + p.c - 1) / p.c;
     p.chunk = p.c >= 8 ? 32u : (1u << p.c);
     return p;
