@@ -658,19 +658,29 @@ public:
         if (!be.template run_simple<NttTwiddleBody>(a, a.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "twiddle kernel");
         return PG_OK;
     }
+    // Transform of `data` in place.  Transforms of more than 2^11 points go through a scratch vector of the same size (first
+    // pass data -> scratch with the bit reversal folded into its loads, last pass scratch -> data); it is only touched by
+    // kernels on the engine's stream, so it goes back to the pool as soon as they are enqueued.
     int ntt_inplace(uint4* data, uint32_t log_n, bool inverse) {
         if (log_n == 0) return PG_OK;                                    // one element: the transform is the identity
         int rc = ntt_twiddles(log_n);
         if (rc) return rc;
         const uint64_t n = 1ull << log_n;
-        NttBitrevBody::Args b; b.data = data; b.n = n; b.log_n = log_n; b.scale = inverse ? 1 : 0; b.factor = fr_one();
-        if (inverse) { Fr raw = fr_zero(); raw.v[0] = (uint32_t)n; raw.v[1] = (uint32_t)(n >> 32); b.factor = fr_inv_fermat(fr_to_mont(raw)); }   // size_inv
-        if (!be.template run_simple<NttBitrevBody>(b, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "bit-reversal kernel");
+        Fr factor = fr_one();
+        if (inverse) { Fr raw = fr_zero(); raw.v[0] = (uint32_t)n; raw.v[1] = (uint32_t)(n >> 32); factor = fr_inv_fermat(fr_to_mont(raw)); }   // size_inv
         const NttPlan plan = ntt_plan(log_n);
+        uint4* work = nullptr;
+        if (plan.n_pass > 1 && !(work = (uint4*)dalloc(sizeof(pg_fr) << log_n))) return fail(PG_ERR_OOM, "NTT scratch vector");
         for (uint32_t p = 0; p < plan.n_pass; p++) {
-            NttPassArgs a{data, ntt_tw, log_n, plan.t0[p], plan.s[p], plan.log_c[p], inverse ? 1 : 0};
-            if (!be.run_ntt_pass(a, n >> (plan.s[p] + plan.log_c[p]))) return fail(PG_ERR_CUDA, "NTT pass kernel");
+            NttPassArgs a; memset(&a, 0, sizeof(a));
+            const bool first = p == 0, last = p + 1 == plan.n_pass;
+            a.src = first ? data : work;                                 // first pass: gather through the bit reversal, scale
+            a.dst = last ? data : work;                                  // last pass: back to the caller's buffer
+            a.tw = ntt_tw; a.log_n = log_n; a.t0 = plan.t0[p]; a.s = plan.s[p]; a.log_c = plan.log_c[p];
+            a.inverse = inverse ? 1 : 0; a.bitrev = first ? 1 : 0; a.scale = first && inverse ? 1 : 0; a.factor = factor;
+            if (!be.run_ntt_pass(a, n >> (plan.s[p] + plan.log_c[p]))) { dfree(work); return fail(PG_ERR_CUDA, "NTT pass kernel"); }
         }
+        dfree(work);
         return PG_OK;
     }
     int fft(uint32_t log_n, int inverse, const pg_fr* src, pg_fr* dst, int on_device) {

@@ -8,8 +8,9 @@
 // Both are natural order in, natural order out.  The DFT of a vector is unique and Fr elements are kept fully reduced, so any
 // correct schedule yields the same limbs as the reference's serial radix-2 loop; the schedule here is chosen for the B200:
 //
-//   1. k_simple<NttBitrevBody>: in-place bit-reversal permutation (pairs swapped by the thread of the smaller index), fused
-//      with the n^-1 scaling of the inverse transform;
+//   1. the bit-reversal permutation (and the n^-1 scaling of the inverse transform) is folded into the loads of the first
+//      pass, which writes to a scratch vector; the last pass writes back to the caller's buffer (transforms of up to 2^11
+//      points are one block and run in place);
 //   2. k_ntt_pass, ceil((log_n - 11) / 8) + 1 launches: a block owns a tile of 2^s x C elements (s butterfly stages; C >= 8
 //      neighbouring sub-transforms so that every global access of a warp covers whole 256-byte runs), keeps it in shared
 //      memory (64 KiB, 128-bit accesses), and runs the s stages there two at a time: a thread holds four elements in
@@ -52,20 +53,6 @@ struct NttTwiddleBody {
     }
 };
 
-// ---- bit-reversal permutation (+ scaling) ------------------------------------------------------------------------------
-struct NttBitrevBody {
-    struct Args { uint4* data; uint64_t n; uint32_t log_n; int scale; Fr factor; };
-    PG_HD static void run(const Args& a, uint64_t i) {
-        const uint64_t r = bitrev64(i, a.log_n);
-        if (i > r) return;
-        Fr x = aos_load(a.data, i);
-        if (i == r) { if (a.scale) aos_store(a.data, i, fr_mul(x, a.factor)); return; }
-        Fr y = aos_load(a.data, r);
-        if (a.scale) { x = fr_mul(x, a.factor); y = fr_mul(y, a.factor); }
-        aos_store(a.data, i, y); aos_store(a.data, r, x);
-    }
-};
-
 // zero-fill of the padding rows [n0, n) of a column
 struct NttZeroBody {
     struct Args { uint4* data; uint64_t n0; uint64_t n; };
@@ -76,7 +63,11 @@ struct NttZeroBody {
 // Index of an element: (g_hi, v, g_lo) with g_lo < 2^t0 and v < 2^s; the pass couples elements that differ in v only.
 // Tile `blk` holds the C = 2^log_c values g = blk*C + c of the combined index g = (g_hi, g_lo), all v: tile element
 // e = v*C + c.  With t0 >= log_c the C elements of a v share g_hi and are neighbours in memory.
-struct NttPassArgs { uint4* data; const uint4* tw; uint32_t log_n, t0, s, log_c; int inverse; };
+// A pass reads its tile from `src` and writes it to `dst` (the same buffer for the passes in the middle).  The first pass
+// of a transform (t0 == 0) can gather its input through the bit-reversal permutation (bitrev != 0) and multiply it by
+// `factor` (scale != 0: the n^-1 of the inverse transform): no separate permutation pass.  Such a pass must not run in place
+// unless it is a single block.
+struct NttPassArgs { const uint4* src; uint4* dst; const uint4* tw; uint32_t log_n, t0, s, log_c; int inverse; int bitrev; int scale; Fr factor; };
 
 PG_HD uint64_t ntt_index(const NttPassArgs& a, uint64_t blk, uint32_t e) {
     const uint32_t c = e & ((1u << a.log_c) - 1u), v = e >> a.log_c;
@@ -137,7 +128,12 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const NttPassArgs a
     const uint32_t blk = blockIdx.x;
     if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
     for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS)
-        tile_store(s_tile, E, e, aos_load(a.data, ntt_index32(a, blk, e)));
+    {
+        const uint32_t idx = ntt_index32(a, blk, e);
+        Fr x = aos_load(a.src, a.bitrev ? (a.log_n ? __brev(idx) >> (32u - a.log_n) : 0u) : idx);
+        if (a.scale) x = fr_mul_eo(x, a.factor);
+        tile_store(s_tile, E, e, x);
+    }
     __syncthreads();
     QRegs q;
 #pragma unroll
@@ -192,7 +188,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const NttPassArgs a
         __syncthreads();
     }
     for (uint32_t e = threadIdx.x; e < E; e += NTT_THREADS)
-        aos_store(a.data, ntt_index32(a, blk, e), tile_load(s_tile, E, e));
+        aos_store(a.dst, ntt_index32(a, blk, e), tile_load(s_tile, E, e));
 }
 #endif
 
@@ -201,7 +197,11 @@ inline void ntt_pass_host(const NttPassArgs& a, uint64_t n_blocks) {
     const uint32_t E = 1u << (a.s + a.log_c);
     Fr* tile = new Fr[E];
     for (uint64_t blk = 0; blk < n_blocks; blk++) {
-        for (uint32_t e = 0; e < E; e++) tile[e] = aos_load(a.data, ntt_index(a, blk, e));
+        for (uint32_t e = 0; e < E; e++) {
+            const uint64_t idx = ntt_index(a, blk, e);
+            tile[e] = aos_load(a.src, a.bitrev ? bitrev64(idx, a.log_n) : idx);
+            if (a.scale) tile[e] = fr_mul(tile[e], a.factor);
+        }
         for (uint32_t u = 0; u < a.s; u++)
             for (uint32_t b = 0; b < E / 2; b++) {
                 uint32_t e0, e1; uint64_t ti;
@@ -210,7 +210,7 @@ inline void ntt_pass_host(const NttPassArgs& a, uint64_t n_blocks) {
                 const Fr x0 = tile[e0];
                 tile[e0] = fr_add(x0, t); tile[e1] = fr_sub(x0, t);
             }
-        for (uint32_t e = 0; e < E; e++) aos_store(a.data, ntt_index(a, blk, e), tile[e]);
+        for (uint32_t e = 0; e < E; e++) aos_store(a.dst, ntt_index(a, blk, e), tile[e]);
     }
     delete[] tile;
 }
