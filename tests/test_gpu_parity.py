@@ -575,3 +575,23 @@ def test_commit_wire_polynomials_gpu(oracle, golden):
 def test_g1_golden_gpu(oracle, golden, golden_g1):
     from tests.test_emu_msm import check_g1_golden
     check_g1_golden(gpu_composer, oracle, golden, golden_g1)
+
+
+def test_fft_round_trip_2p27(oracle, torch_cuda):
+    """2^27 scalars (4 GiB vector, 4 GiB scratch, 2 GiB twiddles; 4 passes): forward then inverse is the identity, and the even
+    outputs equal FFT_(n/2)(low half) + FFT_(n/2)(high half) (decimation + linearity) on a strided sample of 4096 positions."""
+    torch = torch_cuda
+    n = 1 << 27
+    c = gpu_composer()
+    x = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 79, 0, 0, x); c.sync()
+    y = x.clone(); torch.cuda.synchronize()
+    c.fft(y); c.sync()
+    idx = torch.arange(0, n // 2, (n // 2) >> 12, device="cuda")
+    even = y[0::2][idx].cpu().numpy().view(np.uint64)
+    c.fft(y, inverse=True); c.sync()
+    assert torch.equal(y, x)
+    del y
+    lo, hi = x[: n // 2].clone(), x[n // 2:].clone(); torch.cuda.synchronize()
+    c.fft(lo); c.fft(hi); c.sync()
+    s = c.fr_op(1, lo[idx].cpu().numpy().view(np.uint64), hi[idx].cpu().numpy().view(np.uint64))
+    assert np.array_equal(s, even)
