@@ -100,6 +100,38 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_check(self.ctx, &mut bad, &mut first) })?;
         Ok((bad, if first == u64::MAX { None } else { Some(first) }))
     }
+    /// Rows and variables appended so far (`circuit_size()`, `variables.len()`).
+    pub fn counts(&self) -> (u64, u64) {
+        let (mut rows, mut vars) = (0, 0);
+        unsafe { sys::pg_counts(self.ctx, &mut rows, &mut vars) };
+        (rows, vars)
+    }
+    /// log2 of `EvaluationDomain::new(circuit_size).size()`.
+    pub fn domain_log_size(&self) -> u32 {
+        self.counts().0.next_power_of_two().trailing_zeros()
+    }
+    /// Prover round 1, first half: coefficients of w_l, w_r, w_o, w_4 (`domain.ifft` of the zero-padded wire columns),
+    /// four vectors of 2^log_n scalars.
+    pub fn wire_polynomials(&mut self, log_n: u32) -> Result<Vec<Vec<BlsScalar>>, EngineError> {
+        let n = 1usize << log_n;
+        let mut flat = vec![BlsScalar::zero(); 4 * n];
+        self.ok(unsafe { sys::pg_wire_polynomials(self.ctx, log_n, flat.as_mut_ptr() as *mut sys::pg_fr, 0) })?;
+        Ok(flat.chunks(n).map(|c| c.to_vec()).collect())
+    }
+    /// Prover round 1, second half: `commit_key.commit(&w_l_poly)` .. `w_4`.  `powers_of_g` are the CommitKey's G1Affine
+    /// powers in the layout of `sys::pg_g1_affine` (x, y Montgomery limbs; all-zero = infinity).
+    pub fn commit_wire_polynomials(&mut self, log_n: u32, powers_of_g: &[sys::pg_g1_affine]) -> Result<[sys::pg_g1_affine; 4], EngineError> {
+        let mut out = [sys::pg_g1_affine::default(); 4];
+        self.ok(unsafe { sys::pg_commit_wire_polynomials(self.ctx, log_n, powers_of_g.as_ptr(), powers_of_g.len() as u64, 0, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+    /// `msm_variable_base(points, scalars)`.
+    pub fn msm(&mut self, points: &[sys::pg_g1_affine], scalars: &[BlsScalar]) -> Result<sys::pg_g1_affine, EngineError> {
+        assert_eq!(points.len(), scalars.len());
+        let mut out = sys::pg_g1_affine::default();
+        self.ok(unsafe { sys::pg_msm(self.ctx, points.len() as u64, points.as_ptr(), as_fr(scalars), &mut out, 0) })?;
+        Ok(out)
+    }
     /// `composer.variables[var]` of a column.
     pub fn values(&mut self, v: Variables) -> Result<Vec<BlsScalar>, EngineError> {
         let mut out = vec![BlsScalar::zero(); v.n as usize];
