@@ -892,7 +892,14 @@ public:
         MsmDigitsBody::Args dg{d_scalars, keys, vals, n, plan.c, plan.n_windows};
         if (!be.template run_simple<MsmDigitsBody>(dg, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm digits kernel");
         if (!be.sort_pairs(keys, vals, keys2, vals2, count, key_bits)) return fail(PG_ERR_CUDA, "msm sort");
-        MsmBucketBody::Args bk{keys2, vals2, d_points, buckets, count, n_buckets, plan.c};
+        unsigned long long* start = (unsigned long long*)tmp(n_buckets * 8);
+        uint32_t* size_key = (uint32_t*)tmp(n_buckets * 4); uint32_t* ids = (uint32_t*)tmp(n_buckets * 4);
+        uint32_t* size_key2 = (uint32_t*)tmp(n_buckets * 4); uint32_t* ids2 = (uint32_t*)tmp(n_buckets * 4);
+        if (!start || !size_key || !ids || !size_key2 || !ids2) return fail(PG_ERR_OOM, "msm buffers");
+        MsmBoundsBody::Args bd{keys2, start, size_key, ids, count, n_buckets, plan.c};
+        if (!be.template run_simple<MsmBoundsBody>(bd, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm bounds kernel");
+        if (!be.sort_pairs(size_key, ids, size_key2, ids2, n_buckets, 32)) return fail(PG_ERR_CUDA, "msm bucket-order sort");
+        MsmBucketBody::Args bk{ids2, size_key2, start, vals2, d_points, buckets, n_buckets};
         if (!be.run_msm_buckets(bk)) return fail(PG_ERR_CUDA, "msm bucket kernel");
         MsmChunkBody::Args ck{buckets, ping, n_chunks, plan.c, plan.chunk};
         if (!be.template run_simple<MsmChunkBody>(ck, n_chunks, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm chunk kernel");

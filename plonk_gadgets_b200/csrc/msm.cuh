@@ -6,8 +6,11 @@
 //   1. k_simple<MsmDigitsBody>    scalars out of Montgomery form, cut into W = ceil(255/c) unsigned c-bit digits;
 //                                 one (key = window*2^c + digit, value = point index) pair per scalar and window;
 //   2. sort_pairs                 radix sort of the W*n pairs by key (CUB on the device): every bucket becomes a contiguous run;
-//   3. k_simple<MsmBucketBody>    one thread per (window, digit) bucket: binary search of its run, mixed additions of its
-//                                 points into an XYZZ accumulator -- W*n additions in total, W*2^c independent threads;
+//   3. k_simple<MsmBoundsBody>    start and length of every bucket's run (binary search); a second, small radix sort orders the
+//                                 bucket ids by decreasing length;
+//      k_simple<MsmBucketBody>    one thread per (window, digit) bucket, in that order -- the lanes of a warp get buckets of
+//                                 (almost) equal length: mixed additions of the bucket's points into an XYZZ accumulator,
+//                                 W*n additions in total, W*2^c independent threads;
 //   4. k_simple<MsmChunkBody>     per window, chunks of L consecutive buckets: running-sum trick gives sum (d - lo) * B_d,
 //                                 plus lo * (sum B_d) by double-and-add on the small factor lo;
 //   5. k_simple<MsmSumBody>       tree of 16-way sums of the chunk results down to one point per window;
@@ -62,14 +65,32 @@ PG_HD uint64_t msm_lower_bound(const uint32_t* keys, uint64_t count, uint32_t ke
     return lo;
 }
 
-struct MsmBucketBody {
-    struct Args { const uint32_t* keys; const uint32_t* vals; const uint4* points; uint4* buckets; uint64_t count; uint64_t n; /* buckets */ uint32_t c; };
+// run of bucket b in the sorted pairs: start and length (digit 0 buckets get length 0: they contribute nothing).  The length is
+// also written as a sort key (descending) so that the bucket kernel can hand the lanes of a warp buckets of equal length.
+struct MsmBoundsBody {
+    struct Args { const uint32_t* keys; unsigned long long* start; uint32_t* size_key; uint32_t* ids; uint64_t count; uint64_t n; /* buckets */ uint32_t c; };
     PG_HD static void run(const Args& a, uint64_t b) {
-        G1X acc = g1x_inf();
-        if (b & ((1ull << a.c) - 1ull)) {                      // digit 0 contributes nothing
-            const uint64_t lo = msm_lower_bound(a.keys, a.count, (uint32_t)b);
-            for (uint64_t j = lo; j < a.count && a.keys[j] == (uint32_t)b; j++) acc = g1x_madd(acc, g1_affine_load(a.points, a.vals[j]));
+        uint64_t lo = 0, len = 0;
+        if (b & ((1ull << a.c) - 1ull)) {
+            lo = msm_lower_bound(a.keys, a.count, (uint32_t)b);
+            len = msm_lower_bound(a.keys, a.count, (uint32_t)b + 1u) - lo;
         }
+        a.start[b] = lo;
+        a.size_key[b] = 0xffffffffu - (uint32_t)(len > 0xffffffffull ? 0xffffffffull : len);
+        a.ids[b] = (uint32_t)b;
+    }
+};
+
+// One thread per bucket, buckets taken in order of decreasing length (ids sorted by size_key): mixed additions of the bucket's
+// points into an XYZZ accumulator.
+struct MsmBucketBody {
+    struct Args { const uint32_t* ids; const uint32_t* size_key; const unsigned long long* start; const uint32_t* vals; const uint4* points; uint4* buckets;
+                  uint64_t n; /* buckets */ };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        const uint32_t b = a.ids[t];
+        const uint64_t lo = a.start[b], len = 0xffffffffu - a.size_key[t];
+        G1X acc = g1x_inf();
+        for (uint64_t j = lo; j < lo + len; j++) acc = g1x_madd(acc, g1_affine_load(a.points, a.vals[j]));
         g1x_store(a.buckets, b, acc);
     }
 };
