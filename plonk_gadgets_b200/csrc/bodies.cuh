@@ -216,8 +216,10 @@ struct CheckArgs {
     uint64_t n_inst; uint64_t base_row;
     unsigned long long* counters;
     int mode;
-    const SpOp* sp; uint32_t n_sp;      // structure-aware row program of the segment (PG_CHECK_SPARSE), or null
 };
+// structure-aware row program of a segment (PG_CHECK_SPARSE), passed next to CheckArgs: the generic kernel's argument block and
+// code stay exactly as they were measured
+struct SparseProg { const SpOp* ops; uint32_t n; };
 
 // GENERIC mode evaluates  a*(q_m*b + q_l) + q_r*b + q_o*c + q_4*d + q_c + PI  -- the gate polynomial with the bilinear term
 // factored, five multiplications instead of six, still without looking at any selector value: one Montgomery
@@ -286,19 +288,26 @@ struct CheckBody {
     // gate equation of row `row` for instance i: true iff it holds
     template <int MODE, class PoolT>
     PG_HD static bool row_holds(const Args& a, const DevRow& row, const PoolT& pool, const QRegs& q, uint64_t i) {
+        if (MODE != 0) return row_holds_sparse(a, row, pool, q, i);
+        Fr w[5];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
         uint32_t t[9];
-        if (MODE == 0) {
-            Fr w[5];
+        Fr sel[4];
+        sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));   // q_m*b + q_l  (< 2q < 2^256)
 #pragma unroll
-            for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
-            Fr sel[4];
-            sel[0] = fr_add_noreduce(fr_mul_eo(pool(row.sel[0]), w[2], q), pool(row.sel[1]));   // q_m*b + q_l  (< 2q < 2^256)
-#pragma unroll
-            for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
-            fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
-        } else {
-            sparse_terms(t, row, pool, q, i);
-        }
+        for (int k = 1; k < 4; k++) sel[k] = pool(row.sel[k + 1]);                           // q_r q_o q_4
+        fr_dot_wide<4>(t, w + 1, sel, q);                                                     // a*u + b*q_r + c*q_o + d*q_4
+        add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));
+        if (row.pi_param >= 0) add9_fr(t, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
+        else if (row.pi_sel != POOL_ZERO) add9_fr(t, pool(row.pi_sel));
+        return limbs9_is_multiple_of_q(t);
+    }
+    // the same row through the structure-aware term evaluation (small segments; large ones run the compiled program)
+    template <class PoolT>
+    PG_HD static bool row_holds_sparse(const Args& a, const DevRow& row, const PoolT& pool, const QRegs& q, uint64_t i) {
+        uint32_t t[9];
+        sparse_terms(t, row, pool, q, i);
         add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));
         if (row.pi_param >= 0) add9_fr(t, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
         else if (row.pi_sel != POOL_ZERO) add9_fr(t, pool(row.pi_sel));
@@ -309,21 +318,13 @@ struct CheckBody {
     PG_HD static uint32_t run(const Args& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t bad = 0;
         for (uint32_t r = 0; r < a.n_rows; r++) {
+            const DevRow row = a.rows[r];
             if (r + 1 < a.n_rows) {            // request the next row's wire values now: ~2000 multiplier cycles cover the latency
                 const DevRow& nr = a.rows[r + 1];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (MODE != 0) {           // structure-aware: only the wires some non-zero selector reads
-                        const bool used = k == 0 ? (nr.sel[0] | nr.sel[1]) != 0 : k == 1 ? (nr.sel[0] | nr.sel[2]) != 0 : nr.sel[k + 1] != 0;
-                        if (!used) continue;
-                    }
-                    row_prefetch(nr.loc[k], nr.addr[k], i);
-                }
+                for (int k = 0; k < 4; k++) row_prefetch(nr.loc[k], nr.addr[k], i);
             }
-            bool ok;
-            if (MODE == 0) { const DevRow row = a.rows[r]; ok = row_holds<MODE>(a, row, pool, q, i); }
-            else ok = row_holds<MODE>(a, a.rows[r], pool, q, i);      // fields are read where needed (rolled term loop)
-            if (!ok) {
+            if (!row_holds<MODE>(a, row, pool, q, i)) {
                 bad++;
                 const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
                 if (g < first_bad) first_bad = g;
@@ -350,18 +351,18 @@ struct CheckBody {
 constexpr uint32_t SP_AHEAD = 12;
 struct SparseProgBody {
     template <class PoolT>
-    PG_HD static uint32_t run(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
+    PG_HD static uint32_t run(const CheckArgs& a, const SparseProg& prog, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t t[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) t[k] = 0;
         uint32_t mask = ~0u, bad = 0, r = 0;
         Fr v = fr_zero();
 #pragma unroll 1
-        for (uint32_t j = 0; j < a.n_sp; j++) {
-            const SpOp op = a.sp[j];
+        for (uint32_t j = 0; j < prog.n; j++) {
+            const SpOp op = prog.ops[j];
 #if defined(__CUDA_ARCH__)
-            if (j + SP_AHEAD < a.n_sp) {
-                const SpOp& nx = a.sp[j + SP_AHEAD];
+            if (j + SP_AHEAD < prog.n) {
+                const SpOp& nx = prog.ops[j + SP_AHEAD];
                 if (nx.addr) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx.addr + i * nx.stride));
             }
 #endif

@@ -68,13 +68,16 @@ public:
     bool set_check_attrs() {
         PG_CUDA(cudaFuncSetAttribute(k_check<0, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k_check<1, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PG_CUDA(cudaFuncSetAttribute(k_check_prog<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         return true;
     }
     template <int SHAPE>
-    void launch_check(const CheckArgs& a, size_t smem) {
+    void launch_check(const CheckArgs& a, const SparseProg& prog, size_t smem) {
         constexpr int T = CheckShape<SHAPE>::BLOCK_T;
         const unsigned grid = (unsigned)((a.n_inst + T - 1) / T);
-        if (a.mode == PG_CHECK_SPARSE) k_check<1, SHAPE><<<grid, T, smem, stream>>>(a); else k_check<0, SHAPE><<<grid, T, smem, stream>>>(a);
+        if (a.mode == PG_CHECK_SPARSE && prog.ops) k_check_prog<SHAPE><<<grid, T, smem, stream>>>(a, prog);       // compiled row program
+        else if (a.mode == PG_CHECK_SPARSE) k_check<1, SHAPE><<<grid, T, smem, stream>>>(a);
+        else k_check<0, SHAPE><<<grid, T, smem, stream>>>(a);
     }
     void shutdown() {
         for (auto& ev : events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -189,7 +192,7 @@ public:
         toc();
         return launched("k_batch_inv");
     }
-    bool run_check(const CheckArgs& a) {
+    bool run_check(const CheckArgs& a, const SparseProg& prog) {
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         tic(CLS_CHECK, a.n_inst * a.n_rows);
@@ -202,9 +205,9 @@ public:
         }
         // the structure-aware check needs few registers and is latency-bound: 32 warps/SM unless a shape was asked for
         switch (a.mode == PG_CHECK_SPARSE && check_shape == 0 ? 4 : check_shape) {
-            case 1: launch_check<1>(a, smem); break; case 2: launch_check<2>(a, smem); break;
-            case 3: launch_check<3>(a, smem); break; case 4: launch_check<4>(a, smem); break;
-            default: launch_check<0>(a, smem); break;
+            case 1: launch_check<1>(a, prog, smem); break; case 2: launch_check<2>(a, prog, smem); break;
+            case 3: launch_check<3>(a, prog, smem); break; case 4: launch_check<4>(a, prog, smem); break;
+            default: launch_check<0>(a, prog, smem); break;
         }
         toc();
         return launched("k_check");

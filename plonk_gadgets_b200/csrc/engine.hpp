@@ -12,7 +12,7 @@
 //   bool d2d(void*, const void*, size_t), bool sync()
 //   template<class Body> bool run_simple(const typename Body::Args&, uint64_t n, int cls)
 //   bool run_batch_inv(const BatchInvArgs&, int cls)            -- out_slot = in_slot^-1 (or 0) over table slots
-//   bool run_check(const CheckArgs&), bool run_check_rows(const CheckRowsBody::Args&)
+//   bool run_check(const CheckArgs&, const SparseProg&), bool run_check_rows(const CheckRowsBody::Args&)
 //   bool sort_pairs(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t n, uint32_t key_bits)
 //   bool run_msm_buckets(const MsmBucketBody::Args&)             -- one thread per bucket (launch shape chosen by the backend)
 //   bool run_ntt_pass(const NttPassArgs&, uint64_t n_blocks)    -- one group of butterfly stages over all tiles (ntt.cuh)
@@ -511,8 +511,8 @@ public:
             a.param = s.param; a.param_stride = s.n_alloc; a.rows = s.d_rows; a.pool = s.d_pool;
             a.n_rows = (uint32_t)s.t.rows.size(); a.n_pool = (uint32_t)s.t.pool.size();
             a.n_inst = s.n_inst; a.base_row = s.base_row; a.counters = d_counters; a.mode = cfg.check_mode;
-            a.sp = s.d_sp; a.n_sp = (uint32_t)s.sp_ops.size();
-            if (!be.run_check(a)) return fail(PG_ERR_CUDA, "gate-check kernel");
+            const SparseProg prog{s.d_sp, (uint32_t)s.sp_ops.size()};
+            if (!be.run_check(a, prog)) return fail(PG_ERR_CUDA, "gate-check kernel");
         }
         unsigned long long c[CNT_WORDS];
         if ((rc = read_counters(c))) return rc;

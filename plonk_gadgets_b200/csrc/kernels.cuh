@@ -139,12 +139,36 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
     const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
-    if (i < a.n_inst) {
-        SmemPool pool = {s_pool};
-        if (MODE == 1 && a.sp) bad = SparseProgBody::run(a, pool, q, i, first_bad);     // compiled row program (layout.h, SpOp)
-        else bad = CheckBody::run<MODE>(a, pool, q, i, first_bad);
-    }
+    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, q, i, first_bad); }
     // warp-level reduction, then one atomic per warp that saw a violation
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, first_bad, o);
+        first_bad = other < first_bad ? other : first_bad;
+    }
+    if ((threadIdx.x & 31) == 0 && bad) {
+        atomicAdd(a.counters + CNT_UNSAT, (unsigned long long)bad);
+        atomicMin(a.counters + CNT_FIRST_BAD, first_bad);
+    }
+}
+
+// The structure-aware check as a compiled row program (layout.h SpOp, bodies.cuh SparseProgBody); same skeleton as k_check.
+template <int SHAPE>
+__global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>::MIN_BLOCKS) k_check_prog(const CheckArgs a, const SparseProg prog) {
+    constexpr int CHECK_BLOCK = CheckShape<SHAPE>::BLOCK_T;
+    extern __shared__ __align__(16) uint32_t s_pool[];
+    __shared__ uint32_t s_q[8];
+    for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += CHECK_BLOCK) s_pool[t] = a.pool[t];
+    if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
+    __syncthreads();
+    QRegs q;
+#pragma unroll
+    for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
+    const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
+    unsigned long long first_bad = ~0ull;
+    uint32_t bad = 0;
+    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = SparseProgBody::run(a, prog, pool, q, i, first_bad); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         bad += __shfl_xor_sync(0xffffffffu, bad, o);

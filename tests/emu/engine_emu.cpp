@@ -53,7 +53,7 @@ public:
             }
         return true;
     }
-    bool run_check(const CheckArgs& a) {
+    bool run_check(const CheckArgs& a, const SparseProg& prog) {
         HostPool pool = {a.pool};
         const QRegs q = q_regs_default();
         if (a.n_inst < 48 && a.n_rows > 1) {            // the row-parallel mapping (thread = one row of one instance), as for small segments on the GPU
@@ -66,7 +66,7 @@ public:
         }
         for (uint64_t i = 0; i < a.n_inst; i++) {
             unsigned long long fb = ~0ull;
-            const uint32_t bad = a.mode ? (a.sp ? SparseProgBody::run(a, pool, q, i, fb) : CheckBody::run<1>(a, pool, q, i, fb)) : CheckBody::run<0>(a, pool, q, i, fb);
+            const uint32_t bad = a.mode ? (prog.ops ? SparseProgBody::run(a, prog, pool, q, i, fb) : CheckBody::run<1>(a, pool, q, i, fb)) : CheckBody::run<0>(a, pool, q, i, fb);
             if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
         }
         return true;
