@@ -220,6 +220,7 @@ struct CheckArgs {
 // structure-aware row program of a segment (PG_CHECK_SPARSE), passed next to CheckArgs: the generic kernel's argument block and
 // code stay exactly as they were measured
 struct SparseProg { const SpOp* ops; uint32_t n; };
+struct CheckProgArgs { CheckArgs a; SparseProg prog; };      // one argument block for k_check_prog
 
 // GENERIC mode evaluates  a*(q_m*b + q_l) + q_r*b + q_o*c + q_4*d + q_c + PI  -- the gate polynomial with the bilinear term
 // factored, five multiplications instead of six, still without looking at any selector value: one Montgomery

@@ -75,7 +75,7 @@ public:
     void launch_check(const CheckArgs& a, const SparseProg& prog, size_t smem) {
         constexpr int T = CheckShape<SHAPE>::BLOCK_T;
         const unsigned grid = (unsigned)((a.n_inst + T - 1) / T);
-        if (a.mode == PG_CHECK_SPARSE && prog.ops) k_check_prog<SHAPE><<<grid, T, smem, stream>>>(a, prog);       // compiled row program
+        if (a.mode == PG_CHECK_SPARSE && prog.ops) { const CheckProgArgs pa{a, prog}; k_check_prog<SHAPE><<<grid, T, smem, stream>>>(pa); }   // compiled row program
         else if (a.mode == PG_CHECK_SPARSE) k_check<1, SHAPE><<<grid, T, smem, stream>>>(a);
         else k_check<0, SHAPE><<<grid, T, smem, stream>>>(a);
     }
@@ -203,7 +203,7 @@ public:
             toc();
             return launched("k_check_rowpar");
         }
-        // the structure-aware check needs few registers and is latency-bound: 32 warps/SM unless a shape was asked for
+        // the structure-aware check needs few registers and is issue- and latency-bound: 32 warps/SM (64 registers) measured best, unless a shape was asked for
         switch (a.mode == PG_CHECK_SPARSE && check_shape == 0 ? 4 : check_shape) {
             case 1: launch_check<1>(a, prog, smem); break; case 2: launch_check<2>(a, prog, smem); break;
             case 3: launch_check<3>(a, prog, smem); break; case 4: launch_check<4>(a, prog, smem); break;

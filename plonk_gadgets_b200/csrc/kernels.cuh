@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
 
 // The structure-aware check as a compiled row program (layout.h SpOp, bodies.cuh SparseProgBody); same skeleton as k_check.
 template <int SHAPE>
-__global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>::MIN_BLOCKS) k_check_prog(const CheckArgs a, const SparseProg prog) {
+__global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>::MIN_BLOCKS) k_check_prog(const CheckProgArgs args) {
+    const CheckArgs& a = args.a; const SparseProg& prog = args.prog;
     constexpr int CHECK_BLOCK = CheckShape<SHAPE>::BLOCK_T;
     extern __shared__ __align__(16) uint32_t s_pool[];
     __shared__ uint32_t s_q[8];
@@ -168,7 +169,11 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
     const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
-    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = SparseProgBody::run(a, prog, pool, q, i, first_bad); }
+    if (i < a.n_inst) {
+        SmemPool pool = {s_pool};
+        if (prog.ops) bad = SparseProgBody::run(a, prog, pool, q, i, first_bad);
+        else bad = CheckBody::run<1>(a, pool, q, i, first_bad);                   // no program: per-row evaluation
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         bad += __shfl_xor_sync(0xffffffffu, bad, o);
