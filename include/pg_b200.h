@@ -199,6 +199,15 @@ int pg_srs_powers(pg_ctx *ctx, const pg_fr *beta, const pg_g1_affine *base, uint
 int pg_g1_fixed_base_mul(pg_ctx *ctx, uint64_t n, const pg_g1_affine *base, const pg_fr *scalars, pg_g1_affine *out, int on_device);
 int pg_commit_wire_polynomials(pg_ctx *ctx, uint32_t log_n, const pg_g1_affine *powers_of_g, uint64_t n_powers, int powers_on_device,
                                pg_g1_affine *out4);
+/* Evaluation-form commitments.  With the Lagrange-basis form of the SRS for a domain, lagrange[i] = L_i(beta) * base, the
+ * commitment of a polynomial is sum_i f(w^i) * lagrange[i] -- the same group element as sum_j coeff_j * powers_of_g[j] -- so the
+ * wire commitments can be taken from the wire VALUES directly: no FFT, and bits / short accumulators leave most windows empty.
+ * pg_srs_lagrange builds that form for local setups that know beta (like PublicParameters::setup; PG_ERR_ARG if beta lies on the
+ * domain); deriving it from monomial powers alone needs a group FFT (not built).  pg_commit_wire_evaluations returns the same four
+ * points as pg_commit_wire_polynomials; n_points must be exactly 2^log_n. */
+int pg_srs_lagrange(pg_ctx *ctx, const pg_fr *beta, const pg_g1_affine *base, uint32_t log_n, pg_g1_affine *out, int out_on_device);
+int pg_commit_wire_evaluations(pg_ctx *ctx, uint32_t log_n, const pg_g1_affine *lagrange, uint64_t n_points, int points_on_device,
+                               pg_g1_affine *out4);
 /* self-test helper: op 0: out[i] = a[i] + b[i]; op 1: out[i].x[0] = 1 if a[i] is on the curve (or infinity) else 0.  Host buffers. */
 int pg_g1_op(pg_ctx *ctx, int op, uint64_t n, const pg_g1_affine *a, const pg_g1_affine *b, pg_g1_affine *out);
 

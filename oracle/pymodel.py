@@ -418,3 +418,24 @@ def srs_powers(beta: int, n: int, base=G1_GENERATOR):
         out.append(g1_mul(e, base))
         e = e * beta % Q
     return out
+
+
+def lagrange_at(beta: int, log_n: int):
+    """L_i(beta), i < 2^log_n, for the domain generated by group_gen(log_n), from the defining products
+    L_i(X) = prod_{j != i} (X - w^j) / (w^i - w^j)."""
+    n = 1 << log_n
+    w = group_gen(log_n)
+    pts = [pow(w, i, Q) for i in range(n)]
+    out = []
+    for i in range(n):
+        num = den = 1
+        for j in range(n):
+            if j != i:
+                num = num * (beta - pts[j]) % Q
+                den = den * (pts[i] - pts[j]) % Q
+        out.append(num * pow(den, -1, Q) % Q)
+    return out
+
+
+def srs_lagrange(beta: int, log_n: int, base=G1_GENERATOR):
+    return [g1_mul(s, base) for s in lagrange_at(beta, log_n)]

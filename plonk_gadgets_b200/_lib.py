@@ -67,6 +67,8 @@ SIGNATURES = {
     "pg_srs_powers": (_i32, [_vp, _vp, _vp, _u64, _vp, _i32]),
     "pg_g1_fixed_base_mul": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32]),
     "pg_commit_wire_polynomials": (_i32, [_vp, _u32, _vp, _u64, _i32, _vp]),
+    "pg_srs_lagrange": (_i32, [_vp, _vp, _vp, _u32, _vp, _i32]),
+    "pg_commit_wire_evaluations": (_i32, [_vp, _u32, _vp, _u64, _i32, _vp]),
     "pg_g1_op": (_i32, [_vp, _i32, _u64, _vp, _vp, _vp]),
     "pg_fr_to_bytes": (_i32, [_vp, _u64, _vp, _vp, _i32]),
     "pg_fr_from_bytes": (_i32, [_vp, _u64, _vp, _vp, _i32, _pu64, _pu64]),

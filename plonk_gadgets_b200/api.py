@@ -325,6 +325,26 @@ class StandardComposer:
         self._ok(self._L.pg_commit_wire_polynomials(self._ctx, log_n, pp, n, pdev, out.ctypes.data_as(C.c_void_p)), "pg_commit_wire_polynomials")
         return out
 
+    def srs_lagrange(self, beta, log_n: int, base=None, out=None):
+        """Lagrange-basis SRS of the domain 2^log_n: out[i] = L_i(beta) * base (local setups that know beta)."""
+        b = np.ascontiguousarray(beta, dtype=np.uint64).reshape(4)
+        bp = None if base is None else np.ascontiguousarray(base, dtype=np.uint64).reshape(12)
+        bptr = None if bp is None else bp.ctypes.data_as(C.c_void_p)
+        if out is not None:
+            self._ok(self._L.pg_srs_lagrange(self._ctx, b.ctypes.data_as(C.c_void_p), bptr, log_n, C.c_void_p(out.data_ptr()), 1), "pg_srs_lagrange")
+            return out
+        res = np.zeros((1 << log_n, 12), dtype=np.uint64)
+        self._ok(self._L.pg_srs_lagrange(self._ctx, b.ctypes.data_as(C.c_void_p), bptr, log_n, res.ctypes.data_as(C.c_void_p), 0), "pg_srs_lagrange")
+        return res
+
+    def commit_wire_evaluations(self, lagrange, log_n: int | None = None) -> np.ndarray:
+        """(4, 12) uint64: the commitments of commit_wire_polynomials, computed from the wire values against a Lagrange-basis SRS."""
+        log_n = self.domain_log_size() if log_n is None else log_n
+        pp, pdev, n, _keep = self._points(lagrange)
+        out = np.zeros((4, 12), dtype=np.uint64)
+        self._ok(self._L.pg_commit_wire_evaluations(self._ctx, log_n, pp, n, pdev, out.ctypes.data_as(C.c_void_p)), "pg_commit_wire_evaluations")
+        return out
+
     def g1_op(self, op: int, a, b=None) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 12)
         b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 12) if b is not None else None

@@ -129,6 +129,14 @@ int pg_commit_wire_polynomials(pg_ctx* ctx, uint32_t log_n, const pg_g1_affine* 
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, powers_of_g, powers_on_device);
     return ctx->e.commit_wire_polynomials(log_n, powers_of_g, n_powers, powers_on_device, out4);
 }
+int pg_srs_lagrange(pg_ctx* ctx, const pg_fr* beta, const pg_g1_affine* base, uint32_t log_n, pg_g1_affine* out, int out_on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, out, out_on_device);
+    return ctx->e.srs_lagrange(beta, base, log_n, out, out_on_device);
+}
+int pg_commit_wire_evaluations(pg_ctx* ctx, uint32_t log_n, const pg_g1_affine* lagrange, uint64_t n_points, int points_on_device, pg_g1_affine* out4) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, lagrange, points_on_device);
+    return ctx->e.commit_wire_evaluations(log_n, lagrange, n_points, points_on_device, out4);
+}
 int pg_g1_op(pg_ctx* ctx, int op, uint64_t n, const pg_g1_affine* a, const pg_g1_affine* b, pg_g1_affine* out) { PG_NEED_CTX(ctx); return ctx->e.g1_op(op, n, a, b, out); }
 int pg_fr_to_bytes(pg_ctx* ctx, uint64_t n, const pg_fr* src, uint8_t* dst, int on_device) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, src, on_device); PG_ALIGNED(ctx, dst, on_device);

@@ -945,6 +945,19 @@ public:
         release_scratch_from(mark);
         return rc;
     }
+    // the same with the scalars already in device memory and the result in host or device memory
+    int g1_fixed_base_mul_dev(uint64_t n, const pg_g1_affine* base, const uint4* d_scalars, pg_g1_affine* out, int out_on_device) {
+        const size_t mark = scratch.size();
+        uint4* d_out = reinterpret_cast<uint4*>(out);
+        if (!out_on_device) { d_out = (uint4*)dalloc(n * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "point buffer"); scratch.push_back(d_out); }
+        G1FixedBaseMulBody::Args a; a.scalars = d_scalars; a.out = d_out; a.n = n;
+        if (base) memcpy(&a.base, base, sizeof(G1Affine)); else a.base = g1_generator();
+        if (!be.template run_simple<G1FixedBaseMulBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base kernel");
+        if (out_on_device) return PG_OK;
+        const int rc = deliver(out, d_out, n * sizeof(pg_g1_affine), 0);
+        release_scratch_from(mark);
+        return rc;
+    }
     // powers_of_g[i] = beta^i * base, i < n  (PublicParameters::setup)
     int srs_powers(const pg_fr* beta, const pg_g1_affine* base, uint64_t n, pg_g1_affine* out, int out_on_device) {
         if (!beta || (n && !out)) return fail(PG_ERR_ARG, "srs_powers: null argument");
@@ -973,6 +986,53 @@ public:
         if ((rc = wire_polynomials(log_n, reinterpret_cast<pg_fr*>(polys), 1))) return rc;
         for (int w = 0; w < 4; w++)
             if ((rc = msm_dev(n, dp, polys + 2 * (uint64_t)w * n, d_out + 6 * w))) return rc;
+        rc = deliver(out, d_out, 4 * sizeof(pg_g1_affine), 0);
+        release_scratch_from(mark);
+        return rc;
+    }
+    // out[i] = L_i(beta) * base, i < 2^log_n: the Lagrange-basis form of the SRS for that domain (test / local setups that know
+    // beta, like PublicParameters::setup; deriving it from monomial powers alone needs a group FFT, not built)
+    int srs_lagrange(const pg_fr* beta, const pg_g1_affine* base, uint32_t log_n, pg_g1_affine* out, int out_on_device) {
+        if (!beta || !out || log_n > NTT_TWO_ADICITY) return fail(PG_ERR_ARG, "srs_lagrange: null argument or domain larger than 2^32");
+        const uint64_t n = 1ull << log_n;
+        int rc = log_n ? ntt_twiddles(log_n) : PG_OK;
+        if (rc) return rc;
+        const size_t mark = scratch.size();
+        uint4* sc = (uint4*)dalloc(n * sizeof(pg_fr)); if (!sc) return fail(PG_ERR_OOM, "lagrange scalars"); scratch.push_back(sc);
+        LagrangeScalarsBody::Args a; a.tw = ntt_tw; a.out = sc; a.n = n; a.log_n = log_n;
+        memcpy(&a.beta, beta, sizeof(Fr));
+        Fr bn = a.beta;                                                  // beta^n by log_n squarings
+        for (uint32_t k = 0; k < log_n; k++) bn = fr_sqr(bn);
+        const Fr z = fr_sub(bn, fr_one());                               // Z_H(beta) = beta^n - 1
+        if (fr_is_zero(z)) return fail(PG_ERR_ARG, "srs_lagrange: beta lies on the evaluation domain");
+        Fr raw = fr_zero(); raw.v[0] = (uint32_t)n; raw.v[1] = (uint32_t)(n >> 32);
+        a.c = fr_mul(z, fr_inv_fermat(fr_to_mont(raw)));
+        if (!be.template run_simple<LagrangeScalarsBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "lagrange scalar kernel");
+        if ((rc = g1_fixed_base_mul_dev(n, base, sc, out, out_on_device))) return rc;
+        if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
+        release_scratch_from(mark);
+        return PG_OK;
+    }
+    // The four wire commitments from the wire VALUES (evaluation form) against a Lagrange-basis SRS: same group elements as
+    // commit_wire_polynomials against the monomial powers of the same beta, without any FFT and with mostly-empty windows.
+    int commit_wire_evaluations(uint32_t log_n, const pg_g1_affine* lagrange, uint64_t n_points, int points_on_device, pg_g1_affine* out) {
+        if (!lagrange || !out) return fail(PG_ERR_ARG, "commit_wire_evaluations: null argument");
+        if (log_n > NTT_TWO_ADICITY || (1ull << log_n) < n_rows) return fail(PG_ERR_ARG, "commit_wire_evaluations: domain smaller than the circuit or larger than 2^32");
+        const uint64_t n = 1ull << log_n;
+        if (n_points != n) return fail(PG_ERR_ARG, "commit_wire_evaluations: a Lagrange-basis SRS belongs to exactly one domain size");
+        const size_t mark = scratch.size();
+        int rc; const uint4* dp = stage_bytes(lagrange, n * sizeof(pg_g1_affine), points_on_device, &rc); if (!dp) return rc;
+        uint4* vals = (uint4*)dalloc(4 * n * sizeof(pg_fr)); if (!vals) return fail(PG_ERR_OOM, "wire value buffer"); scratch.push_back(vals);
+        uint4* d_out = (uint4*)dalloc(4 * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "commitments"); scratch.push_back(d_out);
+        if ((rc = materialize_dev(0, n_rows, n, nullptr, vals, nullptr, nullptr))) return rc;       // to_scalars(w_l..w_4)
+        for (int w = 0; w < 4; w++) {
+            uint4* col = vals + 2 * (uint64_t)w * n;
+            if (n > n_rows) {
+                NttZeroBody::Args z{col, n_rows, n - n_rows};
+                if (!be.template run_simple<NttZeroBody>(z, z.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "padding kernel");
+            }
+            if ((rc = msm_dev(n, dp, col, d_out + 6 * w))) return rc;
+        }
         rc = deliver(out, d_out, 4 * sizeof(pg_g1_affine), 0);
         release_scratch_from(mark);
         return rc;

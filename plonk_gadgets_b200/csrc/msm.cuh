@@ -147,6 +147,20 @@ struct G1FixedBaseMulBody {
     }
 };
 
+// Lagrange-basis SRS scalars: L_i(beta) = (beta^n - 1) / n * w^i / (beta - w^i), i < n, for the domain generated by w
+// (w^i from the NTT twiddle table: w^(i + n/2) = -w^i).  With powers [L_i(beta)] G a commitment can be computed from the
+// EVALUATIONS of a polynomial over the domain -- sum_i f(w^i) [L_i(beta)] G is the same group element as
+// sum_j coeff_j [beta^j] G -- and wire values are mostly bits and short accumulators: most of their windows are empty.
+struct LagrangeScalarsBody {
+    struct Args { const uint4* tw; uint4* out; uint64_t n; uint32_t log_n; Fr beta, c; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        Fr w = fr_one();
+        if (a.log_n) { const uint64_t h = a.n >> 1; w = i < h ? aos_load(a.tw, i) : fr_neg(aos_load(a.tw, i - h)); }
+        const Fr d = fr_sub(a.beta, w);
+        aos_store(a.out, i, fr_is_zero(d) ? fr_zero() : fr_mul(fr_mul(a.c, w), fr_inv_fermat(d)));   // beta on the domain is rejected by the caller
+    }
+};
+
 // group-law self-test entry (pg_g1_op): 0 = a + b (affine in, affine out), 1 = on-curve flag of a
 struct G1OpBody {
     struct Args { const uint4* a; const uint4* b; uint4* out; uint64_t n; int op; };

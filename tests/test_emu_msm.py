@@ -136,3 +136,29 @@ def test_emu_argument_errors(emu, oracle, golden):
         c.fft(np.zeros((3, 4), dtype=np.uint64))                             # not a power of two
     with pytest.raises(ValueError):
         c.msm(srs[:4], oracle.from_ints([1, 2, 3]))                          # length mismatch
+
+
+def test_emu_lagrange_srs_and_evaluation_commitments(emu, oracle, golden):
+    """Lagrange-basis SRS against the defining products of the big-int model, and the commitments taken from the wire VALUES
+    against it equal the commitments of the wire POLYNOMIALS against the monomial powers of the same beta (and the oracle's)."""
+    from oracle import pymodel as pm
+    c0 = pg.StandardComposer(_cdll=emu)
+    beta_i = 0x1d0c3a5e7f9b2468ace013579bdf02468ace13579bdf048c159d26ae37bf48c1 % Q
+    beta = oracle.from_ints([beta_i])
+    for log_n in (0, 1, 3, 4):
+        got = oracle.g1_to_ints(to_oracle(c0.srs_lagrange(beta[0], log_n)))
+        assert got == pm.srs_lagrange(beta_i, log_n), log_n
+    with pytest.raises(pg.EngineError):
+        c0.srs_lagrange(oracle.from_ints([pm.group_gen(3)])[0], 3)            # beta on the domain
+    for name in ("kat_range_check_0_ok", "batch_is_non_zero_maybe_equal", "kat_max_bound_0_ok"):
+        _s, oc = run_oracle(golden[name]["program"], return_composer=True)
+        _snap, c = run_engine(golden[name]["program"], lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
+        k = c.domain_log_size()
+        mono, lag = c.srs_powers(beta[0], 1 << k), c.srs_lagrange(beta[0], k)
+        from_values = c.commit_wire_evaluations(lag)
+        assert np.array_equal(from_values, c.commit_wire_polynomials(mono)), name
+        polys = oc.wire_polynomials()
+        for w in range(4):
+            assert np.array_equal(to_oracle(from_values[w:w + 1]), oracle.g1_msm(to_oracle(mono), polys[w])), (name, w)
+        with pytest.raises(pg.EngineError):
+            c.commit_wire_evaluations(lag, log_n=k + 1)                       # a Lagrange SRS belongs to one domain size

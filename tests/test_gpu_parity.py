@@ -595,3 +595,35 @@ def test_fft_round_trip_2p27(oracle, torch_cuda):
     c.fft(lo); c.fft(hi); c.sync()
     s = c.fr_op(1, lo[idx].cpu().numpy().view(np.uint64), hi[idx].cpu().numpy().view(np.uint64))
     assert np.array_equal(s, even)
+
+
+def test_evaluation_form_commitments_gpu(oracle, golden, torch_cuda):
+    """pg_commit_wire_evaluations (wire values x Lagrange-basis SRS, no FFT) returns the same four group elements as
+    pg_commit_wire_polynomials (coefficients x monomial powers): on a golden program against the oracle too, and on a batch of
+    1500 range_check instances (domain 2^19) with device-resident SRS forms."""
+    from tests.test_emu_msm import to_oracle
+    from oracle import pymodel as pm
+    torch = torch_cuda
+    beta_i = 0x1d0c3a5e7f9b2468ace013579bdf02468ace13579bdf048c159d26ae37bf48c1 % Q
+    beta = oracle.from_ints([beta_i])
+    c0 = gpu_composer()
+    assert oracle.g1_to_ints(to_oracle(c0.srs_lagrange(beta[0], 4))) == pm.srs_lagrange(beta_i, 4)
+    _s, oc = run_oracle(golden["kat_range_check_0_ok"]["program"], return_composer=True)
+    _snap, c = run_engine(golden["kat_range_check_0_ok"]["program"], gpu_composer, oracle, return_composer=True)
+    k = c.domain_log_size()
+    mono = c.srs_powers(beta[0], 1 << k)
+    got = c.commit_wire_evaluations(c.srs_lagrange(beta[0], k))
+    assert np.array_equal(got, c.commit_wire_polynomials(mono))
+    polys = oc.wire_polynomials()
+    assert all(np.array_equal(to_oracle(got[w:w + 1]), oracle.g1_msm(to_oracle(mono), polys[w])) for w in range(4))
+    # batch, device-resident
+    n = 1500
+    c = gpu_composer()
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 2, 2, 64, wit)
+    w = c.add_input(wit)
+    pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
+    k = c.domain_log_size(); assert k == 19
+    mono = torch.empty((1 << k, 12), dtype=torch.int64, device="cuda"); lag = torch.empty_like(mono); torch.cuda.synchronize()
+    c.srs_powers(beta[0], 1 << k, out=mono); c.srs_lagrange(beta[0], k, out=lag)
+    a, b = c.commit_wire_evaluations(lag), c.commit_wire_polynomials(mono)
+    assert np.array_equal(a, b) and a.any()
