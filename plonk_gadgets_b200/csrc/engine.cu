@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <new>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "engine.hpp"
 #include "kernels.cuh"
 
@@ -218,6 +219,19 @@ public:
         k_materialize_tiled<<<(unsigned)tiles, BLOCK, 0, stream>>>(a);
         toc();
         return launched("k_materialize_tiled");
+    }
+    bool exclusive_sum(const uint32_t* in, uint32_t* out, uint64_t n) {
+        size_t need = 0;
+        PG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (long long)n, stream));
+        if (need > sort_tmp_bytes) {
+            if (sort_tmp) { PG_CUDA(cudaStreamSynchronize(stream)); cudaFree(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0; }
+            PG_CUDA(cudaMalloc(&sort_tmp, need));
+            sort_tmp_bytes = need;
+        }
+        tic(CLS_OTHER, 0);
+        PG_CUDA(cub::DeviceScan::ExclusiveSum(sort_tmp, need, in, out, (long long)n, stream));
+        toc();
+        return launched("cub::DeviceScan::ExclusiveSum");
     }
     // radix sort of (key, value) pairs by the low key_bits of the key (CUB; temporary storage kept for the context's lifetime)
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0;

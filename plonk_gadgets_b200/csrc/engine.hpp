@@ -14,7 +14,8 @@
 //   bool run_batch_inv(const BatchInvArgs&, int cls)            -- out_slot = in_slot^-1 (or 0) over table slots
 //   bool run_check(const CheckArgs&, const SparseProg&), bool run_check_rows(const CheckRowsBody::Args&)
 //   bool sort_pairs(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t n, uint32_t key_bits)
-//   bool run_msm_buckets(const MsmBucketBody::Args&)             -- one thread per bucket (launch shape chosen by the backend)
+//   bool run_msm_buckets(const MsmBucketBody::Args&)             -- one thread per part of a bucket run (launch shape chosen by the backend)
+//   bool exclusive_sum(const uint32_t* in, uint32_t* out, uint64_t n)
 //   bool run_ntt_pass(const NttPassArgs&, uint64_t n_blocks)    -- one group of butterfly stages over all tiles (ntt.cuh)
 //   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), bool ubench(int, double*), timing(pg_timing*, bool reset)
 #pragma once
@@ -899,8 +900,25 @@ public:
         MsmBoundsBody::Args bd{keys2, start, size_key, ids, count, n_buckets, plan.c};
         if (!be.template run_simple<MsmBoundsBody>(bd, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm bounds kernel");
         if (!be.sort_pairs(size_key, ids, size_key2, ids2, n_buckets, 32)) return fail(PG_ERR_CUDA, "msm bucket-order sort");
-        MsmBucketBody::Args bk{ids2, size_key2, start, vals2, d_points, buckets, n_buckets};
+        // bucket sums in three levels (parts of <= 256 entries, groups of <= 64 parts, one thread per bucket): see msm.cuh
+        const uint64_t max_parts = count / MSM_PART + n_buckets, max_groups = max_parts / MSM_GROUP + n_buckets;
+        uint32_t* parts = (uint32_t*)tmp(n_buckets * 4); uint32_t* groups = (uint32_t*)tmp(n_buckets * 4);
+        uint32_t* off1 = (uint32_t*)tmp(n_buckets * 4); uint32_t* off2 = (uint32_t*)tmp(n_buckets * 4);
+        uint32_t* part_owner = (uint32_t*)tmp(max_parts * 4); uint32_t* group_owner = (uint32_t*)tmp(max_groups * 4);
+        uint4* p1 = (uint4*)tmp(max_parts * sizeof(G1X)); uint4* p2 = (uint4*)tmp(max_groups * sizeof(G1X));
+        if (!parts || !groups || !off1 || !off2 || !part_owner || !group_owner || !p1 || !p2) return fail(PG_ERR_OOM, "msm buffers");
+        if (max_parts >= (1ull << 32)) return fail(PG_ERR_ARG, "msm: too many terms for 32-bit part numbers");
+        MsmPartsBody::Args pb{size_key2, parts, groups, n_buckets};
+        if (!be.template run_simple<MsmPartsBody>(pb, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm parts kernel");
+        if (!be.exclusive_sum(parts, off1, n_buckets) || !be.exclusive_sum(groups, off2, n_buckets)) return fail(PG_ERR_CUDA, "msm scan");
+        MsmExpandBody::Args ex{parts, groups, off1, off2, part_owner, group_owner, n_buckets};
+        if (!be.template run_simple<MsmExpandBody>(ex, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm expand kernel");
+        MsmBucketBody::Args bk{ids2, size_key2, start, vals2, d_points, parts, off1, part_owner, p1, max_parts, n_buckets};
         if (!be.run_msm_buckets(bk)) return fail(PG_ERR_CUDA, "msm bucket kernel");
+        MsmGroupSumBody::Args gs{parts, groups, off1, off2, group_owner, p1, p2, max_groups, n_buckets};
+        if (!be.template run_simple<MsmGroupSumBody>(gs, max_groups, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm group kernel");
+        MsmBucketFinishBody::Args bf{ids2, groups, off2, p2, buckets, n_buckets};
+        if (!be.template run_simple<MsmBucketFinishBody>(bf, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm bucket finish kernel");
         MsmChunkBody::Args ck{buckets, ping, n_chunks, plan.c, plan.chunk};
         if (!be.template run_simple<MsmChunkBody>(ck, n_chunks, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm chunk kernel");
         uint32_t seg = (1u << plan.c) / plan.chunk;                    // partial sums per window

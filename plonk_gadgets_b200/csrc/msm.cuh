@@ -8,9 +8,10 @@
 //   2. sort_pairs                 radix sort of the W*n pairs by key (CUB on the device): every bucket becomes a contiguous run;
 //   3. k_simple<MsmBoundsBody>    start and length of every bucket's run (binary search); a second, small radix sort orders the
 //                                 bucket ids by decreasing length;
-//      k_simple<MsmBucketBody>    one thread per (window, digit) bucket, in that order -- the lanes of a warp get buckets of
-//                                 (almost) equal length: mixed additions of the bucket's points into an XYZZ accumulator,
-//                                 W*n additions in total, W*2^c independent threads;
+//      k_simple<MsmBucketBody>    runs are cut into parts of at most 256 entries, numbered in that order -- the lanes of a warp
+//                                 get parts of (almost) equal length, and no thread walks a long run however skewed the
+//                                 scalars are: mixed additions of a part's points into an XYZZ accumulator (W*n in total);
+//                                 MsmGroupSumBody / MsmBucketFinishBody add a bucket's parts (two more levels);
 //   4. k_simple<MsmChunkBody>     per window, chunks of L consecutive buckets: running-sum trick gives sum (d - lo) * B_d,
 //                                 plus lo * (sum B_d) by double-and-add on the small factor lo;
 //   5. k_simple<MsmSumBody>       tree of 16-way sums of the chunk results down to one point per window;
@@ -81,17 +82,63 @@ struct MsmBoundsBody {
     }
 };
 
-// One thread per bucket, buckets taken in order of decreasing length (ids sorted by size_key): mixed additions of the bucket's
-// points into an XYZZ accumulator.
-struct MsmBucketBody {
-    struct Args { const uint32_t* ids; const uint32_t* size_key; const unsigned long long* start; const uint32_t* vals; const uint4* points; uint4* buckets;
-                  uint64_t n; /* buckets */ };
+// Bucket sums in three levels so that no thread ever walks a long run, whatever the scalars look like (wire VALUES put millions of
+// points into the "digit 1" bucket; uniform scalars give every bucket a few dozen):
+//   parts  : a bucket's run is cut into parts of at most MSM_PART entries; parts are numbered bucket after bucket in order of
+//            decreasing bucket length (the order of the small sort), so that neighbouring parts are equally long;
+//   groups : a bucket's parts are cut into groups of at most MSM_GROUP parts;
+//   finish : one thread per bucket adds its groups.
+// Offsets come from two exclusive scans; the totals are bounded on the host (count / MSM_PART + buckets), surplus threads leave.
+constexpr uint32_t MSM_PART = 256, MSM_GROUP = 64;
+struct MsmPartsBody {           // per bucket, in sorted order: number of parts and of groups
+    struct Args { const uint32_t* size_key; uint32_t* parts; uint32_t* groups; uint64_t n; };
     PG_HD static void run(const Args& a, uint64_t t) {
-        const uint32_t b = a.ids[t];
-        const uint64_t lo = a.start[b], len = 0xffffffffu - a.size_key[t];
+        const uint32_t len = 0xffffffffu - a.size_key[t];
+        const uint32_t p = (len + MSM_PART - 1) / MSM_PART;
+        a.parts[t] = p; a.groups[t] = (p + MSM_GROUP - 1) / MSM_GROUP;
+    }
+};
+struct MsmExpandBody {          // owner (sorted bucket position) of every part and of every group
+    struct Args { const uint32_t* parts; const uint32_t* groups; const uint32_t* off1; const uint32_t* off2; uint32_t* part_owner; uint32_t* group_owner; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        for (uint32_t j = 0; j < a.parts[t]; j++) a.part_owner[a.off1[t] + j] = (uint32_t)t;
+        for (uint32_t j = 0; j < a.groups[t]; j++) a.group_owner[a.off2[t] + j] = (uint32_t)t;
+    }
+};
+struct MsmBucketBody {          // level 1: mixed additions of the points of one part into an XYZZ accumulator
+    struct Args { const uint32_t* ids; const uint32_t* size_key; const unsigned long long* start; const uint32_t* vals; const uint4* points;
+                  const uint32_t* parts; const uint32_t* off1; const uint32_t* part_owner; uint4* p1; uint64_t n; /* bound on parts */ uint64_t n_buckets; };
+    PG_HD static void run(const Args& a, uint64_t p) {
+        const uint64_t total = (uint64_t)a.off1[a.n_buckets - 1] + a.parts[a.n_buckets - 1];
+        if (p >= total) return;
+        const uint32_t t = a.part_owner[p], b = a.ids[t];
+        const uint64_t len = 0xffffffffu - a.size_key[t], j = p - a.off1[t];
+        const uint64_t lo = a.start[b] + j * MSM_PART, hi = a.start[b] + (len < (j + 1) * MSM_PART ? len : (j + 1) * MSM_PART);
         G1X acc = g1x_inf();
-        for (uint64_t j = lo; j < lo + len; j++) acc = g1x_madd(acc, g1_affine_load(a.points, a.vals[j]));
-        g1x_store(a.buckets, b, acc);
+        for (uint64_t k = lo; k < hi; k++) acc = g1x_madd(acc, g1_affine_load(a.points, a.vals[k]));
+        g1x_store(a.p1, p, acc);
+    }
+};
+struct MsmGroupSumBody {        // level 2: up to MSM_GROUP consecutive parts of one bucket
+    struct Args { const uint32_t* parts; const uint32_t* groups; const uint32_t* off1; const uint32_t* off2; const uint32_t* group_owner; const uint4* p1; uint4* p2;
+                  uint64_t n; /* bound on groups */ uint64_t n_buckets; };
+    PG_HD static void run(const Args& a, uint64_t g) {
+        const uint64_t total = (uint64_t)a.off2[a.n_buckets - 1] + a.groups[a.n_buckets - 1];
+        if (g >= total) return;
+        const uint32_t t = a.group_owner[g];
+        const uint32_t j = (uint32_t)(g - a.off2[t]), first = j * MSM_GROUP;
+        const uint32_t cnt = a.parts[t] - first < MSM_GROUP ? a.parts[t] - first : MSM_GROUP;
+        G1X acc = g1x_inf();
+        for (uint32_t k = 0; k < cnt; k++) acc = g1x_add(acc, g1x_load(a.p1, (uint64_t)a.off1[t] + first + k));
+        g1x_store(a.p2, g, acc);
+    }
+};
+struct MsmBucketFinishBody {    // level 3: the groups of one bucket
+    struct Args { const uint32_t* ids; const uint32_t* groups; const uint32_t* off2; const uint4* p2; uint4* buckets; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        G1X acc = g1x_inf();
+        for (uint32_t k = 0; k < a.groups[t]; k++) acc = g1x_add(acc, g1x_load(a.p2, (uint64_t)a.off2[t] + k));
+        g1x_store(a.buckets, a.ids[t], acc);
     }
 };
 

@@ -89,6 +89,7 @@ public:
         return true;
     }
     bool run_msm_buckets(const MsmBucketBody::Args& a) { for (uint64_t b = 0; b < a.n; b++) MsmBucketBody::run(a, b); return true; }
+    bool exclusive_sum(const uint32_t* in, uint32_t* out, uint64_t n) { uint32_t acc = 0; for (uint64_t i = 0; i < n; i++) { const uint32_t v = in[i]; out[i] = acc; acc += v; } return true; }
     bool run_ntt_pass(const NttPassArgs& a, uint64_t n_blocks) { ntt_pass_host(a, n_blocks); return true; }
     bool run_check_rows(const CheckRowsBody::Args& a) {
         for (uint64_t i = 0; i < a.n; i++)

@@ -162,3 +162,24 @@ def test_emu_lagrange_srs_and_evaluation_commitments(emu, oracle, golden):
             assert np.array_equal(to_oracle(from_values[w:w + 1]), oracle.g1_msm(to_oracle(mono), polys[w])), (name, w)
         with pytest.raises(pg.EngineError):
             c.commit_wire_evaluations(lag, log_n=k + 1)                       # a Lagrange SRS belongs to one domain size
+
+
+def test_emu_msm_skewed_scalars(emu, oracle):
+    """Scalars as wire values have them: tens of thousands of ones (one bucket whose run spans many parts and more than one
+    group), small values, zeros.  Expected value by linearity: per distinct point, the sum of its scalars (one small MSM in the
+    oracle)."""
+    c = pg.StandardComposer(_cdll=emu)
+    base = oracle.srs_powers(oracle.from_ints([0xabcdef]), 48)
+    n = 40000                                                    # ~30 000 ones: 118 parts of 256 entries, 2 groups of 64 parts
+    idx = np.arange(n) % 48
+    sc = [1] * n
+    for i in range(0, n, 7):
+        sc[i] = 0
+    for i in range(3, n, 11):
+        sc[i] = (i * 2654435761) % 5
+    for i in range(5, n, 501):
+        sc[i] = synth_wide(77, 1)[0]
+    pts = to_engine(base)[idx]
+    got = c.msm(pts, oracle.from_ints(sc))
+    per_point = [sum(sc[i] for i in range(j, n, 48)) % Q for j in range(48)]
+    assert np.array_equal(to_oracle(got.reshape(1, 12)), oracle.g1_msm(base, oracle.from_ints(per_point)))

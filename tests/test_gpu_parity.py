@@ -627,3 +627,34 @@ def test_evaluation_form_commitments_gpu(oracle, golden, torch_cuda):
     c.srs_powers(beta[0], 1 << k, out=mono); c.srs_lagrange(beta[0], k, out=lag)
     a, b = c.commit_wire_evaluations(lag), c.commit_wire_polynomials(mono)
     assert np.array_equal(a, b) and a.any()
+
+
+def test_msm_skewed_scalars_gpu(oracle, torch_cuda):
+    """2^22 terms whose scalars look like wire values (ones, zeros, tiny values, a few full-size ones): the digit-1 bucket of
+    window 0 holds millions of entries.  Expected value by linearity over the 4096 distinct points."""
+    from tests.test_emu_msm import to_oracle
+    torch = torch_cuda
+    n, m = 1 << 22, 1 << 12
+    c = gpu_composer()
+    table = c.srs_powers(oracle.from_ints([0xabcdef])[0], m)
+    pts = torch.from_numpy(table.view(np.int64)).cuda().repeat(n // m, 1)
+    i = np.arange(n, dtype=np.uint64)
+    vals = np.ones(n, dtype=np.uint64)
+    vals[i % 7 == 0] = 0
+    small = i % 11 == 3
+    vals[small] = (i[small] * np.uint64(2654435761)) % np.uint64(5)
+    sc_int = vals.astype(object)
+    big_idx = np.arange(5, n, 50001)
+    bigs = synth_wide(78, len(big_idx))
+    for k, j in enumerate(big_idx):
+        sc_int[j] = bigs[k]
+    # Montgomery form on the device: canonical limbs -> fr_op(to Montgomery) is host-sized, so build small/ones by table lookup
+    lut = oracle.from_ints([0, 1, 2, 3, 4])
+    sc = lut[np.minimum(vals, 4).astype(np.int64)].copy()
+    sc[big_idx] = oracle.from_ints(bigs)
+    sc_dev = torch.from_numpy(sc.view(np.int64)).cuda(); torch.cuda.synchronize()
+    got = c.msm(pts, sc_dev)
+    per_point = np.zeros(m, dtype=object)
+    np.add.at(per_point, (i % m).astype(np.int64), sc_int)
+    want = oracle.g1_msm(to_oracle(table), oracle.from_ints([int(v) % Q for v in per_point]))
+    assert np.array_equal(to_oracle(got.reshape(1, 12)), want)
