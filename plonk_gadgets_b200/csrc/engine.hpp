@@ -900,7 +900,7 @@ public:
         MsmBoundsBody::Args bd{keys2, start, size_key, ids, count, n_buckets, plan.c};
         if (!be.template run_simple<MsmBoundsBody>(bd, n_buckets, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm bounds kernel");
         if (!be.sort_pairs(size_key, ids, size_key2, ids2, n_buckets, 32)) return fail(PG_ERR_CUDA, "msm bucket-order sort");
-        // bucket sums in three levels (parts of <= 256 entries, groups of <= 64 parts, one thread per bucket): see msm.cuh
+        // bucket sums in three levels (parts of <= 512 entries, groups of <= 64 parts, one thread per bucket): see msm.cuh
         const uint64_t max_parts = count / MSM_PART + n_buckets, max_groups = max_parts / MSM_GROUP + n_buckets;
         uint32_t* parts = (uint32_t*)tmp(n_buckets * 4); uint32_t* groups = (uint32_t*)tmp(n_buckets * 4);
         uint32_t* off1 = (uint32_t*)tmp(n_buckets * 4); uint32_t* off2 = (uint32_t*)tmp(n_buckets * 4);

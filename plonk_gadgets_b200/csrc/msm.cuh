@@ -8,7 +8,7 @@
 //   2. sort_pairs                 radix sort of the W*n pairs by key (CUB on the device): every bucket becomes a contiguous run;
 //   3. k_simple<MsmBoundsBody>    start and length of every bucket's run (binary search); a second, small radix sort orders the
 //                                 bucket ids by decreasing length;
-//      k_simple<MsmBucketBody>    runs are cut into parts of at most 256 entries, numbered in that order -- the lanes of a warp
+//      k_simple<MsmBucketBody>    runs are cut into equal parts of at most 512 entries, numbered in that order -- the lanes of a warp
 //                                 get parts of (almost) equal length, and no thread walks a long run however skewed the
 //                                 scalars are: mixed additions of a part's points into an XYZZ accumulator (W*n in total);
 //                                 MsmGroupSumBody / MsmBucketFinishBody add a bucket's parts (two more levels);
@@ -84,12 +84,12 @@ struct MsmBoundsBody {
 
 // Bucket sums in three levels so that no thread ever walks a long run, whatever the scalars look like (wire VALUES put millions of
 // points into the "digit 1" bucket; uniform scalars give every bucket a few dozen):
-//   parts  : a bucket's run is cut into parts of at most MSM_PART entries; parts are numbered bucket after bucket in order of
-//            decreasing bucket length (the order of the small sort), so that neighbouring parts are equally long;
+//   parts  : a bucket's run is cut into ceil(len / MSM_PART) parts of equal length; parts are numbered bucket after bucket in
+//            order of decreasing bucket length (the order of the small sort), so that neighbouring parts are equally long;
 //   groups : a bucket's parts are cut into groups of at most MSM_GROUP parts;
 //   finish : one thread per bucket adds its groups.
 // Offsets come from two exclusive scans; the totals are bounded on the host (count / MSM_PART + buckets), surplus threads leave.
-constexpr uint32_t MSM_PART = 256, MSM_GROUP = 64;
+constexpr uint32_t MSM_PART = 512, MSM_GROUP = 64;
 struct MsmPartsBody {           // per bucket, in sorted order: number of parts and of groups
     struct Args { const uint32_t* size_key; uint32_t* parts; uint32_t* groups; uint64_t n; };
     PG_HD static void run(const Args& a, uint64_t t) {
@@ -112,8 +112,9 @@ struct MsmBucketBody {          // level 1: mixed additions of the points of one
         const uint64_t total = (uint64_t)a.off1[a.n_buckets - 1] + a.parts[a.n_buckets - 1];
         if (p >= total) return;
         const uint32_t t = a.part_owner[p], b = a.ids[t];
-        const uint64_t len = 0xffffffffu - a.size_key[t], j = p - a.off1[t];
-        const uint64_t lo = a.start[b] + j * MSM_PART, hi = a.start[b] + (len < (j + 1) * MSM_PART ? len : (j + 1) * MSM_PART);
+        const uint64_t len = 0xffffffffu - a.size_key[t], j = p - a.off1[t], np = a.parts[t];
+        const uint64_t each = len / np, extra = len % np;                    // equal parts: the first `extra` ones hold one entry more
+        const uint64_t lo = a.start[b] + j * each + (j < extra ? j : extra), hi = lo + each + (j < extra ? 1 : 0);
         G1X acc = g1x_inf();
         for (uint64_t k = lo; k < hi; k++) acc = g1x_madd(acc, g1_affine_load(a.points, a.vals[k]));
         g1x_store(a.p1, p, acc);

@@ -170,7 +170,7 @@ def test_emu_msm_skewed_scalars(emu, oracle):
     oracle)."""
     c = pg.StandardComposer(_cdll=emu)
     base = oracle.srs_powers(oracle.from_ints([0xabcdef]), 48)
-    n = 40000                                                    # ~30 000 ones: 118 parts of 256 entries, 2 groups of 64 parts
+    n = 90000                                                    # ~67 000 ones: 131 parts of <= 512 entries, 3 groups of <= 64 parts
     idx = np.arange(n) % 48
     sc = [1] * n
     for i in range(0, n, 7):
