@@ -125,6 +125,13 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_commit_wire_polynomials(self.ctx, log_n, powers_of_g.as_ptr(), powers_of_g.len() as u64, 0, out.as_mut_ptr()) })?;
         Ok(out)
     }
+    /// The same four commitments from the wire values against the Lagrange-basis form of the SRS (`lagrange[i] = L_i(beta) * g`,
+    /// exactly 2^log_n points): no FFT, and bits / short accumulators leave most windows of the multi-scalar multiplication empty.
+    pub fn commit_wire_evaluations(&mut self, log_n: u32, lagrange: &[sys::pg_g1_affine]) -> Result<[sys::pg_g1_affine; 4], EngineError> {
+        let mut out = [sys::pg_g1_affine::default(); 4];
+        self.ok(unsafe { sys::pg_commit_wire_evaluations(self.ctx, log_n, lagrange.as_ptr(), lagrange.len() as u64, 0, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
     /// `msm_variable_base(points, scalars)`.
     pub fn msm(&mut self, points: &[sys::pg_g1_affine], scalars: &[BlsScalar]) -> Result<sys::pg_g1_affine, EngineError> {
         assert_eq!(points.len(), scalars.len());

@@ -133,6 +133,18 @@ public:
         ok(pg_srs_powers(ctx_, reinterpret_cast<const pg_fr*>(&beta), nullptr, n, out.data(), 0), "pg_srs_powers");
         return out;
     }
+    /// Lagrange-basis form of the SRS for the domain 2^log_n: out[i] = L_i(beta) * G1 generator
+    std::vector<pg_g1_affine> srs_lagrange(const BlsScalar& beta, uint32_t log_n) {
+        std::vector<pg_g1_affine> out((size_t)1 << log_n);
+        ok(pg_srs_lagrange(ctx_, reinterpret_cast<const pg_fr*>(&beta), nullptr, log_n, out.data(), 0), "pg_srs_lagrange");
+        return out;
+    }
+    /// the same four commitments as commit_wire_polynomials, from the wire values against the Lagrange-basis SRS (no FFT)
+    std::vector<pg_g1_affine> commit_wire_evaluations(const std::vector<pg_g1_affine>& lagrange, uint32_t log_n) {
+        std::vector<pg_g1_affine> out(4);
+        ok(pg_commit_wire_evaluations(ctx_, log_n, lagrange.data(), lagrange.size(), 0, out.data()), "pg_commit_wire_evaluations");
+        return out;
+    }
     /// CommitKey::commit of a coefficient vector (msm_variable_base)
     pg_g1_affine commit(const std::vector<pg_g1_affine>& powers_of_g, const std::vector<BlsScalar>& coeffs) {
         if (coeffs.size() > powers_of_g.size()) throw EngineError(PG_ERR_ARG, "commit: polynomial degree exceeds the SRS");

@@ -157,6 +157,9 @@ static void prover_first_round_test() {
         const pg_g1_affine want = composer.commit({powers[0]}, {at_beta});
         EXPECT(std::memcmp(&want, &commits[w], sizeof(want)) == 0, "commit(w_poly) == w_poly(beta) * G");
     }
+    // the same commitments from the wire values against the Lagrange-basis form of the SRS
+    const auto from_values = composer.commit_wire_evaluations(composer.srs_lagrange(beta, k), k);
+    for (int w = 0; w < 4; w++) EXPECT(std::memcmp(&from_values[w], &commits[w], sizeof(pg_g1_affine)) == 0, "evaluation-form commitment == coefficient-form commitment");
     // ifft then fft is the identity on a wire-polynomial column
     std::vector<BlsScalar> col(polys.begin(), polys.begin() + n);
     const auto evals = composer.fft(col, false);
