@@ -74,6 +74,7 @@ extern "C" {
     pub fn pg_select_one_batch(ctx: *mut pg_ctx, y: pg_col, selector: pg_col, out: *mut pg_col) -> c_int;
     pub fn pg_constrain_to_constant_batch(ctx: *mut pg_ctx, a: pg_col, constant: *const pg_fr, n_const: u64, pi: *const pg_fr,
                                           n_pi: u64, on_device: c_int) -> c_int;
+    pub fn pg_range_gate_batch(ctx: *mut pg_ctx, witness: pg_col, num_bits: u32) -> c_int;
     pub fn pg_check(ctx: *mut pg_ctx, n_unsat: *mut u64, first_bad_row: *mut u64) -> c_int;
     pub fn pg_check_rows(ctx: *mut pg_ctx, n: u64, w_val: *const pg_fr, sel: *const pg_fr, pi: *const pg_fr, on_device: c_int,
                          n_unsat: *mut u64, first_bad_row: *mut u64) -> c_int;
@@ -83,6 +84,10 @@ extern "C" {
     pub fn pg_read_variables(ctx: *mut pg_ctx, var0: u64, cnt: u64, dst: *mut pg_fr, dst_on_device: c_int) -> c_int;
     pub fn pg_materialize_rows(ctx: *mut pg_ctx, row0: u64, cnt: u64, w_idx: *mut u64, w_val: *mut pg_fr, sel: *mut pg_fr,
                                pi: *mut pg_fr, dst_on_device: c_int) -> c_int;
+    pub fn pg_check_rows_ex(ctx: *mut pg_ctx, n: u64, w_val: *const pg_fr, sel: *const pg_fr, pi: *const pg_fr, q_arith: *const pg_fr,
+                            q_range: *const pg_fr, on_device: c_int, n_unsat: *mut u64, first_bad_row: *mut u64) -> c_int;
+    pub fn pg_materialize_gate_selectors(ctx: *mut pg_ctx, row0: u64, cnt: u64, q_arith: *mut pg_fr, q_range: *mut pg_fr,
+                                         dst_on_device: c_int) -> c_int;
     pub fn pg_permutation(ctx: *mut pg_ctx, row0: u64, cnt: u64, sigma: *mut u64, dst_on_device: c_int) -> c_int;
     pub fn pg_fft(ctx: *mut pg_ctx, log_n: u32, inverse: c_int, src: *const pg_fr, dst: *mut pg_fr, on_device: c_int) -> c_int;
     pub fn pg_wire_polynomials(ctx: *mut pg_ctx, log_n: u32, dst: *mut pg_fr, dst_on_device: c_int) -> c_int;

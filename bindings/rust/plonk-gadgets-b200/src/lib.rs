@@ -94,6 +94,12 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_select_one_batch(self.ctx, y.col, selector.col, &mut col) })?;
         Ok(Variables { col, n: y.n })
     }
+    /// `for w in witness { composer.range_gate(w, num_bits) }` -- dusk-plonk's native quad-accumulator range gate (the path
+    /// `plonk_gadgets::range` recommends for power-of-two bounds).  `num_bits` even, 2..=256.
+    pub fn range_gate_batch(&mut self, witness: Variables, num_bits: usize) -> Result<(), EngineError> {
+        self.ok(unsafe { sys::pg_range_gate_batch(self.ctx, witness.col, num_bits as u32) })?;
+        Ok(())
+    }
     /// Satisfaction verdict: (unsatisfied rows, first unsatisfied row).
     pub fn check(&mut self) -> Result<(u64, Option<u64>), EngineError> {
         let (mut bad, mut first) = (0, 0);

@@ -133,14 +133,30 @@ int pg_select_one_batch(pg_ctx *ctx, pg_col y, pg_col selector, pg_col *out);
 int pg_constrain_to_constant_batch(pg_ctx *ctx, pg_col a, const pg_fr *constant, uint64_t n_const, const pg_fr *pi,
                                    uint64_t n_pi, int on_device);
 
+/* for i { composer.range_gate(witness_i, num_bits); } -- StandardComposer::range_gate [dusk-plonk 0.8 src/constraint_system/range.rs],
+ * the native quad-accumulator range gate that /root/reference/src/range.rs:9-12 recommends over range_check when the bound is a
+ * power of two.  Per instance: num_bits/2 accumulator variables a_j = 4*a_{j-1} + quad_j (base-4
+ * digits of the witness, most significant first) laid out four per gate on w_4, w_o, w_r, w_l after 1..4 leading zero wires;
+ * ceil(num_bits/8) gates with q_range = 1 (all arithmetic selectors and q_arith 0), one closing gate with q_range = 0, and
+ * assert_equal(last accumulator, witness): ceil(num_bits/8) + 2 rows.  The circuit is satisfied iff the witness < 2^num_bits.
+ * num_bits must be even (the reference asserts) and in 2..256, else PG_ERR_ARG.  Nothing is returned (the reference returns ()). */
+int pg_range_gate_batch(pg_ctx *ctx, pg_col witness, uint32_t num_bits);
+
 /* ---- verdict ------------------------------------------------------------------------------------------------------ */
-/* Arithmetic part of check_circuit_satisfied [dusk-plonk]: evaluates the gate equation on every row of the composer.
+/* Arithmetic and range parts of check_circuit_satisfied [dusk-plonk]: evaluates, on every row of the composer,
+ *   q_arith*(q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + PI + q_c) + q_range*(D(c - 4d) + D(b - 4c) + D(a - 4b) + D(d_next - 4a)),
+ * D(f) = f(f-1)(f-2)(f-3), d_next = fourth wire of the next row (q_range is non-zero only on rows appended by pg_range_gate_batch).
  * *n_unsat = number of rows with a non-zero value; *first_bad_row = smallest such row index or UINT64_MAX. */
 int pg_check(pg_ctx *ctx, uint64_t *n_unsat, uint64_t *first_bad_row);
 /* Same equation over caller-supplied materialised rows (w_val: 4 x n wire values, sel: 6 x n selectors in the order
  * q_m q_l q_r q_o q_4 q_c, pi: n or NULL), column-major. */
 int pg_check_rows(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel, const pg_fr *pi, int on_device,
                   uint64_t *n_unsat, uint64_t *first_bad_row);
+
+/* The full equation of pg_check (arithmetic + range widget) over caller-supplied rows: q_arith and q_range are n scalars each
+ * (NULL q_arith = 1 everywhere, NULL q_range = 0 everywhere); d_next of row i is w_val[3][(i + 1) mod n]. */
+int pg_check_rows_ex(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel, const pg_fr *pi, const pg_fr *q_arith,
+                     const pg_fr *q_range, int on_device, uint64_t *n_unsat, uint64_t *first_bad_row);
 
 /* ---- reading the composer back in the reference's representation --------------------------------------------------- */
 int pg_counts(const pg_ctx *ctx, uint64_t *n_rows, uint64_t *n_vars);        /* composer.circuit_size(), variables.len() */
@@ -154,15 +170,20 @@ int pg_col_read(pg_ctx *ctx, pg_col col, uint64_t i0, uint64_t cnt, pg_fr *dst, 
 int pg_read_variables(pg_ctx *ctx, uint64_t var0, uint64_t cnt, pg_fr *dst, int dst_on_device);
 /* Rows [row0, row0+cnt): any of the outputs may be NULL.  w_idx: 4 x cnt Variable ids (w_l,w_r,w_o,w_4), w_val: 4 x cnt
  * wire values, sel: 6 x cnt (q_m,q_l,q_r,q_o,q_4,q_c), pi: cnt (dense public inputs), all column-major.  On every row
- * q_arith = 1 and q_range = q_logic = q_fixed_group_add = q_variable_group_add = 0. */
+ * q_logic = q_fixed_group_add = q_variable_group_add = 0; q_arith = 1 and q_range = 0 except on the rows of pg_range_gate_batch
+ * (pg_materialize_gate_selectors returns those two columns). */
 int pg_materialize_rows(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *w_idx, pg_fr *w_val, pg_fr *sel, pg_fr *pi,
                         int dst_on_device);
+
+/* q_arith and q_range of rows [row0, row0+cnt) (cnt scalars each; either pointer may be NULL). */
+int pg_materialize_gate_selectors(pg_ctx *ctx, uint64_t row0, uint64_t cnt, pg_fr *q_arith, pg_fr *q_range, int dst_on_device);
 
 /* ---- copy constraints ----------------------------------------------------------------------
  * The permutation argument's input: dusk-plonk appends the four wire positions of every row to perm.variable_map[var]
  * (add_variables_to_map, called by every gate method listed above) and links the positions of one Variable into a cycle.
  * sigma is 4 x cnt, column-major: sigma[w*cnt + t] = successor, in that cycle, of wire w (0 w_l, 1 w_r, 2 w_o, 3 w_4) of
- * row row0 + t, encoded as row*4 + wire.  A position whose Variable is used once maps to itself. */
+ * row row0 + t, encoded as row*4 + wire.  A position whose Variable is used once maps to itself, and so do the three zero wires
+ * (w_l, w_r, w_o) of a range gate's closing row, which dusk-plonk pushes without a map entry. */
 int pg_permutation(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *sigma, int dst_on_device);
 
 /* ---- evaluation domain (first half) -------------------------------------------------------------

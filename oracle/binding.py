@@ -26,8 +26,12 @@ FAITHFUL, FAST = 0, 1
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc).  Idempotent."""
-    if force or not os.path.exists(_SO):
+    # make decides by timestamps (sources newer than the .so => rebuild); a prebuilt .so stays usable where make / gcc are missing
+    try:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, stdout=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        if force or not os.path.exists(_SO):
+            raise
     return _SO
 
 
@@ -57,6 +61,7 @@ def lib():
             "orc_select_zero_batch": (None, [vp, u64, vp, vp, vp]),
             "orc_select_one_batch": (None, [vp, u64, vp, vp, vp]),
             "orc_constrain_to_constant_batch": (None, [vp, u64, vp, vp, vp, i32]),
+            "orc_range_gate_batch": (None, [vp, u64, vp, u64]),
             "orc_set_mode": (None, [i32]),
             "orc_fr_from_u64": (None, [u64, vp]), "orc_fr_mul": (None, [vp, vp, vp]), "orc_fr_add": (None, [vp, vp, vp]),
             "orc_fr_sub": (None, [vp, vp, vp]), "orc_fr_neg": (None, [vp, vp]), "orc_fr_invert": (i32, [vp, vp]),
@@ -238,6 +243,10 @@ class Composer:
         out = np.empty(len(y), dtype=np.uint64)
         lib().orc_select_one_batch(self._c, len(y), _p(y), _p(s), _p(out))
         return out
+
+    def range_gate_batch(self, wit, num_bits: int):
+        wit = np.ascontiguousarray(wit, dtype=np.uint64)
+        lib().orc_range_gate_batch(self._c, len(wit), _p(wit), int(num_bits))
 
     def constrain_to_constant_batch(self, vars_, k, pi=None):
         vars_ = np.ascontiguousarray(vars_, dtype=np.uint64)

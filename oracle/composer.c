@@ -124,6 +124,45 @@ void orc_boolean_gate(orc_composer *c, uint64_t a) {
     push_row(c, a, a, a, c->zero_var, &one, &zero, &zero, &m1, &zero, &zero, NULL);
 }
 
+/* range_gate: restated statement by statement (add_wire closure, padding rule, selector extension, last-gate fix-ups) */
+static void range_add_wire(orc_composer *c, uint64_t base, uint64_t i, uint64_t variable) {
+    uint64_t gate_index = base + (i / 4);            /* four quads fit into one gate */
+    switch (i % 4) {
+        case 0: u64vec_push(&c->w[3], variable); perm_add(c, variable, gate_index, 3); break;   /* WireData::Fourth */
+        case 1: u64vec_push(&c->w[2], variable); perm_add(c, variable, gate_index, 2); break;   /* WireData::Output */
+        case 2: u64vec_push(&c->w[1], variable); perm_add(c, variable, gate_index, 1); break;   /* WireData::Right */
+        default: u64vec_push(&c->w[0], variable); perm_add(c, variable, gate_index, 0); break;  /* WireData::Left */
+    }
+}
+void orc_range_gate(orc_composer *c, uint64_t witness, uint64_t num_bits) {
+    if (num_bits % 2 != 0 || num_bits < 2 || num_bits > 256) die("range_gate: num_bits must be even, 2..256");
+    fr_t value = orc_value_of(c, witness);
+    uint8_t bytes[32]; fr_to_bytes(&value, bytes);   /* bits[j] = bit j of the canonical integer (BitIterator8, reversed) */
+    uint64_t num_gates = num_bits >> 3;
+    if (num_bits % 8 != 0) num_gates += 1;
+    uint64_t num_quads = num_gates * 4;
+    uint64_t pad = 1 + (((num_quads << 1) - num_bits) >> 1);
+    uint64_t used_gates = num_gates + 1;
+    uint64_t base = c->n, last_acc = 0;
+    fr_t accumulator = fr_zero(), four = fr_from_u64(4), zero = fr_zero(), one = fr_one();
+    for (uint64_t i = 0; i < pad; i++) range_add_wire(c, base, i, c->zero_var);
+    for (uint64_t i = pad; i <= num_quads; i++) {
+        uint64_t bit_index = (num_quads - i) << 1;
+        uint64_t q_0 = (bytes[bit_index >> 3] >> (bit_index & 7)) & 1, q_1 = (bytes[(bit_index + 1) >> 3] >> ((bit_index + 1) & 7)) & 1;
+        fr_t quad = fr_from_u64(q_0 + 2 * q_1);
+        accumulator = fr_mul(&four, &accumulator);
+        accumulator = fr_add(&accumulator, &quad);
+        last_acc = orc_add_input(c, &accumulator);
+        range_add_wire(c, base, i, last_acc);
+    }
+    for (uint64_t g = 0; g < used_gates; g++)
+        for (int s = 0; s < ORC_NSEL; s++) frvec_push(&c->sel[s], s == ORC_QRANGE ? &one : &zero);
+    c->n += used_gates;
+    c->sel[ORC_QRANGE].p[c->sel[ORC_QRANGE].len - 1] = zero;        /* switch the range selector off on the last gate */
+    u64vec_push(&c->w[0], c->zero_var); u64vec_push(&c->w[1], c->zero_var); u64vec_push(&c->w[2], c->zero_var);   /* no permutation entries */
+    orc_assert_equal(c, last_acc, witness);
+}
+
 orc_composer *orc_composer_new(void) {
     orc_composer *c = (orc_composer *)calloc(1, sizeof(orc_composer));
     if (!c) die("oom");
@@ -161,6 +200,19 @@ uint64_t orc_check(const orc_composer *c, uint64_t *first_bad) {
         if (pi_i < c->pi_pos.len && c->pi_pos.p[pi_i] == i) { t = fr_add(&t, &c->pi_val.p[pi_i]); pi_i++; }
         t = fr_add(&t, &c->sel[ORC_QC].p[i]);
         t = fr_mul(&c->sel[ORC_QARITH].p[i], &t);
+        if (!fr_is_zero(&c->sel[ORC_QRANGE].p[i])) {   /* q_range * (delta(c-4d) + delta(b-4c) + delta(a-4b) + delta(d_next-4a)) */
+            fr_t dn = orc_value_of(c, c->w[3].p[(i + 1) % c->n]);
+            const fr_t *hi[4] = {&o, &b, &a, &dn}, *lo[4] = {&d, &o, &b, &a};
+            fr_t four = fr_from_u64(4), one = fr_one(), sum = fr_zero();
+            for (int k = 0; k < 4; k++) {
+                fr_t f = fr_mul(&four, lo[k]); f = fr_sub(hi[k], &f);
+                fr_t g = f, p = f;
+                for (int j = 0; j < 3; j++) { g = fr_sub(&g, &one); p = fr_mul(&p, &g); }   /* f (f-1) (f-2) (f-3) */
+                sum = fr_add(&sum, &p);
+            }
+            sum = fr_mul(&c->sel[ORC_QRANGE].p[i], &sum);
+            t = fr_add(&t, &sum);
+        }
         if (!fr_is_zero(&t)) { if (!bad) first = i; bad++; }
     }
     if (first_bad) *first_bad = first;

@@ -56,9 +56,15 @@ uint64_t orc_mul(orc_composer *c, const fr_t *q_m, uint64_t a, uint64_t b, const
 void orc_mul_gate(orc_composer *c, uint64_t a, uint64_t b, uint64_t o, const fr_t *q_m, const fr_t *q_o, const fr_t *q_c, const fr_t *pi);
 void orc_boolean_gate(orc_composer *c, uint64_t a);
 
+/* StandardComposer::range_gate(witness, num_bits) [dusk-plonk 0.8 src/constraint_system/range.rs, recalled; recommended by the
+ * reference for power-of-two bounds, /root/reference/src/range.rs:9-12]: quad accumulators, four per gate (w_4, w_o, w_r, w_l),
+ * q_range = 1 on all used gates but the last, assert_equal(last accumulator, witness).  num_bits must be even, 2..256. */
+void orc_range_gate(orc_composer *c, uint64_t witness, uint64_t num_bits);
+
 /* variables[var] */
 fr_t orc_value_of(const orc_composer *c, uint64_t var);
-/* arithmetic part of check_circuit_satisfied: number of rows with q_arith*(...) != 0; first such row or (uint64_t)-1 */
+/* arithmetic + range part of check_circuit_satisfied: number of rows with q_arith*(...) + q_range*(sum of four deltas) != 0;
+ * first such row or (uint64_t)-1 */
 uint64_t orc_check(const orc_composer *c, uint64_t *first_bad);
 /* construct_dense_pi_vec(): out has c->n entries */
 void orc_dense_pi(const orc_composer *c, fr_t *out);

@@ -122,6 +122,27 @@ def batch_programs():
         dict(op="is_non_zero", var=3, assigned=[hx(x if x < 2 ** 64 else 1) for x in xs]),   # 6
         dict(op="constrain_to_constant", a=5, constant=[hx(1), hx(0), hx(1), hx(0)]),        # 7
         dict(op="constrain_to_constant", a=2, constant=hx(0), pi=[hx(-xs[0]), hx(0), hx(-xs[2]), hx(0)])])  # 8
+    # dusk-plonk's native range gate (the path range.rs:9-12 recommends for power-of-two bounds): satisfied iff
+    # the witness fits num_bits.  Widths cover every padding case (num_bits mod 8 = 0, 2, 4, 6) and the 256-bit maximum.
+    progs["kat_range_gate_8bits_ok"] = dict(satisfied=True, program=[
+        dict(op="add_input", values=[hx(200)]), dict(op="range_gate", witness=0, num_bits=8)])
+    progs["kat_range_gate_8bits_too_large"] = dict(satisfied=False, program=[
+        dict(op="add_input", values=[hx(256)]), dict(op="range_gate", witness=0, num_bits=8)])
+    for nb in (2, 4, 6, 10, 64, 254, 256):
+        top = min(2 ** nb, Q)
+        vals = [0, 1, top - 1, top % Q, u64s[50] % top, w[50] % top, w[51], Q - 1]
+        progs[f"batch_range_gate_{nb}bits"] = dict(program=[
+            dict(op="add_input", values=[hx(x) for x in vals]), dict(op="range_gate", witness=0, num_bits=nb)])
+    # range gates inside a mixed circuit: on an input column and on a gadget's output column, followed by further calls
+    ys = [u64s[52] % 2 ** 32, w[52], 5, 2 ** 32]
+    progs["batch_range_gate_mixed"] = dict(program=[
+        dict(op="add_input", values=[hx(x) for x in ys]),                          # 0
+        dict(op="range_gate", witness=0, num_bits=32),                             # 1 (no column)
+        dict(op="max_bound", max=hx(2 ** 32), witness=0),                          # 2: fits-32-bits flag
+        dict(op="select_zero", x=0, select=2),                                     # 3: x or 0
+        dict(op="range_gate", witness=3, num_bits=34),                             # 4: always satisfied
+        dict(op="range_gate", witness=2, num_bits=2),                              # 5: a bit is a quad
+        dict(op="maybe_equal", a=3, b=0)])                                         # 6
     # scalar_decomposition_test of the reference (range.rs:205-233): -100 in 8 bits -> is_eq = 0
     progs["kat_decomposition_minus100_8bits"] = dict(satisfied=True, program=[
         dict(op="add_input", values=[hx(-100)]), dict(op="max_bound", max=hx(2 ** 7), witness=0)])
@@ -198,7 +219,7 @@ def coeff_digest(cols) -> str:
     return h.hexdigest()
 
 
-def domain_vectors(programs, max_domain: int = 512, max_programs: int = 6):
+def domain_vectors(programs, max_domain: int = 512, max_programs: int = 12):
     """Evaluation-domain fixtures from the defining DFT sums of oracle/pymodel.py: subgroup generators,
     fft / ifft of seeded vectors, and the wire polynomials (ifft of the zero-padded wire columns) of small golden programs."""
     from oracle import pymodel as pm

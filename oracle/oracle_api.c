@@ -106,6 +106,10 @@ void orc_select_zero_batch(orc_composer *c, uint64_t n, const uint64_t *x, const
 void orc_select_one_batch(orc_composer *c, uint64_t n, const uint64_t *y, const uint64_t *s, uint64_t *out_vars) {
     for (uint64_t i = 0; i < n; i++) { uint64_t r = orc_conditionally_select_one(c, y[i], s[i]); if (out_vars) out_vars[i] = r; }
 }
+/* `for i { composer.range_gate(witness_i, num_bits); }` */
+void orc_range_gate_batch(orc_composer *c, uint64_t n, const uint64_t *wit, uint64_t num_bits) {
+    for (uint64_t i = 0; i < n; i++) orc_range_gate(c, wit[i], num_bits);
+}
 /* pi == NULL: no public input; else pi[i] (or pi[0] when uniform) is attached to row i's PI slot */
 void orc_constrain_to_constant_batch(orc_composer *c, uint64_t n, const uint64_t *vars, const fr_t *k, const fr_t *pi, int uniform) {
     for (uint64_t i = 0; i < n; i++) orc_constrain_to_constant(c, vars[i], &k[uniform ? 0 : i], pi ? &pi[uniform ? 0 : i] : NULL);

@@ -121,6 +121,7 @@ class StandardComposer:
         self.w_l, self.w_r, self.w_o, self.w_4 = [], [], [], []
         self.sel = {name: [] for name in SELECTORS}
         self.public_inputs = {}                   # sparse: row -> value
+        self.perm_map = {}                        # perm.variable_map: Variable -> [(row, wire)] in insertion order
         # new(): zero_var (placeholder Variable(0), then bound by its own constant row) and the two dummy constraints
         self.zero_var = 0
         self.zero_var = self.add_witness_to_circuit_description(0)
@@ -139,6 +140,8 @@ class StandardComposer:
     # -- rows
     def _push_row(self, a, b, c, d, q_m, q_l, q_r, q_o, q_4, q_c, pi):
         self.w_l.append(a); self.w_r.append(b); self.w_o.append(c); self.w_4.append(d)
+        for wire, var in enumerate((a, b, c, d)):   # perm.add_variables_to_map(a, b, c, d, n)
+            self.perm_map.setdefault(var, []).append((self.n, wire))
         vals = dict(q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_4=q_4, q_c=q_c, q_arith=1,
                     q_range=0, q_logic=0, q_fixed_group_add=0, q_variable_group_add=0)
         for k in SELECTORS:
@@ -190,6 +193,50 @@ class StandardComposer:
         self._push_row(a, a, a, self.zero_var, 1, 0, 0, -1, 0, 0, None)
         return a
 
+    def range_gate(self, witness: int, num_bits: int):
+        """StandardComposer::range_gate(witness, num_bits) [dusk-plonk 0.8 src/constraint_system/range.rs, recalled] -- the native
+        quad-accumulator range gate the reference recommends for power-of-two bounds (/root/reference/src/range.rs:9-12).
+        Accumulators a_i = 4*a_{i-1} + quad_i over the base-4 digits of the witness, most significant first, four per gate in
+        the order w_4, w_o, w_r, w_l; q_range = 1 on every used gate but the last; the last accumulator is tied to the
+        witness by assert_equal.  Returns the accumulator Variables (the last one replaced by the witness)."""
+        assert num_bits % 2 == 0, "number of bits must be even"
+        columns = (self.w_4, self.w_o, self.w_r, self.w_l)      # i % 4 = 0 -> fourth, 1 -> output, 2 -> right, 3 -> left
+        wire_of = (3, 2, 1, 0)
+        base = self.n
+
+        def add_wire(i, variable):
+            columns[i % 4].append(variable)
+            self.perm_map.setdefault(variable, []).append((base + i // 4, wire_of[i % 4]))
+
+        value = self.variables[witness]
+        bits = [(value >> b) & 1 for b in range(256)]            # BitIterator8 over to_bytes(), reversed: LSB first
+        num_gates = num_bits >> 3
+        if num_bits % 8 != 0:
+            num_gates += 1
+        num_quads = num_gates * 4
+        pad = 1 + (((num_quads << 1) - num_bits) >> 1)
+        used_gates = num_gates + 1
+        accumulators = []
+        accumulator = 0
+        for i in range(pad):
+            add_wire(i, self.zero_var)
+        for i in range(pad, num_quads + 1):
+            bit_index = (num_quads - i) << 1
+            quad = bits[bit_index] + 2 * bits[bit_index + 1]
+            accumulator = (4 * accumulator + quad) % Q
+            accumulator_var = self.add_input(accumulator)
+            accumulators.append(accumulator_var)
+            add_wire(i, accumulator_var)
+        for k in SELECTORS:
+            self.sel[k].extend([1 if k == "q_range" else 0] * used_gates)
+        self.n += used_gates
+        self.sel["q_range"][-1] = 0                              # the range equation looks at the next gate's fourth wire
+        self.w_l.append(self.zero_var); self.w_r.append(self.zero_var); self.w_o.append(self.zero_var)   # not entered in the permutation map
+        last = len(accumulators) - 1
+        self.assert_equal(accumulators[last], witness)
+        accumulators[last] = witness
+        return accumulators
+
     def _add_dummy_constraints(self):
         var_six = self.add_input(6)
         var_one = self.add_input(1)
@@ -204,8 +251,13 @@ class StandardComposer:
         c = self.variables[self.w_o[i]]; d = self.variables[self.w_4[i]]
         s = self.sel
         pi = self.public_inputs.get(i, 0)
+        d_next = self.variables[self.w_4[(i + 1) % self.n]]
+
+        def delta(f):                              # zero iff f is a base-4 digit
+            return f * (f - 1) * (f - 2) * (f - 3)
         return (s["q_arith"][i] * (s["q_m"][i] * a * b + s["q_l"][i] * a + s["q_r"][i] * b
-                                   + s["q_o"][i] * c + s["q_4"][i] * d + pi + s["q_c"][i])) % Q
+                                   + s["q_o"][i] * c + s["q_4"][i] * d + pi + s["q_c"][i])
+                + s["q_range"][i] * (delta(c - 4 * d) + delta(b - 4 * c) + delta(a - 4 * b) + delta(d_next - 4 * a))) % Q
 
     def unsatisfied_rows(self):
         return [i for i in range(self.n) if self.gate_value(i) != 0]

@@ -53,13 +53,16 @@ SIGNATURES = {
     "pg_select_zero_batch": (_i32, [_vp, _u64, _u64, _pu64]),
     "pg_select_one_batch": (_i32, [_vp, _u64, _u64, _pu64]),
     "pg_constrain_to_constant_batch": (_i32, [_vp, _u64, _vp, _u64, _vp, _u64, _i32]),
+    "pg_range_gate_batch": (_i32, [_vp, _u64, _u32]),
     "pg_check": (_i32, [_vp, _pu64, _pu64]),
     "pg_check_rows": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _pu64, _pu64]),
+    "pg_check_rows_ex": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _pu64, _pu64]),
     "pg_counts": (_i32, [_vp, _pu64, _pu64]),
     "pg_col_info": (_i32, [_vp, _u64, _pu64, _pu64, _pu64]),
     "pg_col_read": (_i32, [_vp, _u64, _u64, _u64, _vp, _i32]),
     "pg_read_variables": (_i32, [_vp, _u64, _u64, _vp, _i32]),
     "pg_materialize_rows": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _i32]),
+    "pg_materialize_gate_selectors": (_i32, [_vp, _u64, _u64, _vp, _vp, _i32]),
     "pg_permutation": (_i32, [_vp, _u64, _u64, _vp, _i32]),
     "pg_fft": (_i32, [_vp, _u32, _i32, _vp, _vp, _i32]),
     "pg_wire_polynomials": (_i32, [_vp, _u32, _vp, _i32]),

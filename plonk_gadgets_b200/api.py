@@ -168,6 +168,11 @@ class StandardComposer:
         self._keep += [k1, k2]
         self._ok(self._L.pg_constrain_to_constant_batch(self._ctx, a.col, pc, nc, pp, npi, dev), "pg_constrain_to_constant_batch")
 
+    def range_gate(self, witness: Variables, num_bits: int):
+        """composer.range_gate(witness, num_bits) for every variable of the column [dusk-plonk StandardComposer::range_gate, the native
+        quad-accumulator gate /root/reference/src/range.rs:9-12 recommends for power-of-two bounds]; num_bits even, 2..256."""
+        self._ok(self._L.pg_range_gate_batch(self._ctx, witness.col, int(num_bits)), "pg_range_gate_batch")
+
     def circuit_size(self) -> int:
         r, v = C.c_uint64(), C.c_uint64()
         self._ok(self._L.pg_counts(self._ctx, C.byref(r), C.byref(v)), "pg_counts")
@@ -223,12 +228,27 @@ class StandardComposer:
         self._ok(self._L.pg_materialize_rows(self._ctx, row0, cnt, ptr("w_idx"), ptr("w_val"), ptr("sel"), ptr("pi"), 0), "pg_materialize_rows")
         return out
 
-    def check_rows(self, w_val, sel, pi=None):
-        """Gate equation over caller-supplied materialised rows (host arrays)."""
+    def gate_selectors(self, row0: int = 0, cnt: int | None = None):
+        """(q_arith, q_range), each (cnt,4): 1 / 0 on arithmetic rows, 0 / 1 on the rows of range_gate (0 / 0 on its closing gate)."""
+        cnt = self.circuit_size() - row0 if cnt is None else cnt
+        qa = np.empty((cnt, 4), dtype=np.uint64); qr = np.empty((cnt, 4), dtype=np.uint64)
+        self._ok(self._L.pg_materialize_gate_selectors(self._ctx, row0, cnt, qa.ctypes.data_as(C.c_void_p), qr.ctypes.data_as(C.c_void_p), 0),
+                 "pg_materialize_gate_selectors")
+        return qa, qr
+
+    def check_rows(self, w_val, sel, pi=None, q_arith=None, q_range=None):
+        """Gate equation over caller-supplied materialised rows (host arrays).  With q_arith / q_range (cnt,4) the range widget's
+        term is included (pg_check_rows_ex); without them the arithmetic widget alone."""
         w = np.ascontiguousarray(w_val, dtype=np.uint64); s = np.ascontiguousarray(sel, dtype=np.uint64)
         n = w.shape[1]
         p = np.ascontiguousarray(pi, dtype=np.uint64) if pi is not None else None
         bad, first = C.c_uint64(), C.c_uint64()
+        if q_arith is not None or q_range is not None:
+            qa = np.ascontiguousarray(q_arith, dtype=np.uint64) if q_arith is not None else None
+            qr = np.ascontiguousarray(q_range, dtype=np.uint64) if q_range is not None else None
+            vp = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
+            self._ok(self._L.pg_check_rows_ex(self._ctx, n, vp(w), vp(s), vp(p), vp(qa), vp(qr), 0, C.byref(bad), C.byref(first)), "pg_check_rows_ex")
+            return bad.value, (None if first.value == UINT64_MAX else first.value)
         self._ok(self._L.pg_check_rows(self._ctx, n, w.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p),
                                        p.ctypes.data_as(C.c_void_p) if p is not None else None, 0, C.byref(bad), C.byref(first)), "pg_check_rows")
         return bad.value, (None if first.value == UINT64_MAX else first.value)

@@ -206,6 +206,35 @@ struct ConstrainBody {   // only launched when the constant and/or the public in
     }
 };
 
+// ---------------------------------------------------------------------------------------------------- range_gate
+// Witness side of StandardComposer::range_gate [dusk-plonk 0.8, recalled; SURVEY.md 8f.4, /root/reference/src/range.rs:9-12]: the
+// num_bits/2 accumulators a_j = 4*a_{j-1} + quad_j over the base-4 digits of the canonical witness, most significant quad first
+// (slot j = allocation order).  Bits of the witness above num_bits never enter: then the last accumulator differs from the witness
+// and the closing assert_equal row is what fails.
+struct RangeGateBody {
+    struct Args { DevTab x_tab; uint32_t x_loc; uint4* fr; uint64_t stride; uint64_t n; uint32_t n_acc; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const Fr c = fr_from_mont(loc_load(&a.x_tab, a.x_loc, i));             // to_bytes(): canonical integer
+        const Fr one = fr_one(), two = fr_add(one, one), three = fr_add(two, one);   // BlsScalar::from(quad)
+        Fr acc = fr_zero();
+#pragma unroll
+        for (int limb = 7; limb >= 0; limb--) {                                // limbs by static index: the scalar stays in registers
+#pragma unroll 1
+            for (int sh = 30; sh >= 0; sh -= 2) {
+                const uint32_t bit = 32u * (uint32_t)limb + (uint32_t)sh;      // bit_index = (num_quads - i) << 1, most significant quad first
+                if (bit >= 2u * a.n_acc) continue;
+                const uint32_t quad = (c.v[limb] >> sh) & 3u;                  // q_0 + 2*q_1 (bit is even: both in one limb)
+                acc = fr_add(acc, acc); acc = fr_add(acc, acc);                // four * accumulator
+                Fr q;
+#pragma unroll
+                for (int k = 0; k < 8; k++) q.v[k] = quad == 1u ? one.v[k] : quad == 2u ? two.v[k] : quad == 3u ? three.v[k] : 0u;
+                acc = fr_add(acc, q);
+                tab_store_fr(a.fr, a.stride, a.n_acc - 1u - (bit >> 1), i, acc);
+            }
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------- gate check
 // q_arith*(q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + PI + q_c) for every row of every instance of one segment.
 struct CheckArgs {
@@ -405,10 +434,26 @@ struct SparseProgBody {
     }
 };
 
-// caller-supplied materialised rows (column-major AoS scalars)
+// D(hi - 4*lo), D(f) = f(f-1)(f-2)(f-3): zero iff hi - 4*lo is a base-4 digit (range widget of dusk-plonk, recalled)
+PG_HD Fr range_delta(const Fr& hi, const Fr& lo) {
+    Fr l4 = fr_add(lo, lo); l4 = fr_add(l4, l4);
+    const Fr f = fr_sub(hi, l4), one = fr_one();
+    Fr g = fr_sub(f, one), p = fr_mul(f, g);
+    g = fr_sub(g, one); p = fr_mul(p, g);
+    g = fr_sub(g, one); return fr_mul(p, g);
+}
+PG_HD Fr range_quad_sum(const Fr& a, const Fr& b, const Fr& c, const Fr& d, const Fr& d_next) {
+    Fr sum = fr_add(range_delta(c, d), range_delta(b, c));
+    sum = fr_add(sum, range_delta(a, b));
+    return fr_add(sum, range_delta(d_next, a));
+}
+
+// caller-supplied materialised rows (column-major AoS scalars).  q_arith / q_range null: the arithmetic widget alone (q_arith = 1);
+// otherwise the full  q_arith*(...) + q_range*(sum of the four D terms), d_next = w_4 of row (i+1) mod n.
 struct CheckRowsBody {
-    struct Args { const uint4* w; const uint4* sel; const uint4* pi; uint64_t n; unsigned long long* counters; };
+    struct Args { const uint4* w; const uint4* sel; const uint4* pi; uint64_t n; unsigned long long* counters; const uint4* q_arith; const uint4* q_range; };
     PG_HD static uint32_t run(const Args& a, uint64_t i) {
+        if (a.q_arith || a.q_range) return run_ex(a, i);
         Fr w[5], sel[5];
         w[1] = aos_load(a.w, i); w[2] = aos_load(a.w, a.n + i); w[3] = aos_load(a.w, 2 * a.n + i); w[4] = aos_load(a.w, 3 * a.n + i);
         sel[0] = fr_add_noreduce(fr_mul(aos_load(a.sel, i), w[2]), aos_load(a.sel, a.n + i));         // q_m*b + q_l
@@ -419,6 +464,58 @@ struct CheckRowsBody {
         add9_fr(t, aos_load(a.sel, 5 * a.n + i));
         if (a.pi) add9_fr(t, aos_load(a.pi, i));
         return limbs9_is_multiple_of_q(t) ? 0u : 1u;
+    }
+    PG_HD static uint32_t run_ex(const Args& a, uint64_t i) {
+        const Fr wa = aos_load(a.w, i), wb = aos_load(a.w, a.n + i), wc = aos_load(a.w, 2 * a.n + i), wd = aos_load(a.w, 3 * a.n + i);
+        Fr t = fr_mul(fr_mul(aos_load(a.sel, i), wa), wb);
+        t = fr_add(t, fr_mul(aos_load(a.sel, a.n + i), wa)); t = fr_add(t, fr_mul(aos_load(a.sel, 2 * a.n + i), wb));
+        t = fr_add(t, fr_mul(aos_load(a.sel, 3 * a.n + i), wc)); t = fr_add(t, fr_mul(aos_load(a.sel, 4 * a.n + i), wd));
+        if (a.pi) t = fr_add(t, aos_load(a.pi, i));
+        t = fr_add(t, aos_load(a.sel, 5 * a.n + i));
+        if (a.q_arith) t = fr_mul(aos_load(a.q_arith, i), t);
+        if (a.q_range) {
+            const Fr qr = aos_load(a.q_range, i);
+            if (!fr_is_zero(qr)) t = fr_add(t, fr_mul(qr, range_quad_sum(wa, wb, wc, wd, aos_load(a.w, 3 * a.n + (i + 1 == a.n ? 0 : i + 1)))));
+        }
+        return fr_is_zero(t) ? 0u : 1u;
+    }
+};
+
+// Segments that hold rows of another widget (GATE_RANGE / GATE_NONE, layout.h): one thread per (row, instance), lanes = instances.
+//   arithmetic rows: the same factored evaluation as the generic kernel;
+//   range rows     : q_range*(delta(c - 4d) + delta(b - 4c) + delta(a - 4b) + delta(d_next - 4a)), delta(f) = f(f-1)(f-2)(f-3), with
+//                    d_next the fourth wire of the NEXT row [dusk-plonk check_circuit_satisfied / range widget, recalled] -- inside a
+//                    template a range row is never the last one (range_gate closes with a q_range = 0 gate and assert_equal);
+//   rows with neither selector hold trivially.
+struct GateRowsCheckBody {
+    struct Args { CheckArgs c; uint64_t n; };
+    PG_HD static void run(const Args& g, uint64_t t) {
+        const CheckArgs& a = g.c;
+        const uint32_t r = (uint32_t)(t / a.n_inst); const uint64_t i = t - (uint64_t)r * a.n_inst;
+        const DevRow row = a.rows[r];
+        bool ok = true;
+        if (row.gate == GATE_ARITH) {
+            Fr w[5], sel[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
+            sel[0] = fr_add_noreduce(fr_mul(pool_load(a.pool, row.sel[0]), w[2]), pool_load(a.pool, row.sel[1]));   // q_m*b + q_l
+#pragma unroll
+            for (int k = 1; k < 4; k++) sel[k] = pool_load(a.pool, row.sel[k + 1]);                                   // q_r q_o q_4
+            uint32_t s[9];
+            fr_dot_wide<4>(s, w + 1, sel);
+            add9_fr(s, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool_load(a.pool, row.sel[5]));
+            if (row.pi_param >= 0) add9_fr(s, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
+            else if (row.pi_sel != POOL_ZERO) add9_fr(s, pool_load(a.pool, row.pi_sel));
+            ok = limbs9_is_multiple_of_q(s);
+        } else if (row.gate == GATE_RANGE) {
+            const Fr wa = row_load(row, 0, i), wb = row_load(row, 1, i), wc = row_load(row, 2, i), wd = row_load(row, 3, i);
+            const Fr dn = r + 1 < a.n_rows ? row_load(a.rows[r + 1], 3, i) : fr_zero();
+            ok = fr_is_zero(range_quad_sum(wa, wb, wc, wd, dn));
+        }
+        if (!ok) {
+            counter_add(a.counters + CNT_UNSAT, 1ull);
+            counter_min(a.counters + CNT_FIRST_BAD, (unsigned long long)(a.base_row + i * (uint64_t)a.n_rows + r));
+        }
     }
 };
 
@@ -491,6 +588,17 @@ struct MaterializeBody {
                                                                           : pool_load(s.pool, row.pi_sel));
     }
 };
+// q_arith and q_range columns of rows [row0, row0 + n): one (R = BlsScalar::one()) or zero per row kind
+struct GateSelBody {
+    struct Args { const DevSeg* segs; uint32_t n_segs; uint64_t row0; uint64_t n; uint4* q_arith; uint4* q_range; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        const uint64_t g = a.row0 + t;
+        const DevSeg& s = a.segs[seg_find(a.segs, a.n_segs, g, true)];
+        const uint32_t gate = s.rows[(uint32_t)((g - s.base_row) % s.n_rows)].gate;
+        if (a.q_arith) aos_store(a.q_arith, t, gate == GATE_ARITH ? fr_one() : fr_zero());
+        if (a.q_range) aos_store(a.q_range, t, gate == GATE_RANGE ? fr_one() : fr_zero());
+    }
+};
 // whole instances [inst0, inst0 + n_inst) of ONE segment, written from column offset out_off (row of instance inst0, local row 0)
 struct MatTileArgs { DevSeg seg; uint64_t inst0, n_inst; uint64_t stride, out_off; uint4* w_val; uint4* sel; };
 
@@ -503,6 +611,7 @@ struct MatTileArgs { DevSeg seg; uint64_t inst0, n_inst; uint64_t stride, out_of
 // call order; the zero variable's uses are chained through every instance of every segment.
 // Positions are encoded as row*4 + wire (wire: 0 = w_l, 1 = w_r, 2 = w_o, 3 = w_4).
 constexpr uint32_t PERM_NONE = 0xffffffffu;
+constexpr uint32_t PERM_REF_UNMAPPED = 0x7fffffffu;   // `ref` of a wire position that was never entered in the map: a fixed point of sigma
 struct PermCons { uint32_t seg, op; uint64_t inst_off, n; uint32_t next; uint32_t pad; };   // a consumer of a column: segment `seg` binds it as operand `op`
 struct PermSeg {
     uint64_t base_row, n_inst; uint32_t n_rows, pad;
@@ -551,7 +660,8 @@ struct PermBody {
         for (uint32_t w = 0; w < 4; w++) {
             const uint32_t ref = s.ref[r * 4 + w], nxt = s.next_in_inst[r * 4 + w];
             unsigned long long out;
-            if (nxt != PERM_NONE) out = (s.base_row + i * s.n_rows + (nxt >> 2)) * 4ull + (nxt & 3u);
+            if (ref == PERM_REF_UNMAPPED) out = g * 4ull + w;
+            else if (nxt != PERM_NONE) out = (s.base_row + i * s.n_rows + (nxt >> 2)) * 4ull + (nxt & 3u);
             else if (ref == 0) {                                 // zero variable: next instance, next segment, or wrap to the very first use
                 if (i + 1 < s.n_inst) out = (s.base_row + (i + 1) * s.n_rows + (s.first_zero >> 2)) * 4ull + (s.first_zero & 3u);
                 else {

@@ -65,12 +65,20 @@ int pg_constrain_to_constant_batch(pg_ctx* ctx, pg_col a, const pg_fr* constant,
     return ctx->e.constrain_batch(a, constant, n_const, pi, n_pi, on_device);
 }
 
+int pg_range_gate_batch(pg_ctx* ctx, pg_col witness, uint32_t num_bits) { PG_NEED_CTX(ctx); return ctx->e.range_gate_batch(witness, num_bits); }
+
 int pg_check(pg_ctx* ctx, uint64_t* n_unsat, uint64_t* first_bad_row) { PG_NEED_CTX(ctx); return ctx->e.check(n_unsat, first_bad_row); }
 int pg_check_rows(pg_ctx* ctx, uint64_t n, const pg_fr* w_val, const pg_fr* sel, const pg_fr* pi, int on_device, uint64_t* n_unsat, uint64_t* first_bad_row) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, w_val, on_device); PG_ALIGNED(ctx, sel, on_device); PG_ALIGNED(ctx, pi, on_device);
     return ctx->e.check_rows(n, w_val, sel, pi, on_device, n_unsat, first_bad_row);
 }
 
+int pg_check_rows_ex(pg_ctx* ctx, uint64_t n, const pg_fr* w_val, const pg_fr* sel, const pg_fr* pi, const pg_fr* q_arith, const pg_fr* q_range,
+                     int on_device, uint64_t* n_unsat, uint64_t* first_bad_row) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, w_val, on_device); PG_ALIGNED(ctx, sel, on_device); PG_ALIGNED(ctx, pi, on_device);
+    PG_ALIGNED(ctx, q_arith, on_device); PG_ALIGNED(ctx, q_range, on_device);
+    return ctx->e.check_rows(n, w_val, sel, pi, on_device, n_unsat, first_bad_row, q_arith, q_range);
+}
 int pg_counts(const pg_ctx* ctx, uint64_t* n_rows, uint64_t* n_vars) {
     PG_NEED_CTX(ctx);
     if (n_rows) *n_rows = ctx->e.n_rows;
@@ -99,6 +107,11 @@ int pg_read_variables(pg_ctx* ctx, uint64_t var0, uint64_t cnt, pg_fr* dst, int 
 int pg_materialize_rows(pg_ctx* ctx, uint64_t row0, uint64_t cnt, uint64_t* w_idx, pg_fr* w_val, pg_fr* sel, pg_fr* pi, int dst_on_device) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, w_val, dst_on_device); PG_ALIGNED(ctx, sel, dst_on_device); PG_ALIGNED(ctx, pi, dst_on_device);
     return ctx->e.materialize(row0, cnt, w_idx, w_val, sel, pi, dst_on_device);
+}
+
+int pg_materialize_gate_selectors(pg_ctx* ctx, uint64_t row0, uint64_t cnt, pg_fr* q_arith, pg_fr* q_range, int dst_on_device) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, q_arith, dst_on_device); PG_ALIGNED(ctx, q_range, dst_on_device);
+    return ctx->e.gate_selectors(row0, cnt, q_arith, q_range, dst_on_device);
 }
 
 int pg_permutation(pg_ctx* ctx, uint64_t row0, uint64_t cnt, uint64_t* sigma, int dst_on_device) {

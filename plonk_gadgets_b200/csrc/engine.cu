@@ -160,7 +160,7 @@ public:
     // ---- launches ------------------------------------------------------------------------------------------------
     template <class Body>
     bool run_simple(const typename Body::Args& a, uint64_t n, int cls) {
-        tic(cls, 0);
+        tic(cls, cls == CLS_CHECK ? n : 0);          // a check body run this way evaluates one row per thread
         k_simple<Body><<<grid_for(n), BLOCK, 0, stream>>>(a);
         toc();
         return launched("k_simple");

@@ -44,6 +44,7 @@ struct Segment {
     std::vector<DevRow> rows;
     std::vector<SpOp> sp_ops; SpOp* d_sp = nullptr;    // structure-aware row program (PG_CHECK_SPARSE only)
     std::vector<Column> operands;       // the columns bound as operands (for the permutation map)
+    bool other_gates = false;           // some row belongs to another widget than the arithmetic one (GATE_RANGE / GATE_NONE)
 };
 
 inline Fr fr_from_pg(const pg_fr& x) {
@@ -253,7 +254,8 @@ public:
                 else { const uint32_t e = wr.src - 2u; d.loc[w] = loc_with_tab(loc_of(operands[e]), e + 1); d.var[w] = operands[e].local; }
             }
             for (int k = 0; k < 6; k++) d.sel[k] = src.sel[k];
-            d.pi_sel = src.pi_sel; d.qc_param = src.qc_param; d.pi_param = src.pi_param;
+            d.pi_sel = src.pi_sel; d.qc_param = src.qc_param; d.pi_param = src.pi_param; d.gate = src.gate;
+            if (src.gate != GATE_ARITH) s.other_gates = true;
             for (int w = 0; w < 4; w++) {            // instance-0 address of each wire value (see DevRow::addr)
                 const uint32_t kind = loc_kind(d.loc[w]), pay = loc_payload(d.loc[w]);
                 const DevTab& tb = s.tabs[loc_tab(d.loc[w])];
@@ -263,7 +265,7 @@ public:
             }
             s.rows[r] = d;
         }
-        if (cfg.check_mode == PG_CHECK_SPARSE) build_sparse_program(s);
+        if (cfg.check_mode == PG_CHECK_SPARSE && !s.other_gates) build_sparse_program(s);   // segments with range rows have their own check body
         // rows | variable map | selector pool | structure-aware program go up in ONE copy (one staging image per segment)
         const size_t b_rows = s.rows.size() * sizeof(DevRow), b_var = (T.var_loc.size() * sizeof(uint32_t) + 31) & ~(size_t)31, b_pool = T.pool.size() * sizeof(Fr);
         const size_t b_sp = s.sp_ops.size() * sizeof(SpOp);
@@ -478,6 +480,20 @@ public:
         return PG_OK;
     }
 
+    // for i { composer.range_gate(witness_i, num_bits) } -- dusk-plonk's native range gate, see tmpl_range_gate
+    int range_gate_batch(pg_col cw, uint32_t num_bits) {
+        const Column* w = column(cw);
+        if (!w) return fail(PG_ERR_ARG, "range_gate_batch: unknown column");
+        if (num_bits % 2 != 0 || num_bits < 2 || num_bits > 256) return fail(PG_ERR_ARG, "range_gate_batch: num_bits must be even and in 2..256");
+        Column operand = *w; const uint64_t n = operand.n;
+        int rc = push_segment(make_range_gate_template(num_bits), n, &operand, 1);
+        if (rc) return rc;
+        Segment& s = segs.back();
+        RangeGateBody::Args g{s.tabs[1], loc_with_tab(loc_of(operand), 0), s.fr, s.n_alloc, n, num_bits / 2};
+        if (n && !be.template run_simple<RangeGateBody>(g, n, CLS_WITNESS)) return fail(PG_ERR_CUDA, "range_gate witness kernel");
+        return PG_OK;
+    }
+
     int constrain_batch(pg_col ca, const pg_fr* constant, uint64_t n_const, const pg_fr* pi, uint64_t n_pi, int on_device) {
         const Column* a = column(ca);
         if (!a || !constant) return fail(PG_ERR_ARG, "constrain_to_constant_batch: bad argument");
@@ -512,6 +528,11 @@ public:
             a.param = s.param; a.param_stride = s.n_alloc; a.rows = s.d_rows; a.pool = s.d_pool;
             a.n_rows = (uint32_t)s.t.rows.size(); a.n_pool = (uint32_t)s.t.pool.size();
             a.n_inst = s.n_inst; a.base_row = s.base_row; a.counters = d_counters; a.mode = cfg.check_mode;
+            if (s.other_gates) {                     // rows of the range widget: per-row body, one thread per (row, instance)
+                GateRowsCheckBody::Args g{a, a.n_inst * a.n_rows};
+                if (!be.template run_simple<GateRowsCheckBody>(g, g.n, CLS_CHECK)) return fail(PG_ERR_CUDA, "gate-check kernel (range rows)");
+                continue;
+            }
             const SparseProg prog{s.d_sp, (uint32_t)s.sp_ops.size()};
             if (!be.run_check(a, prog)) return fail(PG_ERR_CUDA, "gate-check kernel");
         }
@@ -521,7 +542,8 @@ public:
         if (first_bad) *first_bad = c[CNT_FIRST_BAD];
         return PG_OK;
     }
-    int check_rows(uint64_t n, const pg_fr* w, const pg_fr* sel, const pg_fr* pi, int on_device, uint64_t* n_unsat, uint64_t* first_bad) {
+    int check_rows(uint64_t n, const pg_fr* w, const pg_fr* sel, const pg_fr* pi, int on_device, uint64_t* n_unsat, uint64_t* first_bad,
+                   const pg_fr* q_arith = nullptr, const pg_fr* q_range = nullptr) {
         if (n && (!w || !sel)) return fail(PG_ERR_ARG, "check_rows: null argument");
         int rc = reset_counters();
         if (rc) return rc;
@@ -530,7 +552,10 @@ public:
             const uint4* ds = stage(sel, 6 * n, on_device, &rc); if (!ds) return rc;
             const uint4* dp = nullptr;
             if (pi) { dp = stage(pi, n, on_device, &rc); if (!dp) return rc; }
-            CheckRowsBody::Args a{dw, ds, dp, n, d_counters};
+            const uint4 *da = nullptr, *dr = nullptr;
+            if (q_arith) { da = stage(q_arith, n, on_device, &rc); if (!da) return rc; }
+            if (q_range) { dr = stage(q_range, n, on_device, &rc); if (!dr) return rc; }
+            CheckRowsBody::Args a{dw, ds, dp, n, d_counters, da, dr};
             if (!be.run_check_rows(a)) return fail(PG_ERR_CUDA, "row-check kernel");
         }
         unsigned long long c[CNT_WORDS];
@@ -636,6 +661,29 @@ public:
         if (sel && (rc = deliver(sel, d_sel, 6 * cnt * sizeof(pg_fr), 0))) return rc;
         if (pi && (rc = deliver(pi, d_pi, cnt * sizeof(pg_fr), 0))) return rc;
         if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
+        release_scratch_from(mark);
+        return PG_OK;
+    }
+
+    // q_arith / q_range columns of rows [row0, row0 + cnt) (either may be null)
+    int gate_selectors(uint64_t row0, uint64_t cnt, pg_fr* q_arith, pg_fr* q_range, int dst_on_device) {
+        if (row0 + cnt > n_rows) return fail(PG_ERR_ARG, "materialize_gate_selectors: range");
+        if (!cnt || (!q_arith && !q_range)) return PG_OK;
+        const size_t mark = scratch.size();
+        auto buf = [&](void* user) -> uint4* {
+            if (!user) return nullptr;
+            if (dst_on_device) return (uint4*)user;
+            void* p = dalloc(cnt * sizeof(pg_fr)); if (p) scratch.push_back(p); return (uint4*)p;
+        };
+        uint4 *d_a = buf(q_arith), *d_r = buf(q_range);
+        if ((q_arith && !d_a) || (q_range && !d_r)) return fail(PG_ERR_OOM, "gate selector buffers");
+        { const int rcs = sync_dsegs(); if (rcs) return rcs; }
+        GateSelBody::Args a{d_segs, (uint32_t)dsegs.size(), row0, cnt, d_a, d_r};
+        if (!be.template run_simple<GateSelBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "gate selector kernel");
+        if (dst_on_device) return PG_OK;
+        int rc;
+        if (q_arith && (rc = deliver(q_arith, d_a, cnt * sizeof(pg_fr), 0))) return rc;
+        if (q_range && (rc = deliver(q_range, d_r, cnt * sizeof(pg_fr), 0))) return rc;
         release_scratch_from(mark);
         return PG_OK;
     }
@@ -753,8 +801,13 @@ public:
             ref[k].assign(NW, 0); next_in[k].assign(NW, PERM_NONE); first_local[k].assign(T.n_vars, PERM_NONE);
             std::vector<uint32_t> last_local(T.n_vars, PERM_NONE); uint32_t last_op[4] = {PERM_NONE, PERM_NONE, PERM_NONE, PERM_NONE}, last_zero = PERM_NONE;
             for (size_t r = 0; r < T.rows.size(); r++)
-                for (uint32_t w = 0; w < 4; w++) {
+                for (uint32_t ow = 0; ow < 4; ow++) {
+                    // order in which the row's wires entered perm.variable_map (templates.hpp PERM_*): a, b, c, d for the arithmetic
+                    // gate methods; fourth, output, right, left for range_gate, whose closing gate enters its fourth wire only
+                    const uint8_t pm = T.rows[r].perm;
+                    const uint32_t w = pm == PERM_LROF ? ow : 3u - ow;
                     const WireRef& wr = T.rows[r].w[w]; const uint32_t pos = (uint32_t)(r * 4 + w);
+                    if (pm == PERM_F_ONLY && w != 3u) { ref[k][pos] = PERM_REF_UNMAPPED; continue; }
                     uint32_t* last; uint32_t* first;
                     if (wr.src == 0 || (T.kind == G_PREAMBLE && wr.src == 1 && wr.idx == 0)) { ref[k][pos] = 0; last = &last_zero; first = &p.first_zero; }
                     else if (wr.src == 1) { ref[k][pos] = 1 + wr.idx; last = &last_local[wr.idx]; first = &first_local[k][wr.idx]; }

@@ -49,13 +49,19 @@ struct DevRow {               // 96 bytes
     uint16_t pi_sel;          // pool index of a uniform public input (0 = the constant zero = no PI)
     int16_t qc_param;         // >= 0: q_c is param slot qc_param of the instance (sel[5] ignored)
     int16_t pi_param;         // >= 0: PI is param slot pi_param of the instance
-    uint16_t pad[7];
+    uint16_t gate;            // GATE_ARITH (q_arith = 1), GATE_RANGE (q_range = 1, q_arith = 0) or GATE_NONE (both 0)
+    uint16_t pad[6];
     // pre-resolved device address of instance 0 of each wire value (FR: the 32-byte scalar; BIT: the 32-bit word holding the
     // bit; ZERO: 0).  The gate-check kernel adds i*32 (or i*4) and never touches the table descriptors: no per-row
     // slot*stride products on the multiplier pipe.
     uint64_t addr[4];
 };
 static_assert(sizeof(DevRow) == 96, "DevRow must stay 96 bytes");
+
+// Which widget's selector is switched on for a row.  The six gadgets of the reference only emit arithmetic rows; dusk-plonk's native
+// range_gate emits rows with q_range = 1 (every selector of the arithmetic widget 0) and one closing row with
+// neither.  Segments that contain such rows are checked by GateRowsCheckBody (bodies.cuh), all others by the k_check kernels.
+enum : uint16_t { GATE_ARITH = 0, GATE_RANGE = 1, GATE_NONE = 2 };
 
 // ---- structure-aware row program (PG_CHECK_SPARSE) ----------------------------------------------------------------------
 // The rows of a template compiled, once per segment on the host, into a linear list of term operations (bodies.cuh,

@@ -19,7 +19,7 @@ namespace pg {
 
 enum GadgetKind : int {
     G_PREAMBLE = 0, G_ADD_INPUT, G_RANGE_CHECK, G_MAX_BOUND, G_MAYBE_EQUAL, G_IS_NON_ZERO, G_IS_NON_ZERO_PARTIAL,
-    G_SELECT_ZERO, G_SELECT_ONE, G_CONSTRAIN
+    G_SELECT_ZERO, G_SELECT_ONE, G_CONSTRAIN, G_RANGE_GATE
 };
 
 // symbolic Variable: the zero variable, a local variable of this gadget instance, or an operand (a Variable that existed
@@ -34,7 +34,11 @@ struct SelRef { uint16_t pool; int16_t param; };
 inline SelRef S_POOL(uint16_t p) { SelRef s = {p, -1}; return s; }
 inline SelRef S_PARAM(int16_t p) { SelRef s = {POOL_ZERO, p}; return s; }
 
-struct RowT { WireRef w[4]; uint16_t sel[6]; uint16_t pi_sel; int16_t qc_param; int16_t pi_param; };
+// gate: GATE_* (layout.h).  perm: how the row enters perm.variable_map -- PERM_LROF: add_variables_to_map(a, b, c, d) (every arithmetic
+// gate method); PERM_FORL: range_gate's add_wire order Fourth, Output, Right, Left; PERM_F_ONLY: range_gate's closing gate, whose
+// w_l, w_r, w_o are pushed without a map entry (their positions stay fixed points of sigma).
+enum : uint8_t { PERM_LROF = 0, PERM_FORL = 1, PERM_F_ONLY = 2 };
+struct RowT { WireRef w[4]; uint16_t sel[6]; uint16_t pi_sel; int16_t qc_param; int16_t pi_param; uint8_t gate; uint8_t perm; };
 
 struct Template {
     int kind = 0; uint32_t k = 0;
@@ -85,8 +89,14 @@ public:
                   SelRef q_c, SelRef pi) {
         RowT r; r.w[0] = a; r.w[1] = b; r.w[2] = c; r.w[3] = d;
         r.sel[0] = q_m; r.sel[1] = q_l; r.sel[2] = q_r; r.sel[3] = q_o; r.sel[4] = q_4; r.sel[5] = q_c.pool;
-        r.qc_param = q_c.param; r.pi_sel = pi.pool; r.pi_param = pi.param;
+        r.qc_param = q_c.param; r.pi_sel = pi.pool; r.pi_param = pi.param; r.gate = GATE_ARITH; r.perm = PERM_LROF;
         t.rows.push_back(r);
+    }
+    // a gate of range_gate: wires given in the order the quads are laid out (w_4, w_o, w_r, w_l), every arithmetic selector 0
+    void push_range_row(WireRef d, WireRef o, WireRef r_, WireRef l, bool last) {
+        push_row(l, r_, o, d, POOL_ZERO, POOL_ZERO, POOL_ZERO, POOL_ZERO, POOL_ZERO, S_POOL(POOL_ZERO), S_POOL(POOL_ZERO));
+        t.rows.back().gate = last ? GATE_NONE : GATE_RANGE;
+        t.rows.back().perm = last ? PERM_F_ONLY : PERM_FORL;
     }
     // poly_gate(a,b,c,q_m,q_l,q_r,q_o,q_c,pi): wires (a,b,c,zero_var), q_4 = 0
     void poly_gate(WireRef a, WireRef b, WireRef c, uint16_t q_m, uint16_t q_l, uint16_t q_r, uint16_t q_o, SelRef q_c, SelRef pi = S_POOL(POOL_ZERO)) {
@@ -195,6 +205,26 @@ inline WireRef tmpl_range_check(TemplateComposer& c, uint32_t k, WireRef witness
     return o;
 }
 
+// ---- dusk-plonk's native range gate --------------------------------------------------------------------------
+// StandardComposer::range_gate(witness, num_bits) [dusk-plonk 0.8 src/constraint_system/range.rs, recalled], the path
+// /root/reference/src/range.rs:9-12 recommends when the bound is a power of two.  num_bits even, 2..256.
+//   num_gates = ceil(num_bits / 8), num_quads = 4 * num_gates, pad = 1 + (2 * num_quads - num_bits) / 2   (1..4 zero wires first)
+//   positions 0..=num_quads: `pad` times the zero variable, then the num_bits/2 accumulators (new variables, most significant
+//   quad first); position i sits in gate i/4 on wire w_4, w_o, w_r, w_l for i%4 = 0, 1, 2, 3; the closing gate holds the last
+//   accumulator on w_4 and zero wires elsewhere and has q_range = 0; then assert_equal(last accumulator, witness).
+// Rows: num_gates + 2, variables: num_bits / 2.
+inline void tmpl_range_gate(TemplateComposer& c, WireRef witness, uint32_t num_bits) {
+    uint32_t num_gates = num_bits >> 3;
+    if (num_bits % 8 != 0) num_gates += 1;
+    const uint32_t num_quads = num_gates * 4;
+    const uint32_t pad = 1 + (((num_quads << 1) - num_bits) >> 1);
+    std::vector<WireRef> pos(num_quads + 1, W_ZERO());
+    for (uint32_t i = pad; i <= num_quads; i++) pos[i] = c.add_input();
+    for (uint32_t g = 0; g < num_gates; g++) c.push_range_row(pos[4 * g], pos[4 * g + 1], pos[4 * g + 2], pos[4 * g + 3], false);
+    c.push_range_row(pos[num_quads], W_ZERO(), W_ZERO(), W_ZERO(), true);
+    c.assert_equal(pos[num_quads], witness);
+}
+
 // ---- whole-call templates ------------------------------------------------------------------------------------------------
 // uniform bounds: m / negmin are constants; otherwise two per-instance parameter slots
 inline Template make_range_template(bool range_check, uint32_t k, bool uniform, const Fr& m, const Fr& negmin, uint32_t* result_local) {
@@ -219,6 +249,11 @@ inline Template make_is_non_zero_template(bool partial) {
 inline Template make_select_template(bool one, uint32_t* result_local) {
     TemplateComposer c; c.t.kind = one ? G_SELECT_ONE : G_SELECT_ZERO; c.t.n_operands = 2;
     *result_local = (one ? tmpl_select_one(c, W_OPERAND(0), W_OPERAND(1)) : tmpl_select_zero(c, W_OPERAND(0), W_OPERAND(1))).idx;
+    return c.t;
+}
+inline Template make_range_gate_template(uint32_t num_bits) {
+    TemplateComposer c; c.t.kind = G_RANGE_GATE; c.t.k = num_bits; c.t.n_operands = 1;
+    tmpl_range_gate(c, W_OPERAND(0), num_bits);
     return c.t;
 }
 inline Template make_add_input_template() {

@@ -89,6 +89,8 @@ public:
         ok(pg_add_input_batch(ctx_, v.n, reinterpret_cast<const pg_fr*>(scalars.data()), 0, &v.col), "pg_add_input_batch");
         return v;
     }
+    /// composer.range_gate(witness, num_bits) per instance [dusk-plonk; recommended at /root/reference/src/range.rs:9-12]
+    void range_gate(Variables witness, size_t num_bits) { ok(pg_range_gate_batch(ctx_, witness.col, (uint32_t)num_bits), "pg_range_gate_batch"); }
     /// composer.constrain_to_constant(a, constant, pi) per instance; `pi` empty = None
     void constrain_to_constant(Variables a, const std::vector<BlsScalar>& constant, const std::vector<BlsScalar>& pi = {}) {
         ok(pg_constrain_to_constant_batch(ctx_, a.col, reinterpret_cast<const pg_fr*>(constant.data()), constant.size(),

@@ -166,8 +166,29 @@ static void prover_first_round_test() {
     EXPECT(composer.fft(evals, true) == col, "ifft(fft(x)) == x");
 }
 
+// The native range gate the reference points to for power-of-two bounds (range.rs:9-12): composer.range_gate(witness, num_bits)
+// is satisfied iff the witness fits num_bits.  One composer per case, as a failing case spoils the whole circuit.
+static void range_gate_test() {
+    struct TestCase { BlsScalar witness; size_t num_bits; bool fits; };
+    std::vector<TestCase> cases = {
+        {BlsScalar::from(0), 2, true}, {BlsScalar::from(3), 2, true}, {BlsScalar::from(4), 2, false},
+        {BlsScalar::from(1023), 10, true}, {BlsScalar::from(1024), 10, false},
+        {two_pow(64) - BlsScalar::one(), 64, true}, {two_pow(64), 64, false},
+        {BlsScalar::zero() - BlsScalar::one(), 254, false}, {BlsScalar::zero() - BlsScalar::one(), 256, true},
+    };
+    for (auto& tc : cases) {
+        StandardComposer composer;
+        const uint64_t rows0 = composer.circuit_size();
+        auto witness = AllocatedScalar::allocate(composer, {tc.witness});
+        composer.range_gate(witness.var, tc.num_bits);
+        EXPECT(composer.circuit_size() - rows0 == (tc.num_bits + 7) / 8 + 2, "range_gate rows");
+        EXPECT((composer.check_circuit_satisfied().first == 0) == tc.fits, "range_gate verdict");
+    }
+}
+
 int main() {
     try {
+        range_gate_test();
         max_bound_test(); range_check_test(); test_maybe_equal();
         test_conditionally_select_0(); test_conditionally_select_1(); test_is_not_zero();
         prover_first_round_test();

@@ -32,6 +32,8 @@ def run_engine(program, make_composer, ob, return_composer: bool = False):
             cols[idx] = pg.conditionally_select_zero(c, cols[op["x"]], cols[op["select"]])
         elif kind == "select_one":
             cols[idx] = pg.conditionally_select_one(c, cols[op["y"]], cols[op["select"]])
+        elif kind == "range_gate":
+            c.range_gate(cols[op["witness"]], int(op["num_bits"]))
         elif kind == "constrain_to_constant":
             pi = ob.from_ints(_vals(op, "pi")) if op.get("pi") is not None else None
             c.constrain_to_constant(cols[op["a"]], ob.from_ints(_vals(op, "constant")), pi)
@@ -47,8 +49,10 @@ def snapshot_of_engine(c, cols, error, ob) -> Snapshot:
     rows = c.rows()
     one = ob.from_ints([1])[0]
     sel = [ob.to_ints(rows["sel"][k]) for k in range(6)]
-    # q_arith = 1 and the four non-arithmetic selectors = 0 on every row (include/pg_b200.h, pg_materialize_rows)
-    sel += [[1] * n_rows] + [[0] * n_rows] * 4
+    # q_arith / q_range from the engine (pg_materialize_gate_selectors); q_logic and the two group-addition selectors are 0 on
+    # every row (include/pg_b200.h, pg_materialize_rows)
+    q_arith, q_range = c.gate_selectors()
+    sel += [ob.to_ints(q_arith), ob.to_ints(q_range)] + [[0] * n_rows] * 3
     assert len(sel) == len(SEL_NAMES) and int(one[0]) != 0
     snap = Snapshot(n_rows, n_vars, variables, rows["w_idx"], sel, ob.to_ints(rows["pi"]), [],
                     {k: [int(x) for x in v.ids()] for k, v in cols.items()}, error)
@@ -61,6 +65,10 @@ def snapshot_of_engine(c, cols, error, ob) -> Snapshot:
     for w in range(4):
         assert ob.to_ints(wv[w]) == [variables[int(i)] for i in rows["w_idx"][w]], f"wire values of column {w}"
     # and the stand-alone row checker must agree on the materialised rows
-    bad2, first2 = c.check_rows(rows["w_val"], rows["sel"], rows["pi"])
+    bad2, first2 = c.check_rows(rows["w_val"], rows["sel"], rows["pi"], q_arith, q_range)
     assert (bad2, first2) == (bad, first), (bad2, first2, bad, first)
+    # without the gate selectors it evaluates the arithmetic widget alone (q_arith = 1): same verdict on the arithmetic rows
+    bad3, first3 = c.check_rows(rows["w_val"], rows["sel"], rows["pi"])
+    arith_bad = [r for r in snap.unsat if sel[6][r]]
+    assert (bad3, first3) == (len(arith_bad), arith_bad[0] if arith_bad else None), (bad3, first3, bad, first)
     return snap

@@ -259,3 +259,20 @@ def test_emu_sparse_program_on_batches(emu, oracle):
     for mode in (pg.CHECK_GENERIC, pg.CHECK_SPARSE):
         snap = run_engine(prog, lambda: pg.StandardComposer(check_mode=mode, _cdll=emu), oracle)
         assert snap.unsat == ref.unsat and snap.digest() == ref.digest(), mode
+
+
+# ---- dusk-plonk's native range gate --------------------------------------------------------------------------
+from tests import range_gate_cases as rgc  # noqa: E402
+
+
+@pytest.mark.parametrize("bits", rgc.WIDTHS)
+def test_emu_range_gate_vs_oracle(emu, oracle, bits):
+    rgc.vs_oracle(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle, bits)
+
+
+def test_emu_range_gate_bad_arguments(emu, oracle):
+    rgc.bad_arguments(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)
+
+
+def test_emu_range_gate_fault_injection(emu, oracle):
+    rgc.fault_injection(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)

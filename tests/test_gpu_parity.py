@@ -658,3 +658,53 @@ def test_msm_skewed_scalars_gpu(oracle, torch_cuda):
     np.add.at(per_point, (i % m).astype(np.int64), sc_int)
     want = oracle.g1_msm(to_oracle(table), oracle.from_ints([int(v) % Q for v in per_point]))
     assert np.array_equal(to_oracle(got.reshape(1, 12)), want)
+
+
+# ---- dusk-plonk's native range gate --------------------------------------------------------------------------
+from tests import range_gate_cases as rgc  # noqa: E402
+
+
+@pytest.mark.parametrize("bits", rgc.WIDTHS)
+def test_range_gate_vs_oracle(oracle, bits):
+    rgc.vs_oracle(gpu_composer, oracle, bits)
+
+
+def test_range_gate_bad_arguments(oracle):
+    rgc.bad_arguments(gpu_composer, oracle)
+
+
+def test_range_gate_fault_injection(oracle):
+    rgc.fault_injection(gpu_composer, oracle)
+
+
+@pytest.mark.parametrize("mode", [pg.CHECK_GENERIC, pg.CHECK_SPARSE])
+def test_range_gate_at_scale(oracle, torch_cuda, mode):
+    """2^22 instances of the 64-bit range gate (10 rows, 32 accumulators each): even instances (uniform u64) fit, odd ones (uniform
+    Fr) do not, so exactly the closing assert_equal rows of the odd instances fail; accumulators of sampled instances against the
+    oracle; then the same on in-range witnesses only: satisfied."""
+    torch = torch_cuda
+    n = 1 << 22
+    c = gpu_composer(check_mode=mode)
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    c.synth(SEED, 7, 2, 64, wit)
+    w = c.add_input(wit)
+    c.range_gate(w, 64)
+    assert c.circuit_size() == 3 + 10 * n and c.num_variables() == 5 + n + 32 * n
+    assert c.check_circuit_satisfied() == (n // 2, 3 + 10 + 9)
+    wv = w.values()
+    rng = random.Random(64)
+    for i in [0, 1, n - 2, n - 1] + [rng.randrange(n) for _ in range(12)]:
+        oc = oracle.Composer()
+        oc.range_gate_batch(oc.add_input_batch(wv[i:i + 1]), 64)
+        assert (oc.variables()[6:] == c.variables(5 + n + 32 * i, 32)).all(), f"accumulators of instance {i}"
+        rows = c.rows(3 + 10 * i, 10, want=("w_idx",))
+        o_w = oc.wires()[:, 3:]
+        remap = np.where(o_w == 0, 0, np.where(o_w == 5, 5 + i, o_w - 6 + 5 + n + 32 * i)).astype(np.uint64)
+        assert (rows["w_idx"] == remap).all(), f"wires of instance {i}"
+    qa, qr = c.gate_selectors(3, 20)
+    one = oracle.from_ints([1])[0]
+    assert (qr[:8] == one).all() and (qr[8:10] == 0).all() and (qa[:9] == 0).all() and (qa[9] == one).all() and (qr[10:18] == one).all()
+    c2 = gpu_composer(check_mode=mode)
+    c2.synth(SEED, 8, 1, 64, wit)
+    c2.range_gate(c2.add_input(wit), 64)
+    assert c2.check_circuit_satisfied() == (0, None)
