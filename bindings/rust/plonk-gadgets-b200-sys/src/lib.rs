@@ -86,6 +86,7 @@ extern "C" {
                                pi: *mut pg_fr, dst_on_device: c_int) -> c_int;
     pub fn pg_check_rows_ex(ctx: *mut pg_ctx, n: u64, w_val: *const pg_fr, sel: *const pg_fr, pi: *const pg_fr, q_arith: *const pg_fr,
                             q_range: *const pg_fr, on_device: c_int, n_unsat: *mut u64, first_bad_row: *mut u64) -> c_int;
+    pub fn pg_poke_variable(ctx: *mut pg_ctx, var: u64, value: *const pg_fr) -> c_int;
     pub fn pg_materialize_gate_selectors(ctx: *mut pg_ctx, row0: u64, cnt: u64, q_arith: *mut pg_fr, q_range: *mut pg_fr,
                                          dst_on_device: c_int) -> c_int;
     pub fn pg_permutation(ctx: *mut pg_ctx, row0: u64, cnt: u64, sigma: *mut u64, dst_on_device: c_int) -> c_int;

@@ -242,6 +242,12 @@ int pg_fr_to_bytes(pg_ctx *ctx, uint64_t n, const pg_fr *src, uint8_t *dst, int 
 int pg_fr_from_bytes(pg_ctx *ctx, uint64_t n, const uint8_t *src, pg_fr *dst, int on_device, uint64_t *n_invalid,
                      uint64_t *first_invalid);
 
+/* ---- fault injection ----------------------------------------------------------------------------------------------------------
+ * Overwrites composer.variables[var] with *value (host pointer), leaving every row as it is: the way to present pg_check with a
+ * witness that violates a constraint (the gadgets themselves only ever produce consistent ones).  Variables stored as packed
+ * bits (the 256 bit variables of a decomposition) cannot be overwritten: PG_ERR_ARG. */
+int pg_poke_variable(pg_ctx *ctx, uint64_t var, const pg_fr *value);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------------------- */
 /* Deterministic synthetic scalars (SplitMix64 counter stream): kind 0 = uniform Fr (512-bit draw reduced mod q, as
  * BlsScalar::from_bytes_wide), kind 1 = uniform integer of `bits` bits (bits <= 254), kind 2 = even index kind 1 / odd

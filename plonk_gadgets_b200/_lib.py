@@ -57,6 +57,7 @@ SIGNATURES = {
     "pg_check": (_i32, [_vp, _pu64, _pu64]),
     "pg_check_rows": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _pu64, _pu64]),
     "pg_check_rows_ex": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _pu64, _pu64]),
+    "pg_poke_variable": (_i32, [_vp, _u64, _vp]),
     "pg_counts": (_i32, [_vp, _pu64, _pu64]),
     "pg_col_info": (_i32, [_vp, _u64, _pu64, _pu64, _pu64]),
     "pg_col_read": (_i32, [_vp, _u64, _u64, _u64, _vp, _i32]),

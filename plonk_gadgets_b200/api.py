@@ -228,6 +228,11 @@ class StandardComposer:
         self._ok(self._L.pg_materialize_rows(self._ctx, row0, cnt, ptr("w_idx"), ptr("w_val"), ptr("sel"), ptr("pi"), 0), "pg_materialize_rows")
         return out
 
+    def poke_variable(self, var: int, value) -> None:
+        """Fault injection: composer.variables[var] = value ((4,) uint64 Montgomery limbs); rows are left as they are."""
+        v = np.ascontiguousarray(value, dtype=np.uint64).reshape(4)
+        self._ok(self._L.pg_poke_variable(self._ctx, int(var), v.ctypes.data_as(C.c_void_p)), "pg_poke_variable")
+
     def gate_selectors(self, row0: int = 0, cnt: int | None = None):
         """(q_arith, q_range), each (cnt,4): 1 / 0 on arithmetic rows, 0 / 1 on the rows of range_gate (0 / 0 on its closing gate)."""
         cnt = self.circuit_size() - row0 if cnt is None else cnt

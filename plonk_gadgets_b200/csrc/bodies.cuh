@@ -481,41 +481,44 @@ struct CheckRowsBody {
     }
 };
 
-// Segments that hold rows of another widget (GATE_RANGE / GATE_NONE, layout.h): one thread per (row, instance), lanes = instances.
-//   arithmetic rows: the same factored evaluation as the generic kernel;
-//   range rows     : q_range*(delta(c - 4d) + delta(b - 4c) + delta(a - 4b) + delta(d_next - 4a)), delta(f) = f(f-1)(f-2)(f-3), with
-//                    d_next the fourth wire of the NEXT row [dusk-plonk check_circuit_satisfied / range widget, recalled] -- inside a
-//                    template a range row is never the last one (range_gate closes with a q_range = 0 gate and assert_equal);
+// Segments that hold rows of another widget (GATE_RANGE / GATE_NONE, layout.h): one thread per (row, instance), lanes = instances
+// (kernels.cuh k_check_gates).
+//   arithmetic rows: the generic kernel's row evaluation (CheckBody::row_holds<0>);
+//   range rows     : q_range*(D(c - 4d) + D(b - 4c) + D(a - 4b) + D(d_next - 4a)), D(f) = f(f-1)(f-2)(f-3), with d_next the fourth
+//                    wire of the NEXT row [dusk-plonk check_circuit_satisfied / range widget, recalled].  Evaluated as
+//                    D(f) = g*(g + 2) = g^2 + 2g, g = f^2 - 3f  (f(f-3) = g, (f-1)(f-2) = g + 2): four squarings, then sum g_k^2 as ONE
+//                    dot product with a single interleaved reduction, plus 2*sum g_k -- 4*(64+48) + 4*64+48 = 752 wide multiplier
+//                    instructions per row instead of 12 full multiplications; the 9-limb sum is tested for "0 mod q" directly.  Inside a template a
+//                    range row is never the last one (range_gate closes with a q_range = 0 gate and assert_equal);
 //   rows with neither selector hold trivially.
 struct GateRowsCheckBody {
-    struct Args { CheckArgs c; uint64_t n; };
-    PG_HD static void run(const Args& g, uint64_t t) {
-        const CheckArgs& a = g.c;
-        const uint32_t r = (uint32_t)(t / a.n_inst); const uint64_t i = t - (uint64_t)r * a.n_inst;
+    template <class PoolT>
+    PG_HD static bool row_ok(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint32_t r, uint64_t i) {
         const DevRow row = a.rows[r];
-        bool ok = true;
-        if (row.gate == GATE_ARITH) {
-            Fr w[5], sel[4];
+        if (row.gate == GATE_ARITH) return CheckBody::row_holds<0>(a, row, pool, q, i);
+        if (row.gate != GATE_RANGE) return true;
+        Fr w[5];                                                                // d, c, b, a, d_next: each term is D(w[k+1] - 4*w[k])
+        w[0] = row_load(row, 3, i); w[1] = row_load(row, 2, i); w[2] = row_load(row, 1, i); w[3] = row_load(row, 0, i);
+        w[4] = r + 1 < a.n_rows ? row_load(a.rows[r + 1], 3, i) : fr_zero();
+        Fr g[4], sum = fr_zero();
 #pragma unroll
-            for (int k = 0; k < 4; k++) w[k + 1] = row_load(row, k, i);
-            sel[0] = fr_add_noreduce(fr_mul(pool_load(a.pool, row.sel[0]), w[2]), pool_load(a.pool, row.sel[1]));   // q_m*b + q_l
-#pragma unroll
-            for (int k = 1; k < 4; k++) sel[k] = pool_load(a.pool, row.sel[k + 1]);                                   // q_r q_o q_4
-            uint32_t s[9];
-            fr_dot_wide<4>(s, w + 1, sel);
-            add9_fr(s, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool_load(a.pool, row.sel[5]));
-            if (row.pi_param >= 0) add9_fr(s, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
-            else if (row.pi_sel != POOL_ZERO) add9_fr(s, pool_load(a.pool, row.pi_sel));
-            ok = limbs9_is_multiple_of_q(s);
-        } else if (row.gate == GATE_RANGE) {
-            const Fr wa = row_load(row, 0, i), wb = row_load(row, 1, i), wc = row_load(row, 2, i), wd = row_load(row, 3, i);
-            const Fr dn = r + 1 < a.n_rows ? row_load(a.rows[r + 1], 3, i) : fr_zero();
-            ok = fr_is_zero(range_quad_sum(wa, wb, wc, wd, dn));
+        for (int k = 0; k < 4; k++) {                                           // unrolled: everything stays in registers
+            Fr l4 = fr_add(w[k], w[k]); l4 = fr_add(l4, l4);
+            const Fr f = fr_sub(w[k + 1], l4);
+            g[k] = fr_sub(fr_mul_eo(f, f, q), fr_add(fr_add(f, f), f));
+            sum = fr_add(sum, g[k]);
         }
-        if (!ok) {
-            counter_add(a.counters + CNT_UNSAT, 1ull);
-            counter_min(a.counters + CNT_FIRST_BAD, (unsigned long long)(a.base_row + i * (uint64_t)a.n_rows + r));
-        }
+        uint32_t t[9];
+        fr_dot_wide<4>(t, g, g, q);                                             // sum g_k^2 (Montgomery: /R) ...
+        add9_fr(t, fr_add(sum, sum));                                           // ... + 2 sum g_k  =  sum g_k (g_k + 2)
+        return limbs9_is_multiple_of_q(t);
+    }
+    template <class PoolT>
+    PG_HD static uint32_t run_one(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint64_t t, unsigned long long& first_bad) {
+        const uint32_t r = (uint32_t)(t / a.n_inst); const uint64_t i = t - (uint64_t)r * a.n_inst;
+        if (row_ok(a, pool, q, r, i)) return 0u;
+        first_bad = a.base_row + i * (uint64_t)a.n_rows + r;
+        return 1u;
     }
 };
 

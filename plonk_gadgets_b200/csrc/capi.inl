@@ -79,6 +79,7 @@ int pg_check_rows_ex(pg_ctx* ctx, uint64_t n, const pg_fr* w_val, const pg_fr* s
     PG_ALIGNED(ctx, q_arith, on_device); PG_ALIGNED(ctx, q_range, on_device);
     return ctx->e.check_rows(n, w_val, sel, pi, on_device, n_unsat, first_bad_row, q_arith, q_range);
 }
+int pg_poke_variable(pg_ctx* ctx, uint64_t var, const pg_fr* value) { PG_NEED_CTX(ctx); return ctx->e.poke_variable(var, value); }
 int pg_counts(const pg_ctx* ctx, uint64_t* n_rows, uint64_t* n_vars) {
     PG_NEED_CTX(ctx);
     if (n_rows) *n_rows = ctx->e.n_rows;

@@ -160,7 +160,7 @@ public:
     // ---- launches ------------------------------------------------------------------------------------------------
     template <class Body>
     bool run_simple(const typename Body::Args& a, uint64_t n, int cls) {
-        tic(cls, cls == CLS_CHECK ? n : 0);          // a check body run this way evaluates one row per thread
+        tic(cls, 0);
         k_simple<Body><<<grid_for(n), BLOCK, 0, stream>>>(a);
         toc();
         return launched("k_simple");
@@ -212,6 +212,15 @@ public:
         }
         toc();
         return launched("k_check");
+    }
+    bool run_check_gates(const CheckArgs& a) {
+        const size_t smem = (size_t)a.n_pool * sizeof(Fr);
+        if (smem > 48 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
+        const uint64_t total = a.n_inst * a.n_rows;
+        tic(CLS_CHECK, total);
+        k_check_gates<<<(unsigned)((total + 127) / 128), 128, smem, stream>>>(a);
+        toc();
+        return launched("k_check_gates");
     }
     bool run_mat_tiled(const MatTileArgs& a) {
         const uint64_t tiles = ((a.n_inst + MT_I - 1) / MT_I) * ((a.seg.n_rows + MT_R - 1) / MT_R);

@@ -13,6 +13,7 @@
 //   template<class Body> bool run_simple(const typename Body::Args&, uint64_t n, int cls)
 //   bool run_batch_inv(const BatchInvArgs&, int cls)            -- out_slot = in_slot^-1 (or 0) over table slots
 //   bool run_check(const CheckArgs&, const SparseProg&), bool run_check_rows(const CheckRowsBody::Args&)
+//   bool run_check_gates(const CheckArgs&)                        -- segments with rows of the range widget (GateRowsCheckBody)
 //   bool sort_pairs(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t n, uint32_t key_bits)
 //   bool run_msm_buckets(const MsmBucketBody::Args&)             -- one thread per part of a bucket run (launch shape chosen by the backend)
 //   bool exclusive_sum(const uint32_t* in, uint32_t* out, uint64_t n)
@@ -529,8 +530,7 @@ public:
             a.n_rows = (uint32_t)s.t.rows.size(); a.n_pool = (uint32_t)s.t.pool.size();
             a.n_inst = s.n_inst; a.base_row = s.base_row; a.counters = d_counters; a.mode = cfg.check_mode;
             if (s.other_gates) {                     // rows of the range widget: per-row body, one thread per (row, instance)
-                GateRowsCheckBody::Args g{a, a.n_inst * a.n_rows};
-                if (!be.template run_simple<GateRowsCheckBody>(g, g.n, CLS_CHECK)) return fail(PG_ERR_CUDA, "gate-check kernel (range rows)");
+                if (!be.run_check_gates(a)) return fail(PG_ERR_CUDA, "gate-check kernel (range rows)");
                 continue;
             }
             const SparseProg prog{s.d_sp, (uint32_t)s.sp_ops.size()};
@@ -586,6 +586,21 @@ public:
         const int rc = deliver(dst, out, cnt * sizeof(pg_fr), 0);
         release_scratch_from(mark);
         return rc;
+    }
+    // Fault injection (tests, diagnostics): overwrite the stored value of one Variable.  Packed bit variables cannot be poked.
+    int poke_variable(uint64_t var, const pg_fr* value) {
+        if (var >= n_vars || !value) return fail(PG_ERR_ARG, "poke_variable: unknown Variable or null value");
+        for (size_t k = segs.size(); k-- > 0;) {
+            Segment& s = segs[k];
+            if (!s.n_inst || !s.t.n_vars || var < s.base_var) continue;
+            const uint64_t off = var - s.base_var, i = off / s.t.n_vars; const uint32_t j = (uint32_t)(off % s.t.n_vars);
+            if (i >= s.n_inst) return fail(PG_ERR_ARG, "poke_variable: Variable outside its segment");
+            const uint32_t loc = s.t.var_loc[j];
+            if (loc_kind(loc) != LOC_FR) return fail(PG_ERR_ARG, "poke_variable: packed bit variables cannot be overwritten");
+            if (!be.h2d(s.fr + 2 * ((uint64_t)loc_payload(loc) * s.n_alloc + i), value, sizeof(pg_fr)) || !be.sync()) return fail(PG_ERR_CUDA, "poke copy");
+            return PG_OK;
+        }
+        return fail(PG_ERR_ARG, "poke_variable: Variable not found");
     }
     int col_read(pg_col c, uint64_t i0, uint64_t cnt, pg_fr* dst, int dst_on_device) {
         const Column* col = column(c);

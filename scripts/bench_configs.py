@@ -126,6 +126,23 @@ def main():
     ms, tim, rows = timed(c, c5)
     emit("C5: mixed circuit (range_check k=65 / max_bound k=253 / is_non_zero / select_one+select_zero), ~2^26 rows", rows - 3, ms, tim)
 
+    # ---- native range gate: 2^24 witnesses, 64 bits each: 10 rows / 32 accumulators per instance, 8 of the rows with
+    #      q_range = 1 (twelve multiplications each: four D(f) = f(f-1)(f-2)(f-3) terms)
+    n = 1 << 24
+    x_rg = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 61, 1, 64, x_rg)
+
+    def rg():
+        c.reset(); w = c.add_input(x_rg); c.range_gate(w, 64)
+        bad, _ = c.check_circuit_satisfied(); assert bad == 0
+    ms, tim, _ = timed(c, rg)
+    emit("range_gate: 2^24 witnesses x 64 bits (dusk-plonk's native quad-accumulator gate; 10 rows, 32 variables per instance)", 10 * n, ms, tim,
+         {"witnesses_per_s": n / (ms * 1e-3), "range_rows_per_s": 8 * n / (tim["check_ms"] * 1e-3) if tim["check_ms"] else None,
+          "table_GB": n * 33 * 32 / 1e9})
+    del x_rg
+    c.reset()
+    w = c.add_input(x_rc); pg.range_check(c, mn, mx, w)          # the read-back lines below run on a composer of arithmetic rows again
+    w = c.add_input(x_mb); pg.max_bound(c, mx252, w)
+
     # ---- read-back kernels: materialise rows / variables of the last composer to device buffers (reference representation)
     cnt = 1 << 22
     w_idx = torch.empty((4, cnt), dtype=torch.int64, device=dev)

@@ -71,6 +71,16 @@ public:
         }
         return true;
     }
+    bool run_check_gates(const CheckArgs& a) {
+        HostPool pool = {a.pool};
+        const QRegs q = q_regs_default();
+        for (uint64_t t = 0; t < a.n_inst * a.n_rows; t++) {
+            unsigned long long fb = ~0ull;
+            const uint32_t bad = GateRowsCheckBody::run_one(a, pool, q, t, fb);
+            if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
+        }
+        return true;
+    }
     bool run_mat_tiled(const MatTileArgs& a) {      // same outputs as the tiled CUDA kernel, element by element
         const DevSeg& s = a.seg;
         for (uint64_t ii = 0; ii < a.n_inst; ii++)

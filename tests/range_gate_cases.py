@@ -82,3 +82,56 @@ def fault_injection(make_composer, oracle, seed=7, trials=24):
         assert got == (len(exp), exp[0] if exp else None), (t, r_, col, got, exp)
         seen_range_failure |= any(r in range_rows for r in exp)
     assert seen_range_failure
+
+
+def poked_witness(make_composer, oracle, modes=(pg.CHECK_GENERIC, pg.CHECK_SPARSE), n=40, trials=10, seed=11, arith="max_bound"):
+    """Overwrite stored variables (accumulators, the witness, a gadget result) of a circuit with range gates and arithmetic
+    rows: pg_check (the kernels themselves) must report exactly the rows a big-int evaluation reports.  The circuit is satisfied
+    before the change, so only rows that read the changed variable -- and, for a fourth wire, the row above (its d_next) -- are
+    re-evaluated, from the engine's own dump of wires and selectors."""
+    vals = [v % 2 ** 30 for v in synth_wide(320, n)]
+    rng = random.Random(seed)
+
+    def delta(f):
+        return f * (f - 1) * (f - 2) * (f - 3)
+    for mode in modes:
+        c = make_composer(check_mode=mode)
+        w = c.add_input(oracle.from_ints(vals))
+        c.range_gate(w, 30)
+        y = pg.max_bound(c, oracle.from_ints([2 ** 30]), w)[0] if arith == "max_bound" else pg.maybe_equal(c, w, w)
+        c.range_gate(y, 2)
+        assert c.check_circuit_satisfied() == (0, None)
+        n_vars, n_rows = c.num_variables(), c.circuit_size()
+        rows = c.rows(want=("w_idx", "sel", "pi")); qa, qr = c.gate_selectors()
+        w_idx = rows["w_idx"]
+        acc0 = 5 + n                                             # first accumulator of the first range gate (15 per instance)
+        pokes = [acc0, acc0 + 14, acc0 + 15 * (n - 1) + 7, 5 + 3, int(y.ids()[2])]
+        pokes += [rng.randrange(acc0, acc0 + 15 * n) for _ in range(trials)]
+        pokes += [int(n_vars - 1 - rng.randrange(n)) for _ in range(2)]      # accumulators of the second range gate (one per instance)
+        hit_range_row = False
+        for var in pokes:
+            old = c.variables(var, 1)[0].copy()
+            new_val = (rng.choice([1, 2, 5, rng.randrange(Q)]) + oracle.to_ints(old[None])[0]) % Q
+            c.poke_variable(var, oracle.from_ints([new_val])[0])
+            cand = set()
+            for k in range(4):
+                for r in np.nonzero(w_idx[k] == var)[0]:
+                    cand.add(int(r))
+                    if k == 3 and r > 0:
+                        cand.add(int(r) - 1)
+            exp = []
+            for r in sorted(cand):
+                ids = [int(w_idx[k, r]) for k in range(4)] + [int(w_idx[3, (r + 1) % n_rows])]
+                a, b, cc, d, dn = (new_val if v == var else oracle.to_ints(c.variables(v, 1))[0] for v in ids)
+                q_m, q_l, q_r, q_o, q_4, q_c = (oracle.to_ints(rows["sel"][k, r:r + 1])[0] for k in range(6))
+                pi, s_a, s_r = (oracle.to_ints(x[r:r + 1])[0] for x in (rows["pi"], qa, qr))
+                g = s_a * (q_m * a * b + q_l * a + q_r * b + q_o * cc + q_4 * d + pi + q_c) \
+                    + s_r * (delta(cc - 4 * d) + delta(b - 4 * cc) + delta(a - 4 * b) + delta(dn - 4 * a))
+                if g % Q:
+                    exp.append(r)
+                    hit_range_row |= bool(s_r)
+            assert exp, var
+            assert c.check_circuit_satisfied() == (len(exp), exp[0]), (mode, var, exp)
+            c.poke_variable(var, old)
+            assert c.check_circuit_satisfied() == (0, None)
+        assert hit_range_row

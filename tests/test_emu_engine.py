@@ -276,3 +276,7 @@ def test_emu_range_gate_bad_arguments(emu, oracle):
 
 def test_emu_range_gate_fault_injection(emu, oracle):
     rgc.fault_injection(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)
+
+
+def test_emu_range_gate_poked_witness(emu, oracle):
+    rgc.poked_witness(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)

@@ -708,3 +708,13 @@ def test_range_gate_at_scale(oracle, torch_cuda, mode):
     c2.synth(SEED, 8, 1, 64, wit)
     c2.range_gate(c2.add_input(wit), 64)
     assert c2.check_circuit_satisfied() == (0, None)
+
+
+def test_range_gate_poked_witness(oracle):
+    """Small segments: the row-parallel kernels."""
+    rgc.poked_witness(gpu_composer, oracle)
+
+
+def test_range_gate_poked_witness_large_segments(oracle):
+    """Enough instances for the one-thread-per-instance kernels (k_check / k_check_prog) next to k_check_gates."""
+    rgc.poked_witness(gpu_composer, oracle, n=148 * 320 + 77, trials=3, arith="maybe_equal")
