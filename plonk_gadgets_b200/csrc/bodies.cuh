@@ -486,9 +486,10 @@ struct CheckRowsBody {
 //   arithmetic rows: the generic kernel's row evaluation (CheckBody::row_holds<0>);
 //   range rows     : q_range*(D(c - 4d) + D(b - 4c) + D(a - 4b) + D(d_next - 4a)), D(f) = f(f-1)(f-2)(f-3), with d_next the fourth
 //                    wire of the NEXT row [dusk-plonk check_circuit_satisfied / range widget, recalled].  Evaluated as
-//                    D(f) = g*(g + 2) = g^2 + 2g, g = f^2 - 3f  (f(f-3) = g, (f-1)(f-2) = g + 2): four squarings, then sum g_k^2 as ONE
-//                    dot product with a single interleaved reduction, plus 2*sum g_k -- 4*(64+48) + 4*64+48 = 752 wide multiplier
-//                    instructions per row instead of 12 full multiplications; the 9-limb sum is tested for "0 mod q" directly.  Inside a template a
+//                    D(f) = u^2 - 1, u = f(f-3) + 1  (f(f-3) = g, (f-1)(f-2) = g + 2, g(g+2) = (g+1)^2 - 1): four multiplications,
+//                    then sum u_k^2 as ONE dot product with a single interleaved reduction, minus 4 -- 4*(64+48) + 4*64+48 = 752
+//                    wide multiplier instructions per row instead of 12 full multiplications; the 9-limb sum is tested for
+//                    "0 mod q" directly.  Inside a template a
 //                    range row is never the last one (range_gate closes with a q_range = 0 gate and assert_equal);
 //   rows with neither selector hold trivially.
 struct GateRowsCheckBody {
@@ -500,17 +501,17 @@ struct GateRowsCheckBody {
         Fr w[5];                                                                // d, c, b, a, d_next: each term is D(w[k+1] - 4*w[k])
         w[0] = row_load(row, 3, i); w[1] = row_load(row, 2, i); w[2] = row_load(row, 1, i); w[3] = row_load(row, 0, i);
         w[4] = r + 1 < a.n_rows ? row_load(a.rows[r + 1], 3, i) : fr_zero();
-        Fr g[4], sum = fr_zero();
+        const Fr one = fr_one(), three = fr_add(fr_add(one, one), one);
+        Fr u[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {                                           // unrolled: everything stays in registers
             Fr l4 = fr_add(w[k], w[k]); l4 = fr_add(l4, l4);
             const Fr f = fr_sub(w[k + 1], l4);
-            g[k] = fr_sub(fr_mul_eo(f, f, q), fr_add(fr_add(f, f), f));
-            sum = fr_add(sum, g[k]);
+            u[k] = fr_add(fr_mul_eo(f, fr_sub(f, three), q), one);              // u = f(f-3) + 1
         }
         uint32_t t[9];
-        fr_dot_wide<4>(t, g, g, q);                                             // sum g_k^2 (Montgomery: /R) ...
-        add9_fr(t, fr_add(sum, sum));                                           // ... + 2 sum g_k  =  sum g_k (g_k + 2)
+        fr_dot_wide<4>(t, u, u, q);                                             // sum u_k^2 ...
+        add9_fr(t, fr_neg(fr_add(three, one)));                                 // ... - 4  =  sum D(f_k)
         return limbs9_is_multiple_of_q(t);
     }
     template <class PoolT>
