@@ -46,8 +46,15 @@ def _worker(rank, world, port, n, q):
     first_global = None if first_local is None else sharding.FRESH_ROWS + off.row_offset + 271 * first_local + 270
     tot_bad, tot_first, tot_err = sharding.allreduce_verdict(n_bad, first_global, 0)
     gathered = sharding.allgather_scalars(torch.from_numpy(y.values().view(np.int64)))
+    # second call shape: the native range gate (10 rows per 64-bit witness), verdict straight from the engine's own check;
+    # odd instances are uniform Fr and do not fit 64 bits, so both shards hold unsatisfied rows
+    c2 = pg.StandardComposer(_cdll=emu)
+    c2.range_gate(c2.add_input(ob.from_ints(wit[lo:hi])), 64)
+    bad2, first2 = c2.check_circuit_satisfied()
+    off2 = sharding.shard_offsets(n, rank, world, 10, 32)
+    rg = sharding.allreduce_verdict(bad2, None if first2 is None else first2 + off2.row_offset, 0)
     if rank == 0:
-        q.put((tot_bad, tot_first, tot_err, gathered.numpy().view(np.uint64).copy(), off.row_offset, off.var_offset))
+        q.put((tot_bad, tot_first, tot_err, gathered.numpy().view(np.uint64).copy(), off.row_offset, off.var_offset, rg))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,7 +73,7 @@ def test_two_rank_sharding_equals_single_run(oracle):
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
     for p in procs: p.start()
-    tot_bad, tot_first, tot_err, gathered, off_r, off_v = q.get(timeout=240)
+    tot_bad, tot_first, tot_err, gathered, off_r, off_v, rg = q.get(timeout=240)
     for p in procs: p.join(timeout=60)
     assert all(p.exitcode == 0 for p in procs)
     # single-process run of the whole batch
@@ -79,6 +86,9 @@ def test_two_rank_sharding_equals_single_run(oracle):
     assert (tot_bad, tot_err) == (2, 0)
     assert tot_first == 3 + 271 * 5 + 270                    # the output row of instance 5 in the sequential numbering
     assert (off_r, off_v) == (0, 0)
+    c2 = pg.StandardComposer(_cdll=emu)
+    c2.range_gate(c2.add_input(oracle.from_ints(wit)), 64)
+    assert rg == c2.check_circuit_satisfied() + (0,) == (n // 2, 3 + 10 + 9, 0)
 
 
 def test_shard_ranges_cover_everything():
