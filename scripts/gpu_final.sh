@@ -11,6 +11,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_
 timeout 600 python bench.py --check-mode sparse --no-cpu-baseline > $OUT/${TAG}_bench_sparse.json 2>> $OUT/${TAG}_bench.err; cut -c1-200 $OUT/${TAG}_bench_sparse.json
 timeout 900 python scripts/bench_configs.py > $OUT/${TAG}_configs_generic.jsonl 2> $OUT/${TAG}_configs.err; cut -c1-160 $OUT/${TAG}_configs_generic.jsonl
 timeout 900 python scripts/bench_configs.py --sparse > $OUT/${TAG}_configs_sparse.jsonl 2>> $OUT/${TAG}_configs.err; cut -c1-160 $OUT/${TAG}_configs_sparse.jsonl
+timeout 600 python scripts/bench_range_gate.py > $OUT/${TAG}_range_gate.jsonl 2> $OUT/${TAG}_range_gate.err; cut -c1-200 $OUT/${TAG}_range_gate.jsonl
 timeout 600 python scripts/bench_ntt.py > $OUT/${TAG}_ntt.jsonl 2> $OUT/${TAG}_ntt.err; cut -c1-160 $OUT/${TAG}_ntt.jsonl
 timeout 900 python scripts/bench_msm.py 16 18 20 22 > $OUT/${TAG}_msm.jsonl 2> $OUT/${TAG}_msm.err; cut -c1-200 $OUT/${TAG}_msm.jsonl
 CMD="python scripts/bench_ntt.py 24"
