@@ -180,16 +180,25 @@ public:
         toc();
         return launched("k_simple<MsmBucketBody>");
     }
+    // One wave: the elements are divided over the blocks that are resident together (sm_count x blocks/SM), so every block
+    // streams its share twice and inverts once.  PG_INV_SHAPE selects the blocks/SM variant for tuning runs (profiles/README.md).
+    int inv_shape = -1;
     bool run_batch_inv(const BatchInvArgs& a_in, int cls) {
         BatchInvArgs a = a_in;
         const uint64_t total = (uint64_t)a.n_pairs * a.n;
         if (!total) return true;
-        a.elems_per_thread = 8;
-        for (uint32_t e : {128u, 32u})
-            if (total / ((uint64_t)BLOCK * e) >= (uint64_t)sm_count * 4) { a.elems_per_thread = e; break; }
+        if (inv_shape < 0) { const char* e = getenv("PG_INV_SHAPE"); inv_shape = e ? atoi(e) : 2; if (inv_shape < 2 || inv_shape > 4) inv_shape = 2; }
+        const uint64_t resident = (uint64_t)sm_count * inv_shape * BLOCK;
+        const uint64_t e = (total + resident - 1) / resident;
+        a.elems_per_thread = (uint32_t)(e < 8 ? 8 : e);
         const uint64_t per_block = (uint64_t)BLOCK * a.elems_per_thread;
+        const unsigned grid = (unsigned)((total + per_block - 1) / per_block);
         tic(cls, 0);
-        k_batch_inv<<<(unsigned)((total + per_block - 1) / per_block), BLOCK, 0, stream>>>(a);
+        switch (inv_shape) {
+            case 3: k_batch_inv<3><<<grid, BLOCK, 0, stream>>>(a); break;      // <= 80 registers
+            case 4: k_batch_inv<4><<<grid, BLOCK, 0, stream>>>(a); break;      // <= 64 registers
+            default: k_batch_inv<2><<<grid, BLOCK, 0, stream>>>(a); break;     // 111 registers, no spills
+        }
         toc();
         return launched("k_batch_inv");
     }

@@ -31,7 +31,7 @@ __device__ __forceinline__ Fr shfl_xor_fr(const Fr& a, int mask) {
     return r;
 }
 
-// Inverse of one NON-ZERO field element per thread, for a whole thread block, with ONE Fermat inversion per block.
+// Inverse of one NON-ZERO field element per thread, for a whole thread block, with ONE inversion per block.
 // Products are combined with an xor-butterfly over warp shuffles (each lane keeps the sibling product of every level),
 // warp totals are staged in shared memory and combined by warp 0 with the same butterfly; the inverse of the block product
 // is pushed back down the two butterflies with one multiplication per level.  Every thread of the block must call.
@@ -46,7 +46,7 @@ __device__ __forceinline__ Fr block_invert_nonzero(const Fr& p, Fr* smem /* NWAR
         Fr h = lane < NWARPS ? smem[lane] : fr_one(), hs[3];
 #pragma unroll
         for (int l = 0; l < 3; l++) { hs[l] = shfl_xor_fr(h, 1 << l); h = fr_mul(h, hs[l]); }    // NWARPS == 8 -> 3 levels
-        Fr ih = fr_inv_fermat(h);                                                                // the block's only inversion
+        Fr ih = lane < NWARPS ? fr_inv_binary(h) : h;                                            // the block's only inversion (the NWARPS lanes hold the same h)
 #pragma unroll
         for (int l = 2; l >= 0; l--) ih = fr_mul(ih, hs[l]);                                     // inverse of smem[lane]
         if (lane < NWARPS) smem[lane] = ih;
@@ -64,42 +64,64 @@ static_assert(NWARPS == 8, "block_invert_nonzero's cross-warp butterfly is writt
 // The n_pairs x n elements are flattened; a block owns a tile of BLOCK*INV_E consecutive elements and thread t walks the
 // elements tile + e*BLOCK + t (every step is a coalesced 128-bit access).
 //   pass 1: running product of the thread's elements (zeros patched to 1), each prefix parked in the OUTPUT slot;
-//   block : one Fermat inversion for the product of all BLOCK*INV_E elements (block_invert_nonzero);
+//   block : one inversion for the product of all BLOCK*INV_E elements (block_invert_nonzero; binary Euclid, fr_inv_binary);
 //   pass 2: walk back -- inverse_e = inv(prefix_e) * prefix_{e-1}, inv(prefix_{e-1}) = inv(prefix_e) * x_e.
 // 3 multiplications per element, no per-element state in registers, one inversion per BLOCK*E elements.  E (elements per
-// thread) is chosen per launch: large enough that the block's single Fermat chain (~333 dependent multiplications on one
-// warp) is amortised, small enough that the grid still fills the chip twice.
-__global__ void __launch_bounds__(BLOCK, 2) k_batch_inv(const BatchInvArgs a) {
+// thread) is chosen per launch so that the whole grid is resident at once (one wave, one inversion per block: the launcher
+// divides the elements over sm_count x MIN_BLOCKS blocks), with a floor of 8 for small batches.
+// Both walks are software-pipelined (the next element's loads are issued before the current multiplication), and the flat index
+// is split into (pair, instance) by at most n_pairs - 1 subtractions instead of a 64-bit division.
+struct InvCursor {
+    uint32_t in_slot, out_slot; uint64_t i; bool valid;
+    __device__ __forceinline__ InvCursor(const BatchInvArgs& a, uint64_t idx, uint64_t total) {
+        valid = idx < total;
+        uint32_t j = 0; i = valid ? idx : 0;
+        while (i >= a.n && j + 1 < a.n_pairs) { i -= a.n; j++; }
+        in_slot = a.in_slot[j]; out_slot = a.out_slot[j];
+    }
+};
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_batch_inv(const BatchInvArgs a) {
     __shared__ Fr smem[NWARPS];
     const uint64_t total = (uint64_t)a.n_pairs * a.n;
     const int INV_E = (int)a.elems_per_thread;
-    const uint64_t tile = (uint64_t)blockIdx.x * ((uint64_t)BLOCK * INV_E);
+    const uint64_t first = (uint64_t)blockIdx.x * ((uint64_t)BLOCK * INV_E) + threadIdx.x;
     Fr p = fr_one();
+    {
+        InvCursor c(a, first, total);
+        Fr xn = c.valid ? tab_load_fr(a.fr, a.stride, c.in_slot, c.i) : fr_zero();
 #pragma unroll 1
-    for (int e = 0; e < INV_E; e++) {
-        const uint64_t idx = tile + (uint64_t)e * BLOCK + threadIdx.x;
-        if (idx < total) {
-            const uint32_t j = (uint32_t)(idx / a.n); const uint64_t i = idx - (uint64_t)j * a.n;
-            const Fr x = tab_load_fr(a.fr, a.stride, a.in_slot[j], i);
-            if (!fr_is_zero(x)) p = fr_mul(p, x);
-            tab_store_fr(a.fr, a.stride, a.out_slot[j], i, p);
+        for (int e = 0; e < INV_E; e++) {
+            const Fr x = xn; const InvCursor cur = c;
+            if (e + 1 < INV_E) {
+                c = InvCursor(a, first + (uint64_t)(e + 1) * BLOCK, total);
+                if (c.valid) xn = tab_load_fr(a.fr, a.stride, c.in_slot, c.i);
+            }
+            if (cur.valid) {
+                if (!fr_is_zero(x)) p = fr_mul(p, x);
+                tab_store_fr(a.fr, a.stride, cur.out_slot, cur.i, p);
+            }
         }
     }
     Fr ig = block_invert_nonzero(p, smem);                           // inverse of the product of this thread's elements
+    {
+        InvCursor c(a, first + (uint64_t)(INV_E - 1) * BLOCK, total);
+        InvCursor cp(a, first + (uint64_t)(INV_E > 1 ? INV_E - 2 : 0) * BLOCK, total);
+        Fr xn = c.valid ? tab_load_fr(a.fr, a.stride, c.in_slot, c.i) : fr_zero();
+        Fr pn = (c.valid && INV_E > 1) ? tab_load_fr(a.fr, a.stride, cp.out_slot, cp.i) : fr_one();   // prefix of element e - 1
 #pragma unroll 1
-    for (int e = INV_E - 1; e >= 0; e--) {
-        const uint64_t idx = tile + (uint64_t)e * BLOCK + threadIdx.x;
-        if (idx < total) {
-            const uint32_t j = (uint32_t)(idx / a.n); const uint64_t i = idx - (uint64_t)j * a.n;
-            const Fr x = tab_load_fr(a.fr, a.stride, a.in_slot[j], i);
-            Fr prev = fr_one();
-            if (e > 0) {                                             // prefix of the previous element of this thread
-                const uint64_t pidx = idx - BLOCK;
-                const uint32_t pj = (uint32_t)(pidx / a.n); const uint64_t pi = pidx - (uint64_t)pj * a.n;
-                prev = tab_load_fr(a.fr, a.stride, a.out_slot[pj], pi);
+        for (int e = INV_E - 1; e >= 0; e--) {
+            const Fr x = xn, prev = pn; const InvCursor cur = c;
+            if (e > 0) {
+                c = cp;                                              // element e - 1 ...
+                xn = tab_load_fr(a.fr, a.stride, c.in_slot, c.i);    // (valid: it lies below a valid or the first invalid index)
+                pn = fr_one();
+                if (e > 1) { cp = InvCursor(a, first + (uint64_t)(e - 2) * BLOCK, total); pn = tab_load_fr(a.fr, a.stride, cp.out_slot, cp.i); }   // ... and its prefix
             }
-            if (fr_is_zero(x)) tab_store_fr(a.fr, a.stride, a.out_slot[j], i, fr_zero());
-            else { tab_store_fr(a.fr, a.stride, a.out_slot[j], i, fr_mul(ig, prev)); ig = fr_mul(ig, x); }
+            if (cur.valid) {
+                if (fr_is_zero(x)) tab_store_fr(a.fr, a.stride, cur.out_slot, cur.i, fr_zero());
+                else { tab_store_fr(a.fr, a.stride, cur.out_slot, cur.i, fr_mul(ig, prev)); ig = fr_mul(ig, x); }
+            }
         }
     }
 }

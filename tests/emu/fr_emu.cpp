@@ -18,6 +18,7 @@ void emu_add(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0;
 void emu_sub(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_sub(a[i], b[i]); }
 void emu_neg(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_neg(a[i]); }
 void emu_inv(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_inv_fermat(a[i]); }
+void emu_inv_binary(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_inv_binary(a[i]); }
 void emu_from_mont(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_from_mont(a[i]); }
 // r (9 limbs) = dot product of K=5 pairs through fr_dot_wide; ok[i] = limbs9_is_multiple_of_q(r + c)
 void emu_dot5(uint64_t n, const Fr* a, const Fr* b, const Fr* c, uint32_t* r9, uint8_t* is_mult) {

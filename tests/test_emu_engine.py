@@ -114,6 +114,25 @@ def test_fr_even_odd_multiplier_host_emulation(fr_emu):
         assert unpack(out) == [f(a, b) for a, b in pairs], fn
 
 
+def test_fr_inversions_host_emulation(fr_emu):
+    """fr_inv_binary (binary extended Euclid, the batch inversion's one inversion per block) and fr_inv_fermat (x^(q-2)) return
+    the same limbs, and both are the big-int inverse: Montgomery form in, Montgomery form out."""
+    import random
+    R = (1 << 256) % Q
+    rng = random.Random(11)
+    vals = [1, 2, 3, 4, Q - 1, Q - 2, R, Q - R, (Q + 1) // 2, 2 ** 32, 2 ** 32 - 1, 2 ** 64 - 1, 2 ** 254, 2 ** 254 + 1, 2 ** 255 % Q,
+            pow(R, -1, Q), pow(2, -1, Q) * R % Q] + [2 ** i for i in range(0, 254, 17)] + [rng.randrange(1, Q) for _ in range(2000)]
+    pack = lambda vs: np.frombuffer(b"".join(v.to_bytes(32, "little") for v in vs), dtype=np.uint64).reshape(-1, 4).copy()
+    unpack = lambda a: [int.from_bytes(a[i].tobytes(), "little") for i in range(a.shape[0])]
+    A = pack(vals)                                     # stored limbs x~ = x R  =>  x = x~ / R
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    expect = [pow(v * pow(R, -1, Q) % Q, -1, Q) * R % Q for v in vals]
+    for fn in ("emu_inv_binary", "emu_inv"):
+        out = np.zeros_like(A)
+        getattr(fr_emu, fn)(C.c_uint64(len(vals)), vp(A), vp(out))
+        assert unpack(out) == expect, fn
+
+
 def test_emu_wire_format(emu, oracle):
     """to_bytes / from_bytes (canonical LE 32 bytes) against the oracle's, including rejection of encodings >= q."""
     import random
