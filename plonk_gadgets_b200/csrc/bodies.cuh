@@ -10,7 +10,7 @@
 // Reference functions restated here (witness arithmetic only; row structure lives in templates.hpp):
 //   RangePre/Post   /root/reference/src/range.rs:27-43 (range_check), :82-113 (max_bound), :53-76 (min_bound),
 //                   :119-158 (scalar_decomposition_gadget), :161-170 (scalar_to_bits)
-//   MaybeEqualPre/Post /root/reference/src/scalar.rs:105-140   IsNonZeroPre   /root/reference/src/scalar.rs:63-97
+//   MaybeEqualFused    /root/reference/src/scalar.rs:105-140   IsNonZeroFused /root/reference/src/scalar.rs:63-97
 //   SelectZeroBody  /root/reference/src/scalar.rs:21-27        SelectOneBody  /root/reference/src/scalar.rs:36-59
 #pragma once
 #include "layout.h"
@@ -149,24 +149,25 @@ struct RangePost {   // after z = u^-1 (or 0) has been written by the batch inve
 
 // ---------------------------------------------------------------------------------------------------- maybe_equal
 struct MaybeEqualArgs { DevTab a_tab, b_tab; uint32_t a_loc, b_loc; uint4* fr; uint64_t stride; uint64_t n; };
-struct MaybeEqualPre {    // slots: 0 = u, 1 = z, 2 = y
+// maybe_equal inside the batch inversion's walks (k_batch_inv<MaybeEqualFused>): u is produced where the first walk would
+// load it, y where the second walk has just written z.  in_slot = 0 (u), out_slot = 1 (z).
+struct MaybeEqualFused {
     typedef MaybeEqualArgs Args;
-    PG_HD static void run(const Args& a, uint64_t i) {
-        tab_store_fr(a.fr, a.stride, 0, i, fr_sub(loc_load(&a.a_tab, a.a_loc, i), loc_load(&a.b_tab, a.b_loc, i)));   // scalar.rs:111-121
+    PG_HD static Fr pre(const Args& a, uint64_t i) {
+        const Fr u = fr_sub(loc_load(&a.a_tab, a.a_loc, i), loc_load(&a.b_tab, a.b_loc, i));                         // scalar.rs:111-121
+        tab_store_fr(a.fr, a.stride, 0, i, u);
+        return u;
     }
-};
-struct MaybeEqualPost {
-    typedef MaybeEqualArgs Args;
-    PG_HD static void run(const Args& a, uint64_t i) {
-        const Fr u = tab_load_fr(a.fr, a.stride, 0, i), z = tab_load_fr(a.fr, a.stride, 1, i);
+    PG_HD static void post(const Args& a, uint64_t i, const Fr& u, const Fr& z) {
         tab_store_fr(a.fr, a.stride, 2, i, fr_sub(fr_one(), fr_mul(z, u)));                                           // y, scalar.rs:126
     }
 };
+struct InvPlain { struct Args {}; };     // the batch inversion without a fused gadget: table slot in, table slot out
 
 // ---------------------------------------------------------------------------------------------------- is_non_zero
-struct IsNonZeroPre {     // slots: 0 = var_assigned, 1 = inv (written by the batch inversion), 2 = one
+struct IsNonZeroFused {   // inside k_batch_inv's first walk (in_slot = 0, out_slot = 1); slots: 0 = var_assigned, 1 = inv, 2 = one
     struct Args { const uint4* assigned; uint4* fr; uint64_t stride; uint64_t n; unsigned long long* counters; };
-    PG_HD static void run(const Args& a, uint64_t i) {
+    PG_HD static Fr pre(const Args& a, uint64_t i) {
         const Fr va = aos_load(a.assigned, i);
         tab_store_fr(a.fr, a.stride, 0, i, va);                                              // var_assigned, scalar.rs:69
         if (fr_is_zero(va)) {                                                                // invert() is None, scalar.rs:73-80
@@ -174,7 +175,9 @@ struct IsNonZeroPre {     // slots: 0 = var_assigned, 1 = inv (written by the ba
             counter_min(a.counters + CNT_FIRST_ERR, (unsigned long long)i);
         }
         tab_store_fr(a.fr, a.stride, 2, i, fr_one());                                        // one, scalar.rs:83
+        return va;
     }
+    PG_HD static void post(const Args&, uint64_t, const Fr&, const Fr&) {}                   // nothing follows the inverse (scalar.rs:84-94 is a row)
 };
 
 // ---------------------------------------------------------------------------------------------------- selections

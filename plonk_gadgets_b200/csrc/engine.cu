@@ -180,28 +180,23 @@ public:
         toc();
         return launched("k_simple<MsmBucketBody>");
     }
-    // One wave: the elements are divided over the blocks that are resident together (sm_count x blocks/SM), so every block
-    // streams its share twice and inverts once.  PG_INV_SHAPE selects the blocks/SM variant for tuning runs (profiles/README.md).
-    int inv_shape = -1;
-    bool run_batch_inv(const BatchInvArgs& a_in, int cls) {
+    // One wave: the elements are divided over the blocks that are resident together (sm_count x 2 blocks/SM), so every block
+    // streams its share twice and inverts once (3 and 4 blocks/SM measured within 3 %: profiles/r03c_batch_inv_shapes.log).
+    template <class Hook>
+    bool run_batch_inv_fused(const BatchInvArgs& a_in, const typename Hook::Args& h, int cls) {
         BatchInvArgs a = a_in;
         const uint64_t total = (uint64_t)a.n_pairs * a.n;
         if (!total) return true;
-        if (inv_shape < 0) { const char* e = getenv("PG_INV_SHAPE"); inv_shape = e ? atoi(e) : 2; if (inv_shape < 2 || inv_shape > 4) inv_shape = 2; }
-        const uint64_t resident = (uint64_t)sm_count * inv_shape * BLOCK;
+        const uint64_t resident = (uint64_t)sm_count * 2 * BLOCK;
         const uint64_t e = (total + resident - 1) / resident;
         a.elems_per_thread = (uint32_t)(e < 8 ? 8 : e);
         const uint64_t per_block = (uint64_t)BLOCK * a.elems_per_thread;
-        const unsigned grid = (unsigned)((total + per_block - 1) / per_block);
         tic(cls, 0);
-        switch (inv_shape) {
-            case 3: k_batch_inv<3><<<grid, BLOCK, 0, stream>>>(a); break;      // <= 80 registers
-            case 4: k_batch_inv<4><<<grid, BLOCK, 0, stream>>>(a); break;      // <= 64 registers
-            default: k_batch_inv<2><<<grid, BLOCK, 0, stream>>>(a); break;     // 111 registers, no spills
-        }
+        k_batch_inv<Hook><<<(unsigned)((total + per_block - 1) / per_block), BLOCK, 0, stream>>>(a, h);
         toc();
         return launched("k_batch_inv");
     }
+    bool run_batch_inv(const BatchInvArgs& a, int cls) { return run_batch_inv_fused<InvPlain>(a, InvPlain::Args{}, cls); }
     bool run_check(const CheckArgs& a, const SparseProg& prog) {
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }

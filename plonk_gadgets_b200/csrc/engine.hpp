@@ -417,8 +417,7 @@ public:
         if (g.n) {
             BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
             inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = g.n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
-            if (!(be.template run_simple<MaybeEqualPre>(g, g.n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS) &&
-                  be.template run_simple<MaybeEqualPost>(g, g.n, CLS_WITNESS))) return fail(PG_ERR_CUDA, "maybe_equal kernels");
+            if (!be.template run_batch_inv_fused<MaybeEqualFused>(inv, g, CLS_WITNESS)) return fail(PG_ERR_CUDA, "maybe_equal kernel");
         }
         *out = new_column((uint32_t)segs.size() - 1, result_local, g.n);
         return PG_OK;
@@ -436,10 +435,10 @@ public:
         if (rc) return rc;
         {
             Segment& s = segs.back();
-            IsNonZeroPre::Args g{src, s.fr, s.n_alloc, n, d_counters};
+            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters};
             BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
             inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
-            if (n && !(be.template run_simple<IsNonZeroPre>(g, n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS))) return fail(PG_ERR_CUDA, "is_non_zero kernels");
+            if (n && !be.template run_batch_inv_fused<IsNonZeroFused>(inv, g, CLS_WITNESS)) return fail(PG_ERR_CUDA, "is_non_zero kernel");
         }
         unsigned long long c[CNT_WORDS];
         if ((rc = read_counters(c))) return rc;

@@ -2,6 +2,7 @@
 // Montgomery batch inversion, the gate-check kernel and the integer-multiply roofline micro-benchmarks.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include "bodies.cuh"
 
 namespace pg {
@@ -80,8 +81,12 @@ struct InvCursor {
         in_slot = a.in_slot[j]; out_slot = a.out_slot[j];
     }
 };
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_batch_inv(const BatchInvArgs a) {
+// Hook (bodies.cuh) fuses a gadget's own element-wise work into the two walks: Hook::pre(h, i) PRODUCES the element to invert
+// (and stores it in the input slot, with whatever else the gadget allocates before the inversion) in place of the first
+// walk's table load; Hook::post(h, i, x, x^-1) stores what the gadget derives from the inverse.  InvPlain: table to table.
+template <class Hook>
+__global__ void __launch_bounds__(BLOCK, 2) k_batch_inv(const BatchInvArgs a, const typename Hook::Args h) {
+    constexpr bool PLAIN = std::is_same<Hook, InvPlain>::value;
     __shared__ Fr smem[NWARPS];
     const uint64_t total = (uint64_t)a.n_pairs * a.n;
     const int INV_E = (int)a.elems_per_thread;
@@ -89,13 +94,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_batch_inv(const BatchInvA
     Fr p = fr_one();
     {
         InvCursor c(a, first, total);
-        Fr xn = c.valid ? tab_load_fr(a.fr, a.stride, c.in_slot, c.i) : fr_zero();
+        Fr xn = fr_zero();
+        if (c.valid) { if constexpr (PLAIN) xn = tab_load_fr(a.fr, a.stride, c.in_slot, c.i); else xn = Hook::pre(h, c.i); }
 #pragma unroll 1
         for (int e = 0; e < INV_E; e++) {
             const Fr x = xn; const InvCursor cur = c;
             if (e + 1 < INV_E) {
                 c = InvCursor(a, first + (uint64_t)(e + 1) * BLOCK, total);
-                if (c.valid) xn = tab_load_fr(a.fr, a.stride, c.in_slot, c.i);
+                if (c.valid) { if constexpr (PLAIN) xn = tab_load_fr(a.fr, a.stride, c.in_slot, c.i); else xn = Hook::pre(h, c.i); }
             }
             if (cur.valid) {
                 if (!fr_is_zero(x)) p = fr_mul(p, x);
@@ -114,13 +120,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_batch_inv(const BatchInvA
             const Fr x = xn, prev = pn; const InvCursor cur = c;
             if (e > 0) {
                 c = cp;                                              // element e - 1 ...
-                xn = tab_load_fr(a.fr, a.stride, c.in_slot, c.i);    // (valid: it lies below a valid or the first invalid index)
+                xn = tab_load_fr(a.fr, a.stride, c.in_slot, c.i);    // (an index past the end is clamped to element 0 by the cursor and not used)
                 pn = fr_one();
                 if (e > 1) { cp = InvCursor(a, first + (uint64_t)(e - 2) * BLOCK, total); pn = tab_load_fr(a.fr, a.stride, cp.out_slot, cp.i); }   // ... and its prefix
             }
             if (cur.valid) {
-                if (fr_is_zero(x)) tab_store_fr(a.fr, a.stride, cur.out_slot, cur.i, fr_zero());
-                else { tab_store_fr(a.fr, a.stride, cur.out_slot, cur.i, fr_mul(ig, prev)); ig = fr_mul(ig, x); }
+                Fr z = fr_zero();
+                if (!fr_is_zero(x)) { z = fr_mul(ig, prev); ig = fr_mul(ig, x); }
+                tab_store_fr(a.fr, a.stride, cur.out_slot, cur.i, z);
+                if constexpr (!PLAIN) Hook::post(h, cur.i, x, z);
             }
         }
     }

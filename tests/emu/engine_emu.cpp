@@ -53,6 +53,16 @@ public:
             }
         return true;
     }
+    template <class Hook>
+    bool run_batch_inv_fused(const BatchInvArgs& a, const typename Hook::Args& h, int) {   // single pair: element i = instance i
+        for (uint64_t i = 0; i < a.n; i++) {
+            const Fr x = Hook::pre(h, i);
+            const Fr z = fr_is_zero(x) ? fr_zero() : fr_inv_fermat(x);
+            tab_store_fr(a.fr, a.stride, a.out_slot[0], i, z);
+            Hook::post(h, i, x, z);
+        }
+        return true;
+    }
     bool run_check(const CheckArgs& a, const SparseProg& prog) {
         HostPool pool = {a.pool};
         const QRegs q = q_regs_default();
