@@ -53,9 +53,10 @@ def test_fr_kernels_vs_oracle(oracle):
     assert [int.from_bytes(fm[i].tobytes(), "little") for i in range(len(pairs))] == [a for a, _ in pairs]
 
 
-@pytest.mark.parametrize("n", [1, 31, 32, 255, 256, 257, 1000, 4096 + 17])
+@pytest.mark.parametrize("n", [1, 31, 32, 255, 256, 257, 1000, 4096 + 17, 620_003])
 def test_block_batch_inversion(oracle, n):
-    """Montgomery's trick across a thread block: zeros anywhere (including whole warps / whole blocks), ragged tails."""
+    """Montgomery's trick across a thread block: zeros anywhere (including whole warps / whole blocks), ragged tails; the last
+    size is past the point where the one-wave grid gives every thread more than the minimum of 8 elements."""
     rng = random.Random(n)
     vals = [rng.randrange(Q) for _ in range(n)]
     for i in range(0, n, 7):
