@@ -234,8 +234,9 @@ PG_HD Fp fp_to_mont(const Fp& raw) {
     const Fp r2 = {{0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u}};
     return fp_mul(raw, r2);
 }
-// a^(p-2); a != 0
-PG_HD Fp fp_inv(const Fp& a) {
+// a^(p-2); a != 0.  Kept as the independent check of fp_inv (tests/emu): 381 squarings + ~190 multiplications, each one
+// dependent on the last.
+PG_HD Fp fp_inv_fermat(const Fp& a) {
     Fp res = fp_one();
 #pragma unroll 1
     for (int i = 11; i >= 0; i--) {
@@ -247,6 +248,51 @@ PG_HD Fp fp_inv(const Fp& a) {
         }
     }
     return res;
+}
+// The same inverse (it is unique) by the binary extended Euclidean algorithm, like fr_inv_binary (fr.cuh): ~550 short
+// shift / add / subtract steps instead of ~570 dependent 12-limb multiplications -- the single-thread tail of every MSM ends
+// with one of these (g1x_to_affine).  Invariant s*a == u, t*a == v (mod p) on the stored integers a~ = a R; at u == v == 1
+// t = a~^-1 and mont(t, R^3) = a^-1 R.  a != 0; variable time.
+PG_HD uint32_t fp_sub_limbs12(uint32_t* r, const uint32_t* a, const uint32_t* b) {   // r = a - b, returns the borrow
+    uint64_t bw = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { uint64_t t = (uint64_t)a[i] - b[i] - bw; r[i] = (uint32_t)t; bw = (t >> 32) & 1; }
+    return (uint32_t)bw;
+}
+PG_HD void fp_shr1(uint32_t* u) {
+#pragma unroll
+    for (int i = 0; i < 11; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 31);
+    u[11] >>= 1;
+}
+PG_HD void fp_halve_mod_p(Fp& s) {           // s/2 mod p: (s + p)/2 when s is odd (s + p < 2^382)
+    const uint32_t odd = 0u - (s.v[0] & 1u);
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { c += (uint64_t)s.v[i] + (fp_p(i) & odd); s.v[i] = (uint32_t)c; c >>= 32; }
+    fp_shr1(s.v);
+}
+PG_HD Fp fp_inv(const Fp& a) {
+    const Fp r3 = {{0xd94ca1e0u, 0xed48ac6bu, 0x03a7adf8u, 0x315f831eu, 0x615e29ddu, 0x9a53352au, 0x921e1761u, 0x34c04e5eu, 0x65724728u, 0x2512d435u, 0x91755d4du, 0x0aa63460u}};   // 2^1152 mod p
+    Fp u = a, v, s = fp_zero(), t = fp_zero(), d;
+#pragma unroll
+    for (int i = 0; i < 12; i++) v.v[i] = fp_p(i);
+    s.v[0] = 1;
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        while (!(u.v[0] & 1u)) { fp_shr1(u.v); fp_halve_mod_p(s); }
+#pragma unroll 1
+        while (!(v.v[0] & 1u)) { fp_shr1(v.v); fp_halve_mod_p(t); }
+        if (fp_sub_limbs12(d.v, u.v, v.v)) {                  // u < v
+            fp_sub_limbs12(v.v, v.v, u.v);
+            t = fp_sub(t, s);
+        } else {
+            u = d;
+            if (fp_is_zero(u)) break;                         // u == v == 1
+            s = fp_sub(s, t);
+        }
+    }
+    return fp_mul(t, r3);
 }
 
 // ---- G1 ----------------------------------------------------------------------------------------------------------------
@@ -311,9 +357,13 @@ PG_HD G1X g1x_add(const G1X& p, const G1X& q) {
     r.zz = fp_mul(fp_mul(p.zz, q.zz), pp); r.zzz = fp_mul(fp_mul(p.zzz, q.zzz), ppp);
     return r;
 }
+// LOCKSTEP: every lane of the warp converts a point of its own -- the fixed-length Fermat chain keeps them in step, the
+// data-dependent Euclid loop would not.
+template <bool LOCKSTEP = false>
 PG_HD G1Affine g1x_to_affine(const G1X& p) {
     if (g1x_is_inf(p)) return g1_affine_inf();
-    const Fp i5 = fp_inv(fp_mul(p.zz, p.zzz));            // Z^-5
+    const Fp zp = fp_mul(p.zz, p.zzz);
+    const Fp i5 = LOCKSTEP ? fp_inv_fermat(zp) : fp_inv(zp);   // Z^-5
     G1Affine a;
     a.x = fp_mul(p.x, fp_mul(i5, p.zzz));                 // X / ZZ
     a.y = fp_mul(p.y, fp_mul(i5, p.zz));                  // Y / ZZZ

@@ -191,7 +191,7 @@ struct G1FixedBaseMulBody {
     struct Args { const uint4* scalars; uint4* out; uint64_t n; G1Affine base; };
     PG_HD static void run(const Args& a, uint64_t i) {
         const Fr k = fr_from_mont(aos_load(a.scalars, i));
-        g1_affine_store(a.out, i, g1x_to_affine(g1x_mul_limbs(g1x_from_affine(a.base), k.v, 8)));
+        g1_affine_store(a.out, i, g1x_to_affine<true>(g1x_mul_limbs(g1x_from_affine(a.base), k.v, 8)));
     }
 };
 

@@ -3,6 +3,7 @@
 // logic (and the "dropped carry is zero" claims) can be checked against big-int arithmetic without a GPU.
 #define PG_EMU_CHECKS 1
 #include "../../plonk_gadgets_b200/csrc/fr.cuh"
+#include "../../plonk_gadgets_b200/csrc/g1.cuh"
 #include <cstdio>
 #include <cstdlib>
 
@@ -19,6 +20,8 @@ void emu_sub(uint64_t n, const Fr* a, const Fr* b, Fr* r) { for (uint64_t i = 0;
 void emu_neg(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_neg(a[i]); }
 void emu_inv(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_inv_fermat(a[i]); }
 void emu_inv_binary(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_inv_binary(a[i]); }
+void emu_fp_inv(uint64_t n, const pg::Fp* a, pg::Fp* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fp_inv(a[i]); }
+void emu_fp_inv_fermat(uint64_t n, const pg::Fp* a, pg::Fp* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fp_inv_fermat(a[i]); }
 void emu_from_mont(uint64_t n, const Fr* a, Fr* r) { for (uint64_t i = 0; i < n; i++) r[i] = pg::fr_from_mont(a[i]); }
 // r (9 limbs) = dot product of K=5 pairs through fr_dot_wide; ok[i] = limbs9_is_multiple_of_q(r + c)
 void emu_dot5(uint64_t n, const Fr* a, const Fr* b, const Fr* c, uint32_t* r9, uint8_t* is_mult) {

@@ -133,6 +133,26 @@ def test_fr_inversions_host_emulation(fr_emu):
         assert unpack(out) == expect, fn
 
 
+def test_fp_inversions_host_emulation(fr_emu):
+    """fp_inv (binary extended Euclid; the end of every MSM, g1x_to_affine) against x^(p-2) and against big ints, Montgomery
+    form (R = 2^384) in and out."""
+    import random
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    R = (1 << 384) % P
+    rng = random.Random(13)
+    vals = [1, 2, 3, P - 1, P - 2, R, P - R, (P + 1) // 2, 2 ** 32, 2 ** 64 - 1, 2 ** 380, 2 ** 380 + 1, pow(R, -1, P)] \
+        + [2 ** i for i in range(0, 381, 29)] + [rng.randrange(1, P) for _ in range(600)]
+    pack = lambda vs: np.frombuffer(b"".join(v.to_bytes(48, "little") for v in vs), dtype=np.uint32).reshape(-1, 12).copy()
+    unpack = lambda a: [int.from_bytes(a[i].tobytes(), "little") for i in range(a.shape[0])]
+    A = pack(vals)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    expect = [pow(v * pow(R, -1, P) % P, -1, P) * R % P for v in vals]
+    for fn in ("emu_fp_inv", "emu_fp_inv_fermat"):
+        out = np.zeros_like(A)
+        getattr(fr_emu, fn)(C.c_uint64(len(vals)), vp(A), vp(out))
+        assert unpack(out) == expect, fn
+
+
 def test_emu_wire_format(emu, oracle):
     """to_bytes / from_bytes (canonical LE 32 bytes) against the oracle's, including rejection of encodings >= q."""
     import random
