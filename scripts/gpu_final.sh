@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round evidence in one call: full GPU test suite, smoke, headline bench (both arms, both check modes), the other BASELINE
-# configurations, the evaluation-domain and commitment kernels, then one ncu --set full capture each of k_ntt_pass and the
-# batch inversion (each only after the same command has exited 0 without ncu).
+# configurations, the evaluation-domain and commitment kernels, then the launch list of C4 and one ncu --set full capture of the
+# batch inversion (each only after the same command has exited 0 without ncu).  What comes back is limited to 64 MiB: one report.
 TAG=${1:-f}
 OUT=gpurun_out; mkdir -p $OUT
 timeout 1800 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log; tail -4 $OUT/${TAG}_pytest.log
@@ -14,14 +14,10 @@ timeout 900 python scripts/bench_configs.py --sparse > $OUT/${TAG}_configs_spars
 timeout 600 python scripts/bench_range_gate.py > $OUT/${TAG}_range_gate.jsonl 2> $OUT/${TAG}_range_gate.err; cut -c1-200 $OUT/${TAG}_range_gate.jsonl
 timeout 600 python scripts/bench_ntt.py > $OUT/${TAG}_ntt.jsonl 2> $OUT/${TAG}_ntt.err; cut -c1-160 $OUT/${TAG}_ntt.jsonl
 timeout 900 python scripts/bench_msm.py 16 18 20 22 > $OUT/${TAG}_msm.jsonl 2> $OUT/${TAG}_msm.err; cut -c1-200 $OUT/${TAG}_msm.jsonl
-CMD="python scripts/bench_ntt.py 24"
-timeout 300 $CMD > $OUT/${TAG}_ntt_plain.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ntt_pass -s 4 -c 2 -f -o $OUT/${TAG}_prof_ntt $CMD > $OUT/${TAG}_ncu_ntt.log 2>&1
-tail -1 $OUT/${TAG}_ncu_ntt.log
 CMD="python scripts/prof_c4.py 24"
 timeout 300 $CMD > $OUT/${TAG}_c4_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches_c4.csv $CMD > $OUT/${TAG}_ncu_c4.log 2>&1
 timeout 300 $CMD > $OUT/${TAG}_c4_plain2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_inv -s 2 -c 2 -f -o $OUT/${TAG}_prof_batch_inv $CMD > $OUT/${TAG}_ncu_c4_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_inv -s 2 -c 1 -f -o $OUT/${TAG}_prof_batch_inv $CMD > $OUT/${TAG}_ncu_c4_full.log 2>&1
 tail -1 $OUT/${TAG}_ncu_c4_full.log
 tail -3 $OUT/${TAG}_bench.err $OUT/${TAG}_configs.err $OUT/${TAG}_ntt.err $OUT/${TAG}_msm.err | cut -c1-200
