@@ -65,3 +65,45 @@ def allgather_scalars(local, device=None):
     out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous())
     return out
+
+
+def allgather_ragged(local, device=None):
+    """All-gather of shards whose lengths differ between ranks (n not a multiple of the world size): the lengths are exchanged
+    first, every shard is padded to the longest, gathered, and trimmed.  Returns the list of the ranks' shards, in rank order."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [local]
+    world = dist.get_world_size()
+    lens = torch.zeros(world, dtype=torch.int64, device=local.device)
+    lens[dist.get_rank()] = local.shape[0]
+    dist.all_reduce(lens, op=dist.ReduceOp.SUM)
+    longest = int(lens.max().item())
+    padded = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((world * longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    return [out[r * longest: r * longest + int(lens[r].item())] for r in range(world)]
+
+
+def allgather_witness_shards(local_vars, call_sizes):
+    """Gather of witness shards: assemble the variable table of the SEQUENTIAL composer of the whole batch from the ranks' tables.
+
+    `local_vars`: this rank's variable table in Variable order ((FRESH_VARS + sum(call_sizes), 4) int64 tensor, e.g.
+    `composer.variables()`); `call_sizes`: how many variables each batched call (add_input, range_check, ...) appended on this
+    rank, in call order -- every rank makes the same calls on its own instance range.  In the sequential composer call k's
+    variables of all instances are contiguous, instance-major, so the result is
+        [fresh variables] [call 0: rank 0 | rank 1 | ...] [call 1: rank 0 | rank 1 | ...] ...
+    (the fresh composer's five variables are the same on every rank and are taken once)."""
+    import torch
+    assert local_vars.shape[0] == FRESH_VARS + sum(call_sizes)
+    shards = allgather_ragged(local_vars)
+    sizes = allgather_ragged(torch.tensor([list(call_sizes)], dtype=torch.int64, device=local_vars.device))
+    parts = [shards[0][:FRESH_VARS]]
+    offs = [FRESH_VARS] * len(shards)
+    for k in range(len(call_sizes)):
+        for r, sh in enumerate(shards):
+            cnt = int(sizes[r][0, k].item())
+            parts.append(sh[offs[r]: offs[r] + cnt])
+            offs[r] += cnt
+    return torch.cat(parts, dim=0)

@@ -45,7 +45,10 @@ def _worker(rank, world, port, n, q):
     off = sharding.shard_offsets(n, rank, world, 271, 653)
     first_global = None if first_local is None else sharding.FRESH_ROWS + off.row_offset + 271 * first_local + 270
     tot_bad, tot_first, tot_err = sharding.allreduce_verdict(n_bad, first_global, 0)
-    gathered = sharding.allgather_scalars(torch.from_numpy(y.values().view(np.int64)))
+    gathered = sharding.allgather_ragged(torch.from_numpy(y.values().view(np.int64)))
+    gathered = torch.cat(gathered, dim=0)
+    # gather of witness shards: the two calls appended 1 and 653 variables per instance
+    table = sharding.allgather_witness_shards(torch.from_numpy(c.variables().view(np.int64)), [hi - lo, 653 * (hi - lo)])
     # second call shape: the native range gate (10 rows per 64-bit witness), verdict straight from the engine's own check;
     # odd instances are uniform Fr and do not fit 64 bits, so both shards hold unsatisfied rows
     c2 = pg.StandardComposer(_cdll=emu)
@@ -54,7 +57,8 @@ def _worker(rank, world, port, n, q):
     off2 = sharding.shard_offsets(n, rank, world, 10, 32)
     rg = sharding.allreduce_verdict(bad2, None if first2 is None else first2 + off2.row_offset, 0)
     if rank == 0:
-        q.put((tot_bad, tot_first, tot_err, gathered.numpy().view(np.uint64).copy(), off.row_offset, off.var_offset, rg))
+        q.put((tot_bad, tot_first, tot_err, gathered.numpy().view(np.uint64).copy(), off.row_offset, off.var_offset, rg,
+               table.numpy().view(np.uint64).copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,13 +71,13 @@ def test_two_rank_sharding_equals_single_run(oracle):
     from tests.programs import synth_wide
     from tests.test_emu_engine import _build
     emu = _lib.bind(C.CDLL(_build("libpg_emu.so", "engine_emu.cpp")))
-    n = 16
+    n = 17                                                   # ragged: 8 + 9 instances
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
     for p in procs: p.start()
-    tot_bad, tot_first, tot_err, gathered, off_r, off_v, rg = q.get(timeout=240)
+    tot_bad, tot_first, tot_err, gathered, off_r, off_v, rg, table = q.get(timeout=240)
     for p in procs: p.join(timeout=60)
     assert all(p.exitcode == 0 for p in procs)
     # single-process run of the whole batch
@@ -83,6 +87,7 @@ def test_two_rank_sharding_equals_single_run(oracle):
     w = c.add_input(oracle.from_ints(wit))
     y = pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), w)
     assert (gathered == y.values()).all()
+    assert table.shape == (5 + n * 654, 4) and (table == c.variables()).all()    # the sequential composer's variable table
     assert (tot_bad, tot_err) == (2, 0)
     assert tot_first == 3 + 271 * 5 + 270                    # the output row of instance 5 in the sequential numbering
     assert (off_r, off_v) == (0, 0)
