@@ -224,7 +224,7 @@ def test_range_check_c2_properties(oracle, torch_cuda, log2n):
 
 
 def test_max_bound_c3_and_scalar_c4_properties(oracle, torch_cuda):
-    """C3 shape (max_bound, 252-bit per-instance bounds, k=253) and C4 shape (is_non_zero + maybe_equal) at 2^18."""
+    """C3 shape (max_bound, 252-bit per-instance bounds, k=253) at 2^18 and C4 shape (is_non_zero + maybe_equal) at 2^20."""
     torch = torch_cuda
     n = 1 << 18
     c = gpu_composer()
@@ -239,8 +239,9 @@ def test_max_bound_c3_and_scalar_c4_properties(oracle, torch_cuda):
     assert (res[0::2] == one).all()
     frac_in = float((res[1::2] == one).all(axis=1).mean())
     assert 0.2 < frac_in < 0.35              # y = 1 iff (max-1-x mod q) fits k = 253 bits: probability 2^253/q ~ 0.277
-    # C4
+    # C4 (2^20 pairs: past the size where the one-wave batch inversion gives a thread more than its minimum of 8 elements)
     c.reset()
+    n = 1 << 20
     a = torch.empty((n, 4), dtype=torch.int64, device="cuda"); b = torch.empty_like(a)
     c.synth(SEED, 41, 0, 0, a); c.synth(SEED, 42, 0, 0, b)
     c.sync()                                 # the engine runs on its own stream: finish before torch touches the buffers
@@ -252,6 +253,12 @@ def test_max_bound_c3_and_scalar_c4_properties(oracle, torch_cuda):
     assert c.check_circuit_satisfied() == (0, None)
     r = eq.values()
     assert (r[0::2] == one).all() and (r[1::2] == 0).all()
+    # the inverses themselves, at both ends of the batch: variables u, z, y of instance i follow the 5 + 2n inputs
+    for i0 in (0, n - 64):
+        uzy = oracle.to_ints(c.variables(5 + 2 * n + 3 * i0, 3 * 64))
+        for j in range(64):
+            u, z, y = uzy[3 * j: 3 * j + 3]
+            assert (u, z, y) == (0, 0, 1) if (i0 + j) % 2 == 0 else (u != 0 and z * u % Q == 1 and y == 0)
 
 
 def test_full_size_metric_config(oracle, torch_cuda):
