@@ -26,6 +26,10 @@ public:
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // device -> pinned-host result copies that overlap with later kernels
     cudaEvent_t copy_ready = nullptr;
+    cudaStream_t in_stream = nullptr;        // chunked host -> device input copies that overlap with the kernels consuming earlier chunks
+    struct PendingCopy { const void* table; uint64_t lo, hi; cudaEvent_t ev; };   // elements [lo, hi) of `table` arrive with `ev`
+    std::vector<PendingCopy> pending;
+    std::vector<cudaEvent_t> sync_ev_free;   // events without timing, for stream ordering only
     bool own_stream = false;
     bool nodev = false;
     bool timing_on = false;
@@ -85,9 +89,13 @@ public:
         for (auto& ev : ev_free) cudaEventDestroy(ev);
         events.clear(); ev_free.clear();
         if (sort_tmp) { cudaFree(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0; }
+        for (auto& pc : pending) cudaEventDestroy(pc.ev);
+        for (auto& ev : sync_ev_free) cudaEventDestroy(ev);
+        pending.clear(); sync_ev_free.clear();
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (in_stream) cudaStreamDestroy(in_stream);
         if (copy_ready) cudaEventDestroy(copy_ready);
-        copy_stream = nullptr; copy_ready = nullptr;
+        copy_stream = nullptr; in_stream = nullptr; copy_ready = nullptr;
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -99,15 +107,65 @@ public:
     }
     void release(void* p) { cudaFree(p); }
     bool h2d(void* dst, const void* src, size_t bytes) { PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); return true; }
+    // ---- input copies that overlap with compute ----------------------------------------------------------------------
+    // h2d_chunked copies `n` elements in chunks on in_stream, one event per chunk.  Until the main stream has waited on those
+    // events the destination is "pending": join_copies() makes it wait on all of them and runs at the head of EVERY operation
+    // that could read device memory (tic() -- i.e. every kernel launch --, d2h, d2d, d2h_async, sync, scans and sorts); the one
+    // consumer that knows about chunks, run_simple_chunked, waits chunk by chunk instead and so overlaps with the copies.
+    // Plain h2d does not join: it only writes buffers of its own.
+    cudaEvent_t get_sync_event() {
+        if (!sync_ev_free.empty()) { cudaEvent_t e = sync_ev_free.back(); sync_ev_free.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e;
+    }
+    void join_copies() {
+        for (auto& pc : pending) { cudaStreamWaitEvent(stream, pc.ev, 0); sync_ev_free.push_back(pc.ev); }
+        pending.clear();
+    }
+    bool h2d_chunked(void* dst, const void* src, uint64_t n, size_t elem, uint64_t chunk) {
+        cudaEvent_t head = get_sync_event();         // the destination may come from the pool: order behind what is queued
+        PG_CUDA(cudaEventRecord(head, stream));
+        PG_CUDA(cudaStreamWaitEvent(in_stream, head, 0));
+        sync_ev_free.push_back(head);
+        for (uint64_t lo = 0; lo < n; lo += chunk) {
+            const uint64_t hi = lo + chunk < n ? lo + chunk : n;
+            PG_CUDA(cudaMemcpyAsync((char*)dst + lo * elem, (const char*)src + lo * elem, (hi - lo) * elem, cudaMemcpyHostToDevice, in_stream));
+            cudaEvent_t ev = get_sync_event();
+            PG_CUDA(cudaEventRecord(ev, in_stream));
+            pending.push_back(PendingCopy{dst, lo, hi, ev});
+        }
+        return true;
+    }
+    // Body over [0, n) whose operand table may still be arriving: if every pending copy targets `table`, one launch per chunk
+    // behind that chunk's event (Body::Args carries the chunk as i0 / n); otherwise the ordinary launch (which joins).
+    template <class Body>
+    bool run_simple_chunked(const typename Body::Args& a_in, uint64_t n, int cls, const void* table) {
+        bool mine = !pending.empty();
+        uint64_t covered = 0;
+        for (auto& pc : pending) { mine = mine && pc.table == table && pc.lo == covered; covered = pc.hi; }
+        if (!mine || covered != n) return run_simple<Body>(a_in, n, cls);
+        std::vector<PendingCopy> chunks; chunks.swap(pending);          // tic() must not join what is waited on below
+        tic(cls, 0);
+        for (auto& pc : chunks) {
+            typename Body::Args a = a_in;
+            a.i0 = pc.lo; a.n = pc.hi - pc.lo;
+            cudaStreamWaitEvent(stream, pc.ev, 0);
+            sync_ev_free.push_back(pc.ev);
+            k_simple<Body><<<grid_for(a.n), BLOCK, 0, stream>>>(a);
+        }
+        toc();
+        return launched("k_simple (chunked)");
+    }
     bool d2h(void* dst, const void* src, size_t bytes) {
+        join_copies();
         PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaStreamSynchronize(stream));
         return true;
     }
-    bool d2d(void* dst, const void* src, size_t bytes) { PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); return true; }
-    bool sync() { PG_CUDA(cudaStreamSynchronize(stream)); PG_CUDA(cudaStreamSynchronize(copy_stream)); return true; }
+    bool d2d(void* dst, const void* src, size_t bytes) { join_copies(); PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); return true; }
+    bool sync() { join_copies(); PG_CUDA(cudaStreamSynchronize(stream)); PG_CUDA(cudaStreamSynchronize(copy_stream)); return true; }
     // copy to (pinned) host memory on the copy stream, ordered after everything enqueued so far; complete after sync()
     bool d2h_async(void* dst, const void* src, size_t bytes) {
+        join_copies();
         PG_CUDA(cudaEventRecord(copy_ready, stream));
         PG_CUDA(cudaStreamWaitEvent(copy_stream, copy_ready, 0));
         PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, copy_stream));
@@ -136,6 +194,7 @@ public:
         events.clear();
     }
     void tic(int cls, uint64_t rows) {
+        join_copies();
         if (!timing_on) return;
         if (events.size() >= 4096) fold_events();    // bounded bookkeeping when nobody collects the timings
         Ev ev{get_event(), get_event(), cls, rows};
@@ -144,6 +203,7 @@ public:
     }
     void toc() { if (timing_on) cudaEventRecord(events.back().b, stream); }
     bool timing(pg_timing* out, bool reset) {
+        join_copies();
         PG_CUDA(cudaStreamSynchronize(stream));
         fold_events();
         *out = acc;

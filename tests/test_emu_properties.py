@@ -114,8 +114,8 @@ def test_sparse_program_random_compositions(emu, oracle, vals, seq, seed):
         elif op == "is_non_zero":
             prog.append(dict(op=op, var=a, assigned=[hx(v if v else 1) for v in col_a]))
         elif op == "max_bound":
-            bits = int(rng.integers(1, 250))
-            prog.append(dict(op=op, max=[hx(2 ** bits + int(rng.integers(0, 2 ** min(bits, 60)))) for _ in range(n)] if seed % 3 == 0 else hx(2 ** bits), witness=a))
+            bits = int(rng.integers(1, 250))      # per-instance bounds: max - 1 in [2^bits, 2^(bits+1)) for every instance (same num_bits)
+            prog.append(dict(op=op, max=[hx(2 ** bits + 1 + int(rng.integers(0, 2 ** min(bits, 60)))) for _ in range(n)] if seed % 3 == 0 else hx(2 ** bits), witness=a))
             cols.append(len(prog) - 1)
         else:
             prog.append(dict(op="constrain_to_constant", a=a, constant=hx(int(rng.integers(0, 3))), pi=[hx(v) for v in col_b] if seed % 2 else None))
