@@ -85,6 +85,7 @@ struct RangeArgs {
     DevTab x_tab; uint32_t x_loc;
     uint4* fr; uint32_t* bits; uint4* param; uint64_t stride;
     uint64_t n; uint32_t k;
+    uint64_t i0;                                     // RangePre only: first instance of this launch (chunked launches behind input copies)
     int uniform; Fr m; Fr negmin;                    // uniform bounds: max-1 and -min
     const uint4* max_aos; const uint4* min_aos;      // per-instance bounds
     uint32_t param_m, param_negmin;
@@ -115,7 +116,8 @@ struct RangePre {
         }
         tab_store_fr(a.fr, a.stride, s.u, i, fr_sub(acc, v));                  // maybe_equal: u = a - b, scalar.rs:111-121
     }
-    PG_HD static void run(const Args& a, uint64_t i) {
+    PG_HD static void run(const Args& a, uint64_t i_launch) {
+        const uint64_t i = a.i0 + i_launch;
         const Fr x = loc_load(&a.x_tab, a.x_loc, i);
         Fr m = a.m, negmin = a.negmin;
         if (!a.uniform) {

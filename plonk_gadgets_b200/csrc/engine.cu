@@ -60,6 +60,7 @@ public:
         if (cfg.stream) { stream = (cudaStream_t)cfg.stream; own_stream = false; }
         else { PG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
         PG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        PG_CUDA(cudaStreamCreateWithFlags(&in_stream, cudaStreamNonBlocking));
         PG_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
         check_shape = cfg.reserved < (uint32_t)CHECK_SHAPES ? (int)cfg.reserved : 0;

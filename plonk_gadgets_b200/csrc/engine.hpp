@@ -34,6 +34,7 @@ namespace pg {
 enum { CLS_CHECK = 0, CLS_WITNESS = 1, CLS_OTHER = 2 };
 
 struct Column { uint32_t seg; uint32_t local; uint64_t inst_off; uint64_t n; };
+constexpr uint64_t INPUT_CHUNKS = 4, INPUT_CHUNK_MIN = 1ull << 20;     // host inputs of at least 2^20 scalars (32 MiB) are copied in four chunks
 
 struct Segment {
     Template t;
@@ -348,7 +349,13 @@ public:
         if (rc) return rc;
         Segment& s = segs.back();
         // a one-slot table of 32-byte scalars has exactly the caller's layout (BlsScalar[n]): the values are copied straight in
-        if (n && !(on_device ? be.d2d(s.fr, values, n * sizeof(pg_fr)) : be.h2d(s.fr, values, n * sizeof(pg_fr)))) return fail(PG_ERR_CUDA, "add_input copy");
+        // Large host batches arrive in INPUT_CHUNKS chunks on the backend's input stream; a range gadget called on the column next
+        // starts on the first chunk while the others are still in flight (run_simple_chunked), anything else waits for all of them.
+        const bool chunked = !on_device && n >= INPUT_CHUNK_MIN;
+        const uint64_t chunk = (((n + INPUT_CHUNKS - 1) / INPUT_CHUNKS) + 1023) & ~1023ull;
+        if (n && !(on_device ? be.d2d(s.fr, values, n * sizeof(pg_fr))
+                   : chunked ? be.h2d_chunked(s.fr, values, n, sizeof(pg_fr), chunk)
+                             : be.h2d(s.fr, values, n * sizeof(pg_fr)))) return fail(PG_ERR_CUDA, "add_input copy");
         *out = new_column((uint32_t)segs.size() - 1, 0, n);
         return PG_OK;
     }
@@ -391,9 +398,12 @@ public:
             BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
             inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = is_range_check ? 2 : 1;
             for (uint32_t e = 0; e < inv.n_pairs; e++) { inv.in_slot[e] = a.d[e].u; inv.out_slot[e] = a.d[e].z; }
+            // the operand's table, when the operand is a whole column of its segment (chunks of a pending input copy are instance ranges of it)
+            const Segment& os = segs[operand.seg];
+            const void* whole = (operand.inst_off == 0 && operand.n == os.n_inst) ? (const void*)os.fr : nullptr;
             const bool ok = is_range_check
-                ? be.template run_simple<RangePre<true>>(a, n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true>>(a, n, CLS_WITNESS)
-                : be.template run_simple<RangePre<false>>(a, n, CLS_WITNESS) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false>>(a, n, CLS_WITNESS);
+                ? be.template run_simple_chunked<RangePre<true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true>>(a, n, CLS_WITNESS)
+                : be.template run_simple_chunked<RangePre<false>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false>>(a, n, CLS_WITNESS);
             if (!ok) return fail(PG_ERR_CUDA, "range witness kernels");
         }
         if (!uniform && n) {

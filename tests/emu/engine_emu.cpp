@@ -31,6 +31,7 @@ public:
     void* alloc(size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 64, bytes ? bytes : 64)) return nullptr; memset(p, 0xA5, bytes); return p; }
     void release(void* p) { free(p); }
     bool h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
+    bool h2d_chunked(void* d, const void* s, uint64_t n, size_t elem, uint64_t) { memcpy(d, s, n * elem); return true; }
     bool d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
     bool d2d(void* d, const void* s, size_t n) { memmove(d, s, n); return true; }
     bool d2h_async(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
@@ -43,6 +44,17 @@ public:
     template <class Body>
     bool run_simple(const typename Body::Args& a, uint64_t n, int) {
         for (uint64_t i = 0; i < n; i++) Body::run(a, i);
+        return true;
+    }
+    // the chunk-by-chunk launch of the CUDA backend (operand still arriving), here in three uneven chunks through the same i0 / n
+    template <class Body>
+    bool run_simple_chunked(const typename Body::Args& a_in, uint64_t n, int, const void*) {
+        const uint64_t cut[4] = {0, n / 3, n / 3 + n / 2, n};     // n/3 + n/2 <= n
+        for (int k = 0; k < 3; k++) {
+            typename Body::Args a = a_in;
+            a.i0 = cut[k]; a.n = cut[k + 1] - cut[k];
+            for (uint64_t i = 0; i < a.n; i++) Body::run(a, i);
+        }
         return true;
     }
     bool run_batch_inv(const BatchInvArgs& a, int) {   // one Fermat inversion per element (the block-wide trick is GPU-only)

@@ -223,6 +223,45 @@ def test_range_check_c2_properties(oracle, torch_cuda, log2n):
         assert (rows["sel"] == o_sel).all(), f"selectors of instance {i}"
 
 
+def test_chunked_host_input_equals_device_input(oracle, torch_cuda):
+    """Host batches of >= 2^20 scalars are copied in chunks on the input stream while RangePre already runs on the chunks that
+    have arrived: every variable must equal the run with device-resident input -- through the chunk-aware consumer (range_check
+    right after add_input), through consumers that wait for the whole copy (maybe_equal; range_check on the first of two pending
+    columns; a read-back), from pinned and from pageable host memory."""
+    torch = torch_cuda
+    n = (1 << 20) + 777                                   # ragged last chunk
+    mn, mx = oracle.from_ints([0]), oracle.from_ints([2 ** 64])
+    c = gpu_composer()
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    c.synth(SEED, 2, 2, 64, wit)
+    c.sync()
+    y = pg.range_check(c, mn, mx, c.add_input(wit))
+    assert c.check_circuit_satisfied() == (0, None)
+    ref_y = y.values()
+    ref_vars = [c.variables(5 + n + 653 * i, 653).copy() for i in (0, n // 4 - 1, n // 4 + 300, n // 2 + 5, n - 1)]
+    pinned = wit.cpu().pin_memory()
+    pageable = pinned.numpy().view(np.uint64).copy()
+    for host in (pinned, pageable):
+        c.reset()
+        y = pg.range_check(c, mn, mx, c.add_input(host))          # chunk by chunk behind the copies
+        assert c.check_circuit_satisfied() == (0, None)
+        assert (y.values() == ref_y).all()
+        for i, ref in zip((0, n // 4 - 1, n // 4 + 300, n // 2 + 5, n - 1), ref_vars):
+            assert (c.variables(5 + n + 653 * i, 653) == ref).all(), i
+    # consumers that are not chunk-aware
+    c.reset()
+    a = c.add_input(pinned); b = c.add_input(pageable)             # two pending columns
+    assert (b.values(n - 3, 3) == pageable[n - 3:]).all()          # read-back waits for the copies
+    eq = pg.maybe_equal(c, a, b)
+    y = pg.range_check(c, mn, mx, a)
+    assert c.check_circuit_satisfied() == (0, None)
+    assert (eq.values() == oracle.from_ints([1])[0]).all() and (y.values() == ref_y).all()
+    c.reset()
+    a = c.add_input(pinned); b = c.add_input(pinned)               # both still in flight when range_check(a) starts
+    y = pg.range_check(c, mn, mx, a)
+    assert c.check_circuit_satisfied() == (0, None) and (y.values() == ref_y).all()
+
+
 def test_max_bound_c3_and_scalar_c4_properties(oracle, torch_cuda):
     """C3 shape (max_bound, 252-bit per-instance bounds, k=253) at 2^18 and C4 shape (is_non_zero + maybe_equal) at 2^20."""
     torch = torch_cuda
