@@ -92,8 +92,10 @@ int pg_sync(pg_ctx *ctx);
 
 /* ---- gadgets ------------------------------------------------------------------------------------------------------
  * `on_device` != 0: the pointer arguments of the call are 32-byte aligned device pointers on cfg.device (read asynchronously on the
- * ctx stream; keep them alive until pg_sync); == 0: host pointers (copied with cudaMemcpyAsync on the ctx stream;
- * pinned memory makes that copy asynchronous). */
+ * ctx stream; keep them alive until pg_sync); == 0: host pointers (copied with cudaMemcpyAsync; pinned memory makes that copy
+ * asynchronous -- keep the buffer alive and unchanged until the next call that returns data or pg_sync).  pg_add_input_batch copies
+ * host batches of 2^20 scalars or more in chunks on a separate input stream, and a range gadget called on that column next starts on
+ * the chunks that have arrived; every other operation waits for the whole copy first. */
 
 /* AllocatedScalar::allocate / composer.add_input over n scalars -- /root/reference/src/allocated_scalar.rs:27-30.
  * Appends n variables, no rows. */
