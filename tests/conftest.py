@@ -11,6 +11,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # property tests: the same examples on every run unless HYPOTHESIS_PROFILE=explore (or --hypothesis-seed) asks for fresh ones
+    try:
+        from hypothesis import settings
+        settings.register_profile("repeatable", derandomize=True)
+        settings.register_profile("explore", derandomize=False)
+        settings.load_profile(os.environ.get("HYPOTHESIS_PROFILE", "repeatable"))
+    except ImportError:
+        pass
 
 
 @pytest.fixture(scope="session")
