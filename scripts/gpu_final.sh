@@ -20,4 +20,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 timeout 300 $CMD > $OUT/${TAG}_c4_plain2.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_inv -s 2 -c 1 -f -o $OUT/${TAG}_prof_batch_inv $CMD > $OUT/${TAG}_ncu_c4_full.log 2>&1
 tail -1 $OUT/${TAG}_ncu_c4_full.log
-tail -3 $OUT/${TAG}_bench.err $OUT/${TAG}_configs.err $OUT/${TAG}_ntt.err $OUT/${TAG}_msm.err | cut -c1-200
+for f in bench configs ntt msm; do tail -n 3 $OUT/${TAG}_$f.err | cut -c1-200; done
