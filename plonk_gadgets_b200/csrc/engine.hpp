@@ -955,7 +955,9 @@ public:
         return stage(reinterpret_cast<const pg_fr*>(p), (bytes + sizeof(pg_fr) - 1) / sizeof(pg_fr), on_device, rc);   // whole 32-byte units
     }
     // device-side MSM: d_points (n affine), d_scalars (n Montgomery scalars) -> d_out (one affine point, 96 bytes)
-    int msm_dev(uint64_t n, const uint4* d_points, const uint4* d_scalars, uint4* d_out) {
+    // `defer` != nullptr: the window sums (n_windows XYZZ points) are parked there instead of being combined; msm_finish combines the
+    // window sums of several MSMs of the same size in one launch.
+    int msm_dev(uint64_t n, const uint4* d_points, const uint4* d_scalars, uint4* d_out, uint4* defer = nullptr) {
         const size_t mark = scratch.size();
         auto tmp = [&](size_t bytes) -> void* { void* q = dalloc(bytes); if (q) scratch.push_back(q); return q; };
         const MsmPlan plan = msm_plan(n);
@@ -1006,11 +1008,22 @@ public:
             if (!be.template run_simple<MsmSumBody>(sm, sm.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm sum kernel");
             std::swap(src, dst); seg = seg_out;
         }
-        MsmFinalBody::Args fin{src, d_out, 1, plan.c, plan.n_windows};
-        if (!be.template run_simple<MsmFinalBody>(fin, 1, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm final kernel");
+        if (defer) { if (!be.d2d(defer, src, (size_t)plan.n_windows * sizeof(G1X))) return fail(PG_ERR_CUDA, "msm window sums"); }
+        else {
+            MsmFinalBody::Args fin{src, d_out, 1, plan.c, plan.n_windows};
+            if (!be.template run_simple<MsmFinalBody>(fin, 1, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm final kernel");
+        }
         release_scratch_from(mark);      // work buffers are only touched by kernels on the engine's stream: stream order makes their reuse safe
         return PG_OK;
     }
+    // d_out[t] = the MSM whose window sums were parked at windows + t * n_windows (count MSMs of n terms each)
+    int msm_finish(uint64_t n, const uint4* windows, uint64_t count, uint4* d_out) {
+        const MsmPlan plan = msm_plan(n);
+        MsmFinalBody::Args fin{windows, d_out, count, plan.c, plan.n_windows};
+        if (!be.template run_simple<MsmFinalBody>(fin, count, CLS_OTHER)) return fail(PG_ERR_CUDA, "msm final kernel");
+        return PG_OK;
+    }
+    static constexpr size_t MSM_MAX_WINDOWS = 256;     // c >= 1
     int msm(uint64_t n, const pg_g1_affine* points, const pg_fr* scalars, pg_g1_affine* out, int on_device) {
         if (!out || (n && (!points || !scalars))) return fail(PG_ERR_ARG, "msm: null argument");
         if (n >= (1ull << 32)) return fail(PG_ERR_ARG, "msm: more than 2^32 - 1 terms");
@@ -1078,9 +1091,11 @@ public:
         int rc; const uint4* dp = stage_bytes(powers, n * sizeof(pg_g1_affine), powers_on_device, &rc); if (!dp) return rc;
         uint4* polys = (uint4*)dalloc(4 * n * sizeof(pg_fr)); if (!polys) return fail(PG_ERR_OOM, "wire polynomial buffer"); scratch.push_back(polys);
         uint4* d_out = (uint4*)dalloc(4 * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "commitments"); scratch.push_back(d_out);
+        uint4* win = (uint4*)dalloc(4 * MSM_MAX_WINDOWS * sizeof(G1X)); if (!win) return fail(PG_ERR_OOM, "window sums"); scratch.push_back(win);
         if ((rc = wire_polynomials(log_n, reinterpret_cast<pg_fr*>(polys), 1))) return rc;
         for (int w = 0; w < 4; w++)
-            if ((rc = msm_dev(n, dp, polys + 2 * (uint64_t)w * n, d_out + 6 * w))) return rc;
+            if ((rc = msm_dev(n, dp, polys + 2 * (uint64_t)w * n, nullptr, win + (size_t)w * msm_plan(n).n_windows * (sizeof(G1X) / sizeof(uint4))))) return rc;
+        if ((rc = msm_finish(n, win, 4, d_out))) return rc;                 // the four Horner chains side by side
         rc = deliver(out, d_out, 4 * sizeof(pg_g1_affine), 0);
         release_scratch_from(mark);
         return rc;
@@ -1119,6 +1134,7 @@ public:
         int rc; const uint4* dp = stage_bytes(lagrange, n * sizeof(pg_g1_affine), points_on_device, &rc); if (!dp) return rc;
         uint4* vals = (uint4*)dalloc(4 * n * sizeof(pg_fr)); if (!vals) return fail(PG_ERR_OOM, "wire value buffer"); scratch.push_back(vals);
         uint4* d_out = (uint4*)dalloc(4 * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "commitments"); scratch.push_back(d_out);
+        uint4* win = (uint4*)dalloc(4 * MSM_MAX_WINDOWS * sizeof(G1X)); if (!win) return fail(PG_ERR_OOM, "window sums"); scratch.push_back(win);
         if ((rc = materialize_dev(0, n_rows, n, nullptr, vals, nullptr, nullptr))) return rc;       // to_scalars(w_l..w_4)
         for (int w = 0; w < 4; w++) {
             uint4* col = vals + 2 * (uint64_t)w * n;
@@ -1126,8 +1142,9 @@ public:
                 NttZeroBody::Args z{col, n_rows, n - n_rows};
                 if (!be.template run_simple<NttZeroBody>(z, z.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "padding kernel");
             }
-            if ((rc = msm_dev(n, dp, col, d_out + 6 * w))) return rc;
+            if ((rc = msm_dev(n, dp, col, nullptr, win + (size_t)w * msm_plan(n).n_windows * (sizeof(G1X) / sizeof(uint4))))) return rc;
         }
+        if ((rc = msm_finish(n, win, 4, d_out))) return rc;
         rc = deliver(out, d_out, 4 * sizeof(pg_g1_affine), 0);
         release_scratch_from(mark);
         return rc;

@@ -173,16 +173,18 @@ struct MsmSumBody {
     }
 };
 
-// result = sum_w 2^(c*w) * window[w], as an affine point
+// result[t] = sum_w 2^(c*w) * window[t][w], as an affine point.  One thread per MSM: the Horner chain (c * n_windows ~ 255 dependent
+// doublings) is serial by nature, so MSMs that are computed together (the four wire commitments) finish in ONE launch -- their
+// chains run side by side in one warp instead of one after the other.
 struct MsmFinalBody {
-    struct Args { const uint4* windows; uint4* out; uint64_t n; /* 1 */ uint32_t c, n_windows; };
-    PG_HD static void run(const Args& a, uint64_t) {
+    struct Args { const uint4* windows; uint4* out; uint64_t n; /* MSMs */ uint32_t c, n_windows; };
+    PG_HD static void run(const Args& a, uint64_t t) {
         G1X total = g1x_inf();
         for (uint32_t w = a.n_windows; w-- > 0;) {
             for (uint32_t k = 0; k < a.c; k++) total = g1x_dbl(total);
-            total = g1x_add(total, g1x_load(a.windows, w));
+            total = g1x_add(total, g1x_load(a.windows, t * a.n_windows + w));
         }
-        g1_affine_store(a.out, 0, g1x_to_affine(total));
+        g1_affine_store(a.out, t, g1x_to_affine(total));
     }
 };
 
