@@ -27,7 +27,7 @@ public:
     cudaStream_t copy_stream = nullptr;      // device -> pinned-host result copies that overlap with later kernels
     cudaEvent_t copy_ready = nullptr;
     cudaStream_t in_stream = nullptr;        // chunked host -> device input copies that overlap with the kernels consuming earlier chunks
-    struct PendingCopy { const void* table; uint64_t lo, hi; cudaEvent_t ev; };   // elements [lo, hi) of `table` arrive with `ev`
+    struct PendingCopy { const void* table; const void* table_end; uint64_t lo, hi; cudaEvent_t ev; };   // elements [lo, hi) of `table` arrive with `ev`
     std::vector<PendingCopy> pending;
     std::vector<cudaEvent_t> sync_ev_free;   // events without timing, for stream ordering only
     bool own_stream = false;
@@ -107,13 +107,19 @@ public:
         return p;
     }
     void release(void* p) { cudaFree(p); }
-    bool h2d(void* dst, const void* src, size_t bytes) { PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); return true; }
+    bool h2d(void* dst, const void* src, size_t bytes) {
+        for (auto& pc : pending)                    // a write INTO a table that is still arriving (pg_poke_variable) must land after it
+            if (dst >= pc.table && dst < pc.table_end) { join_copies(); break; }
+        PG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return true;
+    }
     // ---- input copies that overlap with compute ----------------------------------------------------------------------
     // h2d_chunked copies `n` elements in chunks on in_stream, one event per chunk.  Until the main stream has waited on those
     // events the destination is "pending": join_copies() makes it wait on all of them and runs at the head of EVERY operation
     // that could read device memory (tic() -- i.e. every kernel launch --, d2h, d2d, d2h_async, sync, scans and sorts); the one
     // consumer that knows about chunks, run_simple_chunked, waits chunk by chunk instead and so overlaps with the copies.
-    // Plain h2d does not join: it only writes buffers of its own.
+    // Plain h2d joins only when its destination lies inside a pending table (template uploads and counter resets between
+    // add_input and the range gadget write buffers of their own and must not serialise the pipeline).
     cudaEvent_t get_sync_event() {
         if (!sync_ev_free.empty()) { cudaEvent_t e = sync_ev_free.back(); sync_ev_free.pop_back(); return e; }
         cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); return e;
@@ -132,7 +138,7 @@ public:
             PG_CUDA(cudaMemcpyAsync((char*)dst + lo * elem, (const char*)src + lo * elem, (hi - lo) * elem, cudaMemcpyHostToDevice, in_stream));
             cudaEvent_t ev = get_sync_event();
             PG_CUDA(cudaEventRecord(ev, in_stream));
-            pending.push_back(PendingCopy{dst, lo, hi, ev});
+            pending.push_back(PendingCopy{dst, (const char*)dst + n * elem, lo, hi, ev});
         }
         return true;
     }

@@ -256,6 +256,11 @@ def test_chunked_host_input_equals_device_input(oracle, torch_cuda):
     y = pg.range_check(c, mn, mx, a)
     assert c.check_circuit_satisfied() == (0, None)
     assert (eq.values() == oracle.from_ints([1])[0]).all() and (y.values() == ref_y).all()
+    # a write into a column that is still arriving lands after the copy
+    c.reset()
+    a = c.add_input(pinned)
+    c.poke_variable(5 + n - 2, oracle.from_ints([424242])[0])
+    assert (a.values(n - 2, 1) == oracle.from_ints([424242])).all() and (a.values(n - 1, 1) == pageable[n - 1:]).all()
     c.reset()
     a = c.add_input(pinned); b = c.add_input(pinned)               # both still in flight when range_check(a) starts
     y = pg.range_check(c, mn, mx, a)
