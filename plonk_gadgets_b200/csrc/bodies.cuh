@@ -403,7 +403,12 @@ struct SparseProgBody {
 #pragma unroll
         for (int k = 0; k < 9; k++) t[k] = 0;
         uint32_t mask = ~0u, bad = 0, r = 0;
-        Fr v = fr_zero();
+        // The product register of the multiplication chain lives in local memory (volatile: not promoted): it is touched by the few
+        // operations that multiply, and as a loop-carried register value it cost eight register moves on EVERY operation.
+        volatile uint32_t vmem[8];
+        auto get_v = [&]() { Fr r; for (int k = 0; k < 8; k++) r.v[k] = vmem[k]; return r; };
+        auto set_v = [&](const Fr& r) { for (int k = 0; k < 8; k++) vmem[k] = r.v[k]; };
+        set_v(fr_zero());
 #pragma unroll 1
         for (uint32_t j = 0; j < prog.n; j++) {
             const SpOp op = sp_fetch(prog.ops, j);
@@ -413,28 +418,35 @@ struct SparseProgBody {
                 if (nx.addr) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx.addr + i * nx.stride));
             }
 #endif
-            Fr x = fr_zero(), y = fr_zero();
-            bool mul = false;
-            switch (op.op & 0x7fu) {
-                case SP_ADD_FR: add9_fr(t, ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
-                case SP_SUB_FR: add9_fr(t, fr_neg(ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i))); break;
-                case SP_MASK: mask &= 0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u); break;
-                case SP_BITSEL: {
-                    const uint32_t m = mask & (0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u));
-                    CheckBody::masked_add(t, pool(op.sel), m); mask = ~0u;
-                } break;
-                case SP_MUL_SEL_FR: x = pool(op.sel); y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
-                case SP_LOAD_FR: v = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); break;
-                case SP_MUL_FR: x = v; y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
-                case SP_MULSEL_V: x = pool(op.sel); y = v; mul = true; break;
-                case SP_ADD_V: CheckBody::masked_add(t, op.sh ? fr_neg(v) : v, mask); mask = ~0u; break;
-                case SP_ADD_POOL: add9_fr(t, pool(op.sel)); break;
-                case SP_TRIVIAL: r += op.stride; break;             // `stride` consecutive rows that hold for every witness
-                default: break;                                     // SP_END: nothing to add
-            }
-            if (mul) {                                              // the one multiplier site
-                const Fr p = fr_mul_eo(x, y, q);
-                if ((op.op & 0x7fu) == SP_MUL_SEL_FR) add9_fr(t, p); else v = p;
+            const uint32_t code = op.op & 0x7fu;
+            if (code <= SP_BITSEL) {                                // the operations range rows are made of: no multiplication, `v` untouched
+                switch (code) {
+                    case SP_ADD_FR: add9_fr(t, ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
+                    case SP_SUB_FR: add9_fr(t, fr_neg(ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i))); break;
+                    case SP_MASK: mask &= 0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u); break;
+                    case SP_BITSEL: {
+                        const uint32_t m = mask & (0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u));
+                        CheckBody::masked_add(t, pool(op.sel), m); mask = ~0u;
+                    } break;
+                    default: break;                                 // SP_END: nothing to add
+                }
+            } else {
+                Fr x = fr_zero(), y = fr_zero();
+                bool mul = false;
+                switch (code) {
+                    case SP_MUL_SEL_FR: x = pool(op.sel); y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
+                    case SP_LOAD_FR: set_v(ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
+                    case SP_MUL_FR: x = get_v(); y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
+                    case SP_MULSEL_V: x = pool(op.sel); y = get_v(); mul = true; break;
+                    case SP_ADD_V: { const Fr v = get_v(); CheckBody::masked_add(t, op.sh ? fr_neg(v) : v, mask); mask = ~0u; } break;
+                    case SP_ADD_POOL: add9_fr(t, pool(op.sel)); break;
+                    case SP_TRIVIAL: r += op.stride; break;         // `stride` consecutive rows that hold for every witness
+                    default: break;
+                }
+                if (mul) {                                          // the one multiplier site
+                    const Fr p = fr_mul_eo(x, y, q);
+                    if (code == SP_MUL_SEL_FR) add9_fr(t, p); else set_v(p);
+                }
             }
             if ((op.op & SP_ROW_END) || op.op == SP_END) {          // the row is complete
                 if (!limbs9_is_multiple_of_q(t)) {
