@@ -383,7 +383,13 @@ struct CheckBody {
 // Structure-aware check as a linear program (layout.h, SpOp): the template's rows compiled on the host into the term operations
 // a row needs -- nothing is decided per row on the device, operand addresses are known SP_AHEAD operations ahead (prefetch),
 // and a range_check row costs a handful of adds: the check becomes bound by instruction issue and HBM, not by the multiplier.
-constexpr uint32_t SP_AHEAD = 12;
+#ifndef PG_SP_AHEAD
+#define PG_SP_AHEAD 12
+#endif
+#ifndef PG_SP_PREFETCH
+#define PG_SP_PREFETCH "prefetch.global.L1 [%0];"
+#endif
+constexpr uint32_t SP_AHEAD = PG_SP_AHEAD;
 // one 128-bit load per operation (the 16-byte SpOp, 16-byte aligned in the segment image) instead of one load per field
 PG_HD SpOp sp_fetch(const SpOp* ops, uint32_t j) {
 #if defined(__CUDA_ARCH__)
@@ -415,7 +421,7 @@ struct SparseProgBody {
 #if defined(__CUDA_ARCH__)
             if (j + SP_AHEAD < prog.n) {
                 const SpOp nx = sp_fetch(prog.ops, j + SP_AHEAD);
-                if (nx.addr) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx.addr + i * nx.stride));
+                if (nx.addr) asm volatile(PG_SP_PREFETCH ::"l"(nx.addr + i * nx.stride));
             }
 #endif
             const uint32_t code = op.op & 0x7fu;
