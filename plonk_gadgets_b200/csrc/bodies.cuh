@@ -402,12 +402,18 @@ PG_HD SpOp sp_fetch(const SpOp* ops, uint32_t j) {
     return ops[j];
 #endif
 }
+// A row's accumulator starts at 7q instead of 0, so that "- x" terms are plain 9-limb subtractions (x < q, at most 7 terms per row:
+// five selector terms, q_c, PI) instead of a modular negation and an addition; the row-end test accepts any k*q with k <= 15
+// (7 + at most 7 additions = 14).
+PG_HD void sp_row_init(uint32_t* t) {
+    t[0] = 0x00000007u; t[1] = 0xfffffff9u; t[2] = 0xfff483f8u; t[3] = 0x4a2f7c14u; t[4] = 0x436ce825u;
+    t[5] = 0x6694e838u; t[6] = 0x234e6cf9u; t[7] = 0x2b7f9346u; t[8] = 0x00000003u;
+}
 struct SparseProgBody {
     template <class PoolT>
     PG_HD static uint32_t run(const CheckArgs& a, const SparseProg& prog, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t t[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) t[k] = 0;
+        sp_row_init(t);
         uint32_t mask = ~0u, bad = 0, r = 0;
         // The product register of the multiplication chain lives in local memory (volatile: not promoted): it is touched by the few
         // operations that multiply, and as a loop-carried register value it cost eight register moves on EVERY operation.
@@ -428,7 +434,7 @@ struct SparseProgBody {
             if (code <= SP_BITSEL) {                                // the operations range rows are made of: no multiplication, `v` untouched
                 switch (code) {
                     case SP_ADD_FR: add9_fr(t, ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
-                    case SP_SUB_FR: add9_fr(t, fr_neg(ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i))); break;
+                    case SP_SUB_FR: sub9_fr(t, ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
                     case SP_MASK: mask &= 0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u); break;
                     case SP_BITSEL: {
                         const uint32_t m = mask & (0u - ((reinterpret_cast<const uint32_t*>(op.addr)[i] >> op.sh) & 1u));
@@ -461,8 +467,7 @@ struct SparseProgBody {
                     if (g < first_bad) first_bad = g;
                 }
                 r++; mask = ~0u;
-#pragma unroll
-                for (int k = 0; k < 9; k++) t[k] = 0;
+                sp_row_init(t);
             }
         }
         return bad;

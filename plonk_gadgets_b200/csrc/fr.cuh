@@ -419,6 +419,13 @@ PG_D void add9_fr(uint32_t* r, const Fr& a) {
         : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8])
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
 }
+// r[0..8] -= a[0..7]   (the caller keeps r >= a: SparseProgBody starts every row at 7q)
+PG_D void sub9_fr(uint32_t* r, const Fr& a) {
+    asm("sub.cc.u32 %0, %0, %9;\n\tsubc.cc.u32 %1, %1, %10;\n\tsubc.cc.u32 %2, %2, %11;\n\tsubc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\tsubc.cc.u32 %5, %5, %14;\n\tsubc.cc.u32 %6, %6, %15;\n\tsubc.cc.u32 %7, %7, %16;\n\tsubc.u32 %8, %8, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+}
 #else
 inline void dmad_row_x(uint32_t* X, uint32_t& y7, uint32_t& z, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y) {
     const uint32_t x[4] = {x0, x2, x4, x6};
@@ -464,6 +471,12 @@ inline void add9_fr(uint32_t* r, const Fr& a) {
     for (int i = 0; i < 8; i++) { const uint64_t s = (uint64_t)r[i] + a.v[i] + c; r[i] = (uint32_t)s; c = s >> 32; }
     if ((uint64_t)r[8] + c > 0xffffffffull) PG_EMU_VIOLATION();
     r[8] += (uint32_t)c;
+}
+inline void sub9_fr(uint32_t* r, const Fr& a) {
+    uint64_t bw = 0;
+    for (int i = 0; i < 8; i++) { const uint64_t d = (uint64_t)r[i] - a.v[i] - bw; r[i] = (uint32_t)d; bw = (d >> 32) & 1; }
+    if (r[8] < bw) PG_EMU_VIOLATION();                                   // the accumulator must not go negative
+    r[8] -= (uint32_t)bw;
 }
 #endif
 
