@@ -39,7 +39,8 @@ pub struct pg_cfg {
     pub device: i32,
     pub check_mode: i32,
     pub flags: u32,
-    pub reserved: u32,
+    /// UNSTABLE tuning knob (launch shape of the gate-check kernels); keep 0.
+    pub check_shape: u32,
     pub stream: *mut c_void,
 }
 #[repr(C)]
@@ -52,6 +53,16 @@ pub struct pg_timing {
     pub witness_launches: u64,
     pub other_launches: u64,
     pub check_rows: u64,
+}
+
+pub const PG_NZ_UNIFORM: c_int = 0;
+pub const PG_NZ_REFERENCE: c_int = 1;
+pub const PG_CK_KINDS: usize = 8;
+#[repr(C)]
+#[derive(Default)]
+pub struct pg_check_stats {
+    pub launches: [u64; PG_CK_KINDS],
+    pub rows: [u64; PG_CK_KINDS],
 }
 
 extern "C" {
@@ -70,6 +81,8 @@ extern "C" {
     pub fn pg_maybe_equal_batch(ctx: *mut pg_ctx, a: pg_col, b: pg_col, out: *mut pg_col) -> c_int;
     pub fn pg_is_non_zero_batch(ctx: *mut pg_ctx, var: pg_col, value_assigned: *const pg_fr, on_device: c_int, n_err: *mut u64,
                                 first_err: *mut u64) -> c_int;
+    pub fn pg_is_non_zero_batch_flags(ctx: *mut pg_ctx, var: pg_col, value_assigned: *const pg_fr, on_device: c_int, err_flags: *mut u8,
+                                      layout: c_int, n_err: *mut u64) -> c_int;
     pub fn pg_select_zero_batch(ctx: *mut pg_ctx, x: pg_col, select: pg_col, out: *mut pg_col) -> c_int;
     pub fn pg_select_one_batch(ctx: *mut pg_ctx, y: pg_col, selector: pg_col, out: *mut pg_col) -> c_int;
     pub fn pg_constrain_to_constant_batch(ctx: *mut pg_ctx, a: pg_col, constant: *const pg_fr, n_const: u64, pi: *const pg_fr,
@@ -107,6 +120,7 @@ extern "C" {
                             first_invalid: *mut u64) -> c_int;
     pub fn pg_synth(ctx: *mut pg_ctx, seed: u64, stream: u64, n: u64, kind: c_int, bits: u32, dst_device: *mut pg_fr) -> c_int;
     pub fn pg_get_timing(ctx: *mut pg_ctx, out: *mut pg_timing, reset: c_int) -> c_int;
+    pub fn pg_get_check_stats(ctx: *mut pg_ctx, out: *mut pg_check_stats, reset: c_int) -> c_int;
     pub fn pg_measure_imad_peak(ctx: *mut pg_ctx, wide_mac_per_s: *mut f64, imad_per_s: *mut f64) -> c_int;
     pub fn pg_microbench(ctx: *mut pg_ctx, mode: c_int, ops_per_s: *mut f64) -> c_int;
     pub fn pg_fr_op(ctx: *mut pg_ctx, op: c_int, n: u64, a: *const pg_fr, b: *const pg_fr, out: *mut pg_fr) -> c_int;

@@ -19,6 +19,14 @@ pub struct EngineError {
     pub detail: String,
 }
 
+/// `Error::NonExistingInverse` of a batched `is_non_zero`, with what a batch adds: how many instances failed, and the first.
+#[derive(Debug)]
+pub struct NonZeroBatchError {
+    pub error: Error,
+    pub n_err: u64,
+    pub first_err: u64,
+}
+
 /// n `Variable`s, one per gadget instance of the call that produced them.
 #[derive(Copy, Clone, Debug)]
 pub struct Variables {
@@ -38,7 +46,7 @@ fn as_fr(s: &[BlsScalar]) -> *const sys::pg_fr {
 
 impl BatchComposer {
     pub fn new(device: i32) -> Result<Self, EngineError> {
-        let cfg = sys::pg_cfg { device, check_mode: sys::PG_CHECK_GENERIC, flags: 0, reserved: 0, stream: ptr::null_mut() };
+        let cfg = sys::pg_cfg { device, check_mode: sys::PG_CHECK_GENERIC, flags: 0, check_shape: 0, stream: ptr::null_mut() };
         let mut ctx = ptr::null_mut();
         let rc = unsafe { sys::pg_ctx_create(&cfg, &mut ctx) };
         if rc != sys::PG_OK {
@@ -67,6 +75,14 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_range_check_batch(self.ctx, as_fr(&[min_range]), as_fr(&[max_range]), 1, 0, witness.col, &mut col, &mut k) })?;
         Ok(Variables { col, n: witness.n })
     }
+    /// `range_check` with one `(min_range, max_range)` pair per instance; all pairs must give the same `num_bits`
+    /// (`EngineError { code: PG_ERR_MIXED_BITS, .. }` otherwise, nothing appended).
+    pub fn range_check_batch_per_instance(&mut self, min_range: &[BlsScalar], max_range: &[BlsScalar], witness: Variables) -> Result<(Variables, u64), EngineError> {
+        assert!(min_range.len() as u64 == witness.n && max_range.len() as u64 == witness.n);
+        let (mut col, mut k) = (0, 0);
+        self.ok(unsafe { sys::pg_range_check_batch(self.ctx, as_fr(min_range), as_fr(max_range), witness.n, 0, witness.col, &mut col, &mut k) })?;
+        Ok((Variables { col, n: witness.n }, k))
+    }
     /// `max_bound(composer, max_range, witness) -> (Variable, u64)`.
     pub fn max_bound_batch(&mut self, max_range: BlsScalar, witness: Variables) -> Result<(Variables, u64), EngineError> {
         let (mut col, mut k) = (0, 0);
@@ -78,11 +94,23 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_maybe_equal_batch(self.ctx, a.col, b.col, &mut col) })?;
         Ok(Variables { col, n: a.n })
     }
-    /// `for i { is_non_zero(composer, var_i, value_assigned_i)?; }` -- `Ok(Err(NonExistingInverse))` mirrors the gadget error.
-    pub fn is_non_zero_batch(&mut self, var: Variables, value_assigned: &[BlsScalar]) -> Result<Result<(), Error>, EngineError> {
-        let (mut n_err, mut first) = (0, 0);
-        let rc = self.ok(unsafe { sys::pg_is_non_zero_batch(self.ctx, var.col, as_fr(value_assigned), 0, &mut n_err, &mut first) })?;
-        Ok(if rc == sys::PG_ERR_NON_EXISTING_INVERSE { Err(Error::NonExistingInverse) } else { Ok(()) })
+    /// `for i { is_non_zero(composer, var_i, value_assigned_i)?; }` -- `Ok(Err(..))` mirrors the gadget error of the first zero
+    /// `value_assigned` (the composer then holds what that loop leaves behind); the error carries how many instances of the batch
+    /// have a zero `value_assigned` and the index of the first one.
+    pub fn is_non_zero_batch(&mut self, var: Variables, value_assigned: &[BlsScalar]) -> Result<Result<(), NonZeroBatchError>, EngineError> {
+        let (mut n_err, mut first_err) = (0, 0);
+        let rc = self.ok(unsafe { sys::pg_is_non_zero_batch(self.ctx, var.col, as_fr(value_assigned), 0, &mut n_err, &mut first_err) })?;
+        Ok(if rc == sys::PG_ERR_NON_EXISTING_INVERSE { Err(NonZeroBatchError { error: Error::NonExistingInverse, n_err, first_err }) } else { Ok(()) })
+    }
+    /// `value_assigned.iter().map(|v| is_non_zero(composer, var_i, *v))` with every `Result` kept: the batch does not stop at a
+    /// zero.  `reference_layout`: errored calls leave the 1 variable + 1 row the reference appends before returning `Err`
+    /// (ragged numbering); otherwise every instance appends 3 variables + 3 rows and an errored one fails its last row.
+    pub fn is_non_zero_each(&mut self, var: Variables, value_assigned: &[BlsScalar], reference_layout: bool) -> Result<Vec<Result<(), Error>>, EngineError> {
+        let mut flags = vec![0u8; value_assigned.len()];
+        let mut n_err = 0;
+        let layout = if reference_layout { sys::PG_NZ_REFERENCE } else { sys::PG_NZ_UNIFORM };
+        self.ok(unsafe { sys::pg_is_non_zero_batch_flags(self.ctx, var.col, as_fr(value_assigned), 0, flags.as_mut_ptr(), layout, &mut n_err) })?;
+        Ok(flags.iter().map(|&f| if f != 0 { Err(Error::NonExistingInverse) } else { Ok(()) }).collect())
     }
     pub fn conditionally_select_zero_batch(&mut self, x: Variables, select: Variables) -> Result<Variables, EngineError> {
         let mut col = 0;

@@ -7,7 +7,9 @@
  * and the Python (ctypes) mirror used by the tests in plonk_gadgets_b200/api.py.
  *
  * The reference has no FFI of its own: its "operator interface" is the crate's public Rust functions, all of which take
- * `composer: &mut StandardComposer` first.  Each entry point below cites the reference function it replaces.
+ * `composer: &mut StandardComposer` first.  Each entry point below cites the reference function it replaces; `ref:` is a path
+ * inside the dusk-network/plonk_gadgets v0.6.0 source tree (ref:src/range.rs:27 = src/range.rs line 27 of that crate), [dusk-plonk]
+ * marks behaviour of its dusk-plonk 0.8 dependency.
  *
  * Model.  A pg_ctx owns ONE device-resident composer (dusk-plonk StandardComposer, arithmetic-row subset) on one GPU.
  * Every *_batch call appends n independent gadget instances and is defined to be EQUAL to the sequential program
@@ -19,7 +21,15 @@
  * the reference's own representation (`Vec<BlsScalar>` columns, `Vec<Variable>` wires).
  *
  * Scalars cross the boundary as pg_fr: the raw in-memory form of `BlsScalar([u64;4])` (little-endian limbs of
- * a*2^256 mod q, fully reduced).  Inputs must be fully reduced (< q); this is not checked.
+ * a*2^256 mod q, fully reduced).  Inputs must be fully reduced (< q), as every BlsScalar is.  Single scalars (uniform bounds,
+ * constants, pg_poke_variable) are checked on the host: PG_ERR_ARG.  Batches are checked on the device by the kernel that ingests
+ * them, without a synchronisation: an unreduced scalar is counted, and the next call that reads the device counters -- pg_check,
+ * pg_sync, pg_is_non_zero_batch*, a range gadget with per-instance bounds, pg_fr_from_bytes, pg_check_rows* -- returns PG_ERR_ARG
+ * (pg_last_error names the count and the first index).  The composer then holds values the reference type cannot represent:
+ * reset it.
+ *
+ * A mixed circuit is a sequence of *_batch calls on one ctx (each call one "op" of n instances): there is no separate
+ * pg_circuit_run(op list) entry point, the composer model is that list.  pg_shard_plan splits such a list over GPUs.
  *
  * Threading: a pg_ctx is not thread-safe (the reference API is `&mut`).  All work is enqueued on the ctx's CUDA
  * stream; calls that return host values synchronise that stream.  There is no CPU fallback: every entry point fails
@@ -35,9 +45,9 @@
 extern "C" {
 #endif
 
-#define PG_B200_ABI_VERSION 1
+#define PG_B200_ABI_VERSION 2
 
-/* BlsScalar: /root/reference/src/allocated_scalar.rs:9-12 (dusk_plonk::bls12_381::BlsScalar) */
+/* BlsScalar: ref:src/allocated_scalar.rs:9-12 (dusk_plonk::bls12_381::BlsScalar) */
 typedef struct pg_fr { uint64_t l[4]; } pg_fr;
 
 typedef struct pg_ctx pg_ctx;
@@ -46,11 +56,11 @@ typedef struct pg_ctx pg_ctx;
  * 0 is never a valid column. */
 typedef uint64_t pg_col;
 
-/* Return codes.  > 0 : gadget-level errors of the reference (/root/reference/src/errors.rs:13-18).
+/* Return codes.  > 0 : gadget-level errors of the reference (ref:src/errors.rs:13-18).
  *                < 0 : engine errors (never a silent fallback). */
 enum {
     PG_OK = 0,
-    PG_ERR_NON_EXISTING_INVERSE = 1, /* Error::NonExistingInverse, /root/reference/src/scalar.rs:79 */
+    PG_ERR_NON_EXISTING_INVERSE = 1, /* Error::NonExistingInverse, ref:src/scalar.rs:79 */
     PG_ERR_CUDA = -1,                /* a CUDA call failed; pg_last_error() has the driver's message */
     PG_ERR_ARG = -2,                 /* bad argument (null pointer, unknown column, length mismatch, ...) */
     PG_ERR_OOM = -3,                 /* device allocation failed */
@@ -63,7 +73,12 @@ enum {
  *   GENERIC : q_m*a*b + q_l*a + q_r*b + q_o*c + q_4*d + q_c + PI for arbitrary selector values, no selector inspected (what
  *             dusk-plonk's check_circuit_satisfied / quotient evaluation do); evaluated as a*(q_m*b + q_l) + q_r*b + q_o*c +
  *             q_4*d with one Montgomery multiplication and one four-term dot product sharing a single reduction.
- *   SPARSE  : skips products whose selector is the constant 0 and replaces products by +-1 with add/sub. */
+ *   SPARSE  : structure-aware.  Decisions are taken on the row TEMPLATE (never on witness data): a term whose selector is the
+ *             constant 0, or whose wire is the zero variable, is skipped (the wire is not loaded); selectors +-1 become add / sub;
+ *             a wire that is one of the 256 packed bit variables of a decomposition is read as the bit the table stores for it,
+ *             i.e. it is boolean by construction (b*b = b: the boolean_gate rows of ref:src/range.rs:144 fold to "holds").  Those
+ *             variables cannot be overwritten through pg_poke_variable, so the assumption cannot be violated from outside.
+ *             Same verdict as GENERIC on every composer state this API can produce. */
 enum { PG_CHECK_GENERIC = 0, PG_CHECK_SPARSE = 1 };
 
 enum {
@@ -74,7 +89,8 @@ typedef struct pg_cfg {
     int32_t device;         /* CUDA ordinal */
     int32_t check_mode;     /* PG_CHECK_* */
     uint32_t flags;         /* PG_F_* */
-    uint32_t reserved;      /* tuning knob: launch shape of the gate-check kernel (0 = default; 1..4 = alternatives, see kernels.cuh CheckShape) */
+    uint32_t check_shape;   /* UNSTABLE tuning knob, keep 0: launch shape of the gate-check kernels (1..4 = alternatives, kernels.cuh CheckShape);
+                               never changes results */
     void *stream;           /* cudaStream_t to enqueue on; NULL = the engine creates its own non-blocking stream */
 } pg_cfg;
 
@@ -97,26 +113,26 @@ int pg_sync(pg_ctx *ctx);
  * host batches of 2^20 scalars or more in chunks on a separate input stream, and a range gadget called on that column next starts on
  * the chunks that have arrived; every other operation waits for the whole copy first. */
 
-/* AllocatedScalar::allocate / composer.add_input over n scalars -- /root/reference/src/allocated_scalar.rs:27-30.
+/* AllocatedScalar::allocate / composer.add_input over n scalars -- ref:src/allocated_scalar.rs:27-30.
  * Appends n variables, no rows. */
 int pg_add_input_batch(pg_ctx *ctx, uint64_t n, const pg_fr *values, int on_device, pg_col *out);
 
-/* range_check(composer, min_range, max_range, witness) -- /root/reference/src/range.rs:27-43.
+/* range_check(composer, min_range, max_range, witness) -- ref:src/range.rs:27-43.
  * n_bounds == 1: one public (min,max) pair for all instances; n_bounds == n: per-instance bounds, which must all give the
  * same num_bits (else PG_ERR_MIXED_BITS and nothing is appended).  Per instance 4k+11 rows, 2k+523 variables.
  * *out: the returned Variable (value 1 iff min <= x < max within k bits); *num_bits: k (may be NULL). */
 int pg_range_check_batch(pg_ctx *ctx, const pg_fr *min_range, const pg_fr *max_range, uint64_t n_bounds, int on_device,
                          pg_col witness, pg_col *out, uint64_t *num_bits);
 
-/* max_bound(composer, max_range, witness) -> (Variable, u64) -- /root/reference/src/range.rs:82-113.  2k+5 rows, k+261 vars. */
+/* max_bound(composer, max_range, witness) -> (Variable, u64) -- ref:src/range.rs:82-113.  2k+5 rows, k+261 vars. */
 int pg_max_bound_batch(pg_ctx *ctx, const pg_fr *max_range, uint64_t n_bounds, int on_device, pg_col witness,
                        pg_col *out, uint64_t *num_bits);
 
-/* maybe_equal(composer, a, b) -- /root/reference/src/scalar.rs:105-140.  3 rows, 3 variables; *out = 1 iff a == b.
+/* maybe_equal(composer, a, b) -- ref:src/scalar.rs:105-140.  3 rows, 3 variables; *out = 1 iff a == b.
  * (The AllocatedScalar's host-side `scalar` is the column's own value.) */
 int pg_maybe_equal_batch(pg_ctx *ctx, pg_col a, pg_col b, pg_col *out);
 
-/* for i { is_non_zero(composer, var_i, value_assigned_i)?; } -- /root/reference/src/scalar.rs:63-97.
+/* for i { is_non_zero(composer, var_i, value_assigned_i)?; } -- ref:src/scalar.rs:63-97.
  * 3 rows, 3 variables per instance.  If some value_assigned is zero the call returns PG_ERR_NON_EXISTING_INVERSE and the
  * composer holds what the reference loop leaves behind: the instances before the first zero complete, plus the
  * 1 variable + 1 row the failing call had already appended (scalar.rs:69-71).  *n_err = number of zero values in the
@@ -124,19 +140,33 @@ int pg_maybe_equal_batch(pg_ctx *ctx, pg_col a, pg_col b, pg_col *out);
 int pg_is_non_zero_batch(pg_ctx *ctx, pg_col var, const pg_fr *value_assigned, int on_device, uint64_t *n_err,
                          uint64_t *first_err);
 
-/* conditionally_select_zero(composer, x, select) -- /root/reference/src/scalar.rs:21-27.  1 row, 1 variable. */
+/* for i { results[i] = is_non_zero(composer, var_i, value_assigned_i); } -- ref:src/scalar.rs:63-97 with every Result KEPT instead of
+ * propagated with `?`: a batch does not abort on one zero (ref:src/errors.rs:13-18).  err_flags (n bytes, host or device memory like
+ * value_assigned; may be NULL): 1 where the call returned Err(NonExistingInverse), else 0; *n_err = their number.  Returns PG_OK.
+ *   PG_NZ_UNIFORM  : every instance appends the full 3 variables + 3 rows (Variable numbering stays first + 3*i).  For an errored
+ *                    instance: var_assigned = 0, inv = 0 (invert().unwrap_or(zero), the convention of ref:src/scalar.rs:122), one = 1;
+ *                    its row var*inv - 1 = 0 is unsatisfied, so pg_check reports it too.  One segment, one kernel launch.  This is NOT
+ *                    what the reference appends for an errored call; it is the layout for throughput (BASELINE config C4).
+ *   PG_NZ_REFERENCE: the composer that loop leaves behind, bit for bit: an errored call has appended var_assigned and the assert_equal
+ *                    row only (1 variable + 1 row, ref:src/scalar.rs:69-71 before the return at :79), so numbering is ragged.  The
+ *                    device table is described as 2*n_err + 1 segment views; cost grows with n_err (at most 2^19 errors). */
+enum { PG_NZ_UNIFORM = 0, PG_NZ_REFERENCE = 1 };
+int pg_is_non_zero_batch_flags(pg_ctx *ctx, pg_col var, const pg_fr *value_assigned, int on_device, uint8_t *err_flags, int layout,
+                               uint64_t *n_err);
+
+/* conditionally_select_zero(composer, x, select) -- ref:src/scalar.rs:21-27.  1 row, 1 variable. */
 int pg_select_zero_batch(pg_ctx *ctx, pg_col x, pg_col select, pg_col *out);
-/* conditionally_select_one(composer, y, selector) -- /root/reference/src/scalar.rs:36-59.  4 rows, 4 variables. */
+/* conditionally_select_one(composer, y, selector) -- ref:src/scalar.rs:36-59.  4 rows, 4 variables. */
 int pg_select_one_batch(pg_ctx *ctx, pg_col y, pg_col selector, pg_col *out);
 
 /* composer.constrain_to_constant(a, constant, pi) [dusk-plonk] as used by the reference's tests
- * (/root/reference/tests/range_gadgets_tests.rs:26,:43; tests/scalar_gadgets_tests.rs:30,:78,:135).  1 row, no variable.
+ * (ref:tests/range_gadgets_tests.rs:26,:43; tests/scalar_gadgets_tests.rs:30,:78,:135).  1 row, no variable.
  * n_const / n_pi: 1 (uniform) or n; pi == NULL: no public input. */
 int pg_constrain_to_constant_batch(pg_ctx *ctx, pg_col a, const pg_fr *constant, uint64_t n_const, const pg_fr *pi,
                                    uint64_t n_pi, int on_device);
 
 /* for i { composer.range_gate(witness_i, num_bits); } -- StandardComposer::range_gate [dusk-plonk 0.8 src/constraint_system/range.rs],
- * the native quad-accumulator range gate that /root/reference/src/range.rs:9-12 recommends over range_check when the bound is a
+ * the native quad-accumulator range gate that ref:src/range.rs:9-12 recommends over range_check when the bound is a
  * power of two.  Per instance: num_bits/2 accumulator variables a_j = 4*a_{j-1} + quad_j (base-4
  * digits of the witness, most significant first) laid out four per gate on w_4, w_o, w_r, w_l after 1..4 leading zero wires;
  * ceil(num_bits/8) gates with q_range = 1 (all arithmetic selectors and q_arith 0), one closing gate with q_range = 0, and
@@ -190,7 +220,7 @@ int pg_permutation(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *sigma, in
 
 /* ---- evaluation domain (first half) -------------------------------------------------------------
  * The step that follows the gadget hot path inside Prover::prove [DEP dusk-plonk 0.8, reached from
- * /root/reference/tests/range_gadgets_tests.rs:90-91 and tests/scalar_gadgets_tests.rs (prover.prove)]:
+ * ref:tests/range_gadgets_tests.rs:90-91 and tests/scalar_gadgets_tests.rs (prover.prove)]:
  *     let w_l_scalar = &[&self.to_scalars(&self.cs.w_l)[..], &pad].concat();       // pad = zeros up to domain.size()
  *     let w_l_poly = Polynomial::from_coefficients_vec(domain.ifft(w_l_scalar));   // same for w_r, w_o, w_4
  * pg_fft is EvaluationDomain::fft (inverse == 0) / ifft (inverse != 0) [DEP src/fft/domain.rs] of a vector of 2^log_n
@@ -199,14 +229,14 @@ int pg_permutation(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *sigma, in
  * the same buffer.
  * pg_wire_polynomials writes the coefficient vectors of w_l, w_r, w_o, w_4 (4 x 2^log_n scalars, column-major) for the
  * composer's current rows; 2^log_n must be >= the circuit size (EvaluationDomain::new(circuit_size) takes the next power of
- * two: pass ceil(log2(n_rows)) for the reference's domain).  Commitments (MSM) are out of scope. */
+ * two: pass ceil(log2(n_rows)) for the reference's domain).  Their commitments: next section. */
 int pg_fft(pg_ctx *ctx, uint32_t log_n, int inverse, const pg_fr *src, pg_fr *dst, int on_device);
 int pg_wire_polynomials(pg_ctx *ctx, uint32_t log_n, pg_fr *dst, int dst_on_device);
 
 /* ---- commitments (second half) -----------------------------------------------------------------
  * KZG commitments of coefficient vectors in the BLS12-381 group G1 [DEP dusk-plonk 0.8 CommitKey::commit =
  * dusk-bls12_381 msm_variable_base(&powers_of_g, &poly.coeffs); Prover::prove computes w_l_poly_commit .. w_4_poly_commit right
- * after the wire polynomials; reached from /root/reference/tests/range_gadgets_tests.rs:90-91].
+ * after the wire polynomials; reached from ref:tests/range_gadgets_tests.rs:90-91].
  * pg_g1_affine = the in-memory G1Affine { x: Fp, y: Fp } of dusk-bls12_381 (Fp([u64; 6]), Montgomery form, R = 2^384) without
  * its `infinity` flag byte: the point at infinity is the all-zero pair.
  * pg_msm: out = sum_i scalars[i] * points[i] (one point, written to HOST memory); points/scalars both host or both device.
@@ -235,7 +265,7 @@ int pg_commit_wire_evaluations(pg_ctx *ctx, uint32_t log_n, const pg_g1_affine *
 int pg_g1_op(pg_ctx *ctx, int op, uint64_t n, const pg_g1_affine *a, const pg_g1_affine *b, pg_g1_affine *out);
 
 /* ---- wire format -------------------------------------------------------------------------
- * BlsScalar::to_bytes / from_bytes [dusk_bytes::Serializable<32>, called at /root/reference/src/range.rs:163]: the canonical
+ * BlsScalar::to_bytes / from_bytes [dusk_bytes::Serializable<32>, called at ref:src/range.rs:163]: the canonical
  * little-endian 32-byte encoding used for witness / selector / public-input dumps exchanged with Rust tooling.  n scalars;
  * src and dst are both host (on_device == 0; dst may be unaligned-safe only for host) or both device pointers.
  * from_bytes rejects encodings >= q like the reference: they are counted in *n_invalid (first index in *first_invalid, or
@@ -264,6 +294,14 @@ typedef struct pg_timing {
     uint64_t check_rows;    /* rows evaluated by the gate-check kernels */
 } pg_timing;
 int pg_get_timing(pg_ctx *ctx, pg_timing *out, int reset);   /* needs PG_F_TIMING; synchronises */
+
+/* Which kernel evaluated how many rows since the last reset (counted at launch, no synchronisation).  Kinds:
+ * one thread per instance -- generic equation (k_check), per-row structure-aware terms, compiled structure-aware row program
+ * (k_check_prog); one thread per (instance, row) for segments too small to fill the chip (k_check_rowpar); segments with
+ * range-widget rows (k_check_gates); rows evaluated inside witness generation (PG_F_FUSED_CHECK). */
+enum { PG_CK_INSTANCE_GENERIC = 0, PG_CK_INSTANCE_TERMS = 1, PG_CK_PROGRAM = 2, PG_CK_ROWPAR = 3, PG_CK_GATES = 4, PG_CK_FUSED = 5, PG_CK_KINDS = 8 };
+typedef struct pg_check_stats { uint64_t launches[PG_CK_KINDS]; uint64_t rows[PG_CK_KINDS]; } pg_check_stats;
+int pg_get_check_stats(pg_ctx *ctx, pg_check_stats *out, int reset);
 
 /* Integer-multiply roofline denominators measured on this GPU: 32x32+64->64 multiply-accumulates per second with
  * IMAD.WIDE.U32 chains, and 32-bit IMAD (lo) per second. */

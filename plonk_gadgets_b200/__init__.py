@@ -4,9 +4,9 @@ Only what the path needs: csrc/ (CUDA kernels + C ABI, built into libpg_b200.so)
 API over the C ABI) and this Python mirror used by the tests and the benchmark.  Importing the package does not load the
 CUDA library; creating a StandardComposer does, and fails loudly when it (or a B200) is missing -- there is no CPU path.
 """
-from .api import (AllocatedScalar, CHECK_GENERIC, CHECK_SPARSE, DevicePtr, EngineError, Error, NonExistingInverse,  # noqa: F401
-                  StandardComposer, Variables, conditionally_select_one, conditionally_select_zero, is_non_zero,
-                  max_bound, maybe_equal, range_check)
+from .api import (AllocatedScalar, CHECK_GENERIC, CHECK_SPARSE, DevicePtr, EngineError, Error, NZ_REFERENCE, NZ_UNIFORM,  # noqa: F401
+                  NonExistingInverse, StandardComposer, Variables, conditionally_select_one, conditionally_select_zero,
+                  is_non_zero, is_non_zero_flags, max_bound, maybe_equal, range_check)
 from . import _lib  # noqa: F401
 
 
@@ -19,4 +19,5 @@ class ScalarGadgets:     # /root/reference/src/lib.rs:45
     conditionally_select_zero = staticmethod(conditionally_select_zero)
     conditionally_select_one = staticmethod(conditionally_select_one)
     is_non_zero = staticmethod(is_non_zero)
+    is_non_zero_flags = staticmethod(is_non_zero_flags)
     maybe_equal = staticmethod(maybe_equal)

@@ -24,7 +24,7 @@ class pg_fr(C.Structure):
 
 
 class pg_cfg(C.Structure):
-    _fields_ = [("device", C.c_int32), ("check_mode", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("device", C.c_int32), ("check_mode", C.c_int32), ("flags", C.c_uint32), ("check_shape", C.c_uint32),
                 ("stream", C.c_void_p)]
 
 
@@ -33,6 +33,12 @@ class pg_timing(C.Structure):
                 ("check_launches", C.c_uint64), ("witness_launches", C.c_uint64), ("other_launches", C.c_uint64),
                 ("check_rows", C.c_uint64)]
 
+
+class pg_check_stats(C.Structure):
+    _fields_ = [("launches", C.c_uint64 * 8), ("rows", C.c_uint64 * 8)]
+
+
+ABI_VERSION = 2
 
 # every symbol include/pg_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _i32, _u32 = C.c_void_p, C.c_uint64, C.c_int, C.c_uint32
@@ -50,6 +56,7 @@ SIGNATURES = {
     "pg_max_bound_batch": (_i32, [_vp, _vp, _u64, _i32, _u64, _pu64, _pu64]),
     "pg_maybe_equal_batch": (_i32, [_vp, _u64, _u64, _pu64]),
     "pg_is_non_zero_batch": (_i32, [_vp, _u64, _vp, _i32, _pu64, _pu64]),
+    "pg_is_non_zero_batch_flags": (_i32, [_vp, _u64, _vp, _i32, _vp, _i32, _pu64]),
     "pg_select_zero_batch": (_i32, [_vp, _u64, _u64, _pu64]),
     "pg_select_one_batch": (_i32, [_vp, _u64, _u64, _pu64]),
     "pg_constrain_to_constant_batch": (_i32, [_vp, _u64, _vp, _u64, _vp, _u64, _i32]),
@@ -78,6 +85,7 @@ SIGNATURES = {
     "pg_fr_from_bytes": (_i32, [_vp, _u64, _vp, _vp, _i32, _pu64, _pu64]),
     "pg_synth": (_i32, [_vp, _u64, _u64, _u64, _i32, _u32, _vp]),
     "pg_get_timing": (_i32, [_vp, C.POINTER(pg_timing), _i32]),
+    "pg_get_check_stats": (_i32, [_vp, C.POINTER(pg_check_stats), _i32]),
     "pg_measure_imad_peak": (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pg_microbench": (_i32, [_vp, _i32, C.POINTER(C.c_double)]),
     "pg_fr_op": (_i32, [_vp, _i32, _u64, _vp, _vp, _vp]),
@@ -120,6 +128,6 @@ def load():
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(plonk_gadgets_b200 has no CPU fallback)")
         _cdll = bind(C.CDLL(LIB_PATH))
-        if _cdll.pg_abi_version() != 1:
+        if _cdll.pg_abi_version() != ABI_VERSION:
             raise RuntimeError("libpg_b200.so ABI version mismatch")
     return _cdll

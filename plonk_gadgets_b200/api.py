@@ -112,7 +112,7 @@ class StandardComposer:
 
     def __init__(self, device: int = 0, check_mode: int = CHECK_GENERIC, timing: bool = False, stream: int | None = None, check_shape: int = 0, _cdll=None):
         self._L = _cdll if _cdll is not None else _lib.load()
-        cfg = _lib.pg_cfg(device=device, check_mode=check_mode, flags=F_TIMING if timing else 0, reserved=check_shape, stream=stream)
+        cfg = _lib.pg_cfg(device=device, check_mode=check_mode, flags=F_TIMING if timing else 0, check_shape=check_shape, stream=stream)
         ctx = C.c_void_p()
         rc = self._L.pg_ctx_create(C.byref(cfg), C.byref(ctx))
         if rc != 0:
@@ -406,6 +406,14 @@ class StandardComposer:
         self._ok(self._L.pg_get_timing(self._ctx, C.byref(t), int(reset)), "pg_get_timing")
         return {k: getattr(t, k) for k, _ in _lib.pg_timing._fields_}
 
+    CHECK_KINDS = ("instance_generic", "instance_terms", "program", "rowpar", "gates", "fused")
+
+    def check_stats(self, reset: bool = True) -> dict:
+        """{kind: (launches, rows)} of the gate-check kernels since the last reset (pg_get_check_stats)."""
+        st = _lib.pg_check_stats()
+        self._ok(self._L.pg_get_check_stats(self._ctx, C.byref(st), int(reset)), "pg_get_check_stats")
+        return {k: (int(st.launches[i]), int(st.rows[i])) for i, k in enumerate(self.CHECK_KINDS)}
+
     def measure_imad_peak(self):
         w, l = C.c_double(), C.c_double()
         self._ok(self._L.pg_measure_imad_peak(self._ctx, C.byref(w), C.byref(l)), "pg_measure_imad_peak")
@@ -480,6 +488,30 @@ def is_non_zero(composer: StandardComposer, var: Variables, value_assigned) -> N
     rc = composer._ok(composer._L.pg_is_non_zero_batch(composer._ctx, _var(var).col, p, dev, C.byref(n_err), C.byref(first)), "pg_is_non_zero_batch")
     if rc == 1:
         raise NonExistingInverse(n_err.value, first.value)
+
+
+NZ_UNIFORM, NZ_REFERENCE = 0, 1
+
+
+def is_non_zero_flags(composer: StandardComposer, var: Variables, value_assigned, layout: int = NZ_UNIFORM, flags_out=None) -> np.ndarray:
+    """``[is_non_zero(composer, var_i, value_assigned_i).is_err() for i in range(n)]`` -- /root/reference/src/scalar.rs:63-97 with
+    every Result kept: the batch does not stop at a zero.  Returns the (n,) uint8 error flags (or fills the CUDA tensor `flags_out`
+    when value_assigned lives on the device).  layout NZ_UNIFORM: 3 variables + 3 rows for every instance (errored ones hold
+    inv = 0 and fail their last row); NZ_REFERENCE: errored instances leave 1 variable + 1 row like the reference call does."""
+    p, dev, n, keep = _scalars(value_assigned)
+    if n != _var(var).n:
+        raise ValueError("value_assigned must have one scalar per variable")
+    composer._keep.append(keep)
+    n_err = C.c_uint64()
+    if dev:
+        fp = C.c_void_p(flags_out.data_ptr()) if flags_out is not None else None
+        flags = flags_out
+    else:
+        flags = np.zeros(n, dtype=np.uint8)
+        fp = flags.ctypes.data_as(C.c_void_p)
+    composer._ok(composer._L.pg_is_non_zero_batch_flags(composer._ctx, _var(var).col, p, dev, fp, int(layout), C.byref(n_err)), "pg_is_non_zero_batch_flags")
+    composer.last_n_err = n_err.value
+    return flags
 
 
 def maybe_equal(composer: StandardComposer, a, b) -> Variables:

@@ -31,7 +31,11 @@ PG_HD const Fr& pow2_entry(uint32_t i) {
 }
 
 // counters shared by all kernels of a ctx (device memory, 8 x u64)
-enum { CNT_UNSAT = 0, CNT_FIRST_BAD = 1, CNT_MIXED_BITS = 2, CNT_N_ERR = 3, CNT_FIRST_ERR = 4, CNT_WORDS = 8 };
+// words 0..CNT_STICKY-1 are re-initialised before every use (Engine::reset_counters); CNT_BAD_INPUT / CNT_FIRST_BAD_INPUT are
+// sticky until the composer is reset: every kernel that ingests caller scalars counts the ones that are not fully reduced (>= q)
+// there, and the next call that reads the counters reports PG_ERR_ARG (include/pg_b200.h, "Scalars").
+enum { CNT_UNSAT = 0, CNT_FIRST_BAD = 1, CNT_MIXED_BITS = 2, CNT_N_ERR = 3, CNT_FIRST_ERR = 4, CNT_STICKY = 5,
+       CNT_BAD_INPUT = 5, CNT_FIRST_BAD_INPUT = 6, CNT_WORDS = 8 };
 
 PG_HD void counter_add(unsigned long long* c, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
@@ -46,6 +50,18 @@ PG_HD void counter_min(unsigned long long* c, unsigned long long v) {
 #else
     if (v < *c) *c = v;
 #endif
+}
+
+// ingest check: a caller scalar must be the fully reduced Montgomery form (< q) -- dusk-bls12_381's Scalar always is.  An
+// unreduced value would break invariants the kernels rely on (a table value equal to q is "non-zero" with a zero Montgomery
+// product; the structure-aware check's 7q headroom), so it is counted here and reported as PG_ERR_ARG by the engine.
+PG_HD bool fr_is_reduced(const Fr& a) {
+    const uint32_t q[8] = {PG_Q0, PG_Q1, PG_Q2, PG_Q3, PG_Q4, PG_Q5, PG_Q6, PG_Q7};
+    uint32_t d[8];
+    return fr_sub_limbs(d, a.v, q) != 0;              // a - q borrows  <=>  a < q
+}
+PG_HD void count_unreduced(unsigned long long* counters, const Fr& a, uint64_t index) {
+    if (!fr_is_reduced(a)) { counter_add(counters + CNT_BAD_INPUT, 1ull); counter_min(counters + CNT_FIRST_BAD_INPUT, (unsigned long long)index); }
 }
 
 // bit length of a canonical (non-Montgomery) 256-bit integer
@@ -76,6 +92,12 @@ PG_HD uint32_t num_bits_from_canonical(const Fr& c) {
 struct AddInputBody {
     struct Args { const uint4* src; uint4* fr; uint64_t stride; uint64_t n; };
     PG_HD static void run(const Args& a, uint64_t i) { tab_store_fr(a.fr, a.stride, 0, i, aos_load(a.src, i)); }
+};
+
+// scalars [i0, i0 + n) of a caller batch (already in device memory) are fully reduced, or counted as bad input
+struct ValidateBody {
+    struct Args { const uint4* src; uint64_t i0; uint64_t n; unsigned long long* counters; };
+    PG_HD static void run(const Args& a, uint64_t i) { count_unreduced(a.counters, aos_load(a.src, a.i0 + i), a.i0 + i); }
 };
 
 // ---------------------------------------------------------------------------------------------------- range gadgets
@@ -121,11 +143,15 @@ struct RangePre {
         const Fr x = loc_load(&a.x_tab, a.x_loc, i);
         Fr m = a.m, negmin = a.negmin;
         if (!a.uniform) {
-            m = fr_sub(aos_load(a.max_aos, i), fr_one());                      // max_range - one, range.rs:87
+            const Fr mx = aos_load(a.max_aos, i);
+            count_unreduced(a.counters, mx, i);
+            m = fr_sub(mx, fr_one());                                          // max_range - one, range.rs:87
             tab_store_fr(a.param, a.stride, a.param_m, i, m);
             if (num_bits_from_canonical(fr_from_mont(m)) != a.k) counter_add(a.counters + CNT_MIXED_BITS, 1ull);
             if (RANGE) {
-                negmin = fr_neg(aos_load(a.min_aos, i));                       // q_c = -min_range, range.rs:62
+                const Fr mn = aos_load(a.min_aos, i);
+                count_unreduced(a.counters, mn, i);
+                negmin = fr_neg(mn);                                           // q_c = -min_range, range.rs:62
                 tab_store_fr(a.param, a.stride, a.param_negmin, i, negmin);
             }
         }
@@ -168,14 +194,17 @@ struct InvPlain { struct Args {}; };     // the batch inversion without a fused 
 
 // ---------------------------------------------------------------------------------------------------- is_non_zero
 struct IsNonZeroFused {   // inside k_batch_inv's first walk (in_slot = 0, out_slot = 1); slots: 0 = var_assigned, 1 = inv, 2 = one
-    struct Args { const uint4* assigned; uint4* fr; uint64_t stride; uint64_t n; unsigned long long* counters; };
+    struct Args { const uint4* assigned; uint4* fr; uint64_t stride; uint64_t n; unsigned long long* counters; uint8_t* flags; };
     PG_HD static Fr pre(const Args& a, uint64_t i) {
         const Fr va = aos_load(a.assigned, i);
+        count_unreduced(a.counters, va, i);
         tab_store_fr(a.fr, a.stride, 0, i, va);                                              // var_assigned, scalar.rs:69
-        if (fr_is_zero(va)) {                                                                // invert() is None, scalar.rs:73-80
+        const bool none = fr_is_zero(va);                                                    // invert() is None, scalar.rs:73-80
+        if (none) {
             counter_add(a.counters + CNT_N_ERR, 1ull);
             counter_min(a.counters + CNT_FIRST_ERR, (unsigned long long)i);
         }
+        if (a.flags) a.flags[i] = none ? 1 : 0;                                              // per-instance Result (pg_is_non_zero_batch_flags)
         tab_store_fr(a.fr, a.stride, 2, i, fr_one());                                        // one, scalar.rs:83
         return va;
     }
@@ -204,10 +233,18 @@ struct SelectOneBody {
 
 // ---------------------------------------------------------------------------------------------------- constrain_to_constant
 struct ConstrainBody {   // only launched when the constant and/or the public input is per-instance
-    struct Args { const uint4* constant; const uint4* pi; uint4* param; uint64_t stride; uint64_t n; int32_t param_qc, param_pi; };
+    struct Args { const uint4* constant; const uint4* pi; uint4* param; uint64_t stride; uint64_t n; int32_t param_qc, param_pi; unsigned long long* counters; };
     PG_HD static void run(const Args& a, uint64_t i) {
-        if (a.param_qc >= 0) tab_store_fr(a.param, a.stride, (uint32_t)a.param_qc, i, fr_neg(aos_load(a.constant, i)));   // q_c = -constant
-        if (a.param_pi >= 0) tab_store_fr(a.param, a.stride, (uint32_t)a.param_pi, i, aos_load(a.pi, i));
+        if (a.param_qc >= 0) {
+            const Fr c = aos_load(a.constant, i);
+            count_unreduced(a.counters, c, i);
+            tab_store_fr(a.param, a.stride, (uint32_t)a.param_qc, i, fr_neg(c));                                          // q_c = -constant
+        }
+        if (a.param_pi >= 0) {
+            const Fr p = aos_load(a.pi, i);
+            count_unreduced(a.counters, p, i);
+            tab_store_fr(a.param, a.stride, (uint32_t)a.param_pi, i, p);
+        }
     }
 };
 

@@ -63,7 +63,7 @@ public:
         PG_CUDA(cudaStreamCreateWithFlags(&in_stream, cudaStreamNonBlocking));
         PG_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
-        check_shape = cfg.reserved < (uint32_t)CHECK_SHAPES ? (int)cfg.reserved : 0;
+        check_shape = cfg.check_shape < (uint32_t)CHECK_SHAPES ? (int)cfg.check_shape : 0;
         PG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_MAX_LOG_TILE));
         PG_CUDA(cudaFuncSetAttribute(k_check_rowpar<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k_check_rowpar<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -128,7 +128,7 @@ public:
         for (auto& pc : pending) { cudaStreamWaitEvent(stream, pc.ev, 0); sync_ev_free.push_back(pc.ev); }
         pending.clear();
     }
-    bool h2d_chunked(void* dst, const void* src, uint64_t n, size_t elem, uint64_t chunk) {
+    bool h2d_chunked(void* dst, const void* src, uint64_t n, size_t elem, uint64_t chunk, unsigned long long* counters) {
         cudaEvent_t head = get_sync_event();         // the destination may come from the pool: order behind what is queued
         PG_CUDA(cudaEventRecord(head, stream));
         PG_CUDA(cudaStreamWaitEvent(in_stream, head, 0));
@@ -136,6 +136,10 @@ public:
         for (uint64_t lo = 0; lo < n; lo += chunk) {
             const uint64_t hi = lo + chunk < n ? lo + chunk : n;
             PG_CUDA(cudaMemcpyAsync((char*)dst + lo * elem, (const char*)src + lo * elem, (hi - lo) * elem, cudaMemcpyHostToDevice, in_stream));
+            if (counters) {                          // ingest check of the chunk (scalars must be < q), behind its copy on the same stream
+                const ValidateBody::Args va{reinterpret_cast<const uint4*>(dst), lo, hi - lo, counters};
+                k_simple<ValidateBody><<<grid_for(hi - lo), BLOCK, 0, in_stream>>>(va);
+            }
             cudaEvent_t ev = get_sync_event();
             PG_CUDA(cudaEventRecord(ev, in_stream));
             pending.push_back(PendingCopy{dst, (const char*)dst + n * elem, lo, hi, ev});
@@ -264,6 +268,9 @@ public:
         return launched("k_batch_inv");
     }
     bool run_batch_inv(const BatchInvArgs& a, int cls) { return run_batch_inv_fused<InvPlain>(a, InvPlain::Args{}, cls); }
+    // which kernel evaluated how many rows (pg_get_check_stats): the tests use it to prove that a verdict came from the kernel they mean
+    pg_check_stats ck{};
+    void count_check(int kind, uint64_t rows) { ck.launches[kind]++; ck.rows[kind] += rows; }
     bool run_check(const CheckArgs& a, const SparseProg& prog) {
         const size_t smem = (size_t)a.n_pool * sizeof(Fr);
         if (smem > 64 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
@@ -273,6 +280,7 @@ public:
             const unsigned grid = (unsigned)((total + 127) / 128);
             if (a.mode == PG_CHECK_SPARSE) k_check_rowpar<1><<<grid, 128, smem, stream>>>(a); else k_check_rowpar<0><<<grid, 128, smem, stream>>>(a);
             toc();
+            count_check(PG_CK_ROWPAR, total);
             return launched("k_check_rowpar");
         }
         // the structure-aware check needs few registers and is issue- and latency-bound: 32 warps/SM (64 registers) measured best, unless a shape was asked for
@@ -282,6 +290,7 @@ public:
             default: launch_check<0>(a, prog, smem); break;
         }
         toc();
+        count_check(a.mode != PG_CHECK_SPARSE ? PG_CK_INSTANCE_GENERIC : prog.ops ? PG_CK_PROGRAM : PG_CK_INSTANCE_TERMS, a.n_inst * a.n_rows);
         return launched("k_check");
     }
     bool run_check_gates(const CheckArgs& a) {
@@ -291,6 +300,7 @@ public:
         tic(CLS_CHECK, total);
         k_check_gates<<<(unsigned)((total + 127) / 128), 128, smem, stream>>>(a);
         toc();
+        count_check(PG_CK_GATES, total);
         return launched("k_check_gates");
     }
     bool run_mat_tiled(const MatTileArgs& a) {

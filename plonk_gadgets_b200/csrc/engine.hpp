@@ -20,7 +20,9 @@
 //   bool run_ntt_pass(const NttPassArgs&, uint64_t n_blocks)    -- one group of butterfly stages over all tiles (ntt.cuh)
 //   bool upload_pow2(const Fr*), bool imad_peak(double*, double*), bool ubench(int, double*), timing(pg_timing*, bool reset)
 #pragma once
+#include <stdio.h>
 #include <algorithm>
+#include <stdexcept>
 #include <map>
 #include <string>
 #include <vector>
@@ -47,7 +49,11 @@ struct Segment {
     std::vector<SpOp> sp_ops; SpOp* d_sp = nullptr;    // structure-aware row program (PG_CHECK_SPARSE only)
     std::vector<Column> operands;       // the columns bound as operands (for the permutation map)
     bool other_gates = false;           // some row belongs to another widget than the arithmetic one (GATE_RANGE / GATE_NONE)
+    bool owns_table = true;             // false: fr / bits / param and d_image are views into buffers another segment owns
 };
+// a pre-allocated variable table (and image memory) for a segment that is a VIEW of another segment's storage: instance i of the
+// view is instance first + i of the owner (the SoA stride is the owner's)
+struct SegmentView { uint4* fr; uint64_t n_alloc; unsigned char* image; size_t image_bytes; };
 
 inline Fr fr_from_pg(const pg_fr& x) {
     Fr r;
@@ -125,7 +131,7 @@ public:
         be.shutdown();
     }
     void release_segments() {
-        for (auto& s : segs) { dfree(s.fr); dfree(s.bits); dfree(s.param); dfree(s.d_image); }
+        for (auto& s : segs) if (s.owns_table) { dfree(s.fr); dfree(s.bits); dfree(s.param); dfree(s.d_image); }
         for (void* p : scratch) dfree(p);
         scratch.clear(); segs.clear(); cols.clear(); dsegs.clear(); dsegs_dirty = true;
         n_rows = 0; n_vars = 0;
@@ -134,6 +140,8 @@ public:
     int reset() {
         if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
         release_segments();
+        { const int rcc = reset_counters(true); if (rcc) return rcc; }
+        validation_pending = false;
         std::vector<Fr> vals;
         Template t = make_preamble_template(&vals);
         int rc = push_segment(std::move(t), 1, nullptr, 0);
@@ -235,13 +243,20 @@ public:
     }
     // Appends a segment of n instances of template t whose operands are the given columns.  Allocates the variable
     // table, resolves the symbolic wires and uploads the row program.  The witness kernels run afterwards.
-    int push_segment(Template&& t, uint64_t n, const Column* operands, uint32_t n_operands) {
+    static size_t image_bytes_bound(const Template& T) {      // upper bound of a segment image (the structure-aware program has at most ~12 operations per row)
+        return (T.rows.size() * (sizeof(DevRow) + 12 * sizeof(SpOp)) + T.var_loc.size() * sizeof(uint32_t) + (T.pool.size() + 8 * T.rows.size()) * sizeof(Fr) + 255) & ~(size_t)255;
+    }
+    int push_segment(Template&& t, uint64_t n, const Column* operands, uint32_t n_operands, const SegmentView* view = nullptr) {
         Segment s;
         s.t = std::move(t);
         s.n_inst = n; s.n_alloc = n ? n : 1;
         s.base_row = n_rows; s.base_var = n_vars;
         const Template& T = s.t;
-        if (T.n_fr) { s.fr = (uint4*)dalloc((size_t)T.n_fr * 2 * s.n_alloc * sizeof(uint4)); if (!s.fr) return fail(PG_ERR_OOM, "variable table"); }
+        if (view) {                                   // storage exists already (templates with fr slots only)
+            if (T.n_planes || T.n_params) return fail(PG_ERR_STATE, "segment views hold scalar slots only");
+            s.owns_table = false; s.fr = view->fr; s.n_alloc = view->n_alloc;
+        }
+        else if (T.n_fr) { s.fr = (uint4*)dalloc((size_t)T.n_fr * 2 * s.n_alloc * sizeof(uint4)); if (!s.fr) return fail(PG_ERR_OOM, "variable table"); }
         if (T.n_planes) { s.bits = (uint32_t*)dalloc((size_t)T.n_planes * 8 * s.n_alloc * sizeof(uint32_t)); if (!s.bits) return fail(PG_ERR_OOM, "bit planes"); }
         if (T.n_params) { s.param = (uint4*)dalloc((size_t)T.n_params * 2 * s.n_alloc * sizeof(uint4)); if (!s.param) return fail(PG_ERR_OOM, "parameter table"); }
         s.tabs[0].fr = s.fr; s.tabs[0].bits = s.bits; s.tabs[0].stride = s.n_alloc; s.tabs[0].var_base = s.base_var; s.tabs[0].var_stride = T.n_vars;
@@ -276,7 +291,8 @@ public:
         if (b_rows) memcpy(img.data(), s.rows.data(), b_rows);
         if (!T.var_loc.empty()) memcpy(img.data() + b_rows, T.var_loc.data(), T.var_loc.size() * sizeof(uint32_t));
         memcpy(img.data() + b_rows + b_var, T.pool.data(), b_pool);
-        unsigned char* d_img = (unsigned char*)dalloc(img.size());
+        if (view && img.size() > view->image_bytes) return fail(PG_ERR_STATE, "segment view: image larger than its reserved memory");
+        unsigned char* d_img = view ? view->image : (unsigned char*)dalloc(img.size());
         if (!d_img || !be.h2d(d_img, img.data(), img.size())) return fail(d_img ? PG_ERR_CUDA : PG_ERR_OOM, "template upload");
         s.d_rows = b_rows ? (DevRow*)d_img : nullptr;
         s.d_varloc = T.var_loc.empty() ? nullptr : (uint32_t*)(d_img + b_rows);
@@ -316,8 +332,7 @@ public:
     void pop_segment() {
         Segment& s = segs.back();
         n_rows -= s.n_inst * s.t.rows.size(); n_vars -= s.n_inst * (uint64_t)s.t.n_vars;
-        scratch.push_back(s.fr); scratch.push_back(s.bits); scratch.push_back(s.param);
-        scratch.push_back(s.d_image);
+        if (s.owns_table) { scratch.push_back(s.fr); scratch.push_back(s.bits); scratch.push_back(s.param); scratch.push_back(s.d_image); }
         segs.pop_back();
         dsegs_dirty = true;
     }
@@ -332,15 +347,34 @@ public:
         if (!be.h2d(d, p, count * sizeof(pg_fr))) { *rc = fail(PG_ERR_CUDA, "input copy"); return nullptr; }
         return reinterpret_cast<const uint4*>(d);
     }
+    // Reads the counters back (synchronises).  Unreduced caller scalars seen by any ingest kernel since the composer was reset are
+    // reported here: the composer then holds values the reference type cannot represent and must be reset.
+    bool validation_pending = false;                 // an ingest check was enqueued since the counters were last read
     int read_counters(unsigned long long* out) {
         if (!be.d2h(out, d_counters, CNT_WORDS * sizeof(unsigned long long))) return fail(PG_ERR_CUDA, "counter read");
+        validation_pending = false;
+        if (out[CNT_BAD_INPUT]) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "%llu input scalar(s) not fully reduced (>= q), first at index %llu of its batch: reset the composer",
+                     out[CNT_BAD_INPUT], out[CNT_FIRST_BAD_INPUT]);
+            return fail(PG_ERR_ARG, msg);
+        }
         return PG_OK;
     }
-    int reset_counters() {
-        unsigned long long init[CNT_WORDS] = {0, ~0ull, 0, 0, ~0ull, 0, 0, 0};
-        if (!be.h2d(d_counters, init, sizeof(init))) return fail(PG_ERR_CUDA, "counter reset");
+    // re-initialises the per-call words; `all`: also the sticky bad-input words (composer reset)
+    int reset_counters(bool all = false) {
+        static const unsigned long long init[CNT_WORDS] = {0, ~0ull, 0, 0, ~0ull, 0, ~0ull, 0};
+        if (!be.h2d(d_counters, init, (all ? (size_t)CNT_WORDS : (size_t)CNT_STICKY) * sizeof(unsigned long long))) return fail(PG_ERR_CUDA, "counter reset");
         return PG_OK;
     }
+    // pg_sync: everything enqueued has finished, and no ingest check has failed
+    int sync_checked() {
+        if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
+        if (!validation_pending) return PG_OK;
+        unsigned long long c[CNT_WORDS];
+        return read_counters(c);
+    }
+    static bool host_reduced(const pg_fr& x) { return fr_is_reduced(fr_from_pg(x)); }
 
     // ------------------------------------------------------------------------------------------------ gadgets
     int add_input_batch(uint64_t n, const pg_fr* values, int on_device, pg_col* out) {
@@ -353,9 +387,15 @@ public:
         // starts on the first chunk while the others are still in flight (run_simple_chunked), anything else waits for all of them.
         const bool chunked = !on_device && n >= INPUT_CHUNK_MIN;
         const uint64_t chunk = (((n + INPUT_CHUNKS - 1) / INPUT_CHUNKS) + 1023) & ~1023ull;
+        // every scalar is checked for full reduction on the device once it has arrived (chunked copies: chunk by chunk on the input stream)
         if (n && !(on_device ? be.d2d(s.fr, values, n * sizeof(pg_fr))
-                   : chunked ? be.h2d_chunked(s.fr, values, n, sizeof(pg_fr), chunk)
+                   : chunked ? be.h2d_chunked(s.fr, values, n, sizeof(pg_fr), chunk, d_counters)
                              : be.h2d(s.fr, values, n * sizeof(pg_fr)))) return fail(PG_ERR_CUDA, "add_input copy");
+        if (n && !chunked) {
+            ValidateBody::Args va{s.fr, 0, n, d_counters};
+            if (!be.template run_simple<ValidateBody>(va, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "input validation kernel");
+        }
+        if (n) validation_pending = true;
         *out = new_column((uint32_t)segs.size() - 1, 0, n);
         return PG_OK;
     }
@@ -372,6 +412,7 @@ public:
             if (!be.d2h(&mx0, mx, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "bound read");
             if (is_range_check && !be.d2h(&mn0, mn, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "bound read");
         } else { mx0 = mx[0]; if (is_range_check) mn0 = mn[0]; }
+        if (!host_reduced(mx0) || !host_reduced(mn0)) return fail(PG_ERR_ARG, "range gadget: bound not fully reduced (>= q)");
         const Fr m0 = fr_sub(fr_from_pg(mx0), fr_one());
         const Fr negmin0 = fr_neg(fr_from_pg(mn0));
         const uint32_t k = num_bits_from_canonical(fr_from_mont(m0));
@@ -381,6 +422,7 @@ public:
             d_mx = stage(mx, n, on_device, &rc); if (!d_mx) return rc;
             if (is_range_check) { d_mn = stage(mn, n, on_device, &rc); if (!d_mn) return rc; }
             if ((rc = reset_counters())) return rc;
+            validation_pending = true;
         }
         uint32_t result_local = 0;
         Column operand = *w;
@@ -440,12 +482,13 @@ public:
         int rc; const uint4* src = n ? stage(assigned, n, on_device, &rc) : nullptr;
         if (n && !src) return rc;
         if ((rc = reset_counters())) return rc;
+        validation_pending = true;
         Column operand = *v;
         rc = push_segment(make_is_non_zero_template(false), n, &operand, 1);
         if (rc) return rc;
         {
             Segment& s = segs.back();
-            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters};
+            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters, nullptr};
             BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
             inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
             if (n && !be.template run_batch_inv_fused<IsNonZeroFused>(inv, g, CLS_WITNESS)) return fail(PG_ERR_CUDA, "is_non_zero kernel");
@@ -472,6 +515,83 @@ public:
         if (!be.template run_simple<AddInputBody>(g, 1, CLS_OTHER)) return fail(PG_ERR_CUDA, "is_non_zero partial kernel");
         err = "is_non_zero: value_assigned is zero (NonExistingInverse)";
         return PG_ERR_NON_EXISTING_INVERSE;
+    }
+
+    // for i { results[i] = is_non_zero(composer, var_i, value_assigned_i); } -- every Result kept (scalar.rs:63-97 called without `?`):
+    // a batch does not abort on one zero.  err_flags[i] = 1 where the call returned Err(NonExistingInverse).
+    //   PG_NZ_UNIFORM  : every instance appends the full 3 variables + 3 rows (numbering first + 3i); an errored instance holds
+    //                    var_assigned = 0, inv = 0 (invert().unwrap_or(zero), the convention of scalar.rs:122), one = 1, so its row
+    //                    var*inv - 1 = 0 is unsatisfied: one segment, no host round trip besides the error count.
+    //   PG_NZ_REFERENCE: the composer the reference loop leaves behind -- an errored call has appended var_assigned and the
+    //                    assert_equal row only (scalar.rs:69-71, return at :79): 1 variable + 1 row.  The same device table is
+    //                    re-described as 2*n_err + 1 segment views (runs of completed instances / single partial instances).
+    static constexpr uint64_t NZ_MAX_VIEWS = 1ull << 20;
+    int is_non_zero_flags(pg_col cv, const pg_fr* assigned, int on_device, uint8_t* err_flags, int layout, uint64_t* n_err_out) {
+        const Column* v = column(cv);
+        if (!v || (v->n && !assigned) || (layout != PG_NZ_UNIFORM && layout != PG_NZ_REFERENCE)) return fail(PG_ERR_ARG, "is_non_zero_batch_flags: bad argument");
+        const uint64_t n = v->n;
+        if (n_err_out) *n_err_out = 0;
+        int rc; const uint4* src = n ? stage(assigned, n, on_device, &rc) : nullptr;
+        if (n && !src) return rc;
+        const bool need_flags = err_flags || layout == PG_NZ_REFERENCE;
+        uint8_t* d_flags = nullptr;
+        if (need_flags && n) {
+            if (err_flags && on_device) d_flags = err_flags;
+            else { d_flags = (uint8_t*)dalloc(n); if (!d_flags) return fail(PG_ERR_OOM, "error flags"); scratch.push_back(d_flags); }
+        }
+        if ((rc = reset_counters())) return rc;
+        validation_pending = true;
+        const Column operand = *v;
+        rc = push_segment(make_is_non_zero_template(false), n, &operand, 1);
+        if (rc) return rc;
+        const size_t seg_index = segs.size() - 1;
+        if (n) {
+            Segment& s = segs.back();
+            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters, d_flags};
+            BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
+            inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
+            if (!be.template run_batch_inv_fused<IsNonZeroFused>(inv, g, CLS_WITNESS)) return fail(PG_ERR_CUDA, "is_non_zero kernel");
+        }
+        unsigned long long c[CNT_WORDS];
+        if ((rc = read_counters(c))) return rc;
+        const uint64_t n_err = c[CNT_N_ERR];
+        if (n_err_out) *n_err_out = n_err;
+        std::vector<uint8_t> h_flags;
+        if (layout == PG_NZ_REFERENCE && n_err) { h_flags.resize(n); if (!be.d2h(h_flags.data(), d_flags, n)) return fail(PG_ERR_CUDA, "error flag copy"); }
+        if (err_flags && !on_device && n) {
+            if (!h_flags.empty()) memcpy(err_flags, h_flags.data(), n);
+            else if (!be.d2h(err_flags, d_flags, n)) return fail(PG_ERR_CUDA, "error flag copy");
+        }
+        if (layout == PG_NZ_UNIFORM || !n_err) return PG_OK;
+        // ---- reference layout: runs of completed instances and single partial instances, as views of the table just filled
+        if (2 * n_err + 1 > NZ_MAX_VIEWS) return fail(PG_ERR_ARG, "is_non_zero_batch_flags: too many errored instances for the reference layout (use PG_NZ_UNIFORM)");
+        uint4* table; uint64_t stride;
+        {
+            Segment& s = segs[seg_index];
+            table = s.fr; stride = s.n_alloc;
+            uint64_t f = 0; while (!h_flags[f]) f++;                       // the owning segment keeps the instances before the first error
+            n_rows -= (n - f) * s.t.rows.size(); n_vars -= (n - f) * (uint64_t)s.t.n_vars;
+            s.n_inst = f;
+            dsegs_dirty = true;
+        }
+        const Template full = make_is_non_zero_template(false), part = make_is_non_zero_template(true);
+        const size_t b_full = image_bytes_bound(full), b_part = image_bytes_bound(part);
+        unsigned char* arena = (unsigned char*)dalloc((n_err + 1) * b_full + n_err * b_part);
+        if (!arena) return fail(PG_ERR_OOM, "segment view images");
+        scratch.push_back(arena);
+        uint64_t i = segs[seg_index].n_inst;
+        while (i < n) {
+            uint64_t j = i;
+            const bool err_run = h_flags[i] != 0;
+            if (err_run) j = i + 1; else while (j < n && !h_flags[j]) j++;
+            Column sub = operand; sub.inst_off += i; sub.n = j - i;
+            SegmentView view{table + 2 * i, stride, arena, err_run ? b_part : b_full};
+            arena += view.image_bytes;
+            Template t = err_run ? part : full;
+            if ((rc = push_segment(std::move(t), j - i, &sub, 1, &view))) return rc;
+            i = j;
+        }
+        return PG_OK;
     }
 
     int select_batch(bool one, pg_col cx, pg_col csel, pg_col* out) {
@@ -513,6 +633,7 @@ public:
         pg_fr c0 = {{0, 0, 0, 0}}, p0 = {{0, 0, 0, 0}};
         if (cu) { if (on_device) { if (!be.d2h(&c0, constant, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "constant read"); } else c0 = constant[0]; }
         if (pu) { if (on_device) { if (!be.d2h(&p0, pi, sizeof(pg_fr))) return fail(PG_ERR_CUDA, "pi read"); } else p0 = pi[0]; }
+        if (!host_reduced(c0) || !host_reduced(p0)) return fail(PG_ERR_ARG, "constrain_to_constant_batch: scalar not fully reduced (>= q)");
         int rc = PG_OK; const uint4 *d_c = nullptr, *d_p = nullptr;
         if (!cu) { d_c = stage(constant, n, on_device, &rc); if (!d_c) return rc; }
         if (pi && !pu) { d_p = stage(pi, n, on_device, &rc); if (!d_p) return rc; }
@@ -521,7 +642,8 @@ public:
         if (rc) return rc;
         Segment& s = segs.back();
         if (s.t.n_params && n) {
-            ConstrainBody::Args g{d_c, d_p, s.param, s.n_alloc, n, s.t.param_qc, s.t.param_pi};
+            ConstrainBody::Args g{d_c, d_p, s.param, s.n_alloc, n, s.t.param_qc, s.t.param_pi, d_counters};
+            validation_pending = true;
             if (!be.template run_simple<ConstrainBody>(g, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "constrain kernel");
         }
         return PG_OK;
@@ -599,6 +721,7 @@ public:
     // Fault injection (tests, diagnostics): overwrite the stored value of one Variable.  Packed bit variables cannot be poked.
     int poke_variable(uint64_t var, const pg_fr* value) {
         if (var >= n_vars || !value) return fail(PG_ERR_ARG, "poke_variable: unknown Variable or null value");
+        if (!host_reduced(*value)) return fail(PG_ERR_ARG, "poke_variable: value not fully reduced (>= q)");
         for (size_t k = segs.size(); k-- > 0;) {
             Segment& s = segs[k];
             if (!s.n_inst || !s.t.n_vars || var < s.base_var) continue;

@@ -593,11 +593,15 @@ PG_HD void fr_halve_mod_q(Fr& s) {          // s/2 mod q:  (s + q)/2 when s is o
 }
 PG_HD Fr fr_inv_binary(const Fr& x) {
     Fr u = x, v, s = fr_zero(), t = fr_zero(), d;
+    // 0 has no inverse (and would spin in the halving loop below): a caller that breaks the "x != 0" contract -- e.g. through an
+    // unreduced table value equal to q, whose Montgomery product with anything is 0 -- gets 0 back, i.e. a wrong row, not a hung GPU.
+    if (fr_is_zero(x)) return fr_zero();
 #pragma unroll
     for (int i = 0; i < 8; i++) v.v[i] = fr_q(i);
     s.v[0] = 1;
+    // every pass of the outer loop removes at least one bit from u + v (both below 2^256): 2*256 + 2 passes bound any input
 #pragma unroll 1
-    for (;;) {
+    for (int pass = 0; pass < 2 * 256 + 2; pass++) {
 #pragma unroll 1
         while (!(u.v[0] & 1u)) {
 #pragma unroll

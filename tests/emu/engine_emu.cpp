@@ -31,7 +31,11 @@ public:
     void* alloc(size_t bytes) { void* p = nullptr; if (posix_memalign(&p, 64, bytes ? bytes : 64)) return nullptr; memset(p, 0xA5, bytes); return p; }
     void release(void* p) { free(p); }
     bool h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
-    bool h2d_chunked(void* d, const void* s, uint64_t n, size_t elem, uint64_t) { memcpy(d, s, n * elem); return true; }
+    bool h2d_chunked(void* d, const void* s, uint64_t n, size_t elem, uint64_t, unsigned long long* counters) {
+        memcpy(d, s, n * elem);
+        if (counters) { const ValidateBody::Args va{reinterpret_cast<const uint4*>(d), 0, n, counters}; for (uint64_t i = 0; i < n; i++) ValidateBody::run(va, i); }
+        return true;
+    }
     bool d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
     bool d2d(void* d, const void* s, size_t n) { memmove(d, s, n); return true; }
     bool d2h_async(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
@@ -75,9 +79,12 @@ public:
         }
         return true;
     }
+    pg_check_stats ck{};
+    void count_check(int kind, uint64_t rows) { ck.launches[kind]++; ck.rows[kind] += rows; }
     bool run_check(const CheckArgs& a, const SparseProg& prog) {
         HostPool pool = {a.pool};
         const QRegs q = q_regs_default();
+        count_check(a.n_inst < 48 && a.n_rows > 1 ? PG_CK_ROWPAR : !a.mode ? PG_CK_INSTANCE_GENERIC : prog.ops ? PG_CK_PROGRAM : PG_CK_INSTANCE_TERMS, a.n_inst * a.n_rows);
         if (a.n_inst < 48 && a.n_rows > 1) {            // the row-parallel mapping (thread = one row of one instance), as for small segments on the GPU
             for (uint64_t t = 0; t < a.n_inst * a.n_rows; t++) {
                 unsigned long long fb = ~0ull;
@@ -94,6 +101,7 @@ public:
         return true;
     }
     bool run_check_gates(const CheckArgs& a) {
+        count_check(PG_CK_GATES, a.n_inst * a.n_rows);
         HostPool pool = {a.pool};
         const QRegs q = q_regs_default();
         for (uint64_t t = 0; t < a.n_inst * a.n_rows; t++) {

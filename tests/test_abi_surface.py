@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), name
     _lib.bind(lib)
-    assert lib.pg_abi_version() == 1
+    assert lib.pg_abi_version() == _lib.ABI_VERSION
     assert lib.pg_strerror(1) == b"NonExistingInverse"
 
 

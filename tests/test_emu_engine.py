@@ -39,7 +39,7 @@ def fr_emu():
 
 
 def test_emu_exports_the_abi(emu):
-    assert emu.pg_abi_version() == 1
+    assert emu.pg_abi_version() == _lib.ABI_VERSION
 
 
 def test_emu_matches_golden(emu, golden, oracle):
@@ -319,3 +319,23 @@ def test_emu_range_gate_fault_injection(emu, oracle):
 
 def test_emu_range_gate_poked_witness(emu, oracle):
     rgc.poked_witness(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)
+
+
+# ---- faults inside the range gadgets' own segments, per-instance Results, ingest checks (shared with the GPU tests) -----------
+from tests import fault_cases as fc  # noqa: E402
+
+
+@pytest.mark.parametrize("gadget,bits,per_inst", [("range_check", 8, False), ("max_bound", 12, True), ("range_check", 64, False)])
+def test_emu_poked_range_segment(emu, oracle, gadget, bits, per_inst):
+    """Host emulation of the per-instance check bodies (CheckBody::run<0>, SparseProgBody over the compiled row program): a
+    poked Variable of a range segment makes exactly the rows a big-int evaluation names unsatisfied."""
+    fc.poked_range_segment(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle, n=150 if bits < 64 else 131, gadget=gadget, bits=bits,
+                           per_instance_bounds=per_inst, expect_kind={pg.CHECK_GENERIC: "instance_generic", pg.CHECK_SPARSE: "program"})
+
+
+def test_emu_is_non_zero_flags(emu, oracle):
+    fc.non_zero_flags_vs_oracle(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)
+
+
+def test_emu_unreduced_inputs_rejected(emu, oracle):
+    fc.unreduced_inputs_rejected(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)

@@ -770,3 +770,155 @@ def test_range_gate_poked_witness(oracle):
 def test_range_gate_poked_witness_large_segments(oracle):
     """Enough instances for the one-thread-per-instance kernels (k_check / k_check_prog) next to k_check_gates."""
     rgc.poked_witness(gpu_composer, oracle, n=148 * 320 + 77, trials=3, arith="maybe_equal")
+
+
+# ---- the headline kernels must DETECT violations at their own launch shape (VERDICT r1, item 1) --------------------------------
+from tests import fault_cases as fc  # noqa: E402
+
+HEADLINE_N = 148 * 320 + 77          # past run_check's 320 * SMs threshold: one thread per instance (k_check / k_check_prog)
+KINDS = {pg.CHECK_GENERIC: "instance_generic", pg.CHECK_SPARSE: "program"}
+
+
+def test_poked_range_check_headline_shape(oracle):
+    """range_check k=65 (271 rows / 653 variables), 47 437 instances: V, A_j, U, Zv, Y of both decompositions and O poked at both
+    ends, at warp / block boundaries and mid-batch; `k_check<GENERIC>` and the compiled row program `k_check_prog` must report exactly
+    the rows the big-int evaluation of the dumped rows reports (count and first row).  Fails if either kernel is stubbed to return 0."""
+    fc.poked_range_segment(gpu_composer, oracle, n=HEADLINE_N, gadget="range_check", bits=64, expect_kind=KINDS)
+
+
+def test_poked_max_bound_headline_shape_per_instance_bounds(oracle):
+    """max_bound with per-instance 64-bit bounds (q_c parameter slots): the same at the same launch shape."""
+    fc.poked_range_segment(gpu_composer, oracle, n=HEADLINE_N, gadget="max_bound", bits=64, per_instance_bounds=True, expect_kind=KINDS, seed=6)
+
+
+def test_poked_max_bound_k253(oracle):
+    """C3's shape: max_bound, k = 253 (511 rows, 514 variables), large segment."""
+    fc.poked_range_segment(gpu_composer, oracle, n=HEADLINE_N, gadget="max_bound", bits=252, expect_kind=KINDS, seed=7)
+
+
+def test_is_non_zero_flags_gpu(oracle):
+    fc.non_zero_flags_vs_oracle(gpu_composer, oracle, n=300)
+    fc.non_zero_flags_vs_oracle(gpu_composer, oracle, n=1 << 16, zero_every=1024, mismatch_every=1024, modes=(pg.CHECK_GENERIC,))
+
+
+def test_unreduced_inputs_rejected_gpu(oracle):
+    fc.unreduced_inputs_rejected(gpu_composer, oracle)
+
+
+def test_unreduced_input_in_chunked_host_copy(oracle, torch_cuda):
+    """The ingest check of a chunked host copy runs chunk by chunk on the input stream: an unreduced scalar in the last chunk."""
+    torch = torch_cuda
+    n = (1 << 20) + 5
+    c = gpu_composer()
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 2, 1, 64, wit); c.sync()
+    host = wit.cpu().pin_memory()
+    host[n - 3] = -1                                   # 2^256 - 1
+    y = pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), c.add_input(host))
+    with pytest.raises(pg.EngineError) as e:
+        c.check_circuit_satisfied()
+    assert e.value.code == -2 and f"index {n - 3}" in str(e.value)
+    c.reset()
+    host[n - 3] = 0
+    pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), c.add_input(host))
+    assert c.check_circuit_satisfied() == (0, None)
+
+
+# ---- BASELINE.json configurations at their full sizes (size-independent properties; VERDICT r1, item 1b) ----------------------------
+def test_c3_full_size(oracle, torch_cuda):
+    """C3: 2^22 max_bound instances, per-instance 252-bit bounds (k = 253): 2.14e9 rows, a 35 GB table."""
+    torch = torch_cuda
+    n = 1 << 22
+    if torch.cuda.mem_get_info()[0] < 60 * 2 ** 30:
+        pytest.skip("needs ~40 GB of free HBM")
+    c = gpu_composer(check_mode=pg.CHECK_SPARSE)
+    mx = torch.empty((n, 4), dtype=torch.int64, device="cuda"); wit = torch.empty_like(mx)
+    c.synth(SEED, 31, 3, 252, mx); c.synth(SEED, 32, 2, 250, wit)
+    y, k = pg.max_bound(c, mx, c.add_input(wit))
+    assert k == 253 and c.circuit_size() == 3 + 511 * n and c.num_variables() == 5 + n + 514 * n
+    assert c.check_circuit_satisfied() == (0, None)
+    res = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.read_column_into(y, res); c.sync()
+    one = torch.from_numpy(oracle.from_ints([1]).view(np.int64)).cuda()
+    assert bool((res[0::2] == one).all())
+    frac_in = float((res[1::2] == one).all(dim=1).float().mean())
+    assert 0.26 < frac_in < 0.295                      # y = 1 iff (max-1-x mod q) fits 253 bits: probability 2^253 / q = 0.2764
+    # one instance row by row against the oracle, and a fault in the last instance
+    i = n - 1
+    oc = oracle.Composer()
+    wv = c.variables(5 + i, 1)
+    bound = torch.empty((1, 4), dtype=torch.int64, device="cuda"); bound.copy_(mx[i:i + 1]); torch.cuda.synchronize()
+    oc.max_bound_batch(bound.cpu().numpy().view(np.uint64), oc.add_input_batch(wv))
+    assert (oc.variables()[6:] == c.variables(5 + n + 514 * i, 514)).all()
+    var = 5 + n + 514 * i + 257 + 100                  # an accumulator in the middle of the chain
+    old = c.variables(var, 1)[0].copy()
+    c.poke_variable(var, oracle.from_ints([12345])[0])
+    bad, first = c.check_circuit_satisfied()
+    assert bad == 2 and first == 3 + 511 * i + 2 * 100 + 1      # the accumulate rows that write and read A_100
+    c.close()
+
+
+def test_c4_full_size_with_error_path(oracle, torch_cuda):
+    """C4 as SURVEY.md 8d specifies it: 2^24 x (maybe_equal + is_non_zero), value uniform Fr with 1/1024 forced to zero (the
+    NonExistingInverse path), value_assigned = value except 1/1024 mismatches, maybe_equal with 50 % a = b."""
+    torch = torch_cuda
+    n = 1 << 24
+    c = gpu_composer()
+    a = torch.empty((n, 4), dtype=torch.int64, device="cuda"); b = torch.empty_like(a)
+    c.synth(SEED, 41, 0, 0, a); c.synth(SEED, 42, 0, 0, b); c.sync()
+    b[0::2] = a[0::2]
+    a[5::1024] = 0                                     # forced zeros (b differs there unless even: index 5 mod 1024 is odd)
+    assigned = a.clone()
+    assigned[600::1024, 0] ^= 1                        # mismatching value_assigned
+    flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    va, vb = c.add_input(a), c.add_input(b)
+    eq = pg.maybe_equal(c, va, vb)
+    pg.is_non_zero_flags(c, va, assigned, layout=pg.NZ_UNIFORM, flags_out=flags)
+    assert c.last_n_err == n // 1024
+    bad, first = c.check_circuit_satisfied()
+    c.sync()
+    assert int(flags.sum()) == n // 1024 and bool(flags[5::1024].all())
+    assert bad == 3 * (n // 1024) and first == 3 + 3 * n + 3 * 5 + 2      # zero: var*inv - 1; mismatch: assert_equal and var*inv - 1
+    r = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.read_column_into(eq, r); c.sync()
+    one = torch.from_numpy(oracle.from_ints([1]).view(np.int64)).cuda()
+    assert bool((r[0::2] == one).all()) and bool((r[1::2] == 0).all())
+    # the `?` variant stops at the first zero
+    c.reset()
+    va = c.add_input(a)
+    with pytest.raises(pg.NonExistingInverse) as e:
+        pg.is_non_zero(c, va, a)
+    assert (e.value.n_err, e.value.first_err) == (n // 1024, 5) and c.circuit_size() == 3 + 3 * 5 + 1
+    c.close()
+
+
+def test_c5_full_size(oracle, torch_cuda):
+    """C5: the mixed circuit of 2^26 rows (range_check k=65 / max_bound k=253 / is_non_zero / select_one + select_zero, a quarter
+    of the rows each) on one GPU, both check modes: counts, verdict, result patterns."""
+    torch = torch_cuda
+    q = 1 << 24
+    n_rc, n_mb, n_nz, n_sel = q // 271, q // 511, q // 3, q // 5
+    one = torch.from_numpy(oracle.from_ints([1]).view(np.int64)).cuda()
+    for mode in (pg.CHECK_GENERIC, pg.CHECK_SPARSE):
+        c = gpu_composer(check_mode=mode)
+        x_rc = torch.empty((n_rc, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 51, 2, 64, x_rc)
+        x_mb = torch.empty((n_mb, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 52, 2, 250, x_mb)
+        x_nz = torch.empty((n_nz, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 53, 0, 0, x_nz)
+        x_sel = torch.empty((n_sel, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 54, 0, 0, x_sel)
+        s_sel = torch.empty((n_sel, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 55, 1, 1, s_sel)
+        y_rc = pg.range_check(c, oracle.from_ints([0]), oracle.from_ints([2 ** 64]), c.add_input(x_rc))
+        y_mb, k = pg.max_bound(c, oracle.from_ints([2 ** 252]), c.add_input(x_mb))
+        pg.is_non_zero(c, c.add_input(x_nz), x_nz)
+        x, s = c.add_input(x_sel), c.add_input(s_sel)
+        y1 = pg.conditionally_select_one(c, x, s)
+        y0 = pg.conditionally_select_zero(c, y1, s)
+        rows = 3 + 271 * n_rc + 511 * n_mb + 3 * n_nz + 5 * n_sel
+        assert k == 253 and c.circuit_size() == rows and abs(rows - (1 << 26)) < 2000
+        assert c.check_circuit_satisfied() == (0, None)
+        r = y_rc.values()
+        assert (r[0::2] == oracle.from_ints([1])[0]).all() and (r[1::2] == 0).all()
+        # select_one(x, s) = s ? x : 1 ; select_zero(y, s) = y * s
+        got1 = torch.empty((n_sel, 4), dtype=torch.int64, device="cuda"); c.read_column_into(y1, got1)
+        got0 = torch.empty((n_sel, 4), dtype=torch.int64, device="cuda"); c.read_column_into(y0, got0); c.sync()
+        is_one = (s_sel == one).all(dim=1)
+        assert bool((got1[is_one] == x_sel[is_one]).all()) and bool((got1[~is_one] == one).all())
+        assert bool((got0[is_one] == x_sel[is_one]).all()) and bool((got0[~is_one] == 0).all())
+        c.close()
