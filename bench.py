@@ -10,8 +10,9 @@ One "step" = one pass of the hot path over one batch of synthetic witnesses:
 `value`  : rows generated and evaluated per second with the witnesses already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same step through the C ABI with HOST buffers: pinned-host witnesses copied in, per-instance results
            (32 B each) and the verdict copied out, inside the timed region.
-Multi-GPU: one process per GPU (torchrun), instances sharded (weak scaling: 2^log2n per GPU), the only collective is the
-all-reduce of the verdict counters.  `--impl reference` times the restated reference CPU path (oracle/, faithful cost
+Multi-GPU: one process per GPU (torchrun), instances sharded by pg_shard_plan (weak scaling: 2^log2n per GPU; `--scaling strong`:
+2^log2n in total), the only collective of the step is the all-reduce of the verdict (pg_check_sharded: NCCL through the C ABI),
+executed inside every timed step.  `--impl reference` times the restated reference CPU path (oracle/, faithful cost
 structure: per-bit 256-step pow, hash-map variable store, per-row column pushes) on all host cores, rank 0 only.
 """
 from __future__ import annotations
@@ -31,19 +32,25 @@ METRIC = "Fr gate evals/sec, range_check batch 2^24"
 UNIT = "gate-evals/s"
 ROWS_PER_INSTANCE = 271          # 4k+11, k = 65
 VARS_PER_INSTANCE = 653
-IMAD_PER_ROW = 816               # 6 Fr mul x 136 32x32->64 multiply-accumulates
+IMAD_PER_ROW_DEFINITION = 816    # 6 Fr mul x 136 32x32->64 multiply-accumulates: the DEFINITIONAL cost of a generic gate evaluation
+EXECUTED_WIDE_PER_ROW = 424      # what k_check<GENERIC> executes: one Montgomery multiplication (64 + 48) + a 4-term dot product with one
+                                 # shared reduction (256 + 48) + the "0 mod q" test (8); counted in SASS: profiles/r04_sass_mix.txt
 PACKED_BYTES_PER_INSTANCE = 141 * 32 + 2 * 32   # variable table written by witness generation (141 Fr slots + 2 bit planes)
 
 
-def ncu_traffic(log2n: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of k_check per launch, from the committed `ncu --set full` capture of this
-    command at the metric size (profiles/k_check_traffic.json); None for sizes that were not captured."""
+def ncu_traffic(log2n: int, check_mode: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from a committed `ncu --set full` capture of this
+    command (profiles/k_check_traffic.json: one entry per check mode, with the capture's file name and the git revision it was taken
+    at).  Returns (bytes or None, provenance)."""
     try:
         with open(os.path.join(ROOT, "profiles", "k_check_traffic.json")) as f:
             t = json.load(f)
-        return t["bytes_per_launch"] if t.get("log2n") == log2n else None
+        e = t.get(check_mode)
+        if e and e.get("log2n") == log2n:
+            return e["bytes_per_launch"], f"{e.get('source')} @ {e.get('git')}"
     except Exception:
-        return None
+        pass
+    return None, None
 
 
 def peaks():
@@ -186,6 +193,7 @@ def main():
     ap.add_argument("--check-mode", default="generic", choices=["generic", "sparse"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check-shape", type=int, default=0, help="launch shape of the gate-check kernel (tuning knob)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 2^log2n instances per GPU; strong: 2^log2n in total")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -194,7 +202,6 @@ def main():
     import torch
     import torch.distributed as dist
     import plonk_gadgets_b200 as pg
-    from plonk_gadgets_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -203,7 +210,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = 1 << args.log2n
     warm = max(args.warmup, 3)
     # one non-default torch stream shared with the engine: torch.cuda.Event and the engine's kernels see the same stream
     stream = torch.cuda.Stream(device=dev)
@@ -211,6 +217,18 @@ def main():
     mode = pg.CHECK_GENERIC if args.check_mode == "generic" else pg.CHECK_SPARSE
     c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream, check_shape=args.check_shape)
     assert stream.cuda_stream != 0
+    # sharding: the batch of n_total instances is cut by the C ABI's plan; this rank runs [inst_lo, inst_hi) and numbers its rows as
+    # the sequential composer of the whole batch does
+    n_total = (1 << args.log2n) * (world if args.scaling == "weak" else 1)
+    plan = pg.shard_plan([(pg.OP_ADD_INPUT, 0, n_total, 0), (pg.OP_RANGE_CHECK, 65, n_total, 0)], world, pg.SHARD_EVEN)
+    mine = plan[rank]
+    n = mine[0].inst_hi - mine[0].inst_lo
+    if world > 1:
+        uid = torch.zeros(pg.api.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(pg.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, 0)
+        c.comm_init(bytes(uid.cpu().numpy()), rank, world)          # the engine's own NCCL communicator (verdict all-reduce, gathers)
 
     # synthetic witnesses: even index uniform u64 (in range), odd index uniform Fr (out of range); per-rank stream id
     wit = torch.empty((n, 4), dtype=torch.int64, device=dev)
@@ -228,7 +246,7 @@ def main():
         c.reset()
         w = c.add_input(wit)
         y = pg.range_check(c, mn, mx, w)
-        bad, first = c.check_circuit_satisfied()
+        bad, first, _ = c.check_sharded(mine, 0)                            # local gate check + NCCL all-reduce of the verdict
         return y, bad, first
 
     host_in = torch.empty((n, 4), dtype=torch.int64).pin_memory()
@@ -240,7 +258,7 @@ def main():
         w = c.add_input(host_in)                                           # cudaMemcpyAsync from pinned host memory
         y = pg.range_check(c, mn, mx, w)
         c.read_column_into(y, host_out, asynchronous=True)                 # per-instance results -> pinned host, on the copy stream
-        bad, first = c.check_circuit_satisfied()                           # verdict (device -> host, 16 B); overlaps with the copy
+        bad, first, _ = c.check_sharded(mine, 0)                           # verdict of the whole batch (all-reduce; device -> host, 32 B); overlaps with the copy
         c.sync()                                                           # results have arrived
         return bad
 
@@ -282,13 +300,13 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
 
-    # max over ranks + verdict all-reduce (the only collective of the path)
+    # max over ranks (the verdict all-reduce already ran inside every step: `bad` is the whole batch's count)
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
-    g_bad, g_first, g_err = sharding.allreduce_verdict(tot_bad, None, 0, device=dev)
-    rows_step_total = world * n * ROWS_PER_INSTANCE
+    g_bad, g_err = tot_bad, 0
+    rows_step_total = n_total * ROWS_PER_INSTANCE
     value = rows_step_total * args.steps / (ms * 1e-3)
     e2e_value = rows_step_total * args.steps / (e2e_ms * 1e-3)
 
@@ -298,41 +316,55 @@ def main():
         chain_peak = c.microbench(4)         # the same products issued as the multiplier's mad.lo.cc/madc.hi.cc carry chains
         lo_peak = c.microbench(0)
         fr_mul_peak = c.microbench(6)
-        # two gate-check launches per step (3-row preamble segment + the range_check segment): report per step
+        # two gate-check launches per step on rank 0 (3-row preamble segment + the range_check segment): report per step
         check_ms = tim["check_ms"] / args.steps
         rows_per_launch = tim["check_rows"] / args.steps
-        imad_achieved = rows_per_launch * IMAD_PER_ROW / (check_ms * 1e-3)
         wit_ms = tim["witness_ms"] / args.steps
+        traffic, traffic_src = ncu_traffic(args.log2n if args.scaling == "weak" or world == 1 else -1, args.check_mode)
+        table_bytes = n * PACKED_BYTES_PER_INSTANCE
+        hbm_obj = lambda kernel, ms_: {"kernel": kernel, "achieved": table_bytes / (ms_ * 1e-3) / 1e9 if ms_ else None, "peak": hbm_peak, "unit": "GB/s",
+                                       "peak_source": hbm_src, "frac": (table_bytes / (ms_ * 1e-3) / 1e9 / hbm_peak) if ms_ else None, "ms_per_launch": ms_,
+                                       "algorithmic_bytes_per_launch": table_bytes}
+        if args.check_mode == "generic":
+            executed = rows_per_launch * EXECUTED_WIDE_PER_ROW / (check_ms * 1e-3)
+            roofline = {"bound": "imad", "kernel": "k_check<GENERIC>", "achieved": executed / 1e12, "peak": wide_peak / 1e12,
+                        "unit": f"T 32x32->64 products/s EXECUTED ({EXECUTED_WIDE_PER_ROW} IMAD.WIDE per gate evaluation)",
+                        "frac": executed / wide_peak if wide_peak else None,
+                        "peak_source": "measured in this run: IMAD.WIDE.U32 products on all SMs (pg_microbench mode 1)",
+                        "frac_of_carry_chain_peak": executed / chain_peak if chain_peak else None,
+                        "carry_chain_peak": chain_peak / 1e12, "imad_lo_peak": lo_peak / 1e12, "isolated_fr_mul_per_s": fr_mul_peak,
+                        "definitional_816": {"note": "SURVEY.md 8d counts a generic gate evaluation as 6 separate Montgomery multiplications = 816 "
+                                                     "multiply-accumulates; the kernel evaluates the factored polynomial with one shared reduction, so this "
+                                                     "figure is a rate of DEFINED work, not a pipe utilisation, and may exceed the peak",
+                                             "T_mac_per_s": rows_per_launch * IMAD_PER_ROW_DEFINITION / (check_ms * 1e-3) / 1e12},
+                        "traffic": traffic, "traffic_source": traffic_src, "ms_per_launch": check_ms,
+                        "hbm": hbm_obj("RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", wit_ms)}
+        else:
+            r = hbm_obj("k_check_prog (structure-aware row program: reads the packed variable table once)", check_ms)
+            roofline = {"bound": "hbm", **r, "traffic": traffic, "traffic_source": traffic_src,
+                        "hbm_witness": hbm_obj("RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", wit_ms)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32x8 (Fr Montgomery)", "data": "synthetic",
-            "config": {"workload": f"range_check batch 2^{args.log2n} per GPU, bounds [0, 2^64) (k=65): 271 rows / 653 variables per instance",
+            "config": {"workload": f"range_check batch 2^{args.log2n} {'per GPU' if args.scaling == 'weak' else 'in total'}, bounds [0, 2^64) (k=65): 271 rows / 653 variables per instance",
                        "check_mode": args.check_mode, "l2": "inputs larger than L2 (512 MiB of witnesses, ~77 GB variable table per step)",
-                       "timed_region": "composer reset + add_input + witness generation + gate check + verdict read"},
+                       "timed_region": "composer reset + add_input + witness generation + gate check + verdict all-reduce + verdict read",
+                       "instances_per_gpu": n, "instances_total": n_total},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32 + 64, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(tim["check_launches"] + tim["witness_launches"] + tim["other_launches"]),
-            "roofline": {"bound": "imad", "kernel": "k_check", "achieved": imad_achieved / 1e12, "peak": wide_peak / 1e12,
-                         "unit": "T 32x32->64 multiply-accumulates/s, ALGORITHMIC count 816 per gate eval (6 Fr mul x 136, SURVEY.md 8d)",
-                         "frac": imad_achieved / wide_peak if wide_peak else None,
-                         "peak_source": "measured in this run: IMAD.WIDE.U32 products on all SMs (pg_microbench mode 1); the kernel executes "
-                                        "425 wide products per gate eval (factored polynomial, dot-product reduction), so frac can exceed the executed-instruction share",
-                         "executed_wide_products_per_row": 425, "frac_executed": (rows_per_launch * 425 / (check_ms * 1e-3)) / wide_peak if wide_peak else None,
-                         "frac_executed_of_carry_chain_peak": (rows_per_launch * 425 / (check_ms * 1e-3)) / chain_peak if chain_peak else None,
-                         "carry_chain_peak": chain_peak / 1e12, "imad_lo_peak": lo_peak / 1e12, "isolated_fr_mul_per_s": fr_mul_peak,
-                         "traffic": ncu_traffic(args.log2n), "ms_per_launch": check_ms,
-                         "hbm": {"kernel": "RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", "achieved": n * PACKED_BYTES_PER_INSTANCE / (wit_ms * 1e-3) / 1e9 if wit_ms else None,
-                                 "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
-                                 "frac": (n * PACKED_BYTES_PER_INSTANCE / (wit_ms * 1e-3) / 1e9 / hbm_peak) if wit_ms else None, "ms_per_launch": wit_ms}},
+            "roofline": roofline,
             "kernel_ms": {"check": tim["check_ms"] / args.steps, "witness": tim["witness_ms"] / args.steps, "other": tim["other_ms"] / args.steps},
-            "verdict": {"n_unsat": g_bad, "n_err": g_err},
+            "verdict": {"n_unsat": g_bad, "n_err": g_err,
+                        "collective": "ncclAllReduce(sum, min) inside every step (pg_check_sharded)" if world > 1 else "world of one rank"},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_run(None, os.cpu_count() or 1)
         _emit(line)
     if world > 1:
         dist.barrier()
+        c.comm_destroy()
         dist.destroy_process_group()
     c.close()
     return 0

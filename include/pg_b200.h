@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define PG_B200_ABI_VERSION 2
+#define PG_B200_ABI_VERSION 3
 
 /* BlsScalar: ref:src/allocated_scalar.rs:9-12 (dusk_plonk::bls12_381::BlsScalar) */
 typedef struct pg_fr { uint64_t l[4]; } pg_fr;
@@ -189,6 +189,49 @@ int pg_check_rows(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel,
  * (NULL q_arith = 1 everywhere, NULL q_range = 0 everywhere); d_next of row i is w_val[3][(i + 1) mod n]. */
 int pg_check_rows_ex(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel, const pg_fr *pi, const pg_fr *q_arith,
                      const pg_fr *q_range, int on_device, uint64_t *n_unsat, uint64_t *first_bad_row);
+
+/* ---- multi-GPU: sharding plan and the two collectives -------------------------------------------------
+ * One process and one pg_ctx per GPU.  Gadget instances are independent (ref:src/range.rs:119-158 allocates its own accumulators,
+ * ref:src/scalar.rs:41, :83 their own constant one), so the instances of every batched call are cut into contiguous ranges, one per
+ * rank; a rank makes the same sequence of *_batch calls on its ranges.  No communication inside the kernels; the ranks meet in
+ *   - the all-reduce of the verdict (sum of unsatisfied rows and of NonExistingInverse errors, min of the first bad row), and
+ *   - the gather of per-instance results / witness shards,
+ * both NCCL over NVLink 5 / NVSwitch on the ctx's stream (NCCL is bound at run time: "libnccl.so.2").
+ *
+ * pg_shard_plan is pure host code (no ctx, no GPU): a mixed circuit is a list of calls (pg_op: gadget, num_bits for the range
+ * gadgets, instance count, group); calls with the same `group` share one instance index space (an add_input column and the gadgets
+ * applied to it) and are cut at the same places.  out[rank * n_ops + k] = the instance range of call k that `rank` runs, and the
+ * row / Variable index its first instance has in the SEQUENTIAL composer of the whole circuit (3 rows + 5 variables of the fresh
+ * composer, then call after call: prefix sums of n * rows / n * variables per instance) -- the numbering the reference would
+ * produce.  Policies: PG_SHARD_EVEN cuts every group into equal instance ranges; PG_SHARD_ROWS lays the groups end to end weighted by
+ * rows per instance and cuts that line into equal parts at instance boundaries, so a rank owns a contiguous ~1/world of the rows. */
+enum { PG_OP_ADD_INPUT = 0, PG_OP_RANGE_CHECK = 1, PG_OP_MAX_BOUND = 2, PG_OP_MAYBE_EQUAL = 3, PG_OP_IS_NON_ZERO = 4,
+       PG_OP_SELECT_ZERO = 5, PG_OP_SELECT_ONE = 6, PG_OP_CONSTRAIN = 7, PG_OP_RANGE_GATE = 8 };
+enum { PG_SHARD_EVEN = 0, PG_SHARD_ROWS = 1 };
+typedef struct pg_op { uint32_t gadget; uint32_t num_bits; uint64_t n; uint32_t group; uint32_t reserved; } pg_op;
+typedef struct pg_op_shard { uint64_t inst_lo, inst_hi; uint64_t row_base, var_base; } pg_op_shard;
+/* rows and variables one instance of the gadget appends (range_check 4k+11 / 2k+523, max_bound 2k+5 / k+261, ...) */
+int pg_op_shape(uint32_t gadget, uint32_t num_bits, uint64_t *rows, uint64_t *vars);
+int pg_shard_plan(const pg_op *ops, uint64_t n_ops, uint32_t world, int policy, pg_op_shard *out);
+
+/* Communicator of the ranks of one box.  pg_comm_unique_id (rank 0; no ctx needed) fills a 128-byte id to be handed to the other
+ * ranks out of band; every rank then calls pg_comm_init on its ctx (collective).  Without a communicator the calls below behave as a
+ * world of one rank and NCCL is never loaded. */
+#define PG_COMM_ID_BYTES 128
+int pg_comm_unique_id(uint8_t *id);
+int pg_comm_init(pg_ctx *ctx, const uint8_t *id, uint32_t rank, uint32_t world);
+int pg_comm_destroy(pg_ctx *ctx);
+/* pg_check on a sharded composer followed by the all-reduce: every rank receives the verdict of the WHOLE circuit.  mine = this
+ * rank's row of the plan (n_ops entries; call k since the last reset must be op k and hold inst_hi - inst_lo instances): rows are
+ * numbered from row_base, so *first_bad_row is the index in the sequential composer; mine == NULL: local numbering.  The fresh
+ * composer's three rows are checked by rank 0 only.  *n_err: in = this rank's NonExistingInverse count, out = the sum (may be NULL). */
+int pg_check_sharded(pg_ctx *ctx, const pg_op_shard *mine, uint64_t n_ops, uint64_t *n_unsat, uint64_t *first_bad_row, uint64_t *n_err);
+/* All-gather of a column (per-instance results of a call): dst receives the shards of all ranks in rank order = instance order of
+ * the whole batch.  capacity: scalars dst can hold (PG_ERR_ARG if too small); counts: `world` entries or NULL; *total = their sum. */
+int pg_gather_column(pg_ctx *ctx, pg_col col, pg_fr *dst, uint64_t capacity, int dst_on_device, uint64_t *counts, uint64_t *total);
+/* Gather of witness shards: the Variables that call number `call` (0-based since the last reset) appended on every rank, in the
+ * sequential composer's Variable order -- variables[var_base of rank 0's shard ...) of that call. */
+int pg_gather_variables(pg_ctx *ctx, uint64_t call, pg_fr *dst, uint64_t capacity, int dst_on_device, uint64_t *total);
 
 /* ---- reading the composer back in the reference's representation --------------------------------------------------- */
 int pg_counts(const pg_ctx *ctx, uint64_t *n_rows, uint64_t *n_vars);        /* composer.circuit_size(), variables.len() */

@@ -34,11 +34,19 @@ class pg_timing(C.Structure):
                 ("check_rows", C.c_uint64)]
 
 
+class pg_op(C.Structure):
+    _fields_ = [("gadget", C.c_uint32), ("num_bits", C.c_uint32), ("n", C.c_uint64), ("group", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class pg_op_shard(C.Structure):
+    _fields_ = [("inst_lo", C.c_uint64), ("inst_hi", C.c_uint64), ("row_base", C.c_uint64), ("var_base", C.c_uint64)]
+
+
 class pg_check_stats(C.Structure):
     _fields_ = [("launches", C.c_uint64 * 8), ("rows", C.c_uint64 * 8)]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/pg_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _i32, _u32 = C.c_void_p, C.c_uint64, C.c_int, C.c_uint32
@@ -64,6 +72,14 @@ SIGNATURES = {
     "pg_check": (_i32, [_vp, _pu64, _pu64]),
     "pg_check_rows": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _pu64, _pu64]),
     "pg_check_rows_ex": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _pu64, _pu64]),
+    "pg_op_shape": (_i32, [_u32, _u32, _pu64, _pu64]),
+    "pg_shard_plan": (_i32, [C.POINTER(pg_op), _u64, _u32, _i32, C.POINTER(pg_op_shard)]),
+    "pg_comm_unique_id": (_i32, [_vp]),
+    "pg_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
+    "pg_comm_destroy": (_i32, [_vp]),
+    "pg_check_sharded": (_i32, [_vp, C.POINTER(pg_op_shard), _u64, _pu64, _pu64, _pu64]),
+    "pg_gather_column": (_i32, [_vp, _u64, _vp, _u64, _i32, _pu64, _pu64]),
+    "pg_gather_variables": (_i32, [_vp, _u64, _vp, _u64, _i32, _pu64]),
     "pg_poke_variable": (_i32, [_vp, _u64, _vp]),
     "pg_counts": (_i32, [_vp, _pu64, _pu64]),
     "pg_col_info": (_i32, [_vp, _u64, _pu64, _pu64, _pu64]),

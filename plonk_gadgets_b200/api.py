@@ -30,6 +30,42 @@ F_TIMING = 1
 UINT64_MAX = 2 ** 64 - 1
 
 
+COMM_ID_BYTES = 128
+OP_ADD_INPUT, OP_RANGE_CHECK, OP_MAX_BOUND, OP_MAYBE_EQUAL, OP_IS_NON_ZERO, OP_SELECT_ZERO, OP_SELECT_ONE, OP_CONSTRAIN, OP_RANGE_GATE = range(9)
+SHARD_EVEN, SHARD_ROWS = 0, 1
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0 calls it and hands the 128 bytes to the other ranks)."""
+    L = _lib.load()
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    if L.pg_comm_unique_id(buf) != 0:
+        raise RuntimeError("pg_comm_unique_id failed (NCCL not loadable?)")
+    return bytes(buf)
+
+
+def op_shape(gadget: int, num_bits: int = 0):
+    """(rows, variables) one instance of the gadget appends."""
+    L = _lib.load()
+    r, v = C.c_uint64(), C.c_uint64()
+    if L.pg_op_shape(gadget, num_bits, C.byref(r), C.byref(v)) != 0:
+        raise ValueError("unknown gadget / num_bits")
+    return r.value, v.value
+
+
+def shard_plan(ops, world: int, policy: int = SHARD_EVEN, _cdll=None):
+    """ops: list of (gadget, num_bits, n, group).  Returns plan[rank][k] = pg_op_shard(inst_lo, inst_hi, row_base, var_base): what
+    `rank` runs of call k and where it sits in the sequential composer (pure host code, no GPU needed)."""
+    L = _cdll if _cdll is not None else _lib.load()
+    n = len(ops)
+    arr = (_lib.pg_op * n)(*[_lib.pg_op(g, k, cnt, grp, 0) for (g, k, cnt, grp) in ops])
+    out = (_lib.pg_op_shard * (n * world))()
+    rc = L.pg_shard_plan(arr, n, world, policy, out)
+    if rc != 0:
+        raise ValueError(f"pg_shard_plan: {L.pg_strerror(rc).decode()}")
+    return [[out[r * n + k] for k in range(n)] for r in range(world)]
+
+
 class Error(Exception):
     """Gadget errors (/root/reference/src/errors.rs:13-18)."""
 
@@ -188,6 +224,47 @@ class StandardComposer:
         bad, first = C.c_uint64(), C.c_uint64()
         self._ok(self._L.pg_check(self._ctx, C.byref(bad), C.byref(first)), "pg_check")
         return bad.value, (None if first.value == UINT64_MAX else first.value)
+
+    # -- multi-GPU: communicator, sharded verdict, gathers (include/pg_b200.h "multi-GPU")
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Joins the communicator of the box's ranks (collective).  unique_id: comm_unique_id() of rank 0, handed over out of band."""
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique_id must be COMM_ID_BYTES long")
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._ok(self._L.pg_comm_init(self._ctx, buf, rank, world), "pg_comm_init")
+
+    def comm_destroy(self):
+        self._ok(self._L.pg_comm_destroy(self._ctx), "pg_comm_destroy")
+
+    def check_sharded(self, mine=None, n_err: int = 0):
+        """pg_check of this rank's shard + all-reduce: (n_unsat, first bad row in the sequential composer's numbering or None, n_err)
+        of the WHOLE circuit.  mine: this rank's row of shard_plan(...) (list of pg_op_shard) or None."""
+        bad, first, err = C.c_uint64(), C.c_uint64(), C.c_uint64(n_err)
+        arr, n_ops = None, 0
+        if mine is not None:
+            n_ops = len(mine)
+            arr = (_lib.pg_op_shard * n_ops)(*mine)
+        self._ok(self._L.pg_check_sharded(self._ctx, arr, n_ops, C.byref(bad), C.byref(first), C.byref(err)), "pg_check_sharded")
+        return bad.value, (None if first.value == UINT64_MAX else first.value), err.value
+
+    def gather_column(self, v: "Variables", out=None):
+        """All-gather of a column: (values of all ranks' shards in rank order, per-rank counts).  out: optional device tensor / DevicePtr."""
+        world = 64
+        counts = (C.c_uint64 * world)()
+        total = C.c_uint64()
+        if out is None:
+            # two-step: learn the total with a zero-capacity call would be a collective of its own; callers without `out` pass through host memory sized by the caller's knowledge
+            raise ValueError("gather_column needs a destination (host array or device tensor) sized for all ranks")
+        p, dev, n, keep = _scalars(out)
+        self._ok(self._L.pg_gather_column(self._ctx, v.col, p, n, dev, counts, C.byref(total)), "pg_gather_column")
+        return total.value, [int(x) for x in counts]
+
+    def gather_variables(self, call: int, out):
+        """Gather of witness shards: the Variables of call `call` from all ranks, in the sequential composer's order.  Returns the total."""
+        total = C.c_uint64()
+        p, dev, n, keep = _scalars(out)
+        self._ok(self._L.pg_gather_variables(self._ctx, call, p, n, dev, C.byref(total)), "pg_gather_variables")
+        return total.value
 
     # -- read-back in the reference's representation
     def read_column(self, v: Variables, i0: int = 0, cnt: int | None = None) -> np.ndarray:

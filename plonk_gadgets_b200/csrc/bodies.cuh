@@ -447,27 +447,68 @@ PG_HD void sp_row_init(uint32_t* t) {
     t[5] = 0x6694e838u; t[6] = 0x234e6cf9u; t[7] = 0x2b7f9346u; t[8] = 0x00000003u;
 }
 struct SparseProgBody {
+    // SP_CHAIN (layout.h): L rows  sel_j * bit_j + x_j - x_{j+1} = 0.  Four loads of x in flight; x_{j+1} is the next row's x_j.
+    template <class PoolT>
+    PG_HD static void run_chain(const CheckArgs& a, const SpOp& c0, const SpOp& c1, const SpOp& c2, const PoolT& pool, uint64_t i,
+                                uint32_t& bad, unsigned long long& first_bad, uint32_t& r) {
+        const uint32_t L = c1.sel, rows_per = c1.sh;
+        const uint64_t slot_step = c2.addr >> 4;                     // in uint4 units; bit words: >> 5 (u32 units of an eighth of the distance)
+        const uint4* px = reinterpret_cast<const uint4*>(c0.addr) + 2 * i;
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(c1.addr) + i;
+        const uint64_t word_step = c2.addr >> 5;
+        uint32_t left = 32u - c0.sh;                                 // bits of the current word not yet consumed
+        uint32_t word = *pw >> c0.sh, word_next = 0;
+        if (L > left) { pw += word_step; word_next = *pw; }
+        Fr prev = ld256(px);
+        for (uint32_t j = 0; j < L; j += 4) {
+            Fr nx[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) if (j + u < L) nx[u] = ld256(px + (uint64_t)(j + u + 1) * slot_step);
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+                if (j + u >= L) break;
+                const uint32_t m = 0u - (word & 1u);
+                word >>= 1;
+                if (--left == 0) {                                   // next word (loaded one word ahead)
+                    word = word_next; left = 32;
+                    if (L - (j + u + 1) > 32u) { pw += word_step; word_next = *pw; }
+                }
+                Fr t = pool(c0.sel + j + u);
+#pragma unroll
+                for (int k = 0; k < 8; k++) t.v[k] &= m;
+                if (!fr_sum_equals(prev, t, nx[u])) {
+                    bad++;
+                    const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r + (j + u) * rows_per + (rows_per - 1u);
+                    if (g < first_bad) first_bad = g;
+                }
+                prev = nx[u];
+            }
+        }
+        r += L * rows_per;
+    }
+
     template <class PoolT>
     PG_HD static uint32_t run(const CheckArgs& a, const SparseProg& prog, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t t[9];
         sp_row_init(t);
         uint32_t mask = ~0u, bad = 0, r = 0;
-        // The product register of the multiplication chain lives in local memory (volatile: not promoted): it is touched by the few
-        // operations that multiply, and as a loop-carried register value it cost eight register moves on EVERY operation.
-        volatile uint32_t vmem[8];
-        auto get_v = [&]() { Fr r; for (int k = 0; k < 8; k++) r.v[k] = vmem[k]; return r; };
-        auto set_v = [&](const Fr& r) { for (int k = 0; k < 8; k++) vmem[k] = r.v[k]; };
-        set_v(fr_zero());
+        Fr v = fr_zero();                                            // product register of the multiplication chain (a handful of operations per instance use it)
 #pragma unroll 1
         for (uint32_t j = 0; j < prog.n; j++) {
             const SpOp op = sp_fetch(prog.ops, j);
 #if defined(__CUDA_ARCH__)
             if (j + SP_AHEAD < prog.n) {
                 const SpOp nx = sp_fetch(prog.ops, j + SP_AHEAD);
-                if (nx.addr) asm volatile(PG_SP_PREFETCH ::"l"(nx.addr + i * nx.stride));
+                if (nx.addr && nx.stride) asm volatile(PG_SP_PREFETCH ::"l"(nx.addr + i * nx.stride));
             }
 #endif
             const uint32_t code = op.op & 0x7fu;
+            if (code == SP_CHAIN) {
+                const SpOp c1 = sp_fetch(prog.ops, j + 1), c2 = sp_fetch(prog.ops, j + 2);
+                run_chain(a, op, c1, c2, pool, i, bad, first_bad, r);
+                j += 2;
+                continue;
+            }
             if (code <= SP_BITSEL) {                                // the operations range rows are made of: no multiplication, `v` untouched
                 switch (code) {
                     case SP_ADD_FR: add9_fr(t, ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
@@ -484,17 +525,17 @@ struct SparseProgBody {
                 bool mul = false;
                 switch (code) {
                     case SP_MUL_SEL_FR: x = pool(op.sel); y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
-                    case SP_LOAD_FR: set_v(ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i)); break;
-                    case SP_MUL_FR: x = get_v(); y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
-                    case SP_MULSEL_V: x = pool(op.sel); y = get_v(); mul = true; break;
-                    case SP_ADD_V: { const Fr v = get_v(); CheckBody::masked_add(t, op.sh ? fr_neg(v) : v, mask); mask = ~0u; } break;
+                    case SP_LOAD_FR: v = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); break;
+                    case SP_MUL_FR: x = v; y = ld256(reinterpret_cast<const uint4*>(op.addr) + 2 * i); mul = true; break;
+                    case SP_MULSEL_V: x = pool(op.sel); y = v; mul = true; break;
+                    case SP_ADD_V: { CheckBody::masked_add(t, op.sh ? fr_neg(v) : v, mask); mask = ~0u; } break;
                     case SP_ADD_POOL: add9_fr(t, pool(op.sel)); break;
                     case SP_TRIVIAL: r += op.stride; break;         // `stride` consecutive rows that hold for every witness
                     default: break;
                 }
                 if (mul) {                                          // the one multiplier site
                     const Fr p = fr_mul_eo(x, y, q);
-                    if (code == SP_MUL_SEL_FR) add9_fr(t, p); else set_v(p);
+                    if (code == SP_MUL_SEL_FR) add9_fr(t, p); else v = p;
                 }
             }
             if ((op.op & SP_ROW_END) || op.op == SP_END) {          // the row is complete

@@ -95,6 +95,24 @@ int pg_check_rows_ex(pg_ctx* ctx, uint64_t n, const pg_fr* w_val, const pg_fr* s
     PG_ALIGNED(ctx, q_arith, on_device); PG_ALIGNED(ctx, q_range, on_device);
     PG_TRY(ctx, ctx->e.check_rows(n, w_val, sel, pi, on_device, n_unsat, first_bad_row, q_arith, q_range));
 }
+int pg_op_shape(uint32_t gadget, uint32_t num_bits, uint64_t* rows, uint64_t* vars) { return pg::op_shape(gadget, num_bits, rows, vars) ? PG_OK : PG_ERR_ARG; }
+int pg_shard_plan(const pg_op* ops, uint64_t n_ops, uint32_t world, int policy, pg_op_shard* out) {
+    try { return pg::shard_plan(ops, n_ops, world, policy, out); } catch (...) { return PG_ERR_STATE; }
+}
+int pg_comm_unique_id(uint8_t* id) { return id && PG_BACKEND::comm_unique_id(id) ? PG_OK : PG_ERR_CUDA; }
+int pg_comm_init(pg_ctx* ctx, const uint8_t* id, uint32_t rank, uint32_t world) { PG_NEED_CTX(ctx); PG_TRY(ctx, ctx->e.comm_init(id, rank, world)); }
+int pg_comm_destroy(pg_ctx* ctx) { PG_NEED_CTX(ctx); ctx->e.be.sync(); ctx->e.be.comm_destroy(); return PG_OK; }
+int pg_check_sharded(pg_ctx* ctx, const pg_op_shard* mine, uint64_t n_ops, uint64_t* n_unsat, uint64_t* first_bad_row, uint64_t* n_err) {
+    PG_NEED_CTX(ctx); PG_TRY(ctx, ctx->e.check_sharded(mine, n_ops, n_unsat, first_bad_row, n_err));
+}
+int pg_gather_column(pg_ctx* ctx, pg_col col, pg_fr* dst, uint64_t capacity, int dst_on_device, uint64_t* counts, uint64_t* total) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device);
+    PG_TRY(ctx, ctx->e.gather_column(col, dst, capacity, dst_on_device, counts, total));
+}
+int pg_gather_variables(pg_ctx* ctx, uint64_t call, pg_fr* dst, uint64_t capacity, int dst_on_device, uint64_t* total) {
+    PG_NEED_CTX(ctx); PG_ALIGNED(ctx, dst, dst_on_device);
+    PG_TRY(ctx, ctx->e.gather_variables(call, dst, capacity, dst_on_device, total));
+}
 int pg_poke_variable(pg_ctx* ctx, uint64_t var, const pg_fr* value) { PG_NEED_CTX(ctx); PG_TRY(ctx, ctx->e.poke_variable(var, value)); }
 int pg_counts(const pg_ctx* ctx, uint64_t* n_rows, uint64_t* n_vars) {
     PG_NEED_CTX(ctx);

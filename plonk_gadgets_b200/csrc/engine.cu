@@ -10,6 +10,7 @@
 #include <cub/device/device_scan.cuh>
 #include "engine.hpp"
 #include "kernels.cuh"
+#include "comm.cuh"
 
 namespace pg {
 
@@ -90,6 +91,8 @@ public:
         for (auto& ev : ev_free) cudaEventDestroy(ev);
         events.clear(); ev_free.clear();
         if (sort_tmp) { cudaFree(sort_tmp); sort_tmp = nullptr; sort_tmp_bytes = 0; }
+        comm.destroy();
+        if (d_verdict) { cudaFree(d_verdict); d_verdict = nullptr; }
         for (auto& pc : pending) cudaEventDestroy(pc.ev);
         for (auto& ev : sync_ev_free) cudaEventDestroy(ev);
         pending.clear(); sync_ev_free.clear();
@@ -350,6 +353,45 @@ public:
         k_check_rows<<<grid_for(a.n), BLOCK, 0, stream>>>(a);
         toc();
         return launched("k_check_rows");
+    }
+    // ---- collectives (comm.cuh); without a communicator: a world of one rank, no NCCL ----------------------------------------------
+    Comm comm;
+    unsigned long long* d_verdict = nullptr;
+    const char* comm_error() const { return comm.err[0] ? comm.err : errbuf; }
+    int comm_rank() const { return comm.rank; }
+    int comm_world() const { return comm.world; }
+    static bool comm_unique_id(uint8_t* id) {
+        NcclApi& api = nccl_api();
+        if (const char* e = api.load()) { fprintf(stderr, "pg_comm_unique_id: %s\n", e); return false; }
+        ncclUniqueId uid;
+        if (api.GetUniqueId(&uid) != ncclSuccess) return false;
+        memcpy(id, &uid, sizeof(uid));
+        return true;
+    }
+    bool comm_init(const uint8_t* id, int rank, int world) { join_copies(); if (comm.active()) comm.destroy(); return comm.init(id, rank, world); }
+    void comm_destroy() { comm.destroy(); }
+    bool comm_verdict(const unsigned long long* d_counters, unsigned long long n_err, unsigned long long out[4]) {
+        join_copies();
+        if (comm.active()) return comm.allreduce_verdict(d_counters, n_err, out, stream);
+        if (!d_verdict) PG_CUDA(cudaMalloc(&d_verdict, 4 * sizeof(unsigned long long)));
+        k_verdict_pack<<<1, 1, 0, stream>>>(d_counters, n_err, d_verdict);
+        PG_CUDA(cudaMemcpyAsync(out, d_verdict, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        return true;
+    }
+    bool comm_counts(unsigned long long mine, unsigned long long* counts) {
+        join_copies();
+        if (comm.active()) return comm.allgather_u64(mine, counts, stream);
+        counts[0] = mine;
+        return true;
+    }
+    bool comm_gather(const void* send, void* recv, const unsigned long long* counts) {
+        tic(CLS_OTHER, 0);
+        bool ok = true;
+        if (comm.active()) ok = comm.allgather_ragged(send, recv, counts, stream);
+        else if (cudaMemcpyAsync(recv, send, (size_t)counts[0] * 32, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) { snprintf(errbuf, sizeof(errbuf), "gather copy"); ok = false; }
+        toc();
+        return ok;
     }
     template <int MODE>
     void ubench_launch(uint32_t* buf, int blocks, int iters, int rep) { k_ubench<MODE><<<blocks, BLOCK, 0, stream>>>(buf, 12345u + rep, 0x9e3779b1u, iters); }

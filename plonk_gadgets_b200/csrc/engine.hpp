@@ -28,6 +28,7 @@
 #include <vector>
 #include "../../include/pg_b200.h"
 #include "templates.hpp"
+#include "shard.hpp"
 #include "ntt.cuh"
 #include "msm.cuh"
 
@@ -239,6 +240,57 @@ public:
             if (out.size() > row_start) { out.back().op |= SP_ROW_END; continue; }
             if (!out.empty() && out.back().op == SP_TRIVIAL) out.back().stride++;      // `stride` of SP_TRIVIAL counts the rows (no memory operand: addr = 0)
             else out.push_back(mem(SP_TRIVIAL, 0, 1, 0, 0));
+        }
+        fold_chains(s);
+    }
+    // Peephole pass over the compiled program: runs of  [TRIVIAL(t)] ADD_FR(x_j) SUB_FR(x_{j+1}) BITSEL|ROW_END(bit_j, sel_j)  with consecutive
+    // scalar slots and consecutive packed bits become one SP_CHAIN (layout.h).  Purely structural: nothing is assumed about the gadget
+    // that produced the rows.  The L selectors are copied into a contiguous run of the pool (shared by chains with the same selectors).
+    static void fold_chains(Segment& s) {
+        const std::vector<SpOp> in = s.sp_ops;
+        std::vector<SpOp>& out = s.sp_ops; out.clear();
+        const uint64_t slot_step = (uint64_t)s.n_alloc * 32, word_step = (uint64_t)s.n_alloc * 4;
+        std::vector<std::pair<std::vector<uint16_t>, uint16_t>> runs;          // selector lists already copied -> first pool index
+        auto elem = [&](size_t p, uint32_t& triv) -> bool {                     // does a chain element start at p?  (4 operations, or 3 without leading trivial rows)
+            triv = 0;
+            if (p < in.size() && in[p].op == SP_TRIVIAL) { triv = in[p].stride; p++; }
+            return p + 2 < in.size() && in[p].op == SP_ADD_FR && in[p + 1].op == SP_SUB_FR && in[p + 2].op == (SP_BITSEL | SP_ROW_END) &&
+                   in[p].stride == 32 && in[p + 1].addr == in[p].addr + slot_step;
+        };
+        size_t p = 0;
+        while (p < in.size()) {
+            uint32_t triv = 0;
+            if (!elem(p, triv) || triv + 1 > 255) { out.push_back(in[p++]); continue; }
+            // extend the run
+            const size_t width = triv ? 4 : 3;
+            size_t L = 1, e = p;
+            std::vector<uint16_t> sels;
+            auto at = [&](size_t k, int which) -> const SpOp& { return in[p + k * width + (triv ? 1 : 0) + which]; };
+            sels.push_back(at(0, 2).sel);
+            while (L < 256) {
+                uint32_t t2 = 0;
+                if (!elem(p + L * width, t2) || t2 != triv) break;
+                const SpOp &prev_bit = at(L - 1, 2), &bit = at(L, 2);
+                const bool next_bit = (bit.addr == prev_bit.addr && bit.sh == prev_bit.sh + 1) || (prev_bit.sh == 31 && bit.sh == 0 && bit.addr == prev_bit.addr + word_step);
+                if (!next_bit || at(L, 0).addr != at(L - 1, 1).addr) break;
+                sels.push_back(bit.sel);
+                L++;
+            }
+            (void)e;
+            if (L < SP_CHAIN_MIN || s.t.pool.size() + L > 2000) { out.push_back(in[p++]); continue; }
+            uint16_t first = 0xffff;
+            for (auto& kv : runs) if (kv.first.size() >= L && std::equal(sels.begin(), sels.end(), kv.first.begin())) { first = kv.second; break; }
+            if (first == 0xffff) {
+                first = (uint16_t)s.t.pool.size();
+                for (uint16_t si : sels) { const Fr c = s.t.pool[si]; s.t.pool.push_back(c); }
+                runs.push_back({sels, first});
+            }
+            SpOp c0, c1, c2;
+            c0.addr = at(0, 0).addr; c0.stride = 32; c0.sel = first; c0.op = SP_CHAIN; c0.sh = at(0, 2).sh;
+            c1.addr = at(0, 2).addr; c1.stride = 4; c1.sel = (uint16_t)L; c1.op = SP_CHAIN_AUX; c1.sh = (uint8_t)(triv + 1);
+            c2.addr = slot_step; c2.stride = 0; c2.sel = 0; c2.op = SP_CHAIN_AUX; c2.sh = 0;
+            out.push_back(c0); out.push_back(c1); out.push_back(c2);
+            p += L * width;
         }
     }
     // Appends a segment of n instances of template t whose operands are the given columns.  Allocates the variable
@@ -650,16 +702,20 @@ public:
     }
 
     // ------------------------------------------------------------------------------------------------ verdict
-    int check(uint64_t* n_unsat, uint64_t* first_bad) {
-        int rc = reset_counters();
-        if (rc) return rc;
-        for (const Segment& s : segs) {
+    // Enqueues the gate check of every segment.  `mine` != nullptr (sharded composer, see shard.hpp): segment k + 1 is this rank's
+    // part of call k of the whole circuit, and its rows are numbered from mine[k].row_base -- their indices in the SEQUENTIAL
+    // composer -- so that the first bad row needs no translation before the all-reduce; the fresh composer's three rows exist on
+    // every rank and are checked by rank 0 only.
+    int enqueue_checks(const pg_op_shard* mine = nullptr, bool with_preamble = true) {
+        for (size_t k = 0; k < segs.size(); k++) {
+            const Segment& s = segs[k];
             if (!s.n_inst || s.t.rows.empty()) continue;
+            if (mine && k == 0 && !with_preamble) continue;
             CheckArgs a; memset(&a, 0, sizeof(a));
-            for (int k = 0; k < MAX_TABS; k++) a.tab[k] = s.tabs[k];
+            for (int j = 0; j < MAX_TABS; j++) a.tab[j] = s.tabs[j];
             a.param = s.param; a.param_stride = s.n_alloc; a.rows = s.d_rows; a.pool = s.d_pool;
             a.n_rows = (uint32_t)s.t.rows.size(); a.n_pool = (uint32_t)s.t.pool.size();
-            a.n_inst = s.n_inst; a.base_row = s.base_row; a.counters = d_counters; a.mode = cfg.check_mode;
+            a.n_inst = s.n_inst; a.base_row = (mine && k > 0) ? mine[k - 1].row_base : s.base_row; a.counters = d_counters; a.mode = cfg.check_mode;
             if (s.other_gates) {                     // rows of the range widget: per-row body, one thread per (row, instance)
                 if (!be.run_check_gates(a)) return fail(PG_ERR_CUDA, "gate-check kernel (range rows)");
                 continue;
@@ -667,11 +723,101 @@ public:
             const SparseProg prog{s.d_sp, (uint32_t)s.sp_ops.size()};
             if (!be.run_check(a, prog)) return fail(PG_ERR_CUDA, "gate-check kernel");
         }
+        return PG_OK;
+    }
+    int check(uint64_t* n_unsat, uint64_t* first_bad) {
+        int rc = reset_counters();
+        if (rc) return rc;
+        if ((rc = enqueue_checks())) return rc;
         unsigned long long c[CNT_WORDS];
         if ((rc = read_counters(c))) return rc;
         if (n_unsat) *n_unsat = c[CNT_UNSAT];
         if (first_bad) *first_bad = c[CNT_FIRST_BAD];
         return PG_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------------ multi-GPU
+    // One process (and one ctx) per GPU; the communicator spans the ranks of one box.  Without pg_comm_init the calls below act as
+    // a world of one rank (no NCCL is loaded).
+    int comm_init(const uint8_t* id, uint32_t rank, uint32_t world) {
+        if (!id || !world || rank >= world) return fail(PG_ERR_ARG, "comm_init: bad rank / world / id");
+        if (!be.comm_init(id, (int)rank, (int)world)) return fail(PG_ERR_CUDA, std::string("comm_init: ") + be.comm_error());
+        return PG_OK;
+    }
+    // pg_check of a sharded composer + the all-reduce of the verdict: every rank returns the verdict of the whole circuit.
+    // *n_err (in: this rank's NonExistingInverse count, out: the sum) may be null.
+    int check_sharded(const pg_op_shard* mine, uint64_t n_ops, uint64_t* n_unsat, uint64_t* first_bad, uint64_t* n_err) {
+        if (mine && n_ops + 1 != segs.size()) return fail(PG_ERR_STATE, "check_sharded: the composer must hold exactly one segment per planned call");
+        if (mine) for (uint64_t k = 0; k < n_ops; k++)
+            if (mine[k].inst_hi - mine[k].inst_lo != segs[k + 1].n_inst) return fail(PG_ERR_ARG, "check_sharded: a call's instance count differs from its planned range");
+        int rc = reset_counters();
+        if (rc) return rc;
+        if ((rc = enqueue_checks(mine, be.comm_rank() == 0))) return rc;
+        unsigned long long v[4];
+        if (!be.comm_verdict(d_counters, n_err ? *n_err : 0ull, v)) return fail(PG_ERR_CUDA, std::string("verdict all-reduce: ") + be.comm_error());
+        validation_pending = false;
+        if (v[3]) return fail(PG_ERR_ARG, "input scalar(s) not fully reduced (>= q) on some rank: reset the composers");
+        if (n_unsat) *n_unsat = v[0];
+        if (n_err) *n_err = v[1];
+        if (first_bad) *first_bad = v[2];
+        return PG_OK;
+    }
+    // shards of a ragged all-gather, 32-byte units: `d_send` (mine units) -> dst (all ranks' shards in rank order)
+    int gather_units(const uint4* d_send, uint64_t mine, pg_fr* dst, uint64_t capacity, int dst_on_device, uint64_t* counts_out, uint64_t* total_out) {
+        const uint32_t world = (uint32_t)be.comm_world();
+        std::vector<unsigned long long> counts(world);
+        if (!be.comm_counts(mine, counts.data())) return fail(PG_ERR_CUDA, std::string("gather (counts): ") + be.comm_error());
+        uint64_t total = 0;
+        for (uint32_t g = 0; g < world; g++) { total += counts[g]; if (counts_out) counts_out[g] = counts[g]; }
+        if (total_out) *total_out = total;
+        if (total > capacity) return fail(PG_ERR_ARG, "gather: destination too small for the shards of all ranks");
+        if (!total) return PG_OK;
+        if (!dst) return fail(PG_ERR_ARG, "gather: null destination");
+        const size_t mark = scratch.size();
+        uint4* recv = dst_on_device ? reinterpret_cast<uint4*>(dst) : (uint4*)dalloc(total * sizeof(pg_fr));
+        if (!recv) return fail(PG_ERR_OOM, "gather buffer");
+        if (!dst_on_device) scratch.push_back(recv);
+        if (!be.comm_gather(d_send, recv, counts.data())) return fail(PG_ERR_CUDA, std::string("gather: ") + be.comm_error());
+        if (dst_on_device) return PG_OK;
+        const int rc = deliver(dst, recv, total * sizeof(pg_fr), 0);
+        release_scratch_from(mark);
+        return rc;
+    }
+    // all-gather of a column (the per-instance results of a call): every rank receives the shards of all ranks, in rank order
+    int gather_column(pg_col c, pg_fr* dst, uint64_t capacity, int dst_on_device, uint64_t* counts_out, uint64_t* total_out) {
+        const Column* col = column(c);
+        if (!col) return fail(PG_ERR_ARG, "gather_column: unknown column");
+        const uint64_t n = col->n;
+        const size_t mark = scratch.size();
+        uint4* send = (uint4*)dalloc((n ? n : 1) * sizeof(pg_fr));
+        if (!send) return fail(PG_ERR_OOM, "gather send buffer");
+        scratch.push_back(send);
+        if (n) {
+            ColReadBody::Args a{view_of(*col), loc_with_tab(loc_of(*col), 0), send, n};
+            if (!be.template run_simple<ColReadBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "col_read kernel");
+        }
+        const int rc = gather_units(send, n, dst, capacity, dst_on_device, counts_out, total_out);
+        release_scratch_from(mark);                  // only touched by work on the engine's stream: stream order makes its reuse safe
+        return rc;
+    }
+    // gather of witness shards: the Variables call `call` (0-based since the reset) appended on every rank, in the sequential
+    // composer's Variable order (instance-major; ranks hold consecutive instance ranges, so rank order is instance order)
+    int gather_variables(uint64_t call, pg_fr* dst, uint64_t capacity, int dst_on_device, uint64_t* total_out) {
+        if (call + 1 >= segs.size()) return fail(PG_ERR_ARG, "gather_variables: no such call");
+        const Segment& s = segs[call + 1];
+        const uint64_t cnt = s.n_inst * (uint64_t)s.t.n_vars;
+        if (cnt) { const int rcs = sync_dsegs(); if (rcs) return rcs; }      // (may park the old segment table in `scratch`: before the mark)
+        const size_t mark = scratch.size();
+        uint4* send = (uint4*)dalloc((cnt ? cnt : 1) * sizeof(pg_fr));
+        if (!send) return fail(PG_ERR_OOM, "gather send buffer");
+        scratch.push_back(send);
+        if (cnt) {
+            ReadVarsBody::Args a{d_segs, (uint32_t)dsegs.size(), s.base_var, cnt, send};
+            if (!be.template run_simple<ReadVarsBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "read_variables kernel");
+        }
+        const int rc = gather_units(send, cnt, dst, capacity, dst_on_device, nullptr, total_out);
+        release_scratch_from(mark);
+        return rc;
     }
     int check_rows(uint64_t n, const pg_fr* w, const pg_fr* sel, const pg_fr* pi, int on_device, uint64_t* n_unsat, uint64_t* first_bad,
                    const pg_fr* q_arith = nullptr, const pg_fr* q_range = nullptr) {

@@ -533,6 +533,27 @@ PG_HD Fr fr_add_noreduce(const Fr& a, const Fr& b) {
 #endif
     return r;
 }
+// a + t == b (mod q) for a, t, b < q, without reducing anything: s = a + t < 2q < 2^256, and s - b lies in (-q, 2q), so the
+// congruence holds iff the 256-bit difference does not borrow and equals 0 or q (q0 = 1: the low limb tells which).
+PG_HD bool fr_sum_equals(const Fr& a, const Fr& t, const Fr& b) {
+    const Fr s = fr_add_noreduce(a, t);
+    uint32_t d[8], bw;
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7]), "=&r"(bw)
+        : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+#else
+    bw = fr_sub_limbs(d, s.v, b.v);
+#endif
+    const uint32_t m = 0u - d[0];                      // d[0] == 1: all ones (compare with q); d[0] == 0: zero (compare with 0)
+    uint32_t diff = bw | (d[0] >> 1);
+    diff |= d[1] ^ (PG_Q1 & m); diff |= d[2] ^ (PG_Q2 & m); diff |= d[3] ^ (PG_Q3 & m); diff |= d[4] ^ (PG_Q4 & m);
+    diff |= d[5] ^ (PG_Q5 & m); diff |= d[6] ^ (PG_Q6 & m); diff |= d[7] ^ (PG_Q7 & m);
+    return diff == 0;
+}
 // k*q for k = 0..15 (9 limbs each): since q0 = 1, k*q = k (mod 2^32), so a 9-limb r is 0 mod q iff r == k*q for k = r[0] (r < 16q)
 PG_HD bool limbs9_is_multiple_of_q(const uint32_t* r) {
     const uint32_t k = r[0];

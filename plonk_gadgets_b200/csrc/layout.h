@@ -69,8 +69,16 @@ enum : uint16_t { GATE_ARITH = 0, GATE_RANGE = 1, GATE_NONE = 2 };
 // the operand, `stride` its size per instance (32: scalar, 4: word of packed bits, 0: no memory operand).
 // Flag SP_ROW_END on an operation: the row is complete after it (test the sum, next row).  SP_TRIVIAL: a row whose folded
 // polynomial is identically zero (e.g. b*b - b on a packed bit variable): nothing to evaluate, only the row counter moves.
+// SP_CHAIN (+ two SP_CHAIN_AUX words): a run of L rows of the shape  sel_j * bit_j + x_j - x_{j+1} = 0  over consecutive scalar slots
+// x_0 .. x_L and consecutive packed bits -- the accumulator rows of a bit decomposition (range.rs:146-152) -- found in the compiled
+// program by build_sparse_program and executed as one tight loop: x_{j+1} stays in registers as the next row's x_j (one 32-byte load
+// per row), four loads in flight per thread, no per-row program fetch.
+//   word 0: addr = x_0 of instance 0, stride 32, sel = first index of the L selectors (a contiguous run of the pool), sh = bit position of bit_0
+//   word 1: addr = the 32-bit word holding bit_0 (instance 0), stride 4, sel = L, sh = rows per element (trivially-true rows that precede each chain row + 1)
+//   word 2: addr = distance in bytes between consecutive scalar slots (n_alloc * 32; bit words are an eighth of that apart), stride 0
 enum : uint8_t { SP_END = 0, SP_ADD_FR, SP_SUB_FR, SP_MASK, SP_BITSEL, SP_MUL_SEL_FR, SP_LOAD_FR, SP_MUL_FR, SP_MULSEL_V, SP_ADD_V, SP_ADD_POOL, SP_TRIVIAL,
-                 SP_ROW_END = 0x80 };
+                 SP_CHAIN, SP_CHAIN_AUX, SP_ROW_END = 0x80 };
+constexpr uint32_t SP_CHAIN_MIN = 4;      // shorter runs stay ordinary operations
 struct SpOp { uint64_t addr; uint32_t stride; uint16_t sel; uint8_t op; uint8_t sh; };
 static_assert(sizeof(SpOp) == 16, "SpOp must stay 16 bytes");
 

@@ -107,3 +107,50 @@ def allgather_witness_shards(local_vars, call_sizes):
             parts.append(sh[offs[r]: offs[r] + cnt])
             offs[r] += cnt
     return torch.cat(parts, dim=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Mixed circuits over several GPUs through the C ABI (pg_shard_plan / pg_check_sharded / pg_gather_*; include/pg_b200.h).
+# A circuit is a list of calls; call k is a dict
+#     {"gadget": OP_*, "n": instances, "group": g, "num_bits": k (range gadgets), ...operands}
+# with operands naming EARLIER calls by index ("witness", "a", "b", "x", "select", "var") or carrying data (n scalars:
+# "values", "assigned", "constant"; one scalar: "min", "max").  Calls of one group share the instance index space.
+def plan_of(circuit, world: int, policy: int = 0, _cdll=None):
+    import plonk_gadgets_b200 as pg
+    return pg.shard_plan([(c["gadget"], c.get("num_bits", 0), c["n"], c["group"]) for c in circuit], world, policy, _cdll=_cdll)
+
+
+def run_circuit(composer, circuit, mine=None):
+    """Replays `circuit` on `composer`; with `mine` (this rank's row of the plan) only instances [inst_lo, inst_hi) of every call.
+    Returns (per-call results: Variables or None, local NonExistingInverse count)."""
+    import plonk_gadgets_b200 as pg
+    out, n_err = [], 0
+    for k, c in enumerate(circuit):
+        lo, hi = (0, c["n"]) if mine is None else (mine[k].inst_lo, mine[k].inst_hi)
+        cut = lambda x: x[lo:hi]
+        g = c["gadget"]
+        if g == pg.OP_ADD_INPUT:
+            out.append(composer.add_input(cut(c["values"])))
+        elif g == pg.OP_RANGE_CHECK:
+            out.append(pg.range_check(composer, c["min"], c["max"], out[c["witness"]]))
+        elif g == pg.OP_MAX_BOUND:
+            out.append(pg.max_bound(composer, c["max"], out[c["witness"]])[0])
+        elif g == pg.OP_MAYBE_EQUAL:
+            out.append(pg.maybe_equal(composer, out[c["a"]], out[c["b"]]))
+        elif g == pg.OP_IS_NON_ZERO:
+            pg.is_non_zero_flags(composer, out[c["var"]], cut(c["assigned"]), pg.NZ_UNIFORM)      # host or device scalars
+            n_err += composer.last_n_err
+            out.append(None)
+        elif g == pg.OP_SELECT_ZERO:
+            out.append(pg.conditionally_select_zero(composer, out[c["x"]], out[c["select"]]))
+        elif g == pg.OP_SELECT_ONE:
+            out.append(pg.conditionally_select_one(composer, out[c["x"]], out[c["select"]]))
+        elif g == pg.OP_CONSTRAIN:
+            composer.constrain_to_constant(out[c["a"]], cut(c["constant"]))
+            out.append(None)
+        elif g == pg.OP_RANGE_GATE:
+            composer.range_gate(out[c["witness"]], c["num_bits"])
+            out.append(None)
+        else:
+            raise ValueError(f"unknown gadget {g}")
+    return out, n_err

@@ -79,6 +79,16 @@ public:
         }
         return true;
     }
+    // a world of one rank (the collectives are GPU-side: comm.cuh)
+    const char* comm_error() const { return "the host backend has no communicator"; }
+    int comm_rank() const { return 0; }
+    int comm_world() const { return 1; }
+    static bool comm_unique_id(uint8_t*) { return false; }
+    bool comm_init(const uint8_t*, int, int) { return false; }
+    void comm_destroy() {}
+    bool comm_verdict(const unsigned long long* c, unsigned long long n_err, unsigned long long out[4]) { out[0] = c[CNT_UNSAT]; out[1] = n_err; out[2] = c[CNT_FIRST_BAD]; out[3] = c[CNT_BAD_INPUT]; return true; }
+    bool comm_counts(unsigned long long mine, unsigned long long* counts) { counts[0] = mine; return true; }
+    bool comm_gather(const void* send, void* recv, const unsigned long long* counts) { memcpy(recv, send, (size_t)counts[0] * 32); return true; }
     pg_check_stats ck{};
     void count_check(int kind, uint64_t rows) { ck.launches[kind]++; ck.rows[kind] += rows; }
     bool run_check(const CheckArgs& a, const SparseProg& prog) {
