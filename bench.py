@@ -190,7 +190,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=24, help="instances per GPU = 2^log2n (24 = the BASELINE metric configuration)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--check-mode", default="generic", choices=["generic", "sparse"])
+    ap.add_argument("--check-mode", default="generic", choices=["generic", "sparse", "fused"],
+                    help="generic: the headline (no selector inspected); sparse: structure-aware row program; fused: sparse + PG_F_FUSED_CHECK "
+                         "(rows evaluated inside witness generation, the table is never re-read)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check-shape", type=int, default=0, help="launch shape of the gate-check kernel (tuning knob)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 2^log2n instances per GPU; strong: 2^log2n in total")
@@ -215,7 +217,8 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     mode = pg.CHECK_GENERIC if args.check_mode == "generic" else pg.CHECK_SPARSE
-    c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream, check_shape=args.check_shape)
+    c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream, check_shape=args.check_shape,
+                            fused_check=args.check_mode == "fused")
     assert stream.cuda_stream != 0
     # sharding: the batch of n_total instances is cut by the C ABI's plan; this rank runs [inst_lo, inst_hi) and numbers its rows as
     # the sequential composer of the whole batch does
@@ -339,10 +342,14 @@ def main():
                                              "T_mac_per_s": rows_per_launch * IMAD_PER_ROW_DEFINITION / (check_ms * 1e-3) / 1e12},
                         "traffic": traffic, "traffic_source": traffic_src, "ms_per_launch": check_ms,
                         "hbm": hbm_obj("RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", wit_ms)}
-        else:
+        elif args.check_mode == "sparse":
             r = hbm_obj("k_check_prog (structure-aware row program: reads the packed variable table once)", check_ms)
             roofline = {"bound": "hbm", **r, "traffic": traffic, "traffic_source": traffic_src,
                         "hbm_witness": hbm_obj("RangePre + k_batch_inv + RangePost (witness generation, 3 launches)", wit_ms)}
+        else:
+            r = hbm_obj("RangePre<FUSED> + k_batch_inv + RangePost<FUSED>: witness generation that also evaluates its rows (table written once, "
+                        "never re-read for the verdict)", wit_ms)
+            roofline = {"bound": "hbm", **r, "traffic": traffic, "traffic_source": traffic_src}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,

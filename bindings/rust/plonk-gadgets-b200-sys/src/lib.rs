@@ -65,7 +65,49 @@ pub struct pg_check_stats {
     pub rows: [u64; PG_CK_KINDS],
 }
 
+// ---- multi-GPU: sharding plan and collectives
+pub const PG_OP_ADD_INPUT: u32 = 0;
+pub const PG_OP_RANGE_CHECK: u32 = 1;
+pub const PG_OP_MAX_BOUND: u32 = 2;
+pub const PG_OP_MAYBE_EQUAL: u32 = 3;
+pub const PG_OP_IS_NON_ZERO: u32 = 4;
+pub const PG_OP_SELECT_ZERO: u32 = 5;
+pub const PG_OP_SELECT_ONE: u32 = 6;
+pub const PG_OP_CONSTRAIN: u32 = 7;
+pub const PG_OP_RANGE_GATE: u32 = 8;
+pub const PG_SHARD_EVEN: c_int = 0;
+pub const PG_SHARD_ROWS: c_int = 1;
+pub const PG_COMM_ID_BYTES: usize = 128;
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default)]
+pub struct pg_op {
+    pub gadget: u32,
+    pub num_bits: u32,
+    pub n: u64,
+    pub group: u32,
+    pub reserved: u32,
+}
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default, PartialEq, Eq)]
+pub struct pg_op_shard {
+    pub inst_lo: u64,
+    pub inst_hi: u64,
+    pub row_base: u64,
+    pub var_base: u64,
+}
+
 extern "C" {
+    pub fn pg_op_shape(gadget: u32, num_bits: u32, rows: *mut u64, vars: *mut u64) -> c_int;
+    pub fn pg_shard_plan(ops: *const pg_op, n_ops: u64, world: u32, policy: c_int, out: *mut pg_op_shard) -> c_int;
+    pub fn pg_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn pg_comm_init(ctx: *mut pg_ctx, id: *const u8, rank: u32, world: u32) -> c_int;
+    pub fn pg_comm_destroy(ctx: *mut pg_ctx) -> c_int;
+    pub fn pg_check_sharded(ctx: *mut pg_ctx, mine: *const pg_op_shard, n_ops: u64, n_unsat: *mut u64, first_bad_row: *mut u64,
+                            n_err: *mut u64) -> c_int;
+    pub fn pg_gather_column(ctx: *mut pg_ctx, col: pg_col, dst: *mut pg_fr, capacity: u64, dst_on_device: c_int, counts: *mut u64,
+                            total: *mut u64) -> c_int;
+    pub fn pg_gather_variables(ctx: *mut pg_ctx, call: u64, dst: *mut pg_fr, capacity: u64, dst_on_device: c_int, total: *mut u64) -> c_int;
+    pub fn pg_export_composer(ctx: *mut pg_ctx, path: *const c_char, chunk_rows: u64, flags: u32) -> c_int;
     pub fn pg_abi_version() -> c_int;
     pub fn pg_strerror(code: c_int) -> *const c_char;
     pub fn pg_last_error(ctx: *const pg_ctx) -> *const c_char;

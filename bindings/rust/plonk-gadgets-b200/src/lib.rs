@@ -134,6 +134,35 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_check(self.ctx, &mut bad, &mut first) })?;
         Ok((bad, if first == u64::MAX { None } else { Some(first) }))
     }
+    /// Joins the communicator of the box's ranks (one process and one `BatchComposer` per GPU).  `id`: `comm_unique_id()` of rank 0.
+    pub fn comm_init(&mut self, id: &[u8; sys::PG_COMM_ID_BYTES], rank: u32, world: u32) -> Result<(), EngineError> {
+        self.ok(unsafe { sys::pg_comm_init(self.ctx, id.as_ptr(), rank, world) })?;
+        Ok(())
+    }
+    /// Verdict of the WHOLE sharded circuit on every rank: local gate check, then the NCCL all-reduce (sum of unsatisfied rows and of
+    /// `NonExistingInverse` errors, min of the first bad row in the sequential composer's numbering).  `mine`: this rank's row of
+    /// `shard_plan(..)`; `n_err`: this rank's error count.
+    pub fn check_sharded(&mut self, mine: &[sys::pg_op_shard], n_err: u64) -> Result<(u64, Option<u64>, u64), EngineError> {
+        let (mut bad, mut first, mut err) = (0, 0, n_err);
+        self.ok(unsafe { sys::pg_check_sharded(self.ctx, mine.as_ptr(), mine.len() as u64, &mut bad, &mut first, &mut err) })?;
+        Ok((bad, if first == u64::MAX { None } else { Some(first) }, err))
+    }
+    /// All-gather of a column's values (per-instance results of a call) from every rank, in instance order of the whole batch.
+    pub fn gather_column(&mut self, v: Variables, total: usize) -> Result<Vec<BlsScalar>, EngineError> {
+        let mut out = vec![BlsScalar::zero(); total];
+        let mut got = 0u64;
+        self.ok(unsafe { sys::pg_gather_column(self.ctx, v.col, out.as_mut_ptr() as *mut sys::pg_fr, total as u64, 0, std::ptr::null_mut(), &mut got) })?;
+        out.truncate(got as usize);
+        Ok(out)
+    }
+    /// Gather of witness shards: the Variables batched call number `call` appended on every rank, in the sequential composer's order.
+    pub fn gather_variables(&mut self, call: u64, total: usize) -> Result<Vec<BlsScalar>, EngineError> {
+        let mut out = vec![BlsScalar::zero(); total];
+        let mut got = 0u64;
+        self.ok(unsafe { sys::pg_gather_variables(self.ctx, call, out.as_mut_ptr() as *mut sys::pg_fr, total as u64, 0, &mut got) })?;
+        out.truncate(got as usize);
+        Ok(out)
+    }
     /// Rows and variables appended so far (`circuit_size()`, `variables.len()`).
     pub fn counts(&self) -> (u64, u64) {
         let (mut rows, mut vars) = (0, 0);
@@ -179,6 +208,19 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_col_read(self.ctx, v.col, 0, v.n, out.as_mut_ptr() as *mut sys::pg_fr, 0) })?;
         Ok(out)
     }
+}
+/// `ncclGetUniqueId` through the C ABI: rank 0 calls it and hands the bytes to the other ranks (any channel).
+pub fn comm_unique_id() -> Option<[u8; sys::PG_COMM_ID_BYTES]> {
+    let mut id = [0u8; sys::PG_COMM_ID_BYTES];
+    if unsafe { sys::pg_comm_unique_id(id.as_mut_ptr()) } == sys::PG_OK { Some(id) } else { None }
+}
+/// Splits a mixed circuit (a list of batched calls) over `world` GPUs: `plan[rank][k]` = the instance range of call k that rank runs
+/// and the row / Variable index of its first instance in the sequential composer (prefix sums over the calls).  Pure host code.
+pub fn shard_plan(ops: &[sys::pg_op], world: u32, by_rows: bool) -> Option<Vec<Vec<sys::pg_op_shard>>> {
+    let mut flat = vec![sys::pg_op_shard::default(); ops.len() * world as usize];
+    let policy = if by_rows { sys::PG_SHARD_ROWS } else { sys::PG_SHARD_EVEN };
+    if unsafe { sys::pg_shard_plan(ops.as_ptr(), ops.len() as u64, world, policy, flat.as_mut_ptr()) } != sys::PG_OK { return None; }
+    Some(flat.chunks(ops.len().max(1)).map(|c| c.to_vec()).collect())
 }
 impl Drop for BatchComposer {
     fn drop(&mut self) {

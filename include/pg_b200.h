@@ -82,7 +82,12 @@ enum {
 enum { PG_CHECK_GENERIC = 0, PG_CHECK_SPARSE = 1 };
 
 enum {
-    PG_F_TIMING = 1u        /* record CUDA events around every kernel class (pg_get_timing) */
+    PG_F_TIMING = 1u,       /* record CUDA events around every kernel class (pg_get_timing) */
+    PG_F_FUSED_CHECK = 2u   /* with PG_CHECK_SPARSE: the range gadgets' witness kernels also evaluate the rows they generate (on the values
+                               they hold in registers, structure-aware arithmetic), so the variable table is written once and never read
+                               again for the verdict; pg_check then only launches for segments that were not verified that way or whose
+                               Variables were overwritten since (pg_poke_variable), and adds the recorded verdict.  Same verdict as without
+                               the flag on every composer state this API can produce. */
 };
 
 typedef struct pg_cfg {
@@ -260,6 +265,17 @@ int pg_materialize_gate_selectors(pg_ctx *ctx, uint64_t row0, uint64_t cnt, pg_f
  * row row0 + t, encoded as row*4 + wire.  A position whose Variable is used once maps to itself, and so do the three zero wires
  * (w_l, w_r, w_o) of a range gate's closing row, which dusk-plonk pushes without a map entry. */
 int pg_permutation(pg_ctx *ctx, uint64_t row0, uint64_t cnt, uint64_t *sigma, int dst_on_device);
+
+/* ---- composer export (the import adapter's input) -----------------------------------------------
+ * The reference's tests hand the composer to dusk-plonk: prover.mut_cs() -> gadget calls -> preprocess -> prove
+ * (ref:tests/range_gadgets_tests.rs:82-91).  `Variable(pub(crate) usize)` cannot be forged outside dusk-plonk, so a batch built here
+ * reaches a real StandardComposer by REPLAY: pg_export_composer writes the whole composer -- the list of calls, every Variable's value
+ * as BlsScalar::to_bytes, and per row the four wire Variables, q_m q_l q_r q_o q_4 q_c q_arith q_range and the dense public input
+ * (construct_dense_pi_vec, ref:tests/scalar_gadgets_tests.rs:151), optionally the permutation (flags bit 0) -- to one little-endian
+ * file, in chunks of chunk_rows rows (0 = 2^20); layout: csrc/engine.hpp export_composer.  bindings/rust/plonk-gadgets-b200/src/import.rs
+ * (source only) replays it with add_input / poly_gate / range_gate and checks the Variable numbering as it goes. */
+enum { PG_EXPORT_SIGMA = 1u };
+int pg_export_composer(pg_ctx *ctx, const char *path, uint64_t chunk_rows, uint32_t flags);
 
 /* ---- evaluation domain (first half) -------------------------------------------------------------
  * The step that follows the gadget hot path inside Prover::prove [DEP dusk-plonk 0.8, reached from

@@ -62,6 +62,7 @@ def lib():
             "orc_select_one_batch": (None, [vp, u64, vp, vp, vp]),
             "orc_constrain_to_constant_batch": (None, [vp, u64, vp, vp, vp, i32]),
             "orc_range_gate_batch": (None, [vp, u64, vp, u64]),
+            "orc_poly_gate_batch": (i32, [vp, u64, vp, vp, vp, vp, vp]),
             "orc_set_mode": (None, [i32]),
             "orc_fr_from_u64": (None, [u64, vp]), "orc_fr_mul": (None, [vp, vp, vp]), "orc_fr_add": (None, [vp, vp, vp]),
             "orc_fr_sub": (None, [vp, vp, vp]), "orc_fr_neg": (None, [vp, vp]), "orc_fr_invert": (i32, [vp, vp]),
@@ -247,6 +248,13 @@ class Composer:
     def range_gate_batch(self, wit, num_bits: int):
         wit = np.ascontiguousarray(wit, dtype=np.uint64)
         lib().orc_range_gate_batch(self._c, len(wit), _p(wit), int(num_bits))
+
+    def poly_gate_batch(self, a, b, o, sel6, pi):
+        """n x poly_gate(a, b, o, q_m, q_l, q_r, q_o, q_c, pi): sel6 (6, n, 4) in q_m q_l q_r q_o q_4 q_c order (q_4 must be zero)."""
+        a, b, o = (np.ascontiguousarray(x, dtype=np.uint64) for x in (a, b, o))
+        sel6 = _fr_arr(sel6).reshape(6, len(a), 4); pi = _fr_arr(pi).reshape(len(a), 4)
+        if lib().orc_poly_gate_batch(self._c, len(a), _p(a), _p(b), _p(o), _p(sel6), _p(pi)) != 0:
+            raise ValueError("poly_gate cannot express a row with q_4 != 0")
 
     def constrain_to_constant_batch(self, vars_, k, pi=None):
         vars_ = np.ascontiguousarray(vars_, dtype=np.uint64)

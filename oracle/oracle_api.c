@@ -7,6 +7,7 @@
  *     for i in 0..n { gadget(composer, ..., operand_i) }
  * with the reference's own early-exit for `is_non_zero(..)?` (/root/reference/src/scalar.rs:79).
  */
+#include <string.h>
 #include "gadgets.h"
 #include <pthread.h>
 #include <stdlib.h>
@@ -113,6 +114,19 @@ void orc_range_gate_batch(orc_composer *c, uint64_t n, const uint64_t *wit, uint
 /* pi == NULL: no public input; else pi[i] (or pi[0] when uniform) is attached to row i's PI slot */
 void orc_constrain_to_constant_batch(orc_composer *c, uint64_t n, const uint64_t *vars, const fr_t *k, const fr_t *pi, int uniform) {
     for (uint64_t i = 0; i < n; i++) orc_constrain_to_constant(c, vars[i], &k[uniform ? 0 : i], pi ? &pi[uniform ? 0 : i] : NULL);
+}
+
+/* replay of exported rows (tests of the import adapter's input): n x poly_gate(a, b, o, q_m, q_l, q_r, q_o, q_c, pi) -- the public
+ * StandardComposer method a replaying host uses (call site in the reference: /root/reference/src/scalar.rs:84); sel6 is column-major
+ * q_m q_l q_r q_o q_4 q_c (q_4 must be 0: poly_gate has no fourth wire); pi[i] == 0 is replayed as None */
+int orc_poly_gate_batch(orc_composer *c, uint64_t n, const uint64_t *a, const uint64_t *b, const uint64_t *o, const fr_t *sel6, const fr_t *pi) {
+    const fr_t zero = fr_zero();
+    for (uint64_t i = 0; i < n; i++) {
+        if (memcmp(&sel6[4 * n + i], &zero, sizeof(fr_t)) != 0) return -1;
+        const int has_pi = memcmp(&pi[i], &zero, sizeof(fr_t)) != 0;
+        orc_poly_gate(c, a[i], b[i], o[i], &sel6[i], &sel6[n + i], &sel6[2 * n + i], &sel6[3 * n + i], &sel6[5 * n + i], has_pi ? &pi[i] : NULL);
+    }
+    return 0;
 }
 
 /* ---- timed CPU baseline: the reference path (witness generation through the composer + gate check) -------- */

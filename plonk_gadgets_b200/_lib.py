@@ -88,6 +88,7 @@ SIGNATURES = {
     "pg_materialize_rows": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _vp, _i32]),
     "pg_materialize_gate_selectors": (_i32, [_vp, _u64, _u64, _vp, _vp, _i32]),
     "pg_permutation": (_i32, [_vp, _u64, _u64, _vp, _i32]),
+    "pg_export_composer": (_i32, [_vp, C.c_char_p, _u64, _u32]),
     "pg_fft": (_i32, [_vp, _u32, _i32, _vp, _vp, _i32]),
     "pg_wire_polynomials": (_i32, [_vp, _u32, _vp, _i32]),
     "pg_msm": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32]),

@@ -19,6 +19,7 @@ Every call is equal to the sequential loop ``for i in range(n): gadget(composer,
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -27,6 +28,7 @@ from . import _lib
 
 CHECK_GENERIC, CHECK_SPARSE = 0, 1
 F_TIMING = 1
+F_FUSED_CHECK = 2
 UINT64_MAX = 2 ** 64 - 1
 
 
@@ -146,9 +148,10 @@ class AllocatedScalar:
 class StandardComposer:
     """Device-resident batched composer (dusk-plonk StandardComposer, arithmetic-row subset).  Fresh state: 3 rows, 5 variables."""
 
-    def __init__(self, device: int = 0, check_mode: int = CHECK_GENERIC, timing: bool = False, stream: int | None = None, check_shape: int = 0, _cdll=None):
+    def __init__(self, device: int = 0, check_mode: int = CHECK_GENERIC, timing: bool = False, stream: int | None = None, check_shape: int = 0,
+                 fused_check: bool = False, _cdll=None):
         self._L = _cdll if _cdll is not None else _lib.load()
-        cfg = _lib.pg_cfg(device=device, check_mode=check_mode, flags=F_TIMING if timing else 0, check_shape=check_shape, stream=stream)
+        cfg = _lib.pg_cfg(device=device, check_mode=check_mode, flags=(F_TIMING if timing else 0) | (F_FUSED_CHECK if fused_check else 0), check_shape=check_shape, stream=stream)
         ctx = C.c_void_p()
         rc = self._L.pg_ctx_create(C.byref(cfg), C.byref(ctx))
         if rc != 0:
@@ -224,6 +227,11 @@ class StandardComposer:
         bad, first = C.c_uint64(), C.c_uint64()
         self._ok(self._L.pg_check(self._ctx, C.byref(bad), C.byref(first)), "pg_check")
         return bad.value, (None if first.value == UINT64_MAX else first.value)
+
+    def export(self, path: str, chunk_rows: int = 0, sigma: bool = False):
+        """pg_export_composer: the whole composer (calls, Variable values as to_bytes, wire ids, selector columns, dense PI, optionally
+        the permutation) in one chunked file -- the import adapter's input (read it back with plonk_gadgets_b200.export_format)."""
+        self._ok(self._L.pg_export_composer(self._ctx, os.fsencode(path), chunk_rows, 1 if sigma else 0), "pg_export_composer")
 
     # -- multi-GPU: communicator, sharded verdict, gathers (include/pg_b200.h "multi-GPU"; SURVEY.md 8e)
     def comm_init(self, unique_id: bytes, rank: int, world: int):

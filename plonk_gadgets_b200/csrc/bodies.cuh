@@ -34,8 +34,9 @@ PG_HD const Fr& pow2_entry(uint32_t i) {
 // words 0..CNT_STICKY-1 are re-initialised before every use (Engine::reset_counters); CNT_BAD_INPUT / CNT_FIRST_BAD_INPUT are
 // sticky until the composer is reset: every kernel that ingests caller scalars counts the ones that are not fully reduced (>= q)
 // there, and the next call that reads the counters reports PG_ERR_ARG (include/pg_b200.h, "Scalars").
+// CNT_FUSED_*: verdict of the rows that were evaluated inside witness generation (PG_F_FUSED_CHECK), added in by pg_check.
 enum { CNT_UNSAT = 0, CNT_FIRST_BAD = 1, CNT_MIXED_BITS = 2, CNT_N_ERR = 3, CNT_FIRST_ERR = 4, CNT_STICKY = 5,
-       CNT_BAD_INPUT = 5, CNT_FIRST_BAD_INPUT = 6, CNT_WORDS = 8 };
+       CNT_BAD_INPUT = 5, CNT_FIRST_BAD_INPUT = 6, CNT_FUSED_UNSAT = 7, CNT_FUSED_FIRST = 8, CNT_WORDS = 12 };
 
 PG_HD void counter_add(unsigned long long* c, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
@@ -113,30 +114,52 @@ struct RangeArgs {
     uint32_t param_m, param_negmin;
     DecompSlots d[2]; uint32_t slot_o;
     unsigned long long* counters;
+    uint64_t base_row; uint32_t n_rows;              // FUSED only: global index of the segment's first row, rows per instance
 };
 
 // which table slots the batch inversion reads and writes: out[j] = in[j]^-1 (or 0) for every instance
 struct BatchInvArgs { uint4* fr; uint64_t stride; uint64_t n; uint32_t n_pairs; uint32_t in_slot[4]; uint32_t out_slot[4]; uint32_t elems_per_thread; };
 
-template <bool RANGE>
+// FUSED (PG_F_FUSED_CHECK): the kernels that generate a range gadget's witness also evaluate its rows, on the values they hold in
+// registers and with the structure-aware arithmetic of the compiled row program (packed bits are boolean by construction; a row
+// x + t - y = 0 is tested as fr_sum_equals(x, t, y)), so the table is written once and not read again for the verdict.  Unsatisfied
+// rows are added to the sticky CNT_FUSED_* words; pg_check skips such a segment unless one of its Variables was overwritten since.
+// Local row numbers of a decomposition that starts (with its V row) at row r0:  V: r0, A_0: r0+1, boolean / accumulate of bit p:
+// r0+2+2p / r0+3+2p, u: r0+2k+2, y: r0+2k+3, y*u: r0+2k+4; the second decomposition of range_check starts at 2k+5, y1*y2 is row 4k+10.
+struct FusedVerdict {
+    uint32_t bad = 0, first = ~0u;
+    PG_HD void row(bool holds, uint32_t r) { if (!holds) { bad++; first = first < r ? first : r; } }
+    PG_HD void flush(const RangeArgs& a, uint64_t i) const;
+};
+template <bool RANGE, bool FUSED = false>
 struct RangePre {
     static constexpr int E = RANGE ? 2 : 1;
     typedef RangeArgs Args;
 
     // scalar_decomposition_gadget up to (and including) u = acc - v
-    PG_HD static void decompose(const Args& a, uint64_t i, const DecompSlots& s, const Fr& v) {
+    PG_HD static void decompose(const Args& a, uint64_t i, const DecompSlots& s, const Fr& v, FusedVerdict& fv, uint32_t r0) {
         tab_store_fr(a.fr, a.stride, s.v, i, v);
         const Fr c = fr_from_mont(v);                                          // to_bytes(): canonical integer, range.rs:163
 #pragma unroll
         for (int w = 0; w < 8; w++) a.bits[(uint64_t)(s.plane * 8 + w) * a.stride + i] = c.v[w];   // the 256 bit variables
         Fr acc = fr_zero();
         tab_store_fr(a.fr, a.stride, s.a0, i, acc);                            // A_0 = 0, range.rs:138-141
+        if (FUSED) fv.row(fr_is_zero(acc), r0 + 1);                            // constrain_to_constant(A_0, 0)
         for (uint32_t p = 0; p < a.k; p++) {                                   // range.rs:143-153
             const uint32_t bit = (c.v[p >> 5] >> (p & 31u)) & 1u;
+            const Fr prev = acc;
             if (bit) acc = fr_add(acc, pow2_entry(p));
             tab_store_fr(a.fr, a.stride, s.a0 + 1 + p, i, acc);
+            if (FUSED) {                                                       // 2^p * b_p + A_p - A_{p+1} = 0 (the boolean row holds: packed bit)
+                Fr t = pow2_entry(p);
+#pragma unroll
+                for (int j = 0; j < 8; j++) t.v[j] &= 0u - bit;
+                fv.row(fr_sum_equals(prev, t, acc), r0 + 3 + 2 * p);
+            }
         }
-        tab_store_fr(a.fr, a.stride, s.u, i, fr_sub(acc, v));                  // maybe_equal: u = a - b, scalar.rs:111-121
+        const Fr u = fr_sub(acc, v);
+        tab_store_fr(a.fr, a.stride, s.u, i, u);                               // maybe_equal: u = a - b, scalar.rs:111-121
+        if (FUSED) fv.row(fr_sum_equals(v, u, acc), r0 + 2 * a.k + 2);         // A_k - v - u = 0
     }
     PG_HD static void run(const Args& a, uint64_t i_launch) {
         const uint64_t i = a.i0 + i_launch;
@@ -155,25 +178,50 @@ struct RangePre {
                 tab_store_fr(a.param, a.stride, a.param_negmin, i, negmin);
             }
         }
-        decompose(a, i, a.d[0], fr_sub(m, x));                                 // b - x, range.rs:93-102
-        if (RANGE) decompose(a, i, a.d[E - 1], fr_add(x, negmin));             // x - a, range.rs:60-69
+        FusedVerdict fv;
+        const Fr v0 = fr_sub(m, x);
+        if (FUSED) fv.row(fr_sum_equals(x, v0, m), 0);                         // -x - v + (max - 1) = 0
+        decompose(a, i, a.d[0], v0, fv, 0);                                    // b - x, range.rs:93-102
+        if (RANGE) {
+            const Fr v1 = fr_add(x, negmin);
+            if (FUSED) fv.row(fr_sum_equals(x, negmin, v1), 2 * a.k + 5);      // x - v' - min = 0
+            decompose(a, i, a.d[E - 1], v1, fv, 2 * a.k + 5);                  // x - a, range.rs:60-69
+        }
+        if (FUSED) fv.flush(a, i);
     }
 };
-template <bool RANGE>
+template <bool RANGE, bool FUSED = false>
 struct RangePost {   // after z = u^-1 (or 0) has been written by the batch inversion (scalar.rs:122-123)
     static constexpr int E = RANGE ? 2 : 1;
     typedef RangeArgs Args;
     PG_HD static void run(const Args& a, uint64_t i) {
         Fr y[E];
+        FusedVerdict fv;
 #pragma unroll
         for (int e = 0; e < E; e++) {
             const Fr u = tab_load_fr(a.fr, a.stride, a.d[e].u, i), z = tab_load_fr(a.fr, a.stride, a.d[e].z, i);
-            y[e] = fr_sub(fr_one(), fr_mul(z, u));                             // y = 1 - z*u, scalar.rs:126
+            const Fr zu = fr_mul(z, u);
+            y[e] = fr_sub(fr_one(), zu);                                       // y = 1 - z*u, scalar.rs:126
             tab_store_fr(a.fr, a.stride, a.d[e].y, i, y[e]);
+            if (FUSED) {
+                const uint32_t r0 = e ? 2 * a.k + 5 : 0;
+                fv.row(fr_sum_equals(y[e], zu, fr_one()), r0 + 2 * a.k + 3);   // -z*u - y + 1 = 0
+                fv.row(fr_is_zero(fr_mul(y[e], u)), r0 + 2 * a.k + 4);         // y*u = 0, scalar.rs:129-138
+            }
         }
-        if (RANGE) tab_store_fr(a.fr, a.stride, a.slot_o, i, fr_mul(y[0], y[E - 1]));   // y1*y2, range.rs:42
+        if (RANGE) {
+            const Fr o = fr_mul(y[0], y[E - 1]);
+            tab_store_fr(a.fr, a.stride, a.slot_o, i, o);                      // y1*y2, range.rs:42
+            if (FUSED) fv.row(fr_eq(fr_mul(y[0], y[E - 1]), o), 4 * a.k + 10);
+        }
+        if (FUSED) fv.flush(a, i);
     }
 };
+PG_HD void FusedVerdict::flush(const RangeArgs& a, uint64_t i) const {
+    if (!bad) return;
+    counter_add(a.counters + CNT_FUSED_UNSAT, (unsigned long long)bad);
+    counter_min(a.counters + CNT_FUSED_FIRST, (unsigned long long)(a.base_row + i * (uint64_t)a.n_rows + first));
+}
 
 // ---------------------------------------------------------------------------------------------------- maybe_equal
 struct MaybeEqualArgs { DevTab a_tab, b_tab; uint32_t a_loc, b_loc; uint4* fr; uint64_t stride; uint64_t n; };
@@ -446,26 +494,30 @@ PG_HD void sp_row_init(uint32_t* t) {
     t[0] = 0x00000007u; t[1] = 0xfffffff9u; t[2] = 0xfff483f8u; t[3] = 0x4a2f7c14u; t[4] = 0x436ce825u;
     t[5] = 0x6694e838u; t[6] = 0x234e6cf9u; t[7] = 0x2b7f9346u; t[8] = 0x00000003u;
 }
+struct QDefault { PG_HD QRegs operator()() const { return q_regs_default(); } };
 struct SparseProgBody {
-    // SP_CHAIN (layout.h): L rows  sel_j * bit_j + x_j - x_{j+1} = 0.  Four loads of x in flight; x_{j+1} is the next row's x_j.
-    template <class PoolT>
-    PG_HD static void run_chain(const CheckArgs& a, const SpOp& c0, const SpOp& c1, const SpOp& c2, const PoolT& pool, uint64_t i,
-                                uint32_t& bad, unsigned long long& first_bad, uint32_t& r) {
+    // SP_CHAIN (layout.h): L rows  sel_j * bit_j + x_j - x_{j+1} = 0.  DEPTH loads of x in flight; x_{j+1} is the next row's x_j.
+    template <int DEPTH, class PoolT>
+    PG_HD static void run_chain(const SpOp& c0, const SpOp& c1, const SpOp& c2, const PoolT& pool, uint64_t i,
+                                uint32_t& bad, uint32_t& first_local, uint32_t& r) {
         const uint32_t L = c1.sel, rows_per = c1.sh;
-        const uint64_t slot_step = c2.addr >> 4;                     // in uint4 units; bit words: >> 5 (u32 units of an eighth of the distance)
+        const uint64_t slot_step = c2.addr >> 4, word_step = c2.addr >> 5;   // in uint4 / u32 units (bit words are an eighth of the distance apart)
         const uint4* px = reinterpret_cast<const uint4*>(c0.addr) + 2 * i;
         const uint32_t* pw = reinterpret_cast<const uint32_t*>(c1.addr) + i;
-        const uint64_t word_step = c2.addr >> 5;
         uint32_t left = 32u - c0.sh;                                 // bits of the current word not yet consumed
         uint32_t word = *pw >> c0.sh, word_next = 0;
         if (L > left) { pw += word_step; word_next = *pw; }
         Fr prev = ld256(px);
-        for (uint32_t j = 0; j < L; j += 4) {
-            Fr nx[4];
+        px += slot_step;                                             // -> x_1
+        uint32_t sel = c0.sel, rr = r + rows_per - 1u;               // pool index / local row of the element being tested
+#pragma unroll 1
+        for (uint32_t j = 0; j < L; j += DEPTH) {
+            Fr nx[DEPTH];
 #pragma unroll
-            for (uint32_t u = 0; u < 4; u++) if (j + u < L) nx[u] = ld256(px + (uint64_t)(j + u + 1) * slot_step);
+            for (uint32_t u = 0; u < DEPTH; u++) if (j + u < L) nx[u] = ld256(px + u * slot_step);
+            px += DEPTH * slot_step;
 #pragma unroll
-            for (uint32_t u = 0; u < 4; u++) {
+            for (uint32_t u = 0; u < DEPTH; u++) {
                 if (j + u >= L) break;
                 const uint32_t m = 0u - (word & 1u);
                 word >>= 1;
@@ -473,25 +525,27 @@ struct SparseProgBody {
                     word = word_next; left = 32;
                     if (L - (j + u + 1) > 32u) { pw += word_step; word_next = *pw; }
                 }
-                Fr t = pool(c0.sel + j + u);
+                Fr t = pool(sel);
 #pragma unroll
                 for (int k = 0; k < 8; k++) t.v[k] &= m;
-                if (!fr_sum_equals(prev, t, nx[u])) {
+                if (!fr_sum_equals(u == 0 ? prev : nx[u ? u - 1 : 0], t, nx[u])) {
                     bad++;
-                    const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r + (j + u) * rows_per + (rows_per - 1u);
-                    if (g < first_bad) first_bad = g;
+                    first_local = first_local < rr ? first_local : rr;
                 }
-                prev = nx[u];
+                sel++; rr += rows_per;
             }
+            prev = nx[DEPTH - 1];
         }
         r += L * rows_per;
     }
 
-    template <class PoolT>
-    PG_HD static uint32_t run(const CheckArgs& a, const SparseProg& prog, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
+    // QSrc: where the modulus limbs come from at the (rare) multiplier site -- shared memory on the device, so that they are not
+    // eight registers held for the whole kernel
+    template <int DEPTH, class PoolT, class QSrc>
+    PG_HD static uint32_t run(const CheckArgs& a, const SparseProg& prog, const PoolT& pool, const QSrc& qsrc, uint64_t i, unsigned long long& first_bad) {
         uint32_t t[9];
         sp_row_init(t);
-        uint32_t mask = ~0u, bad = 0, r = 0;
+        uint32_t mask = ~0u, bad = 0, r = 0, first_local = ~0u;      // first unsatisfied row of this instance (local index)
         Fr v = fr_zero();                                            // product register of the multiplication chain (a handful of operations per instance use it)
 #pragma unroll 1
         for (uint32_t j = 0; j < prog.n; j++) {
@@ -505,8 +559,9 @@ struct SparseProgBody {
             const uint32_t code = op.op & 0x7fu;
             if (code == SP_CHAIN) {
                 const SpOp c1 = sp_fetch(prog.ops, j + 1), c2 = sp_fetch(prog.ops, j + 2);
-                run_chain(a, op, c1, c2, pool, i, bad, first_bad, r);
+                run_chain<DEPTH>(op, c1, c2, pool, i, bad, first_local, r);
                 j += 2;
+                sp_row_init(t); v = fr_zero(); mask = ~0u;          // a chain starts and ends at a row boundary: nothing is carried across it
                 continue;
             }
             if (code <= SP_BITSEL) {                                // the operations range rows are made of: no multiplication, `v` untouched
@@ -534,19 +589,22 @@ struct SparseProgBody {
                     default: break;
                 }
                 if (mul) {                                          // the one multiplier site
-                    const Fr p = fr_mul_eo(x, y, q);
+                    const Fr p = fr_mul_eo(x, y, qsrc());
                     if (code == SP_MUL_SEL_FR) add9_fr(t, p); else v = p;
                 }
             }
             if ((op.op & SP_ROW_END) || op.op == SP_END) {          // the row is complete
                 if (!limbs9_is_multiple_of_q(t)) {
                     bad++;
-                    const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
-                    if (g < first_bad) first_bad = g;
+                    first_local = first_local < r ? first_local : r;
                 }
                 r++; mask = ~0u;
                 sp_row_init(t);
             }
+        }
+        if (bad) {
+            const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + first_local;
+            if (g < first_bad) first_bad = g;
         }
         return bad;
     }

@@ -153,6 +153,7 @@ int pg_permutation(pg_ctx* ctx, uint64_t row0, uint64_t cnt, uint64_t* sigma, in
     PG_NEED_CTX(ctx);
     PG_TRY(ctx, ctx->e.permutation(row0, cnt, sigma, dst_on_device));
 }
+int pg_export_composer(pg_ctx* ctx, const char* path, uint64_t chunk_rows, uint32_t flags) { PG_NEED_CTX(ctx); PG_TRY(ctx, ctx->e.export_composer(path, chunk_rows, flags)); }
 int pg_fft(pg_ctx* ctx, uint32_t log_n, int inverse, const pg_fr* src, pg_fr* dst, int on_device) {
     PG_NEED_CTX(ctx); PG_ALIGNED(ctx, src, on_device); PG_ALIGNED(ctx, dst, on_device);
     PG_TRY(ctx, ctx->e.fft(log_n, inverse, src, dst, on_device));

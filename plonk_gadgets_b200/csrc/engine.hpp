@@ -50,6 +50,7 @@ struct Segment {
     std::vector<SpOp> sp_ops; SpOp* d_sp = nullptr;    // structure-aware row program (PG_CHECK_SPARSE only)
     std::vector<Column> operands;       // the columns bound as operands (for the permutation map)
     bool other_gates = false;           // some row belongs to another widget than the arithmetic one (GATE_RANGE / GATE_NONE)
+    bool fused_ok = false;              // PG_F_FUSED_CHECK: every row was evaluated while the witness was generated, and no Variable was overwritten since
     bool owns_table = true;             // false: fr / bits / param and d_image are views into buffers another segment owns
 };
 // a pre-allocated variable table (and image memory) for a segment that is a VIEW of another segment's storage: instance i of the
@@ -415,7 +416,7 @@ public:
     }
     // re-initialises the per-call words; `all`: also the sticky bad-input words (composer reset)
     int reset_counters(bool all = false) {
-        static const unsigned long long init[CNT_WORDS] = {0, ~0ull, 0, 0, ~0ull, 0, ~0ull, 0};
+        static const unsigned long long init[CNT_WORDS] = {0, ~0ull, 0, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0, 0, 0};
         if (!be.h2d(d_counters, init, (all ? (size_t)CNT_WORDS : (size_t)CNT_STICKY) * sizeof(unsigned long long))) return fail(PG_ERR_CUDA, "counter reset");
         return PG_OK;
     }
@@ -495,10 +496,20 @@ public:
             // the operand's table, when the operand is a whole column of its segment (chunks of a pending input copy are instance ranges of it)
             const Segment& os = segs[operand.seg];
             const void* whole = (operand.inst_off == 0 && operand.n == os.n_inst) ? (const void*)os.fr : nullptr;
-            const bool ok = is_range_check
-                ? be.template run_simple_chunked<RangePre<true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true>>(a, n, CLS_WITNESS)
-                : be.template run_simple_chunked<RangePre<false>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false>>(a, n, CLS_WITNESS);
+            // PG_F_FUSED_CHECK (structure-aware mode only): the same kernels also evaluate the rows they generate
+            const bool fused = (cfg.flags & PG_F_FUSED_CHECK) && cfg.check_mode == PG_CHECK_SPARSE;
+            a.base_row = s.base_row; a.n_rows = (uint32_t)s.t.rows.size();
+            bool ok;
+            if (fused)
+                ok = is_range_check
+                    ? be.template run_simple_chunked<RangePre<true, true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true, true>>(a, n, CLS_WITNESS)
+                    : be.template run_simple_chunked<RangePre<false, true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false, true>>(a, n, CLS_WITNESS);
+            else
+                ok = is_range_check
+                    ? be.template run_simple_chunked<RangePre<true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true>>(a, n, CLS_WITNESS)
+                    : be.template run_simple_chunked<RangePre<false>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false>>(a, n, CLS_WITNESS);
             if (!ok) return fail(PG_ERR_CUDA, "range witness kernels");
+            if (fused) { s.fused_ok = true; be.count_check(PG_CK_FUSED, n * s.t.rows.size()); }
         }
         if (!uniform && n) {
             unsigned long long c[CNT_WORDS];
@@ -706,11 +717,12 @@ public:
     // part of call k of the whole circuit, and its rows are numbered from mine[k].row_base -- their indices in the SEQUENTIAL
     // composer -- so that the first bad row needs no translation before the all-reduce; the fresh composer's three rows exist on
     // every rank and are checked by rank 0 only.
-    int enqueue_checks(const pg_op_shard* mine = nullptr, bool with_preamble = true) {
+    int enqueue_checks(const pg_op_shard* mine = nullptr, bool with_preamble = true, bool skip_fused = false) {
         for (size_t k = 0; k < segs.size(); k++) {
             const Segment& s = segs[k];
             if (!s.n_inst || s.t.rows.empty()) continue;
             if (mine && k == 0 && !with_preamble) continue;
+            if (s.fused_ok && skip_fused) continue;  // verdict already in CNT_FUSED_* (pg_check adds it; a sharded check renumbers rows and evaluates them again)
             CheckArgs a; memset(&a, 0, sizeof(a));
             for (int j = 0; j < MAX_TABS; j++) a.tab[j] = s.tabs[j];
             a.param = s.param; a.param_stride = s.n_alloc; a.rows = s.d_rows; a.pool = s.d_pool;
@@ -728,9 +740,12 @@ public:
     int check(uint64_t* n_unsat, uint64_t* first_bad) {
         int rc = reset_counters();
         if (rc) return rc;
-        if ((rc = enqueue_checks())) return rc;
+        if ((rc = enqueue_checks(nullptr, true, true))) return rc;
         unsigned long long c[CNT_WORDS];
         if ((rc = read_counters(c))) return rc;
+        bool any_fused = false;
+        for (const Segment& s : segs) any_fused = any_fused || s.fused_ok;
+        if (any_fused) { c[CNT_UNSAT] += c[CNT_FUSED_UNSAT]; if (c[CNT_FUSED_FIRST] < c[CNT_FIRST_BAD]) c[CNT_FIRST_BAD] = c[CNT_FUSED_FIRST]; }
         if (n_unsat) *n_unsat = c[CNT_UNSAT];
         if (first_bad) *first_bad = c[CNT_FIRST_BAD];
         return PG_OK;
@@ -876,6 +891,9 @@ public:
             const uint32_t loc = s.t.var_loc[j];
             if (loc_kind(loc) != LOC_FR) return fail(PG_ERR_ARG, "poke_variable: packed bit variables cannot be overwritten");
             if (!be.h2d(s.fr + 2 * ((uint64_t)loc_payload(loc) * s.n_alloc + i), value, sizeof(pg_fr)) || !be.sync()) return fail(PG_ERR_CUDA, "poke copy");
+            // the stored witness no longer is what generation verified: this segment and every segment that reads the Variable through an
+            // operand column (segments are appended in call order: all later ones may) go back to the ordinary check
+            for (size_t j = k; j < segs.size(); j++) segs[j].fused_ok = false;
             return PG_OK;
         }
         return fail(PG_ERR_ARG, "poke_variable: Variable not found");
@@ -1155,6 +1173,73 @@ public:
         const int rc = deliver(sigma, out, 4 * cnt * sizeof(uint64_t), 0);
         release_scratch_from(mark);
         return rc;
+    }
+
+    // ------------------------------------------------------------------------------------------------ export
+    // Everything a host needs to rebuild this composer inside a real dusk-plonk StandardComposer (the import adapter replays it:
+    // bindings/rust/.../import.rs), written to one little-endian file in chunks so that the expanded form never has to fit anywhere:
+    //   header   : "PGB2EXP1", u32 version = 1, u32 flags (bit 0: sigma present), u64 n_rows, n_vars, n_calls, chunk_rows, 2 x u64 0
+    //   calls    : n_calls x 64 bytes {u32 kind (GadgetKind), u32 num_bits, u64 n_inst, base_row, base_var, u32 rows/inst, u32 vars/inst,
+    //              u64 first Variable of operand 0 (instance 0), u64 its stride, u64 0} -- range_gate calls are replayed natively
+    //   variables: n_vars x 32 bytes, BlsScalar::to_bytes (canonical little endian)
+    //   row chunks until n_rows: u64 row0, u64 cnt, w_idx[4][cnt] u64 (w_l, w_r, w_o, w_4), sel[8][cnt] x 32 bytes canonical
+    //              (q_m q_l q_r q_o q_4 q_c q_arith q_range), pi[cnt] x 32 bytes canonical (dense), then sigma[4][cnt] u64 if flagged
+    int export_composer(const char* path, uint64_t chunk_rows, uint32_t flags) {
+        if (!path) return fail(PG_ERR_ARG, "export_composer: null path");
+        if (!chunk_rows) chunk_rows = 1ull << 20;
+        FILE* f = fopen(path, "wb");
+        if (!f) return fail(PG_ERR_ARG, std::string("export_composer: cannot open ") + path);
+        struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{f};
+        auto put = [&](const void* p, size_t bytes) { return fwrite(p, 1, bytes, f) == bytes; };
+        const uint64_t n_calls = segs.size();
+        { char magic[8] = {'P', 'G', 'B', '2', 'E', 'X', 'P', '1'}; uint32_t ver = 1, fl = flags & 1u;
+          uint64_t h[6] = {n_rows, n_vars, n_calls, chunk_rows, 0, 0};
+          if (!put(magic, 8) || !put(&ver, 4) || !put(&fl, 4) || !put(h, sizeof(h))) return fail(PG_ERR_STATE, "export_composer: write failed"); }
+        for (const Segment& sg : segs) {
+            uint64_t e[8] = {0, sg.n_inst, sg.base_row, sg.base_var, 0, 0, 0, 0};
+            e[0] = (uint64_t)(uint32_t)sg.t.kind | ((uint64_t)sg.t.k << 32);
+            e[4] = (uint64_t)(uint32_t)sg.t.rows.size() | ((uint64_t)sg.t.n_vars << 32);
+            if (!sg.operands.empty()) { const Column& c = sg.operands[0]; const Segment& os = segs[c.seg]; e[5] = os.base_var + c.inst_off * os.t.n_vars + c.local; e[6] = os.t.n_vars; }
+            if (!put(e, sizeof(e))) return fail(PG_ERR_STATE, "export_composer: write failed");
+        }
+        std::vector<pg_fr> host(chunk_rows * 8);
+        std::vector<uint64_t> idx(chunk_rows * 4);
+        const size_t mark = scratch.size();
+        uint4* d_a = (uint4*)dalloc(chunk_rows * 8 * sizeof(pg_fr)); uint4* d_b = (uint4*)dalloc(chunk_rows * 8 * sizeof(pg_fr));
+        if (!d_a || !d_b) return fail(PG_ERR_OOM, "export buffers");
+        scratch.push_back(d_a); scratch.push_back(d_b);
+        int rc;
+        for (uint64_t v0 = 0; v0 < n_vars; v0 += chunk_rows * 8) {          // variables, canonical bytes
+            const uint64_t cnt = std::min<uint64_t>(chunk_rows * 8, n_vars - v0);
+            if ((rc = read_variables(v0, cnt, reinterpret_cast<pg_fr*>(d_a), 1))) return rc;
+            if ((rc = convert(true, cnt, reinterpret_cast<const pg_fr*>(d_a), reinterpret_cast<pg_fr*>(d_b), 1, nullptr, nullptr))) return rc;
+            if ((rc = deliver(host.data(), d_b, cnt * sizeof(pg_fr), 0))) return rc;
+            if (!put(host.data(), cnt * sizeof(pg_fr))) return fail(PG_ERR_STATE, "export_composer: write failed");
+        }
+        for (uint64_t r0 = 0; r0 < n_rows; r0 += chunk_rows) {
+            const uint64_t cnt = std::min<uint64_t>(chunk_rows, n_rows - r0);
+            const uint64_t hdr[2] = {r0, cnt};
+            if (!put(hdr, sizeof(hdr))) return fail(PG_ERR_STATE, "export_composer: write failed");
+            if ((rc = materialize(r0, cnt, idx.data(), nullptr, nullptr, nullptr, 0))) return rc;
+            if (!put(idx.data(), 4 * cnt * sizeof(uint64_t))) return fail(PG_ERR_STATE, "export_composer: write failed");
+            // selectors: 6 columns + q_arith + q_range, then PI, all to canonical bytes on the device
+            if ((rc = materialize(r0, cnt, nullptr, nullptr, reinterpret_cast<pg_fr*>(d_a), nullptr, 1))) return rc;
+            if ((rc = gate_selectors(r0, cnt, reinterpret_cast<pg_fr*>(d_a + 2 * 6 * cnt), reinterpret_cast<pg_fr*>(d_a + 2 * 7 * cnt), 1))) return rc;
+            if ((rc = convert(true, 8 * cnt, reinterpret_cast<const pg_fr*>(d_a), reinterpret_cast<pg_fr*>(d_b), 1, nullptr, nullptr))) return rc;
+            if ((rc = deliver(host.data(), d_b, 8 * cnt * sizeof(pg_fr), 0))) return rc;
+            if (!put(host.data(), 8 * cnt * sizeof(pg_fr))) return fail(PG_ERR_STATE, "export_composer: write failed");
+            if ((rc = materialize(r0, cnt, nullptr, nullptr, nullptr, reinterpret_cast<pg_fr*>(d_a), 1))) return rc;
+            if ((rc = convert(true, cnt, reinterpret_cast<const pg_fr*>(d_a), reinterpret_cast<pg_fr*>(d_b), 1, nullptr, nullptr))) return rc;
+            if ((rc = deliver(host.data(), d_b, cnt * sizeof(pg_fr), 0))) return rc;
+            if (!put(host.data(), cnt * sizeof(pg_fr))) return fail(PG_ERR_STATE, "export_composer: write failed");
+            if (flags & 1u) {
+                if ((rc = permutation(r0, cnt, idx.data(), 0))) return rc;
+                if (!put(idx.data(), 4 * cnt * sizeof(uint64_t))) return fail(PG_ERR_STATE, "export_composer: write failed");
+            }
+        }
+        if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
+        release_scratch_from(mark);
+        return PG_OK;
     }
 
     // ------------------------------------------------------------------------------------------------ helpers

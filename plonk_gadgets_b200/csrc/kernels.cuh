@@ -184,6 +184,17 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
 }
 
 // The structure-aware check as a compiled row program (layout.h SpOp, bodies.cuh SparseProgBody); same skeleton as k_check.
+// DEPTH: loads in flight per thread inside a chain (register budget: 8 registers per load).
+struct SmemQ {
+    const uint32_t* p;
+    __device__ __forceinline__ QRegs operator()() const { QRegs q;
+#pragma unroll
+        for (int k = 0; k < 8; k++) q.v[k] = p[k];
+        return q; }
+};
+template <int SHAPE> struct ProgDepth { static constexpr int D = 4; };
+template <> struct ProgDepth<3> { static constexpr int D = 2; };
+template <> struct ProgDepth<4> { static constexpr int D = 2; };
 template <int SHAPE>
 __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>::MIN_BLOCKS) k_check_prog(const CheckProgArgs args) {
     const CheckArgs& a = args.a; const SparseProg& prog = args.prog;
@@ -193,16 +204,13 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
     for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += CHECK_BLOCK) s_pool[t] = a.pool[t];
     if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
     __syncthreads();
-    QRegs q;
-#pragma unroll
-    for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
     const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
     if (i < a.n_inst) {
         SmemPool pool = {s_pool};
-        if (prog.ops) bad = SparseProgBody::run(a, prog, pool, q, i, first_bad);
-        else bad = CheckBody::run<1>(a, pool, q, i, first_bad);                   // no program: per-row evaluation
+        SmemQ qs = {s_q};
+        bad = SparseProgBody::run<ProgDepth<SHAPE>::D>(a, prog, pool, qs, i, first_bad);     // (segments without a program are launched as k_check<1>)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -105,7 +105,7 @@ public:
         }
         for (uint64_t i = 0; i < a.n_inst; i++) {
             unsigned long long fb = ~0ull;
-            const uint32_t bad = a.mode ? (prog.ops ? SparseProgBody::run(a, prog, pool, q, i, fb) : CheckBody::run<1>(a, pool, q, i, fb)) : CheckBody::run<0>(a, pool, q, i, fb);
+            const uint32_t bad = a.mode ? (prog.ops ? SparseProgBody::run<4>(a, prog, pool, QDefault(), i, fb) : CheckBody::run<1>(a, pool, q, i, fb)) : CheckBody::run<0>(a, pool, q, i, fb);
             if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
         }
         return true;

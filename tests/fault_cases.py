@@ -48,8 +48,10 @@ def decomposition_targets(k: int, base_row: int) -> dict:
 
 
 def poked_range_segment(make_composer, ob, n: int, gadget: str = "range_check", bits: int = 64, per_instance_bounds: bool = False,
-                        modes=(pg.CHECK_GENERIC, pg.CHECK_SPARSE), expect_kind: dict | None = None, seed: int = 5, wit_dev=None):
-    """`expect_kind`: {mode: kind name of pg_get_check_stats} that must have evaluated the segment's rows (None: not asserted)."""
+                        modes=(pg.CHECK_GENERIC, pg.CHECK_SPARSE), expect_kind: dict | None = None, seed: int = 5, wit_dev=None, fused: bool = False):
+    """`expect_kind`: {mode: kind name of pg_get_check_stats} that must have evaluated the segment's rows (None: not asserted).
+    `fused` (PG_F_FUSED_CHECK, structure-aware mode): the rows are first evaluated inside witness generation (kind "fused", no check
+    launch for the segment); a poke sends the segment back to the check kernel, which must then find the fault."""
     rng = random.Random(seed)
     mx_i = 2 ** bits
     k = bits + 1
@@ -63,7 +65,8 @@ def poked_range_segment(make_composer, ob, n: int, gadget: str = "range_check", 
         targets["O"] = (4 * k + 10, 2)
     instances = sorted({0, 1, 31, 32, 127, 128, n // 2 + 5, n - 129, n - 2, n - 1} & set(range(n)))
     for mode in modes:
-        c = make_composer(check_mode=mode)
+        c = make_composer(check_mode=mode, fused_check=True) if fused else make_composer(check_mode=mode)
+        c.check_stats(reset=True)
         w = c.add_input(ob.from_ints(wit))
         if per_instance_bounds:
             mxs = ob.from_ints([mx_i - (i % 7) for i in range(n)])       # bitlen(max - 1) stays `bits`
@@ -73,11 +76,17 @@ def poked_range_segment(make_composer, ob, n: int, gadget: str = "range_check", 
         y = pg.range_check(c, mns, mxs, w) if gadget == "range_check" else pg.max_bound(c, mxs, w)[0]
         base_row, base_var = 3, 5 + n
         assert c.circuit_size() == base_row + rows_per * n and c.num_variables() == base_var + vars_per * n
-        c.check_stats(reset=True)
-        assert c.check_circuit_satisfied() == (0, None)
-        stats = c.check_stats(reset=True)
-        if expect_kind and expect_kind.get(mode):
-            assert stats[expect_kind[mode]][1] >= rows_per * n, (mode, stats)
+        if fused:                                           # evaluated while generated; pg_check launches for the 3 fresh rows only
+            assert mode == pg.CHECK_SPARSE
+            assert c.check_circuit_satisfied() == (0, None)
+            stats = c.check_stats(reset=True)
+            assert stats["fused"][1] == rows_per * n and stats["program"][1] == 0 and stats["instance_generic"][1] == 0, stats
+        else:
+            c.check_stats(reset=True)
+            assert c.check_circuit_satisfied() == (0, None)
+            stats = c.check_stats(reset=True)
+            if expect_kind and expect_kind.get(mode):
+                assert stats[expect_kind[mode]][1] >= rows_per * n, (mode, stats)
         # single pokes: every named Variable, in rotating instances
         names = sorted(targets)
         for t_i, name in enumerate(names):

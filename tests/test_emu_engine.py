@@ -333,6 +333,19 @@ def test_emu_poked_range_segment(emu, oracle, gadget, bits, per_inst):
                            per_instance_bounds=per_inst, expect_kind={pg.CHECK_GENERIC: "instance_generic", pg.CHECK_SPARSE: "program"})
 
 
+def test_emu_fused_check(emu, golden, oracle):
+    """PG_F_FUSED_CHECK: rows evaluated inside witness generation give the verdicts of the separate check, and a poked segment
+    falls back to the check kernel."""
+    for name in ("batch_mixed_circuit", "batch_max_bound_k8_claims", "kat_range_check_1_wrongclaim", "batch_range_check_k65_per_instance_bounds"):
+        spec = golden[name]
+        snap = run_engine(spec["program"], lambda: pg.StandardComposer(check_mode=pg.CHECK_SPARSE, fused_check=True, _cdll=emu), oracle)
+        assert snap.unsat == spec["expected"]["unsat"], name
+        assert snap.digest() == spec["expected"]["digest"], name
+    for gadget, bits, per_inst in (("range_check", 8, False), ("max_bound", 12, True), ("range_check", 64, False)):
+        fc.poked_range_segment(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle, n=131, gadget=gadget, bits=bits, per_instance_bounds=per_inst,
+                               modes=(pg.CHECK_SPARSE,), expect_kind={pg.CHECK_SPARSE: "program"}, fused=True)
+
+
 def test_emu_is_non_zero_flags(emu, oracle):
     fc.non_zero_flags_vs_oracle(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)
 
