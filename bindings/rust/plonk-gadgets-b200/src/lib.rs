@@ -7,6 +7,7 @@
 //!
 //! `Variable(pub(crate) usize)` cannot be forged outside dusk-plonk, so batched calls return `Variables` (a column id plus
 //! the reference's Variable numbering `first + i*stride`) instead of `Variable`s.
+pub mod import;
 use dusk_plonk::prelude::BlsScalar;
 pub use plonk_gadgets::{AllocatedScalar, Error};
 use plonk_gadgets_b200_sys as sys;
@@ -162,6 +163,12 @@ impl BatchComposer {
         self.ok(unsafe { sys::pg_gather_variables(self.ctx, call, out.as_mut_ptr() as *mut sys::pg_fr, total as u64, 0, &mut got) })?;
         out.truncate(got as usize);
         Ok(out)
+    }
+    /// Writes the whole composer (calls, Variable values, wire ids, selector columns, dense PI) to `path` for `import::import_into`.
+    pub fn export(&mut self, path: &std::path::Path, with_sigma: bool) -> Result<(), EngineError> {
+        let c = std::ffi::CString::new(path.to_str().expect("utf-8 path")).expect("no NUL in path");
+        self.ok(unsafe { sys::pg_export_composer(self.ctx, c.as_ptr(), 0, if with_sigma { 1 } else { 0 }) })?;
+        Ok(())
     }
     /// Rows and variables appended so far (`circuit_size()`, `variables.len()`).
     pub fn counts(&self) -> (u64, u64) {

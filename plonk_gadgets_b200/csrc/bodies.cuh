@@ -38,6 +38,9 @@ PG_HD const Fr& pow2_entry(uint32_t i) {
 enum { CNT_UNSAT = 0, CNT_FIRST_BAD = 1, CNT_MIXED_BITS = 2, CNT_N_ERR = 3, CNT_FIRST_ERR = 4, CNT_STICKY = 5,
        CNT_BAD_INPUT = 5, CNT_FIRST_BAD_INPUT = 6, CNT_FUSED_UNSAT = 7, CNT_FUSED_FIRST = 8, CNT_WORDS = 12 };
 
+// rows [local_base, local_end) of a segment verified inside witness generation, and the index its first row has in the numbering asked for
+struct FusedSpan { unsigned long long local_base, local_end, global_base; };
+
 PG_HD void counter_add(unsigned long long* c, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
     atomicAdd(c, v);

@@ -46,9 +46,21 @@ inline NcclApi& nccl_api() { static NcclApi api; return api; }
 
 static_assert(sizeof(ncclUniqueId) == PG_COMM_ID_BYTES, "PG_COMM_ID_BYTES must be sizeof(ncclUniqueId)");
 
-// pack the verdict words for the all-reduce: v[0] = n_unsat, v[1] = n_err (sum); v[2] = first bad row (min)
-__global__ void k_verdict_pack(const unsigned long long* counters, unsigned long long n_err, unsigned long long* v) {
-    v[0] = counters[CNT_UNSAT]; v[1] = n_err; v[2] = counters[CNT_FIRST_BAD]; v[3] = counters[CNT_BAD_INPUT];
+// pack the verdict words for the all-reduce: v[0] = n_unsat, v[1] = n_err (sum); v[2] = first bad row (min); v[3] = unreduced inputs.
+// Rows that were evaluated inside witness generation (PG_F_FUSED_CHECK) recorded their verdict in CNT_FUSED_* with the local row
+// numbering of the time; `map` lists those segments so that the first bad row is renumbered like the launched checks are.
+__global__ void k_verdict_pack(const unsigned long long* counters, unsigned long long n_err, unsigned long long* v, const FusedSpan* map, uint32_t n_map) {
+    unsigned long long unsat = counters[CNT_UNSAT], first = counters[CNT_FIRST_BAD];
+    if (n_map) {
+        unsat += counters[CNT_FUSED_UNSAT];
+        unsigned long long ff = counters[CNT_FUSED_FIRST];
+        if (ff != ~0ull) {
+            for (uint32_t k = 0; k < n_map; k++)
+                if (ff >= map[k].local_base && ff < map[k].local_end) { ff = map[k].global_base + (ff - map[k].local_base); break; }
+            first = ff < first ? ff : first;
+        }
+    }
+    v[0] = unsat; v[1] = n_err; v[2] = first; v[3] = counters[CNT_BAD_INPUT];
 }
 
 struct Comm {
@@ -76,9 +88,9 @@ struct Comm {
         d_words = nullptr; rank = 0; world = 1;
     }
     // (sum n_unsat, sum n_err, min first_bad, sum bad inputs) over the ranks, from this rank's device counters; returns after the result arrived
-    bool allreduce_verdict(const unsigned long long* d_counters, unsigned long long n_err, unsigned long long out[4], cudaStream_t stream) {
+    bool allreduce_verdict(const unsigned long long* d_counters, unsigned long long n_err, unsigned long long out[4], const FusedSpan* d_map, uint32_t n_map, cudaStream_t stream) {
         NcclApi& api = nccl_api();
-        k_verdict_pack<<<1, 1, 0, stream>>>(d_counters, n_err, d_words);
+        k_verdict_pack<<<1, 1, 0, stream>>>(d_counters, n_err, d_words, d_map, n_map);
         ncclResult_t r = api.GroupStart(); if (r != ncclSuccess) return fail("ncclGroupStart", r);
         r = api.AllReduce(d_words, d_words, 2, ncclUint64, ncclSum, comm, stream); if (r != ncclSuccess) { api.GroupEnd(); return fail("ncclAllReduce(sum)", r); }
         r = api.AllReduce(d_words + 2, d_words + 2, 1, ncclUint64, ncclMin, comm, stream); if (r != ncclSuccess) { api.GroupEnd(); return fail("ncclAllReduce(min)", r); }

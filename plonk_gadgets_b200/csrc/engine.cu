@@ -371,11 +371,11 @@ public:
     }
     bool comm_init(const uint8_t* id, int rank, int world) { join_copies(); if (comm.active()) comm.destroy(); return comm.init(id, rank, world); }
     void comm_destroy() { comm.destroy(); }
-    bool comm_verdict(const unsigned long long* d_counters, unsigned long long n_err, unsigned long long out[4]) {
+    bool comm_verdict(const unsigned long long* d_counters, unsigned long long n_err, unsigned long long out[4], const FusedSpan* d_map, uint32_t n_map) {
         join_copies();
-        if (comm.active()) return comm.allreduce_verdict(d_counters, n_err, out, stream);
+        if (comm.active()) return comm.allreduce_verdict(d_counters, n_err, out, d_map, n_map, stream);
         if (!d_verdict) PG_CUDA(cudaMalloc(&d_verdict, 4 * sizeof(unsigned long long)));
-        k_verdict_pack<<<1, 1, 0, stream>>>(d_counters, n_err, d_verdict);
+        k_verdict_pack<<<1, 1, 0, stream>>>(d_counters, n_err, d_verdict, d_map, n_map);
         PG_CUDA(cudaMemcpyAsync(out, d_verdict, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaStreamSynchronize(stream));
         return true;

@@ -767,9 +767,24 @@ public:
             if (mine[k].inst_hi - mine[k].inst_lo != segs[k + 1].n_inst) return fail(PG_ERR_ARG, "check_sharded: a call's instance count differs from its planned range");
         int rc = reset_counters();
         if (rc) return rc;
-        if ((rc = enqueue_checks(mine, be.comm_rank() == 0))) return rc;
+        if ((rc = enqueue_checks(mine, be.comm_rank() == 0, true))) return rc;
+        // segments whose rows were evaluated inside witness generation: their recorded verdict joins in, renumbered like the launched checks
+        std::vector<FusedSpan> spans;
+        for (size_t k = 0; k < segs.size(); k++) {
+            const Segment& s = segs[k];
+            if (!s.fused_ok || !s.n_inst) continue;
+            spans.push_back(FusedSpan{s.base_row, s.base_row + s.n_inst * s.t.rows.size(), (mine && k > 0) ? mine[k - 1].row_base : s.base_row});
+        }
+        const FusedSpan* d_spans = nullptr;
+        if (!spans.empty()) {
+            void* d = dalloc(spans.size() * sizeof(FusedSpan));
+            if (!d) return fail(PG_ERR_OOM, "fused span table");
+            scratch.push_back(d);
+            if (!be.h2d(d, spans.data(), spans.size() * sizeof(FusedSpan))) return fail(PG_ERR_CUDA, "fused span upload");
+            d_spans = (const FusedSpan*)d;
+        }
         unsigned long long v[4];
-        if (!be.comm_verdict(d_counters, n_err ? *n_err : 0ull, v)) return fail(PG_ERR_CUDA, std::string("verdict all-reduce: ") + be.comm_error());
+        if (!be.comm_verdict(d_counters, n_err ? *n_err : 0ull, v, d_spans, (uint32_t)spans.size())) return fail(PG_ERR_CUDA, std::string("verdict all-reduce: ") + be.comm_error());
         validation_pending = false;
         if (v[3]) return fail(PG_ERR_ARG, "input scalar(s) not fully reduced (>= q) on some rank: reset the composers");
         if (n_unsat) *n_unsat = v[0];

@@ -90,19 +90,32 @@ def main():
     emit("C3: 2^22 max_bound, per-instance 252-bit bounds (k=253, 511 rows each)", 511 * n, ms, tim)
     del mx3, wit3
 
-    # ---- C4: 2^24 x (is_non_zero + maybe_equal)
+    # ---- C4: 2^24 x (is_non_zero + maybe_equal), as SURVEY.md 8d specifies it: value uniform Fr with 1/1024 forced zero (the
+    #      NonExistingInverse path: every Result kept, pg_is_non_zero_batch_flags), value_assigned = value except 1/1024 mismatches
+    #      (their assert_equal row is unsatisfied); maybe_equal with 50 % a = b
     n = 1 << 24
     a = torch.empty((n, 4), dtype=torch.int64, device=dev); b = torch.empty_like(a)
     c.synth(SEED, 41, 0, 0, a); c.synth(SEED, 42, 0, 0, b); b[0::2] = a[0::2]
+    assigned = a.clone()
+    assigned[1023::1024] = 0                                 # forced zeros: Err(NonExistingInverse), row var*inv - 1 unsatisfied (and var != 0: assert_equal too)
+    assigned[511::1024] = b[511::1024]                       # mismatches (odd index: b != a): assert_equal and var*inv - 1 unsatisfied
+    flags = torch.empty(n, dtype=torch.uint8, device=dev)
+    n_zero, n_mis = n // 1024, n // 1024
 
     def c4():
         c.reset(); va = c.add_input(a); vb = c.add_input(b)
-        pg.maybe_equal(c, va, vb); pg.is_non_zero(c, va, a)
-        bad, _ = c.check_circuit_satisfied(); assert bad == 0
-    ms, tim, _ = timed(c, c4)
-    emit("C4: 2^24 x (is_non_zero + maybe_equal): 2^25 inversions, 6 rows per pair", 6 * n, ms, tim,
-         {"inversions_per_s": 2 * n / (ms * 1e-3)})
-    del a, b
+        pg.maybe_equal(c, va, vb)
+        pg.is_non_zero_flags(c, va, assigned, pg.NZ_UNIFORM, flags_out=flags)
+        assert c.last_n_err == n_zero
+        bad, first = c.check_circuit_satisfied()
+        assert bad == 2 * n_zero + 2 * n_mis, (bad, n_zero, n_mis)      # assert_equal AND var*inv - 1 fail in both kinds of instance
+        return first
+    ms, tim, first = timed(c, c4)
+    assert int(flags.sum().item()) == n_zero and bool(flags[1023::1024].all())
+    assert first == 3 + 3 * n + 3 * 511                      # the assert_equal row of the first mismatching instance (rows: 3 fresh, 3n maybe_equal)
+    emit("C4: 2^24 x (is_non_zero + maybe_equal): 2^25 inversions, 6 rows per pair; 1/1024 zeros (per-instance NonExistingInverse flags) and 1/1024 mismatches", 6 * n, ms, tim,
+         {"inversions_per_s": 2 * n / (ms * 1e-3), "n_err": n_zero, "n_unsat": 2 * n_zero + 2 * n_mis})
+    del a, b, assigned, flags
 
     # ---- C5: mixed circuit, 2^26 rows: range_check k=65 / max_bound k=253 / is_non_zero / select_one+select_zero, a quarter each
     q = 1 << 24

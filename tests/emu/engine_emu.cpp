@@ -86,7 +86,19 @@ public:
     static bool comm_unique_id(uint8_t*) { return false; }
     bool comm_init(const uint8_t*, int, int) { return false; }
     void comm_destroy() {}
-    bool comm_verdict(const unsigned long long* c, unsigned long long n_err, unsigned long long out[4]) { out[0] = c[CNT_UNSAT]; out[1] = n_err; out[2] = c[CNT_FIRST_BAD]; out[3] = c[CNT_BAD_INPUT]; return true; }
+    bool comm_verdict(const unsigned long long* c, unsigned long long n_err, unsigned long long out[4], const FusedSpan* map, uint32_t n_map) {
+        unsigned long long unsat = c[CNT_UNSAT], first = c[CNT_FIRST_BAD];
+        if (n_map) {
+            unsat += c[CNT_FUSED_UNSAT];
+            unsigned long long ff = c[CNT_FUSED_FIRST];
+            if (ff != ~0ull) {
+                for (uint32_t k = 0; k < n_map; k++) if (ff >= map[k].local_base && ff < map[k].local_end) { ff = map[k].global_base + (ff - map[k].local_base); break; }
+                if (ff < first) first = ff;
+            }
+        }
+        out[0] = unsat; out[1] = n_err; out[2] = first; out[3] = c[CNT_BAD_INPUT];
+        return true;
+    }
     bool comm_counts(unsigned long long mine, unsigned long long* counts) { counts[0] = mine; return true; }
     bool comm_gather(const void* send, void* recv, const unsigned long long* counts) { memcpy(recv, send, (size_t)counts[0] * 32); return true; }
     pg_check_stats ck{};

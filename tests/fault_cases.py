@@ -81,6 +81,8 @@ def poked_range_segment(make_composer, ob, n: int, gadget: str = "range_check", 
             assert c.check_circuit_satisfied() == (0, None)
             stats = c.check_stats(reset=True)
             assert stats["fused"][1] == rows_per * n and stats["program"][1] == 0 and stats["instance_generic"][1] == 0, stats
+            assert c.check_sharded(None, 0) == (0, None, 0)  # the sharded verdict takes the recorded result too (no launch for the segment)
+            assert c.check_stats(reset=True)["program"][1] == 0
         else:
             c.check_stats(reset=True)
             assert c.check_circuit_satisfied() == (0, None)

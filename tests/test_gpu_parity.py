@@ -796,7 +796,7 @@ def test_poked_max_bound_k253(oracle):
     fc.poked_range_segment(gpu_composer, oracle, n=HEADLINE_N, gadget="max_bound", bits=252, expect_kind=KINDS, seed=7)
 
 
-def test_fused_check_at_the_headline_launch_shape(gpu_composer, oracle):
+def test_fused_check_at_the_headline_launch_shape(oracle):
     """PG_F_FUSED_CHECK: the range gadgets' witness kernels evaluate the rows they generate (kind "fused": no check launch for the
     segment); overwriting a Variable sends the segment back to k_check_prog, which must report exactly the big-int verdict."""
     fc.poked_range_segment(gpu_composer, oracle, n=HEADLINE_N, gadget="range_check", bits=64, modes=(pg.CHECK_SPARSE,),
