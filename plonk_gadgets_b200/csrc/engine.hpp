@@ -1412,14 +1412,8 @@ public:
         if (!n) return PG_OK;
         const size_t mark = scratch.size();
         int rc; const uint4* ds = stage(scalars, n, on_device, &rc); if (!ds) return rc;
-        uint4* d_out = reinterpret_cast<uint4*>(out);
-        if (!on_device) { d_out = (uint4*)dalloc(n * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "point buffer"); scratch.push_back(d_out); }
-        G1FixedBaseMulBody::Args a; a.scalars = ds; a.out = d_out; a.n = n;
-        if (base) memcpy(&a.base, base, sizeof(G1Affine)); else a.base = g1_generator();      // base is always a host pointer (one point)
-        if (!be.template run_simple<G1FixedBaseMulBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base kernel");
-        if (on_device) return PG_OK;
-        rc = deliver(out, d_out, n * sizeof(pg_g1_affine), 0);
-        release_scratch_from(mark);
+        rc = g1_fixed_base_mul_dev(n, base, ds, out, on_device);
+        if (!on_device) release_scratch_from(mark);      // (host results: g1_fixed_base_mul_dev has synchronised)
         return rc;
     }
     // the same with the scalars already in device memory and the result in host or device memory
@@ -1427,10 +1421,29 @@ public:
         const size_t mark = scratch.size();
         uint4* d_out = reinterpret_cast<uint4*>(out);
         if (!out_on_device) { d_out = (uint4*)dalloc(n * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "point buffer"); scratch.push_back(d_out); }
-        G1FixedBaseMulBody::Args a; a.scalars = d_scalars; a.out = d_out; a.n = n;
-        if (base) memcpy(&a.base, base, sizeof(G1Affine)); else a.base = g1_generator();
-        if (!be.template run_simple<G1FixedBaseMulBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base kernel");
-        if (out_on_device) return PG_OK;
+        G1Affine b;
+        if (base) memcpy(&b, base, sizeof(G1Affine)); else b = g1_generator();
+        if (n >= FB_MIN_POINTS) {
+            // windowed table of multiples of the base, then tiles of FB_TILE scalars: <= 32 mixed additions each, batch normalisation
+            const uint64_t n_table = (uint64_t)FB_WINDOWS * FB_ENTRIES, tile = std::min<uint64_t>(n, FB_TILE);
+            uint4* table = (uint4*)dalloc(n_table * sizeof(pg_g1_affine));
+            uint4* xyzz = (uint4*)dalloc(tile * sizeof(G1X)); uint4* prefix = (uint4*)dalloc(tile * sizeof(Fp));
+            if (!table || !xyzz || !prefix) return fail(PG_ERR_OOM, "fixed-base buffers");
+            scratch.push_back(table); scratch.push_back(xyzz); scratch.push_back(prefix);
+            G1WindowTableBody::Args ta; ta.table = table; ta.n = n_table; ta.base = b;
+            if (!be.template run_simple<G1WindowTableBody>(ta, n_table, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base table kernel");
+            for (uint64_t i0 = 0; i0 < n; i0 += tile) {
+                const uint64_t cnt = std::min<uint64_t>(tile, n - i0), threads = (cnt + FB_CHUNK - 1) / FB_CHUNK;
+                G1FixedBaseWindowedBody::Args wa{d_scalars + 2 * i0, table, xyzz, cnt};
+                G1BatchAffineBody::Args na{xyzz, prefix, d_out + 6 * i0, threads, cnt};
+                if (!be.template run_simple<G1FixedBaseWindowedBody>(wa, cnt, CLS_OTHER) || !be.template run_simple<G1BatchAffineBody>(na, threads, CLS_OTHER))
+                    return fail(PG_ERR_CUDA, "fixed-base kernels");
+            }
+        } else {
+            G1FixedBaseMulBody::Args a; a.scalars = d_scalars; a.out = d_out; a.n = n; a.base = b;
+            if (!be.template run_simple<G1FixedBaseMulBody>(a, n, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base kernel");
+        }
+        if (out_on_device) { release_scratch_from(mark); return PG_OK; }      // work buffers are only touched on the engine's stream
         const int rc = deliver(out, d_out, n * sizeof(pg_g1_affine), 0);
         release_scratch_from(mark);
         return rc;
@@ -1439,13 +1452,14 @@ public:
     int srs_powers(const pg_fr* beta, const pg_g1_affine* base, uint64_t n, pg_g1_affine* out, int out_on_device) {
         if (!beta || (n && !out)) return fail(PG_ERR_ARG, "srs_powers: null argument");
         if (!n) return PG_OK;
-        std::vector<pg_fr> pw(n);                                       // util::powers_of(beta, n)
-        Fr b, e = fr_one(); memcpy(&b, beta, sizeof(Fr));
-        for (uint64_t i = 0; i < n; i++) { memcpy(&pw[i], &e, sizeof(Fr)); e = fr_mul(e, b); }
-        if (!out_on_device) return g1_fixed_base_mul(n, base, pw.data(), out, 0);
         const size_t mark = scratch.size();
-        int rc; const uint4* ds = stage(pw.data(), n, 0, &rc); if (!ds) return rc;
-        rc = g1_fixed_base_mul(n, base, reinterpret_cast<const pg_fr*>(ds), out, 1);
+        uint4* pw = (uint4*)dalloc(n * sizeof(pg_fr));                     // util::powers_of(beta, n), on the device
+        if (!pw) return fail(PG_ERR_OOM, "powers of beta");
+        scratch.push_back(pw);
+        FrPowersBody::Args pa; memcpy(&pa.beta, beta, sizeof(Fr)); pa.out = pw; pa.n = (n + FRPOW_CHUNK - 1) / FRPOW_CHUNK; pa.n_points = n;
+        if (!host_reduced(*beta)) return fail(PG_ERR_ARG, "srs_powers: beta not fully reduced (>= q)");
+        if (!be.template run_simple<FrPowersBody>(pa, pa.n, CLS_OTHER)) return fail(PG_ERR_CUDA, "powers kernel");
+        const int rc = g1_fixed_base_mul_dev(n, base, pw, out, out_on_device);
         if (!be.sync()) return fail(PG_ERR_CUDA, "sync");
         release_scratch_from(mark);
         return rc;

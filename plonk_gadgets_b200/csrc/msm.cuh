@@ -197,6 +197,83 @@ struct G1FixedBaseMulBody {
     }
 };
 
+// util::powers_of(beta, n): out[i] = beta^i.  Thread t owns i in [64t, 64t + 64): beta^(64t) by square-and-multiply, then 63 products.
+constexpr uint64_t FRPOW_CHUNK = 64;
+struct FrPowersBody {
+    struct Args { Fr beta; uint4* out; uint64_t n; uint64_t n_points; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        Fr acc = fr_one(), sq = a.beta;
+#pragma unroll 1
+        for (uint64_t e = t * FRPOW_CHUNK; e; e >>= 1) { if (e & 1) acc = fr_mul(acc, sq); sq = fr_mul(sq, sq); }
+        const uint64_t lo = t * FRPOW_CHUNK, hi = lo + FRPOW_CHUNK < a.n_points ? lo + FRPOW_CHUNK : a.n_points;
+#pragma unroll 1
+        for (uint64_t i = lo; i < hi; i++) { aos_store(a.out, i, acc); acc = fr_mul(acc, a.beta); }
+    }
+};
+
+// The same through a windowed table of multiples of the base (used from FB_MIN_POINTS scalars on): table[w * 255 + d - 1] =
+// d * 2^(8w) * base for the 32 byte-windows of a scalar, so that one scalar multiplication is at most 32 mixed additions instead of
+// 255 doublings + ~128 additions; the XYZZ results are normalised to affine with Montgomery's trick (one inversion per FB_CHUNK points).
+// The accumulated scalar stays below q < the group order at every step, so an addition never meets its own operand (no doubling
+// case); the complete formulas cover it anyway.
+constexpr uint32_t FB_WINDOWS = 32, FB_ENTRIES = 255, FB_CHUNK = 32;
+constexpr uint64_t FB_MIN_POINTS = 512, FB_TILE = 1ull << 20;
+struct G1WindowTableBody {
+    struct Args { uint4* table; uint64_t n; G1Affine base; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        const uint32_t w = (uint32_t)(t / FB_ENTRIES), d = (uint32_t)(t % FB_ENTRIES) + 1u;
+        G1X p = g1x_from_affine(a.base);
+#pragma unroll 1
+        for (uint32_t j = 0; j < 8u * w; j++) p = g1x_dbl(p);                       // 2^(8w) * base
+        g1_affine_store(a.table, t, g1x_to_affine<true>(g1x_mul_limbs(p, &d, 1)));
+    }
+};
+struct G1FixedBaseWindowedBody {
+    struct Args { const uint4* scalars; const uint4* table; uint4* xyzz; uint64_t n; };
+    PG_HD static void run(const Args& a, uint64_t i) {
+        const Fr k = fr_from_mont(aos_load(a.scalars, i));
+        G1X acc = g1x_inf();
+#pragma unroll 1
+        for (uint32_t w = 0; w < FB_WINDOWS; w++) {
+            const uint32_t d = (k.v[w >> 2] >> (8u * (w & 3u))) & 255u;
+            if (d) acc = g1x_madd(acc, g1_affine_load(a.table, (uint64_t)w * FB_ENTRIES + d - 1u));
+        }
+        g1x_store(a.xyzz, i, acc);
+    }
+};
+// n_points XYZZ points -> affine.  Thread t owns the points t, t + n, t + 2n, ... (n = number of threads: neighbouring lanes touch
+// neighbouring points); prefix products of Z^5 = zz*zzz are parked in `prefix`, one inversion per thread.
+struct G1BatchAffineBody {
+    struct Args { const uint4* xyzz; uint4* prefix; uint4* out; uint64_t n; uint64_t n_points; };
+    PG_HD static void run(const Args& a, uint64_t t) {
+        Fp p = fp_one();
+        uint64_t last = t;
+#pragma unroll 1
+        for (uint64_t e = t; e < a.n_points; e += a.n) {
+            const G1X P = g1x_load(a.xyzz, e);
+            if (!g1x_is_inf(P)) p = fp_mul(p, fp_mul(P.zz, P.zzz));
+            fp_store(a.prefix + 3 * e, p);
+            last = e;
+        }
+        Fp inv = fp_inv_fermat(p);                                                   // fixed-length chain: the lanes stay in step
+#pragma unroll 1
+        for (uint64_t e = last;; e -= a.n) {
+            const G1X P = g1x_load(a.xyzz, e);
+            if (g1x_is_inf(P)) g1_affine_store(a.out, e, g1_affine_inf());
+            else {
+                const Fp prev = e >= a.n + t ? fp_load(a.prefix + 3 * (e - a.n)) : fp_one();
+                const Fp i5 = fp_mul(inv, prev);                                     // (zz*zzz)^-1 of this point
+                inv = fp_mul(inv, fp_mul(P.zz, P.zzz));
+                G1Affine q;
+                q.x = fp_mul(P.x, fp_mul(i5, P.zzz));                                // X / ZZ
+                q.y = fp_mul(P.y, fp_mul(i5, P.zz));                                 // Y / ZZZ
+                g1_affine_store(a.out, e, q);
+            }
+            if (e < a.n + t) break;
+        }
+    }
+};
+
 // Lagrange-basis SRS scalars: L_i(beta) = (beta^n - 1) / n * w^i / (beta - w^i), i < n, for the domain generated by w
 // (w^i from the NTT twiddle table: w^(i + n/2) = -w^i).  With powers [L_i(beta)] G a commitment can be computed from the
 // EVALUATIONS of a polynomial over the domain -- sum_i f(w^i) [L_i(beta)] G is the same group element as

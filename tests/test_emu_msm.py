@@ -48,6 +48,23 @@ def test_emu_group_law(emu, oracle):
     assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, 5, axis=0), sc))
 
 
+def test_emu_windowed_fixed_base(emu, oracle):
+    """From 512 scalars on pg_g1_fixed_base_mul / pg_srs_powers go through the table of window multiples and the batch
+    normalisation (msm.cuh: G1WindowTableBody, G1FixedBaseWindowedBody, G1BatchAffineBody) and the device-side powers of beta."""
+    c = pg.StandardComposer(_cdll=emu)
+    rnd = random.Random(21)
+    n = 530                                                  # not a multiple of the normalisation chunk
+    ks = [0, 1, 255, 256, 2 ** 248, Q - 1, 2 ** 64 - 1] + [rnd.randrange(Q) for _ in range(n - 7)]
+    ks[40] = 0; ks[n - 1] = 0                                # points at infinity inside and at the end of a chunk
+    sc = oracle.from_ints(ks)
+    g = oracle.g1_generator()
+    assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, n, axis=0), sc))
+    base = oracle.g1_mul(g, oracle.from_ints([rnd.randrange(Q)]))
+    assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc[:520], base=to_engine(base))), oracle.g1_mul(np.repeat(base, 520, axis=0), sc[:520]))
+    beta = oracle.from_ints([rnd.randrange(Q)])
+    assert np.array_equal(to_oracle(c.srs_powers(beta[0], 600)), oracle.srs_powers(beta, 600))
+
+
 @pytest.mark.parametrize("n", [1, 2, 7, 33, 100, 300])
 def test_emu_msm_matches_oracle(emu, oracle, n):
     c = pg.StandardComposer(_cdll=emu)

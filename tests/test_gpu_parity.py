@@ -534,6 +534,13 @@ def test_g1_group_law_gpu(oracle):
     assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, 64, axis=0), sc))
     beta = oracle.from_ints([rnd.randrange(Q)])
     assert np.array_equal(to_oracle(c.srs_powers(beta[0], 48)), oracle.srs_powers(beta, 48))
+    # from 512 scalars on: table of window multiples + batch normalisation, powers of beta computed on the device
+    n = 3000
+    ks = [0, 1, 255, 256, 2 ** 248, Q - 1] + [rnd.randrange(Q) for _ in range(n - 6)]
+    ks[77] = 0; ks[n - 1] = 0
+    sc = oracle.from_ints(ks)
+    assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, n, axis=0), sc))
+    assert np.array_equal(to_oracle(c.srs_powers(beta[0], 2500)), oracle.srs_powers(beta, 2500))
 
 
 @pytest.mark.parametrize("n", [1, 2, 7, 33, 100, 1000, 6000])
