@@ -302,7 +302,12 @@ public:
         if (smem > 48 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         const uint64_t total = a.n_inst * a.n_rows;
         tic(CLS_CHECK, total);
-        k_check_gates<<<(unsigned)((total + 127) / 128), 128, smem, stream>>>(a);
+        const unsigned grid = (unsigned)((total + 127) / 128);
+        switch (check_shape) {                                   // 24 warps/SM measured best (profiles/README.md, run r04i); shapes 1 / 3 for tuning runs
+            case 1: k_check_gates<5><<<grid, 128, smem, stream>>>(a); break;
+            case 3: k_check_gates<7><<<grid, 128, smem, stream>>>(a); break;
+            default: k_check_gates<6><<<grid, 128, smem, stream>>>(a); break;
+        }
         toc();
         count_check(PG_CK_GATES, total);
         return launched("k_check_gates");

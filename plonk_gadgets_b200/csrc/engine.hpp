@@ -57,6 +57,27 @@ struct Segment {
 // view is instance first + i of the owner (the SoA stride is the owner's)
 struct SegmentView { uint4* fr; uint64_t n_alloc; unsigned char* image; size_t image_bytes; };
 
+// Range templates are expensive to build on the host (k = 253: 1019 rows, 514 pool entries, ~0.2 ms with the structure-aware program),
+// and a caller that repeats a circuit (a prover loop, the benches) repeats them: the built template, and the resolved segment image
+// (rows with addresses, structure-aware program, extended pool) when the tables sit at the same device addresses, are kept.
+struct RangeTemplateKey {
+    int range_check; uint32_t k; int uniform; Fr m, negmin;
+    bool operator==(const RangeTemplateKey& o) const { return range_check == o.range_check && k == o.k && uniform == o.uniform && fr_eq(m, o.m) && fr_eq(negmin, o.negmin); }
+};
+struct ResolvedKey {
+    uint64_t n_alloc; const void *fr, *bits, *param; int check_mode; DevTab tab1; uint32_t op_loc, op_local;     // operand: its table, location and local index
+    bool operator==(const ResolvedKey& o) const {
+        return n_alloc == o.n_alloc && fr == o.fr && bits == o.bits && param == o.param && check_mode == o.check_mode && tab1.fr == o.tab1.fr &&
+               tab1.bits == o.tab1.bits && tab1.stride == o.tab1.stride && op_loc == o.op_loc && op_local == o.op_local;
+    }
+};
+struct CachedRange {
+    RangeTemplateKey key; Template t; uint32_t result_local = 0;
+    bool resolved = false; ResolvedKey rkey{}; std::vector<DevRow> rows; std::vector<SpOp> sp_ops; std::vector<Fr> pool; std::vector<unsigned char> img;
+    uint64_t stamp = 0;
+};
+constexpr size_t RANGE_CACHE_SLOTS = 16;
+
 inline Fr fr_from_pg(const pg_fr& x) {
     Fr r;
     for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)x.l[i]; r.v[2 * i + 1] = (uint32_t)(x.l[i] >> 32); }
@@ -78,6 +99,17 @@ public:
     std::multimap<size_t, void*> pool_free;          // size -> buffer (exact-size reuse across composer resets)
     std::map<void*, size_t> pool_live;
     std::vector<void*> scratch;                      // temporaries that must outlive the enqueued work (freed on reset)
+
+    std::vector<CachedRange> range_cache; uint64_t cache_clock = 0;
+    CachedRange* range_cache_get(const RangeTemplateKey& key) {            // the slot of `key`, built on a miss (the least recently used slot is replaced)
+        for (auto& c : range_cache) if (c.key == key) { c.stamp = ++cache_clock; return &c; }
+        CachedRange* slot;
+        if (range_cache.size() < RANGE_CACHE_SLOTS) { range_cache.emplace_back(); slot = &range_cache.back(); }
+        else { slot = &range_cache[0]; for (auto& c : range_cache) if (c.stamp < slot->stamp) slot = &c; *slot = CachedRange(); }
+        slot->key = key; slot->stamp = ++cache_clock;
+        slot->t = make_range_template(key.range_check != 0, key.k, key.uniform != 0, key.m, key.negmin, &slot->result_local);
+        return slot;
+    }
 
     // ------------------------------------------------------------------------------------------------ memory
     void* dalloc(size_t bytes) {
@@ -299,7 +331,7 @@ public:
     static size_t image_bytes_bound(const Template& T) {      // upper bound of a segment image (the structure-aware program has at most ~12 operations per row)
         return (T.rows.size() * (sizeof(DevRow) + 12 * sizeof(SpOp)) + T.var_loc.size() * sizeof(uint32_t) + (T.pool.size() + 8 * T.rows.size()) * sizeof(Fr) + 255) & ~(size_t)255;
     }
-    int push_segment(Template&& t, uint64_t n, const Column* operands, uint32_t n_operands, const SegmentView* view = nullptr) {
+    int push_segment(Template&& t, uint64_t n, const Column* operands, uint32_t n_operands, const SegmentView* view = nullptr, CachedRange* cache = nullptr) {
         Segment s;
         s.t = std::move(t);
         s.n_inst = n; s.n_alloc = n ? n : 1;
@@ -314,6 +346,13 @@ public:
         if (T.n_params) { s.param = (uint4*)dalloc((size_t)T.n_params * 2 * s.n_alloc * sizeof(uint4)); if (!s.param) return fail(PG_ERR_OOM, "parameter table"); }
         s.tabs[0].fr = s.fr; s.tabs[0].bits = s.bits; s.tabs[0].stride = s.n_alloc; s.tabs[0].var_base = s.base_var; s.tabs[0].var_stride = T.n_vars;
         for (uint32_t e = 0; e < n_operands; e++) { s.tabs[e + 1] = view_of(operands[e]); s.operands.push_back(operands[e]); }
+        ResolvedKey rk; memset(&rk, 0, sizeof(rk));
+        rk.n_alloc = s.n_alloc; rk.fr = s.fr; rk.bits = s.bits; rk.param = s.param; rk.check_mode = cfg.check_mode; rk.tab1 = s.tabs[1];
+        if (cache && n_operands == 1) { rk.op_loc = loc_of(operands[0]); rk.op_local = operands[0].local; }
+        std::vector<unsigned char> img;
+        if (cache && n_operands == 1 && !view && cache->resolved && cache->rkey == rk) {      // same template over tables at the same addresses: the image is known
+            s.rows = cache->rows; s.sp_ops = cache->sp_ops; s.t.pool = cache->pool; img = cache->img;
+        } else {
         s.rows.resize(T.rows.size());
         for (size_t r = 0; r < T.rows.size(); r++) {
             const RowT& src = T.rows[r]; DevRow d; memset(&d, 0, sizeof(d));
@@ -337,13 +376,19 @@ public:
         }
         if (cfg.check_mode == PG_CHECK_SPARSE && !s.other_gates) build_sparse_program(s);   // segments with range rows have their own check body
         // rows | variable map | selector pool | structure-aware program go up in ONE copy (one staging image per segment)
+        const size_t b_rows0 = s.rows.size() * sizeof(DevRow), b_var0 = (T.var_loc.size() * sizeof(uint32_t) + 31) & ~(size_t)31, b_pool0 = T.pool.size() * sizeof(Fr);
+        const size_t b_sp0 = s.sp_ops.size() * sizeof(SpOp);
+        img.resize(b_rows0 + b_var0 + b_pool0 + b_sp0);
+        if (b_sp0) memcpy(img.data() + b_rows0 + b_var0 + b_pool0, s.sp_ops.data(), b_sp0);
+        if (b_rows0) memcpy(img.data(), s.rows.data(), b_rows0);
+        if (!T.var_loc.empty()) memcpy(img.data() + b_rows0, T.var_loc.data(), T.var_loc.size() * sizeof(uint32_t));
+        memcpy(img.data() + b_rows0 + b_var0, T.pool.data(), b_pool0);
+        if (cache && n_operands == 1 && !view) {
+            cache->resolved = true; cache->rkey = rk; cache->rows = s.rows; cache->sp_ops = s.sp_ops; cache->pool = s.t.pool; cache->img = img;
+        }
+        }
         const size_t b_rows = s.rows.size() * sizeof(DevRow), b_var = (T.var_loc.size() * sizeof(uint32_t) + 31) & ~(size_t)31, b_pool = T.pool.size() * sizeof(Fr);
         const size_t b_sp = s.sp_ops.size() * sizeof(SpOp);
-        std::vector<unsigned char> img(b_rows + b_var + b_pool + b_sp);
-        if (b_sp) memcpy(img.data() + b_rows + b_var + b_pool, s.sp_ops.data(), b_sp);
-        if (b_rows) memcpy(img.data(), s.rows.data(), b_rows);
-        if (!T.var_loc.empty()) memcpy(img.data() + b_rows, T.var_loc.data(), T.var_loc.size() * sizeof(uint32_t));
-        memcpy(img.data() + b_rows + b_var, T.pool.data(), b_pool);
         if (view && img.size() > view->image_bytes) return fail(PG_ERR_STATE, "segment view: image larger than its reserved memory");
         unsigned char* d_img = view ? view->image : (unsigned char*)dalloc(img.size());
         if (!d_img || !be.h2d(d_img, img.data(), img.size())) return fail(d_img ? PG_ERR_CUDA : PG_ERR_OOM, "template upload");
@@ -479,7 +524,12 @@ public:
         }
         uint32_t result_local = 0;
         Column operand = *w;
-        rc = push_segment(make_range_template(is_range_check, k, uniform, m0, negmin0, &result_local), n, &operand, 1);
+        RangeTemplateKey tkey; memset(&tkey, 0, sizeof(tkey));
+        tkey.range_check = is_range_check ? 1 : 0; tkey.k = k; tkey.uniform = uniform ? 1 : 0;
+        if (uniform) { tkey.m = m0; tkey.negmin = negmin0; }          // (per-instance bounds: the template holds parameter slots, not values)
+        CachedRange* cached = range_cache_get(tkey);
+        result_local = cached->result_local;
+        { Template tcopy = cached->t; rc = push_segment(std::move(tcopy), n, &operand, 1, nullptr, cached); }
         if (rc) return rc;
         Segment& s = segs.back();
         RangeArgs a; memset(&a, 0, sizeof(a));

@@ -253,7 +253,9 @@ __global__ void __launch_bounds__(128, 5) k_check_rowpar(const CheckArgs a) {
 }
 
 // Segments with rows of the range widget (bodies.cuh GateRowsCheckBody): thread = one row of one instance, lanes = instances.
-__global__ void __launch_bounds__(128, 5) k_check_gates(const CheckArgs a) {
+// MINB: blocks per SM (5 -> 96 registers, 20 warps/SM; 6 -> 80 registers, 24 warps/SM; 7 -> 72 registers, 28 warps/SM).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_check_gates(const CheckArgs a) {
     extern __shared__ __align__(16) uint32_t s_pool[];
     __shared__ uint32_t s_q[8];
     for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += 128) s_pool[t] = a.pool[t];

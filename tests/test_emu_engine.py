@@ -346,6 +346,36 @@ def test_emu_fused_check(emu, golden, oracle):
                                modes=(pg.CHECK_SPARSE,), expect_kind={pg.CHECK_SPARSE: "program"}, fused=True)
 
 
+@pytest.mark.parametrize("mode", [pg.CHECK_GENERIC, pg.CHECK_SPARSE])
+def test_emu_template_cache_reuse(emu, golden, oracle, mode):
+    """A ctx keeps built range templates and resolved segment images across composer resets (engine.hpp range_cache): programs
+    repeated and interleaved on ONE ctx must give the states fresh contexts give -- same bounds on another operand column, other
+    bounds on the same tables, per-instance bounds, and a poke in between (the cache holds structure, never values)."""
+    shared = pg.StandardComposer(check_mode=mode, _cdll=emu)
+    def reuse():
+        shared.reset()
+        return shared
+    names = ["batch_range_check_k65", "batch_max_bound_k8_claims", "batch_range_check_k65", "batch_range_check_k65_per_instance_bounds",
+             "batch_mixed_circuit", "kat_range_check_1_wrongclaim", "batch_max_bound_k8_claims", "batch_mixed_circuit", "kat_range_check_0_ok",
+             "kat_range_check_1_ok", "batch_range_check_k65"]
+    for name in names:
+        spec = golden[name]
+        snap = run_engine(spec["program"], reuse, oracle)
+        assert snap.unsat == spec["expected"]["unsat"], name
+        assert snap.digest() == spec["expected"]["digest"], name
+    # the same bounds over two different operand columns of one segment layout
+    xs = [3, 200, 70000, 2 ** 20]
+    for first in (True, False, True):
+        shared.reset()
+        a = shared.add_input(oracle.from_ints(xs)); b = shared.add_input(oracle.from_ints([x + 1 for x in xs]))
+        y = pg.range_check(shared, oracle.from_ints([100]), oracle.from_ints([70001]), a if first else b)
+        want = [1 if 100 <= (x if first else x + 1) < 70001 else 0 for x in xs]
+        assert oracle.to_ints(y.values()) == want
+        assert shared.check_circuit_satisfied() == (0, None)
+        w_idx = shared.rows(3, 4 * 18 + 11, want=("w_idx",))["w_idx"]
+        assert int(w_idx[0, 0]) == (5 if first else 5 + len(xs))          # the first row's wire is the operand's Variable
+
+
 def test_emu_is_non_zero_flags(emu, oracle):
     fc.non_zero_flags_vs_oracle(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)
 
