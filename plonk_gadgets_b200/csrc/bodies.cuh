@@ -671,34 +671,84 @@ struct CheckRowsBody {
 //                    "0 mod q" directly.  Inside a template a
 //                    range row is never the last one (range_gate closes with a q_range = 0 gate and assert_equal);
 //   rows with neither selector hold trivially.
+//   PG_CHECK_SPARSE: arithmetic rows through the structure-aware term evaluation, range rows through the digit test (see below).
 struct GateRowsCheckBody {
-    template <class PoolT>
-    PG_HD static bool row_ok(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint32_t r, uint64_t i) {
-        const DevRow row = a.rows[r];
-        if (row.gate == GATE_ARITH) return CheckBody::row_holds<0>(a, row, pool, q, i);
-        if (row.gate != GATE_RANGE) return true;
-        Fr w[5];                                                                // d, c, b, a, d_next: each term is D(w[k+1] - 4*w[k])
-        w[0] = row_load(row, 3, i); w[1] = row_load(row, 2, i); w[2] = row_load(row, 1, i); w[3] = row_load(row, 0, i);
-        w[4] = r + 1 < a.n_rows ? row_load(a.rows[r + 1], 3, i) : fr_zero();
+    // the range widget's term of one row: w = d, c, b, a, d_next (each term is D(w[k+1] - 4*w[k]))
+    PG_HD static bool range_row_holds(const Fr* w, const QRegs& q, int mode) {
         const Fr one = fr_one(), three = fr_add(fr_add(one, one), one);
-        Fr u[4];
+        Fr f[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {                                           // unrolled: everything stays in registers
             Fr l4 = fr_add(w[k], w[k]); l4 = fr_add(l4, l4);
-            const Fr f = fr_sub(w[k + 1], l4);
-            u[k] = fr_add(fr_mul_eo(f, fr_sub(f, three), q), one);              // u = f(f-3) + 1
+            f[k] = fr_sub(w[k + 1], l4);
         }
+        if (mode != 0) {
+            // structure-aware: D(f) = f(f-1)(f-2)(f-3) vanishes iff f is a base-4 digit (a field has no zero divisors), so a row whose
+            // four differences all are digits holds and nothing is multiplied; any other row goes through the polynomial below -- the
+            // verdict is the same for every witness.  Lanes of a warp share the row, so honest batches never leave the fast path.
+            const Fr two = fr_add(one, one);
+            bool digits = true;
+#pragma unroll
+            for (int k = 0; k < 4; k++) digits = digits && (fr_is_zero(f[k]) || fr_eq(f[k], one) || fr_eq(f[k], two) || fr_eq(f[k], three));
+            if (digits) return true;
+        }
+        Fr u[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) u[k] = fr_add(fr_mul_eo(f[k], fr_sub(f[k], three), q), one);   // u = f(f-3) + 1
         uint32_t t[9];
         fr_dot_wide<4>(t, u, u, q);                                             // sum u_k^2 ...
         add9_fr(t, fr_neg(fr_add(three, one)));                                 // ... - 4  =  sum D(f_k)
         return limbs9_is_multiple_of_q(t);
     }
     template <class PoolT>
+    PG_HD static bool arith_row_holds(const CheckArgs& a, const DevRow& row, const PoolT& pool, const QRegs& q, uint64_t i) {
+        return a.mode != 0 ? CheckBody::row_holds_sparse(a, row, pool, q, i) : CheckBody::row_holds<0>(a, row, pool, q, i);
+    }
+    template <class PoolT>
+    PG_HD static bool row_ok(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint32_t r, uint64_t i) {
+        const DevRow row = a.rows[r];
+        if (row.gate == GATE_ARITH) return arith_row_holds(a, row, pool, q, i);
+        if (row.gate != GATE_RANGE) return true;
+        Fr w[5];
+        w[0] = row_load(row, 3, i); w[1] = row_load(row, 2, i); w[2] = row_load(row, 1, i); w[3] = row_load(row, 0, i);
+        w[4] = r + 1 < a.n_rows ? row_load(a.rows[r + 1], 3, i) : fr_zero();
+        return range_row_holds(w, q, a.mode);
+    }
+    // one (row, instance) pair per call: segments too small to fill the chip with one thread per instance
+    template <class PoolT>
     PG_HD static uint32_t run_one(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint64_t t, unsigned long long& first_bad) {
         const uint32_t r = (uint32_t)(t / a.n_inst); const uint64_t i = t - (uint64_t)r * a.n_inst;
         if (row_ok(a, pool, q, r, i)) return 0u;
         first_bad = a.base_row + i * (uint64_t)a.n_rows + r;
         return 1u;
+    }
+    // one instance per call, rows walked in order (like CheckBody::run): the fourth wire of the next row -- needed as d_next by a range
+    // row -- is loaded once and kept as that row's own d; the next row's other wires are requested while this row is evaluated
+    template <class PoolT>
+    PG_HD static uint32_t run(const CheckArgs& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
+        uint32_t bad = 0, first_local = ~0u;
+        Fr d_cur = row_load(a.rows[0], 3, i);
+        for (uint32_t r = 0; r < a.n_rows; r++) {
+            const DevRow row = a.rows[r];
+            Fr d_next = fr_zero();
+            if (r + 1 < a.n_rows) {
+                const DevRow& nr = a.rows[r + 1];
+                d_next = row_load(nr, 3, i);
+#pragma unroll
+                for (int k = 0; k < 3; k++) row_prefetch(nr.loc[k], nr.addr[k], i);
+            }
+            bool ok = true;
+            if (row.gate == GATE_ARITH) ok = arith_row_holds(a, row, pool, q, i);
+            else if (row.gate == GATE_RANGE) {
+                Fr w[5];
+                w[0] = d_cur; w[1] = row_load(row, 2, i); w[2] = row_load(row, 1, i); w[3] = row_load(row, 0, i); w[4] = d_next;
+                ok = range_row_holds(w, q, a.mode);
+            }
+            if (!ok) { bad++; first_local = first_local < r ? first_local : r; }
+            d_cur = d_next;
+        }
+        if (bad) { const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + first_local; if (g < first_bad) first_bad = g; }
+        return bad;
     }
 };
 

@@ -302,6 +302,14 @@ public:
         if (smem > 48 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         const uint64_t total = a.n_inst * a.n_rows;
         tic(CLS_CHECK, total);
+        // PG_GATES_WALK=1 (tuning runs): one thread per instance walking the rows, for segments that fill the chip that way
+        static const int walk = getenv("PG_GATES_WALK") ? atoi(getenv("PG_GATES_WALK")) : 0;
+        if (walk && a.n_inst >= (uint64_t)sm_count * 320) {
+            k_check_gates_walk<<<(unsigned)((a.n_inst + 127) / 128), 128, smem, stream>>>(a);
+            toc();
+            count_check(PG_CK_GATES, total);
+            return launched("k_check_gates_walk");
+        }
         const unsigned grid = (unsigned)((total + 127) / 128);
         switch (check_shape) {                                   // 24 warps/SM measured best (profiles/README.md, run r04i); shapes 1 / 3 for tuning runs
             case 1: k_check_gates<5><<<grid, 128, smem, stream>>>(a); break;

@@ -280,6 +280,32 @@ __global__ void __launch_bounds__(128, MINB) k_check_gates(const CheckArgs a) {
     }
 }
 
+// The same segments with one thread per instance walking the rows (GateRowsCheckBody::run): large segments.
+__global__ void __launch_bounds__(128, 5) k_check_gates_walk(const CheckArgs a) {
+    extern __shared__ __align__(16) uint32_t s_pool[];
+    __shared__ uint32_t s_q[8];
+    for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += 128) s_pool[t] = a.pool[t];
+    if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
+    __syncthreads();
+    QRegs q;
+#pragma unroll
+    for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
+    const uint64_t i = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    unsigned long long first_bad = ~0ull;
+    uint32_t bad = 0;
+    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = GateRowsCheckBody::run(a, pool, q, i, first_bad); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, first_bad, o);
+        first_bad = other < first_bad ? other : first_bad;
+    }
+    if ((threadIdx.x & 31) == 0 && bad) {
+        atomicAdd(a.counters + CNT_UNSAT, (unsigned long long)bad);
+        atomicMin(a.counters + CNT_FIRST_BAD, first_bad);
+    }
+}
+
 __global__ void __launch_bounds__(BLOCK) k_check_rows(const CheckRowsBody::Args a) {
     const uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     uint32_t bad = i < a.n ? CheckRowsBody::run(a, i) : 0u;

@@ -24,7 +24,8 @@ def main():
     widths = args[1:] or [16, 64, 128, 254]
     n = 1 << log2n
     shape = int(os.environ.get("PG_CHECK_SHAPE", "0"))           # launch shape of the gate-check kernels (tuning runs)
-    c = pg.StandardComposer(device=0, timing=True, stream=stream.cuda_stream, check_shape=shape)
+    mode = pg.CHECK_SPARSE if os.environ.get("PG_CHECK_MODE") == "sparse" else pg.CHECK_GENERIC
+    c = pg.StandardComposer(device=0, timing=True, stream=stream.cuda_stream, check_shape=shape, check_mode=mode)
     wit = torch.empty((n, 4), dtype=torch.int64, device=dev)
     for bits in widths:
         c.synth(SEED, 61, 1, bits, wit)

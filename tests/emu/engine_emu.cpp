@@ -126,6 +126,14 @@ public:
         count_check(PG_CK_GATES, a.n_inst * a.n_rows);
         HostPool pool = {a.pool};
         const QRegs q = q_regs_default();
+        if (a.n_inst >= 48) {                            // one thread per instance walking the rows, as for large segments on the GPU
+            for (uint64_t i = 0; i < a.n_inst; i++) {
+                unsigned long long fb = ~0ull;
+                const uint32_t bad = GateRowsCheckBody::run(a, pool, q, i, fb);
+                if (bad) { a.counters[CNT_UNSAT] += bad; if (fb < a.counters[CNT_FIRST_BAD]) a.counters[CNT_FIRST_BAD] = fb; }
+            }
+            return true;
+        }
         for (uint64_t t = 0; t < a.n_inst * a.n_rows; t++) {
             unsigned long long fb = ~0ull;
             const uint32_t bad = GateRowsCheckBody::run_one(a, pool, q, t, fb);

@@ -319,6 +319,8 @@ def test_emu_range_gate_fault_injection(emu, oracle):
 
 def test_emu_range_gate_poked_witness(emu, oracle):
     rgc.poked_witness(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle)
+    # 60 instances: the per-instance walk of the rows (GateRowsCheckBody::run: the next row's fourth wire carried as d_next / d)
+    rgc.poked_witness(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle, n=60, trials=8, seed=12)
 
 
 # ---- faults inside the range gadgets' own segments, per-instance Results, ingest checks (shared with the GPU tests) -----------
