@@ -302,8 +302,11 @@ public:
         if (smem > 48 * 1024) { snprintf(errbuf, sizeof(errbuf), "selector pool of %u entries exceeds the shared-memory budget", a.n_pool); return false; }
         const uint64_t total = a.n_inst * a.n_rows;
         tic(CLS_CHECK, total);
-        // PG_GATES_WALK=1 (tuning runs): one thread per instance walking the rows, for segments that fill the chip that way
-        static const int walk = getenv("PG_GATES_WALK") ? atoi(getenv("PG_GATES_WALK")) : 0;
+        // Large segments in the structure-aware mode: one thread per instance walking the rows (every accumulator loaded once; 7.2 vs
+        // 8.1 ms at 2^24 x 64 bits).  In the generic mode the (row, instance) mapping stays: the walk measured 18.8 vs 18.1 ms -- the range
+        // rows are bound by their multiplications either way (profiles/README.md, run r04k).  PG_GATES_WALK=0/1 overrides (tuning runs).
+        static const int walk_env = getenv("PG_GATES_WALK") ? atoi(getenv("PG_GATES_WALK")) : -1;
+        const bool walk = walk_env >= 0 ? walk_env != 0 : a.mode == PG_CHECK_SPARSE;
         if (walk && a.n_inst >= (uint64_t)sm_count * 320) {
             k_check_gates_walk<<<(unsigned)((a.n_inst + 127) / 128), 128, smem, stream>>>(a);
             toc();
@@ -311,10 +314,10 @@ public:
             return launched("k_check_gates_walk");
         }
         const unsigned grid = (unsigned)((total + 127) / 128);
-        switch (check_shape) {                                   // 24 warps/SM measured best (profiles/README.md, run r04i); shapes 1 / 3 for tuning runs
-            case 1: k_check_gates<5><<<grid, 128, smem, stream>>>(a); break;
+        switch (check_shape) {                                   // 20 / 24 / 28 warps per SM measure the same (18.16 / 18.05 / 18.26 ms, run r04j)
+            case 2: k_check_gates<6><<<grid, 128, smem, stream>>>(a); break;
             case 3: k_check_gates<7><<<grid, 128, smem, stream>>>(a); break;
-            default: k_check_gates<6><<<grid, 128, smem, stream>>>(a); break;
+            default: k_check_gates<5><<<grid, 128, smem, stream>>>(a); break;
         }
         toc();
         count_check(PG_CK_GATES, total);
