@@ -111,7 +111,7 @@ struct RangeArgs {
     DevTab x_tab; uint32_t x_loc;
     uint4* fr; uint32_t* bits; uint4* param; uint64_t stride;
     uint64_t n; uint32_t k;
-    uint64_t i0;                                     // RangePre only: first instance of this launch (chunked launches behind input copies)
+    uint64_t i0;                                     // first instance of this launch (chunked launches behind input copies)
     int uniform; Fr m; Fr negmin;                    // uniform bounds: max-1 and -min
     const uint4* max_aos; const uint4* min_aos;      // per-instance bounds
     uint32_t param_m, param_negmin;
@@ -197,7 +197,8 @@ template <bool RANGE, bool FUSED = false>
 struct RangePost {   // after z = u^-1 (or 0) has been written by the batch inversion (scalar.rs:122-123)
     static constexpr int E = RANGE ? 2 : 1;
     typedef RangeArgs Args;
-    PG_HD static void run(const Args& a, uint64_t i) {
+    PG_HD static void run(const Args& a, uint64_t i_launch) {
+        const uint64_t i = a.i0 + i_launch;                                    // (chunked launches: see RangePre)
         Fr y[E];
         FusedVerdict fv;
 #pragma unroll

@@ -168,6 +168,7 @@ public:
         for (auto& s : segs) if (s.owns_table) { dfree(s.fr); dfree(s.bits); dfree(s.param); dfree(s.d_image); }
         for (void* p : scratch) dfree(p);
         scratch.clear(); segs.clear(); cols.clear(); dsegs.clear(); dsegs_dirty = true;
+        be.drop_result_chunks();
         n_rows = 0; n_vars = 0;
     }
     // StandardComposer::new(): 5 variables, 3 rows
@@ -549,15 +550,16 @@ public:
             // PG_F_FUSED_CHECK (structure-aware mode only): the same kernels also evaluate the rows they generate
             const bool fused = (cfg.flags & PG_F_FUSED_CHECK) && cfg.check_mode == PG_CHECK_SPARSE;
             a.base_row = s.base_row; a.n_rows = (uint32_t)s.t.rows.size();
+            // decomposition -> inversion -> results; with the fused check, behind a chunked input copy, the three run chunk by chunk, so
+            // that an asynchronous read of the results (pg_col_read, dst_on_device = 2) starts on the first chunk while the later ones
+            // are computed (without the fused check that copy runs under the gate-check kernel anyway)
             bool ok;
             if (fused)
-                ok = is_range_check
-                    ? be.template run_simple_chunked<RangePre<true, true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true, true>>(a, n, CLS_WITNESS)
-                    : be.template run_simple_chunked<RangePre<false, true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false, true>>(a, n, CLS_WITNESS);
+                ok = is_range_check ? be.template run_range_pipeline<RangePre<true, true>, RangePost<true, true>>(a, inv, n, whole, s.fr, true)
+                                    : be.template run_range_pipeline<RangePre<false, true>, RangePost<false, true>>(a, inv, n, whole, s.fr, true);
             else
-                ok = is_range_check
-                    ? be.template run_simple_chunked<RangePre<true>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<true>>(a, n, CLS_WITNESS)
-                    : be.template run_simple_chunked<RangePre<false>>(a, n, CLS_WITNESS, whole) && be.run_batch_inv(inv, CLS_WITNESS) && be.template run_simple<RangePost<false>>(a, n, CLS_WITNESS);
+                ok = is_range_check ? be.template run_range_pipeline<RangePre<true>, RangePost<true>>(a, inv, n, whole, s.fr, false)
+                                    : be.template run_range_pipeline<RangePre<false>, RangePost<false>>(a, inv, n, whole, s.fr, false);
             if (!ok) return fail(PG_ERR_CUDA, "range witness kernels");
             if (fused) { s.fused_ok = true; be.count_check(PG_CK_FUSED, n * s.t.rows.size()); }
         }
@@ -975,6 +977,12 @@ public:
         if (!to_device) scratch.push_back(out);
         Column sub = *col; sub.inst_off += i0; sub.n = cnt;
         ColReadBody::Args a{view_of(sub), loc_with_tab(loc_of(sub), 0), out, cnt};
+        // results of a range call that ran chunk by chunk, read asynchronously and whole: gather and copy each chunk on the copy stream
+        // as soon as that chunk's results exist (the kernels of the later chunks are still running on the main stream)
+        if (dst_on_device == 2 && sub.inst_off == 0 && cnt == segs[sub.seg].n_inst && be.result_chunks_of(segs[sub.seg].fr)) {
+            if (!be.col_read_chunked(a, dst, segs[sub.seg].fr)) return fail(PG_ERR_CUDA, "chunked asynchronous result copy");
+            return PG_OK;
+        }
         if (!be.template run_simple<ColReadBody>(a, cnt, CLS_OTHER)) return fail(PG_ERR_CUDA, "col_read kernel");
         if (to_device) return PG_OK;
         if (dst_on_device == 2) {                 // pinned host, asynchronous: the staging buffer lives until the next reset

@@ -61,6 +61,25 @@ public:
         }
         return true;
     }
+    // the range gadgets' three kernels; in three uneven chunks (as behind a chunked input copy on the GPU) when n is large enough
+    void drop_result_chunks() {}
+    bool result_chunks_of(const void*) const { return false; }
+    bool col_read_chunked(const ColReadBody::Args&, void*, const void*) { return false; }
+    template <class Pre, class Post>
+    bool run_range_pipeline(const typename Pre::Args& a_in, const BatchInvArgs& inv_in, uint64_t n, const void* operand_table, const void*, bool chunk_results) {
+        if (n < 6 || !chunk_results) return run_simple_chunked<Pre>(a_in, n, 0, operand_table) && run_batch_inv(inv_in, 0) && run_simple<Post>(a_in, n, 0);
+        const uint64_t cut[4] = {0, n / 3, n / 3 + n / 2, n};
+        for (int k = 0; k < 3; k++) {
+            typename Pre::Args a = a_in;
+            a.i0 = cut[k]; a.n = cut[k + 1] - cut[k];
+            BatchInvArgs inv = inv_in;
+            inv.fr = inv_in.fr + 2 * cut[k]; inv.n = a.n;
+            for (uint64_t i = 0; i < a.n; i++) Pre::run(a, i);
+            if (!run_batch_inv(inv, 0)) return false;
+            for (uint64_t i = 0; i < a.n; i++) Post::run(a, i);
+        }
+        return true;
+    }
     bool run_batch_inv(const BatchInvArgs& a, int) {   // one Fermat inversion per element (the block-wide trick is GPU-only)
         for (uint32_t j = 0; j < a.n_pairs; j++)
             for (uint64_t i = 0; i < a.n; i++) {

@@ -396,6 +396,44 @@ def test_async_result_copy(oracle, torch_cuda):
     assert (host.numpy().view(np.uint64) == y.values()).all()
 
 
+@pytest.mark.parametrize("mode,fused", [(pg.CHECK_GENERIC, False), (pg.CHECK_SPARSE, False), (pg.CHECK_SPARSE, True)])
+def test_chunked_range_pipeline_with_async_read(oracle, torch_cuda, mode, fused):
+    """Behind a chunked input copy the range gadgets run decomposition / inversion / results chunk by chunk, and an asynchronous read
+    of the whole result column is issued per chunk on the copy stream (it overlaps with the later chunks' kernels): results, the
+    table and the verdict must equal the device-input run; range_check and max_bound, per-instance bounds too."""
+    torch = torch_cuda
+    n = (1 << 20) + 4099                                  # ragged last chunk
+    c = gpu_composer(check_mode=mode, fused_check=fused)
+    wit = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 2, 2, 64, wit); c.sync()
+    mxs = torch.empty((n, 4), dtype=torch.int64, device="cuda"); c.synth(SEED, 77, 3, 64, mxs); c.sync()     # 64-bit bounds with the top bit set
+    mn, mx = oracle.from_ints([0]), oracle.from_ints([2 ** 64])
+    pinned = wit.cpu().pin_memory()
+    for gadget in ("range_check", "max_bound_per_instance"):
+        def build(src):
+            c.reset()
+            w = c.add_input(src)
+            return pg.range_check(c, mn, mx, w) if gadget == "range_check" else pg.max_bound(c, mxs, w)[0]
+        y = build(wit)                                    # device input: three launches over all instances
+        assert c.check_circuit_satisfied() == (0, None)
+        ref_y = y.values()
+        vpi = 653 if gadget == "range_check" else 326
+        picks = (0, n // 4 - 1, n // 4 + 1024, n // 2 + 5, n - 1)
+        ref_vars = [c.variables(5 + n + vpi * i, vpi).copy() for i in picks]
+        host = torch.zeros((n, 4), dtype=torch.int64).pin_memory()
+        y = build(pinned)                                 # host input: chunk by chunk
+        c.read_column_into(y, host, asynchronous=True)    # per chunk on the copy stream
+        assert c.check_circuit_satisfied() == (0, None)
+        c.sync()
+        assert (host.numpy().view(np.uint64) == ref_y).all()
+        assert (y.values() == ref_y).all()
+        for i, ref in zip(picks, ref_vars):
+            assert (c.variables(5 + n + vpi * i, vpi) == ref).all(), (gadget, i)
+        # a partial asynchronous read takes the ordinary path
+        part = torch.zeros((1000, 4), dtype=torch.int64).pin_memory()
+        c.read_column_into(y, part, i0=n // 2, cnt=1000, asynchronous=True); c.sync()
+        assert (part.numpy().view(np.uint64) == ref_y[n // 2: n // 2 + 1000]).all()
+
+
 @pytest.mark.parametrize("mode", [pg.CHECK_GENERIC, pg.CHECK_SPARSE])
 def test_check_modes_at_scale(oracle, torch_cuda, mode):
     """2^18 range_check instances: both evaluations give verdict 0, and both see two injected wrong claims."""
