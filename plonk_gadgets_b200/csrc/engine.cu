@@ -344,9 +344,9 @@ public:
             count_check(PG_CK_ROWPAR, total);
             return launched("k_check_rowpar");
         }
-        // the structure-aware check streams the table (HBM-bound): 24 warps/SM with four 32-byte loads in flight per thread measured best
-        // (profiles/r04c), unless a shape was asked for
-        switch (a.mode == PG_CHECK_SPARSE && check_shape == 0 ? 2 : check_shape) {
+        // the structure-aware check streams the table (HBM-bound): 20 warps/SM with three 32-byte loads in flight per thread (no register
+        // spill, no local memory) and 24 warps/SM with four measure the same, 12.95 / 12.98 ms (profiles/README.md, run r04n)
+        switch (check_shape) {
             case 1: launch_check<1>(a, prog, smem); break; case 2: launch_check<2>(a, prog, smem); break;
             case 3: launch_check<3>(a, prog, smem); break; case 4: launch_check<4>(a, prog, smem); break;
             default: launch_check<0>(a, prog, smem); break;

@@ -193,6 +193,7 @@ struct SmemQ {
         return q; }
 };
 template <int SHAPE> struct ProgDepth { static constexpr int D = 4; };
+template <> struct ProgDepth<0> { static constexpr int D = 3; };     // 102 registers: no spill at all with three loads in flight
 template <> struct ProgDepth<3> { static constexpr int D = 2; };
 template <> struct ProgDepth<4> { static constexpr int D = 2; };
 template <int SHAPE>

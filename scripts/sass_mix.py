@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "plonk_gadgets_b200", "libpg_b200.so")
-HOT = ["k_checkILi0ELi0E", "k_check_progILi2E", "k_check_progILi4E", "k_check_gates", "k_check_rowparILi0E", "k_batch_invINS_15MaybeEqualFused",
+HOT = ["k_checkILi0ELi0E", "k_check_progILi0E", "k_check_progILi2E", "k_check_gates_walk", "k_check_gatesILi5E", "k_check_gates", "k_check_rowparILi0E", "k_batch_invINS_15MaybeEqualFused",
        "k_batch_invINS_8InvPlain", "RangePreILb1ELb0E", "RangePreILb1ELb1E", "RangePostILb1ELb0E", "k_materialize_tiled", "k_ntt_pass", "MsmBucketBody"]
 KEYS = ["IMAD.WIDE.U32.X", "IMAD.WIDE.U32", "IMAD.WIDE", "IMAD.HI.U32", "IMAD.X", "IMAD.MOV", "IMAD.MOV.U32", "IMAD.IADD", "IMAD.SHL", "IMAD", "IADD3.X", "IADD3",
         "LOP3.LUT", "SEL", "MOV", "LDG.E.ENL2.256", "STG.E.ENL2.256", "LDG.E.128", "LDG.E", "LDS.128", "UBLKCP.G.S", "STL", "LDL", "STL.64", "LDL.64", "LDL.LU", "BAR.SYNC"]
