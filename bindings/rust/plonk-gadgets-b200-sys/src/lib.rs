@@ -97,6 +97,8 @@ pub struct pg_op_shard {
 }
 
 extern "C" {
+    pub fn pg_template_get(gadget: u32, num_bits: u32, a: *const pg_fr, b: *const pg_fr, n_rows: *mut u64, n_vars: *mut u64, w_ref: *mut i64,
+                           sel: *mut pg_fr, gate: *mut u32) -> c_int;
     pub fn pg_op_shape(gadget: u32, num_bits: u32, rows: *mut u64, vars: *mut u64) -> c_int;
     pub fn pg_shard_plan(ops: *const pg_op, n_ops: u64, world: u32, policy: c_int, out: *mut pg_op_shard) -> c_int;
     pub fn pg_comm_unique_id(id: *mut u8) -> c_int;

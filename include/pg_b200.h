@@ -195,6 +195,17 @@ int pg_check_rows(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel,
 int pg_check_rows_ex(pg_ctx *ctx, uint64_t n, const pg_fr *w_val, const pg_fr *sel, const pg_fr *pi, const pg_fr *q_arith,
                      const pg_fr *q_range, int on_device, uint64_t *n_unsat, uint64_t *first_bad_row);
 
+/* ---- row templates ------------------------------------------------------------------------------------------------------------
+ * What ONE instance of a gadget appends, in the reference's order (the structure depends only on public data -- the
+ * property the reference's verifier-side circuit rebuild relies on, ref:tests/scalar_gadgets_tests.rs:43,:60): pure host code, no ctx.
+ * a / b: the public scalars of the call -- range_check: (min_range, max_range); max_bound: (NULL, max_range); constrain_to_constant:
+ * (pi or NULL, constant); others: ignored.  num_bits: range_gate's width; for range_check / max_bound 0 or the width the bound implies.
+ * w_ref (4 x n_rows, column-major w_l w_r w_o w_4): 0 = the zero variable, 1 + j = the j-th Variable the instance allocates,
+ * -1 - e = operand e (witness / a, b / x, select / var).  sel (6 x n_rows): q_m q_l q_r q_o q_4 q_c.  gate (n_rows): 0 arithmetic
+ * (q_arith = 1), 1 range widget (q_range = 1), 2 neither.  Output buffers may be NULL (sizes only). */
+int pg_template_get(uint32_t gadget, uint32_t num_bits, const pg_fr *a, const pg_fr *b, uint64_t *n_rows, uint64_t *n_vars,
+                    int64_t *w_ref, pg_fr *sel, uint32_t *gate);
+
 /* ---- multi-GPU: sharding plan and the two collectives -------------------------------------------------
  * One process and one pg_ctx per GPU.  Gadget instances are independent (ref:src/range.rs:119-158 allocates its own accumulators,
  * ref:src/scalar.rs:41, :83 their own constant one), so the instances of every batched call are cut into contiguous ranges, one per

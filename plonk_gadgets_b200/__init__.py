@@ -6,7 +6,7 @@ CUDA library; creating a StandardComposer does, and fails loudly when it (or a B
 """
 from .api import (AllocatedScalar, CHECK_GENERIC, CHECK_SPARSE, DevicePtr, EngineError, Error, NZ_REFERENCE, NZ_UNIFORM,  # noqa: F401
                   NonExistingInverse, StandardComposer, Variables, conditionally_select_one, conditionally_select_zero,
-                  is_non_zero, is_non_zero_flags, max_bound, maybe_equal, range_check, comm_unique_id, op_shape, shard_plan,
+                  is_non_zero, is_non_zero_flags, max_bound, maybe_equal, range_check, comm_unique_id, op_shape, shard_plan, template_get,
                   SHARD_EVEN, SHARD_ROWS, OP_ADD_INPUT, OP_RANGE_CHECK, OP_MAX_BOUND, OP_MAYBE_EQUAL, OP_IS_NON_ZERO, OP_SELECT_ZERO,
                   OP_SELECT_ONE, OP_CONSTRAIN, OP_RANGE_GATE)
 from . import _lib  # noqa: F401

@@ -72,6 +72,7 @@ SIGNATURES = {
     "pg_check": (_i32, [_vp, _pu64, _pu64]),
     "pg_check_rows": (_i32, [_vp, _u64, _vp, _vp, _vp, _i32, _pu64, _pu64]),
     "pg_check_rows_ex": (_i32, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _i32, _pu64, _pu64]),
+    "pg_template_get": (_i32, [_u32, _u32, _vp, _vp, _pu64, _pu64, _vp, _vp, _vp]),
     "pg_op_shape": (_i32, [_u32, _u32, _pu64, _pu64]),
     "pg_shard_plan": (_i32, [C.POINTER(pg_op), _u64, _u32, _i32, C.POINTER(pg_op_shard)]),
     "pg_comm_unique_id": (_i32, [_vp]),

@@ -55,6 +55,24 @@ def op_shape(gadget: int, num_bits: int = 0):
     return r.value, v.value
 
 
+def template_get(gadget: int, num_bits: int = 0, a=None, b=None, _cdll=None):
+    """Rows one instance of a gadget appends (pg_template_get): (w_ref (4, rows) int64, sel (6, rows, 4) uint64, gate (rows,) uint32,
+    n_vars).  a / b: the call's public scalars ((4,) uint64 Montgomery limbs): range_check (min, max), max_bound (None, max),
+    constrain_to_constant (pi or None, constant)."""
+    L = _cdll if _cdll is not None else _lib.load()
+    ptr = lambda x: None if x is None else np.ascontiguousarray(x, dtype=np.uint64).reshape(4).ctypes.data_as(C.c_void_p)
+    keep = [None if x is None else np.ascontiguousarray(x, dtype=np.uint64).reshape(4) for x in (a, b)]
+    pa, pb = (None if k is None else k.ctypes.data_as(C.c_void_p) for k in keep)
+    rows, nv = C.c_uint64(), C.c_uint64()
+    if L.pg_template_get(gadget, num_bits, pa, pb, C.byref(rows), C.byref(nv), None, None, None) != 0:
+        raise ValueError("pg_template_get: bad gadget / bounds / num_bits")
+    w = np.zeros((4, rows.value), dtype=np.int64); sel = np.zeros((6, rows.value, 4), dtype=np.uint64); gate = np.zeros(rows.value, dtype=np.uint32)
+    rc = L.pg_template_get(gadget, num_bits, pa, pb, C.byref(rows), C.byref(nv), w.ctypes.data_as(C.c_void_p), sel.ctypes.data_as(C.c_void_p),
+                           gate.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return w, sel, gate, nv.value
+
+
 def shard_plan(ops, world: int, policy: int = SHARD_EVEN, _cdll=None):
     """ops: list of (gadget, num_bits, n, group).  Returns plan[rank][k] = pg_op_shard(inst_lo, inst_hi, row_base, var_base): what
     `rank` runs of call k and where it sits in the sequential composer (pure host code, no GPU needed)."""

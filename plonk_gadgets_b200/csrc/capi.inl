@@ -95,6 +95,9 @@ int pg_check_rows_ex(pg_ctx* ctx, uint64_t n, const pg_fr* w_val, const pg_fr* s
     PG_ALIGNED(ctx, q_arith, on_device); PG_ALIGNED(ctx, q_range, on_device);
     PG_TRY(ctx, ctx->e.check_rows(n, w_val, sel, pi, on_device, n_unsat, first_bad_row, q_arith, q_range));
 }
+int pg_template_get(uint32_t gadget, uint32_t num_bits, const pg_fr* a, const pg_fr* b, uint64_t* n_rows, uint64_t* n_vars, int64_t* w_ref, pg_fr* sel, uint32_t* gate) {
+    try { return pg::template_get(gadget, num_bits, a, b, n_rows, n_vars, w_ref, sel, gate); } catch (...) { return PG_ERR_STATE; }
+}
 int pg_op_shape(uint32_t gadget, uint32_t num_bits, uint64_t* rows, uint64_t* vars) { return pg::op_shape(gadget, num_bits, rows, vars) ? PG_OK : PG_ERR_ARG; }
 int pg_shard_plan(const pg_op* ops, uint64_t n_ops, uint32_t world, int policy, pg_op_shard* out) {
     try { return pg::shard_plan(ops, n_ops, world, policy, out); } catch (...) { return PG_ERR_STATE; }

@@ -12,6 +12,7 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/pg_b200.h"
+#include "templates.hpp"
 
 namespace pg {
 
@@ -36,6 +37,55 @@ inline bool op_shape(uint32_t gadget, uint32_t k, uint64_t* rows, uint64_t* vars
 }
 
 constexpr uint64_t FRESH_ROWS = 3, FRESH_VARS = 5;     // StandardComposer::new()
+
+// pg_template_get: the rows ONE instance of a gadget appends, in the reference's order -- what "emits the same selector rows" means,
+// without materialising a batch.  Wire references: 0 = the zero variable, 1 + j = the j-th Variable the instance allocates (Variable id
+// first + j), -1 - e = operand e (the Variable(s) passed in: witness / a, b / x, select / var).  Selectors q_m q_l q_r q_o q_4 q_c as values;
+// entries that depend on per-instance bounds / constants are the ones of the bounds passed here.  gate: 0 arithmetic (q_arith = 1),
+// 1 range widget (q_range = 1), 2 neither.  Buffers may be null (sizes only).
+inline int template_get(uint32_t gadget, uint32_t num_bits, const pg_fr* mn, const pg_fr* mx, uint64_t* n_rows, uint64_t* n_vars,
+                        int64_t* w_ref, pg_fr* sel, uint32_t* gate) {
+    auto fr_of = [](const pg_fr* x) { Fr r = fr_zero(); if (x) for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)x->l[i]; r.v[2 * i + 1] = (uint32_t)(x->l[i] >> 32); } return r; };
+    Template t; uint32_t result_local = 0;
+    if (fr_is_zero(h_pow2[0])) {                               // the 2^i table of the range templates (filled by the first ctx otherwise)
+        h_pow2[0] = fr_one();
+        for (int i = 1; i < 256; i++) h_pow2[i] = fr_add(h_pow2[i - 1], h_pow2[i - 1]);
+    }
+    switch (gadget) {
+        case PG_OP_ADD_INPUT: t = make_add_input_template(); break;
+        case PG_OP_RANGE_CHECK: case PG_OP_MAX_BOUND: {
+            if (!mx || (gadget == PG_OP_RANGE_CHECK && !mn)) return PG_ERR_ARG;
+            const Fr m = fr_sub(fr_of(mx), fr_one());
+            const uint32_t k = num_bits_from_canonical(fr_from_mont(m));
+            if (num_bits && num_bits != k) return PG_ERR_ARG;                      // num_bits is implied by the bound (range.rs:87-90)
+            t = make_range_template(gadget == PG_OP_RANGE_CHECK, k, true, m, fr_neg(fr_of(mn)), &result_local);
+        } break;
+        case PG_OP_MAYBE_EQUAL: t = make_maybe_equal_template(&result_local); break;
+        case PG_OP_IS_NON_ZERO: t = make_is_non_zero_template(false); break;
+        case PG_OP_SELECT_ZERO: t = make_select_template(false, &result_local); break;
+        case PG_OP_SELECT_ONE: t = make_select_template(true, &result_local); break;
+        case PG_OP_CONSTRAIN: t = make_constrain_template(true, fr_neg(fr_of(mx)), mn != nullptr, true, fr_of(mn)); break;   // mx: the constant, mn: the PI (or null)
+        case PG_OP_RANGE_GATE: if (num_bits < 2 || num_bits > 256 || (num_bits & 1)) return PG_ERR_ARG; t = make_range_gate_template(num_bits); break;
+        default: return PG_ERR_ARG;
+    }
+    const uint64_t R = t.rows.size();
+    if (n_rows) *n_rows = R;
+    if (n_vars) *n_vars = t.n_vars;
+    for (uint64_t r = 0; r < R; r++) {
+        const RowT& row = t.rows[r];
+        for (int w = 0; w < 4 && w_ref; w++) {
+            const WireRef& wr = row.w[w];
+            w_ref[(uint64_t)w * R + r] = wr.src == 0 ? 0 : wr.src == 1 ? 1 + (int64_t)wr.idx : -1 - (int64_t)(wr.src - 2);
+        }
+        for (int k = 0; k < 6 && sel; k++) {
+            const Fr v = t.pool[row.sel[k]];
+            pg_fr& o = sel[(uint64_t)k * R + r];
+            for (int i = 0; i < 4; i++) o.l[i] = (uint64_t)v.v[2 * i] | ((uint64_t)v.v[2 * i + 1] << 32);
+        }
+        if (gate) gate[r] = row.gate;
+    }
+    return PG_OK;
+}
 
 // out[rank * n_ops + k] = what `rank` runs of call k.  Calls with the same `group` share one instance index space (a column and the
 // gadgets applied to it: instance i of each of them must live on the same rank) and must have the same n; groups are numbered in

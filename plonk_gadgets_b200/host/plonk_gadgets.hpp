@@ -69,8 +69,8 @@ struct Variables {
 /// Device-resident batched StandardComposer (fresh: 3 rows, 5 variables).
 class StandardComposer {
 public:
-    explicit StandardComposer(int device = 0, int check_mode = PG_CHECK_GENERIC) {
-        pg_cfg cfg{}; cfg.device = device; cfg.check_mode = check_mode;
+    explicit StandardComposer(int device = 0, int check_mode = PG_CHECK_GENERIC, bool fused_check = false) {
+        pg_cfg cfg{}; cfg.device = device; cfg.check_mode = check_mode; cfg.flags = fused_check ? PG_F_FUSED_CHECK : 0u;
         int rc = pg_ctx_create(&cfg, &ctx_);
         if (rc != PG_OK) throw EngineError(rc, std::string("pg_ctx_create: ") + pg_strerror(rc));
     }
@@ -111,6 +111,39 @@ public:
         return out;
     }
     void reset() { ok(pg_composer_reset(ctx_), "pg_composer_reset"); }
+    /// composer.variables[var0 .. var0 + cnt) in Variable order
+    std::vector<BlsScalar> variables(uint64_t var0, uint64_t cnt) {
+        std::vector<BlsScalar> out(cnt);
+        ok(pg_read_variables(ctx_, var0, cnt, reinterpret_cast<pg_fr*>(out.data()), 0), "pg_read_variables");
+        return out;
+    }
+    /// The hand-over to a real dusk-plonk StandardComposer (prover.mut_cs(), /root/reference/tests/range_gadgets_tests.rs:82-91):
+    /// the whole composer in one file, replayed by bindings/rust/plonk-gadgets-b200/src/import.rs
+    void export_to(const std::string& path, bool with_sigma = false) { ok(pg_export_composer(ctx_, path.c_str(), 0, with_sigma ? PG_EXPORT_SIGMA : 0u), "pg_export_composer"); }
+
+    // ---- several GPUs: one process and one composer per GPU (include/pg_b200.h, "multi-GPU") ----
+    void comm_init(const uint8_t* unique_id, uint32_t rank, uint32_t world) { ok(pg_comm_init(ctx_, unique_id, rank, world), "pg_comm_init"); }
+    struct Verdict { uint64_t n_unsat, first_bad_row, n_err; };
+    /// verdict of the WHOLE sharded circuit on every rank; `mine`: this rank's row of shard_plan(..) (empty: local numbering)
+    Verdict check_sharded(const std::vector<pg_op_shard>& mine, uint64_t n_err_local = 0) {
+        Verdict v{0, 0, n_err_local};
+        ok(pg_check_sharded(ctx_, mine.empty() ? nullptr : mine.data(), mine.size(), &v.n_unsat, &v.first_bad_row, &v.n_err), "pg_check_sharded");
+        return v;
+    }
+    /// the per-instance results of a call from every rank, in instance order of the whole batch (`total` = sum of the ranks' lengths)
+    std::vector<BlsScalar> gather_column(Variables v, uint64_t total) {
+        std::vector<BlsScalar> out(total); uint64_t got = 0;
+        ok(pg_gather_column(ctx_, v.col, reinterpret_cast<pg_fr*>(out.data()), total, 0, nullptr, &got), "pg_gather_column");
+        out.resize(got);
+        return out;
+    }
+    /// gather of witness shards: the Variables of call number `call` from every rank, in the sequential composer's order
+    std::vector<BlsScalar> gather_variables(uint64_t call, uint64_t total) {
+        std::vector<BlsScalar> out(total); uint64_t got = 0;
+        ok(pg_gather_variables(ctx_, call, reinterpret_cast<pg_fr*>(out.data()), total, 0, &got), "pg_gather_variables");
+        out.resize(got);
+        return out;
+    }
 
     // ---- the prover's first round ([DEP] dusk-plonk 0.8 Prover::prove: to_scalars + pad, domain.ifft, commit_key.commit) ----
     /// log2 of EvaluationDomain::new(circuit_size).size()
@@ -215,6 +248,15 @@ inline bool is_non_zero(StandardComposer& composer, Variables var, const std::ve
     if (rc == PG_ERR_NON_EXISTING_INVERSE) { if (err) *err = Error::NonExistingInverse; if (first_err) *first_err = first; return false; }
     return true;
 }
+/// The same loop with every Result kept (a batch does not abort on one zero, /root/reference/src/errors.rs:13-18): errs[i] is true
+/// where is_non_zero(composer, var_i, value_assigned_i) returned Err(NonExistingInverse).  reference_layout: errored calls leave the
+/// 1 variable + 1 row of scalar.rs:69-71 behind, as the reference does; otherwise 3 + 3 everywhere (the errored instance fails its last row).
+inline std::vector<bool> is_non_zero_each(StandardComposer& composer, Variables var, const std::vector<BlsScalar>& value_assigned, bool reference_layout = false) {
+    std::vector<uint8_t> flags(value_assigned.size()); uint64_t n_err = 0;
+    composer.ok(pg_is_non_zero_batch_flags(composer.raw(), var.col, reinterpret_cast<const pg_fr*>(value_assigned.data()), 0, flags.data(),
+                                           reference_layout ? PG_NZ_REFERENCE : PG_NZ_UNIFORM, &n_err), "pg_is_non_zero_batch_flags");
+    return std::vector<bool>(flags.begin(), flags.end());
+}
 /// /root/reference/src/scalar.rs:105-140
 inline Variables maybe_equal(StandardComposer& composer, AllocatedScalar a, AllocatedScalar b) {
     Variables out; out.n = a.var.n;
@@ -222,5 +264,16 @@ inline Variables maybe_equal(StandardComposer& composer, AllocatedScalar a, Allo
     return out;
 }
 }  // namespace ScalarGadgets
+
+/// Cuts a mixed circuit (a list of batched calls) over `world` GPUs: plan[rank][k] = the instance range of call k that rank runs and
+/// the row / Variable index of its first instance in the sequential composer (pure host code).
+inline std::vector<std::vector<pg_op_shard>> shard_plan(const std::vector<pg_op>& ops, uint32_t world, bool by_rows = false) {
+    std::vector<pg_op_shard> flat(ops.size() * world);
+    const int rc = pg_shard_plan(ops.data(), ops.size(), world, by_rows ? PG_SHARD_ROWS : PG_SHARD_EVEN, flat.data());
+    if (rc != PG_OK) throw EngineError(rc, std::string("pg_shard_plan: ") + pg_strerror(rc));
+    std::vector<std::vector<pg_op_shard>> plan(world);
+    for (uint32_t r = 0; r < world; r++) plan[r].assign(flat.begin() + (size_t)r * ops.size(), flat.begin() + (size_t)(r + 1) * ops.size());
+    return plan;
+}
 
 }  // namespace plonk_gadgets

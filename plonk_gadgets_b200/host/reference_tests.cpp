@@ -186,9 +186,50 @@ static void range_gate_test() {
     }
 }
 
+// Round 2: every Result of a batched is_non_zero kept (scalar_gadgets_tests.rs:199: zero -> Err, without stopping the batch), the
+// structure-aware and fused checks, the sharded verdict / gathers as a world of one rank, and the export for the import adapter.
+static void batch_extensions_test() {
+    const BlsScalar r1 = BlsScalar::from(77) * BlsScalar::from(0xabcdef0123456789ULL);
+    {
+        StandardComposer composer;
+        std::vector<BlsScalar> vals = {r1, BlsScalar::zero(), r1 + r1, BlsScalar::zero(), r1};
+        auto v = composer.add_input(vals);
+        const auto errs = is_non_zero_each(composer, v, vals);
+        EXPECT(errs == std::vector<bool>({false, true, false, true, false}), "per-instance NonExistingInverse flags");
+        EXPECT(composer.circuit_size() == 3 + 3 * 5 && composer.check_circuit_satisfied().first == 2, "errored instances fail their last row");
+        StandardComposer ref_layout;
+        auto v2 = ref_layout.add_input(vals);
+        is_non_zero_each(ref_layout, v2, vals, true);
+        EXPECT(ref_layout.circuit_size() == 3 + 3 * 3 + 2 * 1 && ref_layout.num_variables() == 5 + 5 + 3 * 3 + 2 * 1, "reference layout: 1 variable + 1 row per errored call");
+    }
+    for (int fused = 0; fused < 2; fused++) {
+        StandardComposer composer(0, PG_CHECK_SPARSE, fused != 0);
+        std::vector<BlsScalar> w;
+        for (uint64_t i = 0; i < 300; i++) w.push_back(i % 2 ? -BlsScalar::from(i + 1) : BlsScalar::from(50000 + i));
+        auto witness = AllocatedScalar::allocate(composer, w);
+        auto res = range_check(composer, {BlsScalar::from(50000)}, {BlsScalar::from(250000)}, witness);
+        const std::vector<pg_op> ops = {{PG_OP_ADD_INPUT, 0, 300, 0, 0}, {PG_OP_RANGE_CHECK, 19, 300, 0, 0}};
+        const auto plan = shard_plan(ops, 1, true);
+        EXPECT(plan[0][1].row_base == 3 && plan[0][1].var_base == 5 + 300 && plan[0][1].inst_hi == 300, "shard plan of one rank = the whole circuit");
+        const auto v = composer.check_sharded(plan[0]);
+        EXPECT(v.n_unsat == 0 && v.first_bad_row == UINT64_MAX, "sharded verdict (world of one)");
+        const auto all = composer.gather_column(res, 300);
+        EXPECT(all == composer.values(res) && all[0] == BlsScalar::one() && all[1] == BlsScalar::zero(), "gathered results");
+        const uint64_t vars_per = 2 * 19 + 523;
+        EXPECT(composer.gather_variables(1, 300 * vars_per) == composer.variables(5 + 300, 300 * vars_per), "gathered witness shard == the composer's variables");
+        composer.export_to("/tmp/pg_cpp_mirror_export.pgexp", true);
+        FILE* f = std::fopen("/tmp/pg_cpp_mirror_export.pgexp", "rb");
+        char magic[8] = {0}; uint32_t ver = 0, flags = 0; uint64_t head[3] = {0, 0, 0};
+        const bool read_ok = f && std::fread(magic, 1, 8, f) == 8 && std::fread(&ver, 4, 1, f) == 1 && std::fread(&flags, 4, 1, f) == 1 && std::fread(head, 8, 3, f) == 3;
+        if (f) std::fclose(f);
+        EXPECT(read_ok && std::memcmp(magic, "PGB2EXP1", 8) == 0 && ver == 1 && flags == 1 && head[0] == composer.circuit_size() && head[1] == composer.num_variables() && head[2] == 3,
+               "export header: rows, variables, calls (fresh + add_input + range_check)");
+    }
+}
+
 int main() {
     try {
-        range_gate_test();
+        range_gate_test(); batch_extensions_test();
         max_bound_test(); range_check_test(); test_maybe_equal();
         test_conditionally_select_0(); test_conditionally_select_1(); test_is_not_zero();
         prover_first_round_test();
