@@ -78,7 +78,11 @@ enum {
  *             a wire that is one of the 256 packed bit variables of a decomposition is read as the bit the table stores for it,
  *             i.e. it is boolean by construction (b*b = b: the boolean_gate rows of ref:src/range.rs:144 fold to "holds").  Those
  *             variables cannot be overwritten through pg_poke_variable, so the assumption cannot be violated from outside.
- *             Same verdict as GENERIC on every composer state this API can produce. */
+ *             Runs of rows  sel_j*bit_j + x_j - x_{j+1} = 0  over consecutive Variables (the accumulator rows of ref:src/range.rs:146-152)
+ *             are evaluated as one loop with x_{j+1} kept in registers (one 32-byte load per row), as  x_j + t == x_{j+1} (mod q)
+ *             without a reduction.  Rows of the range widget (pg_range_gate_batch): D(f) = f(f-1)(f-2)(f-3) vanishes iff f is a base-4
+ *             digit, so a row whose four differences are digits holds without a multiplication; any other row is evaluated through
+ *             the polynomial.  Same verdict as GENERIC on every composer state this API can produce. */
 enum { PG_CHECK_GENERIC = 0, PG_CHECK_SPARSE = 1 };
 
 enum {
@@ -94,8 +98,8 @@ typedef struct pg_cfg {
     int32_t device;         /* CUDA ordinal */
     int32_t check_mode;     /* PG_CHECK_* */
     uint32_t flags;         /* PG_F_* */
-    uint32_t check_shape;   /* UNSTABLE tuning knob, keep 0: launch shape of the gate-check kernels (1..4 = alternatives, kernels.cuh CheckShape);
-                               never changes results */
+    uint32_t check_shape;   /* UNSTABLE tuning knob, keep 0: launch shape (threads x blocks per SM, loads in flight) of the gate-check kernels
+                               (1..4 = alternatives, kernels.cuh CheckShape / ProgDepth); never changes results */
     void *stream;           /* cudaStream_t to enqueue on; NULL = the engine creates its own non-blocking stream */
 } pg_cfg;
 

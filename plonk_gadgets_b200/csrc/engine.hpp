@@ -158,7 +158,7 @@ public:
     void destroy() {
         be.sync();
         release_segments();
-        dfree(d_counters); dfree(d_segs); dfree(ntt_tw); ntt_tw = nullptr;
+        dfree(d_counters); dfree(d_segs); dfree(ntt_tw); ntt_tw = nullptr; dfree(fb_table_gen); fb_table_gen = nullptr;
         for (auto& kv : pool_free) be.release(kv.second);
         for (auto& kv : pool_live) be.release(kv.first);
         pool_free.clear(); pool_live.clear();
@@ -1075,6 +1075,7 @@ public:
     // ------------------------------------------------------------------------------------------------ evaluation domain
     // SURVEY.md 8f.2 (first half): EvaluationDomain::fft / ifft and the wire polynomials of Prover::prove; see ntt.cuh.
     uint4* ntt_tw = nullptr; uint32_t ntt_tw_log_n = 0;
+    uint4* fb_table_gen = nullptr;                   // window multiples of the G1 generator (g1_fixed_base_mul_dev), kept for the life of the ctx
     int ntt_twiddles(uint32_t log_n) {
         if (ntt_tw && ntt_tw_log_n == log_n) return PG_OK;
         if (ntt_tw) { be.sync(); dfree(ntt_tw); ntt_tw = nullptr; }
@@ -1481,15 +1482,25 @@ public:
         if (!out_on_device) { d_out = (uint4*)dalloc(n * sizeof(pg_g1_affine)); if (!d_out) return fail(PG_ERR_OOM, "point buffer"); scratch.push_back(d_out); }
         G1Affine b;
         if (base) memcpy(&b, base, sizeof(G1Affine)); else b = g1_generator();
-        if (n >= FB_MIN_POINTS) {
+        // The table costs a few milliseconds to build (its critical path is 248 dependent doublings and one inversion on a thread):
+        // worth it from FB_MIN_POINTS scalars on, or from FB_MIN_POINTS_CACHED when it exists already -- the generator's table is kept
+        // for the life of the ctx (PublicParameters::setup and the Lagrange-basis SRS both multiply the generator).
+        const char* fb_env = getenv("PG_FB_MIN");                                                                  // tests
+        const uint64_t min_env = fb_env ? strtoull(fb_env, nullptr, 10) : 0;
+        const bool have_table = !base && fb_table_gen;
+        if (n >= (min_env ? min_env : have_table ? FB_MIN_POINTS_CACHED : FB_MIN_POINTS)) {
             // windowed table of multiples of the base, then tiles of FB_TILE scalars: <= 32 mixed additions each, batch normalisation
             const uint64_t n_table = (uint64_t)FB_WINDOWS * FB_ENTRIES, tile = std::min<uint64_t>(n, FB_TILE);
-            uint4* table = (uint4*)dalloc(n_table * sizeof(pg_g1_affine));
+            uint4* table = have_table ? fb_table_gen : (uint4*)dalloc(n_table * sizeof(pg_g1_affine));
             uint4* xyzz = (uint4*)dalloc(tile * sizeof(G1X)); uint4* prefix = (uint4*)dalloc(tile * sizeof(Fp));
             if (!table || !xyzz || !prefix) return fail(PG_ERR_OOM, "fixed-base buffers");
-            scratch.push_back(table); scratch.push_back(xyzz); scratch.push_back(prefix);
-            G1WindowTableBody::Args ta; ta.table = table; ta.n = n_table; ta.base = b;
-            if (!be.template run_simple<G1WindowTableBody>(ta, n_table, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base table kernel");
+            if (!have_table && base) scratch.push_back(table);
+            scratch.push_back(xyzz); scratch.push_back(prefix);
+            if (!have_table) {
+                G1WindowTableBody::Args ta; ta.table = table; ta.n = n_table; ta.base = b;
+                if (!be.template run_simple<G1WindowTableBody>(ta, n_table, CLS_OTHER)) return fail(PG_ERR_CUDA, "fixed-base table kernel");
+                if (!base) fb_table_gen = table;
+            }
             for (uint64_t i0 = 0; i0 < n; i0 += tile) {
                 const uint64_t cnt = std::min<uint64_t>(tile, n - i0), threads = (cnt + FB_CHUNK - 1) / FB_CHUNK;
                 G1FixedBaseWindowedBody::Args wa{d_scalars + 2 * i0, table, xyzz, cnt};

@@ -211,13 +211,13 @@ struct FrPowersBody {
     }
 };
 
-// The same through a windowed table of multiples of the base (used from FB_MIN_POINTS scalars on): table[w * 255 + d - 1] =
+// The same through a windowed table of multiples of the base (used from FB_MIN_POINTS scalars on, FB_MIN_POINTS_CACHED when the table exists): table[w * 255 + d - 1] =
 // d * 2^(8w) * base for the 32 byte-windows of a scalar, so that one scalar multiplication is at most 32 mixed additions instead of
 // 255 doublings + ~128 additions; the XYZZ results are normalised to affine with Montgomery's trick (one inversion per FB_CHUNK points).
 // The accumulated scalar stays below q < the group order at every step, so an addition never meets its own operand (no doubling
 // case); the complete formulas cover it anyway.
 constexpr uint32_t FB_WINDOWS = 32, FB_ENTRIES = 255, FB_CHUNK = 32;
-constexpr uint64_t FB_MIN_POINTS = 512, FB_TILE = 1ull << 20;
+constexpr uint64_t FB_MIN_POINTS = 65536, FB_MIN_POINTS_CACHED = 256, FB_TILE = 1ull << 20;    // building the table: ~10 ms (248 dependent doublings); the plain kernel does 3.1 M/s
 struct G1WindowTableBody {
     struct Args { uint4* table; uint64_t n; G1Affine base; };
     PG_HD static void run(const Args& a, uint64_t t) {

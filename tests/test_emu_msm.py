@@ -48,9 +48,10 @@ def test_emu_group_law(emu, oracle):
     assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, 5, axis=0), sc))
 
 
-def test_emu_windowed_fixed_base(emu, oracle):
+def test_emu_windowed_fixed_base(emu, oracle, monkeypatch):
     """From 512 scalars on pg_g1_fixed_base_mul / pg_srs_powers go through the table of window multiples and the batch
     normalisation (msm.cuh: G1WindowTableBody, G1FixedBaseWindowedBody, G1BatchAffineBody) and the device-side powers of beta."""
+    monkeypatch.setenv("PG_FB_MIN", "512")                   # (the table pays off from 2^14 scalars on; forced here at test sizes)
     c = pg.StandardComposer(_cdll=emu)
     rnd = random.Random(21)
     n = 530                                                  # not a multiple of the normalisation chunk

@@ -572,7 +572,12 @@ def test_g1_group_law_gpu(oracle):
     assert np.array_equal(to_oracle(c.g1_fixed_base_mul(sc)), oracle.g1_mul(np.repeat(g, 64, axis=0), sc))
     beta = oracle.from_ints([rnd.randrange(Q)])
     assert np.array_equal(to_oracle(c.srs_powers(beta[0], 48)), oracle.srs_powers(beta, 48))
-    # from 512 scalars on: table of window multiples + batch normalisation, powers of beta computed on the device
+    # table of window multiples + batch normalisation (from 2^16 scalars on, or 256 once the generator's table exists), powers of beta
+    # computed on the device
+    big = oracle.from_ints([rnd.randrange(Q) for _ in range(1 << 16)])
+    got = to_oracle(c.g1_fixed_base_mul(big))
+    pick = [0, 1, 777, (1 << 16) - 1]
+    assert np.array_equal(got[pick], oracle.g1_mul(np.repeat(g, len(pick), axis=0), big[pick]))
     n = 3000
     ks = [0, 1, 255, 256, 2 ** 248, Q - 1] + [rnd.randrange(Q) for _ in range(n - 6)]
     ks[77] = 0; ks[n - 1] = 0
