@@ -273,14 +273,11 @@ class StandardComposer:
         self._ok(self._L.pg_check_sharded(self._ctx, arr, n_ops, C.byref(bad), C.byref(first), C.byref(err)), "pg_check_sharded")
         return bad.value, (None if first.value == UINT64_MAX else first.value), err.value
 
-    def gather_column(self, v: "Variables", out=None):
-        """All-gather of a column: (values of all ranks' shards in rank order, per-rank counts).  out: optional device tensor / DevicePtr."""
-        world = 64
-        counts = (C.c_uint64 * world)()
+    def gather_column(self, v: "Variables", out):
+        """All-gather of a column (per-instance results of a call): fills `out` (host array or device tensor sized for the shards of
+        all ranks) in rank order = instance order of the whole batch.  Returns (total, [count of rank 0, count of rank 1, ...])."""
+        counts = (C.c_uint64 * 64)()
         total = C.c_uint64()
-        if out is None:
-            # two-step: learn the total with a zero-capacity call would be a collective of its own; callers without `out` pass through host memory sized by the caller's knowledge
-            raise ValueError("gather_column needs a destination (host array or device tensor) sized for all ranks")
         p, dev, n, keep = _scalars(out)
         self._ok(self._L.pg_gather_column(self._ctx, v.col, p, n, dev, counts, C.byref(total)), "pg_gather_column")
         return total.value, [int(x) for x in counts]
