@@ -164,6 +164,26 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(index: int):
+    """One process per GPU: run this process (and first-touch its pinned host buffers) on the CPUs NVML reports as local to GPU `index`,
+    so that eight ranks do not stream their host<->device copies through one socket's memory.  Returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < n_cpu}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 _JSON_FD = None
 
 
@@ -210,6 +230,7 @@ def main():
         raise SystemExit("bench.py needs a B200: plonk_gadgets_b200 has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None      # pinned host buffers next to the GPU they feed (end-to-end leg)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warm = max(args.warmup, 3)
@@ -357,7 +378,8 @@ def main():
             "config": {"workload": f"range_check batch 2^{args.log2n} {'per GPU' if args.scaling == 'weak' else 'in total'}, bounds [0, 2^64) (k=65): 271 rows / 653 variables per instance",
                        "check_mode": args.check_mode, "l2": "inputs larger than L2 (512 MiB of witnesses, ~77 GB variable table per step)",
                        "timed_region": "composer reset + add_input + witness generation + gate check + verdict all-reduce + verdict read",
-                       "instances_per_gpu": n, "instances_total": n_total},
+                       "instances_per_gpu": n, "instances_total": n_total,
+                       "host_numa_binding": f"rank bound to the {numa} CPUs local to its GPU" if numa else "none"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32 + 64, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(tim["check_launches"] + tim["witness_launches"] + tim["other_launches"]),
@@ -366,7 +388,7 @@ def main():
             "verdict": {"n_unsat": g_bad, "n_err": g_err,
                         "collective": "ncclAllReduce(sum, min) inside every step (pg_check_sharded)" if world > 1 else "world of one rank"},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:               # the CPU baseline is a single-GPU-run item (rank 0 at N = 1)
             line["cpu_baseline"] = cpu_reference_run(None, os.cpu_count() or 1)
         _emit(line)
     if world > 1:
