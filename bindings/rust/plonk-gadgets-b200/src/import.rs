@@ -114,6 +114,8 @@ pub fn import_into<R: Read>(composer: &mut StandardComposer, mut src: R) -> Resu
         done += cnt as u64;
     }
     // ---- replay, call by call (call 0 is the fresh composer itself: zero variable + the two dummy rows)
+    // (`zero_var()` / `circuit_size()` are dusk-plonk 0.8 accessors recalled from memory, like everything marked [dusk-plonk] in this
+    // repository: this file has never met a compiler.)
     let mut vars: Vec<Variable> = Vec::with_capacity(n_vars as usize);
     vars.push(composer.zero_var());
     // Variables 1..=4 of StandardComposer::new() (6, 1, 7, -20) are not reachable through a public accessor; they never appear on a
