@@ -87,11 +87,13 @@ enum { PG_CHECK_GENERIC = 0, PG_CHECK_SPARSE = 1 };
 
 enum {
     PG_F_TIMING = 1u,       /* record CUDA events around every kernel class (pg_get_timing) */
-    PG_F_FUSED_CHECK = 2u   /* with PG_CHECK_SPARSE: the range gadgets' witness kernels also evaluate the rows they generate (on the values
-                               they hold in registers, structure-aware arithmetic), so the variable table is written once and never read
-                               again for the verdict; pg_check then only launches for segments that were not verified that way or whose
-                               Variables were overwritten since (pg_poke_variable), and adds the recorded verdict.  Same verdict as without
-                               the flag on every composer state this API can produce. */
+    PG_F_FUSED_CHECK = 2u   /* with PG_CHECK_SPARSE: the gadgets' witness kernels also evaluate the rows they generate (on the values they hold
+                               in registers, structure-aware arithmetic) -- range_check, max_bound, maybe_equal, is_non_zero (the _flags call in
+                               the uniform layout), conditionally_select_* -- so the variable table is written once and never read again for
+                               the verdict; pg_check / pg_check_sharded then only launch for what was not verified that way (the fresh rows,
+                               constrain_to_constant and range_gate rows, is_non_zero with `?` semantics) or whose Variables were overwritten
+                               since (pg_poke_variable), and add the recorded verdict.  Same verdict as without the flag on every composer
+                               state this API can produce. */
 };
 
 typedef struct pg_cfg {

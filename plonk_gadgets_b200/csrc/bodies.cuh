@@ -133,7 +133,15 @@ struct FusedVerdict {
     uint32_t bad = 0, first = ~0u;
     PG_HD void row(bool holds, uint32_t r) { if (!holds) { bad++; first = first < r ? first : r; } }
     PG_HD void flush(const RangeArgs& a, uint64_t i) const;
+    // rows of instance i start at global row `row0`
+    PG_HD void flush_at(unsigned long long* counters, unsigned long long row0) const {
+        if (!bad) return;
+        counter_add(counters + CNT_FUSED_UNSAT, (unsigned long long)bad);
+        counter_min(counters + CNT_FUSED_FIRST, row0 + first);
+    }
 };
+// what the scalar gadgets' kernels need to evaluate their own rows (PG_F_FUSED_CHECK): null counters = not fused
+struct FusedSite { unsigned long long* counters; unsigned long long base_row; };
 template <bool RANGE, bool FUSED = false>
 struct RangePre {
     static constexpr int E = RANGE ? 2 : 1;
@@ -228,25 +236,36 @@ PG_HD void FusedVerdict::flush(const RangeArgs& a, uint64_t i) const {
 }
 
 // ---------------------------------------------------------------------------------------------------- maybe_equal
-struct MaybeEqualArgs { DevTab a_tab, b_tab; uint32_t a_loc, b_loc; uint4* fr; uint64_t stride; uint64_t n; };
+struct MaybeEqualArgs { DevTab a_tab, b_tab; uint32_t a_loc, b_loc; uint4* fr; uint64_t stride; uint64_t n; FusedSite fused; };
 // maybe_equal inside the batch inversion's walks (k_batch_inv<MaybeEqualFused>): u is produced where the first walk would
-// load it, y where the second walk has just written z.  in_slot = 0 (u), out_slot = 1 (z).
+// load it, y where the second walk has just written z.  in_slot = 0 (u), out_slot = 1 (z).  Rows (3 per instance): a - b - u = 0,
+// -z*u - y + 1 = 0, y*u = 0.
 struct MaybeEqualFused {
     typedef MaybeEqualArgs Args;
     PG_HD static Fr pre(const Args& a, uint64_t i) {
-        const Fr u = fr_sub(loc_load(&a.a_tab, a.a_loc, i), loc_load(&a.b_tab, a.b_loc, i));                         // scalar.rs:111-121
+        const Fr va = loc_load(&a.a_tab, a.a_loc, i), vb = loc_load(&a.b_tab, a.b_loc, i);
+        const Fr u = fr_sub(va, vb);                                                                                    // scalar.rs:111-121
         tab_store_fr(a.fr, a.stride, 0, i, u);
+        if (a.fused.counters) { FusedVerdict fv; fv.row(fr_sum_equals(vb, u, va), 0); fv.flush_at(a.fused.counters, a.fused.base_row + 3 * i); }
         return u;
     }
     PG_HD static void post(const Args& a, uint64_t i, const Fr& u, const Fr& z) {
-        tab_store_fr(a.fr, a.stride, 2, i, fr_sub(fr_one(), fr_mul(z, u)));                                           // y, scalar.rs:126
+        const Fr zu = fr_mul(z, u), y = fr_sub(fr_one(), zu);
+        tab_store_fr(a.fr, a.stride, 2, i, y);                                                                          // y, scalar.rs:126
+        if (a.fused.counters) {
+            FusedVerdict fv;
+            fv.row(fr_sum_equals(y, zu, fr_one()), 1);
+            fv.row(fr_is_zero(fr_mul(y, u)), 2);                                                                        // scalar.rs:129-138
+            fv.flush_at(a.fused.counters, a.fused.base_row + 3 * i);
+        }
     }
 };
 struct InvPlain { struct Args {}; };     // the batch inversion without a fused gadget: table slot in, table slot out
 
 // ---------------------------------------------------------------------------------------------------- is_non_zero
-struct IsNonZeroFused {   // inside k_batch_inv's first walk (in_slot = 0, out_slot = 1); slots: 0 = var_assigned, 1 = inv, 2 = one
-    struct Args { const uint4* assigned; uint4* fr; uint64_t stride; uint64_t n; unsigned long long* counters; uint8_t* flags; };
+struct IsNonZeroFused {   // inside k_batch_inv's walks (in_slot = 0, out_slot = 1); slots: 0 = var_assigned, 1 = inv, 2 = one
+    struct Args { const uint4* assigned; uint4* fr; uint64_t stride; uint64_t n; unsigned long long* counters; uint8_t* flags;
+                  DevTab var_tab; uint32_t var_loc; FusedSite fused; };      // var_*: the operand column (read by the fused check only)
     PG_HD static Fr pre(const Args& a, uint64_t i) {
         const Fr va = aos_load(a.assigned, i);
         count_unreduced(a.counters, va, i);
@@ -258,28 +277,45 @@ struct IsNonZeroFused {   // inside k_batch_inv's first walk (in_slot = 0, out_s
         }
         if (a.flags) a.flags[i] = none ? 1 : 0;                                              // per-instance Result (pg_is_non_zero_batch_flags)
         tab_store_fr(a.fr, a.stride, 2, i, fr_one());                                        // one, scalar.rs:83
+        if (a.fused.counters) {                                                              // var - var_assigned = 0 (the constant-one row holds)
+            FusedVerdict fv; fv.row(fr_eq(loc_load(&a.var_tab, a.var_loc, i), va), 0); fv.flush_at(a.fused.counters, a.fused.base_row + 3 * i);
+        }
         return va;
     }
-    PG_HD static void post(const Args&, uint64_t, const Fr&, const Fr&) {}                   // nothing follows the inverse (scalar.rs:84-94 is a row)
+    PG_HD static void post(const Args& a, uint64_t i, const Fr&, const Fr& inv) {            // var*inv - 1 = 0, scalar.rs:84-94
+        if (!a.fused.counters) return;
+        FusedVerdict fv; fv.row(fr_eq(fr_mul(loc_load(&a.var_tab, a.var_loc, i), inv), fr_one()), 2); fv.flush_at(a.fused.counters, a.fused.base_row + 3 * i);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------- selections
 struct SelectZeroBody {
-    struct Args { DevTab x_tab, s_tab; uint32_t x_loc, s_loc; uint4* fr; uint64_t stride; uint64_t n; };
+    struct Args { DevTab x_tab, s_tab; uint32_t x_loc, s_loc; uint4* fr; uint64_t stride; uint64_t n; FusedSite fused; };
     PG_HD static void run(const Args& a, uint64_t i) {
-        tab_store_fr(a.fr, a.stride, 0, i, fr_mul(loc_load(&a.x_tab, a.x_loc, i), loc_load(&a.s_tab, a.s_loc, i)));   // scalar.rs:26
+        const Fr x = loc_load(&a.x_tab, a.x_loc, i), s = loc_load(&a.s_tab, a.s_loc, i);
+        const Fr r = fr_mul(x, s);                                                            // scalar.rs:26
+        tab_store_fr(a.fr, a.stride, 0, i, r);
+        if (a.fused.counters) { FusedVerdict fv; fv.row(fr_eq(fr_mul(x, s), r), 0); fv.flush_at(a.fused.counters, a.fused.base_row + i); }   // x*s - r = 0
     }
 };
 struct SelectOneBody {
-    struct Args { DevTab y_tab, s_tab; uint32_t y_loc, s_loc; uint4* fr; uint64_t stride; uint64_t n; };
+    struct Args { DevTab y_tab, s_tab; uint32_t y_loc, s_loc; uint4* fr; uint64_t stride; uint64_t n; FusedSite fused; };
     PG_HD static void run(const Args& a, uint64_t i) {
         const Fr y = loc_load(&a.y_tab, a.y_loc, i), s = loc_load(&a.s_tab, a.s_loc, i), one = fr_one();
         const Fr sy = fr_mul(y, s);                                                           // scalar.rs:43
         const Fr oms = fr_sub(one, s);                                                        // scalar.rs:45-50
+        const Fr r = fr_add(sy, oms);                                                         // scalar.rs:53-58
         tab_store_fr(a.fr, a.stride, 0, i, one);                                              // scalar.rs:41
         tab_store_fr(a.fr, a.stride, 1, i, sy);
         tab_store_fr(a.fr, a.stride, 2, i, oms);
-        tab_store_fr(a.fr, a.stride, 3, i, fr_add(sy, oms));                                  // scalar.rs:53-58
+        tab_store_fr(a.fr, a.stride, 3, i, r);
+        if (a.fused.counters) {                                   // rows: one = 1 (holds), y*s - sy = 0, one - s - oms = 0, sy + oms - r = 0
+            FusedVerdict fv;
+            fv.row(fr_eq(fr_mul(y, s), sy), 1);
+            fv.row(fr_sum_equals(s, oms, one), 2);
+            fv.row(fr_sum_equals(sy, oms, r), 3);
+            fv.flush_at(a.fused.counters, a.fused.base_row + 4 * i);
+        }
     }
 };
 

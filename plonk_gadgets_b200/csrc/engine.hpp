@@ -548,7 +548,7 @@ public:
             const Segment& os = segs[operand.seg];
             const void* whole = (operand.inst_off == 0 && operand.n == os.n_inst) ? (const void*)os.fr : nullptr;
             // PG_F_FUSED_CHECK (structure-aware mode only): the same kernels also evaluate the rows they generate
-            const bool fused = (cfg.flags & PG_F_FUSED_CHECK) && cfg.check_mode == PG_CHECK_SPARSE;
+            const bool fused = fused_mode();
             a.base_row = s.base_row; a.n_rows = (uint32_t)s.t.rows.size();
             // decomposition -> inversion -> results; with the fused check, behind a chunked input copy, the three run chunk by chunk, so
             // that an asynchronous read of the results (pg_col_read, dst_on_device = 2) starts on the first chunk while the later ones
@@ -573,6 +573,11 @@ public:
         return PG_OK;
     }
 
+    // PG_F_FUSED_CHECK (structure-aware mode): the gadget's own kernels evaluate its rows; marks the segment and counts the rows
+    bool fused_mode() const { return (cfg.flags & PG_F_FUSED_CHECK) && cfg.check_mode == PG_CHECK_SPARSE; }
+    FusedSite fused_site(const Segment& s) const { return fused_mode() ? FusedSite{d_counters, s.base_row} : FusedSite{nullptr, 0}; }
+    void mark_fused(Segment& s) { if (fused_mode() && s.n_inst) { s.fused_ok = true; be.count_check(PG_CK_FUSED, s.n_inst * s.t.rows.size()); } }
+
     int maybe_equal_batch(pg_col ca, pg_col cb, pg_col* out) {
         const Column *a = column(ca), *b = column(cb);
         if (!a || !b || !out || a->n != b->n) return fail(PG_ERR_ARG, "maybe_equal_batch: bad columns");
@@ -580,11 +585,12 @@ public:
         int rc = push_segment(make_maybe_equal_template(&result_local), ops[0].n, ops, 2);
         if (rc) return rc;
         Segment& s = segs.back();
-        MaybeEqualArgs g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, ops[0].n};
+        MaybeEqualArgs g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, ops[0].n, fused_site(s)};
         if (g.n) {
             BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
             inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = g.n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
             if (!be.template run_batch_inv_fused<MaybeEqualFused>(inv, g, CLS_WITNESS)) return fail(PG_ERR_CUDA, "maybe_equal kernel");
+            mark_fused(s);
         }
         *out = new_column((uint32_t)segs.size() - 1, result_local, g.n);
         return PG_OK;
@@ -603,7 +609,7 @@ public:
         if (rc) return rc;
         {
             Segment& s = segs.back();
-            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters, nullptr};
+            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters, nullptr, s.tabs[1], loc_with_tab(loc_of(operand), 0), FusedSite{nullptr, 0}};   // (`?` semantics may truncate the segment: not fused)
             BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
             inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
             if (n && !be.template run_batch_inv_fused<IsNonZeroFused>(inv, g, CLS_WITNESS)) return fail(PG_ERR_CUDA, "is_non_zero kernel");
@@ -662,10 +668,13 @@ public:
         const size_t seg_index = segs.size() - 1;
         if (n) {
             Segment& s = segs.back();
-            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters, d_flags};
+            // the uniform layout keeps every instance's three rows where the kernel numbers them: its rows can be evaluated in the kernel
+            const FusedSite site = layout == PG_NZ_UNIFORM ? fused_site(s) : FusedSite{nullptr, 0};
+            IsNonZeroFused::Args g{src, s.fr, s.n_alloc, n, d_counters, d_flags, s.tabs[1], loc_with_tab(loc_of(operand), 0), site};
             BatchInvArgs inv; memset(&inv, 0, sizeof(inv));
             inv.fr = s.fr; inv.stride = s.n_alloc; inv.n = n; inv.n_pairs = 1; inv.in_slot[0] = 0; inv.out_slot[0] = 1;
             if (!be.template run_batch_inv_fused<IsNonZeroFused>(inv, g, CLS_WITNESS)) return fail(PG_ERR_CUDA, "is_non_zero kernel");
+            if (layout == PG_NZ_UNIFORM) mark_fused(s);
         }
         unsigned long long c[CNT_WORDS];
         if ((rc = read_counters(c))) return rc;
@@ -718,9 +727,10 @@ public:
         Segment& s = segs.back();
         const uint64_t n = ops[0].n;
         bool ok = true;
-        if (one) { SelectOneBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, n}; if (n) ok = be.template run_simple<SelectOneBody>(g, n, CLS_WITNESS); }
-        else { SelectZeroBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, n}; if (n) ok = be.template run_simple<SelectZeroBody>(g, n, CLS_WITNESS); }
+        if (one) { SelectOneBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, n, fused_site(s)}; if (n) ok = be.template run_simple<SelectOneBody>(g, n, CLS_WITNESS); }
+        else { SelectZeroBody::Args g{s.tabs[1], s.tabs[2], loc_with_tab(loc_of(ops[0]), 0), loc_with_tab(loc_of(ops[1]), 0), s.fr, s.n_alloc, n, fused_site(s)}; if (n) ok = be.template run_simple<SelectZeroBody>(g, n, CLS_WITNESS); }
         if (!ok) return fail(PG_ERR_CUDA, "select kernel");
+        if (n) mark_fused(s);
         *out = new_column((uint32_t)segs.size() - 1, result_local, n);
         return PG_OK;
     }

@@ -48,8 +48,9 @@ def emit(name, rows, ms, tim, extra=None):
 
 
 def main():
-    mode = pg.CHECK_SPARSE if "--sparse" in sys.argv else pg.CHECK_GENERIC
-    c = pg.StandardComposer(device=0, check_mode=mode, timing=True, stream=stream.cuda_stream)
+    fused = "--fused" in sys.argv                                  # structure-aware + PG_F_FUSED_CHECK: rows evaluated by the gadgets' own kernels
+    mode = pg.CHECK_SPARSE if "--sparse" in sys.argv or fused else pg.CHECK_GENERIC
+    c = pg.StandardComposer(device=0, check_mode=mode, timing=True, stream=stream.cuda_stream, fused_check=fused)
     zero_2p64 = to_mont(c, [0, 2 ** 64])
     mn, mx = zero_2p64[0:1].copy(), zero_2p64[1:2].copy()
 

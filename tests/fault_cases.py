@@ -248,3 +248,49 @@ def unreduced_inputs_rejected(make_composer, ob):
         assert e.value.code == -2
     assert c.check_circuit_satisfied()[0] == 0
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------------- fused check, scalar gadgets
+def fused_scalar_gadgets(make_composer, ob, n: int = 90):
+    """PG_F_FUSED_CHECK over maybe_equal / is_non_zero (every Result kept) / conditionally_select_*: the rows are evaluated by the
+    gadgets' own kernels (kind "fused": the check launches only for the fresh rows and the claim rows), the verdict equals the one of
+    an unfused structure-aware composer on the same inputs -- including the rows errored and mismatching is_non_zero instances fail --
+    and overwriting a Variable afterwards sends the affected segments back to the check kernel."""
+    vals = synth_wide(321, n)
+    other = [v if i % 2 == 0 else (v + 1 + i) % Q for i, v in enumerate(vals)]
+    assigned = list(vals)
+    assigned[7] = 0; assigned[n - 2] = 0                    # Err(NonExistingInverse): rows 0 and 2 of those instances are unsatisfied
+    assigned[11] = (assigned[11] + 5) % Q                   # mismatch: rows 0 and 2 as well
+    sel = [v & 1 for v in synth_wide(322, n)]
+    verdicts = []
+    for fused in (False, True):
+        c = make_composer(check_mode=pg.CHECK_SPARSE, fused_check=fused)
+        c.check_stats(reset=True)
+        a = c.add_input(ob.from_ints(vals)); b = c.add_input(ob.from_ints(other)); s = c.add_input(ob.from_ints(sel))
+        eq = pg.maybe_equal(c, a, b)
+        flags = pg.is_non_zero_flags(c, a, ob.from_ints(assigned), pg.NZ_UNIFORM)
+        so = pg.conditionally_select_one(c, a, s)
+        sz = pg.conditionally_select_zero(c, so, s)
+        c.constrain_to_constant(eq, ob.from_ints([1 if i % 2 == 0 else 0 for i in range(n)]))        # true claims
+        assert flags.sum() == 2 and flags[7] and flags[n - 2]
+        got = c.check_circuit_satisfied()
+        stats = c.check_stats(reset=True)
+        n_rows = c.circuit_size()
+        exp = eval_rows(ob, c.rows(0, n_rows, want=("w_val", "sel", "pi")))
+        assert got == (len(exp), exp[0]) and len(exp) == 6, (fused, got, exp)
+        if fused:
+            assert stats["fused"][1] == n * (3 + 3 + 4 + 1), stats            # maybe_equal, is_non_zero, select_one, select_zero
+            assert stats["program"][1] + stats["rowpar"][1] + stats["instance_terms"][1] == 3 + n, stats    # fresh rows + claim rows only
+        verdicts.append(got)
+        assert ob.to_ints(sz.values()) == [v * s_ * s_ % Q if s_ else 0 for v, s_ in zip(vals, sel)]
+        # a poke after generation: the segment (and the later ones) go back to the kernel, which finds exactly the big-int verdict
+        first_var, stride = c._col_geometry(so.col)
+        var = first_var + stride * (n // 2)
+        old = c.variables(var, 1)[0].copy()
+        c.poke_variable(var, ob.from_ints([(ob.to_ints(old[None])[0] + 3) % Q])[0])
+        exp2 = eval_rows(ob, c.rows(0, n_rows, want=("w_val", "sel", "pi")))
+        assert len(exp2) > len(exp) and c.check_circuit_satisfied() == (len(exp2), exp2[0])
+        c.poke_variable(var, old)
+        assert c.check_circuit_satisfied() == got
+        c.close()
+    assert verdicts[0] == verdicts[1]

@@ -338,11 +338,14 @@ def test_emu_poked_range_segment(emu, oracle, gadget, bits, per_inst):
 def test_emu_fused_check(emu, golden, oracle):
     """PG_F_FUSED_CHECK: rows evaluated inside witness generation give the verdicts of the separate check, and a poked segment
     falls back to the check kernel."""
-    for name in ("batch_mixed_circuit", "batch_max_bound_k8_claims", "kat_range_check_1_wrongclaim", "batch_range_check_k65_per_instance_bounds"):
+    for name in ("batch_mixed_circuit", "batch_max_bound_k8_claims", "kat_range_check_1_wrongclaim", "batch_range_check_k65_per_instance_bounds",
+                 "batch_is_non_zero_maybe_equal", "kat_is_non_zero_mismatch", "kat_select_one_sel1", "kat_select_zero_sel1_claim0",
+                 "kat_maybe_equal_20_3330_wrongclaim", "batch_range_gate_mixed"):
         spec = golden[name]
         snap = run_engine(spec["program"], lambda: pg.StandardComposer(check_mode=pg.CHECK_SPARSE, fused_check=True, _cdll=emu), oracle)
         assert snap.unsat == spec["expected"]["unsat"], name
         assert snap.digest() == spec["expected"]["digest"], name
+    fc.fused_scalar_gadgets(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle, n=90)
     for gadget, bits, per_inst in (("range_check", 8, False), ("max_bound", 12, True), ("range_check", 64, False)):
         fc.poked_range_segment(lambda **kw: pg.StandardComposer(_cdll=emu, **kw), oracle, n=131, gadget=gadget, bits=bits, per_instance_bounds=per_inst,
                                modes=(pg.CHECK_SPARSE,), expect_kind={pg.CHECK_SPARSE: "program"}, fused=True)

@@ -846,6 +846,13 @@ def test_poked_max_bound_k253(oracle):
     fc.poked_range_segment(gpu_composer, oracle, n=HEADLINE_N, gadget="max_bound", bits=252, expect_kind=KINDS, seed=7)
 
 
+def test_fused_check_scalar_gadgets(oracle):
+    """PG_F_FUSED_CHECK over maybe_equal / is_non_zero / conditionally_select_* at a size that takes the one-thread-per-instance kernels
+    when a poke sends a segment back to them (tests/fault_cases.py)."""
+    fc.fused_scalar_gadgets(gpu_composer, oracle, n=90)
+    fc.fused_scalar_gadgets(gpu_composer, oracle, n=HEADLINE_N)
+
+
 def test_fused_check_at_the_headline_launch_shape(oracle):
     """PG_F_FUSED_CHECK: the range gadgets' witness kernels evaluate the rows they generate (kind "fused": no check launch for the
     segment); overwriting a Variable sends the segment back to k_check_prog, which must report exactly the big-int verdict."""
