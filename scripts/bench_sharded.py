@@ -52,8 +52,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for mode_name, mode in (("generic", pg.CHECK_GENERIC), ("sparse", pg.CHECK_SPARSE)):
-        c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream)
+    for mode_name, mode in (("generic", pg.CHECK_GENERIC), ("sparse", pg.CHECK_SPARSE), ("fused", pg.CHECK_SPARSE)):
+        c = pg.StandardComposer(device=local, check_mode=mode, timing=True, stream=stream.cuda_stream, fused_check=mode_name == "fused")
         c.comm_init(fresh_uid(), rank, world)
         to_mont = lambda ints: c.fr_op(0, np.array([[(v >> (64 * k)) & (2 ** 64 - 1) for k in range(4)] for v in ints], dtype=np.uint64), np.repeat(R2, len(ints), axis=0))
         b = to_mont([0, 2 ** 64, 2 ** 252])

@@ -22,13 +22,13 @@ def _sequential(oracle, circuit, device=0):
     return c, outs, (bad, first, n_err)
 
 
-@pytest.mark.parametrize("mode", [pg.CHECK_GENERIC, pg.CHECK_SPARSE])
-def test_world_of_one_over_nccl(oracle, mode):
+@pytest.mark.parametrize("mode,fused", [(pg.CHECK_GENERIC, False), (pg.CHECK_SPARSE, False), (pg.CHECK_SPARSE, True)])
+def test_world_of_one_over_nccl(oracle, mode, fused):
     from tests.test_shard_plan import mixed_circuit
     circuit = mixed_circuit(oracle, scale=40, wrong_claims=(3, 200))
     ref, ref_outs, verdict = _sequential(oracle, circuit)
     assert verdict[0] == 3 and verdict[2] == 1
-    c = pg.StandardComposer(device=0, check_mode=mode)
+    c = pg.StandardComposer(device=0, check_mode=mode, fused_check=fused)
     c.comm_init(pg.comm_unique_id(), 0, 1)
     mine = sharding.plan_of(circuit, 1, pg.SHARD_ROWS)[0]
     outs, n_err = sharding.run_circuit(c, circuit, mine)
@@ -49,13 +49,13 @@ def test_world_of_one_over_nccl(oracle, mode):
     c.close(); ref.close()
 
 
-def _rank(rank, world, uid, policy, mode, q):
+def _rank(rank, world, uid, policy, mode, fused, q):
     sys.path.insert(0, ROOT)
     import torch
     from oracle import binding as ob
     from tests.test_shard_plan import mixed_circuit
     circuit = mixed_circuit(ob, scale=40, wrong_claims=(3, 200))
-    c = pg.StandardComposer(device=rank, check_mode=mode)
+    c = pg.StandardComposer(device=rank, check_mode=mode, fused_check=fused)
     c.comm_init(uid, rank, world)
     mine = sharding.plan_of(circuit, world, policy)[rank]
     outs, n_err = sharding.run_circuit(c, circuit, mine)
@@ -76,8 +76,8 @@ def _rank(rank, world, uid, policy, mode, q):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("policy,mode", [(0, 0), (1, 1)])
-def test_two_gpus_equal_the_sequential_composer(oracle, policy, mode):
+@pytest.mark.parametrize("policy,mode,fused", [(0, 0, False), (1, 1, False), (0, 1, True)])
+def test_two_gpus_equal_the_sequential_composer(oracle, policy, mode, fused):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
@@ -88,7 +88,7 @@ def test_two_gpus_equal_the_sequential_composer(oracle, policy, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     uid = pg.comm_unique_id()
-    procs = [ctx.Process(target=_rank, args=(r, 2, uid, policy, mode, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank, args=(r, 2, uid, policy, mode, fused, q)) for r in range(2)]
     for p in procs: p.start()
     got = [q.get(timeout=600) for _ in range(2)]
     for p in procs: p.join(timeout=120)
