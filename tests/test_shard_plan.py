@@ -133,3 +133,41 @@ def test_two_rank_mixed_circuit_equals_sequential_composer(oracle, policy):
     w = oc.add_input_batch(circuit[0]["values"])
     y = oc.range_check_batch(circuit[1]["min"], circuit[1]["max"], w)
     assert (table[: oc.n_vars] == oc.variables()).all()
+
+
+# ---- properties of the plan over random circuits (hypothesis; the same examples on every run unless HYPOTHESIS_PROFILE=explore) ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_GADGETS = [(pg.OP_ADD_INPUT, 0), (pg.OP_RANGE_CHECK, 65), (pg.OP_RANGE_CHECK, 2), (pg.OP_MAX_BOUND, 253), (pg.OP_MAYBE_EQUAL, 0),
+            (pg.OP_IS_NON_ZERO, 0), (pg.OP_SELECT_ZERO, 0), (pg.OP_SELECT_ONE, 0), (pg.OP_CONSTRAIN, 0), (pg.OP_RANGE_GATE, 64)]
+
+
+@settings(max_examples=60, deadline=None)
+@given(groups=st.lists(st.tuples(st.integers(0, 5000), st.lists(st.sampled_from(_GADGETS), min_size=1, max_size=4)), min_size=1, max_size=6),
+       world=st.integers(1, 9), policy=st.sampled_from([0, 1]), interleave=st.booleans())
+def test_plan_properties_random_circuits(groups, world, policy, interleave):
+    ops = []
+    for g, (n, gadgets) in enumerate(groups):
+        ops += [(gad, bits, n, g) for gad, bits in gadgets]
+    if interleave:                                           # a group's calls need not be adjacent
+        ops = ops[::2] + ops[1::2]
+    plan = pg.shard_plan(ops, world, policy, _cdll=_lib.load())
+    shapes = [pg.op_shape(gad, bits) for gad, bits, _, _ in ops]
+    row, var = 3, 5
+    for k, (gad, bits, n, grp) in enumerate(ops):
+        r, v = shapes[k]
+        assert plan[0][k].inst_lo == 0 and plan[-1][k].inst_hi == n
+        for rank in range(world):
+            s = plan[rank][k]
+            assert s.inst_lo <= s.inst_hi <= n
+            assert rank + 1 == world or s.inst_hi == plan[rank + 1][k].inst_lo               # ranges tile [0, n) in rank order
+            assert (s.row_base, s.var_base) == (row + s.inst_lo * r, var + s.inst_lo * v)      # prefix sums = the sequential composer
+            first = next(j for j in range(len(ops)) if ops[j][3] == grp)
+            assert (s.inst_lo, s.inst_hi) == (plan[rank][first].inst_lo, plan[rank][first].inst_hi)   # one cut per group
+        row += n * r; var += n * v
+    if policy == pg.SHARD_ROWS:
+        rows_of = [sum((plan[rank][k].inst_hi - plan[rank][k].inst_lo) * shapes[k][0] for k in range(len(ops))) for rank in range(world)]
+        weight = {}
+        for k, (_, _, _, grp) in enumerate(ops):
+            weight[grp] = weight.get(grp, 0) + shapes[k][0]
+        assert max(rows_of) - min(rows_of) <= 2 * max(weight.values())                        # balanced to within an instance of the heaviest group
