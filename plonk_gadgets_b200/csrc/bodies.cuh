@@ -705,14 +705,21 @@ struct CheckRowsBody {
 //                    D(f) = u^2 - 1, u = f(f-3) + 1  (f(f-3) = g, (f-1)(f-2) = g + 2, g(g+2) = (g+1)^2 - 1): four multiplications,
 //                    then sum u_k^2 as ONE dot product with a single interleaved reduction, minus 4 -- 4*(64+48) + 4*64+48 = 752
 //                    wide multiplier instructions per row instead of 12 full multiplications; the 9-limb sum is tested for
-//                    "0 mod q" directly.  Inside a template a
+//                    "0 mod q" directly.  (Writing u as the square (f - 3/2)^2 - 5/4 and squaring with 36 products brings a row
+//                    to 528 products and is slower: the additions a squaring needs cost more integer-pipe time than the
+//                    products save on the multiplier pipe -- profiles/r05a_range_rows_variants.md.)  Inside a template a
 //                    range row is never the last one (range_gate closes with a q_range = 0 gate and assert_equal);
 //   rows with neither selector hold trivially.
 //   PG_CHECK_SPARSE: arithmetic rows through the structure-aware term evaluation, range rows through the digit test (see below).
 struct GateRowsCheckBody {
     // the range widget's term of one row: w = d, c, b, a, d_next (each term is D(w[k+1] - 4*w[k]))
     PG_HD static bool range_row_holds(const Fr* w, const QRegs& q, int mode) {
-        const Fr one = fr_one(), three = fr_add(fr_add(one, one), one);
+        // Montgomery forms of the small constants (literals: an fr_add chain here would be recomputed by every thread)
+        const Fr one = fr_one();
+        const Fr two = {{0xfffffffcu, 0x00000003u, 0x00069004u, 0xb1096ff4u, 0xd9789feau, 0x33189fdfu, 0x598a0adfu, 0x304962b3u}};
+        const Fr three = {{0xfffffffau, 0x00000005u, 0x0009d806u, 0x098e27eeu, 0xc634efe0u, 0xcca4efcfu, 0x064f104eu, 0x486e140du}};
+        const Fr minus_three = {{0x00000007u, 0xfffffff9u, 0xfff483f8u, 0x4a2f7c14u, 0x436ce825u, 0x6694e838u, 0x234e6cf9u, 0x2b7f9346u}};
+        const Fr minus_four = {{0x00000009u, 0xfffffff7u, 0xfff13bf6u, 0xf1aac41au, 0x56b0982fu, 0xcd089848u, 0x76896789u, 0x135ae1ecu}};
         Fr f[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {                                           // unrolled: everything stays in registers
@@ -723,18 +730,20 @@ struct GateRowsCheckBody {
             // structure-aware: D(f) = f(f-1)(f-2)(f-3) vanishes iff f is a base-4 digit (a field has no zero divisors), so a row whose
             // four differences all are digits holds and nothing is multiplied; any other row goes through the polynomial below -- the
             // verdict is the same for every witness.  Lanes of a warp share the row, so honest batches never leave the fast path.
-            const Fr two = fr_add(one, one);
             bool digits = true;
 #pragma unroll
             for (int k = 0; k < 4; k++) digits = digits && (fr_is_zero(f[k]) || fr_eq(f[k], one) || fr_eq(f[k], two) || fr_eq(f[k], three));
             if (digits) return true;
         }
+        // u = f(f-3) + 1.  Neither f - 3 nor u is reduced: the multiplier's SCANNED operand (the second) may be any 256-bit value when
+        // the first is below q (the running value stays below 2q; tests/emu), the dot product takes operands below 2q -- an addition
+        // without the conditional subtraction each.
         Fr u[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) u[k] = fr_add(fr_mul_eo(f[k], fr_sub(f[k], three), q), one);   // u = f(f-3) + 1
+        for (int k = 0; k < 4; k++) u[k] = fr_add_noreduce(fr_mul_eo(f[k], fr_add_noreduce(f[k], minus_three), q), one);
         uint32_t t[9];
         fr_dot_wide<4>(t, u, u, q);                                             // sum u_k^2 ...
-        add9_fr(t, fr_neg(fr_add(three, one)));                                 // ... - 4  =  sum D(f_k)
+        add9_fr(t, minus_four);                                                 // ... - 4  =  sum D(f_k)
         return limbs9_is_multiple_of_q(t);
     }
     template <class PoolT>

@@ -78,7 +78,10 @@ struct Comm {
         ncclResult_t r = api.CommInitRank(&comm, world_, uid, rank_);
         if (r != ncclSuccess) { comm = nullptr; return fail("ncclCommInitRank", r); }
         rank = rank_; world = world_;
-        if (cudaMalloc(&d_words, (size_t)(8 + 2 * world) * sizeof(unsigned long long)) != cudaSuccess) { snprintf(err, sizeof(err), "cudaMalloc(comm scratch)"); return false; }
+        if (cudaMalloc(&d_words, (size_t)(8 + 2 * world) * sizeof(unsigned long long)) != cudaSuccess) {
+            destroy();                                  // no half-initialised communicator: active() must stay false
+            snprintf(err, sizeof(err), "cudaMalloc(comm scratch)"); return false;
+        }
         return true;
     }
     void destroy() {

@@ -969,8 +969,17 @@ public:
             if (loc_kind(loc) != LOC_FR) return fail(PG_ERR_ARG, "poke_variable: packed bit variables cannot be overwritten");
             if (!be.h2d(s.fr + 2 * ((uint64_t)loc_payload(loc) * s.n_alloc + i), value, sizeof(pg_fr)) || !be.sync()) return fail(PG_ERR_CUDA, "poke copy");
             // the stored witness no longer is what generation verified: this segment and every segment that reads the Variable through an
-            // operand column (segments are appended in call order: all later ones may) go back to the ordinary check
-            for (size_t j = k; j < segs.size(); j++) segs[j].fused_ok = false;
+            // operand column (segments are appended in call order: all later ones may) go back to the ordinary check.  The verdict
+            // recorded at generation is ONE pair of sticky words for the whole composer, so the unsatisfied rows an invalidated segment
+            // had recorded (is_non_zero instances that errored or mismatched) cannot be taken out of it again: the whole composer goes
+            // back to the check kernels and the recorded verdict is dropped -- calls made after this start a fresh record.
+            bool had_fused = false;
+            for (Segment& t : segs) { had_fused = had_fused || t.fused_ok; t.fused_ok = false; }
+            if (had_fused) {
+                static const unsigned long long fresh[2] = {0, ~0ull};
+                static_assert(CNT_FUSED_FIRST == CNT_FUSED_UNSAT + 1, "the two words are reset with one copy");
+                if (!be.h2d(d_counters + CNT_FUSED_UNSAT, fresh, sizeof(fresh)) || !be.sync()) return fail(PG_ERR_CUDA, "poke: verdict record reset");
+            }
             return PG_OK;
         }
         return fail(PG_ERR_ARG, "poke_variable: Variable not found");

@@ -268,6 +268,7 @@ def fused_scalar_gadgets(make_composer, ob, n: int = 90):
         c.check_stats(reset=True)
         a = c.add_input(ob.from_ints(vals)); b = c.add_input(ob.from_ints(other)); s = c.add_input(ob.from_ints(sel))
         eq = pg.maybe_equal(c, a, b)
+        nz_first_var = c.num_variables()
         flags = pg.is_non_zero_flags(c, a, ob.from_ints(assigned), pg.NZ_UNIFORM)
         so = pg.conditionally_select_one(c, a, s)
         sz = pg.conditionally_select_zero(c, so, s)
@@ -291,6 +292,19 @@ def fused_scalar_gadgets(make_composer, ob, n: int = 90):
         exp2 = eval_rows(ob, c.rows(0, n_rows, want=("w_val", "sel", "pi")))
         assert len(exp2) > len(exp) and c.check_circuit_satisfied() == (len(exp2), exp2[0])
         c.poke_variable(var, old)
+        assert c.check_circuit_satisfied() == got
+        # a poke into the segment whose generation-time verdict held unsatisfied rows (the errored / mismatching is_non_zero instances)
+        # while an earlier segment (maybe_equal) had been verified at generation too: those rows must not be counted twice
+        var = nz_first_var + 3 * (n // 3) + 1                   # the inverse of instance n // 3 (VA, I, ONE per instance)
+        old = c.variables(var, 1)[0].copy()
+        c.poke_variable(var, ob.from_ints([(ob.to_ints(old[None])[0] + 9) % Q])[0])
+        exp3 = eval_rows(ob, c.rows(0, n_rows, want=("w_val", "sel", "pi")))
+        assert len(exp3) == len(exp) + 1 and c.check_circuit_satisfied() == (len(exp3), exp3[0])
+        c.poke_variable(var, old)
+        assert c.check_circuit_satisfied() == got
+        # gadgets called after a poke are recorded afresh
+        y2 = pg.maybe_equal(c, a, a)
+        c.constrain_to_constant(y2, ob.from_ints([1] * n))
         assert c.check_circuit_satisfied() == got
         c.close()
     assert verdicts[0] == verdicts[1]

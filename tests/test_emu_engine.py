@@ -108,6 +108,15 @@ def test_fr_even_odd_multiplier_host_emulation(fr_emu):
         getattr(fr_emu, fn)(C.c_uint64(len(pairs)), vp(A), vp(B), vp(out))
         assert unpack(out) == [a * b * rinv % Q for a, b in pairs], fn
     assert fr_emu.emu_violations() == 0
+    # the SCANNED (second) operand of the multiplier may be ANY 256-bit value when the first is below q (the running value stays below
+    # 2q): the range widget's rows pass f - 3 as the unreduced sum f + (q - 3) (bodies.cuh range_row_holds)
+    wide = [2 ** 256 - 1, 2 ** 256 - 2 ** 32, 2 * Q - 1, 2 * Q - 2, Q, Q + 1] + [rng.randrange(2 ** 256) for _ in range(2000)]
+    small = [Q - 1, Q - 2, 1, 0, R, Q >> 1] + [rng.randrange(Q) for _ in range(2000)]
+    W, S = pack(wide), pack(small)
+    out = np.zeros_like(S)
+    fr_emu.emu_mul_eo(C.c_uint64(len(small)), vp(S), vp(W), vp(out))
+    assert unpack(out) == [a * b * rinv % Q for a, b in zip(small, wide)]
+    assert fr_emu.emu_violations() == 0
     for fn, f in (("emu_add", lambda a, b: (a + b) % Q), ("emu_sub", lambda a, b: (a - b) % Q)):
         out = np.zeros_like(A)
         getattr(fr_emu, fn)(C.c_uint64(len(pairs)), vp(A), vp(B), vp(out))
