@@ -65,7 +65,8 @@ public:
         PG_CUDA(cudaEventCreateWithFlags(&copy_ready, cudaEventDisableTiming));
         timing_on = (cfg.flags & PG_F_TIMING) != 0;
         check_shape = cfg.check_shape < (uint32_t)CHECK_SHAPES ? (int)cfg.check_shape : 0;
-        PG_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_MAX_LOG_TILE));
+        PG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_MAX_LOG_TILE));
+        PG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_MAX_LOG_TILE));
         PG_CUDA(cudaFuncSetAttribute(k_check_rowpar<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PG_CUDA(cudaFuncSetAttribute(k_check_rowpar<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         if (!set_check_attrs<0>() || !set_check_attrs<1>() || !set_check_attrs<2>() || !set_check_attrs<3>() || !set_check_attrs<4>()) return false;
@@ -419,7 +420,8 @@ public:
     bool run_ntt_pass(const NttPassArgs& a, uint64_t n_blocks) {
         const size_t smem = (size_t)32 << (a.s + a.log_c);
         tic(CLS_OTHER, 0);
-        k_ntt_pass<<<(unsigned)n_blocks, NTT_THREADS, smem, stream>>>(a);
+        if (a.inverse) k_ntt_pass<true><<<(unsigned)n_blocks, NTT_THREADS, smem, stream>>>(a);
+        else k_ntt_pass<false><<<(unsigned)n_blocks, NTT_THREADS, smem, stream>>>(a);
         toc();
         return launched("k_ntt_pass");
     }

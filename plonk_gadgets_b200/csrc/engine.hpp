@@ -1098,12 +1098,12 @@ public:
     int ntt_twiddles(uint32_t log_n) {
         if (ntt_tw && ntt_tw_log_n == log_n) return PG_OK;
         if (ntt_tw) { be.sync(); dfree(ntt_tw); ntt_tw = nullptr; }
-        const uint64_t n_half = 1ull << (log_n - 1);
-        ntt_tw = (uint4*)dalloc(n_half * sizeof(pg_fr));
+        const uint64_t n_entries = (1ull << (log_n - 1)) + 1;             // w^0 .. w^(n/2) (= -1: the inverse transform's entry for i = 0)
+        ntt_tw = (uint4*)dalloc(n_entries * sizeof(pg_fr));
         if (!ntt_tw) return fail(PG_ERR_OOM, "twiddle table");
         ntt_tw_log_n = log_n;
         NttTwiddleBody::Args a;
-        a.tw = ntt_tw; a.n_half = n_half; a.n = (n_half + 15) / 16; a.log_n = log_n;
+        a.tw = ntt_tw; a.n_entries = n_entries; a.n = (n_entries + 15) / 16; a.log_n = log_n;
         Fr w = fr_root_of_unity();                                       // EvaluationDomain::new: group_gen
         for (uint32_t i = log_n; i < NTT_TWO_ADICITY; i++) w = fr_sqr(w);
         a.pw2[0] = w;

@@ -17,8 +17,10 @@
 //      registers and does the four decimation-in-time butterflies (1 Montgomery multiplication, 1 add, 1 sub each) of a
 //      stage pair between two barriers.  The vector crosses HBM once per pass (3 passes at 2^26) while the
 //      log_n/2 multiplications per element stay on the multiplier pipe: the transform is IMAD-bound like the gate check.
-//   Twiddles w^i (i < n/2) come from a table built once per domain size by k_simple<NttTwiddleBody> (inverse transform:
-//   w^-i = -w^(n/2 - i)); a pass touches about as many table bytes as data bytes, mostly out of L2.
+//   Twiddles w^i (i <= n/2) come from a table built once per domain size by k_simple<NttTwiddleBody>.  The inverse transform
+//   reads the same table backwards, w^-i = -w^(n/2 - i), and never negates: with t' = x1 * w^(n/2 - i) = -(x1 * w^-i) the
+//   butterfly's outputs are x0 - t' and x0 + t' -- the forward butterfly with its two results exchanged (entry n/2 = -1 serves
+//   i = 0).  A pass touches about as many table bytes as data bytes, mostly out of L2.
 #pragma once
 #include "layout.h"
 
@@ -41,15 +43,15 @@ PG_HD uint64_t bitrev64(uint64_t x, uint32_t bits) {
 #endif
 }
 
-// ---- twiddle table: tw[i] = w^i, i < n/2; 16 consecutive entries per call --------------------------------------------
+// ---- twiddle table: tw[i] = w^i, i <= n/2 (n_entries = n/2 + 1; the last one is -1); 16 consecutive entries per call -----
 struct NttTwiddleBody {
-    struct Args { uint4* tw; uint64_t n_half; uint64_t n; /* calls */ uint32_t log_n; Fr pw2[NTT_TWO_ADICITY]; /* w^(2^b) */ };
+    struct Args { uint4* tw; uint64_t n_entries; uint64_t n; /* calls */ uint32_t log_n; Fr pw2[NTT_TWO_ADICITY]; /* w^(2^b) */ };
     PG_HD static void run(const Args& a, uint64_t j) {
         const uint64_t i0 = j * 16;
         Fr x = fr_one();
-        for (uint32_t b = 4; b + 1 < a.log_n; b++)
+        for (uint32_t b = 4; b < a.log_n; b++)
             if ((i0 >> b) & 1) x = fr_mul(x, a.pw2[b]);
-        for (uint32_t r = 0; r < 16 && i0 + r < a.n_half; r++) { aos_store(a.tw, i0 + r, x); x = fr_mul(x, a.pw2[0]); }
+        for (uint32_t r = 0; r < 16 && i0 + r < a.n_entries; r++) { aos_store(a.tw, i0 + r, x); x = fr_mul(x, a.pw2[0]); }
     }
 };
 
@@ -86,10 +88,9 @@ PG_HD void ntt_butterfly(const NttPassArgs& a, uint64_t blk, uint32_t u, uint32_
     const uint64_t pos = ((uint64_t)low << a.t0) | (g & ((1ull << a.t0) - 1ull));     // index inside the half block of size m = 2^(t0+u)
     tw_index = pos << (a.log_n - 1u - (a.t0 + u));                                    // pos * n / (2m)  < n/2
 }
+// forward: w^i.  Inverse: w^(n/2 - i) = -w^-i -- the caller exchanges the butterfly's two results instead of negating
 PG_HD Fr ntt_twiddle(const NttPassArgs& a, uint64_t tw_index) {
-    if (!a.inverse) return aos_load(a.tw, tw_index);
-    if (tw_index == 0) return fr_one();
-    return fr_neg(aos_load(a.tw, (1ull << (a.log_n - 1u)) - tw_index));                // w^-i = -w^(n/2 - i)
+    return aos_load(a.tw, a.inverse ? (1ull << (a.log_n - 1u)) - tw_index : tw_index);
 }
 
 #if defined(__CUDACC__)
@@ -112,15 +113,56 @@ __device__ __forceinline__ uint32_t ntt_index32(const NttPassArgs& a, uint32_t b
     const uint32_t sh = a.t0 + a.s;
     return (sh < 32u ? g_hi << sh : 0u) | (v << a.t0) | g_lo;
 }
+template <bool INV>
 __device__ __forceinline__ Fr ntt_twiddle32(const NttPassArgs& a, uint32_t ti) {
-    if (!a.inverse) return aos_load(a.tw, ti);
-    if (ti == 0) return fr_one();
-    return fr_neg(aos_load(a.tw, (1u << (a.log_n - 1u)) - ti));
+    return aos_load(a.tw, INV ? (1u << (a.log_n - 1u)) - ti : ti);
+}
+// x0, x1 <- x0 + w x1, x0 - w x1 with t = x1 * (table entry): the inverse transform's entry is -w, so its results are exchanged
+template <bool INV>
+__device__ __forceinline__ void ntt_bfly(Fr& x0, Fr& x1, const Fr& t) {
+    const Fr s = fr_add(x0, t), d = fr_sub(x0, t);
+    x0 = INV ? d : s; x1 = INV ? s : d;
 }
 
 // Two butterfly stages per trip through shared memory: a thread takes the four elements that differ in bits u and u+1 of v,
 // runs stage t0+u on the pairs (0,1), (2,3) -- they share one twiddle -- and stage t0+u+1 on (0,2), (1,3), whose twiddle
 // exponents differ by n/4.  An odd stage count ends with one radix-2 step.
+// stages t0+u and t0+u+1 on the tile (FIRST: t0 = u = 0, see k_ntt_pass)
+template <bool INV, bool FIRST>
+__device__ __forceinline__ void ntt_stage_pair(const NttPassArgs& a, uint4* s_tile, uint32_t E, uint32_t blk, uint32_t u, const QRegs& q) {
+    const uint32_t c_mask = (1u << a.log_c) - 1u, lo_mask = a.t0 ? 0xffffffffu >> (32u - a.t0) : 0u;
+    const uint32_t sh = a.log_n - 1u - (a.t0 + u);                // stage t0+u: exponent = pos << sh
+#pragma unroll 1
+    for (uint32_t r = threadIdx.x; r < E / 4; r += NTT_THREADS) {
+        const uint32_t c = r & c_mask, bf = r >> a.log_c;
+        const uint32_t low = bf & ((1u << u) - 1u);
+        const uint32_t v0 = ((bf >> u) << (u + 2)) | low;
+        const uint32_t e0 = (v0 << a.log_c) | c, d = 1u << (u + a.log_c);
+        const uint32_t pos = (low << a.t0) | (((blk << a.log_c) | c) & lo_mask);
+        const uint32_t ti = pos << sh;
+        Fr x0 = tile_load(s_tile, E, e0), x1 = tile_load(s_tile, E, e0 + d);
+        Fr x2 = tile_load(s_tile, E, e0 + 2 * d), x3 = tile_load(s_tile, E, e0 + 3 * d);
+        if (FIRST) {                                              // ti == 0
+            ntt_bfly<false>(x0, x1, x1);
+            ntt_bfly<false>(x2, x3, x3);
+            ntt_bfly<false>(x0, x2, x2);
+        } else {
+            const Fr w = ntt_twiddle32<INV>(a, ti);
+            const Fr t1 = fr_mul_eo(x1, w, q), t3 = fr_mul_eo(x3, w, q);
+            ntt_bfly<INV>(x0, x1, t1);
+            ntt_bfly<INV>(x2, x3, t3);
+            const Fr wa = ntt_twiddle32<INV>(a, ti >> 1);
+            const Fr t2 = fr_mul_eo(x2, wa, q);
+            ntt_bfly<INV>(x0, x2, t2);
+        }
+        const Fr wb = ntt_twiddle32<INV>(a, (ti >> 1) + (1u << (a.log_n - 2u)));
+        const Fr t3 = fr_mul_eo(x3, wb, q);
+        ntt_bfly<INV>(x1, x3, t3);
+        tile_store(s_tile, E, e0, x0); tile_store(s_tile, E, e0 + d, x1);
+        tile_store(s_tile, E, e0 + 2 * d, x2); tile_store(s_tile, E, e0 + 3 * d, x3);
+    }
+}
+template <bool INV>
 __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const NttPassArgs a) {
     extern __shared__ __align__(16) uint4 s_tile[];               // [2 halves][E]
     __shared__ uint32_t s_q[8];
@@ -140,37 +182,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const NttPassArgs a
     for (int k = 0; k < 8; k++) q.v[k] = s_q[k];
     const uint32_t c_mask = (1u << a.log_c) - 1u, lo_mask = a.t0 ? 0xffffffffu >> (32u - a.t0) : 0u;
     uint32_t u = 0;
-    for (; u + 2 <= a.s; u += 2) {
-        const uint32_t sh = a.log_n - 1u - (a.t0 + u);            // stage t0+u: exponent = pos << sh
-#pragma unroll 1
-        for (uint32_t r = threadIdx.x; r < E / 4; r += NTT_THREADS) {
-            const uint32_t c = r & c_mask, bf = r >> a.log_c;
-            const uint32_t low = bf & ((1u << u) - 1u);
-            const uint32_t v0 = ((bf >> u) << (u + 2)) | low;
-            const uint32_t e0 = (v0 << a.log_c) | c, d = 1u << (u + a.log_c);
-            const uint32_t pos = (low << a.t0) | (((blk << a.log_c) | c) & lo_mask);
-            const uint32_t ti = pos << sh;
-            Fr x0 = tile_load(s_tile, E, e0), x1 = tile_load(s_tile, E, e0 + d);
-            Fr x2 = tile_load(s_tile, E, e0 + 2 * d), x3 = tile_load(s_tile, E, e0 + 3 * d);
-            {
-                const Fr w = ntt_twiddle32(a, ti);
-                const Fr t1 = fr_mul_eo(x1, w, q), t3 = fr_mul_eo(x3, w, q);
-                x1 = fr_sub(x0, t1); x0 = fr_add(x0, t1);
-                x3 = fr_sub(x2, t3); x2 = fr_add(x2, t3);
-            }
-            {
-                const Fr wa = ntt_twiddle32(a, ti >> 1);
-                const Fr t2 = fr_mul_eo(x2, wa, q);
-                x2 = fr_sub(x0, t2); x0 = fr_add(x0, t2);
-                const Fr wb = ntt_twiddle32(a, (ti >> 1) + (1u << (a.log_n - 2u)));
-                const Fr t3 = fr_mul_eo(x3, wb, q);
-                x3 = fr_sub(x1, t3); x1 = fr_add(x1, t3);
-            }
-            tile_store(s_tile, E, e0, x0); tile_store(s_tile, E, e0 + d, x1);
-            tile_store(s_tile, E, e0 + 2 * d, x2); tile_store(s_tile, E, e0 + 3 * d, x3);
-        }
-        __syncthreads();
-    }
+    // The first two stages of a transform (t0 = 0, u = 0) have the twiddles w^0 = 1 (stage 0, and the pairs (0,2) of stage 1) and
+    // w^(n/4) (the pairs (1,3)): one multiplication per group of four instead of four.
+    if (a.t0 == 0 && a.s >= 2) { ntt_stage_pair<INV, true>(a, s_tile, E, blk, 0, q); __syncthreads(); u = 2; }
+    for (; u + 2 <= a.s; u += 2) { ntt_stage_pair<INV, false>(a, s_tile, E, blk, u, q); __syncthreads(); }
     if (u < a.s) {                                                // last single stage
         const uint32_t sh = a.log_n - 1u - (a.t0 + u);
 #pragma unroll 1
@@ -180,10 +195,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const NttPassArgs a
             const uint32_t v0 = ((bf >> u) << (u + 1)) | low;
             const uint32_t e0 = (v0 << a.log_c) | c, e1 = e0 + (1u << (u + a.log_c));
             const uint32_t pos = (low << a.t0) | (((blk << a.log_c) | c) & lo_mask);
-            const Fr w = ntt_twiddle32(a, pos << sh);
-            const Fr x0 = tile_load(s_tile, E, e0);
-            const Fr t = fr_mul_eo(tile_load(s_tile, E, e1), w, q);
-            tile_store(s_tile, E, e0, fr_add(x0, t)); tile_store(s_tile, E, e1, fr_sub(x0, t));
+            const Fr w = ntt_twiddle32<INV>(a, pos << sh);
+            Fr x0 = tile_load(s_tile, E, e0), x1 = tile_load(s_tile, E, e1);
+            const Fr t = fr_mul_eo(x1, w, q);
+            ntt_bfly<INV>(x0, x1, t);
+            tile_store(s_tile, E, e0, x0); tile_store(s_tile, E, e1, x1);
         }
         __syncthreads();
     }
@@ -208,7 +224,8 @@ inline void ntt_pass_host(const NttPassArgs& a, uint64_t n_blocks) {
                 ntt_butterfly(a, blk, u, b, e0, e1, ti);
                 const Fr t = fr_mul(tile[e1], ntt_twiddle(a, ti));
                 const Fr x0 = tile[e0];
-                tile[e0] = fr_add(x0, t); tile[e1] = fr_sub(x0, t);
+                if (a.inverse) { tile[e0] = fr_sub(x0, t); tile[e1] = fr_add(x0, t); }
+                else { tile[e0] = fr_add(x0, t); tile[e1] = fr_sub(x0, t); }
             }
         for (uint32_t e = 0; e < E; e++) aos_store(a.dst, ntt_index(a, blk, e), tile[e]);
     }
