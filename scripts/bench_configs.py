@@ -79,6 +79,18 @@ def main():
     ms, tim, _ = timed(c, c2)
     emit("C2: 2^20 range_check, 64-bit bound (k=65)", 271 * n, ms, tim)
 
+    # ---- C2 with per-instance random bounds of one width: max_i - 1 in [2^63, 2^64) (k = 65 for every instance),
+    #      min_i uniform below 2^63 <= max_i; the two V rows' q_c are per-instance parameters
+    mx2 = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 21, 3, 64, mx2)
+    mn2 = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 22, 1, 63, mn2)
+
+    def c2b():
+        c.reset(); w = c.add_input(wit); pg.range_check(c, mn2, mx2, w)
+        bad, _ = c.check_circuit_satisfied(); assert bad == 0
+    ms, tim, _ = timed(c, c2b)
+    emit("C2b: 2^20 range_check, per-instance random 64-bit bounds (k=65; max_i - 1 in [2^63, 2^64), min_i < 2^63)", 271 * n, ms, tim)
+    del mx2, mn2
+
     # ---- C3: 2^22 max_bound with 252-bit per-instance bounds (k=253)
     n = 1 << 22
     mx3 = torch.empty((n, 4), dtype=torch.int64, device=dev); c.synth(SEED, 31, 3, 252, mx3)
