@@ -33,8 +33,9 @@ UNIT = "gate-evals/s"
 ROWS_PER_INSTANCE = 271          # 4k+11, k = 65
 VARS_PER_INSTANCE = 653
 IMAD_PER_ROW_DEFINITION = 816    # 6 Fr mul x 136 32x32->64 multiply-accumulates: the DEFINITIONAL cost of a generic gate evaluation
-EXECUTED_WIDE_PER_ROW = 428      # wide-class IMADs in the row loop of k_check<GENERIC> (SASS): one Montgomery multiplication (64 + 48), a 4-term dot product with one
-                                 # shared reduction (256 + 48), the "0 mod q" test (8) and 4 of address arithmetic; profiles/r04_sass_mix.txt
+EXECUTED_WIDE_PER_ROW = 420      # wide-class IMADs a row of k_check<GENERIC> executes (SASS): one Montgomery multiplication (64 + 48), a 4-term dot product with one
+                                 # shared reduction (256 + 48) and 4 of address arithmetic; the "0 mod q" test compares with a shared-memory table of k*q since
+                                 # run r05e (8 more products before); profiles/r05_sass_mix.txt
 PACKED_BYTES_PER_INSTANCE = 141 * 32 + 2 * 32   # variable table written by witness generation (141 Fr slots + 2 bit planes)
 
 

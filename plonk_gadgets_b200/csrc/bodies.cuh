@@ -461,6 +461,22 @@ struct CheckBody {
         add9_fr(t, row.qc_param >= 0 ? tab_load_fr(a.param, a.param_stride, (uint32_t)row.qc_param, i) : pool(row.sel[5]));
         if (row.pi_param >= 0) add9_fr(t, tab_load_fr(a.param, a.param_stride, (uint32_t)row.pi_param, i));
         else if (row.pi_sel != POOL_ZERO) add9_fr(t, pool(row.pi_sel));
+        return pool_is_multiple_of_q(pool, t);
+    }
+    // t == k*q for k = t[0] <= 15: through the pool's table of multiples when it has one (three 128-bit shared-memory loads instead of
+    // eight products), else by multiplying
+    template <class PoolT>
+    PG_HD static bool pool_is_multiple_of_q(const PoolT& pool, const uint32_t* t) {
+#if defined(__CUDA_ARCH__)
+        if (pool.kq) {
+            const uint32_t k = t[0] < 15u ? t[0] : 15u;
+            const uint4* e = reinterpret_cast<const uint4*>(pool.kq + 12 * k);
+            const uint4 a0 = e[0], a1 = e[1], a2 = e[2];
+            uint32_t diff = (a0.x ^ t[0]) | (a0.y ^ t[1]) | (a0.z ^ t[2]) | (a0.w ^ t[3]) | (a1.x ^ t[4]) | (a1.y ^ t[5]) | (a1.z ^ t[6]) | (a1.w ^ t[7]) | (a2.x ^ t[8]);
+            return diff == 0;                  // (t[0] > 15 differs from 15*q's low limb 15)
+        }
+#endif
+        (void)pool;
         return limbs9_is_multiple_of_q(t);
     }
     // the same row through the structure-aware term evaluation (small segments; large ones run the compiled program)

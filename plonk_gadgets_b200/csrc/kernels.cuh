@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_batch_inv(const BatchInvArgs a, co
 // ---------------------------------------------------------------------------------------------------- gate check
 struct SmemPool {
     const uint32_t* p;
+    const uint32_t* kq = nullptr;              // k*q for k = 0..15, 12 words apart (k_check: the row-end test compares instead of multiplying)
     __device__ __forceinline__ Fr operator()(uint32_t idx) const {
         const uint4 lo = *reinterpret_cast<const uint4*>(p + 8 * idx), hi = *reinterpret_cast<const uint4*>(p + 8 * idx + 4);
         Fr r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
@@ -162,6 +163,13 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
     __shared__ uint32_t s_q[8];
     for (uint32_t t = threadIdx.x; t < a.n_pool * 8; t += CHECK_BLOCK) s_pool[t] = a.pool[t];
     if (threadIdx.x < 8) s_q[threadIdx.x] = c_q[threadIdx.x];
+    __shared__ __align__(16) uint32_t s_kq[16 * 12];
+    if (threadIdx.x < 16) {
+        unsigned long long c = 0;
+        for (int j = 0; j < 8; j++) { c += (unsigned long long)c_q[j] * threadIdx.x; s_kq[12 * threadIdx.x + j] = (uint32_t)c; c >>= 32; }
+        s_kq[12 * threadIdx.x + 8] = (uint32_t)c;
+        s_kq[12 * threadIdx.x + 9] = s_kq[12 * threadIdx.x + 10] = s_kq[12 * threadIdx.x + 11] = 0;
+    }
     __syncthreads();
     QRegs q;                                   // modulus limbs in vector registers (see QRegs in fr.cuh)
 #pragma unroll
@@ -169,7 +177,10 @@ __global__ void __launch_bounds__(CheckShape<SHAPE>::BLOCK_T, CheckShape<SHAPE>:
     const uint64_t i = (uint64_t)blockIdx.x * CHECK_BLOCK + threadIdx.x;
     unsigned long long first_bad = ~0ull;
     uint32_t bad = 0;
-    if (i < a.n_inst) { SmemPool pool = {s_pool}; bad = CheckBody::run<MODE>(a, pool, q, i, first_bad); }
+    if (i < a.n_inst) {
+        SmemPool pool = {s_pool, s_kq};
+        bad = CheckBody::run<MODE>(a, pool, q, i, first_bad);
+    }
     // warp-level reduction, then one atomic per warp that saw a violation
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

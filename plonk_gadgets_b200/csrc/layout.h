@@ -130,9 +130,17 @@ PG_HD Fr loc_load(const DevTab* tabs, uint32_t loc, uint64_t i) {
     for (int k = 0; k < 8; k++) r.v[k] = b ? one.v[k] : 0u;
     return r;
 }
+#if defined(__CUDACC__)
+__device__ __align__(32) const uint4 g_zero_fr[2] = {};      // the zero variable's value as a loadable scalar (row_load)
+#endif
 // the same through the pre-resolved addresses of a DevRow
 PG_HD Fr row_load(const DevRow& row, int w, uint64_t i) {
     const uint32_t kind = loc_kind(row.loc[w]);
+#if defined(__CUDA_ARCH__)
+    // the zero variable's wire is a load too (one 32-byte broadcast out of L1): eight register initialisations per zero wire, half of
+    // which ptxas puts on the multiplier pipe, cost the generic check 1.7 ms of 261 (run r05e)
+    if (kind != LOC_BIT) return ld256(kind == LOC_FR ? reinterpret_cast<const uint4*>(row.addr[w]) + 2 * i : g_zero_fr);
+#endif
     if (kind == LOC_ZERO) return fr_zero();
     if (kind == LOC_FR) return ld256(reinterpret_cast<const uint4*>(row.addr[w]) + 2 * i);
     const uint32_t word = reinterpret_cast<const uint32_t*>(row.addr[w])[i];
