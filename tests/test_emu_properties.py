@@ -9,6 +9,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 
 import plonk_gadgets_b200 as pg
 from plonk_gadgets_b200 import _lib
+from tests import property_cases as pc
 from tests.engine_runner import run_engine
 from tests.programs import Q, hx, run_oracle
 from tests.test_emu_engine import _build
@@ -40,28 +41,14 @@ def test_range_gadgets_random_bounds(emu, oracle, bits, seed, extra):
     assert r[0] == 1 and r[1] == 1 and r[2] == 0
 
 
-ops = st.sampled_from(["maybe_equal", "select_zero", "select_one", "is_non_zero", "max_bound", "constrain"])
+ops = st.sampled_from(pc.OPS)
 
 
 @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(n=st.integers(1, 5), vals=st.lists(scalars, min_size=10, max_size=10), seq=st.lists(ops, min_size=1, max_size=6), seed=st.integers(0, 1000))
 def test_random_gadget_compositions(emu, oracle, n, vals, seq, seed):
     """Later calls consume the columns earlier calls produced; the whole composer must equal the oracle's."""
-    rng = np.random.default_rng(seed)
-    prog = [dict(op="add_input", values=[hx(v) for v in vals[:n]]), dict(op="add_input", values=[hx(v) for v in vals[5:5 + n]])]
-    cols = [0, 1]                                  # program indices that returned a column
-    for op in seq:
-        a, b = int(rng.choice(cols)), int(rng.choice(cols))
-        if op == "maybe_equal":
-            prog.append(dict(op=op, a=a, b=b)); cols.append(len(prog) - 1)
-        elif op in ("select_zero", "select_one"):
-            prog.append(dict(op=op, **({"x": a} if op == "select_zero" else {"y": a}), select=b)); cols.append(len(prog) - 1)
-        elif op == "is_non_zero":
-            prog.append(dict(op=op, var=a, assigned=[hx(v) for v in vals[:n]]))
-        elif op == "max_bound":
-            prog.append(dict(op=op, max=hx(2 ** int(rng.integers(1, 250))), witness=a)); cols.append(len(prog) - 1)
-        else:
-            prog.append(dict(op="constrain_to_constant", a=a, constant=hx(int(rng.integers(0, 3))), pi=[hx(v) for v in vals[:n]] if seed % 2 else None))
+    prog = pc.small_composition(n, vals, seq, seed)
     from tests.programs import expected_sigma
     so, oc = run_oracle(prog, return_composer=True)
     se, c = run_engine(prog, lambda: pg.StandardComposer(_cdll=emu), oracle, return_composer=True)
@@ -99,26 +86,7 @@ def test_fault_injection_flips_exactly_its_row(emu, oracle, row, col, delta):
 def test_sparse_program_random_compositions(emu, oracle, vals, seq, seed):
     """Batches of 48 instances go through the compiled structure-aware row program (SparseProgBody): for random gadget
     sequences -- satisfied or not -- its list of violated rows must be the oracle's, like the generic evaluation's."""
-    rng = np.random.default_rng(seed)
-    n = 48
-    col_a = [vals[i % 8] if i % 3 else (vals[i % 8] + i) % Q for i in range(n)]
-    col_b = [vals[(i + 3) % 8] if i % 2 else col_a[i] for i in range(n)]
-    prog = [dict(op="add_input", values=[hx(v) for v in col_a]), dict(op="add_input", values=[hx(v) for v in col_b])]
-    cols = [0, 1]
-    for op in seq:
-        a, b = int(rng.choice(cols)), int(rng.choice(cols))
-        if op == "maybe_equal":
-            prog.append(dict(op=op, a=a, b=b)); cols.append(len(prog) - 1)
-        elif op in ("select_zero", "select_one"):
-            prog.append(dict(op=op, **({"x": a} if op == "select_zero" else {"y": a}), select=b)); cols.append(len(prog) - 1)
-        elif op == "is_non_zero":
-            prog.append(dict(op=op, var=a, assigned=[hx(v if v else 1) for v in col_a]))
-        elif op == "max_bound":
-            bits = int(rng.integers(1, 250))      # per-instance bounds: max - 1 in [2^bits, 2^(bits+1)) for every instance (same num_bits)
-            prog.append(dict(op=op, max=[hx(2 ** bits + 1 + int(rng.integers(0, 2 ** min(bits, 60)))) for _ in range(n)] if seed % 3 == 0 else hx(2 ** bits), witness=a))
-            cols.append(len(prog) - 1)
-        else:
-            prog.append(dict(op="constrain_to_constant", a=a, constant=hx(int(rng.integers(0, 3))), pi=[hx(v) for v in col_b] if seed % 2 else None))
+    prog = pc.batch_composition(vals, seq, seed)
     so = run_oracle(prog)
     for mode in (pg.CHECK_SPARSE, pg.CHECK_GENERIC):
         se = run_engine(prog, lambda: pg.StandardComposer(check_mode=mode, _cdll=emu), oracle)
