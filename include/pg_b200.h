@@ -91,9 +91,10 @@ enum {
                                in registers, structure-aware arithmetic) -- range_check, max_bound, maybe_equal, is_non_zero (the _flags call in
                                the uniform layout), conditionally_select_* -- so the variable table is written once and never read again for
                                the verdict; pg_check / pg_check_sharded then only launch for what was not verified that way (the fresh rows,
-                               constrain_to_constant and range_gate rows, is_non_zero with `?` semantics) or whose Variables were overwritten
-                               since (pg_poke_variable), and add the recorded verdict.  Same verdict as without the flag on every composer
-                               state this API can produce. */
+                               constrain_to_constant and range_gate rows, is_non_zero with `?` semantics) and add the recorded verdict.
+                               pg_poke_variable drops the record: every segment present at that moment goes back to the check kernels (calls
+                               made afterwards are recorded afresh).  Same verdict as without the flag on every composer state this API can
+                               produce. */
 };
 
 typedef struct pg_cfg {
