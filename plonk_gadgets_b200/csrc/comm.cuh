@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace pg {
@@ -119,6 +120,16 @@ struct Comm {
     // broadcast per rank inside a group (NCCL fuses them: every GPU reads the G - 1 other shards over NVLink concurrently)
     bool allgather_ragged(const void* send, void* recv, const unsigned long long* counts, cudaStream_t stream) {
         NcclApi& api = nccl_api();
+        // shards of equal length (the even cut of a uniform batch): one ncclAllGather -- NCCL's own all-gather algorithms instead of
+        // `world` concurrent broadcasts (PG_GATHER_BCAST=1 forces the general path; tuning runs)
+        bool equal = counts[0] != 0;
+        for (int g = 1; g < world; g++) equal = equal && counts[g] == counts[0];
+        static const bool force_bcast = [] { const char* e = getenv("PG_GATHER_BCAST"); return e && e[0] == '1'; }();
+        if (equal && !force_bcast) {
+            ncclResult_t ra = api.AllGather(send, recv, (size_t)counts[0] * 4, ncclUint64, comm, stream);
+            if (ra != ncclSuccess) return fail("ncclAllGather", ra);
+            return true;
+        }
         ncclResult_t r = api.GroupStart(); if (r != ncclSuccess) return fail("ncclGroupStart", r);
         unsigned long long off = 0;
         for (int g = 0; g < world; g++) {
