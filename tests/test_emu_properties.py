@@ -91,3 +91,38 @@ def test_sparse_program_random_compositions(emu, oracle, vals, seq, seed):
     for mode in (pg.CHECK_SPARSE, pg.CHECK_GENERIC):
         se = run_engine(prog, lambda: pg.StandardComposer(check_mode=mode, _cdll=emu), oracle)
         assert se.error == so.error and se.digest() == so.digest() and se.unsat == so.unsat, mode
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(vals=st.lists(scalars, min_size=8, max_size=8), seq=st.lists(ops, min_size=1, max_size=5), seed=st.integers(0, 1000),
+       n=st.sampled_from([5, 33, 48]), pokes=st.lists(st.tuples(st.integers(0, 2 ** 30), scalars), min_size=1, max_size=4))
+def test_fused_verdict_record_survives_pokes(emu, oracle, vals, seq, seed, n, pokes):
+    """PG_F_FUSED_CHECK: whatever is overwritten after generation (any Variable of any segment, also one whose segment had recorded
+    unsatisfied rows) and whatever is called afterwards, pg_check returns the big-int verdict of the composer's own row dump."""
+    from tests.fault_cases import eval_rows
+
+    def bigint_verdict(c):
+        bad = eval_rows(oracle, c.rows(0, c.circuit_size(), want=("w_val", "sel", "pi")))
+        return (len(bad), bad[0] if bad else None)
+
+    prog = pc.batch_composition(vals, seq, seed, n=n)
+    se, c = run_engine(prog, lambda: pg.StandardComposer(check_mode=pg.CHECK_SPARSE, fused_check=True, _cdll=emu), oracle, return_composer=True)
+    assert c.check_circuit_satisfied() == bigint_verdict(c)
+    nv = c.num_variables()
+    for where, value in pokes:
+        try:
+            c.poke_variable(5 + where % (nv - 5), oracle.from_ints([value])[0])
+        except pg.EngineError:
+            continue                                   # a packed bit variable: cannot be overwritten
+        assert c.check_circuit_satisfied() == bigint_verdict(c)
+    if se.error is None:                               # calls made after a poke are recorded afresh
+        a = c.add_input(oracle.from_ints(vals[:4] + [0] * (n - 4)))
+        pg.maybe_equal(c, a, a)
+        pg.is_non_zero_flags(c, a, oracle.from_ints([v if i % 2 else 0 for i, v in enumerate(vals[:4] + [1] * (n - 4))]), pg.NZ_UNIFORM)
+        assert c.check_circuit_satisfied() == bigint_verdict(c)
+        try:
+            c.poke_variable(nv + 1, oracle.from_ints([pokes[0][1]])[0])
+            assert c.check_circuit_satisfied() == bigint_verdict(c)
+        except pg.EngineError:
+            pass
+    c.close()
