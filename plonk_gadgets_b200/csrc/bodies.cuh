@@ -493,13 +493,11 @@ struct CheckBody {
     template <int MODE, class PoolT>
     PG_HD static uint32_t run(const Args& a, const PoolT& pool, const QRegs& q, uint64_t i, unsigned long long& first_bad) {
         uint32_t bad = 0;
+        // (No prefetch of the next row's wires: requesting them into L1 one row ahead -- eight more warp-uniform loads of the next
+        // template row, four kind tests and four cache-control instructions per row -- was worth 5 % when it came in with run r01g and
+        // costs 2.7 % on the leaner row loop of run r05e: 256.2 -> 249.3 ms, run r05n.  Twenty resident warps per SM hide the loads.)
         for (uint32_t r = 0; r < a.n_rows; r++) {
             const DevRow row = a.rows[r];
-            if (r + 1 < a.n_rows) {            // request the next row's wire values now: ~2000 multiplier cycles cover the latency
-                const DevRow& nr = a.rows[r + 1];
-#pragma unroll
-                for (int k = 0; k < 4; k++) row_prefetch(nr.loc[k], nr.addr[k], i);
-            }
             if (!row_holds<MODE>(a, row, pool, q, i)) {
                 bad++;
                 const unsigned long long g = a.base_row + i * (uint64_t)a.n_rows + r;
@@ -797,7 +795,7 @@ struct GateRowsCheckBody {
                 const DevRow& nr = a.rows[r + 1];
                 d_next = row_load(nr, 3, i);
 #pragma unroll
-                for (int k = 0; k < 3; k++) row_prefetch(nr.loc[k], nr.addr[k], i);
+                for (int k = 0; k < 3; k++) row_prefetch(nr.loc[k], nr.addr[k], i);   // (no effect either way here: run r05o)
             }
             bool ok = true;
             if (row.gate == GATE_ARITH) ok = arith_row_holds(a, row, pool, q, i);
